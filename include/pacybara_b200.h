@@ -1,0 +1,170 @@
+/*
+ * pacybara_b200.h -- C ABI of the B200-native barcode-clustering hot path.
+ *
+ * The reference (rothlab/pacybara) has no FFI: its boundary for this path is three
+ * processes connected by files.  Each entry point below replaces the
+ * compute of one of those processes; the file parsing/writing stays in the host layer
+ * (pacybara_b200/*.py), which binds this header with ctypes.
+ *
+ *   pcb_bucket        <- src/pacybara_precluster.py:28-39,68-76   (addRecord + output order)
+ *   pcb_edit_pairs    <- src/pacybara.sh:448-468                  (seqret + bowtie2-build +
+ *                        bowtie2 --all + awk + src/pacybara_calcEdits.R:128-172)
+ *   pcb_merge         <- src/pacybara_cluster.py:385-477,515-537  (seed + main clustering,
+ *                        consensus genotype / barcode)
+ *   pcb_cluster_reads <- the three of them back to back, nothing leaving the device
+ *
+ * Conventions
+ *   - every function returns 0 on success or a PCB_E_* code; pcb_last_error() gives the text;
+ *   - `mem` says where ALL array arguments of that call live: PCB_MEM_HOST (the library
+ *     copies in and out on its own stream) or PCB_MEM_DEVICE (pointers into the memory of the
+ *     context's device; nothing is copied, results stay there);
+ *   - the caller owns every array and sizes it as documented; scalars returned through
+ *     pointers are always host memory;
+ *   - barcodes are ASCII over {A,C,G,T}, 1..64 nt, one per row of a [n, stride] uint8 matrix;
+ *     anything else is refused with PCB_E_INPUT (no fallback path exists);
+ *   - one context per GPU and per host thread; calls on one context are serialised.
+ *
+ * There is no CPU implementation behind this ABI: without a CUDA device every entry point
+ * that computes fails with PCB_E_CUDA.
+ */
+#ifndef PACYBARA_B200_H
+#define PACYBARA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCB_ABI_VERSION 1
+
+enum {
+  PCB_OK = 0,
+  PCB_E_CUDA = 1,      /* CUDA runtime / no device */
+  PCB_E_INPUT = 2,     /* malformed input (non-ACGT base, length 0 or > 64, bad ids, ...) */
+  PCB_E_CAPACITY = 3,  /* caller buffer too small; the needed size is reported */
+  PCB_E_STATE = 4,     /* call order (e.g. fetch before compute) */
+  PCB_E_UPTAG = 5      /* a clustered read has no uptag (the reference's KeyError, :519) */
+};
+
+enum { PCB_MEM_HOST = 0, PCB_MEM_DEVICE = 1 };
+
+#define PCB_FILL INT32_MIN          /* per-read outputs of components another shard owns */
+#define PCB_NEEDS_ALIGNMENT (-2)    /* consensus the reference hands to muscle (:523-530) */
+
+/* counters readable after a call (pcb_stat) */
+enum {
+  PCB_STAT_PAIRS_SCORED = 0,   /* candidate pairs that went through the Myers kernel */
+  PCB_STAT_CELLS = 1,          /* sum over those pairs of len_i * len_j (GCUPS numerator) */
+  PCB_STAT_EDGES = 2,          /* unique pairs with dist <= k */
+  PCB_STAT_SEED_LEN = 3,       /* q of the pigeonhole seeds used */
+  PCB_STAT_KERNEL_LAUNCHES = 4,/* kernels launched by this context so far */
+  PCB_STAT_COMPONENTS = 5,
+  PCB_STAT_LINKS = 6,          /* accepted merges in the main clustering */
+  PCB_STAT_TESTS = 7,          /* cluster-pair tests evaluated in the main clustering */
+  PCB_STAT_BUCKETS = 8,
+  PCB_STAT_PROBE_NS = 9,       /* device time of the last distance kernel, ns (CUDA events) */
+  PCB_STAT_COUNT = 16
+};
+
+typedef struct pcb_ctx pcb_ctx;
+
+int pcb_abi_version(void);
+/* Text of the last error on this context (or of the last failed pcb_ctx_create when ctx is NULL). */
+const char *pcb_last_error(const pcb_ctx *ctx);
+int pcb_ctx_create(int device, pcb_ctx **out);
+void pcb_ctx_destroy(pcb_ctx *ctx);
+int64_t pcb_stat(const pcb_ctx *ctx, int which);
+/* Block until everything queued on the context's stream has finished. */
+int pcb_sync(pcb_ctx *ctx);
+/* The context's cudaStream_t, for callers that time with their own CUDA events. */
+void *pcb_stream(pcb_ctx *ctx);
+
+/*
+ * a1 -- exact-barcode bucketing (src/pacybara_precluster.py:28-39, 68-76).
+ *   seq, qual      [R, stride] ASCII (qual = Phred+33), len [R]
+ * outputs (caller-sized for the worst case U = R):
+ *   bucket_of_read [R]        bucket index of each read; buckets are numbered in first-seen order
+ *   n_buckets      host int   U
+ *   bucket_ptr     [R+1]      CSR over buckets (first U+1 entries valid)
+ *   bucket_reads   [R]        reads of each bucket in arrival order
+ *   bucket_qsum    [R, stride] per-position min(93, sum of Phred) of each bucket (first U rows)
+ * The barcode of bucket b is the row seq[bucket_reads[bucket_ptr[b]]].
+ */
+int pcb_bucket(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *qual, const int32_t *len,
+               int32_t R, int32_t stride, int32_t *bucket_of_read, int32_t *n_buckets,
+               int32_t *bucket_ptr, int32_t *bucket_reads, uint8_t *bucket_qsum);
+
+/*
+ * a2+a3 -- every unordered pair of distinct barcodes with Levenshtein distance <= k
+ * (replaces bowtie2 all-vs-all + pacybara_calcEdits.R; dist := unit-cost Levenshtein).
+ *   seq [U, stride], len [U]: the unique barcodes;  0 <= k <= 8
+ *   q_begin, q_end: this call scores the pairs whose "query" barcode lies in [q_begin, q_end);
+ *     every unordered pair has exactly one query side, so disjoint ranges that cover [0, U)
+ *     produce disjoint edge sets whose union is the full result (multi-GPU sharding).
+ *   n_edges: host int64, number of pairs found.  The pairs stay in the context until
+ *   pcb_edit_pairs_fetch copies them out: ei < ej, sorted by (ei, ej), ed = distance.
+ */
+int pcb_edit_pairs(pcb_ctx *ctx, int mem, const uint8_t *seq, const int32_t *len, int32_t U, int32_t stride,
+                   int32_t k, int32_t q_begin, int32_t q_end, int64_t *n_edges);
+int pcb_edit_pairs_fetch(pcb_ctx *ctx, int mem, int32_t *ei, int32_t *ej, int32_t *ed, int64_t cap);
+
+/*
+ * a4..a13 -- seed clustering, greedy genotype-aware merge and consensus
+ * (src/pacybara_cluster.py:385-455, 464-477, 515-537).
+ *
+ * inputs
+ *   bucket_ptr [U+1], bucket_reads [R]   buckets and their reads in arrival order
+ *   lexrank [R]     rank of the read id in string order (makePID, :152-157)
+ *   bc_id [R]       id of the read's barcode string;  up_id [R] id of its uptag string, -1 if the
+ *                   read has none, or NULL when no uptag file is given (:537)
+ *   geno_ptr [R+1], geno_mut, geno_q [nnz]  genotype calls per read, distinct mutation ids within
+ *                   a read, input order;  mut_rank [n_mut] rank in (digit key, string) order (:475)
+ *   pair_q, pair_r, pair_d, pair_ed [n_pairs]  unique unordered bucket pairs in visiting order:
+ *                   (q, r) direction of the row that introduced the pair in the pass that visits it,
+ *                   d = distance the lookup table ends with (:266), ed = visiting pass 1..maxDiff or 0
+ *                   for lookup-only pairs (host helper: hostdata.dedupe_ed_rows / pairs_from_edges)
+ *   shard_rank / shard_count  components are dealt round-robin; entries of components owned by
+ *                   other shards are left at PCB_FILL (combine shards with an element-wise max)
+ * outputs (all [R] unless noted; a "row" is a cluster or an unclustered read and is named by
+ * its representative read = first member)
+ *   read_root       representative read of the row the read belongs to
+ *   read_pos        position of the read in the row's member list (reference list order)
+ *   row_size        members (valid at representative reads, 0 at other reads)
+ *   row_key         int64: creation order of the surviving cluster id, -1 for singletons
+ *   row_bc, row_up  consensus barcode / uptag id, or PCB_NEEDS_ALIGNMENT
+ *   row_call_off (int64), row_call_n, call_mut [nnz]  consensus / singleton genotype
+ */
+int pcb_merge(pcb_ctx *ctx, int mem, int32_t R, int32_t U,
+              const int32_t *bucket_ptr, const int32_t *bucket_reads, const int32_t *lexrank,
+              const int32_t *bc_id, const int32_t *up_id,
+              const int32_t *geno_ptr, const int32_t *geno_mut, const int32_t *geno_q,
+              const int32_t *mut_rank, int32_t n_mut,
+              int64_t n_pairs, const int32_t *pair_q, const int32_t *pair_r, const int32_t *pair_d,
+              const int32_t *pair_ed,
+              int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches,
+              int32_t shard_rank, int32_t shard_count,
+              int32_t *read_root, int32_t *read_pos, int32_t *row_size, int64_t *row_key,
+              int32_t *row_bc, int32_t *row_up, int64_t *row_call_off, int32_t *row_call_n,
+              int32_t *call_mut);
+
+/*
+ * The whole hot path on one device: bucketing -> distances (k = 2*max_diff) -> merge, with
+ * nothing returning to the host in between.  bc_id is the bucket index.  Inputs as pcb_bucket
+ * plus the read-level arrays of pcb_merge; outputs as pcb_bucket (bucket_of_read, n_buckets)
+ * and pcb_merge.  n_edges (host int64, may be NULL) receives the number of distance pairs.
+ */
+int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *qual, const int32_t *len,
+                      int32_t R, int32_t stride, const int32_t *lexrank, const int32_t *up_id,
+                      const int32_t *geno_ptr, const int32_t *geno_mut, const int32_t *geno_q,
+                      const int32_t *mut_rank, int32_t n_mut,
+                      int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches,
+                      int32_t *bucket_of_read, int32_t *n_buckets, int64_t *n_edges,
+                      int32_t *read_root, int32_t *read_pos, int32_t *row_size, int64_t *row_key,
+                      int32_t *row_bc, int32_t *row_up, int64_t *row_call_off, int32_t *row_call_n,
+                      int32_t *call_mut);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PACYBARA_B200_H */

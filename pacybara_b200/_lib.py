@@ -1,0 +1,60 @@
+"""ctypes binding of include/pacybara_b200.h.  There is no fallback: if the CUDA library is
+missing or no device is present, importing works but every use raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_pcb.so")
+
+PCB_OK, PCB_E_CUDA, PCB_E_INPUT, PCB_E_CAPACITY, PCB_E_STATE, PCB_E_UPTAG = range(6)
+MEM_HOST, MEM_DEVICE = 0, 1
+FILL = -(1 << 31)
+NEEDS_ALIGNMENT = -2
+STAT = dict(pairs_scored=0, cells=1, edges=2, seed_len=3, kernel_launches=4, components=5, links=6, tests=7,
+            buckets=8, probe_ns=9)
+
+# every symbol include/pacybara_b200.h declares
+SYMBOLS = ["pcb_abi_version", "pcb_last_error", "pcb_ctx_create", "pcb_ctx_destroy", "pcb_stat", "pcb_sync",
+           "pcb_stream", "pcb_bucket", "pcb_edit_pairs", "pcb_edit_pairs_fetch", "pcb_merge", "pcb_cluster_reads"]
+
+
+class PcbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"pacybara_b200 error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """The CDLL, loaded once.  Raises if the library has not been built (python -m pacybara_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO):
+            raise PcbError(PCB_E_CUDA, f"{SO} is missing: build it with `python -m pacybara_b200.build` "
+                                       "(there is no CPU implementation to fall back to)")
+        lib = C.CDLL(SO)
+        vp, i32, i64, dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double
+        lib.pcb_abi_version.restype = C.c_int
+        lib.pcb_last_error.restype = C.c_char_p
+        lib.pcb_last_error.argtypes = [vp]
+        lib.pcb_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+        lib.pcb_ctx_destroy.argtypes = [vp]
+        lib.pcb_ctx_destroy.restype = None
+        lib.pcb_stat.restype = i64
+        lib.pcb_stat.argtypes = [vp, C.c_int]
+        lib.pcb_sync.argtypes = [vp]
+        lib.pcb_stream.restype = vp
+        lib.pcb_stream.argtypes = [vp]
+        lib.pcb_bucket.argtypes = [vp, C.c_int, vp, vp, vp, i32, i32, vp, C.POINTER(i32), vp, vp, vp]
+        lib.pcb_edit_pairs.argtypes = [vp, C.c_int, vp, vp, i32, i32, i32, i32, i32, C.POINTER(i64)]
+        lib.pcb_edit_pairs_fetch.argtypes = [vp, C.c_int, vp, vp, vp, i64]
+        lib.pcb_merge.argtypes = ([vp, C.c_int, i32, i32] + [vp] * 9 + [i32, i64] + [vp] * 4 +
+                                  [i32, i32, dbl, i32, i32, i32] + [vp] * 9)
+        lib.pcb_cluster_reads.argtypes = ([vp, C.c_int, vp, vp, vp, i32, i32] + [vp] * 6 + [i32, i32, i32, dbl, i32] +
+                                          [vp, C.POINTER(i32), C.POINTER(i64)] + [vp] * 9)
+        _lib = lib
+    return _lib

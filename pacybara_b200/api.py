@@ -1,0 +1,202 @@
+"""Python host API over the C-ABI (include/pacybara_b200.h).
+
+One `Context` per GPU.  Every method takes either numpy arrays (host memory; the library copies
+in and out) or torch CUDA tensors (device memory; nothing is copied) -- all arrays of one call
+must be of the same kind -- and returns arrays of that kind.  torch is only used to own device
+memory; every computation happens in the hand-written kernels behind the ABI.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from .hostdata import MERGE_OUTPUTS, MergeProblem, PairList
+
+_NP2TORCH = None
+
+
+def _torch():
+    import torch
+    global _NP2TORCH
+    if _NP2TORCH is None:
+        _NP2TORCH = {np.dtype(np.uint8): torch.uint8, np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64}
+    return torch
+
+
+def _is_dev(x) -> bool:
+    return x is not None and hasattr(x, "data_ptr")
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        self.device = int(device)
+        h = C.c_void_p()
+        rc = self.lib.pcb_ctx_create(self.device, C.byref(h))
+        if rc != 0:
+            raise _lib.PcbError(rc, (self.lib.pcb_last_error(None) or b"").decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pcb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ helpers
+    def _check(self, rc: int):
+        if rc != 0:
+            raise _lib.PcbError(rc, (self.lib.pcb_last_error(self.h) or b"").decode())
+
+    def stat(self, name: str) -> int:
+        return int(self.lib.pcb_stat(self.h, _lib.STAT[name]))
+
+    def stats(self) -> Dict[str, int]:
+        return {k: self.stat(k) for k in _lib.STAT}
+
+    def sync(self):
+        self._check(self.lib.pcb_sync(self.h))
+
+    def stream_handle(self) -> int:
+        return int(self.lib.pcb_stream(self.h) or 0)
+
+    def _kind(self, *arrays) -> int:
+        kinds = {_is_dev(a) for a in arrays if a is not None}
+        if len(kinds) > 1:
+            raise TypeError("all arrays of a call must be numpy (host) or all torch CUDA tensors (device)")
+        dev = kinds.pop() if kinds else False
+        if dev:
+            for a in arrays:
+                if a is not None and (not a.is_cuda or a.device.index != self.device or not a.is_contiguous()):
+                    raise TypeError(f"device arrays must be contiguous tensors on cuda:{self.device}")
+        return _lib.MEM_DEVICE if dev else _lib.MEM_HOST
+
+    def _in(self, a, dtype, keep: list):
+        """pointer of an input array (numpy arrays are made contiguous / cast; kept alive in `keep`)."""
+        if a is None:
+            return None
+        if _is_dev(a):
+            if a.dtype != _NP2TORCH[np.dtype(dtype)]:
+                raise TypeError(f"device array has dtype {a.dtype}, expected {np.dtype(dtype)}")
+            return C.c_void_p(a.data_ptr())
+        a = np.ascontiguousarray(a, dtype=dtype)
+        keep.append(a)
+        return a.ctypes.data_as(C.c_void_p)
+
+    def _out(self, mem: int, shape, dtype):
+        if mem == _lib.MEM_DEVICE:
+            torch = _torch()
+            t = torch.empty(shape, dtype=_NP2TORCH[np.dtype(dtype)], device=f"cuda:{self.device}")
+            return t, C.c_void_p(t.data_ptr())
+        a = np.empty(shape, dtype=dtype)
+        return a, a.ctypes.data_as(C.c_void_p)
+
+    # ------------------------------------------------------------------ a1
+    def bucket(self, seq, qual, length, want_qsum: bool = True) -> Dict:
+        """Exact-barcode bucketing (pcb_bucket).  seq/qual: [R, stride] uint8, length: [R] int32."""
+        if _is_dev(seq):
+            _torch()
+        mem = self._kind(seq, qual, length)
+        R, stride = int(seq.shape[0]), int(seq.shape[1])
+        keep: list = []
+        bor, p_bor = self._out(mem, (max(R, 1),), np.int32)
+        bptr, p_bptr = self._out(mem, (R + 1,), np.int32)
+        breads, p_breads = self._out(mem, (max(R, 1),), np.int32)
+        if want_qsum:
+            qsum, p_qsum = self._out(mem, (max(R, 1), stride), np.uint8)
+        else:
+            qsum, p_qsum = None, None
+        nb = C.c_int32(0)
+        self._check(self.lib.pcb_bucket(self.h, mem, self._in(seq, np.uint8, keep), self._in(qual, np.uint8, keep),
+                                        self._in(length, np.int32, keep), R, stride, p_bor, C.byref(nb), p_bptr,
+                                        p_breads, p_qsum))
+        U = int(nb.value)
+        first = breads[bptr[:U].long()] if mem == _lib.MEM_DEVICE else breads[bptr[:U]]
+        return dict(n_buckets=U, bucket_of_read=bor[:R], bucket_ptr=bptr[: U + 1], bucket_reads=breads[:R],
+                    bucket_qsum=None if qsum is None else qsum[:U], first_read=first,
+                    bucket_seq=seq[first.long()] if mem == _lib.MEM_DEVICE else np.asarray(seq)[first],
+                    bucket_len=length[first.long()] if mem == _lib.MEM_DEVICE else np.asarray(length)[first])
+
+    # ------------------------------------------------------------------ a2+a3
+    def edit_pairs(self, seq, length, k: int, q_range: Optional[Tuple[int, int]] = None):
+        """All pairs i<j of the U barcodes with Levenshtein <= k, sorted by (i, j) (pcb_edit_pairs)."""
+        if _is_dev(seq):
+            _torch()
+        mem = self._kind(seq, length)
+        U, stride = int(seq.shape[0]), int(seq.shape[1])
+        lo, hi = (0, U) if q_range is None else q_range
+        keep: list = []
+        n = C.c_int64(0)
+        self._check(self.lib.pcb_edit_pairs(self.h, mem, self._in(seq, np.uint8, keep), self._in(length, np.int32, keep),
+                                            U, stride, int(k), int(lo), int(hi), C.byref(n)))
+        E = int(n.value)
+        ei, p_i = self._out(mem, (max(E, 1),), np.int32)
+        ej, p_j = self._out(mem, (max(E, 1),), np.int32)
+        ed, p_d = self._out(mem, (max(E, 1),), np.int32)
+        self._check(self.lib.pcb_edit_pairs_fetch(self.h, mem, p_i, p_j, p_d, max(E, 1)))
+        return ei[:E], ej[:E], ed[:E]
+
+    # ------------------------------------------------------------------ a4..a13
+    def merge(self, p: MergeProblem, pairs: PairList, shard: Tuple[int, int] = (0, 1)) -> Dict:
+        """Seed clustering + greedy merge + consensus (pcb_merge).  Arrays inside `p` and `pairs`
+        may be numpy or torch CUDA tensors."""
+        arrays = [p.bucket_ptr, p.bucket_reads, p.lexrank, p.bc_id, p.up_id, p.geno_ptr, p.geno_mut, p.geno_q,
+                  p.mut_rank, pairs.q, pairs.r, pairs.d, pairs.ed]
+        if any(_is_dev(a) for a in arrays):
+            _torch()
+        mem = self._kind(*arrays)
+        R = int(p.n_reads)
+        nnz = int(p.geno_mut.shape[0])
+        keep: list = []
+        ins = [self._in(a, np.int32, keep) for a in arrays]
+        outs, ptrs = {}, []
+        for name, dt in MERGE_OUTPUTS:
+            outs[name], ptr = self._out(mem, (max(R, 1),), dt)
+            ptrs.append(ptr)
+        outs["call_mut"], p_call = self._out(mem, (max(nnz, 1),), np.int32)
+        self._check(self.lib.pcb_merge(self.h, mem, R, int(p.n_buckets), *ins[:9], int(p.mut_rank.shape[0]),
+                                       int(pairs.q.shape[0]), *ins[9:], int(p.max_diff), int(p.min_qual),
+                                       float(p.min_jaccard), int(p.min_matches), int(shard[0]), int(shard[1]),
+                                       *ptrs, p_call))
+        out = {k: v[:R] for k, v in outs.items() if k != "call_mut"}
+        out["call_mut"] = outs["call_mut"][:nnz]
+        return out
+
+    # ------------------------------------------------------------------ the whole path
+    def cluster_reads(self, seq, qual, length, lexrank, up_id, geno_ptr, geno_mut, geno_q, mut_rank,
+                      max_diff: int = 2, min_qual: int = 32, min_jaccard: float = 0.2, min_matches: int = 1) -> Dict:
+        """Bucketing -> distances (k = 2*max_diff) -> merge on the device (pcb_cluster_reads)."""
+        arrays = [seq, qual, length, lexrank, up_id, geno_ptr, geno_mut, geno_q, mut_rank]
+        if any(_is_dev(a) for a in arrays):
+            _torch()
+        mem = self._kind(*arrays)
+        R, stride = int(seq.shape[0]), int(seq.shape[1])
+        nnz = int(geno_mut.shape[0])
+        keep: list = []
+        dts = [np.uint8, np.uint8] + [np.int32] * 7
+        ins = [self._in(a, dt, keep) for a, dt in zip(arrays, dts)]
+        bor, p_bor = self._out(mem, (max(R, 1),), np.int32)
+        outs, ptrs = {}, []
+        for name, dt in MERGE_OUTPUTS:
+            outs[name], ptr = self._out(mem, (max(R, 1),), dt)
+            ptrs.append(ptr)
+        outs["call_mut"], p_call = self._out(mem, (max(nnz, 1),), np.int32)
+        nb, ne = C.c_int32(0), C.c_int64(0)
+        self._check(self.lib.pcb_cluster_reads(self.h, mem, ins[0], ins[1], ins[2], R, stride, *ins[3:],
+                                               int(mut_rank.shape[0]), int(max_diff), int(min_qual),
+                                               float(min_jaccard), int(min_matches), p_bor, C.byref(nb), C.byref(ne),
+                                               *ptrs, p_call))
+        out = {k: v[:R] for k, v in outs.items() if k != "call_mut"}
+        out["call_mut"] = outs["call_mut"][:nnz]
+        out["bucket_of_read"] = bor[:R]
+        out["n_buckets"] = int(nb.value)
+        out["n_edges"] = int(ne.value)
+        return out

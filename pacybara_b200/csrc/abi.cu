@@ -1,0 +1,260 @@
+// abi.cu -- the extern "C" boundary declared in include/pacybara_b200.h.
+// Host pointers are staged through stream-ordered device buffers; device pointers are used as
+// they are.  Every entry point converts exceptions into a PCB_E_* code plus pcb_last_error().
+#include <cstring>
+
+#include "common.cuh"
+
+using namespace pcb;
+
+static thread_local std::string g_create_error;
+
+namespace {
+
+template <typename T>
+struct InArr {
+  const T *p = nullptr;
+  DevBuf<T> own;
+  InArr(pcb_ctx *ctx, int mem, const T *src, size_t n) {
+    if (!src) return;
+    if (mem == PCB_MEM_DEVICE) { p = src; return; }
+    own.alloc(ctx, n);
+    if (n) PCB_CUDA(cudaMemcpyAsync(own.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    p = own.p;
+  }
+};
+
+template <typename T>
+struct OutArr {
+  T *p = nullptr;
+  T *host = nullptr;
+  DevBuf<T> own;
+  pcb_ctx *ctx;
+  OutArr(pcb_ctx *c, int mem, T *dst, size_t n) : ctx(c) {
+    if (!dst) return;
+    if (mem == PCB_MEM_DEVICE) { p = dst; return; }
+    own.alloc(c, n);
+    p = own.p; host = dst;
+  }
+  void commit(size_t n) {
+    if (host && n) PCB_CUDA(cudaMemcpyAsync(host, p, n * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+};
+
+template <typename F>
+int guarded(pcb_ctx *ctx, F f) {
+  if (!ctx) return PCB_E_STATE;
+  try {
+    PCB_CUDA(cudaSetDevice(ctx->device));
+    f();
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->err.clear();
+    return PCB_OK;
+  } catch (const Error &e) {
+    ctx->err = e.what();
+    cudaStreamSynchronize(ctx->stream);
+    cudaGetLastError();
+    return e.code;
+  } catch (const std::exception &e) {
+    ctx->err = e.what();
+    cudaStreamSynchronize(ctx->stream);
+    return PCB_E_CUDA;
+  }
+}
+
+__global__ void pairs_from_edges_kernel(const int32_t *__restrict__ ed, int64_t n, int32_t max_diff, int32_t *__restrict__ ped) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) ped[i] = (ed[i] >= 1 && ed[i] <= max_diff) ? ed[i] : 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pcb_abi_version(void) { return PCB_ABI_VERSION; }
+
+const char *pcb_last_error(const pcb_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int pcb_ctx_create(int device, pcb_ctx **out) {
+  if (!out) return PCB_E_STATE;
+  *out = nullptr;
+  pcb_ctx *ctx = nullptr;
+  try {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+      throw Error(PCB_E_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) +
+                                  " (this library has no CPU implementation)");
+    if (device < 0 || device >= n) throw Error(PCB_E_CUDA, "device index out of range");
+    PCB_CUDA(cudaSetDevice(device));
+    ctx = new pcb_ctx();
+    ctx->device = device;
+    PCB_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
+    PCB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    PCB_CUDA(cudaEventCreate(&ctx->ev0));
+    PCB_CUDA(cudaEventCreate(&ctx->ev1));
+    cudaMemPool_t pool;
+    PCB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;
+    PCB_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    *out = ctx;
+    return PCB_OK;
+  } catch (const Error &e) {
+    g_create_error = e.what();
+    delete ctx;
+    cudaGetLastError();
+    return e.code;
+  }
+}
+
+void pcb_ctx_destroy(pcb_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  if (ctx->edges.ei) cudaFreeAsync(ctx->edges.ei, ctx->stream);
+  if (ctx->edges.ej) cudaFreeAsync(ctx->edges.ej, ctx->stream);
+  if (ctx->edges.ed) cudaFreeAsync(ctx->edges.ed, ctx->stream);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+int64_t pcb_stat(const pcb_ctx *ctx, int which) {
+  if (!ctx || which < 0 || which >= PCB_STAT_COUNT) return -1;
+  return ctx->stats[which];
+}
+
+int pcb_sync(pcb_ctx *ctx) {
+  return guarded(ctx, [&] {});
+}
+
+void *pcb_stream(pcb_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int pcb_bucket(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *qual, const int32_t *len, int32_t R,
+               int32_t stride, int32_t *bucket_of_read, int32_t *n_buckets, int32_t *bucket_ptr,
+               int32_t *bucket_reads, uint8_t *bucket_qsum) {
+  return guarded(ctx, [&] {
+    if (R < 0 || stride < 1) throw Error(PCB_E_INPUT, "bad shape");
+    size_t cells = (size_t)R * stride;
+    InArr<uint8_t> d_seq(ctx, mem, seq, cells), d_qual(ctx, mem, qual, cells);
+    InArr<int32_t> d_len(ctx, mem, len, R);
+    OutArr<int32_t> o_bor(ctx, mem, bucket_of_read, R), o_ptr(ctx, mem, bucket_ptr, (size_t)R + 1), o_reads(ctx, mem, bucket_reads, R);
+    OutArr<uint8_t> o_qsum(ctx, mem, bucket_qsum, cells);
+    if (bucket_qsum && !qual) throw Error(PCB_E_INPUT, "quality sums requested without qualities");
+    BucketOut bo{o_bor.p, o_ptr.p, o_reads.p, o_qsum.p};
+    int32_t U = bucket_reads_dev(ctx, d_seq.p, d_qual.p, d_len.p, R, stride, bo, nullptr);
+    if (n_buckets) *n_buckets = U;
+    o_bor.commit(R); o_ptr.commit((size_t)U + 1); o_reads.commit(R); o_qsum.commit((size_t)U * stride);
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int pcb_edit_pairs(pcb_ctx *ctx, int mem, const uint8_t *seq, const int32_t *len, int32_t U, int32_t stride, int32_t k,
+                   int32_t q_begin, int32_t q_end, int64_t *n_edges) {
+  return guarded(ctx, [&] {
+    if (U < 0 || stride < 1) throw Error(PCB_E_INPUT, "bad shape");
+    InArr<uint8_t> d_seq(ctx, mem, seq, (size_t)U * stride);
+    InArr<int32_t> d_len(ctx, mem, len, U);
+    PackedBarcodes bc;
+    pack_barcodes(ctx, d_seq.p, d_len.p, nullptr, U, stride, bc);
+    edit_pairs_dev(ctx, bc, k, q_begin, q_end);
+    if (n_edges) *n_edges = ctx->edges.n;
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int pcb_edit_pairs_fetch(pcb_ctx *ctx, int mem, int32_t *ei, int32_t *ej, int32_t *ed, int64_t cap) {
+  return guarded(ctx, [&] {
+    if (!ctx->edges.valid) throw Error(PCB_E_STATE, "pcb_edit_pairs_fetch before pcb_edit_pairs");
+    int64_t n = ctx->edges.n;
+    if (cap < n) throw Error(PCB_E_CAPACITY, "edge buffers hold " + std::to_string(cap) + ", need " + std::to_string(n));
+    cudaMemcpyKind kind = mem == PCB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    if (n) {
+      PCB_CUDA(cudaMemcpyAsync(ei, ctx->edges.ei, n * sizeof(int32_t), kind, ctx->stream));
+      PCB_CUDA(cudaMemcpyAsync(ej, ctx->edges.ej, n * sizeof(int32_t), kind, ctx->stream));
+      PCB_CUDA(cudaMemcpyAsync(ed, ctx->edges.ed, n * sizeof(int32_t), kind, ctx->stream));
+    }
+  });
+}
+
+int pcb_merge(pcb_ctx *ctx, int mem, int32_t R, int32_t U, const int32_t *bucket_ptr, const int32_t *bucket_reads,
+              const int32_t *lexrank, const int32_t *bc_id, const int32_t *up_id, const int32_t *geno_ptr,
+              const int32_t *geno_mut, const int32_t *geno_q, const int32_t *mut_rank, int32_t n_mut, int64_t n_pairs,
+              const int32_t *pair_q, const int32_t *pair_r, const int32_t *pair_d, const int32_t *pair_ed,
+              int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches, int32_t shard_rank,
+              int32_t shard_count, int32_t *read_root, int32_t *read_pos, int32_t *row_size, int64_t *row_key,
+              int32_t *row_bc, int32_t *row_up, int64_t *row_call_off, int32_t *row_call_n, int32_t *call_mut) {
+  return guarded(ctx, [&] {
+    if (R < 0 || U < 0 || n_pairs < 0) throw Error(PCB_E_INPUT, "bad shape");
+    int64_t nnz = 0;
+    if (R > 0) {
+      if (mem == PCB_MEM_DEVICE) nnz = read_scalar(ctx, geno_ptr + R); else nnz = geno_ptr[R];
+    }
+    InArr<int32_t> d_bptr(ctx, mem, bucket_ptr, (size_t)U + 1), d_breads(ctx, mem, bucket_reads, R), d_lex(ctx, mem, lexrank, R),
+        d_bc(ctx, mem, bc_id, R), d_up(ctx, mem, up_id, R), d_gptr(ctx, mem, geno_ptr, (size_t)R + 1),
+        d_gmut(ctx, mem, geno_mut, nnz), d_gq(ctx, mem, geno_q, nnz), d_rank(ctx, mem, mut_rank, n_mut),
+        d_pq(ctx, mem, pair_q, n_pairs), d_pr(ctx, mem, pair_r, n_pairs), d_pd(ctx, mem, pair_d, n_pairs),
+        d_pe(ctx, mem, pair_ed, n_pairs);
+    OutArr<int32_t> o_root(ctx, mem, read_root, R), o_pos(ctx, mem, read_pos, R), o_size(ctx, mem, row_size, R),
+        o_bc(ctx, mem, row_bc, R), o_up(ctx, mem, row_up, R), o_calln(ctx, mem, row_call_n, R), o_call(ctx, mem, call_mut, nnz);
+    OutArr<int64_t> o_key(ctx, mem, row_key, R), o_calloff(ctx, mem, row_call_off, R);
+    MergeIn in{R, U, n_mut, d_bptr.p, d_breads.p, d_lex.p, d_bc.p, d_up.p, d_gptr.p, d_gmut.p, d_gq.p, d_rank.p,
+               n_pairs, d_pq.p, d_pr.p, d_pd.p, d_pe.p, max_diff, min_qual, min_matches, min_jaccard, shard_rank, shard_count};
+    MergeOut out{o_root.p, o_pos.p, o_size.p, o_key.p, o_bc.p, o_up.p, o_calloff.p, o_calln.p, o_call.p};
+    merge_dev(ctx, in, out);
+    o_root.commit(R); o_pos.commit(R); o_size.commit(R); o_bc.commit(R); o_up.commit(R); o_calln.commit(R);
+    o_call.commit(nnz); o_key.commit(R); o_calloff.commit(R);
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *qual, const int32_t *len, int32_t R,
+                      int32_t stride, const int32_t *lexrank, const int32_t *up_id, const int32_t *geno_ptr,
+                      const int32_t *geno_mut, const int32_t *geno_q, const int32_t *mut_rank, int32_t n_mut,
+                      int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches,
+                      int32_t *bucket_of_read, int32_t *n_buckets, int64_t *n_edges, int32_t *read_root,
+                      int32_t *read_pos, int32_t *row_size, int64_t *row_key, int32_t *row_bc, int32_t *row_up,
+                      int64_t *row_call_off, int32_t *row_call_n, int32_t *call_mut) {
+  return guarded(ctx, [&] {
+    if (R < 0 || stride < 1) throw Error(PCB_E_INPUT, "bad shape");
+    if (max_diff < 0 || max_diff > 3) throw Error(PCB_E_INPUT, "maxDiff must be between 0 and 3");
+    int64_t nnz = 0;
+    if (R > 0) {
+      if (mem == PCB_MEM_DEVICE) nnz = read_scalar(ctx, geno_ptr + R); else nnz = geno_ptr[R];
+    }
+    size_t cells = (size_t)R * stride;
+    InArr<uint8_t> d_seq(ctx, mem, seq, cells), d_qual(ctx, mem, qual, cells);
+    InArr<int32_t> d_len(ctx, mem, len, R), d_lex(ctx, mem, lexrank, R), d_up(ctx, mem, up_id, R),
+        d_gptr(ctx, mem, geno_ptr, (size_t)R + 1), d_gmut(ctx, mem, geno_mut, nnz), d_gq(ctx, mem, geno_q, nnz),
+        d_rank(ctx, mem, mut_rank, n_mut);
+    OutArr<int32_t> o_bor(ctx, mem, bucket_of_read, R), o_root(ctx, mem, read_root, R), o_pos(ctx, mem, read_pos, R),
+        o_size(ctx, mem, row_size, R), o_bc(ctx, mem, row_bc, R), o_up(ctx, mem, row_up, R),
+        o_calln(ctx, mem, row_call_n, R), o_call(ctx, mem, call_mut, nnz);
+    OutArr<int64_t> o_key(ctx, mem, row_key, R), o_calloff(ctx, mem, row_call_off, R);
+    DevBuf<int32_t> bptr(ctx, (size_t)R + 1), breads(ctx, R), bor_tmp;
+    int32_t *bor = o_bor.p;
+    if (!bor) { bor_tmp.alloc(ctx, R); bor = bor_tmp.p; }
+    // a1: buckets
+    PackedBarcodes uniq;
+    BucketOut bo{bor, bptr.p, breads.p, nullptr};
+    int32_t U = bucket_reads_dev(ctx, d_seq.p, d_qual.p, d_len.p, R, stride, bo, &uniq);
+    if (n_buckets) *n_buckets = U;
+    // a2+a3: distances up to 2*maxDiff (what pacybara.sh:466-468 asks of calcEdits.R)
+    edit_pairs_dev(ctx, uniq, 2 * max_diff, 0, U);
+    int64_t E = ctx->edges.n;
+    if (n_edges) *n_edges = E;
+    DevBuf<int32_t> ped(ctx, (size_t)E);
+    if (E) PCB_LAUNCH(ctx, pairs_from_edges_kernel, grid_for(E, 256), 256, 0, ctx->edges.ed, E, max_diff, ped.p);
+    // a4..a13: merge; the barcode id of a read is its bucket
+    MergeIn in{R, U, n_mut, bptr.p, breads.p, d_lex.p, bor, d_up.p, d_gptr.p, d_gmut.p, d_gq.p, d_rank.p,
+               E, ctx->edges.ei, ctx->edges.ej, ctx->edges.ed, ped.p, max_diff, min_qual, min_matches, min_jaccard, 0, 1};
+    MergeOut out{o_root.p, o_pos.p, o_size.p, o_key.p, o_bc.p, o_up.p, o_calloff.p, o_calln.p, o_call.p};
+    merge_dev(ctx, in, out);
+    o_bor.commit(R); o_root.commit(R); o_pos.commit(R); o_size.commit(R); o_bc.commit(R); o_up.commit(R);
+    o_calln.commit(R); o_call.commit(nnz); o_key.commit(R); o_calloff.commit(R);
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+}  // extern "C"

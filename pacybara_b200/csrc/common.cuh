@@ -1,0 +1,150 @@
+// common.cuh -- context, error handling, stream-ordered device buffers, launch helper.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/pacybara_b200.h"
+
+namespace pcb {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define PCB_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess)                                                                      \
+      throw pcb::Error(PCB_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " (" + \
+                                       __FILE__ + ":" + std::to_string(__LINE__) + ")");       \
+  } while (0)
+
+}  // namespace pcb
+
+// Result of the last pcb_edit_pairs call, kept on the device until fetched.
+struct pcb_edges {
+  int32_t *ei = nullptr, *ej = nullptr, *ed = nullptr;
+  int64_t n = 0;
+  bool valid = false;
+};
+
+struct pcb_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int64_t stats[PCB_STAT_COUNT] = {0};
+  pcb_edges edges;
+};
+
+namespace pcb {
+
+// Stream-ordered allocation out of the device's default pool (kept warm: the release
+// threshold is raised at context creation, so steady-state steps never reach the OS).
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  cudaStream_t s = nullptr;
+  DevBuf() {}
+  DevBuf(pcb_ctx *ctx, size_t count) { alloc(ctx, count); }
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+  DevBuf &operator=(DevBuf &&o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  void alloc(pcb_ctx *ctx, size_t count) {
+    release();
+    s = ctx->stream; n = count;
+    PCB_CUDA(cudaMallocAsync((void **)&p, (count ? count : 1) * sizeof(T), s));
+  }
+  void release() {
+    if (p) { cudaFreeAsync(p, s); p = nullptr; n = 0; }
+  }
+  T *detach() { T *q = p; p = nullptr; n = 0; return q; }
+  ~DevBuf() { release(); }
+  operator T *() const { return p; }
+};
+
+inline unsigned grid_for(size_t n, unsigned block) {
+  size_t g = (n + block - 1) / block;
+  return (unsigned)(g ? g : 1);
+}
+
+#define PCB_LAUNCH(ctx, kernel, grid, block, smem, ...)                 \
+  do {                                                                  \
+    kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);    \
+    (ctx)->stats[PCB_STAT_KERNEL_LAUNCHES]++;                           \
+    PCB_CUDA(cudaGetLastError());                                       \
+  } while (0)
+
+template <typename T>
+inline T read_scalar(pcb_ctx *ctx, const T *dev) {
+  T v;
+  PCB_CUDA(cudaMemcpyAsync(&v, dev, sizeof(T), cudaMemcpyDeviceToHost, ctx->stream));
+  PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return v;
+}
+
+// ---- primitives (prims.cu)
+void exclusive_scan_u32(pcb_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n);   // out may alias in
+void exclusive_scan_i64(pcb_ctx *ctx, const int64_t *in, int64_t *out, size_t n);
+// Stable LSD radix sort of (key, val) pairs on the low `bits` bits of the key.  Both buffer pairs
+// must hold n items; returns 0 if the result is in (k0, v0), 1 if in (k1, v1).
+int radix_sort_pairs(pcb_ctx *ctx, uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, size_t n, int bits);
+void fill_i32(pcb_ctx *ctx, int32_t *p, size_t n, int32_t v);
+void fill_i64(pcb_ctx *ctx, int64_t *p, size_t n, int64_t v);
+void iota_u32(pcb_ctx *ctx, uint32_t *p, size_t n);
+inline int bits_for(uint64_t max_value) {
+  int b = 1;
+  while (b < 64 && (max_value >> b)) b++;
+  return b;
+}
+
+// ---- stages on device memory (bucket.cu, edit_pairs.cu, merge.cu)
+struct PackedBarcodes {      // planes of n barcodes: x = plane L (bit 0 of each base), y = plane H
+  DevBuf<ulonglong2> planes;
+  DevBuf<int32_t> len;
+  int32_t n = 0, min_len = 0, max_len = 0;
+};
+// ASCII rows (optionally gathered through `rows`) -> planes; throws PCB_E_INPUT on bad input
+void pack_barcodes(pcb_ctx *ctx, const uint8_t *seq, const int32_t *len, const int32_t *rows, int32_t n,
+                   int32_t stride, PackedBarcodes &out);
+
+struct BucketOut {           // all device pointers, caller-owned
+  int32_t *bucket_of_read, *bucket_ptr, *bucket_reads;
+  uint8_t *bucket_qsum;      // may be null
+};
+int32_t bucket_reads_dev(pcb_ctx *ctx, const uint8_t *seq, const uint8_t *qual, const int32_t *len, int32_t R,
+                         int32_t stride, const BucketOut &out, PackedBarcodes *unique_out);
+
+void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q_begin, int32_t q_end);
+
+struct MergeIn {             // device pointers
+  int32_t R, U, n_mut;
+  const int32_t *bucket_ptr, *bucket_reads, *lexrank, *bc_id, *up_id;
+  const int32_t *geno_ptr, *geno_mut, *geno_q, *mut_rank;
+  int64_t n_pairs;
+  const int32_t *pair_q, *pair_r, *pair_d, *pair_ed;
+  int32_t max_diff, min_qual, min_matches;
+  double min_jaccard;
+  int32_t shard_rank, shard_count;
+};
+struct MergeOut {            // device pointers, caller-owned
+  int32_t *read_root, *read_pos, *row_size;
+  int64_t *row_key;
+  int32_t *row_bc, *row_up;
+  int64_t *row_call_off;
+  int32_t *row_call_n, *call_mut;
+};
+void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out);
+
+}  // namespace pcb

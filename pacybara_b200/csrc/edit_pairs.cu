@@ -1,0 +1,217 @@
+// edit_pairs.cu -- all pairs of unique barcodes within Levenshtein distance k (rows a2+a3).
+//
+// Replaces the bowtie2 all-vs-all alignment and src/pacybara_calcEdits.R (src/pacybara.sh:448-468).
+//
+// Candidate generation (pigeonhole): split the query into k+1 pieces; if lev(query, target) <= k
+// one piece occurs unchanged in the target, displaced by at most k.  So:
+//   1. index   every q-gram of every barcode into the bin (position, q-gram)      [seed_count/fill]
+//   2. probe   for each query piece t and shift s, walk the bin (start_t + s, q-gram of piece t),
+//              and score each entry with the bit-parallel Myers kernel             [probe_kernel]
+//   3. order   sort the hits by (i, j), drop the duplicates a pair found through several
+//              pieces produces                                                     [radix sort + compact]
+// q = floor(min length / (k+1)), capped so that the bin table stays small; q = 0 (barcodes shorter
+// than k+1) degenerates to one bin, i.e. all pairs.
+//
+// Roofline: the probe kernel is integer-ALU bound (~14 LOP3/IADD/SHF per text column per pair,
+// nothing to feed a tensor core with); its HBM traffic is the bin entries (4 B) plus the 16-byte
+// planes of each scored target, mostly served by L2.  See DESIGN.md for the op and byte counts.
+#include "common.cuh"
+#include "myers.cuh"
+
+namespace pcb {
+
+struct SeedGeom {
+  int32_t q;         // seed length (0: single bin)
+  int32_t npos;      // target positions indexed: 0 .. npos-1
+  int32_t k;
+  uint32_t nbins;
+};
+
+__device__ __forceinline__ uint32_t seed_bin(const SeedGeom g, uint64_t L, uint64_t H, int src_pos, int bin_pos) {
+  if (g.q == 0) return 0u;
+  return ((uint32_t)bin_pos << (2 * g.q)) | qgram_key(L, H, src_pos, g.q);
+}
+
+__global__ void seed_count_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int32_t U,
+                                  SeedGeom g, uint32_t *__restrict__ bin_cnt) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)U * g.npos) return;
+  int32_t j = (int32_t)(i / g.npos), p = (int32_t)(i % g.npos);
+  if (g.q > 0 && p + g.q > len[j]) return;
+  ulonglong2 pl = planes[j];
+  atomicAdd(&bin_cnt[seed_bin(g, pl.x, pl.y, p, p)], 1u);
+}
+
+__global__ void seed_fill_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int32_t U,
+                                 SeedGeom g, uint32_t *__restrict__ cursor, int32_t *__restrict__ ent) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)U * g.npos) return;
+  int32_t j = (int32_t)(i / g.npos), p = (int32_t)(i % g.npos);
+  if (g.q > 0 && p + g.q > len[j]) return;
+  ulonglong2 pl = planes[j];
+  uint32_t at = atomicAdd(&cursor[seed_bin(g, pl.x, pl.y, p, p)], 1u);
+  ent[at] = j;
+}
+
+// One thread per probe (query i, piece t, shift s).  counters: [0] hits emitted, [1] pairs scored,
+// [2] cells (sum len_i * len_j).
+template <bool WIDE>
+__global__ void __launch_bounds__(256) probe_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len,
+                                                    int32_t q_begin, int32_t q_end, SeedGeom g,
+                                                    const uint32_t *__restrict__ bin_off, const int32_t *__restrict__ ent,
+                                                    uint64_t *__restrict__ hit_key, uint32_t *__restrict__ hit_d,
+                                                    unsigned long long cap, int key_shift, unsigned long long *counters) {
+  const int n_shift = g.q == 0 ? 1 : 2 * g.k + 1;
+  const int per_query = g.q == 0 ? 1 : (g.k + 1) * n_shift;
+  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t n_probe = (size_t)(q_end - q_begin) * per_query;
+  unsigned long long scored = 0, cells = 0;
+  if (tid < n_probe) {
+    int32_t i = q_begin + (int32_t)(tid / per_query);
+    int32_t rem = (int32_t)(tid % per_query);
+    int32_t t = rem / n_shift, s = rem % n_shift - (g.q == 0 ? 0 : g.k);
+    int32_t m = len[i];
+    int32_t st = g.q == 0 ? 0 : (int32_t)((int64_t)t * m / (g.k + 1));
+    int32_t p = st + s;
+    if (p >= 0 && p < g.npos) {
+      ulonglong2 a = planes[i];
+      uint32_t bin = seed_bin(g, a.x, a.y, st, p);
+      uint32_t lo = bin_off[bin], hi = bin_off[bin + 1];
+      for (uint32_t e = lo; e < hi; e++) {
+        int32_t j = ent[e];
+        if (j == i || !is_query_side(i, j)) continue;
+        int32_t n = len[j];
+        int32_t dl = m - n;
+        if (dl > g.k || -dl > g.k) continue;
+        ulonglong2 b = planes[j];
+        int d = WIDE ? myers64(a.x, a.y, m, b.x, b.y, n)
+                     : myers32((uint32_t)a.x, (uint32_t)a.y, m, (uint32_t)b.x, (uint32_t)b.y, n);
+        scored++; cells += (unsigned long long)(m * n);
+        if (d <= g.k) {
+          unsigned long long at = atomicAdd(&counters[0], 1ull);
+          if (at < cap) {
+            uint32_t x = i < j ? i : j, y = i < j ? j : i;
+            hit_key[at] = ((uint64_t)x << key_shift) | y;
+            hit_d[at] = (uint32_t)d;
+          }
+        }
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    scored += __shfl_down_sync(0xFFFFFFFFu, scored, o);
+    cells += __shfl_down_sync(0xFFFFFFFFu, cells, o);
+  }
+  if ((threadIdx.x & 31) == 0 && scored) { atomicAdd(&counters[1], scored); atomicAdd(&counters[2], cells); }
+}
+
+__global__ void flag_unique_kernel(const uint64_t *__restrict__ key, size_t n, uint32_t *__restrict__ flag) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1u : 0u;
+}
+
+__global__ void compact_edges_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ d, const uint32_t *__restrict__ rank,
+                                     size_t n, int key_shift, int32_t *__restrict__ ei, int32_t *__restrict__ ej,
+                                     int32_t *__restrict__ ed) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (i == 0 || key[i] != key[i - 1]) {
+    uint32_t at = rank[i];
+    ei[at] = (int32_t)(key[i] >> key_shift);
+    ej[at] = (int32_t)(key[i] & ((1ull << key_shift) - 1ull));
+    ed[at] = (int32_t)d[i];
+  }
+}
+
+static void free_edges(pcb_ctx *ctx) {
+  pcb_edges &e = ctx->edges;
+  if (e.ei) cudaFreeAsync(e.ei, ctx->stream);
+  if (e.ej) cudaFreeAsync(e.ej, ctx->stream);
+  if (e.ed) cudaFreeAsync(e.ed, ctx->stream);
+  e = pcb_edges();
+}
+
+void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q_begin, int32_t q_end) {
+  free_edges(ctx);
+  const int32_t U = bc.n;
+  ctx->stats[PCB_STAT_PAIRS_SCORED] = ctx->stats[PCB_STAT_CELLS] = ctx->stats[PCB_STAT_EDGES] = 0;
+  ctx->stats[PCB_STAT_PROBE_NS] = 0;
+  if (k < 0 || k > 8) throw Error(PCB_E_INPUT, "k must be in 0..8");
+  if (q_begin < 0 || q_end > U || q_begin > q_end) throw Error(PCB_E_INPUT, "query range outside [0, U)");
+  pcb_edges &res = ctx->edges;
+  res.valid = true;
+  if (U < 2 || q_begin == q_end) return;
+
+  SeedGeom g;
+  g.k = k;
+  g.q = bc.min_len / (k + 1);
+  if (g.q > 12) g.q = 12;
+  while (g.q > 0 && ((uint64_t)(bc.max_len - g.q + 1) << (2 * g.q)) > (1ull << 26)) g.q--;
+  g.npos = g.q == 0 ? 1 : bc.max_len - g.q + 1;
+  g.nbins = g.q == 0 ? 1u : (uint32_t)g.npos << (2 * g.q);
+  ctx->stats[PCB_STAT_SEED_LEN] = g.q;
+
+  // ---- index
+  DevBuf<uint32_t> bin_off(ctx, (size_t)g.nbins + 1), cursor(ctx, (size_t)g.nbins + 1);
+  DevBuf<int32_t> ent(ctx, (size_t)U * g.npos);
+  PCB_CUDA(cudaMemsetAsync(bin_off.p, 0, ((size_t)g.nbins + 1) * sizeof(uint32_t), ctx->stream));
+  size_t n_slots = (size_t)U * g.npos;
+  PCB_LAUNCH(ctx, seed_count_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, U, g, bin_off.p);
+  exclusive_scan_u32(ctx, bin_off.p, bin_off.p, (size_t)g.nbins + 1);
+  PCB_CUDA(cudaMemcpyAsync(cursor.p, bin_off.p, ((size_t)g.nbins + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+  PCB_LAUNCH(ctx, seed_fill_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, U, g, cursor.p, ent.p);
+
+  // ---- probe (re-run with a larger hit buffer if the first guess overflows)
+  const int key_shift = bits_for((uint64_t)(U - 1));
+  const int per_query = g.q == 0 ? 1 : (k + 1) * (2 * k + 1);
+  size_t n_probe = (size_t)(q_end - q_begin) * per_query;
+  unsigned long long cap = 8ull * (unsigned long long)(q_end - q_begin) + (1ull << 16);
+  DevBuf<unsigned long long> counters(ctx, 4);
+  DevBuf<uint64_t> hk0, hk1;
+  DevBuf<uint32_t> hv0, hv1;
+  unsigned long long h_counters[4];
+  const bool wide = bc.max_len > 32;
+  for (int attempt = 0;; attempt++) {
+    hk0.alloc(ctx, cap); hv0.alloc(ctx, cap);
+    PCB_CUDA(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    PCB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (wide)
+      PCB_LAUNCH(ctx, probe_kernel<true>, grid_for(n_probe, 256), 256, 0, bc.planes.p, bc.len.p, q_begin, q_end, g,
+                 bin_off.p, ent.p, hk0.p, hv0.p, cap, key_shift, counters.p);
+    else
+      PCB_LAUNCH(ctx, probe_kernel<false>, grid_for(n_probe, 256), 256, 0, bc.planes.p, bc.len.p, q_begin, q_end, g,
+                 bin_off.p, ent.p, hk0.p, hv0.p, cap, key_shift, counters.p);
+    PCB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    PCB_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    PCB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->stats[PCB_STAT_PROBE_NS] = (int64_t)(ms * 1e6);
+    if (h_counters[0] <= cap) break;
+    if (attempt >= 2) throw Error(PCB_E_CUDA, "hit buffer overflowed twice");
+    cap = h_counters[0];
+  }
+  ctx->stats[PCB_STAT_PAIRS_SCORED] = (int64_t)h_counters[1];
+  ctx->stats[PCB_STAT_CELLS] = (int64_t)h_counters[2];
+  size_t n_hits = (size_t)h_counters[0];
+  if (n_hits == 0) return;
+
+  // ---- canonical order, duplicates removed
+  hk1.alloc(ctx, n_hits); hv1.alloc(ctx, n_hits);
+  int where = radix_sort_pairs(ctx, hk0.p, hv0.p, hk1.p, hv1.p, n_hits, 2 * key_shift);
+  uint64_t *sk = where ? hk1.p : hk0.p;
+  uint32_t *sv = where ? hv1.p : hv0.p;
+  DevBuf<uint32_t> rank(ctx, n_hits);
+  PCB_LAUNCH(ctx, flag_unique_kernel, grid_for(n_hits, 256), 256, 0, sk, n_hits, rank.p);
+  uint32_t last_flag = read_scalar(ctx, rank.p + (n_hits - 1));
+  exclusive_scan_u32(ctx, rank.p, rank.p, n_hits);
+  size_t n_edges = (size_t)read_scalar(ctx, rank.p + (n_hits - 1)) + last_flag;
+  PCB_CUDA(cudaMallocAsync((void **)&res.ei, n_edges * sizeof(int32_t), ctx->stream));
+  PCB_CUDA(cudaMallocAsync((void **)&res.ej, n_edges * sizeof(int32_t), ctx->stream));
+  PCB_CUDA(cudaMallocAsync((void **)&res.ed, n_edges * sizeof(int32_t), ctx->stream));
+  PCB_LAUNCH(ctx, compact_edges_kernel, grid_for(n_hits, 256), 256, 0, sk, sv, rank.p, n_hits, key_shift, res.ei, res.ej, res.ed);
+  res.n = (int64_t)n_edges;
+  ctx->stats[PCB_STAT_EDGES] = res.n;
+}
+
+}  // namespace pcb

@@ -1,0 +1,393 @@
+// merge_core.h -- the per-component cluster replay (seed step, greedy merge, consensus).
+//
+// One connected component of the "link" graph (buckets joined by a row with
+// 1 <= dist <= maxDiff) is an independent unit of the reference's sequential algorithm
+// (src/pacybara_cluster.py:385-455; the reference's own abandoned plan says the same,
+// src/legacy/pacybara_parstrat.py:63-87).  process_component() replays that algorithm for
+// one component, exactly, in the reference's visiting order.  On the GPU one thread runs
+// one component (merge.cu); the function is __host__ __device__ so that the identical code
+// can be exercised without a GPU by tests/host_emul (a unit-test harness, never a product
+// path: the shipped library only ever launches it as a kernel).
+//
+// Formulation (equivalent to the reference's read-pair loops, proven against the oracle):
+//  * a cluster is a linked list of reads (rd_next) hanging off a slot; slots form a
+//    union-find so that "relabel every member" (:198-199) is O(alpha); the root carries the
+//    reference-visible attributes (creation key of the surviving cid, head, tail, size);
+//  * addLink(rid1, rid2) keeps rid1's cluster id and appends rid2's list (:193-202);
+//  * the size rule |log2(s1/s2)| >= ed is the integer test max >= min << ed (exact for
+//    every size below 2^26);
+//  * the transitive rule (:442) only depends on the buckets of the members, so it runs over
+//    bucket runs of the two member lists and looks distances up in the sorted adjacency;
+//  * the genotype rule (:447-452) needs, per mutation, (#reads with Q>0, sum Q) of each side:
+//    accumulated in a small open-addressing table in per-component scratch;
+//  * a failed test between two clusters is remembered until the next merge in the component
+//    (the state it depended on cannot change before that), which turns the |b1| x |b2|
+//    read-pair expansion of a row into one test per distinct cluster pair.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define PCB_HD __host__ __device__ __forceinline__
+#else
+#define PCB_HD inline
+#endif
+
+namespace pcb {
+
+struct GenoSlot {          // 32 bytes
+  int32_t key;             // mutation id (or barcode id when counting), -1 empty
+  int32_t obs1, obs2;      // #reads with Q>0 on each side / #reads carrying the key
+  int32_t pad;
+  int64_t sum1, sum2;      // sum of Q on each side
+};
+
+struct MergeParams {
+  int32_t maxDiff, minQual, minMatches;
+  double minJaccard;
+};
+
+#ifndef PCB_FILL                        // same values as include/pacybara_b200.h
+#define PCB_FILL INT32_MIN              // "not produced by this shard"
+#define PCB_NEEDS_ALIGNMENT (-2)        // reference would call muscle (:530)
+#endif
+
+struct MergeCtx {
+  // problem (read-only)
+  int32_t R, U;
+  const int32_t *bucket_ptr, *bucket_reads, *bucket_of_read, *lexrank, *bc_id, *up_id;
+  const int32_t *geno_ptr, *geno_mut, *geno_q, *mut_rank;
+  // unique bucket pairs: symmetric adjacency sorted by (a, nbr), and the per-component
+  // visiting lists (pairs with 1 <= ed <= maxDiff, grouped by component, visiting order kept)
+  const int32_t *adj_ptr, *adj_nbr, *adj_d;
+  const int32_t *comp_ptr, *comp_buckets;            // component -> buckets (ascending)
+  const int32_t *cpair_ptr, *cpair_q, *cpair_r, *cpair_ed;
+  // per-component scratch
+  const int64_t *scr_slot_off;   // into slots[]  (capacity = scr_slot_cap[c], a power of two)
+  const int32_t *scr_slot_cap;
+  const int64_t *scr_list_off;   // into lists[]  (capacity 2 * (#reads + #geno entries) of the component)
+  const int64_t *call_off;       // into call_mut[] (capacity = #geno entries of the component)
+  GenoSlot *slots;
+  int32_t *lists;
+  // cluster state (size R)
+  int32_t *rd_slot, *rd_next;
+  int32_t *sl_parent, *sl_head, *sl_tail, *sl_size;
+  int64_t *sl_key;
+  // outputs (size R unless noted)
+  int32_t *read_root, *read_pos;                     // representative read of the row, position in it
+  int32_t *row_size, *row_bc, *row_up, *row_call_n;  // valid at representative reads
+  int64_t *row_key, *row_call_off;
+  int32_t *call_mut;                                 // [nnz]
+  int32_t *status;                                   // [4]: error code, detail, #links, #tests
+  MergeParams prm;
+};
+
+PCB_HD int32_t slot_find(const MergeCtx &c, int32_t s) {
+  while (c.sl_parent[s] != s) {
+    int32_t g = c.sl_parent[c.sl_parent[s]];
+    c.sl_parent[s] = g;
+    s = g;
+  }
+  return s;
+}
+PCB_HD int32_t cluster_of(const MergeCtx &c, int32_t r) {
+  int32_t s = c.rd_slot[r];
+  return s < 0 ? -1 : slot_find(c, s);
+}
+
+// src/pacybara_cluster.py:185-220
+PCB_HD void add_link(const MergeCtx &c, int32_t rid1, int32_t rid2, int64_t new_key) {
+  int32_t c1 = cluster_of(c, rid1), c2 = cluster_of(c, rid2);
+  if (c1 >= 0) {
+    if (c2 >= 0) {
+      if (c1 == c2) return;
+      int32_t head = c.sl_head[c1], tail = c.sl_tail[c2], size = c.sl_size[c1] + c.sl_size[c2];
+      int64_t key = c.sl_key[c1];
+      c.rd_next[c.sl_tail[c1]] = c.sl_head[c2];
+      int32_t root = c.sl_size[c1] >= c.sl_size[c2] ? c1 : c2;
+      int32_t child = root == c1 ? c2 : c1;
+      c.sl_parent[child] = root;
+      c.sl_head[root] = head; c.sl_tail[root] = tail; c.sl_size[root] = size; c.sl_key[root] = key;
+    } else {
+      c.rd_next[c.sl_tail[c1]] = rid2; c.rd_next[rid2] = -1;
+      c.sl_tail[c1] = rid2; c.sl_size[c1] += 1; c.rd_slot[rid2] = c1;
+    }
+  } else if (c2 >= 0) {
+    c.rd_next[c.sl_tail[c2]] = rid1; c.rd_next[rid1] = -1;
+    c.sl_tail[c2] = rid1; c.sl_size[c2] += 1; c.rd_slot[rid1] = c2;
+  } else {
+    int32_t s = rid1;
+    c.sl_parent[s] = s; c.sl_head[s] = rid1; c.sl_tail[s] = rid2; c.sl_size[s] = 2; c.sl_key[s] = new_key;
+    c.rd_next[rid1] = rid2; c.rd_next[rid2] = -1;
+    c.rd_slot[rid1] = s; c.rd_slot[rid2] = s;
+  }
+}
+
+PCB_HD uint32_t hash_i32(int32_t k) {
+  uint32_t x = (uint32_t)k;
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+
+struct Table {
+  GenoSlot *slots; int32_t mask; int32_t *touched; int32_t n_touched;
+};
+PCB_HD GenoSlot *table_slot(Table &t, int32_t key) {
+  uint32_t i = hash_i32(key) & (uint32_t)t.mask;
+  for (;;) {
+    GenoSlot *s = &t.slots[i];
+    if (s->key == key) return s;
+    if (s->key == -1) {
+      s->key = key; s->obs1 = s->obs2 = 0; s->sum1 = s->sum2 = 0;
+      t.touched[t.n_touched++] = (int32_t)i;
+      return s;
+    }
+    i = (i + 1) & (uint32_t)t.mask;
+  }
+}
+PCB_HD const GenoSlot *table_find(const Table &t, int32_t key) {
+  uint32_t i = hash_i32(key) & (uint32_t)t.mask;
+  for (;;) {
+    const GenoSlot *s = &t.slots[i];
+    if (s->key == key) return s;
+    if (s->key == -1) return nullptr;
+    i = (i + 1) & (uint32_t)t.mask;
+  }
+}
+PCB_HD void table_clear(Table &t) {
+  for (int32_t i = 0; i < t.n_touched; i++) t.slots[t.touched[i]].key = -1;
+  t.n_touched = 0;
+}
+
+// distance between two buckets as edistLookup holds it (:236,:266,:294); -1 = absent (inf)
+PCB_HD int32_t lookup_dist(const MergeCtx &c, int32_t a, int32_t b) {
+  if (a == b) return 0;
+  int32_t lo = c.adj_ptr[a], hi = c.adj_ptr[a + 1];
+  while (lo < hi) {
+    int32_t mid = (lo + hi) >> 1;
+    if (c.adj_nbr[mid] < b) lo = mid + 1; else hi = mid;
+  }
+  return (lo < c.adj_ptr[a + 1] && c.adj_nbr[lo] == b) ? c.adj_d[lo] : -1;
+}
+
+// SEED CLUSTERING of one bucket (:385-400)
+PCB_HD void seed_bucket(const MergeCtx &c, int32_t b, Table &tab) {
+  int32_t lo = c.bucket_ptr[b], n = c.bucket_ptr[b + 1] - lo;
+  if (n < 2) return;
+  const int32_t *rids = c.bucket_reads + lo;
+  // varMatrix + filterSeqError (:338-356): per mutation #reads with Q>0 and sum of Q over the bucket
+  for (int32_t i = 0; i < n; i++)
+    for (int32_t e = c.geno_ptr[rids[i]]; e < c.geno_ptr[rids[i] + 1]; e++) {
+      GenoSlot *s = table_slot(tab, c.geno_mut[e]);
+      int32_t q = c.geno_q[e];
+      if (q > 0) s->obs1++;
+      s->sum1 += q;
+    }
+  int32_t n_created = 0;
+  for (int32_t i = 1; i < n; i++) {
+    int32_t ri = rids[i];
+    for (int32_t j = 0; j < i; j++) {
+      int32_t rj = rids[j];
+      int32_t ci = cluster_of(c, ri);
+      if (ci >= 0 && ci == cluster_of(c, rj)) continue;     // addLink would be a no-op
+      // calcJaccard on presence over the kept mutations (:358-367)
+      int32_t ni = 0, nj = 0, inters = 0;
+      for (int32_t e = c.geno_ptr[ri]; e < c.geno_ptr[ri + 1]; e++) {
+        if (c.geno_q[e] <= 0) continue;
+        const GenoSlot *s = table_find(tab, c.geno_mut[e]);
+        if (!(s->obs1 > 1 || s->sum1 > c.prm.minQual)) continue;
+        ni++;
+        for (int32_t f = c.geno_ptr[rj]; f < c.geno_ptr[rj + 1]; f++)
+          if (c.geno_mut[f] == c.geno_mut[e]) { if (c.geno_q[f] > 0) inters++; break; }
+      }
+      for (int32_t f = c.geno_ptr[rj]; f < c.geno_ptr[rj + 1]; f++) {
+        if (c.geno_q[f] <= 0) continue;
+        const GenoSlot *s = table_find(tab, c.geno_mut[f]);
+        if (s->obs1 > 1 || s->sum1 > c.prm.minQual) nj++;
+      }
+      int32_t uni = ni + nj - inters;
+      bool ok = uni == 0 || ((double)inters / (double)uni > c.prm.minJaccard && inters >= c.prm.minMatches);
+      if (ok) {
+        bool fresh = c.rd_slot[ri] < 0 && c.rd_slot[rj] < 0;
+        add_link(c, ri, rj, ((int64_t)b << 32) | (int64_t)n_created);
+        if (fresh) n_created++;
+      }
+    }
+  }
+  table_clear(tab);
+}
+
+// accumulate one side of the genotype rule; side 0 -> (obs1,sum1), side 1 -> (obs2,sum2)
+PCB_HD void accumulate_side(const MergeCtx &c, Table &tab, int32_t cl, int32_t single, int side) {
+  int32_t r = cl >= 0 ? c.sl_head[cl] : single;
+  while (r >= 0) {
+    for (int32_t e = c.geno_ptr[r]; e < c.geno_ptr[r + 1]; e++) {
+      GenoSlot *s = table_slot(tab, c.geno_mut[e]);
+      int32_t q = c.geno_q[e];
+      if (side == 0) { if (q > 0) s->obs1++; s->sum1 += q; }
+      else           { if (q > 0) s->obs2++; s->sum2 += q; }
+    }
+    r = cl >= 0 ? c.rd_next[r] : -1;
+  }
+}
+
+// one visit of the main loop body (:419-455) for the ordered read pair (rid1, rid2)
+// returns 1 if the pair was linked
+PCB_HD int visit_pair(const MergeCtx &c, Table &tab, int32_t *runs, int32_t rid1, int32_t rid2, int32_t ed,
+                      int32_t c1, int32_t c2) {
+  int32_t size1 = c1 >= 0 ? c.sl_size[c1] : 1, size2 = c2 >= 0 ? c.sl_size[c2] : 1;
+  int32_t mx = size1 > size2 ? size1 : size2, mn = size1 > size2 ? size2 : size1;
+  if ((int64_t)mx < ((int64_t)mn << ed)) return 0;                         // :435-440
+  // transitive rule (:442-445): bucket runs of cluster 2, then every bucket run of cluster 1 against them
+  int32_t n_runs = 0, last = -1;
+  for (int32_t r = c2 >= 0 ? c.sl_head[c2] : rid2; r >= 0; r = c2 >= 0 ? c.rd_next[r] : -1) {
+    int32_t b = c.bucket_of_read[r];
+    if (b != last) { runs[n_runs++] = b; last = b; }
+  }
+  int32_t maxED = 0; last = -1;
+  for (int32_t r = c1 >= 0 ? c.sl_head[c1] : rid1; r >= 0; r = c1 >= 0 ? c.rd_next[r] : -1) {
+    int32_t a = c.bucket_of_read[r];
+    if (a == last) continue;
+    last = a;
+    for (int32_t k = 0; k < n_runs; k++) {
+      int32_t d = lookup_dist(c, a, runs[k]);
+      if (d < 0) return 0;                                                 // inf
+      if (d > maxED) maxED = d;
+    }
+  }
+  if (maxED > 2 * ed) return 0;
+  // genotype rule (:447-452)
+  accumulate_side(c, tab, c1, rid1, 0);
+  accumulate_side(c, tab, c2, rid2, 1);
+  int32_t inters = 0, uni = 0;
+  for (int32_t i = 0; i < tab.n_touched; i++) {
+    const GenoSlot *s = &tab.slots[tab.touched[i]];
+    if (!(s->obs1 + s->obs2 > 1 || s->sum1 + s->sum2 > c.prm.minQual)) continue;   // filterSeqError
+    bool p1 = s->sum1 > 0, p2 = s->sum2 > 0;
+    if (p1 && p2) inters++;
+    if (p1 || p2) uni++;
+  }
+  table_clear(tab);
+  if (uni == 0 || (double)inters / (double)uni > c.prm.minJaccard) {
+    add_link(c, rid1, rid2, -1);
+    return 1;
+  }
+  return 0;
+}
+
+// consensus of one id column (barcode or uptag) over a member list (:515-532)
+PCB_HD int32_t consensus_id(const MergeCtx &c, Table &tab, const int32_t *ids, int32_t head, int32_t size, int32_t *err) {
+  int32_t best = -1, bestCnt = 0, nTop = 0;
+  for (int32_t r = head; r >= 0; r = c.rd_next[r]) {
+    int32_t id = ids[r];
+    if (id < 0) { *err = 1; id = 0x7fffffff; }
+    table_slot(tab, id)->obs1++;
+  }
+  for (int32_t i = 0; i < tab.n_touched; i++) {
+    const GenoSlot *s = &tab.slots[tab.touched[i]];
+    if (s->obs1 > bestCnt) { bestCnt = s->obs1; best = s->key; nTop = 1; }
+    else if (s->obs1 == bestCnt) nTop++;
+  }
+  table_clear(tab);
+  if (nTop == 1) return best;
+  if (size == 2) return ids[head];
+  return PCB_NEEDS_ALIGNMENT;
+}
+
+PCB_HD void process_component(const MergeCtx &c, int32_t comp) {
+  Table tab;
+  tab.slots = c.slots + c.scr_slot_off[comp];
+  tab.mask = c.scr_slot_cap[comp] - 1;
+  int32_t *lists = c.lists + c.scr_list_off[comp];
+  int64_t list_cap = (c.scr_list_off[comp + 1] - c.scr_list_off[comp]) / 2;
+  tab.touched = lists;                 // first half: touched slots; second half: bucket runs / call sort
+  tab.n_touched = 0;
+  int32_t *runs = lists + list_cap;
+  int32_t b_lo = c.comp_ptr[comp], b_hi = c.comp_ptr[comp + 1];
+
+  // ---- seed clustering, bucket by bucket
+  for (int32_t bi = b_lo; bi < b_hi; bi++) seed_bucket(c, c.comp_buckets[bi], tab);
+
+  // ---- main clustering: the component's rows, pass by pass, in visiting order
+  int32_t n_links = 0, n_tests = 0;
+  int32_t memo_a[4], memo_b[4], memo_n = 0, memo_w = 0;
+  for (int32_t p = c.cpair_ptr[comp]; p < c.cpair_ptr[comp + 1]; p++) {
+    int32_t bq = c.cpair_q[p], br = c.cpair_r[p], ed = c.cpair_ed[p];
+    for (int32_t x = c.bucket_ptr[bq]; x < c.bucket_ptr[bq + 1]; x++) {
+      int32_t rx = c.bucket_reads[x];
+      for (int32_t y = c.bucket_ptr[br]; y < c.bucket_ptr[br + 1]; y++) {
+        int32_t ry = c.bucket_reads[y];
+        int32_t rid1 = rx, rid2 = ry;                                       // makePID order (:152-157)
+        if (!(c.lexrank[rx] < c.lexrank[ry])) { rid1 = ry; rid2 = rx; }
+        int32_t c1 = cluster_of(c, rid1), c2 = cluster_of(c, rid2);
+        if (c1 >= 0 && c1 == c2) continue;                                  // :424
+        int32_t ida = c1 >= 0 ? c1 : ~rid1, idb = c2 >= 0 ? c2 : ~rid2;
+        bool seen = false;
+        for (int32_t k = 0; k < memo_n; k++) if (memo_a[k] == ida && memo_b[k] == idb) { seen = true; break; }
+        if (seen) continue;
+        n_tests++;
+        if (visit_pair(c, tab, runs, rid1, rid2, ed, c1, c2)) { n_links++; memo_n = 0; memo_w = 0; }
+        else { memo_a[memo_w] = ida; memo_b[memo_w] = idb; memo_w = (memo_w + 1) & 3; if (memo_n < 4) memo_n++; }
+      }
+    }
+    memo_n = 0; memo_w = 0;   // ids of a failed pair are only compared within one row
+  }
+
+  // ---- consensus + rows (:464-477, :515-537, :546-567)
+  int64_t call_pos = c.call_off[comp];
+  int32_t err = 0;
+  for (int32_t bi = b_lo; bi < b_hi; bi++) {
+    int32_t b = c.comp_buckets[bi];
+    for (int32_t x = c.bucket_ptr[b]; x < c.bucket_ptr[b + 1]; x++) {
+      int32_t r = c.bucket_reads[x];
+      int32_t cl = cluster_of(c, r);
+      if (cl < 0) {
+        // singleton (:560-567): calls with Q >= minQual in input order
+        c.read_root[r] = r; c.read_pos[r] = 0; c.row_size[r] = 1; c.row_key[r] = -1;
+        c.row_bc[r] = c.bc_id[r]; c.row_up[r] = c.up_id ? c.up_id[r] : c.bc_id[r];
+        c.row_call_off[r] = call_pos;
+        int32_t n = 0;
+        for (int32_t e = c.geno_ptr[r]; e < c.geno_ptr[r + 1]; e++)
+          if (c.geno_q[e] >= c.prm.minQual) { c.call_mut[call_pos + n] = c.geno_mut[e]; n++; }
+        c.row_call_n[r] = n; call_pos += n;
+        continue;
+      }
+      int32_t head = c.sl_head[cl];
+      if (head != r) continue;                     // each cluster is emitted when its head comes by
+      int32_t size = c.sl_size[cl], pos = 0;
+      for (int32_t m = head; m >= 0; m = c.rd_next[m]) {
+        c.read_root[m] = head; c.read_pos[m] = pos++;
+        if (m != head) c.row_size[m] = 0;
+        // genotype vote (:468-470): Q where the read has the key, -minQual where it has not
+        for (int32_t e = c.geno_ptr[m]; e < c.geno_ptr[m + 1]; e++) {
+          GenoSlot *s = table_slot(tab, c.geno_mut[e]);
+          s->obs1++; s->sum1 += c.geno_q[e];
+        }
+      }
+      c.row_size[head] = size; c.row_key[head] = c.sl_key[cl];
+      int32_t n = 0;
+      int32_t *calls = c.call_mut + call_pos;
+      for (int32_t i = 0; i < tab.n_touched; i++) {
+        const GenoSlot *s = &tab.slots[tab.touched[i]];
+        if (s->sum1 - (int64_t)c.prm.minQual * (int64_t)(size - s->obs1) > 0) {
+          int32_t v = s->key, k = n - 1;           // insertion sort by the (digit key, string) rank (:475)
+          while (k >= 0 && c.mut_rank[calls[k]] > c.mut_rank[v]) { calls[k + 1] = calls[k]; k--; }
+          calls[k + 1] = v; n++;
+        }
+      }
+      table_clear(tab);
+      c.row_call_off[head] = call_pos; c.row_call_n[head] = n; call_pos += n;
+      c.row_bc[head] = consensus_id(c, tab, c.bc_id, head, size, &err);
+      int32_t uerr = 0;
+      c.row_up[head] = c.up_id ? consensus_id(c, tab, c.up_id, head, size, &uerr) : c.row_bc[head];
+      if (uerr) { c.status[0] = 3; c.status[1] = head; }     // clustered read without uptag: KeyError in the reference
+    }
+  }
+#if defined(__CUDA_ARCH__)
+  if (n_links) atomicAdd(&c.status[2], n_links);
+  if (n_tests) atomicAdd(&c.status[3], n_tests);
+#else
+  c.status[2] += n_links; c.status[3] += n_tests;
+#endif
+}
+
+}  // namespace pcb

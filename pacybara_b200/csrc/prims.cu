@@ -1,0 +1,181 @@
+// prims.cu -- hand-written device primitives used by every stage: exclusive scan and a
+// stable LSD radix sort.  Both are HBM-bound streaming kernels (bytes per item).
+#include "common.cuh"
+
+namespace pcb {
+
+// ------------------------------------------------------------------------------------ scan
+// Reduce-then-scan over tiles of 2048 items: (1) tile sums, (2) recursive scan of the sums,
+// (3) tile-local scan seeded with the tile offset.  2 reads + 1 write per item.
+constexpr int SCAN_BLOCK = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_BLOCK * SCAN_ITEMS;
+
+template <typename T>
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_tile_sums(const T *__restrict__ in, T *__restrict__ sums, size_t n) {
+  __shared__ T warp_sum[SCAN_BLOCK / 32];
+  size_t base = (size_t)blockIdx.x * SCAN_TILE;
+  T s = 0;
+  for (int i = threadIdx.x; i < SCAN_TILE; i += SCAN_BLOCK) {
+    size_t idx = base + i;
+    if (idx < n) s += in[idx];
+  }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, o);
+  if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    T t = 0;
+    for (int w = 0; w < SCAN_BLOCK / 32; w++) t += warp_sum[w];
+    sums[blockIdx.x] = t;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SCAN_BLOCK) scan_tiles(const T *in, T *out, const T *__restrict__ tile_off, size_t n) {
+  __shared__ T sh[SCAN_TILE];
+  __shared__ T warp_tot[SCAN_BLOCK / 32];
+  size_t base = (size_t)blockIdx.x * SCAN_TILE;
+  for (int i = threadIdx.x; i < SCAN_TILE; i += SCAN_BLOCK) {
+    size_t idx = base + i;
+    sh[i] = idx < n ? in[idx] : (T)0;
+  }
+  __syncthreads();
+  T loc[SCAN_ITEMS];
+  T s = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { loc[k] = sh[threadIdx.x * SCAN_ITEMS + k]; s += loc[k]; }
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  T inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    T t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) warp_tot[warp] = inc;
+  __syncthreads();
+  T run = tile_off[blockIdx.x] + inc - s;
+  for (int w = 0; w < warp; w++) run += warp_tot[w];
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; k++) { sh[threadIdx.x * SCAN_ITEMS + k] = run; run += loc[k]; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < SCAN_TILE; i += SCAN_BLOCK) {
+    size_t idx = base + i;
+    if (idx < n) out[idx] = sh[i];
+  }
+}
+
+template <typename T>
+static void exclusive_scan(pcb_ctx *ctx, const T *in, T *out, size_t n) {
+  if (n == 0) return;
+  size_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  DevBuf<T> sums(ctx, tiles);
+  if (tiles == 1) {
+    PCB_CUDA(cudaMemsetAsync(sums.p, 0, sizeof(T), ctx->stream));
+  } else {
+    PCB_LAUNCH(ctx, scan_tile_sums<T>, (unsigned)tiles, SCAN_BLOCK, 0, in, sums.p, n);
+    exclusive_scan<T>(ctx, sums.p, sums.p, tiles);
+  }
+  PCB_LAUNCH(ctx, scan_tiles<T>, (unsigned)tiles, SCAN_BLOCK, 0, in, out, sums.p, n);
+}
+
+void exclusive_scan_u32(pcb_ctx *ctx, const uint32_t *in, uint32_t *out, size_t n) { exclusive_scan<uint32_t>(ctx, in, out, n); }
+void exclusive_scan_i64(pcb_ctx *ctx, const int64_t *in, int64_t *out, size_t n) { exclusive_scan<int64_t>(ctx, in, out, n); }
+
+// ------------------------------------------------------------------------------------ sort
+// 8 bits per pass.  A block owns a tile of 4096 consecutive items; warp w owns the w-th 512 of
+// them and walks them 32 at a time, so "tile order, then warp order, then row order" is the
+// input order and the sort is stable.  Per pass: histogram kernel -> scan of the
+// [digit][block] table -> scatter kernel that ranks with __match_any_sync.
+constexpr int SORT_BLOCK = 256;
+constexpr int SORT_WARPS = SORT_BLOCK / 32;
+constexpr int SORT_ROWS = 16;
+constexpr int SORT_TILE = SORT_BLOCK * SORT_ROWS;
+
+__device__ __forceinline__ void sort_count_tile(const uint64_t *__restrict__ keys, size_t n, int shift,
+                                                uint32_t (*cnt)[256]) {
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int d = threadIdx.x; d < SORT_WARPS * 256; d += SORT_BLOCK) (&cnt[0][0])[d] = 0;
+  __syncthreads();
+  size_t base = (size_t)blockIdx.x * SORT_TILE + (size_t)warp * (32 * SORT_ROWS);
+#pragma unroll 4
+  for (int r = 0; r < SORT_ROWS; r++) {
+    size_t idx = base + r * 32 + lane;
+    if (idx < n) atomicAdd(&cnt[warp][(keys[idx] >> shift) & 0xFF], 1u);
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(SORT_BLOCK) sort_hist(const uint64_t *__restrict__ keys, size_t n, int shift,
+                                                        uint32_t *__restrict__ ghist, uint32_t nblocks) {
+  __shared__ uint32_t cnt[SORT_WARPS][256];
+  sort_count_tile(keys, n, shift, cnt);
+  uint32_t t = 0;
+  for (int w = 0; w < SORT_WARPS; w++) t += cnt[w][threadIdx.x];
+  ghist[(size_t)threadIdx.x * nblocks + blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(SORT_BLOCK) sort_scatter(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
+                                                           uint64_t *__restrict__ okeys, uint32_t *__restrict__ ovals, size_t n,
+                                                           int shift, const uint32_t *__restrict__ goff, uint32_t nblocks) {
+  __shared__ uint32_t cnt[SORT_WARPS][256];
+  sort_count_tile(keys, n, shift, cnt);
+  {
+    uint32_t run = goff[(size_t)threadIdx.x * nblocks + blockIdx.x];
+    for (int w = 0; w < SORT_WARPS; w++) { uint32_t c = cnt[w][threadIdx.x]; cnt[w][threadIdx.x] = run; run += c; }
+  }
+  __syncthreads();
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  size_t base = (size_t)blockIdx.x * SORT_TILE + (size_t)warp * (32 * SORT_ROWS);
+  for (int r = 0; r < SORT_ROWS; r++) {
+    size_t idx = base + r * 32 + lane;
+    bool valid = idx < n;
+    uint64_t key = valid ? keys[idx] : 0;
+    uint32_t val = valid ? vals[idx] : 0;
+    uint32_t digit = valid ? (uint32_t)((key >> shift) & 0xFF) : 0xFFFFFFFFu;
+    uint32_t peers = __match_any_sync(0xFFFFFFFFu, digit);
+    uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    uint32_t pos = valid ? cnt[warp][digit] + rank : 0;
+    __syncwarp();
+    if (valid && rank == 0) cnt[warp][digit] += __popc(peers);
+    __syncwarp();
+    if (valid) { okeys[pos] = key; ovals[pos] = val; }
+  }
+}
+
+int radix_sort_pairs(pcb_ctx *ctx, uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, size_t n, int bits) {
+  if (n == 0) return 0;
+  uint32_t nblocks = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
+  DevBuf<uint32_t> ghist(ctx, (size_t)256 * nblocks);
+  int cur = 0;
+  for (int shift = 0; shift < bits; shift += 8) {
+    uint64_t *ki = cur ? k1 : k0, *ko = cur ? k0 : k1;
+    uint32_t *vi = cur ? v1 : v0, *vo = cur ? v0 : v1;
+    PCB_LAUNCH(ctx, sort_hist, nblocks, SORT_BLOCK, 0, ki, n, shift, ghist.p, nblocks);
+    exclusive_scan_u32(ctx, ghist.p, ghist.p, (size_t)256 * nblocks);
+    PCB_LAUNCH(ctx, sort_scatter, nblocks, SORT_BLOCK, 0, ki, vi, ko, vo, n, shift, ghist.p, nblocks);
+    cur ^= 1;
+  }
+  return cur;
+}
+
+// ------------------------------------------------------------------------------------ small
+template <typename T>
+__global__ void fill_kernel(T *p, size_t n, T v) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void iota_kernel(uint32_t *p, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (uint32_t)i;
+}
+void fill_i32(pcb_ctx *ctx, int32_t *p, size_t n, int32_t v) {
+  if (n) PCB_LAUNCH(ctx, fill_kernel<int32_t>, grid_for(n, 256), 256, 0, p, n, v);
+}
+void fill_i64(pcb_ctx *ctx, int64_t *p, size_t n, int64_t v) {
+  if (n) PCB_LAUNCH(ctx, fill_kernel<int64_t>, grid_for(n, 256), 256, 0, p, n, v);
+}
+void iota_u32(pcb_ctx *ctx, uint32_t *p, size_t n) {
+  if (n) PCB_LAUNCH(ctx, iota_kernel, grid_for(n, 256), 256, 0, p, n);
+}
+
+}  // namespace pcb

@@ -492,3 +492,41 @@ def load_cluster_job(ed_stream: Iterable[str], geno_stream: Iterable[str], precl
                         mut_rank=geno.mut_rank(), max_diff=max_diff, min_qual=min_qual,
                         min_jaccard=min_jaccard, min_matches=min_matches)
     return ClusterJob(prob, ed_q, ed_r, ed_d, pc.ids, bc_names, up_names, geno.mut_strings)
+
+
+# --------------------------------------------------------------------------- a14: rows from the merge outputs
+
+MERGE_OUTPUTS = (("read_root", np.int32), ("read_pos", np.int32), ("row_size", np.int32), ("row_key", np.int64),
+                 ("row_bc", np.int32), ("row_up", np.int32), ("row_call_off", np.int64), ("row_call_n", np.int32))
+
+
+def rows_from_merge_outputs(out: Dict[str, np.ndarray]) -> ClusterRows:
+    """Per-read / per-representative arrays of pcb_merge -> the table layout of
+    pacybara_cluster.py:546-567: clusters in creation order of the surviving cluster id, then
+    the unclustered reads (the reference emits those in `set` order; read order here)."""
+    row_size = out["row_size"]
+    rep = np.nonzero(row_size > 0)[0]
+    key = out["row_key"][rep]
+    single = key < 0
+    order = np.lexsort((rep, key, single))
+    rep = rep[order]
+    n_rows = rep.shape[0]
+    R = row_size.shape[0]
+    row_of_rep = np.full(R, -1, dtype=np.int64)
+    row_of_rep[rep] = np.arange(n_rows)
+    row_of_read = row_of_rep[out["read_root"]]
+    members = np.lexsort((out["read_pos"], row_of_read)).astype(np.int32)
+    sizes = row_size[rep].astype(np.int64)
+    row_ptr = np.zeros(n_rows + 1, dtype=np.int64)
+    np.cumsum(sizes, out=row_ptr[1:])
+    if int(row_ptr[-1]) != R:
+        raise RuntimeError(f"merge outputs are inconsistent: rows hold {int(row_ptr[-1])} reads, expected {R}")
+    ncall = out["row_call_n"][rep].astype(np.int64)
+    call_ptr = np.zeros(n_rows + 1, dtype=np.int64)
+    np.cumsum(ncall, out=call_ptr[1:])
+    tot = int(call_ptr[-1])
+    src = np.repeat(out["row_call_off"][rep] - call_ptr[:-1], ncall) + np.arange(tot)
+    call_mut = out["call_mut"][src] if tot else np.zeros(0, dtype=np.int32)
+    return ClusterRows(row_ptr.astype(np.int32), members, out["row_bc"][rep].astype(np.int32),
+                       out["row_up"][rep].astype(np.int32), call_ptr.astype(np.int32),
+                       call_mut.astype(np.int32), n_clusters=int((~single).sum()))

@@ -1,0 +1,78 @@
+"""The fused hot path on arrays: what bench.py times and what the drop-in CLIs call.
+
+reads (barcode, quality, genotype) -> buckets -> distance pairs -> clusters, one C-ABI call
+(`pcb_cluster_reads`) on one GPU, or the sharded variant over torch.distributed (multigpu.py).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import hostdata
+from .api import Context
+from .canon import mut_sort_key
+
+
+@dataclass
+class ReadArrays:
+    """Array form of (bcExtract_*.fastq.gz, genoExtract.csv.gz [, uptag fastq]) for R reads."""
+    seq: np.ndarray          # uint8 [R, stride]
+    qual: np.ndarray         # uint8 [R, stride]
+    length: np.ndarray       # int32 [R]
+    lexrank: np.ndarray      # int32 [R]
+    geno_ptr: np.ndarray     # int32 [R+1]
+    geno_mut: np.ndarray     # int32 [nnz]
+    geno_q: np.ndarray       # int32 [nnz]
+    mut_rank: np.ndarray     # int32 [M]
+    up_id: Optional[np.ndarray] = None   # int32 [R]
+
+    @property
+    def n_reads(self) -> int:
+        return int(self.length.shape[0])
+
+
+def mut_rank_of(mut_strings: List[str]) -> np.ndarray:
+    order = sorted(range(len(mut_strings)), key=lambda i: mut_sort_key(mut_strings[i]))
+    rank = np.empty(len(order), dtype=np.int32)
+    rank[np.asarray(order, dtype=np.int64)] = np.arange(len(order), dtype=np.int32)
+    return rank
+
+
+def arrays_from_library(lib, ctx: Optional[Context] = None) -> Tuple[ReadArrays, Dict]:
+    """ReadArrays of a synth.Library plus the string tables the writer needs.  For combo
+    libraries the uptag ids come from bucketing the uptag strings (needs `ctx`)."""
+    ids = lib.read_ids()
+    names = dict(ids=ids, mut_names=lib.mut_strings(), up_names=None)
+    up_id = None
+    if lib.uptag_len is not None:
+        if ctx is None:
+            raise ValueError("a combo library needs a Context to bucket its uptags")
+        useq = lib.uptag_seq()
+        b = ctx.bucket(useq, lib.qual, lib.uptag_len, want_qsum=False)
+        up_id = b["bucket_of_read"].astype(np.int32)
+        names["up_names"] = hostdata.matrix_to_strings(b["bucket_seq"], b["bucket_len"])
+    ra = ReadArrays(seq=lib.seq, qual=lib.qual, length=lib.length.astype(np.int32),
+                    lexrank=hostdata.lexrank_of(ids), geno_ptr=lib.geno_ptr.astype(np.int32),
+                    geno_mut=lib.geno_mut.astype(np.int32), geno_q=lib.geno_q.astype(np.int32),
+                    mut_rank=mut_rank_of(names["mut_names"]), up_id=up_id)
+    return ra, names
+
+
+def cluster_reads(ctx: Context, ra: ReadArrays, max_diff: int = 2, min_qual: int = 32, min_jaccard: float = 0.2,
+                  min_matches: int = 1) -> Dict:
+    return ctx.cluster_reads(ra.seq, ra.qual, ra.length, ra.lexrank, ra.up_id, ra.geno_ptr, ra.geno_mut, ra.geno_q,
+                             ra.mut_rank, max_diff=max_diff, min_qual=min_qual, min_jaccard=min_jaccard,
+                             min_matches=min_matches)
+
+
+def table_from_outputs(out: Dict, ra: ReadArrays, names: Dict):
+    """Rows (virtualBarcode, upBarcode, reads, size, geno) of a fused run on host arrays."""
+    rows = hostdata.rows_from_merge_outputs(out)
+    bor = np.asarray(out["bucket_of_read"])
+    U = int(out["n_buckets"])
+    first = np.full(U, np.iinfo(np.int64).max, dtype=np.int64)
+    np.minimum.at(first, bor, np.arange(bor.shape[0]))
+    bc_names = hostdata.matrix_to_strings(np.asarray(ra.seq)[first], np.asarray(ra.length)[first])
+    return hostdata.rows_to_table(rows, names["ids"], bc_names, names["up_names"], names["mut_names"])

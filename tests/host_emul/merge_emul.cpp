@@ -1,0 +1,121 @@
+// merge_emul.cpp -- UNIT-TEST HARNESS, not a product path.
+// Compiles pacybara_b200/csrc/merge_core.h for the host and runs process_component() over
+// every component sequentially, with the preprocessing (adjacency, components, grouping)
+// done by plain std:: code, so that the sequential replay logic the GPU threads execute can
+// be checked against the oracle in the GPU-less build container.  The shipped library never
+// runs this: it launches the same function as a CUDA kernel (csrc/merge.cu).
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "merge_core.h"
+
+using namespace pcb;
+
+static int32_t uf_find(std::vector<int32_t> &p, int32_t x) {
+  while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; }
+  return x;
+}
+
+extern "C" int emul_merge(int32_t R, int32_t U, const int32_t *bucket_ptr, const int32_t *bucket_reads,
+                          const int32_t *lexrank, const int32_t *bc_id, const int32_t *up_id,
+                          const int32_t *geno_ptr, const int32_t *geno_mut, const int32_t *geno_q,
+                          const int32_t *mut_rank, int64_t n_pairs, const int32_t *pair_q, const int32_t *pair_r,
+                          const int32_t *pair_d, const int32_t *pair_ed, int32_t max_diff, int32_t min_qual,
+                          double min_jaccard, int32_t min_matches, int32_t shard_rank, int32_t shard_count,
+                          int32_t *read_root, int32_t *read_pos, int32_t *row_size, int64_t *row_key,
+                          int32_t *row_bc, int32_t *row_up, int64_t *row_call_off, int32_t *row_call_n,
+                          int32_t *call_mut, int32_t *status) {
+  std::vector<int32_t> bucket_of_read(R);
+  for (int32_t b = 0; b < U; b++)
+    for (int32_t x = bucket_ptr[b]; x < bucket_ptr[b + 1]; x++) bucket_of_read[bucket_reads[x]] = b;
+  // adjacency
+  struct E { int32_t a, b, d; };
+  std::vector<E> adj;
+  for (int64_t p = 0; p < n_pairs; p++) {
+    adj.push_back({pair_q[p], pair_r[p], pair_d[p]});
+    adj.push_back({pair_r[p], pair_q[p], pair_d[p]});
+  }
+  std::sort(adj.begin(), adj.end(), [](const E &x, const E &y) { return x.a != y.a ? x.a < y.a : x.b < y.b; });
+  std::vector<int32_t> adj_ptr(U + 1, 0), adj_nbr(adj.size()), adj_d(adj.size());
+  for (size_t i = 0; i < adj.size(); i++) { adj_ptr[adj[i].a + 1]++; adj_nbr[i] = adj[i].b; adj_d[i] = adj[i].d; }
+  for (int32_t b = 0; b < U; b++) adj_ptr[b + 1] += adj_ptr[b];
+  // components of the link graph
+  std::vector<int32_t> par(U);
+  std::iota(par.begin(), par.end(), 0);
+  for (int64_t p = 0; p < n_pairs; p++)
+    if (pair_ed[p] >= 1) {
+      int32_t a = uf_find(par, pair_q[p]), b = uf_find(par, pair_r[p]);
+      if (a != b) par[std::max(a, b)] = std::min(a, b);
+    }
+  std::vector<int32_t> label(U), comp_of_label(U, -1), comp_buckets(U), comp_ptr;
+  for (int32_t b = 0; b < U; b++) label[b] = uf_find(par, b);
+  std::vector<int32_t> order(U);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return label[x] < label[y]; });
+  int32_t n_comp = 0;
+  for (int32_t i = 0; i < U; i++) {
+    if (i == 0 || label[order[i]] != label[order[i - 1]]) { comp_of_label[label[order[i]]] = n_comp++; comp_ptr.push_back(i); }
+    comp_buckets[i] = order[i];
+  }
+  comp_ptr.push_back(U);
+  std::vector<int32_t> cpair_ptr(n_comp + 1, 0), cq, cr, ce;
+  std::vector<int64_t> pidx;
+  for (int64_t p = 0; p < n_pairs; p++) if (pair_ed[p] >= 1) pidx.push_back(p);
+  std::stable_sort(pidx.begin(), pidx.end(), [&](int64_t x, int64_t y) {
+    return comp_of_label[label[pair_q[x]]] < comp_of_label[label[pair_q[y]]]; });
+  for (int64_t p : pidx) { cpair_ptr[comp_of_label[label[pair_q[p]]] + 1]++; cq.push_back(pair_q[p]); cr.push_back(pair_r[p]); ce.push_back(pair_ed[p]); }
+  for (int32_t c = 0; c < n_comp; c++) cpair_ptr[c + 1] += cpair_ptr[c];
+  // scratch
+  std::vector<int64_t> slot_off(n_comp + 1, 0), list_off(n_comp + 1, 0), call_off(n_comp + 1, 0);
+  std::vector<int32_t> slot_cap(n_comp);
+  for (int32_t c = 0; c < n_comp; c++) {
+    int64_t reads = 0, nnz = 0;
+    for (int32_t i = comp_ptr[c]; i < comp_ptr[c + 1]; i++) {
+      int32_t b = comp_buckets[i];
+      reads += bucket_ptr[b + 1] - bucket_ptr[b];
+      for (int32_t x = bucket_ptr[b]; x < bucket_ptr[b + 1]; x++) nnz += geno_ptr[bucket_reads[x] + 1] - geno_ptr[bucket_reads[x]];
+    }
+    int64_t need = 2 * std::max<int64_t>(std::max(reads, nnz), 1);
+    int32_t cap = 2; while (cap < need) cap <<= 1;
+    slot_cap[c] = cap;
+    slot_off[c + 1] = slot_off[c] + cap;
+    list_off[c + 1] = list_off[c] + 2 * (reads + nnz);
+    call_off[c + 1] = call_off[c] + nnz;
+  }
+  std::vector<GenoSlot> slots(slot_off[n_comp]);
+  for (auto &s : slots) s.key = -1;
+  std::vector<int32_t> lists(list_off[n_comp] + 1);
+  std::vector<int32_t> rd_slot(R, -1), rd_next(R, -1), sl_parent(R, -1), sl_head(R, -1), sl_tail(R, -1), sl_size(R, 0);
+  std::vector<int64_t> sl_key(R, -1);
+  int64_t nnz_tot = geno_ptr[R];
+  for (int32_t r = 0; r < R; r++) {
+    read_root[r] = read_pos[r] = row_size[r] = row_bc[r] = row_up[r] = row_call_n[r] = PCB_FILL;
+    row_key[r] = INT64_MIN; row_call_off[r] = INT64_MIN;
+  }
+  for (int64_t i = 0; i < nnz_tot; i++) call_mut[i] = PCB_FILL;
+  status[0] = status[1] = status[2] = status[3] = 0;
+
+  MergeCtx c;
+  memset(&c, 0, sizeof(c));
+  c.R = R; c.U = U;
+  c.bucket_ptr = bucket_ptr; c.bucket_reads = bucket_reads; c.bucket_of_read = bucket_of_read.data();
+  c.lexrank = lexrank; c.bc_id = bc_id; c.up_id = up_id;
+  c.geno_ptr = geno_ptr; c.geno_mut = geno_mut; c.geno_q = geno_q; c.mut_rank = mut_rank;
+  c.adj_ptr = adj_ptr.data(); c.adj_nbr = adj_nbr.data(); c.adj_d = adj_d.data();
+  c.comp_ptr = comp_ptr.data(); c.comp_buckets = comp_buckets.data();
+  c.cpair_ptr = cpair_ptr.data(); c.cpair_q = cq.data(); c.cpair_r = cr.data(); c.cpair_ed = ce.data();
+  c.scr_slot_off = slot_off.data(); c.scr_slot_cap = slot_cap.data(); c.scr_list_off = list_off.data();
+  c.call_off = call_off.data(); c.slots = slots.data(); c.lists = lists.data();
+  c.rd_slot = rd_slot.data(); c.rd_next = rd_next.data(); c.sl_parent = sl_parent.data();
+  c.sl_head = sl_head.data(); c.sl_tail = sl_tail.data(); c.sl_size = sl_size.data(); c.sl_key = sl_key.data();
+  c.read_root = read_root; c.read_pos = read_pos; c.row_size = row_size; c.row_key = row_key;
+  c.row_bc = row_bc; c.row_up = row_up; c.row_call_off = row_call_off; c.row_call_n = row_call_n;
+  c.call_mut = call_mut; c.status = status;
+  c.prm.maxDiff = max_diff; c.prm.minQual = min_qual; c.prm.minMatches = min_matches; c.prm.minJaccard = min_jaccard;
+  for (int32_t comp = 0; comp < n_comp; comp++)
+    if (comp % shard_count == shard_rank) process_component(c, comp);
+  return n_comp;
+}

@@ -1,0 +1,273 @@
+"""Parity of the CUDA path with the oracle / the reference's golden tables, through the C-ABI.
+
+Bit-exact is the bar everywhere (integer and index work; the one float compare is the same
+IEEE fp64 divide the reference does)."""
+import io
+
+import numpy as np
+import pytest
+
+from pacybara_b200 import canon, hostdata, synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+CASES = [n for n in util.golden_names() if n != "kat10"]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from pacybara_b200.api import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+# ----------------------------------------------------------------------------- a1 bucketing
+@pytest.mark.parametrize("name", util.golden_names())
+def test_bucket_golden(ctx, name):
+    case = util.load_golden(name)
+    reads = hostdata.parse_fastq_for_precluster(io.StringIO(case["fastq"]))
+    res = ctx.bucket(reads.seq, reads.qual, reads.length)
+    assert util.preclust_text(reads, res) == case["preclust"]
+
+
+@pytest.mark.parametrize("cfg,scale", [("cfg1", 1.0), ("cfg3", 0.02), ("cfg2", 1.0)])
+def test_bucket_vs_oracle(ctx, cfg, scale):
+    from oracle import orc
+    lib = synth.make_config(cfg, seed=3, scale=scale)
+    res = ctx.bucket(lib.seq, lib.qual, lib.length)
+    ref = orc.precluster(lib.seq, lib.qual, lib.length)
+    assert res["n_buckets"] == ref["n_buckets"]
+    assert np.array_equal(res["bucket_of_read"], ref["bucket_of_read"])
+    assert np.array_equal(res["first_read"], ref["first_read"])
+    assert np.array_equal(res["bucket_qsum"], ref["qsum"])
+    # arrival order inside every bucket == stable sort of the reads by bucket
+    assert np.array_equal(res["bucket_reads"], np.argsort(ref["bucket_of_read"], kind="stable"))
+    assert np.array_equal(np.diff(res["bucket_ptr"]), np.bincount(ref["bucket_of_read"], minlength=ref["n_buckets"]))
+
+
+def test_bucket_edge_shapes(ctx):
+    # a single read; all reads identical; every read different; 64-nt barcodes
+    one = hostdata.strings_to_matrix([b"ACGT"])
+    r = ctx.bucket(one[0], np.full_like(one[0], 73), one[1])
+    assert r["n_buckets"] == 1 and r["bucket_qsum"][0].tolist() == [40, 40, 40, 40]
+    same = hostdata.strings_to_matrix([b"ACGTACGT"] * 1000)
+    r = ctx.bucket(same[0], np.full_like(same[0], 35), same[1])
+    assert r["n_buckets"] == 1 and int(r["bucket_ptr"][1]) == 1000
+    assert r["bucket_qsum"][0].tolist() == [93] * 8                  # 1000 * 2 capped at 93
+    assert np.array_equal(r["bucket_reads"], np.arange(1000))
+    rng = np.random.default_rng(0)
+    long_ = rng.integers(0, 4, size=(500, 64))
+    mat = synth.BASES[long_].astype(np.uint8)
+    r = ctx.bucket(mat, np.full_like(mat, 40), np.full(500, 64, dtype=np.int32))
+    assert r["n_buckets"] == len({row.tobytes() for row in mat})
+    # same bases, different lengths are different barcodes
+    pre = hostdata.strings_to_matrix([b"AAAA", b"AAA", b"AAAA", b"AAAAA", b"AAA"])
+    r = ctx.bucket(pre[0], np.full_like(pre[0], 50), pre[1])
+    assert r["bucket_of_read"].tolist() == [0, 1, 0, 2, 1]
+
+
+def test_bad_input_is_refused(ctx):
+    from pacybara_b200._lib import PcbError, PCB_E_INPUT
+    bad = hostdata.strings_to_matrix([b"ACGT", b"ACNT"])
+    with pytest.raises(PcbError) as e:
+        ctx.bucket(bad[0], np.full_like(bad[0], 50), bad[1])
+    assert e.value.code == PCB_E_INPUT
+    too_long = hostdata.strings_to_matrix([b"A" * 65])
+    with pytest.raises(PcbError):
+        ctx.edit_pairs(too_long[0], too_long[1], 2)
+
+
+# ----------------------------------------------------------------------------- a2+a3 distances
+def _edges_equal(got, want):
+    for g, w in zip(got, want):
+        assert np.array_equal(np.asarray(g), np.asarray(w))
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 4, 6])
+def test_edit_pairs_vs_exhaustive_dp(ctx, k):
+    """Every pair goes through the full DP in the oracle (no candidate filter)."""
+    from oracle import orc
+    lib = synth.make_library(n_clones=120, n_reads=2500, p_err=0.03, p_near=0.4, seed=21 + k)
+    b = util.oracle_buckets(hostdata.FastqReads([], lib.seq, lib.qual, lib.length))
+    got = ctx.edit_pairs(b["bucket_seq"], b["bucket_len"], k)
+    want = orc.edit_pairs(b["bucket_seq"], b["bucket_len"], k, method="brute")
+    assert len(want[0]) > 0 or k == 0
+    _edges_equal(got, want)
+
+
+@pytest.mark.parametrize("bc_len,combo,k", [(25, False, 4), (25, True, 6), (12, False, 2), (6, False, 4), (3, False, 3)])
+def test_edit_pairs_lengths(ctx, bc_len, combo, k):
+    """One-word and two-word barcodes, and barcodes shorter than k+1 (q = 0: one bin, all pairs)."""
+    from oracle import orc
+    lib = synth.make_library(n_clones=150, n_reads=1500, bc_len=bc_len, combo=combo, p_err=0.03, p_near=0.3, seed=5)
+    b = util.oracle_buckets(hostdata.FastqReads([], lib.seq, lib.qual, lib.length))
+    got = ctx.edit_pairs(b["bucket_seq"], b["bucket_len"], k)
+    want = orc.edit_pairs(b["bucket_seq"], b["bucket_len"], k, method="brute")
+    _edges_equal(got, want)
+
+
+def test_edit_pairs_cfg1_full_and_sharded(ctx):
+    from oracle import orc
+    lib = synth.make_config("cfg1", seed=1)
+    b = util.oracle_buckets(hostdata.FastqReads([], lib.seq, lib.qual, lib.length))
+    U = b["n_buckets"]
+    want = orc.edit_pairs(b["bucket_seq"], b["bucket_len"], 4, method="seeded")
+    got = ctx.edit_pairs(b["bucket_seq"], b["bucket_len"], 4)
+    _edges_equal(got, want)
+    assert ctx.stat("edges") == len(want[0]) and ctx.stat("pairs_scored") >= len(want[0])
+    # query shards: disjoint, union = everything
+    cuts = [0, U // 3, U // 2, U]
+    parts = [ctx.edit_pairs(b["bucket_seq"], b["bucket_len"], 4, q_range=(cuts[i], cuts[i + 1])) for i in range(3)]
+    assert sum(len(p[0]) for p in parts) == len(want[0])
+    ei, ej, ed = (np.concatenate([p[t] for p in parts]) for t in range(3))
+    order = np.lexsort((ej, ei))
+    _edges_equal((ei[order], ej[order], ed[order]), want)
+
+
+# ----------------------------------------------------------------------------- a4..a13 merge
+def _merge_table(ctx, job, shards=1):
+    p = job.problem
+    pairs = hostdata.dedupe_ed_rows(job.ed_q, job.ed_r, job.ed_d, p.n_buckets, p.max_diff)
+    outs = [ctx.merge(p, pairs, (s, shards)) for s in range(shards)]
+    merged = {k: np.maximum.reduce([o[k] for o in outs]) for k in outs[0]}
+    return hostdata.rows_from_merge_outputs(merged)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_merge_golden(ctx, name):
+    case = util.load_golden(name)
+    job = util.job_from_golden(case)
+    rows = _merge_table(ctx, job)
+    if case["exit_code"] != 0:
+        assert (rows.row_bc == hostdata.NEEDS_ALIGNMENT).any() or (rows.row_up == hostdata.NEEDS_ALIGNMENT).any()
+        return
+    got = util.table_of(job, rows)
+    want = util.golden_table(case)
+    assert got == want, canon.diff_tables(got, want)
+
+
+@pytest.mark.parametrize("name", ["rand_dense_d2", "rand_collide", "rand_d3_combo"])
+def test_merge_sharded(ctx, name):
+    case = util.load_golden(name)
+    job = util.job_from_golden(case)
+    got = util.table_of(job, _merge_table(ctx, job, shards=4))
+    assert got == util.golden_table(case)
+
+
+def test_merge_order_matches_oracle(ctx):
+    from oracle import orc
+    case = util.load_golden("rand_lexids")
+    job = util.job_from_golden(case)
+    rows = _merge_table(ctx, job)
+    ref = orc.cluster(job.problem, job.ed_q, job.ed_r, job.ed_d)
+    for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
+        assert np.array_equal(getattr(rows, f), getattr(ref, f)), f
+
+
+def test_missing_uptag_is_an_error(ctx):
+    from pacybara_b200._lib import PcbError, PCB_E_UPTAG
+    case = util.load_golden("kat2b")
+    job = util.job_from_golden(case)
+    job.problem.up_id = job.problem.up_id.copy()
+    job.problem.up_id[:] = -1
+    pairs = hostdata.dedupe_ed_rows(job.ed_q, job.ed_r, job.ed_d, job.problem.n_buckets, 2)
+    with pytest.raises(PcbError) as e:
+        ctx.merge(job.problem, pairs)
+    assert e.value.code == PCB_E_UPTAG
+
+
+# ----------------------------------------------------------------------------- the fused path
+def _fused_vs_oracle(ctx, lib, device=False, **params):
+    from pacybara_b200 import pipeline
+    ra, names = pipeline.arrays_from_library(lib, ctx)
+    p = dict(max_diff=lib.params.get("max_diff", 2), min_qual=lib.params.get("min_qual", 32), min_jaccard=0.2, min_matches=1)
+    p.update(params)
+    if device:
+        import torch
+        dev = {k: (None if v is None else torch.from_numpy(np.ascontiguousarray(v)).cuda())
+               for k, v in vars(ra).items()}
+        out = ctx.cluster_reads(dev["seq"], dev["qual"], dev["length"], dev["lexrank"], dev["up_id"], dev["geno_ptr"],
+                                dev["geno_mut"], dev["geno_q"], dev["mut_rank"], **p)
+        out = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}
+    else:
+        out = pipeline.cluster_reads(ctx, ra, **p)
+    got = canon.canon_table(pipeline.table_from_outputs(out, ra, names))
+    want = canon.canon_table(util.oracle_table_for_library(lib, ra, names, **p))
+    assert len(got) == len(want)
+    assert got == want, canon.diff_tables(got, want)
+    return out
+
+
+@pytest.mark.parametrize("seed", [1, 2])
+def test_fused_cfg1(ctx, seed):
+    out = _fused_vs_oracle(ctx, synth.make_config("cfg1", seed=seed))
+    assert ctx.stat("links") > 0
+
+
+def test_fused_cfg1_device_memory(ctx):
+    _fused_vs_oracle(ctx, synth.make_config("cfg1", seed=4), device=True)
+
+
+def test_fused_cfg1_golden_digest(ctx):
+    """The committed digest of the reference's own cfg-1 table (tests/golden/cfg1_seed1)."""
+    import hashlib
+    from oracle.make_golden import lib_texts
+    from pacybara_b200 import pipeline
+    case = util.load_golden("cfg1_seed1")
+    lib = synth.make_config("cfg1", seed=1)
+    fastq, geno, _ = lib_texts(lib)
+    if hashlib.sha256((fastq + geno).encode()).hexdigest() != case["input_digest"]:
+        pytest.skip("numpy random streams differ from the build container's")
+    ra, names = pipeline.arrays_from_library(lib, ctx)
+    out = pipeline.cluster_reads(ctx, ra, **case["params"])
+    got = canon.canon_table(pipeline.table_from_outputs(out, ra, names))
+    assert 2 * out["n_edges"] == case["n_ed_rows"]
+    assert canon.table_digest(got) == case["digest"]
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n_clones=300, n_reads=4000, p_err=0.03, p_near=0.4, p_collide=0.2, seed=31),
+    dict(n_clones=300, n_reads=4000, combo=True, p_err=0.01, p_near=0.3, seed=32, max_diff=3),
+    dict(n_clones=200, n_reads=5000, p_err=0.02, p_near=0.4, skew=1.5, seed=33, id_style="plain"),
+    dict(n_clones=400, n_reads=3000, p_err=0.02, p_near=0.3, seed=34, max_diff=1),
+])
+def test_fused_random(ctx, kw):
+    kw = dict(kw)
+    md = kw.pop("max_diff", 2)
+    lib = synth.make_library(**kw)
+    try:
+        _fused_vs_oracle(ctx, lib, max_diff=md)
+    except RuntimeError as e:      # a tied >=3-read consensus: both sides must flag it
+        assert "muscle" in str(e)
+
+
+def test_fused_cfg2_scaled_vs_oracle(ctx):
+    _fused_vs_oracle(ctx, synth.make_config("cfg2", seed=1, scale=0.2))
+
+
+def test_fused_cfg2_full_size_properties(ctx):
+    """cfg 2 at full size (1M reads): invariants that need no oracle run."""
+    from pacybara_b200 import pipeline
+    lib = synth.make_config("cfg2", seed=1)
+    ra, names = pipeline.arrays_from_library(lib, ctx)
+    out = pipeline.cluster_reads(ctx, ra)
+    R = lib.n_reads
+    rows = hostdata.rows_from_merge_outputs(out)             # raises unless every read is in exactly one row
+    assert int(rows.row_ptr[-1]) == R
+    assert np.array_equal(np.sort(rows.row_members), np.arange(R))
+    bor = out["bucket_of_read"]
+    # reads of one row are within 2*maxDiff buckets of each other only through edges: same bucket => same component,
+    # and a cluster never mixes reads whose clones have different planted barcodes AND disjoint genotypes
+    sizes = np.diff(rows.row_ptr)
+    assert sizes.max() < 2000 and (sizes >= 1).all()
+    # idempotence of bucketing: bucketing the unique barcodes again gives the identity
+    first = np.full(out["n_buckets"], R, dtype=np.int64)
+    np.minimum.at(first, bor, np.arange(R))
+    again = ctx.bucket(lib.seq[first], lib.qual[first], lib.length[first], want_qsum=False)
+    assert again["n_buckets"] == out["n_buckets"]
+    assert np.array_equal(again["bucket_of_read"], np.arange(out["n_buckets"]))
+    # most clones come back as one dominant cluster
+    top = rows.row_members[rows.row_ptr[:-1]]
+    assert rows.n_clusters > 0.9 * lib.params["n_clones"]

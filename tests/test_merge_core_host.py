@@ -1,0 +1,60 @@
+"""The per-component replay (csrc/merge_core.h), compiled for the host, against the reference's
+golden tables and against the oracle.  This exercises the exact function the GPU threads run,
+without a GPU; the CUDA launch path itself is covered by the -m gpu tests."""
+import numpy as np
+import pytest
+
+from oracle import orc
+from pacybara_b200 import canon, hostdata, synth
+from tests import util
+
+CASES = [n for n in util.golden_names() if n != "kat10"]
+
+
+def _run(job, shard_count=1):
+    p = job.problem
+    pairs = hostdata.dedupe_ed_rows(job.ed_q, job.ed_r, job.ed_d, p.n_buckets, p.max_diff)
+    outs = [util.emul_merge(p, pairs, (s, shard_count)) for s in range(shard_count)]
+    merged = {k: np.maximum.reduce([o[k] for o in outs]) for k, _ in hostdata.MERGE_OUTPUTS}
+    merged["call_mut"] = np.maximum.reduce([o["call_mut"] for o in outs])
+    return hostdata.rows_from_merge_outputs(merged), outs
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_replay_matches_reference(name):
+    case = util.load_golden(name)
+    job = util.job_from_golden(case)
+    rows, _ = _run(job)
+    if case["exit_code"] != 0:
+        assert (rows.row_bc == hostdata.NEEDS_ALIGNMENT).any() or (rows.row_up == hostdata.NEEDS_ALIGNMENT).any()
+        return
+    got = util.table_of(job, rows)
+    want = util.golden_table(case)
+    assert got == want, canon.diff_tables(got, want)
+
+
+@pytest.mark.parametrize("name", ["rand_dense_d2", "rand_collide", "rand_d3_combo"])
+def test_sharded_replay_is_identical(name):
+    """Components dealt to 3 shards and combined with an element-wise max (the multi-GPU merge)."""
+    case = util.load_golden(name)
+    job = util.job_from_golden(case)
+    rows, _ = _run(job, shard_count=3)
+    got = util.table_of(job, rows)
+    assert got == util.golden_table(case)
+
+
+@pytest.mark.parametrize("name", ["rand_dense_d2", "rand_lexids", "rand_private_heavy"])
+def test_row_and_member_order_match_oracle(name):
+    """Beyond the canonical table: cluster rows come out in the reference's creation order and
+    members in its list order (the oracle keeps both)."""
+    case = util.load_golden(name)
+    job = util.job_from_golden(case)
+    rows, _ = _run(job)
+    ref = orc.cluster(job.problem, job.ed_q, job.ed_r, job.ed_d)
+    assert rows.n_clusters == ref.n_clusters
+    assert np.array_equal(rows.row_ptr, ref.row_ptr)
+    assert np.array_equal(rows.row_members, ref.row_members)
+    assert np.array_equal(rows.row_bc, ref.row_bc)
+    assert np.array_equal(rows.row_up, ref.row_up)
+    assert np.array_equal(rows.call_ptr, ref.call_ptr)
+    assert np.array_equal(rows.call_mut, ref.call_mut)

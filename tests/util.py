@@ -66,3 +66,67 @@ def oracle_buckets(reads: hostdata.FastqReads) -> Dict:
     return dict(n_buckets=U, bucket_of_read=r["bucket_of_read"], bucket_ptr=ptr, bucket_reads=order,
                 bucket_seq=reads.seq[r["first_read"]], bucket_len=reads.length[r["first_read"]],
                 bucket_qsum=r["qsum"])
+
+
+# ---------------------------------------------------------------------------------------------
+# host emulation of the per-component replay (tests/host_emul/merge_emul.cpp): unit-test only
+
+_EMUL = None
+
+
+def emul_lib():
+    global _EMUL
+    if _EMUL is None:
+        import ctypes as C
+        import subprocess
+        here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "host_emul")
+        so = os.path.join(here, "libmerge_emul.so")
+        src = os.path.join(here, "merge_emul.cpp")
+        hdr = os.path.join(os.path.dirname(here), "..", "pacybara_b200", "csrc", "merge_core.h")
+        if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr)):
+            cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+            subprocess.run([cxx, "-O1", "-shared", "-fPIC", "-I", os.path.dirname(hdr), "-o", so, src], check=True)
+        _EMUL = C.CDLL(so)
+    return _EMUL
+
+
+def emul_merge(p: hostdata.MergeProblem, pairs: hostdata.PairList, shard=(0, 1)) -> Dict[str, np.ndarray]:
+    import ctypes as C
+    R = p.n_reads
+    nnz = int(p.geno_ptr[-1])
+    out = {k: np.zeros(max(R, 1), dtype=dt) for k, dt in hostdata.MERGE_OUTPUTS}
+    out["call_mut"] = np.zeros(max(nnz, 1), dtype=np.int32)
+    status = np.zeros(4, dtype=np.int32)
+    ptr = lambda a: None if a is None else np.ascontiguousarray(a).ctypes.data_as(C.c_void_p)
+    keep = [np.ascontiguousarray(x, dtype=np.int32) for x in
+            (p.bucket_ptr, p.bucket_reads, p.lexrank, p.bc_id, p.geno_ptr, p.geno_mut, p.geno_q, p.mut_rank,
+             pairs.q, pairs.r, pairs.d, pairs.ed)]
+    up = None if p.up_id is None else np.ascontiguousarray(p.up_id, dtype=np.int32)
+    n = emul_lib().emul_merge(C.c_int32(R), C.c_int32(p.n_buckets), ptr(keep[0]), ptr(keep[1]), ptr(keep[2]),
+                              ptr(keep[3]), ptr(up), ptr(keep[4]), ptr(keep[5]), ptr(keep[6]), ptr(keep[7]),
+                              C.c_int64(len(pairs.q)), ptr(keep[8]), ptr(keep[9]), ptr(keep[10]), ptr(keep[11]),
+                              C.c_int32(p.max_diff), C.c_int32(p.min_qual), C.c_double(p.min_jaccard),
+                              C.c_int32(p.min_matches), C.c_int32(shard[0]), C.c_int32(shard[1]),
+                              *[ptr(out[k]) for k, _ in hostdata.MERGE_OUTPUTS], ptr(out["call_mut"]), ptr(status))
+    out = {k: v[:R] if k != "call_mut" else v[:nnz] for k, v in out.items()}
+    out["status"] = status
+    out["n_components"] = n
+    return out
+
+
+def oracle_table_for_library(lib, ra, names, max_diff=2, min_qual=32, min_jaccard=0.2, min_matches=1):
+    """The whole hot path through the CPU oracle: bucketing, seeded DP distances at k = 2*maxDiff,
+    literal cluster restatement.  Rows as (virtualBarcode, upBarcode, reads, size, geno)."""
+    from oracle import orc
+    reads = hostdata.FastqReads(names["ids"], lib.seq, lib.qual, lib.length)
+    b = oracle_buckets(reads)
+    ei, ej, ed = orc.edit_pairs(b["bucket_seq"], b["bucket_len"], 2 * max_diff, method="seeded")
+    q, r, d = hostdata.canonical_rows(ei, ej, ed)
+    prob = hostdata.MergeProblem(n_reads=lib.n_reads, n_buckets=b["n_buckets"], bucket_ptr=b["bucket_ptr"],
+                                 bucket_reads=b["bucket_reads"], lexrank=ra.lexrank, bc_id=b["bucket_of_read"],
+                                 up_id=ra.up_id, geno_ptr=ra.geno_ptr, geno_mut=ra.geno_mut, geno_q=ra.geno_q,
+                                 mut_rank=ra.mut_rank, max_diff=max_diff, min_qual=min_qual,
+                                 min_jaccard=min_jaccard, min_matches=min_matches)
+    rows = orc.cluster(prob, q, r, d)
+    bc_names = hostdata.matrix_to_strings(b["bucket_seq"], b["bucket_len"])
+    return hostdata.rows_to_table(rows, names["ids"], bc_names, names["up_names"], names["mut_names"])
