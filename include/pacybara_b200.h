@@ -108,6 +108,9 @@ int pcb_bucket(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *qual, c
 int pcb_edit_pairs(pcb_ctx *ctx, int mem, const uint8_t *seq, const int32_t *len, int32_t U, int32_t stride,
                    int32_t k, int32_t q_begin, int32_t q_end, int64_t *n_edges);
 int pcb_edit_pairs_fetch(pcb_ctx *ctx, int mem, int32_t *ei, int32_t *ej, int32_t *ed, int64_t cap);
+/* Sort n edges in place by (ei, ej): puts the concatenation of several shards' edge lists
+ * (after the all-gather) back into the canonical row order the merge visits them in. */
+int pcb_sort_edges(pcb_ctx *ctx, int mem, int32_t *ei, int32_t *ej, int32_t *ed, int64_t n, int32_t U);
 
 /*
  * a4..a13 -- seed clustering, greedy genotype-aware merge and consensus

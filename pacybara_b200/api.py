@@ -77,6 +77,9 @@ class Context:
             for a in arrays:
                 if a is not None and (not a.is_cuda or a.device.index != self.device or not a.is_contiguous()):
                     raise TypeError(f"device arrays must be contiguous tensors on cuda:{self.device}")
+            # the library works on its own stream: whatever torch still has queued for these tensors
+            # must have finished (the library itself returns only after its stream has drained)
+            _torch().cuda.current_stream(self.device).synchronize()
         return _lib.MEM_DEVICE if dev else _lib.MEM_HOST
 
     def _in(self, a, dtype, keep: list):
@@ -143,6 +146,20 @@ class Context:
         ed, p_d = self._out(mem, (max(E, 1),), np.int32)
         self._check(self.lib.pcb_edit_pairs_fetch(self.h, mem, p_i, p_j, p_d, max(E, 1)))
         return ei[:E], ej[:E], ed[:E]
+
+    def sort_edges(self, ei, ej, ed, n_buckets: int):
+        """Sort edge arrays in place by (ei, ej) (pcb_sort_edges)."""
+        if _is_dev(ei):
+            _torch()
+        mem = self._kind(ei, ej, ed)
+        n = int(ei.shape[0])
+        if mem == _lib.MEM_HOST:
+            for a in (ei, ej, ed):
+                if a.dtype != np.int32 or not a.flags.c_contiguous:
+                    raise TypeError("host edge arrays must be contiguous int32 (sorted in place)")
+        keep: list = []
+        self._check(self.lib.pcb_sort_edges(self.h, mem, self._in(ei, np.int32, keep), self._in(ej, np.int32, keep),
+                                            self._in(ed, np.int32, keep), n, int(n_buckets)))
 
     # ------------------------------------------------------------------ a4..a13
     def merge(self, p: MergeProblem, pairs: PairList, shard: Tuple[int, int] = (0, 1)) -> Dict:

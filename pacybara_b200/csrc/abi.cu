@@ -67,6 +67,21 @@ __global__ void pairs_from_edges_kernel(const int32_t *__restrict__ ed, int64_t 
   if (i < n) ped[i] = (ed[i] >= 1 && ed[i] <= max_diff) ? ed[i] : 0;
 }
 
+__global__ void edge_keys_kernel(const int32_t *__restrict__ ei, const int32_t *__restrict__ ej, const int32_t *__restrict__ ed,
+                                 int64_t n, int shift, uint64_t *__restrict__ key, uint32_t *__restrict__ val) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { key[i] = ((uint64_t)(uint32_t)ei[i] << shift) | (uint32_t)ej[i]; val[i] = (uint32_t)ed[i]; }
+}
+__global__ void edge_unpack_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ val, int64_t n, int shift,
+                                   int32_t *__restrict__ ei, int32_t *__restrict__ ej, int32_t *__restrict__ ed) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    ei[i] = (int32_t)(key[i] >> shift);
+    ej[i] = (int32_t)(key[i] & ((1ull << shift) - 1ull));
+    ed[i] = (int32_t)val[i];
+  }
+}
+
 }  // namespace
 
 extern "C" {
@@ -175,6 +190,22 @@ int pcb_edit_pairs_fetch(pcb_ctx *ctx, int mem, int32_t *ei, int32_t *ej, int32_
       PCB_CUDA(cudaMemcpyAsync(ej, ctx->edges.ej, n * sizeof(int32_t), kind, ctx->stream));
       PCB_CUDA(cudaMemcpyAsync(ed, ctx->edges.ed, n * sizeof(int32_t), kind, ctx->stream));
     }
+  });
+}
+
+int pcb_sort_edges(pcb_ctx *ctx, int mem, int32_t *ei, int32_t *ej, int32_t *ed, int64_t n, int32_t U) {
+  return guarded(ctx, [&] {
+    if (n <= 0) return;
+    InArr<int32_t> d_i(ctx, mem, ei, n), d_j(ctx, mem, ej, n), d_d(ctx, mem, ed, n);
+    int shift = bits_for((uint64_t)(U > 1 ? U - 1 : 1));
+    DevBuf<uint64_t> k0(ctx, n), k1(ctx, n);
+    DevBuf<uint32_t> v0(ctx, n), v1(ctx, n);
+    PCB_LAUNCH(ctx, edge_keys_kernel, grid_for(n, 256), 256, 0, d_i.p, d_j.p, d_d.p, n, shift, k0.p, v0.p);
+    int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, n, 2 * shift);
+    OutArr<int32_t> o_i(ctx, mem, ei, n), o_j(ctx, mem, ej, n), o_d(ctx, mem, ed, n);
+    PCB_LAUNCH(ctx, edge_unpack_kernel, grid_for(n, 256), 256, 0, w ? k1.p : k0.p, w ? v1.p : v0.p, n, shift, o_i.p, o_j.p, o_d.p);
+    o_i.commit(n); o_j.commit(n); o_d.commit(n);
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
   });
 }
 

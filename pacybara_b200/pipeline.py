@@ -76,3 +76,23 @@ def table_from_outputs(out: Dict, ra: ReadArrays, names: Dict):
     np.minimum.at(first, bor, np.arange(bor.shape[0]))
     bc_names = hostdata.matrix_to_strings(np.asarray(ra.seq)[first], np.asarray(ra.length)[first])
     return hostdata.rows_to_table(rows, names["ids"], bc_names, names["up_names"], names["mut_names"])
+
+
+def arrays_from_text(fastq_stream, geno_stream, uptag_stream=None, ctx: Optional[Context] = None
+                     ) -> Tuple[ReadArrays, Dict]:
+    """ReadArrays from the text inputs of the path (extracted-barcode FASTQ, genoExtract CSV and
+    optionally the uptag FASTQ), parsed with the reference's own quirks (hostdata)."""
+    reads = hostdata.parse_fastq_for_precluster(fastq_stream)
+    index = {rid: i for i, rid in enumerate(reads.ids)}
+    if len(index) != len(reads.ids):
+        raise hostdata.FormatError("duplicate read id in the barcode FASTQ")
+    geno = hostdata.parse_geno(geno_stream, index, len(reads.ids))
+    up_id, up_names = None, None
+    if uptag_stream is not None:
+        tags = hostdata.parse_uptags(uptag_stream)
+        if len(tags) > 0:
+            up_id, up_names = hostdata.intern_strings([tags.get(rid) for rid in reads.ids])
+    ra = ReadArrays(seq=reads.seq, qual=reads.qual, length=reads.length, lexrank=hostdata.lexrank_of(reads.ids),
+                    geno_ptr=geno.geno_ptr, geno_mut=geno.geno_mut, geno_q=geno.geno_q, mut_rank=geno.mut_rank(),
+                    up_id=up_id)
+    return ra, dict(ids=reads.ids, mut_names=geno.mut_strings, up_names=up_names)
