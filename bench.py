@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=1)
     ap.add_argument("--cpu-sample-reads", type=int, default=100_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--full-table", action="store_true",
+                    help="materialise every pair up to 2*maxDiff (the calcEdits table) instead of on-demand distances")
     return ap.parse_args()
 
 
@@ -191,7 +193,7 @@ def main():
             return multigpu.cluster_reads_sharded(ctx, arrs, params, rank, world, on_device=on_device)
         a = arrs if on_device else {k: v.numpy() for k, v in arrs.items()}
         return ctx.cluster_reads(a["seq"], a["qual"], a["length"], a["lexrank"], a.get("up_id"), a["geno_ptr"],
-                                 a["geno_mut"], a["geno_q"], a["mut_rank"], **params)
+                                 a["geno_mut"], a["geno_q"], a["mut_rank"], full_table=args.full_table, **params)
 
     def timed(arrs, on_device, steps):
         total_ms, probe_ns, out = 0.0, [], None
@@ -252,7 +254,8 @@ def main():
     words = 1 if bc_len + 6 <= 32 else 2
     # algorithmic bytes per launch: 16 B planes + 4 B length per query probe and per scored
     # candidate, 4 B per walked bin entry (>= scored), 12 B per hit
-    per_query = (2 * params["max_diff"] + 1) * (4 * params["max_diff"] + 1)
+    kk = (2 if args.full_table else 1) * params["max_diff"]
+    per_query = (kk + 1) * (2 * kk + 1)
     algo_bytes = U * per_query * 20 + pairs * 24 + E * 12
     roof = dict(bound="hbm", achieved=algo_bytes / probe_s / 1e9, peak=hbm_peak, unit="GB/s",
                 frac=algo_bytes / probe_s / 1e9 / hbm_peak, traffic=None, kernel="probe_kernel<false>",
@@ -281,7 +284,9 @@ def main():
                 ms_per_step=ms_per_step, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="int32",
                 data="synthetic",
                 config=dict(workload=workload, n_reads=R, n_buckets=U, n_distance_pairs=E, barcode_nt=bc_len,
-                            max_diff=params["max_diff"], k=2 * params["max_diff"], seed_len=stats["seed_len"],
+                            max_diff=params["max_diff"], pair_search_k=(2 if args.full_table else 1) * params["max_diff"],
+                            distance_table="full (<= 2*maxDiff)" if args.full_table else "<= maxDiff + on-demand in merge",
+                            seed_len=stats["seed_len"],
                             l2="flushed between steps (512 MiB write)", parallelism=f"query-shard x{world}" if world > 1 else "1 GPU"),
                 e2e=dict(value=R / (e2e_ms / args.steps * 1e-3), unit="reads/s", h2d_bytes_per_step=h2d_bytes,
                          d2h_bytes_per_step=d2h_bytes, ms_per_step=e2e_ms / args.steps),

@@ -152,16 +152,24 @@ int pcb_merge(pcb_ctx *ctx, int mem, int32_t R, int32_t U,
               int32_t *call_mut);
 
 /*
- * The whole hot path on one device: bucketing -> distances (k = 2*max_diff) -> merge, with
- * nothing returning to the host in between.  bc_id is the bucket index.  Inputs as pcb_bucket
- * plus the read-level arrays of pcb_merge; outputs as pcb_bucket (bucket_of_read, n_buckets)
- * and pcb_merge.  n_edges (host int64, may be NULL) receives the number of distance pairs.
+ * The whole hot path on one device: bucketing -> distances -> merge, with nothing returning to
+ * the host in between.  bc_id is the bucket index.  Inputs as pcb_bucket plus the read-level
+ * arrays of pcb_merge; outputs as pcb_bucket (bucket_of_read, n_buckets) and pcb_merge.
+ * n_edges (host int64, may be NULL) receives the number of distance pairs found.
+ *
+ * flags = 0: the pair search runs at k = max_diff (the pairs a pass can visit); the distances up
+ *   to 2*max_diff that the transitive rule (:442) looks up -- always between two buckets of one
+ *   connected component -- are scored on demand inside the merge.  Same clusters, far fewer
+ *   candidates.
+ * flags = PCB_CLUSTER_FULL_TABLE: the pair search runs at k = 2*max_diff, i.e. the table
+ *   pacybara.sh:466-468 asks of calcEdits.R is materialised (fetch it with pcb_edit_pairs_fetch).
  */
+#define PCB_CLUSTER_FULL_TABLE 1
 int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *qual, const int32_t *len,
                       int32_t R, int32_t stride, const int32_t *lexrank, const int32_t *up_id,
                       const int32_t *geno_ptr, const int32_t *geno_mut, const int32_t *geno_q,
                       const int32_t *mut_rank, int32_t n_mut,
-                      int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches,
+                      int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches, int32_t flags,
                       int32_t *bucket_of_read, int32_t *n_buckets, int64_t *n_edges,
                       int32_t *read_root, int32_t *read_pos, int32_t *row_size, int64_t *row_key,
                       int32_t *row_bc, int32_t *row_up, int64_t *row_call_off, int32_t *row_call_n,

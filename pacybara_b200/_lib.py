@@ -12,6 +12,7 @@ PCB_OK, PCB_E_CUDA, PCB_E_INPUT, PCB_E_CAPACITY, PCB_E_STATE, PCB_E_UPTAG = rang
 MEM_HOST, MEM_DEVICE = 0, 1
 FILL = -(1 << 31)
 NEEDS_ALIGNMENT = -2
+CLUSTER_FULL_TABLE = 1
 STAT = dict(pairs_scored=0, cells=1, edges=2, seed_len=3, kernel_launches=4, components=5, links=6, tests=7,
             buckets=8, probe_ns=9)
 
@@ -55,7 +56,7 @@ def load():
         lib.pcb_sort_edges.argtypes = [vp, C.c_int, vp, vp, vp, i64, i32]
         lib.pcb_merge.argtypes = ([vp, C.c_int, i32, i32] + [vp] * 9 + [i32, i64] + [vp] * 4 +
                                   [i32, i32, dbl, i32, i32, i32] + [vp] * 9)
-        lib.pcb_cluster_reads.argtypes = ([vp, C.c_int, vp, vp, vp, i32, i32] + [vp] * 6 + [i32, i32, i32, dbl, i32] +
+        lib.pcb_cluster_reads.argtypes = ([vp, C.c_int, vp, vp, vp, i32, i32] + [vp] * 6 + [i32, i32, i32, dbl, i32, i32] +
                                           [vp, C.POINTER(i32), C.POINTER(i64)] + [vp] * 9)
         _lib = lib
     return _lib

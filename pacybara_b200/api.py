@@ -189,8 +189,11 @@ class Context:
 
     # ------------------------------------------------------------------ the whole path
     def cluster_reads(self, seq, qual, length, lexrank, up_id, geno_ptr, geno_mut, geno_q, mut_rank,
-                      max_diff: int = 2, min_qual: int = 32, min_jaccard: float = 0.2, min_matches: int = 1) -> Dict:
-        """Bucketing -> distances (k = 2*max_diff) -> merge on the device (pcb_cluster_reads)."""
+                      max_diff: int = 2, min_qual: int = 32, min_jaccard: float = 0.2, min_matches: int = 1,
+                      full_table: bool = False) -> Dict:
+        """Bucketing -> distances -> merge on the device (pcb_cluster_reads).  full_table=True
+        materialises every pair up to 2*max_diff (the calcEdits table) instead of scoring the
+        transitive-rule distances on demand; the clusters are the same."""
         arrays = [seq, qual, length, lexrank, up_id, geno_ptr, geno_mut, geno_q, mut_rank]
         if any(_is_dev(a) for a in arrays):
             _torch()
@@ -209,7 +212,8 @@ class Context:
         nb, ne = C.c_int32(0), C.c_int64(0)
         self._check(self.lib.pcb_cluster_reads(self.h, mem, ins[0], ins[1], ins[2], R, stride, *ins[3:],
                                                int(mut_rank.shape[0]), int(max_diff), int(min_qual),
-                                               float(min_jaccard), int(min_matches), p_bor, C.byref(nb), C.byref(ne),
+                                               float(min_jaccard), int(min_matches),
+                                               _lib.CLUSTER_FULL_TABLE if full_table else 0, p_bor, C.byref(nb), C.byref(ne),
                                                *ptrs, p_call))
         out = {k: v[:R] for k, v in outs.items() if k != "call_mut"}
         out["call_mut"] = outs["call_mut"][:nnz]

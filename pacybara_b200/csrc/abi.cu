@@ -243,7 +243,7 @@ int pcb_merge(pcb_ctx *ctx, int mem, int32_t R, int32_t U, const int32_t *bucket
 int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *qual, const int32_t *len, int32_t R,
                       int32_t stride, const int32_t *lexrank, const int32_t *up_id, const int32_t *geno_ptr,
                       const int32_t *geno_mut, const int32_t *geno_q, const int32_t *mut_rank, int32_t n_mut,
-                      int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches,
+                      int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches, int32_t flags,
                       int32_t *bucket_of_read, int32_t *n_buckets, int64_t *n_edges, int32_t *read_root,
                       int32_t *read_pos, int32_t *row_size, int64_t *row_key, int32_t *row_bc, int32_t *row_up,
                       int64_t *row_call_off, int32_t *row_call_n, int32_t *call_mut) {
@@ -271,8 +271,10 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
     BucketOut bo{bor, bptr.p, breads.p, nullptr};
     int32_t U = bucket_reads_dev(ctx, d_seq.p, d_qual.p, d_len.p, R, stride, bo, &uniq);
     if (n_buckets) *n_buckets = U;
-    // a2+a3: distances up to 2*maxDiff (what pacybara.sh:466-468 asks of calcEdits.R)
-    edit_pairs_dev(ctx, uniq, 2 * max_diff, 0, U);
+    // a2+a3: either the full table up to 2*maxDiff (what pacybara.sh:466-468 asks of calcEdits.R), or only
+    // the pairs a pass can visit (<= maxDiff) with the transitive-rule distances scored on demand
+    const bool full = (flags & PCB_CLUSTER_FULL_TABLE) != 0;
+    edit_pairs_dev(ctx, uniq, full ? 2 * max_diff : max_diff, 0, U);
     int64_t E = ctx->edges.n;
     if (n_edges) *n_edges = E;
     DevBuf<int32_t> ped(ctx, (size_t)E);
@@ -280,6 +282,7 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
     // a4..a13: merge; the barcode id of a read is its bucket
     MergeIn in{R, U, n_mut, bptr.p, breads.p, d_lex.p, bor, d_up.p, d_gptr.p, d_gmut.p, d_gq.p, d_rank.p,
                E, ctx->edges.ei, ctx->edges.ej, ctx->edges.ed, ped.p, max_diff, min_qual, min_matches, min_jaccard, 0, 1};
+    if (!full) { in.planes = uniq.planes.p; in.blen = uniq.len.p; in.compute_k = 2 * max_diff; in.wide = uniq.max_len > 32; }
     MergeOut out{o_root.p, o_pos.p, o_size.p, o_key.p, o_bc.p, o_up.p, o_calloff.p, o_calln.p, o_call.p};
     merge_dev(ctx, in, out);
     o_bor.commit(R); o_root.commit(R); o_pos.commit(R); o_size.commit(R); o_bc.commit(R); o_up.commit(R);

@@ -137,6 +137,10 @@ struct MergeIn {             // device pointers
   int32_t max_diff, min_qual, min_matches;
   double min_jaccard;
   int32_t shard_rank, shard_count;
+  // on-demand distances (see merge_core.h); planes == nullptr / compute_k < 0: the pair list is all there is
+  const ulonglong2 *planes = nullptr;
+  const int32_t *blen = nullptr;
+  int32_t compute_k = -1, wide = 0;
 };
 struct MergeOut {            // device pointers, caller-owned
   int32_t *read_root, *read_pos, *row_size;

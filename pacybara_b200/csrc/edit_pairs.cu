@@ -53,56 +53,131 @@ __global__ void seed_fill_kernel(const ulonglong2 *__restrict__ planes, const in
   ent[at] = j;
 }
 
-// One thread per probe (query i, piece t, shift s).  counters: [0] hits emitted, [1] pairs scored,
-// [2] cells (sum len_i * len_j).
+// Device-side Myers for one-word barcodes, tuned for the ALU/FMA pipe split of sm_100a: the text
+// planes are bit-reversed once so that the current column's bits sit in the sign position (one
+// arithmetic shift gives the all-ones/all-zero mask, one add moves to the next column), and the
+// two carries-in are written as adds so that ptxas can place them on the FMA pipe (IMAD.IADD).
+// Same recurrence and same result as pcb::myers32 (myers.cuh), which the host tests pin to the DP.
+__device__ __forceinline__ int myers32_dev(uint32_t pL, uint32_t pH, int m, uint32_t tL, uint32_t tH, int n) {
+  uint32_t Pv = 0xFFFFFFFFu, Mv = 0u;
+  uint32_t rl = __brev(tL), rh = __brev(tH);
+#pragma unroll 5
+  for (int j = 0; j < n; j++) {
+    uint32_t cl = (uint32_t)((int32_t)rl >> 31), ch = (uint32_t)((int32_t)rh >> 31);
+    rl += rl; rh += rh;
+    uint32_t Eq = ~((pL ^ cl) | (pH ^ ch));
+    uint32_t Xv = Eq | Mv;
+    uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+    uint32_t Ph = Mv | ~(Xh | Pv);
+    uint32_t Mh = Pv & Xh;
+    asm("mad.lo.u32 %0, %0, 2, 1;" : "+r"(Ph));   // (Ph << 1) | 1 as one IMAD (FMA pipe)
+    Mh = Mh + Mh;
+    Pv = Mh | ~(Xv | Ph);
+    Mv = Ph & Xv;
+  }
+  uint32_t rows = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
+  return n + __popc(Pv & rows) - __popc(Mv & rows);
+}
+
+// Probe kernel: one warp per block of 32 probes (query i, piece t, shift s), candidates compacted
+// through a per-warp shared-memory queue so that the Myers recurrence always runs on full warps.
+//   filter phase   every lane walks the bin of its own probe (coalesced 4-byte entries), keeps the
+//                  targets j for which i is the query side of {i, j}, and appends (i, j) to the
+//                  warp's queue (ballot + popc prefix);
+//   score phase    whenever 32 pairs are queued, each lane takes one: 16-byte plane loads for both
+//                  barcodes (L2-resident table), length filter, bit-parallel distance, hit emission.
+// Blocks of probes are handed out by an atomic counter (bins differ in size).
+// counters: [0] hits emitted, [1] pairs scored, [2] cells (sum len_i * len_j), [3] next block of probes.
+constexpr int PROBE_WARPS = 8;
+
 template <bool WIDE>
-__global__ void __launch_bounds__(256) probe_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len,
-                                                    int32_t q_begin, int32_t q_end, SeedGeom g,
-                                                    const uint32_t *__restrict__ bin_off, const int32_t *__restrict__ ent,
-                                                    uint64_t *__restrict__ hit_key, uint32_t *__restrict__ hit_d,
-                                                    unsigned long long cap, int key_shift, unsigned long long *counters) {
+__device__ __forceinline__ void score_pair(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int2 pr,
+                                           int k, uint64_t *__restrict__ hit_key, uint32_t *__restrict__ hit_d,
+                                           unsigned long long cap, int key_shift, unsigned long long *counters,
+                                           unsigned long long &scored, unsigned long long &cells) {
+  int32_t i = pr.x, j = pr.y;
+  int32_t m = len[i], n = len[j];
+  int32_t dl = m - n;
+  if (dl > k || -dl > k) return;
+  ulonglong2 a = planes[i], b = planes[j];
+  int d = WIDE ? myers64(a.x, a.y, m, b.x, b.y, n)
+               : myers32_dev((uint32_t)a.x, (uint32_t)a.y, m, (uint32_t)b.x, (uint32_t)b.y, n);
+  scored++; cells += (unsigned long long)(m * n);
+  if (d <= k) {
+    unsigned long long at = atomicAdd(&counters[0], 1ull);
+    if (at < cap) {
+      uint32_t x = i < j ? i : j, y = i < j ? j : i;
+      hit_key[at] = ((uint64_t)x << key_shift) | y;
+      hit_d[at] = (uint32_t)d;
+    }
+  }
+}
+
+template <bool WIDE>
+__global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len,
+                                                                  int32_t q_begin, int32_t q_end, SeedGeom g,
+                                                                  const uint32_t *__restrict__ bin_off, const int32_t *__restrict__ ent,
+                                                                  uint64_t *__restrict__ hit_key, uint32_t *__restrict__ hit_d,
+                                                                  unsigned long long cap, int key_shift, unsigned long long *counters) {
+  __shared__ int2 queue[PROBE_WARPS][64];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lt_mask = (1u << lane) - 1u;
   const int n_shift = g.q == 0 ? 1 : 2 * g.k + 1;
   const int per_query = g.q == 0 ? 1 : (g.k + 1) * n_shift;
-  size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t n_probe = (size_t)(q_end - q_begin) * per_query;
+  const unsigned long long n_probe = (unsigned long long)(q_end - q_begin) * per_query;
+  const unsigned long long n_blocks = (n_probe + 31) / 32;
   unsigned long long scored = 0, cells = 0;
-  if (tid < n_probe) {
-    int32_t i = q_begin + (int32_t)(tid / per_query);
-    int32_t rem = (int32_t)(tid % per_query);
-    int32_t t = rem / n_shift, s = rem % n_shift - (g.q == 0 ? 0 : g.k);
-    int32_t m = len[i];
-    int32_t st = g.q == 0 ? 0 : (int32_t)((int64_t)t * m / (g.k + 1));
-    int32_t p = st + s;
-    if (p >= 0 && p < g.npos) {
-      ulonglong2 a = planes[i];
-      uint32_t bin = seed_bin(g, a.x, a.y, st, p);
-      uint32_t lo = bin_off[bin], hi = bin_off[bin + 1];
-      for (uint32_t e = lo; e < hi; e++) {
-        int32_t j = ent[e];
-        if (j == i || !is_query_side(i, j)) continue;
-        int32_t n = len[j];
-        int32_t dl = m - n;
-        if (dl > g.k || -dl > g.k) continue;
-        ulonglong2 b = planes[j];
-        int d = WIDE ? myers64(a.x, a.y, m, b.x, b.y, n)
-                     : myers32((uint32_t)a.x, (uint32_t)a.y, m, (uint32_t)b.x, (uint32_t)b.y, n);
-        scored++; cells += (unsigned long long)(m * n);
-        if (d <= g.k) {
-          unsigned long long at = atomicAdd(&counters[0], 1ull);
-          if (at < cap) {
-            uint32_t x = i < j ? i : j, y = i < j ? j : i;
-            hit_key[at] = ((uint64_t)x << key_shift) | y;
-            hit_d[at] = (uint32_t)d;
-          }
-        }
+  int cnt = 0;                                   // queued pairs (warp-uniform, < 32 between steps)
+  for (;;) {
+    unsigned long long blk = 0;
+    if (lane == 0) blk = atomicAdd(&counters[3], 1ull);
+    blk = __shfl_sync(0xFFFFFFFFu, blk, 0);
+    if (blk >= n_blocks) break;
+    unsigned long long pid = blk * 32 + lane;
+    uint32_t lo = 0, hi = 0;
+    int32_t qi = -1;
+    if (pid < n_probe) {
+      qi = q_begin + (int32_t)(pid / per_query);
+      int32_t rem = (int32_t)(pid % per_query);
+      int32_t t = rem / n_shift, s = rem % n_shift - (g.q == 0 ? 0 : g.k);
+      int32_t m = len[qi];
+      int32_t st = g.q == 0 ? 0 : (int32_t)((int64_t)t * m / (g.k + 1));
+      int32_t p = st + s;
+      if (p >= 0 && p < g.npos) {
+        ulonglong2 a = planes[qi];
+        uint32_t bin = seed_bin(g, a.x, a.y, st, p);
+        lo = bin_off[bin]; hi = bin_off[bin + 1];
+      }
+    }
+    while (__any_sync(0xFFFFFFFFu, lo < hi)) {
+      bool keep = false;
+      int32_t j = 0;
+      if (lo < hi) {
+        j = ent[lo++];
+        keep = j != qi && is_query_side(qi, j);
+      }
+      uint32_t mask = __ballot_sync(0xFFFFFFFFu, keep);
+      if (keep) queue[warp][cnt + __popc(mask & lt_mask)] = make_int2(qi, j);
+      cnt += __popc(mask);
+      __syncwarp();
+      if (cnt >= 32) {
+        score_pair<WIDE>(planes, len, queue[warp][lane], g.k, hit_key, hit_d, cap, key_shift, counters, scored, cells);
+        int rest = cnt - 32;
+        int2 carry = make_int2(0, 0);
+        if (lane < rest) carry = queue[warp][32 + lane];
+        __syncwarp();
+        if (lane < rest) queue[warp][lane] = carry;
+        cnt = rest;
+        __syncwarp();
       }
     }
   }
+  if (lane < cnt) score_pair<WIDE>(planes, len, queue[warp][lane], g.k, hit_key, hit_d, cap, key_shift, counters, scored, cells);
   for (int o = 16; o > 0; o >>= 1) {
     scored += __shfl_down_sync(0xFFFFFFFFu, scored, o);
     cells += __shfl_down_sync(0xFFFFFFFFu, cells, o);
   }
-  if ((threadIdx.x & 31) == 0 && scored) { atomicAdd(&counters[1], scored); atomicAdd(&counters[2], cells); }
+  if (lane == 0 && scored) { atomicAdd(&counters[1], scored); atomicAdd(&counters[2], cells); }
 }
 
 __global__ void flag_unique_kernel(const uint64_t *__restrict__ key, size_t n, uint32_t *__restrict__ flag) {
@@ -175,11 +250,15 @@ void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q
     hk0.alloc(ctx, cap); hv0.alloc(ctx, cap);
     PCB_CUDA(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
     PCB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    // persistent grid: a multiple of the SM count, blocks of probes handed out by counters[3]
+    unsigned n_cta = (unsigned)ctx->sm_count * 8u;
+    unsigned need = grid_for((n_probe + 31) / 32, PROBE_WARPS);
+    if (need < n_cta) n_cta = need;
     if (wide)
-      PCB_LAUNCH(ctx, probe_kernel<true>, grid_for(n_probe, 256), 256, 0, bc.planes.p, bc.len.p, q_begin, q_end, g,
+      PCB_LAUNCH(ctx, probe_kernel<true>, n_cta, PROBE_WARPS * 32, 0, bc.planes.p, bc.len.p, q_begin, q_end, g,
                  bin_off.p, ent.p, hk0.p, hv0.p, cap, key_shift, counters.p);
     else
-      PCB_LAUNCH(ctx, probe_kernel<false>, grid_for(n_probe, 256), 256, 0, bc.planes.p, bc.len.p, q_begin, q_end, g,
+      PCB_LAUNCH(ctx, probe_kernel<false>, n_cta, PROBE_WARPS * 32, 0, bc.planes.p, bc.len.p, q_begin, q_end, g,
                  bin_off.p, ent.p, hk0.p, hv0.p, cap, key_shift, counters.p);
     PCB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     PCB_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));

@@ -280,6 +280,8 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   c.lexrank = in.lexrank; c.bc_id = in.bc_id; c.up_id = in.up_id;
   c.geno_ptr = in.geno_ptr; c.geno_mut = in.geno_mut; c.geno_q = in.geno_q; c.mut_rank = in.mut_rank;
   c.adj_ptr = adj_ptr.p; c.adj_nbr = adj_nbr.p; c.adj_d = adj_d.p;
+  c.planes = (const uint64_t *)in.planes; c.blen = in.blen;
+  c.compute_k = in.planes ? in.compute_k : -1; c.wide = in.wide;
   c.comp_ptr = comp_ptr.p; c.comp_buckets = comp_buckets.p;
   c.cpair_ptr = cpair_ptr.p; c.cpair_q = cq.p; c.cpair_r = cr.p; c.cpair_ed = ce.p;
   c.scr_slot_off = slot_off.p; c.scr_slot_cap = slot_cap.p; c.scr_list_off = list_off.p; c.call_off = call_off.p;

@@ -26,11 +26,7 @@
 #pragma once
 #include <stdint.h>
 
-#if defined(__CUDACC__)
-#define PCB_HD __host__ __device__ __forceinline__
-#else
-#define PCB_HD inline
-#endif
+#include "myers.cuh"
 
 namespace pcb {
 
@@ -59,6 +55,12 @@ struct MergeCtx {
   // unique bucket pairs: symmetric adjacency sorted by (a, nbr), and the per-component
   // visiting lists (pairs with 1 <= ed <= maxDiff, grouped by component, visiting order kept)
   const int32_t *adj_ptr, *adj_nbr, *adj_d;
+  // optional on-demand distances: when compute_k >= 0 the adjacency is only complete up to
+  // maxDiff and a pair it does not hold is scored on the spot (planes[2b], planes[2b+1] = bit
+  // planes L, H of bucket b); the value is used when <= compute_k, else the pair is "absent"
+  const uint64_t *planes;
+  const int32_t *blen;
+  int32_t compute_k, wide;
   const int32_t *comp_ptr, *comp_buckets;            // component -> buckets (ascending)
   const int32_t *cpair_ptr, *cpair_q, *cpair_r, *cpair_ed;
   // per-component scratch
@@ -166,7 +168,15 @@ PCB_HD int32_t lookup_dist(const MergeCtx &c, int32_t a, int32_t b) {
     int32_t mid = (lo + hi) >> 1;
     if (c.adj_nbr[mid] < b) lo = mid + 1; else hi = mid;
   }
-  return (lo < c.adj_ptr[a + 1] && c.adj_nbr[lo] == b) ? c.adj_d[lo] : -1;
+  if (lo < c.adj_ptr[a + 1] && c.adj_nbr[lo] == b) return c.adj_d[lo];
+  if (c.compute_k < 0) return -1;
+  int32_t m = c.blen[a], n = c.blen[b];
+  int32_t dl = m > n ? m - n : n - m;
+  if (dl > c.compute_k) return -1;
+  int32_t d = c.wide ? myers64(c.planes[2 * a], c.planes[2 * a + 1], m, c.planes[2 * b], c.planes[2 * b + 1], n)
+                     : myers32((uint32_t)c.planes[2 * a], (uint32_t)c.planes[2 * a + 1], m,
+                               (uint32_t)c.planes[2 * b], (uint32_t)c.planes[2 * b + 1], n);
+  return d <= c.compute_k ? d : -1;
 }
 
 // SEED CLUSTERING of one bucket (:385-400)

@@ -27,7 +27,8 @@ extern "C" int emul_merge(int32_t R, int32_t U, const int32_t *bucket_ptr, const
                           double min_jaccard, int32_t min_matches, int32_t shard_rank, int32_t shard_count,
                           int32_t *read_root, int32_t *read_pos, int32_t *row_size, int64_t *row_key,
                           int32_t *row_bc, int32_t *row_up, int64_t *row_call_off, int32_t *row_call_n,
-                          int32_t *call_mut, int32_t *status) {
+                          int32_t *call_mut, int32_t *status,
+                          const uint64_t *planes, const int32_t *blen, int32_t compute_k, int32_t wide) {
   std::vector<int32_t> bucket_of_read(R);
   for (int32_t b = 0; b < U; b++)
     for (int32_t x = bucket_ptr[b]; x < bucket_ptr[b + 1]; x++) bucket_of_read[bucket_reads[x]] = b;
@@ -105,6 +106,7 @@ extern "C" int emul_merge(int32_t R, int32_t U, const int32_t *bucket_ptr, const
   c.lexrank = lexrank; c.bc_id = bc_id; c.up_id = up_id;
   c.geno_ptr = geno_ptr; c.geno_mut = geno_mut; c.geno_q = geno_q; c.mut_rank = mut_rank;
   c.adj_ptr = adj_ptr.data(); c.adj_nbr = adj_nbr.data(); c.adj_d = adj_d.data();
+  c.planes = planes; c.blen = blen; c.compute_k = planes ? compute_k : -1; c.wide = wide;
   c.comp_ptr = comp_ptr.data(); c.comp_buckets = comp_buckets.data();
   c.cpair_ptr = cpair_ptr.data(); c.cpair_q = cq.data(); c.cpair_r = cr.data(); c.cpair_ed = ce.data();
   c.scr_slot_off = slot_off.data(); c.scr_slot_cap = slot_cap.data(); c.scr_list_off = list_off.data();

@@ -179,11 +179,13 @@ def test_missing_uptag_is_an_error(ctx):
 
 
 # ----------------------------------------------------------------------------- the fused path
-def _fused_vs_oracle(ctx, lib, device=False, **params):
+def _fused_vs_oracle(ctx, lib, device=False, full_table=False, **params):
     from pacybara_b200 import pipeline
     ra, names = pipeline.arrays_from_library(lib, ctx)
     p = dict(max_diff=lib.params.get("max_diff", 2), min_qual=lib.params.get("min_qual", 32), min_jaccard=0.2, min_matches=1)
     p.update(params)
+    want = canon.canon_table(util.oracle_table_for_library(lib, ra, names, **p))
+    p["full_table"] = full_table
     if device:
         import torch
         dev = {k: (None if v is None else torch.from_numpy(np.ascontiguousarray(v)).cuda())
@@ -194,15 +196,15 @@ def _fused_vs_oracle(ctx, lib, device=False, **params):
     else:
         out = pipeline.cluster_reads(ctx, ra, **p)
     got = canon.canon_table(pipeline.table_from_outputs(out, ra, names))
-    want = canon.canon_table(util.oracle_table_for_library(lib, ra, names, **p))
     assert len(got) == len(want)
     assert got == want, canon.diff_tables(got, want)
     return out
 
 
-@pytest.mark.parametrize("seed", [1, 2])
-def test_fused_cfg1(ctx, seed):
-    out = _fused_vs_oracle(ctx, synth.make_config("cfg1", seed=seed))
+@pytest.mark.parametrize("seed,full", [(1, False), (2, False), (1, True)])
+def test_fused_cfg1(ctx, seed, full):
+    """full=False: pairs up to maxDiff + on-demand transitive distances; full=True: the whole table."""
+    out = _fused_vs_oracle(ctx, synth.make_config("cfg1", seed=seed), full_table=full)
     assert ctx.stat("links") > 0
 
 
@@ -222,10 +224,13 @@ def test_fused_cfg1_golden_digest(ctx):
         pytest.skip("numpy random streams differ from the build container's")
     # through the text parsers: the reference drops reads whose quality line starts with '@'
     ra, names = pipeline.arrays_from_text(io.StringIO(fastq), io.StringIO(geno), io.StringIO(uptag))
-    out = pipeline.cluster_reads(ctx, ra, **case["params"])
+    out = pipeline.cluster_reads(ctx, ra, full_table=True, **case["params"])
     got = canon.canon_table(pipeline.table_from_outputs(out, ra, names))
     assert 2 * out["n_edges"] == case["n_ed_rows"]
     assert canon.table_digest(got) == case["digest"]
+    out = pipeline.cluster_reads(ctx, ra, **case["params"])          # on-demand distances: same table
+    assert out["n_edges"] < case["n_ed_rows"] // 2
+    assert canon.table_digest(canon.canon_table(pipeline.table_from_outputs(out, ra, names))) == case["digest"]
 
 
 @pytest.mark.parametrize("kw", [
@@ -238,10 +243,11 @@ def test_fused_random(ctx, kw):
     kw = dict(kw)
     md = kw.pop("max_diff", 2)
     lib = synth.make_library(**kw)
-    try:
-        _fused_vs_oracle(ctx, lib, max_diff=md)
-    except RuntimeError as e:      # a tied >=3-read consensus: both sides must flag it
-        assert "muscle" in str(e)
+    for full in (False, True):
+        try:
+            _fused_vs_oracle(ctx, lib, max_diff=md, full_table=full)
+        except RuntimeError as e:      # a tied >=3-read consensus: both sides must flag it
+            assert "muscle" in str(e)
 
 
 def test_fused_cfg2_scaled_vs_oracle(ctx):

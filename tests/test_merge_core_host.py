@@ -58,3 +58,25 @@ def test_row_and_member_order_match_oracle(name):
     assert np.array_equal(rows.row_up, ref.row_up)
     assert np.array_equal(rows.call_ptr, ref.call_ptr)
     assert np.array_equal(rows.call_mut, ref.call_mut)
+
+
+@pytest.mark.parametrize("name", ["rand_dense_d2", "rand_collide", "rand_d3_combo", "rand_d1", "rand_shortbc"])
+def test_on_demand_distances_give_the_same_clusters(name):
+    """The fused path's default: the pair list only holds dist <= maxDiff, the distances in
+    (maxDiff, 2*maxDiff] that the transitive rule needs are scored on demand from the bit planes."""
+    case = util.load_golden(name)
+    job = util.job_from_golden(case)
+    p = job.problem
+    keep = job.ed_d <= p.max_diff
+    pairs = hostdata.dedupe_ed_rows(job.ed_q[keep], job.ed_r[keep], job.ed_d[keep], p.n_buckets, p.max_diff)
+    seqs = [s.encode() for s in job.bc_names]
+    # bucket b's barcode: bc_id of its first read
+    first = p.bucket_reads[p.bucket_ptr[:-1]]
+    mat, lens = hostdata.strings_to_matrix([seqs[i] for i in p.bc_id[first]], 64)
+    out = util.emul_merge(p, pairs, planes=util.pack_planes(mat, lens), blen=lens, compute_k=2 * p.max_diff)
+    got = util.table_of(job, hostdata.rows_from_merge_outputs(out))
+    assert got == util.golden_table(case)
+    # and without them the truncated table is NOT enough (the test would be vacuous otherwise)
+    if name in ("rand_dense_d2", "rand_d3_combo"):
+        out2 = util.emul_merge(p, pairs)
+        assert util.table_of(job, hostdata.rows_from_merge_outputs(out2)) != util.golden_table(case)

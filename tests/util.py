@@ -90,7 +90,20 @@ def emul_lib():
     return _EMUL
 
 
-def emul_merge(p: hostdata.MergeProblem, pairs: hostdata.PairList, shard=(0, 1)) -> Dict[str, np.ndarray]:
+def pack_planes(seq: np.ndarray, length: np.ndarray) -> np.ndarray:
+    """uint64 [U, 2] bit planes (L, H) of ASCII barcodes -- the layout csrc/myers.cuh works on."""
+    code = np.zeros(seq.shape, dtype=np.uint64)
+    for ch, v in ((ord("C"), 1), (ord("G"), 2), (ord("T"), 3)):
+        code[seq == ch] = v
+    cols = np.arange(seq.shape[1], dtype=np.uint64)[None, :]
+    valid = cols < length[:, None].astype(np.uint64)
+    L = np.where(valid, (code & np.uint64(1)) << cols, np.uint64(0)).sum(axis=1, dtype=np.uint64)
+    H = np.where(valid, ((code >> np.uint64(1)) & np.uint64(1)) << cols, np.uint64(0)).sum(axis=1, dtype=np.uint64)
+    return np.ascontiguousarray(np.stack([L, H], axis=1))
+
+
+def emul_merge(p: hostdata.MergeProblem, pairs: hostdata.PairList, shard=(0, 1), planes=None, blen=None,
+               compute_k=-1) -> Dict[str, np.ndarray]:
     import ctypes as C
     R = p.n_reads
     nnz = int(p.geno_ptr[-1])
@@ -107,7 +120,9 @@ def emul_merge(p: hostdata.MergeProblem, pairs: hostdata.PairList, shard=(0, 1))
                               C.c_int64(len(pairs.q)), ptr(keep[8]), ptr(keep[9]), ptr(keep[10]), ptr(keep[11]),
                               C.c_int32(p.max_diff), C.c_int32(p.min_qual), C.c_double(p.min_jaccard),
                               C.c_int32(p.min_matches), C.c_int32(shard[0]), C.c_int32(shard[1]),
-                              *[ptr(out[k]) for k, _ in hostdata.MERGE_OUTPUTS], ptr(out["call_mut"]), ptr(status))
+                              *[ptr(out[k]) for k, _ in hostdata.MERGE_OUTPUTS], ptr(out["call_mut"]), ptr(status),
+                              ptr(planes), ptr(None if blen is None else np.ascontiguousarray(blen, dtype=np.int32)),
+                              C.c_int32(compute_k), C.c_int32(0 if blen is None or int(np.max(blen)) <= 32 else 1))
     out = {k: v[:R] if k != "call_mut" else v[:nnz] for k, v in out.items()}
     out["status"] = status
     out["n_components"] = n
