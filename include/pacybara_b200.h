@@ -127,6 +127,12 @@ int pcb_sort_edges(pcb_ctx *ctx, int mem, int32_t *ei, int32_t *ej, int32_t *ed,
  *                   (q, r) direction of the row that introduced the pair in the pass that visits it,
  *                   d = distance the lookup table ends with (:266), ed = visiting pass 1..maxDiff or 0
  *                   for lookup-only pairs (host helper: hostdata.dedupe_ed_rows / pairs_from_edges)
+ *   bucket_seq [U, stride], bucket_len [U], on_demand_k  optional (NULL / -1 to disable): when given,
+ *                   a distance the transitive rule (:442) looks up and the pair list does not hold is
+ *                   scored on the spot from the barcodes and used if <= on_demand_k.  With the pair
+ *                   list complete up to max_diff and on_demand_k = 2*max_diff this gives exactly the
+ *                   clusters of the full table (lookups never leave a connected component).  The
+ *                   drop-in pacybara_cluster.py never sets it: there the EDFILE is the only authority.
  *   shard_rank / shard_count  components are dealt round-robin; entries of components owned by
  *                   other shards are left at PCB_FILL (combine shards with an element-wise max)
  * outputs (all [R] unless noted; a "row" is a cluster or an unclustered read and is named by
@@ -146,6 +152,7 @@ int pcb_merge(pcb_ctx *ctx, int mem, int32_t R, int32_t U,
               int64_t n_pairs, const int32_t *pair_q, const int32_t *pair_r, const int32_t *pair_d,
               const int32_t *pair_ed,
               int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches,
+              const uint8_t *bucket_seq, const int32_t *bucket_len, int32_t stride, int32_t on_demand_k,
               int32_t shard_rank, int32_t shard_count,
               int32_t *read_root, int32_t *read_pos, int32_t *row_size, int64_t *row_key,
               int32_t *row_bc, int32_t *row_up, int64_t *row_call_off, int32_t *row_call_n,
@@ -155,7 +162,8 @@ int pcb_merge(pcb_ctx *ctx, int mem, int32_t R, int32_t U,
  * The whole hot path on one device: bucketing -> distances -> merge, with nothing returning to
  * the host in between.  bc_id is the bucket index.  Inputs as pcb_bucket plus the read-level
  * arrays of pcb_merge; outputs as pcb_bucket (bucket_of_read, n_buckets) and pcb_merge.
- * n_edges (host int64, may be NULL) receives the number of distance pairs found.
+ * n_edges (host int64, may be NULL) receives the number of distance pairs found.  `qual` is
+ * accepted for symmetry with pcb_bucket and may be NULL: the clustering never reads qualities.
  *
  * flags = 0: the pair search runs at k = max_diff (the pairs a pass can visit); the distances up
  *   to 2*max_diff that the transitive rule (:442) looks up -- always between two buckets of one

@@ -55,7 +55,7 @@ def load():
         lib.pcb_edit_pairs_fetch.argtypes = [vp, C.c_int, vp, vp, vp, i64]
         lib.pcb_sort_edges.argtypes = [vp, C.c_int, vp, vp, vp, i64, i32]
         lib.pcb_merge.argtypes = ([vp, C.c_int, i32, i32] + [vp] * 9 + [i32, i64] + [vp] * 4 +
-                                  [i32, i32, dbl, i32, i32, i32] + [vp] * 9)
+                                  [i32, i32, dbl, i32, vp, vp, i32, i32, i32, i32] + [vp] * 9)
         lib.pcb_cluster_reads.argtypes = ([vp, C.c_int, vp, vp, vp, i32, i32] + [vp] * 6 + [i32, i32, i32, dbl, i32, i32] +
                                           [vp, C.POINTER(i32), C.POINTER(i64)] + [vp] * 9)
         _lib = lib

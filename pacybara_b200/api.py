@@ -31,9 +31,14 @@ def _is_dev(x) -> bool:
 
 
 class Context:
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, pinned_outputs: bool = False):
+        """pinned_outputs: host-memory results are written into page-locked buffers that are REUSED by
+        the next call of the same method (copy what you keep) -- device-to-host copies then run at
+        full PCIe rate instead of being staged through pageable memory."""
         self.lib = _lib.load()
         self.device = int(device)
+        self.pinned_outputs = bool(pinned_outputs)
+        self._pinned: Dict = {}
         h = C.c_void_p()
         rc = self.lib.pcb_ctx_create(self.device, C.byref(h))
         if rc != 0:
@@ -94,11 +99,19 @@ class Context:
         keep.append(a)
         return a.ctypes.data_as(C.c_void_p)
 
-    def _out(self, mem: int, shape, dtype):
+    def _out(self, mem: int, shape, dtype, tag: str = ""):
         if mem == _lib.MEM_DEVICE:
             torch = _torch()
             t = torch.empty(shape, dtype=_NP2TORCH[np.dtype(dtype)], device=f"cuda:{self.device}")
             return t, C.c_void_p(t.data_ptr())
+        if self.pinned_outputs and tag:
+            torch = _torch()
+            key = (tag, tuple(shape), np.dtype(dtype).str)
+            t = self._pinned.get(key)
+            if t is None:
+                t = self._pinned[key] = torch.empty(shape, dtype=_NP2TORCH[np.dtype(dtype)]).pin_memory()
+            a = t.numpy()
+            return a, a.ctypes.data_as(C.c_void_p)
         a = np.empty(shape, dtype=dtype)
         return a, a.ctypes.data_as(C.c_void_p)
 
@@ -162,26 +175,32 @@ class Context:
                                             self._in(ed, np.int32, keep), n, int(n_buckets)))
 
     # ------------------------------------------------------------------ a4..a13
-    def merge(self, p: MergeProblem, pairs: PairList, shard: Tuple[int, int] = (0, 1)) -> Dict:
+    def merge(self, p: MergeProblem, pairs: PairList, shard: Tuple[int, int] = (0, 1), bucket_seq=None,
+              bucket_len=None, on_demand_k: int = -1) -> Dict:
         """Seed clustering + greedy merge + consensus (pcb_merge).  Arrays inside `p` and `pairs`
-        may be numpy or torch CUDA tensors."""
+        may be numpy or torch CUDA tensors.  bucket_seq/bucket_len/on_demand_k: score distances the
+        pair list lacks on demand (see the header); never used for an EDFILE-driven run."""
         arrays = [p.bucket_ptr, p.bucket_reads, p.lexrank, p.bc_id, p.up_id, p.geno_ptr, p.geno_mut, p.geno_q,
                   p.mut_rank, pairs.q, pairs.r, pairs.d, pairs.ed]
+        extra = [bucket_seq, bucket_len]
         if any(_is_dev(a) for a in arrays):
             _torch()
-        mem = self._kind(*arrays)
+        mem = self._kind(*arrays, *extra)
         R = int(p.n_reads)
         nnz = int(p.geno_mut.shape[0])
         keep: list = []
         ins = [self._in(a, np.int32, keep) for a in arrays]
+        p_bseq, p_blen = self._in(bucket_seq, np.uint8, keep), self._in(bucket_len, np.int32, keep)
+        stride = int(bucket_seq.shape[1]) if bucket_seq is not None else 1
         outs, ptrs = {}, []
         for name, dt in MERGE_OUTPUTS:
-            outs[name], ptr = self._out(mem, (max(R, 1),), dt)
+            outs[name], ptr = self._out(mem, (max(R, 1),), dt, "m_" + name)
             ptrs.append(ptr)
-        outs["call_mut"], p_call = self._out(mem, (max(nnz, 1),), np.int32)
+        outs["call_mut"], p_call = self._out(mem, (max(nnz, 1),), np.int32, "m_call_mut")
         self._check(self.lib.pcb_merge(self.h, mem, R, int(p.n_buckets), *ins[:9], int(p.mut_rank.shape[0]),
                                        int(pairs.q.shape[0]), *ins[9:], int(p.max_diff), int(p.min_qual),
-                                       float(p.min_jaccard), int(p.min_matches), int(shard[0]), int(shard[1]),
+                                       float(p.min_jaccard), int(p.min_matches), p_bseq, p_blen, stride,
+                                       int(on_demand_k) if bucket_seq is not None else -1, int(shard[0]), int(shard[1]),
                                        *ptrs, p_call))
         out = {k: v[:R] for k, v in outs.items() if k != "call_mut"}
         out["call_mut"] = outs["call_mut"][:nnz]
@@ -203,12 +222,12 @@ class Context:
         keep: list = []
         dts = [np.uint8, np.uint8] + [np.int32] * 7
         ins = [self._in(a, dt, keep) for a, dt in zip(arrays, dts)]
-        bor, p_bor = self._out(mem, (max(R, 1),), np.int32)
+        bor, p_bor = self._out(mem, (max(R, 1),), np.int32, "c_bor")
         outs, ptrs = {}, []
         for name, dt in MERGE_OUTPUTS:
-            outs[name], ptr = self._out(mem, (max(R, 1),), dt)
+            outs[name], ptr = self._out(mem, (max(R, 1),), dt, "c_" + name)
             ptrs.append(ptr)
-        outs["call_mut"], p_call = self._out(mem, (max(nnz, 1),), np.int32)
+        outs["call_mut"], p_call = self._out(mem, (max(nnz, 1),), np.int32, "c_call_mut")
         nb, ne = C.c_int32(0), C.c_int64(0)
         self._check(self.lib.pcb_cluster_reads(self.h, mem, ins[0], ins[1], ins[2], R, stride, *ins[3:],
                                                int(mut_rank.shape[0]), int(max_diff), int(min_qual),

@@ -213,8 +213,9 @@ int pcb_merge(pcb_ctx *ctx, int mem, int32_t R, int32_t U, const int32_t *bucket
               const int32_t *lexrank, const int32_t *bc_id, const int32_t *up_id, const int32_t *geno_ptr,
               const int32_t *geno_mut, const int32_t *geno_q, const int32_t *mut_rank, int32_t n_mut, int64_t n_pairs,
               const int32_t *pair_q, const int32_t *pair_r, const int32_t *pair_d, const int32_t *pair_ed,
-              int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches, int32_t shard_rank,
-              int32_t shard_count, int32_t *read_root, int32_t *read_pos, int32_t *row_size, int64_t *row_key,
+              int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches,
+              const uint8_t *bucket_seq, const int32_t *bucket_len, int32_t stride, int32_t on_demand_k,
+              int32_t shard_rank, int32_t shard_count, int32_t *read_root, int32_t *read_pos, int32_t *row_size, int64_t *row_key,
               int32_t *row_bc, int32_t *row_up, int64_t *row_call_off, int32_t *row_call_n, int32_t *call_mut) {
   return guarded(ctx, [&] {
     if (R < 0 || U < 0 || n_pairs < 0) throw Error(PCB_E_INPUT, "bad shape");
@@ -233,6 +234,13 @@ int pcb_merge(pcb_ctx *ctx, int mem, int32_t R, int32_t U, const int32_t *bucket
     MergeIn in{R, U, n_mut, d_bptr.p, d_breads.p, d_lex.p, d_bc.p, d_up.p, d_gptr.p, d_gmut.p, d_gq.p, d_rank.p,
                n_pairs, d_pq.p, d_pr.p, d_pd.p, d_pe.p, max_diff, min_qual, min_matches, min_jaccard, shard_rank, shard_count};
     MergeOut out{o_root.p, o_pos.p, o_size.p, o_key.p, o_bc.p, o_up.p, o_calloff.p, o_calln.p, o_call.p};
+    PackedBarcodes bc;
+    if (bucket_seq && bucket_len && on_demand_k >= 0 && U > 0) {
+      InArr<uint8_t> d_bseq(ctx, mem, bucket_seq, (size_t)U * stride);
+      InArr<int32_t> d_blen(ctx, mem, bucket_len, U);
+      pack_barcodes(ctx, d_bseq.p, d_blen.p, nullptr, U, stride, bc);
+      in.planes = bc.planes.p; in.blen = bc.len.p; in.compute_k = on_demand_k; in.wide = bc.max_len > 32;
+    }
     merge_dev(ctx, in, out);
     o_root.commit(R); o_pos.commit(R); o_size.commit(R); o_bc.commit(R); o_up.commit(R); o_calln.commit(R);
     o_call.commit(nnz); o_key.commit(R); o_calloff.commit(R);
@@ -255,7 +263,8 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
       if (mem == PCB_MEM_DEVICE) nnz = read_scalar(ctx, geno_ptr + R); else nnz = geno_ptr[R];
     }
     size_t cells = (size_t)R * stride;
-    InArr<uint8_t> d_seq(ctx, mem, seq, cells), d_qual(ctx, mem, qual, cells);
+    (void)qual;   // qualities only feed the per-bucket sums of pcb_bucket; the clustering never reads them
+    InArr<uint8_t> d_seq(ctx, mem, seq, cells);
     InArr<int32_t> d_len(ctx, mem, len, R), d_lex(ctx, mem, lexrank, R), d_up(ctx, mem, up_id, R),
         d_gptr(ctx, mem, geno_ptr, (size_t)R + 1), d_gmut(ctx, mem, geno_mut, nnz), d_gq(ctx, mem, geno_q, nnz),
         d_rank(ctx, mem, mut_rank, n_mut);
@@ -269,7 +278,7 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
     // a1: buckets
     PackedBarcodes uniq;
     BucketOut bo{bor, bptr.p, breads.p, nullptr};
-    int32_t U = bucket_reads_dev(ctx, d_seq.p, d_qual.p, d_len.p, R, stride, bo, &uniq);
+    int32_t U = bucket_reads_dev(ctx, d_seq.p, nullptr, d_len.p, R, stride, bo, &uniq);
     if (n_buckets) *n_buckets = U;
     // a2+a3: either the full table up to 2*maxDiff (what pacybara.sh:466-468 asks of calcEdits.R), or only
     // the pairs a pass can visit (<= maxDiff) with the transitive-rule distances scored on demand

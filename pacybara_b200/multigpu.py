@@ -48,21 +48,23 @@ def gather_edges(ei, ej, ed, world: int):
     return cat[0].contiguous(), cat[1].contiguous(), cat[2].contiguous()
 
 
-def cluster_reads_sharded(ctx: Context, arrs: Dict, params: Dict, rank: int, world: int, on_device: bool = True) -> Dict:
+def cluster_reads_sharded(ctx: Context, arrs: Dict, params: Dict, rank: int, world: int, on_device: bool = True,
+                          full_table: bool = False) -> Dict:
     """`arrs`: dict of torch tensors (seq, qual, length, lexrank, geno_ptr, geno_mut, geno_q, mut_rank[, up_id]),
     CUDA tensors when on_device else pinned host tensors (copied in here; results copied back)."""
     import torch
     import torch.distributed as dist
     dev = f"cuda:{ctx.device}"
-    a = arrs if on_device else {k: v.to(dev, non_blocking=True) for k, v in arrs.items()}
+    a = arrs if on_device else {k: v.to(dev, non_blocking=True) for k, v in arrs.items() if k != "qual"}
     max_diff = int(params["max_diff"])
     R = int(a["length"].shape[0])
     # 1. buckets (replicated)
-    b = ctx.bucket(a["seq"], a["qual"], a["length"], want_qsum=False)
+    b = ctx.bucket(a["seq"], None, a["length"], want_qsum=False)      # qualities are not needed for clustering
     U = b["n_buckets"]
     # 2. my slice of the query buckets
     lo, hi = shard_range(U, rank, world)
-    ei, ej, ed = ctx.edit_pairs(b["bucket_seq"].contiguous(), b["bucket_len"].contiguous(), 2 * max_diff, q_range=(lo, hi))
+    bseq, blen = b["bucket_seq"].contiguous(), b["bucket_len"].contiguous()
+    ei, ej, ed = ctx.edit_pairs(bseq, blen, (2 if full_table else 1) * max_diff, q_range=(lo, hi))
     local_stats = dict(pairs_scored=ctx.stat("pairs_scored"), cells=ctx.stat("cells"), probe_ns=ctx.stat("probe_ns"))
     # 3. exchange edges
     ei, ej, ed = gather_edges(ei, ej, ed, world)
@@ -74,7 +76,11 @@ def cluster_reads_sharded(ctx: Context, arrs: Dict, params: Dict, rank: int, wor
                         geno_mut=a["geno_mut"], geno_q=a["geno_q"], mut_rank=a["mut_rank"], max_diff=max_diff,
                         min_qual=int(params["min_qual"]), min_jaccard=float(params["min_jaccard"]),
                         min_matches=int(params["min_matches"]))
-    out = ctx.merge(prob, PairList(ei, ej, ed, ped), shard=(rank, world))
+    if full_table:
+        out = ctx.merge(prob, PairList(ei, ej, ed, ped), shard=(rank, world))
+    else:
+        out = ctx.merge(prob, PairList(ei, ej, ed, ped), shard=(rank, world), bucket_seq=bseq, bucket_len=blen,
+                        on_demand_k=2 * max_diff)
     # 5. combine
     for name in list(out.keys()):
         dist.all_reduce(out[name], op=dist.ReduceOp.MAX)

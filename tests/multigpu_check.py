@@ -30,9 +30,10 @@ def main():
     ra, names = pipeline.arrays_from_library(lib, ctx)
     params = dict(max_diff=lib.params["max_diff"], min_qual=lib.params["min_qual"], min_jaccard=0.2, min_matches=1)
     dev = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in vars(ra).items() if v is not None}
-    out = multigpu.cluster_reads_sharded(ctx, dev, params, rank, world, on_device=True)
+    full = os.environ.get("PCB_FULL_TABLE", "0") == "1"
+    out = multigpu.cluster_reads_sharded(ctx, dev, params, rank, world, on_device=True, full_table=full)
     single = ctx.cluster_reads(dev["seq"], dev["qual"], dev["length"], dev["lexrank"], dev.get("up_id"), dev["geno_ptr"],
-                               dev["geno_mut"], dev["geno_q"], dev["mut_rank"], full_table=True, **params)
+                               dev["geno_mut"], dev["geno_q"], dev["mut_rank"], full_table=full, **params)
     bad = [k for k in ("read_root", "read_pos", "row_size", "row_key", "row_bc", "row_up", "row_call_n", "bucket_of_read")
            if not torch.equal(out[k], single[k])]
     # call_mut offsets are component-relative in both runs, so the arrays must agree too
