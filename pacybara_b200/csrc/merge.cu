@@ -2,14 +2,23 @@
 // bucket-pair list into per-component work, then one thread per connected component replaying
 // the reference's sequential algorithm (merge_core.h).
 //
-//   adjacency     symmetric (a, nbr, d) sorted by (a, nbr): the lookup table of :236,:266
 //   components    lock-free union-find over the pairs a pass visits (1 <= ed <= maxDiff);
 //                 label = smallest bucket of the component
-//   grouping      buckets and visiting pairs gathered per component with the stable radix sort,
+//   renumbering   buckets are sorted by (component work descending, component label), reads by
+//                 (new bucket, arrival order), and every per-read / per-bucket array the replay touches
+//                 is gathered into that order: a component's working set becomes a handful of
+//                 contiguous cache lines instead of one sector per read scattered over HBM, and
+//                 neighbouring threads (= neighbouring components of similar size) follow similar
+//                 control flow.  The renumbering is an identity relabelling: nothing in the algorithm
+//                 depends on the numeric value of a read or bucket id (string order of read ids comes
+//                 in through `lexrank`, creation keys are mapped back to the old bucket numbers).
+//   adjacency     symmetric (a, nbr, d) sorted by (a, nbr) in the new numbering: the lookup table of :236,:266
+//   visiting      pairs a pass visits, grouped per component by a STABLE sort on (component, ed),
 //                 which keeps the reference's visiting order inside every component
 //   replay        process_component(): seed step, greedy merge, consensus
+//   scatter       outputs back to the caller's read numbering
 // Everything except the replay is HBM-bound streaming; the replay is latency-bound pointer work
-// whose parallelism is the number of components (hundreds of thousands at cfg 2).
+// whose parallelism is the number of components (about 10^5 at cfg 2).
 #include <cstring>
 
 #include "common.cuh"
@@ -17,38 +26,7 @@
 
 namespace pcb {
 
-__global__ void bucket_of_read_kernel(const int32_t *__restrict__ bucket_ptr, const int32_t *__restrict__ bucket_reads,
-                                      int32_t R, int32_t U, int32_t *__restrict__ bucket_of_read) {
-  int32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= R) return;
-  int32_t lo = 0, hi = U;                       // last b with bucket_ptr[b] <= x
-  while (hi - lo > 1) {
-    int32_t mid = (lo + hi) >> 1;
-    if (bucket_ptr[mid] <= x) lo = mid; else hi = mid;
-  }
-  bucket_of_read[bucket_reads[x]] = lo;
-}
-
-__global__ void adj_keys_kernel(const int32_t *__restrict__ pq, const int32_t *__restrict__ pr, const int32_t *__restrict__ pd,
-                                int64_t n_pairs, int shift, uint64_t *__restrict__ key, uint32_t *__restrict__ val,
-                                uint32_t *__restrict__ adj_cnt) {
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pairs) return;
-  uint32_t a = (uint32_t)pq[p], b = (uint32_t)pr[p];
-  key[2 * p] = ((uint64_t)a << shift) | b;
-  key[2 * p + 1] = ((uint64_t)b << shift) | a;
-  val[2 * p] = val[2 * p + 1] = (uint32_t)pd[p];
-  atomicAdd(&adj_cnt[a], 1u);
-  atomicAdd(&adj_cnt[b], 1u);
-}
-
-__global__ void adj_unpack_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ val, int64_t n, int shift,
-                                  int32_t *__restrict__ nbr, int32_t *__restrict__ d) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  nbr[i] = (int32_t)(key[i] & ((1ull << shift) - 1ull));
-  d[i] = (int32_t)val[i];
-}
+constexpr uint32_t WORK_CAP = 1023;     // component work classes used for ordering (10 bits)
 
 __device__ __forceinline__ int32_t uf_find(int32_t *parent, int32_t x) {
   for (;;) {
@@ -66,9 +44,9 @@ __global__ void uf_init_kernel(int32_t *parent, int32_t U) {
 }
 
 __global__ void uf_union_kernel(const int32_t *__restrict__ pq, const int32_t *__restrict__ pr, const int32_t *__restrict__ ped,
-                                int64_t n_pairs, int32_t *parent) {
+                                int64_t n_pairs, int32_t max_diff, int32_t *parent) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pairs || ped[p] < 1) return;
+  if (p >= n_pairs || ped[p] < 1 || ped[p] > max_diff) return;
   int32_t a = pq[p], b = pr[p];
   for (;;) {
     a = uf_find(parent, a);
@@ -79,10 +57,23 @@ __global__ void uf_union_kernel(const int32_t *__restrict__ pq, const int32_t *_
   }
 }
 
-__global__ void uf_label_kernel(int32_t *parent, int32_t U, uint64_t *__restrict__ key, uint32_t *__restrict__ val) {
+// label[b] = root; work[root] += reads of b
+__global__ void uf_label_kernel(int32_t *parent, const int32_t *__restrict__ bucket_ptr, int32_t U,
+                                int32_t *__restrict__ label, uint32_t *__restrict__ work) {
   int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= U) return;
-  key[b] = (uint64_t)(uint32_t)uf_find(parent, b);
+  int32_t l = uf_find(parent, b);
+  label[b] = l;
+  atomicAdd(&work[l], (uint32_t)(bucket_ptr[b + 1] - bucket_ptr[b]));
+}
+
+__global__ void comp_keys_kernel(const int32_t *__restrict__ label, const uint32_t *__restrict__ work, int32_t U, int bbits,
+                                 uint64_t *__restrict__ key, uint32_t *__restrict__ val) {
+  int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= U) return;
+  uint32_t l = (uint32_t)label[b];
+  uint32_t w = work[l] < WORK_CAP ? work[l] : WORK_CAP;
+  key[b] = ((uint64_t)(WORK_CAP - w) << bbits) | l;          // heavy components first
   val[b] = (uint32_t)b;
 }
 
@@ -91,29 +82,100 @@ __global__ void comp_flag_kernel(const uint64_t *__restrict__ key, int32_t U, ui
   if (i < U) flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1u : 0u;
 }
 
-// rank = exclusive scan of the flags: component index of sorted position i is rank[i] + flag - 1
+// sorted position i = new bucket id.  rank = exclusive scan of the head flags.
 __global__ void comp_assign_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ val, const uint32_t *__restrict__ rank,
-                                   int32_t U, int32_t n_comp, int32_t *__restrict__ comp_buckets, int32_t *__restrict__ comp_ptr,
-                                   int32_t *__restrict__ comp_of_bucket) {
+                                   const int32_t *__restrict__ bucket_ptr, int32_t U, int32_t n_comp,
+                                   int32_t *__restrict__ old_of_new_b, int32_t *__restrict__ new_of_old_b,
+                                   int32_t *__restrict__ comp_ptr, int32_t *__restrict__ comp_of_new_b, uint32_t *__restrict__ nb_cnt) {
   int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= U) return;
   bool head = i == 0 || key[i] != key[i - 1];
   int32_t c = (int32_t)rank[i] + (head ? 1 : 0) - 1;
   int32_t b = (int32_t)val[i];
-  comp_buckets[i] = b;
-  comp_of_bucket[b] = c;
+  old_of_new_b[i] = b;
+  new_of_old_b[b] = i;
+  comp_of_new_b[i] = c;
+  nb_cnt[i] = (uint32_t)(bucket_ptr[b + 1] - bucket_ptr[b]);
   if (head) comp_ptr[c] = i;
-  if (i == U - 1) comp_ptr[n_comp] = U;
+  if (i == U - 1) { comp_ptr[n_comp] = U; nb_cnt[U] = 0; }
+}
+
+// one thread per position x of the caller's bucket_reads: where does that read go?
+__global__ void read_renumber_kernel(const int32_t *__restrict__ bucket_ptr, const int32_t *__restrict__ bucket_reads, int32_t R, int32_t U,
+                                     const int32_t *__restrict__ new_of_old_b, const uint32_t *__restrict__ nb_ptr,
+                                     const int32_t *__restrict__ lexrank, const int32_t *__restrict__ bc_id, const int32_t *__restrict__ up_id,
+                                     const int32_t *__restrict__ geno_ptr,
+                                     int32_t *__restrict__ old_of_new_r, int32_t *__restrict__ n_bor, int32_t *__restrict__ n_lex,
+                                     int32_t *__restrict__ n_bc, int32_t *__restrict__ n_up, uint32_t *__restrict__ n_gcnt) {
+  int32_t x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x >= R) return;
+  int32_t lo = 0, hi = U;                       // last b with bucket_ptr[b] <= x
+  while (hi - lo > 1) {
+    int32_t mid = (lo + hi) >> 1;
+    if (bucket_ptr[mid] <= x) lo = mid; else hi = mid;
+  }
+  int32_t nb = new_of_old_b[lo];
+  int32_t nr = (int32_t)nb_ptr[nb] + (x - bucket_ptr[lo]);
+  int32_t r = bucket_reads[x];
+  old_of_new_r[nr] = r;
+  n_bor[nr] = nb;
+  n_lex[nr] = lexrank[r];
+  n_bc[nr] = bc_id[r];
+  if (up_id) n_up[nr] = up_id[r];
+  n_gcnt[nr] = (uint32_t)(geno_ptr[r + 1] - geno_ptr[r]);
+  if (x == R - 1) n_gcnt[R] = 0;
+}
+
+__global__ void geno_gather_kernel(const int32_t *__restrict__ old_of_new_r, const int32_t *__restrict__ geno_ptr,
+                                   const int32_t *__restrict__ geno_mut, const int32_t *__restrict__ geno_q, int32_t R,
+                                   const uint32_t *__restrict__ n_gptr, int32_t *__restrict__ n_gmut, int32_t *__restrict__ n_gq) {
+  int32_t nr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nr >= R) return;
+  int32_t r = old_of_new_r[nr];
+  int32_t src = geno_ptr[r], n = geno_ptr[r + 1] - src;
+  uint32_t dst = n_gptr[nr];
+  for (int32_t e = 0; e < n; e++) { n_gmut[dst + e] = geno_mut[src + e]; n_gq[dst + e] = geno_q[src + e]; }
+}
+
+__global__ void planes_gather_kernel(const int32_t *__restrict__ old_of_new_b, const ulonglong2 *__restrict__ planes,
+                                     const int32_t *__restrict__ blen, int32_t U, ulonglong2 *__restrict__ n_planes,
+                                     int32_t *__restrict__ n_blen) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= U) return;
+  n_planes[i] = planes[old_of_new_b[i]];
+  n_blen[i] = blen[old_of_new_b[i]];
+}
+
+__global__ void adj_keys_kernel(const int32_t *__restrict__ pq, const int32_t *__restrict__ pr, const int32_t *__restrict__ pd,
+                                int64_t n_pairs, const int32_t *__restrict__ new_of_old_b, int shift,
+                                uint64_t *__restrict__ key, uint32_t *__restrict__ val, uint32_t *__restrict__ adj_cnt) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  uint32_t a = (uint32_t)new_of_old_b[pq[p]], b = (uint32_t)new_of_old_b[pr[p]];
+  key[2 * p] = ((uint64_t)a << shift) | b;
+  key[2 * p + 1] = ((uint64_t)b << shift) | a;
+  val[2 * p] = val[2 * p + 1] = (uint32_t)pd[p];
+  atomicAdd(&adj_cnt[a], 1u);
+  atomicAdd(&adj_cnt[b], 1u);
+}
+
+__global__ void adj_unpack_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ val, int64_t n, int shift,
+                                  int32_t *__restrict__ nbr, int32_t *__restrict__ d) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  nbr[i] = (int32_t)(key[i] & ((1ull << shift) - 1ull));
+  d[i] = (int32_t)val[i];
 }
 
 __global__ void cpair_keys_kernel(const int32_t *__restrict__ pq, const int32_t *__restrict__ ped, int64_t n_pairs,
-                                  const int32_t *__restrict__ comp_of_bucket, int32_t n_comp, int32_t max_diff,
+                                  const int32_t *__restrict__ new_of_old_b, const int32_t *__restrict__ comp_of_new_b,
+                                  int32_t n_comp, int32_t max_diff,
                                   uint64_t *__restrict__ key, uint32_t *__restrict__ val, uint32_t *__restrict__ cnt) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_pairs) return;
   int32_t ed = ped[p];
   bool visit = ed >= 1 && ed <= max_diff;
-  uint32_t c = visit ? (uint32_t)comp_of_bucket[pq[p]] : (uint32_t)n_comp;
+  uint32_t c = visit ? (uint32_t)comp_of_new_b[new_of_old_b[pq[p]]] : (uint32_t)n_comp;
   key[p] = ((uint64_t)c << 2) | (uint64_t)(visit ? ed : 0);
   val[p] = (uint32_t)p;
   if (visit) atomicAdd(&cnt[c], 1u);
@@ -121,35 +183,23 @@ __global__ void cpair_keys_kernel(const int32_t *__restrict__ pq, const int32_t 
 
 __global__ void cpair_gather_kernel(const uint32_t *__restrict__ order, int64_t n, const int32_t *__restrict__ pq,
                                     const int32_t *__restrict__ pr, const int32_t *__restrict__ ped,
+                                    const int32_t *__restrict__ new_of_old_b,
                                     int32_t *__restrict__ cq, int32_t *__restrict__ cr, int32_t *__restrict__ ce) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t p = order[i];
-  cq[i] = pq[p]; cr[i] = pr[p]; ce[i] = ped[p];
+  cq[i] = new_of_old_b[pq[p]]; cr[i] = new_of_old_b[pr[p]]; ce[i] = ped[p];
 }
 
-__global__ void comp_load_kernel(const int32_t *__restrict__ bucket_ptr, const int32_t *__restrict__ bucket_reads,
-                                 const int32_t *__restrict__ geno_ptr, const int32_t *__restrict__ comp_of_bucket, int32_t U,
-                                 unsigned long long *__restrict__ comp_reads, unsigned long long *__restrict__ comp_nnz) {
-  int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= U) return;
-  unsigned long long nnz = 0;
-  for (int32_t x = bucket_ptr[b]; x < bucket_ptr[b + 1]; x++) {
-    int32_t r = bucket_reads[x];
-    nnz += (unsigned long long)(geno_ptr[r + 1] - geno_ptr[r]);
-  }
-  int32_t c = comp_of_bucket[b];
-  atomicAdd(&comp_reads[c], (unsigned long long)(bucket_ptr[b + 1] - bucket_ptr[b]));
-  atomicAdd(&comp_nnz[c], nnz);
-}
-
-__global__ void comp_scratch_kernel(const unsigned long long *__restrict__ comp_reads, const unsigned long long *__restrict__ comp_nnz,
-                                    int32_t n_comp, int32_t *__restrict__ slot_cap, int64_t *__restrict__ slot_sz,
-                                    int64_t *__restrict__ list_sz, int64_t *__restrict__ call_sz) {
+// components are contiguous in the new numbering: sizes come straight from the prefix arrays
+__global__ void comp_scratch_kernel(const int32_t *__restrict__ comp_ptr, const uint32_t *__restrict__ nb_ptr,
+                                    const uint32_t *__restrict__ n_gptr, int32_t n_comp, int32_t *__restrict__ slot_cap,
+                                    int64_t *__restrict__ slot_sz, int64_t *__restrict__ list_sz, int64_t *__restrict__ call_sz) {
   int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c > n_comp) return;
   if (c == n_comp) { slot_sz[c] = list_sz[c] = call_sz[c] = 0; return; }
-  unsigned long long reads = comp_reads[c], nnz = comp_nnz[c];
+  uint32_t r_lo = nb_ptr[comp_ptr[c]], r_hi = nb_ptr[comp_ptr[c + 1]];
+  unsigned long long reads = r_hi - r_lo, nnz = n_gptr[r_hi] - n_gptr[r_lo];
   unsigned long long need = 2ull * (reads > nnz ? reads : nnz);
   if (need < 2) need = 2;
   unsigned long long cap = 2;
@@ -167,6 +217,38 @@ __global__ void __launch_bounds__(64) component_kernel(MergeCtx c, int32_t n_com
   process_component(c, comp);
 }
 
+__global__ void init_outputs_kernel(int32_t R, int64_t nnz, int32_t *t_root, int32_t *t_pos, int32_t *t_size, int64_t *t_key,
+                                    int32_t *t_bc, int32_t *t_up, int64_t *t_calloff, int32_t *t_calln, int32_t *call_mut) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < R) {
+    t_root[i] = t_pos[i] = t_size[i] = t_bc[i] = t_up[i] = t_calln[i] = PCB_FILL;
+    t_key[i] = INT64_MIN; t_calloff[i] = INT64_MIN;
+  }
+  if (i < nnz) call_mut[i] = PCB_FILL;
+}
+
+// new numbering -> the caller's numbering.  Rows of components another shard owns stay PCB_FILL.
+__global__ void scatter_outputs_kernel(int32_t R, const int32_t *__restrict__ old_of_new_r, const int32_t *__restrict__ old_of_new_b,
+                                       const int32_t *__restrict__ t_root, const int32_t *__restrict__ t_pos,
+                                       const int32_t *__restrict__ t_size, const int64_t *__restrict__ t_key,
+                                       const int32_t *__restrict__ t_bc, const int32_t *__restrict__ t_up,
+                                       const int64_t *__restrict__ t_calloff, const int32_t *__restrict__ t_calln, MergeOut out) {
+  int32_t nr = blockIdx.x * blockDim.x + threadIdx.x;
+  if (nr >= R) return;
+  int32_t r = old_of_new_r[nr];
+  int32_t root = t_root[nr];
+  out.read_root[r] = root == PCB_FILL ? PCB_FILL : old_of_new_r[root];
+  out.read_pos[r] = t_pos[nr];
+  out.row_size[r] = t_size[nr];
+  int64_t key = t_key[nr];
+  if (key >= 0) key = ((int64_t)old_of_new_b[(int32_t)(key >> 32)] << 32) | (key & 0xFFFFFFFFll);   // creation order is by caller bucket
+  out.row_key[r] = key;
+  out.row_bc[r] = t_bc[nr];
+  out.row_up[r] = t_up[nr];
+  out.row_call_off[r] = t_calloff[nr];
+  out.row_call_n[r] = t_calln[nr];
+}
+
 void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   const int32_t R = in.R, U = in.U;
   const int64_t P = in.n_pairs;
@@ -177,19 +259,51 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   if (in.shard_count < 1 || in.shard_rank < 0 || in.shard_rank >= in.shard_count) throw Error(PCB_E_INPUT, "bad shard");
   if (R == 0 || U == 0) return;
   const int64_t nnz = (int64_t)read_scalar(ctx, in.geno_ptr + R);
-
-  // outputs start as "not mine"
-  fill_i32(ctx, out.read_root, R, PCB_FILL); fill_i32(ctx, out.read_pos, R, PCB_FILL);
-  fill_i32(ctx, out.row_size, R, PCB_FILL); fill_i32(ctx, out.row_bc, R, PCB_FILL);
-  fill_i32(ctx, out.row_up, R, PCB_FILL); fill_i32(ctx, out.row_call_n, R, PCB_FILL);
-  fill_i64(ctx, out.row_key, R, INT64_MIN); fill_i64(ctx, out.row_call_off, R, INT64_MIN);
-  fill_i32(ctx, out.call_mut, (size_t)nnz, PCB_FILL);
-
-  DevBuf<int32_t> bucket_of_read(ctx, R);
-  PCB_LAUNCH(ctx, bucket_of_read_kernel, grid_for(R, 256), 256, 0, in.bucket_ptr, in.bucket_reads, R, U, bucket_of_read.p);
-
   const int bbits = bits_for((uint64_t)(U > 1 ? U - 1 : 1));
-  // ---- adjacency
+  const bool on_demand = in.planes != nullptr && in.compute_k >= 0;
+
+  // ---- components of the link graph, ordered by work
+  DevBuf<int32_t> label(ctx, U), old_of_new_b(ctx, U), new_of_old_b(ctx, U), comp_of_new_b(ctx, U), comp_ptr(ctx, (size_t)U + 1);
+  DevBuf<uint32_t> nb_ptr(ctx, (size_t)U + 1);
+  int32_t n_comp = 0;
+  {
+    DevBuf<int32_t> parent(ctx, U);
+    DevBuf<uint32_t> work(ctx, U), rank(ctx, U);
+    DevBuf<uint64_t> k0(ctx, U), k1(ctx, U);
+    DevBuf<uint32_t> v0(ctx, U), v1(ctx, U);
+    PCB_CUDA(cudaMemsetAsync(work.p, 0, (size_t)U * sizeof(uint32_t), ctx->stream));
+    PCB_LAUNCH(ctx, uf_init_kernel, grid_for(U, 256), 256, 0, parent.p, U);
+    if (P > 0) PCB_LAUNCH(ctx, uf_union_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_r, in.pair_ed, P, in.max_diff, parent.p);
+    PCB_LAUNCH(ctx, uf_label_kernel, grid_for(U, 256), 256, 0, parent.p, in.bucket_ptr, U, label.p, work.p);
+    PCB_LAUNCH(ctx, comp_keys_kernel, grid_for(U, 256), 256, 0, label.p, work.p, U, bbits, k0.p, v0.p);
+    int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, U, bbits + 10);
+    uint64_t *sk = w ? k1.p : k0.p;
+    uint32_t *sv = w ? v1.p : v0.p;
+    PCB_LAUNCH(ctx, comp_flag_kernel, grid_for(U, 256), 256, 0, sk, U, rank.p);
+    uint32_t last_flag = read_scalar(ctx, rank.p + (U - 1));
+    exclusive_scan_u32(ctx, rank.p, rank.p, U);
+    n_comp = (int32_t)(read_scalar(ctx, rank.p + (U - 1)) + last_flag);
+    PCB_LAUNCH(ctx, comp_assign_kernel, grid_for(U, 256), 256, 0, sk, sv, rank.p, in.bucket_ptr, U, n_comp, old_of_new_b.p,
+               new_of_old_b.p, comp_ptr.p, comp_of_new_b.p, nb_ptr.p);
+    exclusive_scan_u32(ctx, nb_ptr.p, nb_ptr.p, (size_t)U + 1);
+  }
+  ctx->stats[PCB_STAT_COMPONENTS] = n_comp;
+
+  // ---- reads and genotypes gathered into component order
+  DevBuf<int32_t> old_of_new_r(ctx, R), n_bor(ctx, R), n_lex(ctx, R), n_bc(ctx, R), n_up(ctx, in.up_id ? R : 1);
+  DevBuf<uint32_t> n_gptr(ctx, (size_t)R + 1);
+  DevBuf<int32_t> n_gmut(ctx, (size_t)nnz), n_gq(ctx, (size_t)nnz);
+  PCB_LAUNCH(ctx, read_renumber_kernel, grid_for(R, 256), 256, 0, in.bucket_ptr, in.bucket_reads, R, U, new_of_old_b.p, nb_ptr.p,
+             in.lexrank, in.bc_id, in.up_id, in.geno_ptr, old_of_new_r.p, n_bor.p, n_lex.p, n_bc.p, n_up.p, n_gptr.p);
+  exclusive_scan_u32(ctx, n_gptr.p, n_gptr.p, (size_t)R + 1);
+  PCB_LAUNCH(ctx, geno_gather_kernel, grid_for(R, 256), 256, 0, old_of_new_r.p, in.geno_ptr, in.geno_mut, in.geno_q, R, n_gptr.p,
+             n_gmut.p, n_gq.p);
+  DevBuf<ulonglong2> n_planes(ctx, on_demand ? U : 1);
+  DevBuf<int32_t> n_blen(ctx, on_demand ? U : 1);
+  if (on_demand)
+    PCB_LAUNCH(ctx, planes_gather_kernel, grid_for(U, 256), 256, 0, old_of_new_b.p, in.planes, in.blen, U, n_planes.p, n_blen.p);
+
+  // ---- adjacency (new bucket ids)
   DevBuf<int32_t> adj_ptr(ctx, (size_t)U + 1), adj_nbr(ctx, (size_t)(2 * P)), adj_d(ctx, (size_t)(2 * P));
   {
     DevBuf<uint32_t> cnt(ctx, (size_t)U + 1);
@@ -197,7 +311,8 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
     if (P > 0) {
       DevBuf<uint64_t> k0(ctx, 2 * P), k1(ctx, 2 * P);
       DevBuf<uint32_t> v0(ctx, 2 * P), v1(ctx, 2 * P);
-      PCB_LAUNCH(ctx, adj_keys_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_r, in.pair_d, P, bbits, k0.p, v0.p, cnt.p);
+      PCB_LAUNCH(ctx, adj_keys_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_r, in.pair_d, P, new_of_old_b.p, bbits,
+                 k0.p, v0.p, cnt.p);
       int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, 2 * P, 2 * bbits);
       PCB_LAUNCH(ctx, adj_unpack_kernel, grid_for(2 * P, 256), 256, 0, w ? k1.p : k0.p, w ? v1.p : v0.p, 2 * P, bbits,
                  adj_nbr.p, adj_d.p);
@@ -206,28 +321,7 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
     PCB_CUDA(cudaMemcpyAsync(adj_ptr.p, cnt.p, ((size_t)U + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
   }
 
-  // ---- components
-  DevBuf<int32_t> parent(ctx, U), comp_buckets(ctx, U), comp_of_bucket(ctx, U), comp_ptr(ctx, (size_t)U + 1);
-  int32_t n_comp = 0;
-  {
-    PCB_LAUNCH(ctx, uf_init_kernel, grid_for(U, 256), 256, 0, parent.p, U);
-    if (P > 0) PCB_LAUNCH(ctx, uf_union_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_r, in.pair_ed, P, parent.p);
-    DevBuf<uint64_t> k0(ctx, U), k1(ctx, U);
-    DevBuf<uint32_t> v0(ctx, U), v1(ctx, U), rank(ctx, U);
-    PCB_LAUNCH(ctx, uf_label_kernel, grid_for(U, 256), 256, 0, parent.p, U, k0.p, v0.p);
-    int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, U, bbits);
-    uint64_t *sk = w ? k1.p : k0.p;
-    uint32_t *sv = w ? v1.p : v0.p;
-    PCB_LAUNCH(ctx, comp_flag_kernel, grid_for(U, 256), 256, 0, sk, U, rank.p);
-    uint32_t last_flag = read_scalar(ctx, rank.p + (U - 1));
-    exclusive_scan_u32(ctx, rank.p, rank.p, U);
-    n_comp = (int32_t)(read_scalar(ctx, rank.p + (U - 1)) + last_flag);
-    PCB_LAUNCH(ctx, comp_assign_kernel, grid_for(U, 256), 256, 0, sk, sv, rank.p, U, n_comp, comp_buckets.p, comp_ptr.p,
-               comp_of_bucket.p);
-  }
-  ctx->stats[PCB_STAT_COMPONENTS] = n_comp;
-
-  // ---- visiting pairs per component
+  // ---- visiting pairs per component (stable: the caller's visiting order survives inside a component)
   DevBuf<int32_t> cpair_ptr(ctx, (size_t)n_comp + 2), cq(ctx, (size_t)P), cr(ctx, (size_t)P), ce(ctx, (size_t)P);
   {
     DevBuf<uint32_t> cnt(ctx, (size_t)n_comp + 2);
@@ -235,11 +329,11 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
     if (P > 0) {
       DevBuf<uint64_t> k0(ctx, P), k1(ctx, P);
       DevBuf<uint32_t> v0(ctx, P), v1(ctx, P);
-      PCB_LAUNCH(ctx, cpair_keys_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_ed, P, comp_of_bucket.p, n_comp,
-                 in.max_diff, k0.p, v0.p, cnt.p);
+      PCB_LAUNCH(ctx, cpair_keys_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_ed, P, new_of_old_b.p, comp_of_new_b.p,
+                 n_comp, in.max_diff, k0.p, v0.p, cnt.p);
       int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, P, bits_for((uint64_t)n_comp) + 2);
       PCB_LAUNCH(ctx, cpair_gather_kernel, grid_for(P, 256), 256, 0, w ? v1.p : v0.p, P, in.pair_q, in.pair_r, in.pair_ed,
-                 cq.p, cr.p, ce.p);
+                 new_of_old_b.p, cq.p, cr.p, ce.p);
     }
     exclusive_scan_u32(ctx, cnt.p, cnt.p, (size_t)n_comp + 2);
     PCB_CUDA(cudaMemcpyAsync(cpair_ptr.p, cnt.p, ((size_t)n_comp + 2) * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -248,51 +342,51 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   // ---- scratch
   DevBuf<int32_t> slot_cap(ctx, (size_t)n_comp + 1);
   DevBuf<int64_t> slot_off(ctx, (size_t)n_comp + 1), list_off(ctx, (size_t)n_comp + 1), call_off(ctx, (size_t)n_comp + 1);
-  {
-    DevBuf<unsigned long long> comp_reads(ctx, (size_t)n_comp + 1), comp_nnz(ctx, (size_t)n_comp + 1);
-    PCB_CUDA(cudaMemsetAsync(comp_reads.p, 0, ((size_t)n_comp + 1) * sizeof(unsigned long long), ctx->stream));
-    PCB_CUDA(cudaMemsetAsync(comp_nnz.p, 0, ((size_t)n_comp + 1) * sizeof(unsigned long long), ctx->stream));
-    PCB_LAUNCH(ctx, comp_load_kernel, grid_for(U, 256), 256, 0, in.bucket_ptr, in.bucket_reads, in.geno_ptr, comp_of_bucket.p, U,
-               comp_reads.p, comp_nnz.p);
-    PCB_LAUNCH(ctx, comp_scratch_kernel, grid_for((size_t)n_comp + 1, 256), 256, 0, comp_reads.p, comp_nnz.p, n_comp, slot_cap.p,
-               slot_off.p, list_off.p, call_off.p);
-    exclusive_scan_i64(ctx, slot_off.p, slot_off.p, (size_t)n_comp + 1);
-    exclusive_scan_i64(ctx, list_off.p, list_off.p, (size_t)n_comp + 1);
-    exclusive_scan_i64(ctx, call_off.p, call_off.p, (size_t)n_comp + 1);
-  }
+  PCB_LAUNCH(ctx, comp_scratch_kernel, grid_for((size_t)n_comp + 1, 256), 256, 0, comp_ptr.p, nb_ptr.p, n_gptr.p, n_comp, slot_cap.p,
+             slot_off.p, list_off.p, call_off.p);
+  exclusive_scan_i64(ctx, slot_off.p, slot_off.p, (size_t)n_comp + 1);
+  exclusive_scan_i64(ctx, list_off.p, list_off.p, (size_t)n_comp + 1);
+  exclusive_scan_i64(ctx, call_off.p, call_off.p, (size_t)n_comp + 1);
   int64_t n_slots = read_scalar(ctx, slot_off.p + n_comp);
   int64_t n_list = read_scalar(ctx, list_off.p + n_comp);
   DevBuf<GenoSlot> slots(ctx, (size_t)n_slots);
   DevBuf<int32_t> lists(ctx, (size_t)n_list + 1);
   PCB_CUDA(cudaMemsetAsync(slots.p, 0xFF, (size_t)n_slots * sizeof(GenoSlot), ctx->stream));
 
-  // ---- cluster state
+  // ---- cluster state and outputs in the new numbering
   DevBuf<int32_t> rd_slot(ctx, R), rd_next(ctx, R), sl_parent(ctx, R), sl_head(ctx, R), sl_tail(ctx, R), sl_size(ctx, R), status(ctx, 4);
   DevBuf<int64_t> sl_key(ctx, R);
+  DevBuf<int32_t> t_root(ctx, R), t_pos(ctx, R), t_size(ctx, R), t_bc(ctx, R), t_up(ctx, R), t_calln(ctx, R);
+  DevBuf<int64_t> t_key(ctx, R), t_calloff(ctx, R);
   PCB_CUDA(cudaMemsetAsync(rd_slot.p, 0xFF, (size_t)R * sizeof(int32_t), ctx->stream));
   PCB_CUDA(cudaMemsetAsync(rd_next.p, 0xFF, (size_t)R * sizeof(int32_t), ctx->stream));
   PCB_CUDA(cudaMemsetAsync(status.p, 0, 4 * sizeof(int32_t), ctx->stream));
+  // everything starts as "not mine" (rows of components another shard owns, per-row fields of non-representative reads)
+  PCB_LAUNCH(ctx, init_outputs_kernel, grid_for((size_t)(R > nnz ? R : nnz), 256), 256, 0, R, nnz, t_root.p, t_pos.p, t_size.p,
+             t_key.p, t_bc.p, t_up.p, t_calloff.p, t_calln.p, out.call_mut);
 
   MergeCtx c;
   memset(&c, 0, sizeof(c));
   c.R = R; c.U = U;
-  c.bucket_ptr = in.bucket_ptr; c.bucket_reads = in.bucket_reads; c.bucket_of_read = bucket_of_read.p;
-  c.lexrank = in.lexrank; c.bc_id = in.bc_id; c.up_id = in.up_id;
-  c.geno_ptr = in.geno_ptr; c.geno_mut = in.geno_mut; c.geno_q = in.geno_q; c.mut_rank = in.mut_rank;
+  c.bucket_ptr = (const int32_t *)nb_ptr.p; c.bucket_reads = nullptr; c.bucket_of_read = n_bor.p;
+  c.lexrank = n_lex.p; c.bc_id = n_bc.p; c.up_id = in.up_id ? n_up.p : nullptr;
+  c.geno_ptr = (const int32_t *)n_gptr.p; c.geno_mut = n_gmut.p; c.geno_q = n_gq.p; c.mut_rank = in.mut_rank;
   c.adj_ptr = adj_ptr.p; c.adj_nbr = adj_nbr.p; c.adj_d = adj_d.p;
-  c.planes = (const uint64_t *)in.planes; c.blen = in.blen;
-  c.compute_k = in.planes ? in.compute_k : -1; c.wide = in.wide;
-  c.comp_ptr = comp_ptr.p; c.comp_buckets = comp_buckets.p;
+  c.planes = on_demand ? (const uint64_t *)n_planes.p : nullptr; c.blen = on_demand ? n_blen.p : nullptr;
+  c.compute_k = on_demand ? in.compute_k : -1; c.wide = in.wide;
+  c.comp_ptr = comp_ptr.p; c.comp_buckets = nullptr;
   c.cpair_ptr = cpair_ptr.p; c.cpair_q = cq.p; c.cpair_r = cr.p; c.cpair_ed = ce.p;
   c.scr_slot_off = slot_off.p; c.scr_slot_cap = slot_cap.p; c.scr_list_off = list_off.p; c.call_off = call_off.p;
   c.slots = slots.p; c.lists = lists.p;
   c.rd_slot = rd_slot.p; c.rd_next = rd_next.p; c.sl_parent = sl_parent.p; c.sl_head = sl_head.p;
   c.sl_tail = sl_tail.p; c.sl_size = sl_size.p; c.sl_key = sl_key.p;
-  c.read_root = out.read_root; c.read_pos = out.read_pos; c.row_size = out.row_size; c.row_key = out.row_key;
-  c.row_bc = out.row_bc; c.row_up = out.row_up; c.row_call_off = out.row_call_off; c.row_call_n = out.row_call_n;
+  c.read_root = t_root.p; c.read_pos = t_pos.p; c.row_size = t_size.p; c.row_key = t_key.p;
+  c.row_bc = t_bc.p; c.row_up = t_up.p; c.row_call_off = t_calloff.p; c.row_call_n = t_calln.p;
   c.call_mut = out.call_mut; c.status = status.p;
   c.prm.maxDiff = in.max_diff; c.prm.minQual = in.min_qual; c.prm.minMatches = in.min_matches; c.prm.minJaccard = in.min_jaccard;
   PCB_LAUNCH(ctx, component_kernel, grid_for(n_comp, 64), 64, 0, c, n_comp, in.shard_rank, in.shard_count);
+  PCB_LAUNCH(ctx, scatter_outputs_kernel, grid_for(R, 256), 256, 0, R, old_of_new_r.p, old_of_new_b.p, t_root.p, t_pos.p, t_size.p,
+             t_key.p, t_bc.p, t_up.p, t_calloff.p, t_calln.p, out);
 
   int32_t h_status[4];
   PCB_CUDA(cudaMemcpyAsync(h_status, status.p, sizeof(h_status), cudaMemcpyDeviceToHost, ctx->stream));

@@ -183,10 +183,11 @@ PCB_HD int32_t lookup_dist(const MergeCtx &c, int32_t a, int32_t b) {
 PCB_HD void seed_bucket(const MergeCtx &c, int32_t b, Table &tab) {
   int32_t lo = c.bucket_ptr[b], n = c.bucket_ptr[b + 1] - lo;
   if (n < 2) return;
-  const int32_t *rids = c.bucket_reads + lo;
+  const int32_t *rids = c.bucket_reads ? c.bucket_reads + lo : nullptr;     // null: reads are numbered lo, lo+1, ...
+#define PCB_RID(i) (rids ? rids[i] : lo + (i))
   // varMatrix + filterSeqError (:338-356): per mutation #reads with Q>0 and sum of Q over the bucket
   for (int32_t i = 0; i < n; i++)
-    for (int32_t e = c.geno_ptr[rids[i]]; e < c.geno_ptr[rids[i] + 1]; e++) {
+    for (int32_t e = c.geno_ptr[PCB_RID(i)]; e < c.geno_ptr[PCB_RID(i) + 1]; e++) {
       GenoSlot *s = table_slot(tab, c.geno_mut[e]);
       int32_t q = c.geno_q[e];
       if (q > 0) s->obs1++;
@@ -194,9 +195,9 @@ PCB_HD void seed_bucket(const MergeCtx &c, int32_t b, Table &tab) {
     }
   int32_t n_created = 0;
   for (int32_t i = 1; i < n; i++) {
-    int32_t ri = rids[i];
+    int32_t ri = PCB_RID(i);
     for (int32_t j = 0; j < i; j++) {
-      int32_t rj = rids[j];
+      int32_t rj = PCB_RID(j);
       int32_t ci = cluster_of(c, ri);
       if (ci >= 0 && ci == cluster_of(c, rj)) continue;     // addLink would be a no-op
       // calcJaccard on presence over the kept mutations (:358-367)
@@ -224,6 +225,7 @@ PCB_HD void seed_bucket(const MergeCtx &c, int32_t b, Table &tab) {
     }
   }
   table_clear(tab);
+#undef PCB_RID
 }
 
 // accumulate one side of the genotype rule; side 0 -> (obs1,sum1), side 1 -> (obs2,sum2)
@@ -315,7 +317,7 @@ PCB_HD void process_component(const MergeCtx &c, int32_t comp) {
   int32_t b_lo = c.comp_ptr[comp], b_hi = c.comp_ptr[comp + 1];
 
   // ---- seed clustering, bucket by bucket
-  for (int32_t bi = b_lo; bi < b_hi; bi++) seed_bucket(c, c.comp_buckets[bi], tab);
+  for (int32_t bi = b_lo; bi < b_hi; bi++) seed_bucket(c, c.comp_buckets ? c.comp_buckets[bi] : bi, tab);
 
   // ---- main clustering: the component's rows, pass by pass, in visiting order
   int32_t n_links = 0, n_tests = 0;
@@ -323,9 +325,9 @@ PCB_HD void process_component(const MergeCtx &c, int32_t comp) {
   for (int32_t p = c.cpair_ptr[comp]; p < c.cpair_ptr[comp + 1]; p++) {
     int32_t bq = c.cpair_q[p], br = c.cpair_r[p], ed = c.cpair_ed[p];
     for (int32_t x = c.bucket_ptr[bq]; x < c.bucket_ptr[bq + 1]; x++) {
-      int32_t rx = c.bucket_reads[x];
+      int32_t rx = c.bucket_reads ? c.bucket_reads[x] : x;
       for (int32_t y = c.bucket_ptr[br]; y < c.bucket_ptr[br + 1]; y++) {
-        int32_t ry = c.bucket_reads[y];
+        int32_t ry = c.bucket_reads ? c.bucket_reads[y] : y;
         int32_t rid1 = rx, rid2 = ry;                                       // makePID order (:152-157)
         if (!(c.lexrank[rx] < c.lexrank[ry])) { rid1 = ry; rid2 = rx; }
         int32_t c1 = cluster_of(c, rid1), c2 = cluster_of(c, rid2);
@@ -346,9 +348,9 @@ PCB_HD void process_component(const MergeCtx &c, int32_t comp) {
   int64_t call_pos = c.call_off[comp];
   int32_t err = 0;
   for (int32_t bi = b_lo; bi < b_hi; bi++) {
-    int32_t b = c.comp_buckets[bi];
+    int32_t b = c.comp_buckets ? c.comp_buckets[bi] : bi;
     for (int32_t x = c.bucket_ptr[b]; x < c.bucket_ptr[b + 1]; x++) {
-      int32_t r = c.bucket_reads[x];
+      int32_t r = c.bucket_reads ? c.bucket_reads[x] : x;
       int32_t cl = cluster_of(c, r);
       if (cl < 0) {
         // singleton (:560-567): calls with Q >= minQual in input order
