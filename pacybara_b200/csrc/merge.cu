@@ -19,6 +19,7 @@
 //   scatter       outputs back to the caller's read numbering
 // Everything except the replay is HBM-bound streaming; the replay is latency-bound pointer work
 // whose parallelism is the number of components (about 10^5 at cfg 2).
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -210,11 +211,61 @@ __global__ void comp_scratch_kernel(const int32_t *__restrict__ comp_ptr, const 
   call_sz[c] = (int64_t)nnz;
 }
 
-__global__ void __launch_bounds__(64) component_kernel(MergeCtx c, int32_t n_comp, int32_t shard_rank, int32_t shard_count) {
-  int32_t comp = blockIdx.x * blockDim.x + threadIdx.x;
-  if (comp >= n_comp) return;
-  if (comp % shard_count != shard_rank) return;
-  process_component(c, comp);
+// The replay is divergent, latency-bound pointer chasing: lanes of a warp that run different components
+// serialise, and every read-modify-write of cluster state or of the scratch table is a dependent
+// round trip.  Two measures (profiles/r01d):
+//  * only every (32 / per_warp)-th lane takes a component: fewer serialised components per warp,
+//    several times more warps in flight;
+//  * a component whose working set is small (<= SM_READS reads and <= SM_READS genotype entries,
+//    i.e. almost all of them) keeps ALL of its mutable state -- cluster lists, union-find, scratch
+//    table -- in shared memory (MergeState with r0 = first read): a round trip costs ~30 cycles
+//    instead of an L2 access.  Larger components use the global arrays, unchanged.
+constexpr int COMP_BLOCK = 128;
+constexpr int SM_READS = 32;
+constexpr int SM_SLOTS = 2 * SM_READS;
+struct __align__(16) CompSmem {
+  GenoSlot slots[SM_SLOTS];
+  int64_t sl_key[SM_READS];
+  int32_t lists[4 * SM_READS];
+  int32_t rd_slot[SM_READS], rd_next[SM_READS], sl_parent[SM_READS], sl_head[SM_READS], sl_tail[SM_READS], sl_size[SM_READS];
+};
+
+__global__ void __launch_bounds__(COMP_BLOCK) component_kernel(MergeCtx c, int32_t n_comp, int32_t shard_rank, int32_t shard_count,
+                                                               int32_t per_warp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  CompSmem *sm_all = reinterpret_cast<CompSmem *>(smem_raw);
+  const int32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t lane = threadIdx.x & 31;
+  const int32_t stride = 32 / per_warp;                 // lanes per component
+  const int32_t group = lane / stride, sub = lane % stride;
+  const int32_t comp = (tid >> 5) * per_warp + group;
+  const bool mine = comp < n_comp && comp % shard_count == shard_rank;
+  bool in_smem = false;
+  CompSmem *sm = sm_all + ((threadIdx.x >> 5) * per_warp + group);
+  int32_t r_lo = 0;
+  if (mine) {
+    r_lo = c.bucket_ptr[c.comp_ptr[comp]];
+    int32_t reads = c.bucket_ptr[c.comp_ptr[comp + 1]] - r_lo;
+    int32_t nnz = c.geno_ptr[r_lo + reads] - c.geno_ptr[r_lo];
+    in_smem = reads <= SM_READS && nnz <= SM_READS;
+    if (in_smem) {                                      // the component's lanes initialise its state together
+      for (int32_t i = sub; i < SM_SLOTS; i += stride) sm->slots[i].key = -1;
+      for (int32_t i = sub; i < reads; i += stride) { sm->rd_slot[i] = -1; sm->rd_next[i] = -1; }
+    }
+  }
+  __syncwarp();
+  if (!mine || sub != 0) return;
+  if (in_smem) {
+    MergeState st;
+    st.r0 = r_lo;
+    st.rd_slot = sm->rd_slot; st.rd_next = sm->rd_next; st.sl_parent = sm->sl_parent; st.sl_head = sm->sl_head;
+    st.sl_tail = sm->sl_tail; st.sl_size = sm->sl_size; st.sl_key = sm->sl_key;
+    st.slots = sm->slots; st.slot_mask = SM_SLOTS - 1;
+    st.lists = sm->lists; st.list_cap = 2 * SM_READS;
+    process_component(c, st, comp);
+  } else {
+    process_component(c, global_state(c, comp), comp);
+  }
 }
 
 __global__ void init_outputs_kernel(int32_t R, int64_t nnz, int32_t *t_root, int32_t *t_pos, int32_t *t_size, int64_t *t_key,
@@ -384,7 +435,13 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   c.row_bc = t_bc.p; c.row_up = t_up.p; c.row_call_off = t_calloff.p; c.row_call_n = t_calln.p;
   c.call_mut = out.call_mut; c.status = status.p;
   c.prm.maxDiff = in.max_diff; c.prm.minQual = in.min_qual; c.prm.minMatches = in.min_matches; c.prm.minJaccard = in.min_jaccard;
-  PCB_LAUNCH(ctx, component_kernel, grid_for(n_comp, 64), 64, 0, c, n_comp, in.shard_rank, in.shard_count);
+  int per_warp = 4;
+  if (const char *e = getenv("PCB_COMP_PER_WARP")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) per_warp = v; }
+  size_t n_threads = ((size_t)n_comp + per_warp - 1) / per_warp * 32;
+  size_t smem_bytes = (size_t)(COMP_BLOCK / 32) * per_warp * sizeof(CompSmem);
+  PCB_CUDA(cudaFuncSetAttribute(component_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  PCB_LAUNCH(ctx, component_kernel, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, smem_bytes, c, n_comp, in.shard_rank,
+             in.shard_count, per_warp);
   PCB_LAUNCH(ctx, scatter_outputs_kernel, grid_for(R, 256), 256, 0, R, old_of_new_r.p, old_of_new_b.p, t_root.p, t_pos.p, t_size.p,
              t_key.p, t_bc.p, t_up.p, t_calloff.p, t_calln.p, out);
 

@@ -63,14 +63,14 @@ struct MergeCtx {
   int32_t compute_k, wide;
   const int32_t *comp_ptr, *comp_buckets;            // component -> buckets (ascending)
   const int32_t *cpair_ptr, *cpair_q, *cpair_r, *cpair_ed;
-  // per-component scratch
+  // per-component scratch (global-memory variant; see MergeState)
   const int64_t *scr_slot_off;   // into slots[]  (capacity = scr_slot_cap[c], a power of two)
   const int32_t *scr_slot_cap;
   const int64_t *scr_list_off;   // into lists[]  (capacity 2 * (#reads + #geno entries) of the component)
   const int64_t *call_off;       // into call_mut[] (capacity = #geno entries of the component)
   GenoSlot *slots;
   int32_t *lists;
-  // cluster state (size R)
+  // cluster state in global memory (size R)
   int32_t *rd_slot, *rd_next;
   int32_t *sl_parent, *sl_head, *sl_tail, *sl_size;
   int64_t *sl_key;
@@ -83,58 +83,88 @@ struct MergeCtx {
   MergeParams prm;
 };
 
-PCB_HD int32_t slot_find(const MergeCtx &c, int32_t s) {
-  while (c.sl_parent[s] != s) {
-    int32_t g = c.sl_parent[c.sl_parent[s]];
-    c.sl_parent[s] = g;
+// The mutable working set of ONE component: cluster state of its reads (indexed by read - r0) and its
+// scratch table / lists.  It lives either in the global arrays of MergeCtx (r0 = 0) or, for components
+// small enough, in shared memory (r0 = first read of the component) -- every read-modify-write of the
+// replay then costs a shared-memory round trip instead of an L2 one.
+struct MergeState {
+  int32_t r0;
+  int32_t *rd_slot, *rd_next;
+  int32_t *sl_parent, *sl_head, *sl_tail, *sl_size;
+  int64_t *sl_key;
+  GenoSlot *slots;
+  int32_t slot_mask;
+  int32_t *lists;
+  int64_t list_cap;          // lists holds 2 * list_cap ints
+};
+
+PCB_HD MergeState global_state(const MergeCtx &c, int32_t comp) {
+  MergeState s;
+  s.r0 = 0;
+  s.rd_slot = c.rd_slot; s.rd_next = c.rd_next; s.sl_parent = c.sl_parent; s.sl_head = c.sl_head;
+  s.sl_tail = c.sl_tail; s.sl_size = c.sl_size; s.sl_key = c.sl_key;
+  s.slots = c.slots + c.scr_slot_off[comp];
+  s.slot_mask = c.scr_slot_cap[comp] - 1;
+  s.lists = c.lists + c.scr_list_off[comp];
+  s.list_cap = (c.scr_list_off[comp + 1] - c.scr_list_off[comp]) / 2;
+  return s;
+}
+
+PCB_HD int32_t slot_find(const MergeCtx &c, const MergeState &st, int32_t s) {
+  while (st.sl_parent[(s) - st.r0] != s) {
+    int32_t g = st.sl_parent[(st.sl_parent[(s) - st.r0]) - st.r0];
+    st.sl_parent[(s) - st.r0] = g;
     s = g;
   }
   return s;
 }
-PCB_HD int32_t cluster_of(const MergeCtx &c, int32_t r) {
-  int32_t s = c.rd_slot[r];
-  return s < 0 ? -1 : slot_find(c, s);
+PCB_HD int32_t cluster_of(const MergeCtx &c, const MergeState &st, int32_t r) {
+  int32_t s = st.rd_slot[(r) - st.r0];
+  return s < 0 ? -1 : slot_find(c, st, s);
 }
 
 // src/pacybara_cluster.py:185-220
-PCB_HD void add_link(const MergeCtx &c, int32_t rid1, int32_t rid2, int64_t new_key) {
-  int32_t c1 = cluster_of(c, rid1), c2 = cluster_of(c, rid2);
+PCB_HD void add_link(const MergeCtx &c, const MergeState &st, int32_t rid1, int32_t rid2, int64_t new_key) {
+  int32_t c1 = cluster_of(c, st, rid1), c2 = cluster_of(c, st, rid2);
   if (c1 >= 0) {
     if (c2 >= 0) {
       if (c1 == c2) return;
-      int32_t head = c.sl_head[c1], tail = c.sl_tail[c2], size = c.sl_size[c1] + c.sl_size[c2];
-      int64_t key = c.sl_key[c1];
-      c.rd_next[c.sl_tail[c1]] = c.sl_head[c2];
-      int32_t root = c.sl_size[c1] >= c.sl_size[c2] ? c1 : c2;
+      int32_t head = st.sl_head[(c1) - st.r0], tail = st.sl_tail[(c2) - st.r0], size = st.sl_size[(c1) - st.r0] + st.sl_size[(c2) - st.r0];
+      int64_t key = st.sl_key[(c1) - st.r0];
+      st.rd_next[(st.sl_tail[(c1) - st.r0]) - st.r0] = st.sl_head[(c2) - st.r0];
+      int32_t root = st.sl_size[(c1) - st.r0] >= st.sl_size[(c2) - st.r0] ? c1 : c2;
       int32_t child = root == c1 ? c2 : c1;
-      c.sl_parent[child] = root;
-      c.sl_head[root] = head; c.sl_tail[root] = tail; c.sl_size[root] = size; c.sl_key[root] = key;
+      st.sl_parent[(child) - st.r0] = root;
+      st.sl_head[(root) - st.r0] = head; st.sl_tail[(root) - st.r0] = tail; st.sl_size[(root) - st.r0] = size; st.sl_key[(root) - st.r0] = key;
     } else {
-      c.rd_next[c.sl_tail[c1]] = rid2; c.rd_next[rid2] = -1;
-      c.sl_tail[c1] = rid2; c.sl_size[c1] += 1; c.rd_slot[rid2] = c1;
+      st.rd_next[(st.sl_tail[(c1) - st.r0]) - st.r0] = rid2; st.rd_next[(rid2) - st.r0] = -1;
+      st.sl_tail[(c1) - st.r0] = rid2; st.sl_size[(c1) - st.r0] += 1; st.rd_slot[(rid2) - st.r0] = c1;
     }
   } else if (c2 >= 0) {
-    c.rd_next[c.sl_tail[c2]] = rid1; c.rd_next[rid1] = -1;
-    c.sl_tail[c2] = rid1; c.sl_size[c2] += 1; c.rd_slot[rid1] = c2;
+    st.rd_next[(st.sl_tail[(c2) - st.r0]) - st.r0] = rid1; st.rd_next[(rid1) - st.r0] = -1;
+    st.sl_tail[(c2) - st.r0] = rid1; st.sl_size[(c2) - st.r0] += 1; st.rd_slot[(rid1) - st.r0] = c2;
   } else {
     int32_t s = rid1;
-    c.sl_parent[s] = s; c.sl_head[s] = rid1; c.sl_tail[s] = rid2; c.sl_size[s] = 2; c.sl_key[s] = new_key;
-    c.rd_next[rid1] = rid2; c.rd_next[rid2] = -1;
-    c.rd_slot[rid1] = s; c.rd_slot[rid2] = s;
+    st.sl_parent[(s) - st.r0] = s; st.sl_head[(s) - st.r0] = rid1; st.sl_tail[(s) - st.r0] = rid2; st.sl_size[(s) - st.r0] = 2; st.sl_key[(s) - st.r0] = new_key;
+    st.rd_next[(rid1) - st.r0] = rid2; st.rd_next[(rid2) - st.r0] = -1;
+    st.rd_slot[(rid1) - st.r0] = s; st.rd_slot[(rid2) - st.r0] = s;
   }
 }
 
-PCB_HD uint32_t hash_i32(int32_t k) {
-  uint32_t x = (uint32_t)k;
-  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
-  return x;
-}
+// Fibonacci hashing: one multiply, the table index is the top bits
+PCB_HD uint32_t hash_i32(int32_t k, int32_t shift) { return ((uint32_t)k * 0x9E3779B1u) >> shift; }
 
 struct Table {
-  GenoSlot *slots; int32_t mask; int32_t *touched; int32_t n_touched;
+  GenoSlot *slots; int32_t mask; int32_t shift; int32_t *touched; int32_t n_touched;
 };
+PCB_HD void table_init(Table &t, GenoSlot *slots, int32_t mask, int32_t *touched) {
+  t.slots = slots; t.mask = mask; t.touched = touched; t.n_touched = 0;
+  int32_t bits = 0;
+  while ((1 << bits) <= mask) bits++;          // mask = 2^bits - 1, bits >= 1
+  t.shift = 32 - bits;
+}
 PCB_HD GenoSlot *table_slot(Table &t, int32_t key) {
-  uint32_t i = hash_i32(key) & (uint32_t)t.mask;
+  uint32_t i = hash_i32(key, t.shift);
   for (;;) {
     GenoSlot *s = &t.slots[i];
     if (s->key == key) return s;
@@ -147,7 +177,7 @@ PCB_HD GenoSlot *table_slot(Table &t, int32_t key) {
   }
 }
 PCB_HD const GenoSlot *table_find(const Table &t, int32_t key) {
-  uint32_t i = hash_i32(key) & (uint32_t)t.mask;
+  uint32_t i = hash_i32(key, t.shift);
   for (;;) {
     const GenoSlot *s = &t.slots[i];
     if (s->key == key) return s;
@@ -180,7 +210,7 @@ PCB_HD int32_t lookup_dist(const MergeCtx &c, int32_t a, int32_t b) {
 }
 
 // SEED CLUSTERING of one bucket (:385-400)
-PCB_HD void seed_bucket(const MergeCtx &c, int32_t b, Table &tab) {
+PCB_HD void seed_bucket(const MergeCtx &c, const MergeState &st, int32_t b, Table &tab) {
   int32_t lo = c.bucket_ptr[b], n = c.bucket_ptr[b + 1] - lo;
   if (n < 2) return;
   const int32_t *rids = c.bucket_reads ? c.bucket_reads + lo : nullptr;     // null: reads are numbered lo, lo+1, ...
@@ -196,10 +226,10 @@ PCB_HD void seed_bucket(const MergeCtx &c, int32_t b, Table &tab) {
   int32_t n_created = 0;
   for (int32_t i = 1; i < n; i++) {
     int32_t ri = PCB_RID(i);
+    int32_t ci = -1;                                             // read i is in no cluster when its row of pairs starts
     for (int32_t j = 0; j < i; j++) {
       int32_t rj = PCB_RID(j);
-      int32_t ci = cluster_of(c, ri);
-      if (ci >= 0 && ci == cluster_of(c, rj)) continue;     // addLink would be a no-op
+      if (ci >= 0 && ci == cluster_of(c, st, rj)) continue;     // addLink would be a no-op
       // calcJaccard on presence over the kept mutations (:358-367)
       int32_t ni = 0, nj = 0, inters = 0;
       for (int32_t e = c.geno_ptr[ri]; e < c.geno_ptr[ri + 1]; e++) {
@@ -218,9 +248,13 @@ PCB_HD void seed_bucket(const MergeCtx &c, int32_t b, Table &tab) {
       int32_t uni = ni + nj - inters;
       bool ok = uni == 0 || ((double)inters / (double)uni > c.prm.minJaccard && inters >= c.prm.minMatches);
       if (ok) {
-        bool fresh = c.rd_slot[ri] < 0 && c.rd_slot[rj] < 0;
-        add_link(c, ri, rj, ((int64_t)b << 32) | (int64_t)n_created);
+        bool fresh = st.rd_slot[(ri) - st.r0] < 0 && st.rd_slot[(rj) - st.r0] < 0;
+        add_link(c, st, ri, rj, ((int64_t)b << 32) | (int64_t)n_created);
         if (fresh) n_created++;
+        ci = cluster_of(c, st, ri);
+        // during the seed step a cluster only holds reads of this bucket: once it holds all of 0..i,
+        // every remaining pair (i, j) is a no-op
+        if (st.sl_size[(ci) - st.r0] == i + 1) break;
       }
     }
   }
@@ -229,8 +263,8 @@ PCB_HD void seed_bucket(const MergeCtx &c, int32_t b, Table &tab) {
 }
 
 // accumulate one side of the genotype rule; side 0 -> (obs1,sum1), side 1 -> (obs2,sum2)
-PCB_HD void accumulate_side(const MergeCtx &c, Table &tab, int32_t cl, int32_t single, int side) {
-  int32_t r = cl >= 0 ? c.sl_head[cl] : single;
+PCB_HD void accumulate_side(const MergeCtx &c, const MergeState &st, Table &tab, int32_t cl, int32_t single, int side) {
+  int32_t r = cl >= 0 ? st.sl_head[(cl) - st.r0] : single;
   while (r >= 0) {
     for (int32_t e = c.geno_ptr[r]; e < c.geno_ptr[r + 1]; e++) {
       GenoSlot *s = table_slot(tab, c.geno_mut[e]);
@@ -238,25 +272,29 @@ PCB_HD void accumulate_side(const MergeCtx &c, Table &tab, int32_t cl, int32_t s
       if (side == 0) { if (q > 0) s->obs1++; s->sum1 += q; }
       else           { if (q > 0) s->obs2++; s->sum2 += q; }
     }
-    r = cl >= 0 ? c.rd_next[r] : -1;
+    r = cl >= 0 ? st.rd_next[(r) - st.r0] : -1;
   }
 }
 
 // one visit of the main loop body (:419-455) for the ordered read pair (rid1, rid2)
 // returns 1 if the pair was linked
-PCB_HD int visit_pair(const MergeCtx &c, Table &tab, int32_t *runs, int32_t rid1, int32_t rid2, int32_t ed,
-                      int32_t c1, int32_t c2) {
-  int32_t size1 = c1 >= 0 ? c.sl_size[c1] : 1, size2 = c2 >= 0 ? c.sl_size[c2] : 1;
+// `cache_root`: the cluster whose genotype sums currently sit in side 1 of the table (-1: none).  A
+// cluster's sums only change when it merges, and the merged sums are exactly side 1 + side 2 of the test
+// that allowed the merge, so the usual "many satellites join one big cluster" sequence accumulates the
+// big side once instead of once per test.
+PCB_HD int visit_pair(const MergeCtx &c, const MergeState &st, Table &tab, int32_t *runs, int32_t rid1, int32_t rid2, int32_t ed,
+                      int32_t c1, int32_t c2, int32_t &cache_root) {
+  int32_t size1 = c1 >= 0 ? st.sl_size[(c1) - st.r0] : 1, size2 = c2 >= 0 ? st.sl_size[(c2) - st.r0] : 1;
   int32_t mx = size1 > size2 ? size1 : size2, mn = size1 > size2 ? size2 : size1;
   if ((int64_t)mx < ((int64_t)mn << ed)) return 0;                         // :435-440
   // transitive rule (:442-445): bucket runs of cluster 2, then every bucket run of cluster 1 against them
   int32_t n_runs = 0, last = -1;
-  for (int32_t r = c2 >= 0 ? c.sl_head[c2] : rid2; r >= 0; r = c2 >= 0 ? c.rd_next[r] : -1) {
+  for (int32_t r = c2 >= 0 ? st.sl_head[(c2) - st.r0] : rid2; r >= 0; r = c2 >= 0 ? st.rd_next[(r) - st.r0] : -1) {
     int32_t b = c.bucket_of_read[r];
     if (b != last) { runs[n_runs++] = b; last = b; }
   }
   int32_t maxED = 0; last = -1;
-  for (int32_t r = c1 >= 0 ? c.sl_head[c1] : rid1; r >= 0; r = c1 >= 0 ? c.rd_next[r] : -1) {
+  for (int32_t r = c1 >= 0 ? st.sl_head[(c1) - st.r0] : rid1; r >= 0; r = c1 >= 0 ? st.rd_next[(r) - st.r0] : -1) {
     int32_t a = c.bucket_of_read[r];
     if (a == last) continue;
     last = a;
@@ -267,9 +305,16 @@ PCB_HD int visit_pair(const MergeCtx &c, Table &tab, int32_t *runs, int32_t rid1
     }
   }
   if (maxED > 2 * ed) return 0;
-  // genotype rule (:447-452)
-  accumulate_side(c, tab, c1, rid1, 0);
-  accumulate_side(c, tab, c2, rid2, 1);
+  // genotype rule (:447-452); the test is symmetric in the two sides, so whichever is cached stays side 1
+  if (c1 >= 0 && c1 == cache_root) {
+    accumulate_side(c, st, tab, c2, rid2, 1);
+  } else if (c2 >= 0 && c2 == cache_root) {
+    accumulate_side(c, st, tab, c1, rid1, 1);
+  } else {
+    table_clear(tab);
+    if (c1 < 0 && c2 >= 0) { accumulate_side(c, st, tab, c2, rid2, 0); accumulate_side(c, st, tab, c1, rid1, 1); cache_root = c2; }
+    else                   { accumulate_side(c, st, tab, c1, rid1, 0); accumulate_side(c, st, tab, c2, rid2, 1); cache_root = c1; }
+  }
   int32_t inters = 0, uni = 0;
   for (int32_t i = 0; i < tab.n_touched; i++) {
     const GenoSlot *s = &tab.slots[tab.touched[i]];
@@ -278,18 +323,31 @@ PCB_HD int visit_pair(const MergeCtx &c, Table &tab, int32_t *runs, int32_t rid1
     if (p1 && p2) inters++;
     if (p1 || p2) uni++;
   }
-  table_clear(tab);
-  if (uni == 0 || (double)inters / (double)uni > c.prm.minJaccard) {
-    add_link(c, rid1, rid2, -1);
-    return 1;
+  bool link = uni == 0 || (double)inters / (double)uni > c.prm.minJaccard;
+  if (link) add_link(c, st, rid1, rid2, -1);
+  if (cache_root < 0) {
+    table_clear(tab);                                  // side 1 was a lone read: nothing worth keeping
+  } else {
+    for (int32_t i = 0; i < tab.n_touched; i++) {      // fold (merged) or drop (rejected) side 2
+      GenoSlot *s = &tab.slots[tab.touched[i]];
+      if (link) { s->obs1 += s->obs2; s->sum1 += s->sum2; }
+      s->obs2 = 0; s->sum2 = 0;
+    }
+    if (link) cache_root = cluster_of(c, st, rid1);
   }
-  return 0;
+  return link ? 1 : 0;
 }
 
 // consensus of one id column (barcode or uptag) over a member list (:515-532)
-PCB_HD int32_t consensus_id(const MergeCtx &c, Table &tab, const int32_t *ids, int32_t head, int32_t size, int32_t *err) {
+PCB_HD int32_t consensus_id(const MergeCtx &c, const MergeState &st, Table &tab, const int32_t *ids, int32_t head, int32_t size, int32_t *err) {
   int32_t best = -1, bestCnt = 0, nTop = 0;
-  for (int32_t r = head; r >= 0; r = c.rd_next[r]) {
+  {                                      // all members agree (the usual case): that id is the unique top
+    int32_t first = ids[head];
+    bool same = first >= 0;
+    for (int32_t r = st.rd_next[(head) - st.r0]; same && r >= 0; r = st.rd_next[(r) - st.r0]) same = ids[r] == first;
+    if (same) return first;
+  }
+  for (int32_t r = head; r >= 0; r = st.rd_next[(r) - st.r0]) {
     int32_t id = ids[r];
     if (id < 0) { *err = 1; id = 0x7fffffff; }
     table_slot(tab, id)->obs1++;
@@ -305,22 +363,17 @@ PCB_HD int32_t consensus_id(const MergeCtx &c, Table &tab, const int32_t *ids, i
   return PCB_NEEDS_ALIGNMENT;
 }
 
-PCB_HD void process_component(const MergeCtx &c, int32_t comp) {
+PCB_HD void process_component(const MergeCtx &c, const MergeState &st, int32_t comp) {
   Table tab;
-  tab.slots = c.slots + c.scr_slot_off[comp];
-  tab.mask = c.scr_slot_cap[comp] - 1;
-  int32_t *lists = c.lists + c.scr_list_off[comp];
-  int64_t list_cap = (c.scr_list_off[comp + 1] - c.scr_list_off[comp]) / 2;
-  tab.touched = lists;                 // first half: touched slots; second half: bucket runs / call sort
-  tab.n_touched = 0;
-  int32_t *runs = lists + list_cap;
+  table_init(tab, st.slots, st.slot_mask, st.lists);     // lists: first half touched slots, second half bucket runs
+  int32_t *runs = st.lists + st.list_cap;
   int32_t b_lo = c.comp_ptr[comp], b_hi = c.comp_ptr[comp + 1];
 
   // ---- seed clustering, bucket by bucket
-  for (int32_t bi = b_lo; bi < b_hi; bi++) seed_bucket(c, c.comp_buckets ? c.comp_buckets[bi] : bi, tab);
+  for (int32_t bi = b_lo; bi < b_hi; bi++) seed_bucket(c, st, c.comp_buckets ? c.comp_buckets[bi] : bi, tab);
 
   // ---- main clustering: the component's rows, pass by pass, in visiting order
-  int32_t n_links = 0, n_tests = 0;
+  int32_t n_links = 0, n_tests = 0, cache_root = -1;
   int32_t memo_a[4], memo_b[4], memo_n = 0, memo_w = 0;
   for (int32_t p = c.cpair_ptr[comp]; p < c.cpair_ptr[comp + 1]; p++) {
     int32_t bq = c.cpair_q[p], br = c.cpair_r[p], ed = c.cpair_ed[p];
@@ -330,14 +383,14 @@ PCB_HD void process_component(const MergeCtx &c, int32_t comp) {
         int32_t ry = c.bucket_reads ? c.bucket_reads[y] : y;
         int32_t rid1 = rx, rid2 = ry;                                       // makePID order (:152-157)
         if (!(c.lexrank[rx] < c.lexrank[ry])) { rid1 = ry; rid2 = rx; }
-        int32_t c1 = cluster_of(c, rid1), c2 = cluster_of(c, rid2);
+        int32_t c1 = cluster_of(c, st, rid1), c2 = cluster_of(c, st, rid2);
         if (c1 >= 0 && c1 == c2) continue;                                  // :424
         int32_t ida = c1 >= 0 ? c1 : ~rid1, idb = c2 >= 0 ? c2 : ~rid2;
         bool seen = false;
         for (int32_t k = 0; k < memo_n; k++) if (memo_a[k] == ida && memo_b[k] == idb) { seen = true; break; }
         if (seen) continue;
         n_tests++;
-        if (visit_pair(c, tab, runs, rid1, rid2, ed, c1, c2)) { n_links++; memo_n = 0; memo_w = 0; }
+        if (visit_pair(c, st, tab, runs, rid1, rid2, ed, c1, c2, cache_root)) { n_links++; memo_n = 0; memo_w = 0; }
         else { memo_a[memo_w] = ida; memo_b[memo_w] = idb; memo_w = (memo_w + 1) & 3; if (memo_n < 4) memo_n++; }
       }
     }
@@ -345,13 +398,14 @@ PCB_HD void process_component(const MergeCtx &c, int32_t comp) {
   }
 
   // ---- consensus + rows (:464-477, :515-537, :546-567)
+  table_clear(tab);                                    // drop whatever the main loop left cached
   int64_t call_pos = c.call_off[comp];
   int32_t err = 0;
   for (int32_t bi = b_lo; bi < b_hi; bi++) {
     int32_t b = c.comp_buckets ? c.comp_buckets[bi] : bi;
     for (int32_t x = c.bucket_ptr[b]; x < c.bucket_ptr[b + 1]; x++) {
       int32_t r = c.bucket_reads ? c.bucket_reads[x] : x;
-      int32_t cl = cluster_of(c, r);
+      int32_t cl = cluster_of(c, st, r);
       if (cl < 0) {
         // singleton (:560-567): calls with Q >= minQual in input order
         c.read_root[r] = r; c.read_pos[r] = 0; c.row_size[r] = 1; c.row_key[r] = -1;
@@ -363,10 +417,10 @@ PCB_HD void process_component(const MergeCtx &c, int32_t comp) {
         c.row_call_n[r] = n; call_pos += n;
         continue;
       }
-      int32_t head = c.sl_head[cl];
+      int32_t head = st.sl_head[(cl) - st.r0];
       if (head != r) continue;                     // each cluster is emitted when its head comes by
-      int32_t size = c.sl_size[cl], pos = 0;
-      for (int32_t m = head; m >= 0; m = c.rd_next[m]) {
+      int32_t size = st.sl_size[(cl) - st.r0], pos = 0;
+      for (int32_t m = head; m >= 0; m = st.rd_next[(m) - st.r0]) {
         c.read_root[m] = head; c.read_pos[m] = pos++;
         if (m != head) c.row_size[m] = 0;
         // genotype vote (:468-470): Q where the read has the key, -minQual where it has not
@@ -375,7 +429,7 @@ PCB_HD void process_component(const MergeCtx &c, int32_t comp) {
           s->obs1++; s->sum1 += c.geno_q[e];
         }
       }
-      c.row_size[head] = size; c.row_key[head] = c.sl_key[cl];
+      c.row_size[head] = size; c.row_key[head] = st.sl_key[(cl) - st.r0];
       int32_t n = 0;
       int32_t *calls = c.call_mut + call_pos;
       for (int32_t i = 0; i < tab.n_touched; i++) {
@@ -388,9 +442,9 @@ PCB_HD void process_component(const MergeCtx &c, int32_t comp) {
       }
       table_clear(tab);
       c.row_call_off[head] = call_pos; c.row_call_n[head] = n; call_pos += n;
-      c.row_bc[head] = consensus_id(c, tab, c.bc_id, head, size, &err);
+      c.row_bc[head] = consensus_id(c, st, tab, c.bc_id, head, size, &err);
       int32_t uerr = 0;
-      c.row_up[head] = c.up_id ? consensus_id(c, tab, c.up_id, head, size, &uerr) : c.row_bc[head];
+      c.row_up[head] = c.up_id ? consensus_id(c, st, tab, c.up_id, head, size, &uerr) : c.row_bc[head];
       if (uerr) { c.status[0] = 3; c.status[1] = head; }     // clustered read without uptag: KeyError in the reference
     }
   }

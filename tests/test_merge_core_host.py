@@ -80,3 +80,34 @@ def test_on_demand_distances_give_the_same_clusters(name):
     if name in ("rand_dense_d2", "rand_d3_combo"):
         out2 = util.emul_merge(p, pairs)
         assert util.table_of(job, hostdata.rows_from_merge_outputs(out2)) != util.golden_table(case)
+
+
+@pytest.mark.parametrize("seed,kw", [
+    (101, dict(n_clones=400, n_reads=6000, p_err=0.03, p_near=0.5, p_collide=0.2, skew=1.2)),
+    (102, dict(n_clones=50, n_reads=4000, p_err=0.04, p_near=0.6, p_private=0.4, p_private_hq=0.1, p_dropout=0.2)),
+    (103, dict(n_clones=300, n_reads=3000, bc_len=10, p_err=0.03, p_near=0.5)),
+])
+def test_replay_vs_oracle_on_fresh_random_libraries(seed, kw):
+    """Beyond the committed goldens: dense, skewed libraries (big buckets, many satellites per cluster,
+    collisions) through the oracle and through the replay, full table and on-demand distances."""
+    lib = synth.make_library(seed=seed, **kw)
+    ids = lib.read_ids()
+    reads = hostdata.FastqReads(ids, lib.seq, lib.qual, lib.length)
+    b = util.oracle_buckets(reads)
+    md = 2
+    ei, ej, ed = orc.edit_pairs(b["bucket_seq"], b["bucket_len"], 2 * md, method="seeded")
+    q, r, d = hostdata.canonical_rows(ei, ej, ed)
+    from pacybara_b200 import pipeline
+    prob = hostdata.MergeProblem(n_reads=lib.n_reads, n_buckets=b["n_buckets"], bucket_ptr=b["bucket_ptr"],
+                                 bucket_reads=b["bucket_reads"], lexrank=hostdata.lexrank_of(ids), bc_id=b["bucket_of_read"],
+                                 up_id=None, geno_ptr=lib.geno_ptr.astype(np.int32), geno_mut=lib.geno_mut, geno_q=lib.geno_q,
+                                 mut_rank=pipeline.mut_rank_of(lib.mut_strings()), max_diff=md, min_qual=32)
+    ref = orc.cluster(prob, q, r, d)
+    full = hostdata.rows_from_merge_outputs(util.emul_merge(prob, hostdata.pairs_from_edges(ei, ej, ed, md)))
+    keep = ed <= md
+    fast = hostdata.rows_from_merge_outputs(util.emul_merge(
+        prob, hostdata.pairs_from_edges(ei[keep], ej[keep], ed[keep], md),
+        planes=util.pack_planes(b["bucket_seq"], b["bucket_len"]), blen=b["bucket_len"], compute_k=2 * md))
+    for rows in (full, fast):
+        for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
+            assert np.array_equal(getattr(rows, f), getattr(ref, f)), f
