@@ -201,8 +201,12 @@ def main():
         return ctx.cluster_reads(a["seq"], a["qual"], a["length"], a["lexrank"], a.get("up_id"), a["geno_ptr"],
                                  a["geno_mut"], a["geno_q"], a["mut_rank"], full_table=args.full_table, **params)
 
+    STAGES = ("t_bucket_ns", "t_index_ns", "probe_ns", "t_hits_ns", "t_prep_ns", "t_replay_ns", "t_scatter_ns")
+    stage_acc = {}
+
     def timed(arrs, on_device, steps):
         total_ms, probe_ns, out = 0.0, [], None
+        stage_acc.clear()
         for _ in range(steps):
             flush.fill_(1)
             torch.cuda.synchronize()
@@ -220,6 +224,8 @@ def main():
                 ms = float(t.item())
             total_ms += ms
             probe_ns.append(ctx.stat("probe_ns"))
+            for k in STAGES:
+                stage_acc.setdefault(k, []).append(ctx.stat(k) * 1e-6)
         return total_ms, probe_ns, out
 
     timed(resident, True, args.warmup)
@@ -234,6 +240,7 @@ def main():
     launches = ctx.stat("kernel_launches") - launches0
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     stats = ctx.stats()
+    stage_ms = {k.replace("t_", "").replace("_ns", ""): statistics.mean(v) for k, v in stage_acc.items()}
     # e2e: same call, pinned host inputs, host outputs
     timed(pinned, False, 1)
     e2e_ms, _, out_h = timed(pinned, False, args.steps)
@@ -298,7 +305,7 @@ def main():
                          d2h_bytes_per_step=d2h_bytes, ms_per_step=e2e_ms / args.steps),
                 gpu_launches=launches, clocks=clocks, roofline=roof, roofline_alu=alu,
                 edit_distance_gcups=(cells / probe_s / 1e9) if probe_s == probe_s else None,
-                kernel_ms=dict(probe=probe_s * 1e3))
+                kernel_ms=dict(probe=probe_s * 1e3), stage_ms=stage_ms)
     if world == 1 and not args.no_cpu_baseline:
         base, _, _ = cpu_baseline(args, params)
         line["cpu_baseline"] = base

@@ -64,6 +64,13 @@ enum {
   PCB_STAT_TESTS = 7,          /* cluster-pair tests evaluated in the main clustering */
   PCB_STAT_BUCKETS = 8,
   PCB_STAT_PROBE_NS = 9,       /* device time of the last distance kernel, ns (CUDA events) */
+  /* device time of the stages of the last call, ns, from CUDA events on the context's stream */
+  PCB_STAT_T_BUCKET_NS = 10,   /* pack + table + numbering + read grouping */
+  PCB_STAT_T_INDEX_NS = 11,    /* seed index (count, scan, fill) */
+  PCB_STAT_T_HITS_NS = 12,     /* hit sort + de-duplication */
+  PCB_STAT_T_PREP_NS = 13,     /* merge preprocessing: components, renumbering, adjacency, visiting lists, scratch */
+  PCB_STAT_T_REPLAY_NS = 14,   /* component_kernel */
+  PCB_STAT_T_SCATTER_NS = 15,  /* outputs back to the caller's numbering */
   PCB_STAT_COUNT = 16
 };
 

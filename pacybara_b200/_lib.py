@@ -14,7 +14,8 @@ FILL = -(1 << 31)
 NEEDS_ALIGNMENT = -2
 CLUSTER_FULL_TABLE = 1
 STAT = dict(pairs_scored=0, cells=1, edges=2, seed_len=3, kernel_launches=4, components=5, links=6, tests=7,
-            buckets=8, probe_ns=9)
+            buckets=8, probe_ns=9, t_bucket_ns=10, t_index_ns=11, t_hits_ns=12, t_prep_ns=13, t_replay_ns=14,
+            t_scatter_ns=15)
 
 # every symbol include/pacybara_b200.h declares
 SYMBOLS = ["pcb_abi_version", "pcb_last_error", "pcb_ctx_create", "pcb_ctx_destroy", "pcb_stat", "pcb_sync",

@@ -108,6 +108,7 @@ int pcb_ctx_create(int device, pcb_ctx **out) {
     PCB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     PCB_CUDA(cudaEventCreate(&ctx->ev0));
     PCB_CUDA(cudaEventCreate(&ctx->ev1));
+    for (int k = 0; k < 8; k++) PCB_CUDA(cudaEventCreate(&ctx->stage_ev[k]));
     cudaMemPool_t pool;
     PCB_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t keep = UINT64_MAX;
@@ -131,6 +132,7 @@ void pcb_ctx_destroy(pcb_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  for (int k = 0; k < 8; k++) if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -276,10 +278,12 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
     int32_t *bor = o_bor.p;
     if (!bor) { bor_tmp.alloc(ctx, R); bor = bor_tmp.p; }
     // a1: buckets
+    stage_begin(ctx);
     PackedBarcodes uniq;
     BucketOut bo{bor, bptr.p, breads.p, nullptr};
     int32_t U = bucket_reads_dev(ctx, d_seq.p, nullptr, d_len.p, R, stride, bo, &uniq);
     if (n_buckets) *n_buckets = U;
+    stage_end(ctx, PCB_STAT_T_BUCKET_NS);
     // a2+a3: either the full table up to 2*maxDiff (what pacybara.sh:466-468 asks of calcEdits.R), or only
     // the pairs a pass can visit (<= maxDiff) with the transitive-rule distances scored on demand
     const bool full = (flags & PCB_CLUSTER_FULL_TABLE) != 0;
@@ -294,6 +298,7 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
     if (!full) { in.planes = uniq.planes.p; in.blen = uniq.len.p; in.compute_k = 2 * max_diff; in.wide = uniq.max_len > 32; }
     MergeOut out{o_root.p, o_pos.p, o_size.p, o_key.p, o_bc.p, o_up.p, o_calloff.p, o_calln.p, o_call.p};
     merge_dev(ctx, in, out);
+    stage_collect(ctx);
     o_bor.commit(R); o_root.commit(R); o_pos.commit(R); o_size.commit(R); o_bc.commit(R); o_up.commit(R);
     o_calln.commit(R); o_call.commit(nnz); o_key.commit(R); o_calloff.commit(R);
     PCB_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -38,6 +38,9 @@ struct pcb_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t stage_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int stage_id[8] = {0};      // stat index the interval ENDING at mark k is charged to
+  int n_marks = 0;
   std::string err;
   int64_t stats[PCB_STAT_COUNT] = {0};
   pcb_edges edges;
@@ -85,6 +88,28 @@ inline unsigned grid_for(size_t n, unsigned block) {
     (ctx)->stats[PCB_STAT_KERNEL_LAUNCHES]++;                           \
     PCB_CUDA(cudaGetLastError());                                       \
   } while (0)
+
+// Stage timing: stage_begin() once, stage_end(stat) after each stage; stage_collect() after the stream
+// has drained turns the event intervals into stats[stat] (ns).
+inline void stage_begin(pcb_ctx *ctx) {
+  ctx->n_marks = 0;
+  for (int s = PCB_STAT_T_BUCKET_NS; s <= PCB_STAT_T_SCATTER_NS; s++) ctx->stats[s] = 0;
+  if (ctx->stage_ev[0]) { cudaEventRecord(ctx->stage_ev[0], ctx->stream); ctx->n_marks = 1; }
+}
+inline void stage_end(pcb_ctx *ctx, int stat) {
+  if (ctx->n_marks == 0 || ctx->n_marks >= 8) return;
+  cudaEventRecord(ctx->stage_ev[ctx->n_marks], ctx->stream);
+  ctx->stage_id[ctx->n_marks] = stat;
+  ctx->n_marks++;
+}
+inline void stage_collect(pcb_ctx *ctx) {
+  for (int k = 1; k < ctx->n_marks; k++) {
+    float ms = 0.f;
+    if (ctx->stage_id[k] >= 0 && cudaEventElapsedTime(&ms, ctx->stage_ev[k - 1], ctx->stage_ev[k]) == cudaSuccess)
+      ctx->stats[ctx->stage_id[k]] += (int64_t)(ms * 1e6);
+  }
+  ctx->n_marks = 0;
+}
 
 template <typename T>
 inline T read_scalar(pcb_ctx *ctx, const T *dev) {

@@ -236,6 +236,7 @@ void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q
   PCB_CUDA(cudaMemcpyAsync(cursor.p, bin_off.p, ((size_t)g.nbins + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
   PCB_LAUNCH(ctx, seed_fill_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, U, g, cursor.p, ent.p);
 
+  stage_end(ctx, PCB_STAT_T_INDEX_NS);
   // ---- probe (re-run with a larger hit buffer if the first guess overflows)
   const int key_shift = bits_for((uint64_t)(U - 1));
   const int per_query = g.q == 0 ? 1 : (k + 1) * (2 * k + 1);
@@ -270,6 +271,7 @@ void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q
     if (attempt >= 2) throw Error(PCB_E_CUDA, "hit buffer overflowed twice");
     cap = h_counters[0];
   }
+  stage_end(ctx, -1);      // the probe interval itself is PCB_STAT_PROBE_NS (ev0/ev1 above)
   ctx->stats[PCB_STAT_PAIRS_SCORED] = (int64_t)h_counters[1];
   ctx->stats[PCB_STAT_CELLS] = (int64_t)h_counters[2];
   size_t n_hits = (size_t)h_counters[0];
@@ -291,6 +293,7 @@ void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q
   PCB_LAUNCH(ctx, compact_edges_kernel, grid_for(n_hits, 256), 256, 0, sk, sv, rank.p, n_hits, key_shift, res.ei, res.ej, res.ed);
   res.n = (int64_t)n_edges;
   ctx->stats[PCB_STAT_EDGES] = res.n;
+  stage_end(ctx, PCB_STAT_T_HITS_NS);
 }
 
 }  // namespace pcb

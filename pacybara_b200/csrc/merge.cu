@@ -221,8 +221,12 @@ __global__ void comp_scratch_kernel(const int32_t *__restrict__ comp_ptr, const 
 //    table -- in shared memory (MergeState with r0 = first read): a round trip costs ~30 cycles
 //    instead of an L2 access.  Larger components use the global arrays, unchanged.
 constexpr int COMP_BLOCK = 128;
-constexpr int SM_READS = 32;
+#ifndef PCB_SM_READS
+#define PCB_SM_READS 32
+#endif
+constexpr int SM_READS = PCB_SM_READS;
 constexpr int SM_SLOTS = 2 * SM_READS;
+static_assert((SM_SLOTS & (SM_SLOTS - 1)) == 0, "the scratch table size must be a power of two");
 struct __align__(16) CompSmem {
   GenoSlot slots[SM_SLOTS];
   int64_t sl_key[SM_READS];
@@ -440,10 +444,13 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   size_t n_threads = ((size_t)n_comp + per_warp - 1) / per_warp * 32;
   size_t smem_bytes = (size_t)(COMP_BLOCK / 32) * per_warp * sizeof(CompSmem);
   PCB_CUDA(cudaFuncSetAttribute(component_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+  stage_end(ctx, PCB_STAT_T_PREP_NS);
   PCB_LAUNCH(ctx, component_kernel, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, smem_bytes, c, n_comp, in.shard_rank,
              in.shard_count, per_warp);
+  stage_end(ctx, PCB_STAT_T_REPLAY_NS);
   PCB_LAUNCH(ctx, scatter_outputs_kernel, grid_for(R, 256), 256, 0, R, old_of_new_r.p, old_of_new_b.p, t_root.p, t_pos.p, t_size.p,
              t_key.p, t_bc.p, t_up.p, t_calloff.p, t_calln.p, out);
+  stage_end(ctx, PCB_STAT_T_SCATTER_NS);
 
   int32_t h_status[4];
   PCB_CUDA(cudaMemcpyAsync(h_status, status.p, sizeof(h_status), cudaMemcpyDeviceToHost, ctx->stream));
