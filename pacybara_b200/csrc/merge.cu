@@ -24,6 +24,7 @@
 
 #include "common.cuh"
 #include "merge_core.h"
+#include "merge_warp.cuh"
 
 namespace pcb {
 
@@ -207,69 +208,33 @@ __global__ void comp_scratch_kernel(const int32_t *__restrict__ comp_ptr, const 
   while (cap < need) cap <<= 1;
   slot_cap[c] = (int32_t)cap;
   slot_sz[c] = (int64_t)cap;
-  list_sz[c] = (int64_t)(2ull * (reads + nnz));
+  list_sz[c] = (int64_t)(2ull * (reads + nnz) + 8);      // 4 counters, touched list, run list (merge_warp.cuh)
   call_sz[c] = (int64_t)nnz;
 }
 
-// The replay is divergent, latency-bound pointer chasing: lanes of a warp that run different components
-// serialise, and every read-modify-write of cluster state or of the scratch table is a dependent
-// round trip.  Two measures (profiles/r01d):
-//  * only every (32 / per_warp)-th lane takes a component: fewer serialised components per warp,
-//    several times more warps in flight;
-//  * a component whose working set is small (<= SM_READS reads and <= SM_READS genotype entries,
-//    i.e. almost all of them) keeps ALL of its mutable state -- cluster lists, union-find, scratch
-//    table -- in shared memory (MergeState with r0 = first read): a round trip costs ~30 cycles
-//    instead of an L2 access.  Larger components use the global arrays, unchanged.
+// Two launch shapes for the replay (merge_core.h / merge_warp.cuh):
+//  * component_kernel_warp (default): one WARP per component, uniform control flow, lanes share the
+//    order-independent work.  Components are numbered heaviest first, so the long ones start first.
+//  * component_kernel_thread (PCB_REPLAY=thread): one THREAD per component running the host-testable
+//    process_component().  Divergent lanes serialise, so only every (32 / per_warp)-th lane is used.
 constexpr int COMP_BLOCK = 128;
-#ifndef PCB_SM_READS
-#define PCB_SM_READS 32
-#endif
-constexpr int SM_READS = PCB_SM_READS;
-constexpr int SM_SLOTS = 2 * SM_READS;
-static_assert((SM_SLOTS & (SM_SLOTS - 1)) == 0, "the scratch table size must be a power of two");
-struct __align__(16) CompSmem {
-  GenoSlot slots[SM_SLOTS];
-  int64_t sl_key[SM_READS];
-  int32_t lists[4 * SM_READS];
-  int32_t rd_slot[SM_READS], rd_next[SM_READS], sl_parent[SM_READS], sl_head[SM_READS], sl_tail[SM_READS], sl_size[SM_READS];
-};
 
-__global__ void __launch_bounds__(COMP_BLOCK) component_kernel(MergeCtx c, int32_t n_comp, int32_t shard_rank, int32_t shard_count,
-                                                               int32_t per_warp) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  CompSmem *sm_all = reinterpret_cast<CompSmem *>(smem_raw);
+__global__ void __launch_bounds__(COMP_BLOCK) component_kernel_warp(MergeCtx c, int32_t n_comp, int32_t shard_rank, int32_t shard_count) {
+  const int32_t comp = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (comp >= n_comp) return;
+  if (comp % shard_count != shard_rank) return;
+  process_component_warp(c, global_state(c, comp), comp, threadIdx.x & 31);
+}
+
+__global__ void __launch_bounds__(COMP_BLOCK) component_kernel_thread(MergeCtx c, int32_t n_comp, int32_t shard_rank, int32_t shard_count,
+                                                                      int32_t per_warp) {
   const int32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int32_t lane = threadIdx.x & 31;
-  const int32_t stride = 32 / per_warp;                 // lanes per component
-  const int32_t group = lane / stride, sub = lane % stride;
-  const int32_t comp = (tid >> 5) * per_warp + group;
-  const bool mine = comp < n_comp && comp % shard_count == shard_rank;
-  bool in_smem = false;
-  CompSmem *sm = sm_all + ((threadIdx.x >> 5) * per_warp + group);
-  int32_t r_lo = 0;
-  if (mine) {
-    r_lo = c.bucket_ptr[c.comp_ptr[comp]];
-    int32_t reads = c.bucket_ptr[c.comp_ptr[comp + 1]] - r_lo;
-    int32_t nnz = c.geno_ptr[r_lo + reads] - c.geno_ptr[r_lo];
-    in_smem = reads <= SM_READS && nnz <= SM_READS;
-    if (in_smem) {                                      // the component's lanes initialise its state together
-      for (int32_t i = sub; i < SM_SLOTS; i += stride) sm->slots[i].key = -1;
-      for (int32_t i = sub; i < reads; i += stride) { sm->rd_slot[i] = -1; sm->rd_next[i] = -1; }
-    }
-  }
-  __syncwarp();
-  if (!mine || sub != 0) return;
-  if (in_smem) {
-    MergeState st;
-    st.r0 = r_lo;
-    st.rd_slot = sm->rd_slot; st.rd_next = sm->rd_next; st.sl_parent = sm->sl_parent; st.sl_head = sm->sl_head;
-    st.sl_tail = sm->sl_tail; st.sl_size = sm->sl_size; st.sl_key = sm->sl_key;
-    st.slots = sm->slots; st.slot_mask = SM_SLOTS - 1;
-    st.lists = sm->lists; st.list_cap = 2 * SM_READS;
-    process_component(c, st, comp);
-  } else {
-    process_component(c, global_state(c, comp), comp);
-  }
+  const int32_t stride = 32 / per_warp;
+  if ((tid & 31) % stride != 0) return;
+  const int32_t comp = (tid >> 5) * per_warp + (tid & 31) / stride;
+  if (comp >= n_comp) return;
+  if (comp % shard_count != shard_rank) return;
+  process_component(c, global_state(c, comp), comp);
 }
 
 __global__ void init_outputs_kernel(int32_t R, int64_t nnz, int32_t *t_root, int32_t *t_pos, int32_t *t_size, int64_t *t_key,
@@ -406,7 +371,7 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   int64_t n_list = read_scalar(ctx, list_off.p + n_comp);
   DevBuf<GenoSlot> slots(ctx, (size_t)n_slots);
   DevBuf<int32_t> lists(ctx, (size_t)n_list + 1);
-  PCB_CUDA(cudaMemsetAsync(slots.p, 0xFF, (size_t)n_slots * sizeof(GenoSlot), ctx->stream));
+  PCB_CUDA(cudaMemsetAsync(slots.p, 0, (size_t)n_slots * sizeof(GenoSlot), ctx->stream));     // all-zero = empty
 
   // ---- cluster state and outputs in the new numbering
   DevBuf<int32_t> rd_slot(ctx, R), rd_next(ctx, R), sl_parent(ctx, R), sl_head(ctx, R), sl_tail(ctx, R), sl_size(ctx, R), status(ctx, 4);
@@ -439,14 +404,18 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   c.row_bc = t_bc.p; c.row_up = t_up.p; c.row_call_off = t_calloff.p; c.row_call_n = t_calln.p;
   c.call_mut = out.call_mut; c.status = status.p;
   c.prm.maxDiff = in.max_diff; c.prm.minQual = in.min_qual; c.prm.minMatches = in.min_matches; c.prm.minJaccard = in.min_jaccard;
-  int per_warp = 4;
-  if (const char *e = getenv("PCB_COMP_PER_WARP")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) per_warp = v; }
-  size_t n_threads = ((size_t)n_comp + per_warp - 1) / per_warp * 32;
-  size_t smem_bytes = (size_t)(COMP_BLOCK / 32) * per_warp * sizeof(CompSmem);
-  PCB_CUDA(cudaFuncSetAttribute(component_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
   stage_end(ctx, PCB_STAT_T_PREP_NS);
-  PCB_LAUNCH(ctx, component_kernel, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, smem_bytes, c, n_comp, in.shard_rank,
-             in.shard_count, per_warp);
+  const char *mode = getenv("PCB_REPLAY");
+  if (mode && strcmp(mode, "thread") == 0) {
+    int per_warp = 4;
+    if (const char *e = getenv("PCB_COMP_PER_WARP")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) per_warp = v; }
+    size_t n_threads = ((size_t)n_comp + per_warp - 1) / per_warp * 32;
+    PCB_LAUNCH(ctx, component_kernel_thread, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_comp, in.shard_rank, in.shard_count,
+               per_warp);
+  } else {
+    PCB_LAUNCH(ctx, component_kernel_warp, grid_for((size_t)n_comp * 32, COMP_BLOCK), COMP_BLOCK, 0, c, n_comp, in.shard_rank,
+               in.shard_count);
+  }
   stage_end(ctx, PCB_STAT_T_REPLAY_NS);
   PCB_LAUNCH(ctx, scatter_outputs_kernel, grid_for(R, 256), 256, 0, R, old_of_new_r.p, old_of_new_b.p, t_root.p, t_pos.p, t_size.p,
              t_key.p, t_bc.p, t_up.p, t_calloff.p, t_calln.p, out);

@@ -30,8 +30,8 @@
 
 namespace pcb {
 
-struct GenoSlot {          // 32 bytes
-  int32_t key;             // mutation id (or barcode id when counting), -1 empty
+struct GenoSlot {          // 32 bytes; an all-zero slot is empty, so a memset(0) makes a table
+  int32_t key;             // mutation id (or barcode id when counting) PLUS ONE, 0 = empty
   int32_t obs1, obs2;      // #reads with Q>0 on each side / #reads carrying the key
   int32_t pad;
   int64_t sum1, sum2;      // sum of Q on each side
@@ -95,7 +95,7 @@ struct MergeState {
   GenoSlot *slots;
   int32_t slot_mask;
   int32_t *lists;
-  int64_t list_cap;          // lists holds 2 * list_cap ints
+  int64_t list_cap;          // lists holds 8 + 2 * list_cap ints
 };
 
 PCB_HD MergeState global_state(const MergeCtx &c, int32_t comp) {
@@ -106,7 +106,7 @@ PCB_HD MergeState global_state(const MergeCtx &c, int32_t comp) {
   s.slots = c.slots + c.scr_slot_off[comp];
   s.slot_mask = c.scr_slot_cap[comp] - 1;
   s.lists = c.lists + c.scr_list_off[comp];
-  s.list_cap = (c.scr_list_off[comp + 1] - c.scr_list_off[comp]) / 2;
+  s.list_cap = (c.scr_list_off[comp + 1] - c.scr_list_off[comp]) / 2 - 4;     // region = 8 + 2 * list_cap ints
   return s;
 }
 
@@ -167,9 +167,9 @@ PCB_HD GenoSlot *table_slot(Table &t, int32_t key) {
   uint32_t i = hash_i32(key, t.shift);
   for (;;) {
     GenoSlot *s = &t.slots[i];
-    if (s->key == key) return s;
-    if (s->key == -1) {
-      s->key = key; s->obs1 = s->obs2 = 0; s->sum1 = s->sum2 = 0;
+    if (s->key == key + 1) return s;
+    if (s->key == 0) {
+      s->key = key + 1;                          // the other fields of an empty slot are already zero
       t.touched[t.n_touched++] = (int32_t)i;
       return s;
     }
@@ -180,13 +180,16 @@ PCB_HD const GenoSlot *table_find(const Table &t, int32_t key) {
   uint32_t i = hash_i32(key, t.shift);
   for (;;) {
     const GenoSlot *s = &t.slots[i];
-    if (s->key == key) return s;
-    if (s->key == -1) return nullptr;
+    if (s->key == key + 1) return s;
+    if (s->key == 0) return nullptr;
     i = (i + 1) & (uint32_t)t.mask;
   }
 }
 PCB_HD void table_clear(Table &t) {
-  for (int32_t i = 0; i < t.n_touched; i++) t.slots[t.touched[i]].key = -1;
+  for (int32_t i = 0; i < t.n_touched; i++) {
+    GenoSlot *s = &t.slots[t.touched[i]];
+    s->key = 0; s->obs1 = s->obs2 = 0; s->sum1 = s->sum2 = 0;
+  }
   t.n_touched = 0;
 }
 
@@ -349,12 +352,12 @@ PCB_HD int32_t consensus_id(const MergeCtx &c, const MergeState &st, Table &tab,
   }
   for (int32_t r = head; r >= 0; r = st.rd_next[(r) - st.r0]) {
     int32_t id = ids[r];
-    if (id < 0) { *err = 1; id = 0x7fffffff; }
+    if (id < 0) { *err = 1; id = 0x7ffffffe; }
     table_slot(tab, id)->obs1++;
   }
   for (int32_t i = 0; i < tab.n_touched; i++) {
     const GenoSlot *s = &tab.slots[tab.touched[i]];
-    if (s->obs1 > bestCnt) { bestCnt = s->obs1; best = s->key; nTop = 1; }
+    if (s->obs1 > bestCnt) { bestCnt = s->obs1; best = s->key - 1; nTop = 1; }
     else if (s->obs1 == bestCnt) nTop++;
   }
   table_clear(tab);
@@ -435,7 +438,7 @@ PCB_HD void process_component(const MergeCtx &c, const MergeState &st, int32_t c
       for (int32_t i = 0; i < tab.n_touched; i++) {
         const GenoSlot *s = &tab.slots[tab.touched[i]];
         if (s->sum1 - (int64_t)c.prm.minQual * (int64_t)(size - s->obs1) > 0) {
-          int32_t v = s->key, k = n - 1;           // insertion sort by the (digit key, string) rank (:475)
+          int32_t v = s->key - 1, k = n - 1;       // insertion sort by the (digit key, string) rank (:475)
           while (k >= 0 && c.mut_rank[calls[k]] > c.mut_rank[v]) { calls[k + 1] = calls[k]; k--; }
           calls[k + 1] = v; n++;
         }

@@ -83,11 +83,11 @@ extern "C" int emul_merge(int32_t R, int32_t U, const int32_t *bucket_ptr, const
     int32_t cap = 2; while (cap < need) cap <<= 1;
     slot_cap[c] = cap;
     slot_off[c + 1] = slot_off[c] + cap;
-    list_off[c + 1] = list_off[c] + 2 * (reads + nnz);
+    list_off[c + 1] = list_off[c] + 2 * (reads + nnz) + 8;
     call_off[c + 1] = call_off[c] + nnz;
   }
   std::vector<GenoSlot> slots(slot_off[n_comp]);
-  for (auto &s : slots) s.key = -1;
+  memset(slots.data(), 0, slots.size() * sizeof(GenoSlot));
   std::vector<int32_t> lists(list_off[n_comp] + 1);
   std::vector<int32_t> rd_slot(R, -1), rd_next(R, -1), sl_parent(R, -1), sl_head(R, -1), sl_tail(R, -1), sl_size(R, 0);
   std::vector<int64_t> sl_key(R, -1);
