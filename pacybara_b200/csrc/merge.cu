@@ -213,17 +213,53 @@ __global__ void comp_scratch_kernel(const int32_t *__restrict__ comp_ptr, const 
 }
 
 // Two launch shapes for the replay (merge_core.h / merge_warp.cuh):
-//  * component_kernel_warp (default): one WARP per component, uniform control flow, lanes share the
-//    order-independent work.  Components are numbered heaviest first, so the long ones start first.
-//  * component_kernel_thread (PCB_REPLAY=thread): one THREAD per component running the host-testable
+//  * component_kernel_thread (default): one THREAD per component running the host-testable
 //    process_component().  Divergent lanes serialise, so only every (32 / per_warp)-th lane is used.
+//    Components are numbered heaviest first, so the long ones start first.
+//  * component_kernel_warp (PCB_REPLAY=warp): one WARP per component, uniform control flow, lanes share
+//    the order-independent work (merge_warp.cuh).  Measured on cfg 2 (r01f) it is instruction-fetch bound
+//    (6.7 k SASS instructions, no_instruction is the top stall) and slower than the thread kernel for the
+//    10-read components that dominate there; it is the shape that scales to components of thousands of reads.
 constexpr int COMP_BLOCK = 128;
 
+// Mutable working set of one small component in shared memory: cluster lists, union-find, scratch table,
+// lists.  Every read-modify-write of the replay then costs a shared-memory round trip (~30 cycles) instead
+// of an L2 one; at one component per warp this fits at full occupancy (8 blocks x 4 warps x 3.6 KB per SM).
+#ifndef PCB_SM_READS
+#define PCB_SM_READS 32
+#endif
+constexpr int SM_READS = PCB_SM_READS;
+constexpr int SM_SLOTS = 2 * SM_READS;
+static_assert((SM_SLOTS & (SM_SLOTS - 1)) == 0, "the scratch table size must be a power of two");
+struct __align__(16) CompSmem {
+  GenoSlot slots[SM_SLOTS];
+  int64_t sl_key[SM_READS];
+  int32_t lists[8 + 4 * SM_READS];
+  int32_t rd_slot[SM_READS], rd_next[SM_READS], sl_parent[SM_READS], sl_head[SM_READS], sl_tail[SM_READS], sl_size[SM_READS];
+};
+
 __global__ void __launch_bounds__(COMP_BLOCK) component_kernel_warp(MergeCtx c, int32_t n_comp, int32_t shard_rank, int32_t shard_count) {
+  __shared__ CompSmem sm_all[COMP_BLOCK / 32];
   const int32_t comp = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
   if (comp >= n_comp) return;
   if (comp % shard_count != shard_rank) return;
-  process_component_warp(c, global_state(c, comp), comp, threadIdx.x & 31);
+  const int32_t r_lo = c.bucket_ptr[c.comp_ptr[comp]];
+  const int32_t reads = c.bucket_ptr[c.comp_ptr[comp + 1]] - r_lo;
+  const int32_t nnz = c.geno_ptr[r_lo + reads] - c.geno_ptr[r_lo];
+  MergeState st = global_state(c, comp);
+  if (reads <= SM_READS && nnz <= SM_READS) {
+    CompSmem *sm = &sm_all[threadIdx.x >> 5];
+    for (int32_t i = lane; i < SM_SLOTS; i += 32) { GenoSlot z; z.key = 0; z.obs1 = z.obs2 = z.pad = 0; z.sum1 = z.sum2 = 0; sm->slots[i] = z; }
+    for (int32_t i = lane; i < reads; i += 32) { sm->rd_slot[i] = -1; sm->rd_next[i] = -1; }
+    __syncwarp();
+    st.r0 = r_lo;
+    st.rd_slot = sm->rd_slot; st.rd_next = sm->rd_next; st.sl_parent = sm->sl_parent; st.sl_head = sm->sl_head;
+    st.sl_tail = sm->sl_tail; st.sl_size = sm->sl_size; st.sl_key = sm->sl_key;
+    st.slots = sm->slots; st.slot_mask = SM_SLOTS - 1;
+    st.lists = sm->lists; st.list_cap = 2 * SM_READS;
+  }
+  process_component_warp(c, st, comp, lane);        // one call site: the same code runs on either memory
 }
 
 __global__ void __launch_bounds__(COMP_BLOCK) component_kernel_thread(MergeCtx c, int32_t n_comp, int32_t shard_rank, int32_t shard_count,
@@ -406,7 +442,7 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   c.prm.maxDiff = in.max_diff; c.prm.minQual = in.min_qual; c.prm.minMatches = in.min_matches; c.prm.minJaccard = in.min_jaccard;
   stage_end(ctx, PCB_STAT_T_PREP_NS);
   const char *mode = getenv("PCB_REPLAY");
-  if (mode && strcmp(mode, "thread") == 0) {
+  if (!(mode && strcmp(mode, "warp") == 0)) {
     int per_warp = 4;
     if (const char *e = getenv("PCB_COMP_PER_WARP")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) per_warp = v; }
     size_t n_threads = ((size_t)n_comp + per_warp - 1) / per_warp * 32;

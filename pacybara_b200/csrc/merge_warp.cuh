@@ -97,8 +97,29 @@ __device__ __forceinline__ void w_accumulate_side(const MergeCtx &c, const Merge
   __syncwarp();
 }
 
+// calcJaccard on presence over the kept mutations (:358-367) and the seed acceptance rule (:398); the table
+// holds the bucket-wide (#reads with Q>0, sum Q) per mutation that filterSeqError needs
+__device__ __noinline__ bool w_seed_pair_ok(const MergeCtx &c, const WTable &t, int32_t ri, int32_t rj) {
+  int32_t ni = 0, nj = 0, inters = 0;
+  for (int32_t e = c.geno_ptr[ri]; e < c.geno_ptr[ri + 1]; e++) {
+    if (c.geno_q[e] <= 0) continue;
+    const GenoSlot *s = w_table_find(t, c.geno_mut[e]);
+    if (!(s->obs1 > 1 || s->sum1 > c.prm.minQual)) continue;
+    ni++;
+    for (int32_t f = c.geno_ptr[rj]; f < c.geno_ptr[rj + 1]; f++)
+      if (c.geno_mut[f] == c.geno_mut[e]) { if (c.geno_q[f] > 0) inters++; break; }
+  }
+  for (int32_t f = c.geno_ptr[rj]; f < c.geno_ptr[rj + 1]; f++) {
+    if (c.geno_q[f] <= 0) continue;
+    const GenoSlot *s = w_table_find(t, c.geno_mut[f]);
+    if (s->obs1 > 1 || s->sum1 > c.prm.minQual) nj++;
+  }
+  const int32_t uni = ni + nj - inters;
+  return uni == 0 || ((double)inters / (double)uni > c.prm.minJaccard && inters >= c.prm.minMatches);
+}
+
 // SEED CLUSTERING of one bucket (:385-400)
-__device__ __forceinline__ void w_seed_bucket(const MergeCtx &c, const MergeState &st, const WTable &t, int32_t b, int lane) {
+__device__ __noinline__ void w_seed_bucket(const MergeCtx &c, const MergeState &st, const WTable &t, int32_t b, int lane) {
   const int32_t lo = c.bucket_ptr[b], n = c.bucket_ptr[b + 1] - lo;
   if (n < 2) return;
   const int32_t *rids = c.bucket_reads ? c.bucket_reads + lo : nullptr;
@@ -111,29 +132,28 @@ __device__ __forceinline__ void w_seed_bucket(const MergeCtx &c, const MergeStat
     const int32_t ri = PCB_RID(i);
     int32_t ci = -1;
     bool done = false;
-    for (int32_t j0 = 0; j0 < i && !done; j0 += 32) {
+    // Usual case: reads 0..i-1 already form one cluster and read i is compatible with read 0 -- then the row
+    // ends after its first pair.  Test that pair on its own (uniformly) before fanning the rest out.
+    int32_t j_first = 0;
+    {
+      const int32_t r0 = PCB_RID(0);
+      const int32_t c0 = w_cluster_of(st, r0);
+      if (c0 >= 0 && ((volatile int32_t *)st.sl_size)[c0 - st.r0] == i) {
+        if (w_seed_pair_ok(c, t, ri, r0)) {
+          if (lane == 0) add_link(c, st, ri, r0, -1);      // joins cluster c0 (no new cluster id), which then holds 0..i
+          __syncwarp();
+          continue;
+        }
+        j_first = 1;                                       // pair (i, 0) is done and was rejected
+      }
+    }
+    for (int32_t j0 = j_first; j0 < i && !done; j0 += 32) {
       const int32_t j = j0 + lane;
       const bool act = j < i;
       const int32_t rj = act ? PCB_RID(j) : -1;
       bool ok = false;
       if (act && !(ci >= 0 && w_cluster_of(st, rj) == ci)) {
-        // calcJaccard on presence over the kept mutations (:358-367)
-        int32_t ni = 0, nj = 0, inters = 0;
-        for (int32_t e = c.geno_ptr[ri]; e < c.geno_ptr[ri + 1]; e++) {
-          if (c.geno_q[e] <= 0) continue;
-          const GenoSlot *s = w_table_find(t, c.geno_mut[e]);
-          if (!(s->obs1 > 1 || s->sum1 > c.prm.minQual)) continue;
-          ni++;
-          for (int32_t f = c.geno_ptr[rj]; f < c.geno_ptr[rj + 1]; f++)
-            if (c.geno_mut[f] == c.geno_mut[e]) { if (c.geno_q[f] > 0) inters++; break; }
-        }
-        for (int32_t f = c.geno_ptr[rj]; f < c.geno_ptr[rj + 1]; f++) {
-          if (c.geno_q[f] <= 0) continue;
-          const GenoSlot *s = w_table_find(t, c.geno_mut[f]);
-          if (s->obs1 > 1 || s->sum1 > c.prm.minQual) nj++;
-        }
-        int32_t uni = ni + nj - inters;
-        ok = uni == 0 || ((double)inters / (double)uni > c.prm.minJaccard && inters >= c.prm.minMatches);
+        ok = w_seed_pair_ok(c, t, ri, rj);
       }
       uint32_t mask = __ballot_sync(PCB_FULL, ok);
       while (mask) {                                                 // apply in ascending j, as the reference does
@@ -158,7 +178,7 @@ __device__ __forceinline__ void w_seed_bucket(const MergeCtx &c, const MergeStat
 }
 
 // one visit of the main loop body (:419-455); uniform across the warp.  Returns 1 if linked.
-__device__ __forceinline__ int w_visit_pair(const MergeCtx &c, const MergeState &st, const WTable &t, int32_t *runs, int32_t rid1,
+__device__ __noinline__ int w_visit_pair(const MergeCtx &c, const MergeState &st, const WTable &t, int32_t *runs, int32_t rid1,
                                             int32_t rid2, int32_t ed, int32_t c1, int32_t c2, int32_t &cache_root, int lane) {
   const int32_t size1 = c1 >= 0 ? st.sl_size[c1 - st.r0] : 1, size2 = c2 >= 0 ? st.sl_size[c2 - st.r0] : 1;
   const int32_t mx = size1 > size2 ? size1 : size2, mn = size1 > size2 ? size2 : size1;
@@ -223,7 +243,7 @@ __device__ __forceinline__ int w_visit_pair(const MergeCtx &c, const MergeState 
 }
 
 // consensus of one id column over a member list (:515-532); uniform.
-__device__ __forceinline__ int32_t w_consensus_id(const MergeCtx &c, const MergeState &st, const WTable &t, const int32_t *ids,
+__device__ __noinline__ int32_t w_consensus_id(const MergeCtx &c, const MergeState &st, const WTable &t, const int32_t *ids,
                                                   int32_t head, int32_t size, int32_t *err, int lane) {
   const int32_t first = ids[head];
   bool same = first >= 0;
@@ -249,7 +269,7 @@ __device__ __forceinline__ int32_t w_consensus_id(const MergeCtx &c, const Merge
   return PCB_NEEDS_ALIGNMENT;
 }
 
-__device__ __forceinline__ void process_component_warp(const MergeCtx &c, const MergeState &st, int32_t comp, int lane) {
+__device__ __noinline__ void process_component_warp(const MergeCtx &c, const MergeState &st, int32_t comp, int lane) {
   WTable t;
   t.slots = st.slots; t.mask = st.slot_mask;
   { int32_t bits = 0; while ((1 << bits) <= st.slot_mask) bits++; t.shift = 32 - bits; }
