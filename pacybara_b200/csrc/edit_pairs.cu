@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(const ulonglong
                                                                   int32_t q_begin, int32_t q_end, SeedGeom g,
                                                                   const uint32_t *__restrict__ bin_off, const int32_t *__restrict__ ent,
                                                                   uint64_t *__restrict__ hit_key, uint32_t *__restrict__ hit_d,
-                                                                  unsigned long long cap, int key_shift, unsigned long long *counters) {
+                                                                  unsigned long long cap, int key_shift, unsigned long long *counters,
+                                                                  int32_t len_lo, int32_t len_hi) {
   __shared__ int2 queue[PROBE_WARPS][64];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lt_mask = (1u << lane) - 1u;
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(const ulonglong
       int32_t m = len[qi];
       int32_t st = g.q == 0 ? 0 : (int32_t)((int64_t)t * m / (g.k + 1));
       int32_t p = st + s;
-      if (p >= 0 && p < g.npos) {
+      if (p >= 0 && p < g.npos && m >= len_lo && m <= len_hi) {     // queries of other lengths use the other index
         ulonglong2 a = planes[qi];
         uint32_t bin = seed_bin(g, a.x, a.y, st, p);
         lo = bin_off[bin]; hi = bin_off[bin + 1];
@@ -178,6 +179,11 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(const ulonglong
     cells += __shfl_down_sync(0xFFFFFFFFu, cells, o);
   }
   if (lane == 0 && scored) { atomicAdd(&counters[1], scored); atomicAdd(&counters[2], cells); }
+}
+
+__global__ void len_hist_kernel(const int32_t *__restrict__ len, int32_t U, uint32_t *__restrict__ hist) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < U) atomicAdd(&hist[len[i]], 1u);        // lengths were validated to 1..64 when packing
 }
 
 __global__ void flag_unique_kernel(const uint64_t *__restrict__ key, size_t n, uint32_t *__restrict__ flag) {
@@ -217,30 +223,56 @@ void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q
   res.valid = true;
   if (U < 2 || q_begin == q_end) return;
 
-  SeedGeom g;
-  g.k = k;
-  g.q = bc.min_len / (k + 1);
-  if (g.q > 12) g.q = 12;
-  while (g.q > 0 && ((uint64_t)(bc.max_len - g.q + 1) << (2 * g.q)) > (1ull << 26)) g.q--;
-  g.npos = g.q == 0 ? 1 : bc.max_len - g.q + 1;
-  g.nbins = g.q == 0 ? 1u : (uint32_t)g.npos << (2 * g.q);
-  ctx->stats[PCB_STAT_SEED_LEN] = g.q;
-
-  // ---- index
-  DevBuf<uint32_t> bin_off(ctx, (size_t)g.nbins + 1), cursor(ctx, (size_t)g.nbins + 1);
-  DevBuf<int32_t> ent(ctx, (size_t)U * g.npos);
-  PCB_CUDA(cudaMemsetAsync(bin_off.p, 0, ((size_t)g.nbins + 1) * sizeof(uint32_t), ctx->stream));
-  size_t n_slots = (size_t)U * g.npos;
-  PCB_LAUNCH(ctx, seed_count_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, U, g, bin_off.p);
-  exclusive_scan_u32(ctx, bin_off.p, bin_off.p, (size_t)g.nbins + 1);
-  PCB_CUDA(cudaMemcpyAsync(cursor.p, bin_off.p, ((size_t)g.nbins + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-  PCB_LAUNCH(ctx, seed_fill_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, U, g, cursor.p, ent.p);
+  // ---- seed lengths.  A query of length m splits into k+1 pieces of at least floor(m/(k+1)) bases, so it can
+  // probe an index of q-grams with q up to that.  Most barcodes share one length; the few shorter ones (deletions)
+  // would force the short q on everybody, so there are up to two indexes over all targets: q_hi for the queries
+  // long enough for it, q_lo for the rest.  Either way every pair is found through its query side.
+  DevBuf<uint32_t> d_hist(ctx, 66);
+  PCB_CUDA(cudaMemsetAsync(d_hist.p, 0, 66 * sizeof(uint32_t), ctx->stream));
+  PCB_LAUNCH(ctx, len_hist_kernel, grid_for(U, 256), 256, 0, bc.len.p, U, d_hist.p);
+  uint32_t h_hist[66];
+  PCB_CUDA(cudaMemcpyAsync(h_hist, d_hist.p, sizeof(h_hist), cudaMemcpyDeviceToHost, ctx->stream));
+  PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  int32_t mode_len = bc.min_len;
+  for (int32_t l = 1; l <= 64; l++) if (h_hist[l] > h_hist[mode_len]) mode_len = l;
+  auto make_geom = [&](int32_t q) {
+    SeedGeom g;
+    g.k = k;
+    g.q = q > 12 ? 12 : q;
+    while (g.q > 0 && ((uint64_t)(bc.max_len - g.q + 1) << (2 * g.q)) > (1ull << 26)) g.q--;
+    g.npos = g.q == 0 ? 1 : bc.max_len - g.q + 1;
+    g.nbins = g.q == 0 ? 1u : (uint32_t)g.npos << (2 * g.q);
+    return g;
+  };
+  struct SeedIndex { SeedGeom g; DevBuf<uint32_t> bin_off; DevBuf<int32_t> ent; int32_t len_lo, len_hi; };
+  SeedIndex idx[2];
+  int n_idx = 1;
+  idx[0].g = make_geom(mode_len / (k + 1));
+  idx[0].len_lo = idx[0].g.q * (k + 1); idx[0].len_hi = 64;
+  if (bc.min_len < idx[0].len_lo) {
+    idx[1].g = make_geom(bc.min_len / (k + 1));
+    idx[1].len_lo = 0; idx[1].len_hi = idx[0].len_lo - 1;
+    if (idx[1].g.q == idx[0].g.q) idx[0].len_lo = 0; else n_idx = 2;
+  } else {
+    idx[0].len_lo = 0;
+  }
+  ctx->stats[PCB_STAT_SEED_LEN] = idx[0].g.q;
+  for (int t = 0; t < n_idx; t++) {
+    const SeedGeom &g = idx[t].g;
+    DevBuf<uint32_t> cursor(ctx, (size_t)g.nbins + 1);
+    idx[t].bin_off.alloc(ctx, (size_t)g.nbins + 1);
+    idx[t].ent.alloc(ctx, (size_t)U * g.npos);
+    PCB_CUDA(cudaMemsetAsync(idx[t].bin_off.p, 0, ((size_t)g.nbins + 1) * sizeof(uint32_t), ctx->stream));
+    size_t n_slots = (size_t)U * g.npos;
+    PCB_LAUNCH(ctx, seed_count_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, U, g, idx[t].bin_off.p);
+    exclusive_scan_u32(ctx, idx[t].bin_off.p, idx[t].bin_off.p, (size_t)g.nbins + 1);
+    PCB_CUDA(cudaMemcpyAsync(cursor.p, idx[t].bin_off.p, ((size_t)g.nbins + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    PCB_LAUNCH(ctx, seed_fill_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, U, g, cursor.p, idx[t].ent.p);
+  }
 
   stage_end(ctx, PCB_STAT_T_INDEX_NS);
   // ---- probe (re-run with a larger hit buffer if the first guess overflows)
   const int key_shift = bits_for((uint64_t)(U - 1));
-  const int per_query = g.q == 0 ? 1 : (k + 1) * (2 * k + 1);
-  size_t n_probe = (size_t)(q_end - q_begin) * per_query;
   unsigned long long cap = 8ull * (unsigned long long)(q_end - q_begin) + (1ull << 16);
   DevBuf<unsigned long long> counters(ctx, 4);
   DevBuf<uint64_t> hk0, hk1;
@@ -251,16 +283,22 @@ void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q
     hk0.alloc(ctx, cap); hv0.alloc(ctx, cap);
     PCB_CUDA(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
     PCB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-    // persistent grid: a multiple of the SM count, blocks of probes handed out by counters[3]
-    unsigned n_cta = (unsigned)ctx->sm_count * 8u;
-    unsigned need = grid_for((n_probe + 31) / 32, PROBE_WARPS);
-    if (need < n_cta) n_cta = need;
-    if (wide)
-      PCB_LAUNCH(ctx, probe_kernel<true>, n_cta, PROBE_WARPS * 32, 0, bc.planes.p, bc.len.p, q_begin, q_end, g,
-                 bin_off.p, ent.p, hk0.p, hv0.p, cap, key_shift, counters.p);
-    else
-      PCB_LAUNCH(ctx, probe_kernel<false>, n_cta, PROBE_WARPS * 32, 0, bc.planes.p, bc.len.p, q_begin, q_end, g,
-                 bin_off.p, ent.p, hk0.p, hv0.p, cap, key_shift, counters.p);
+    for (int t = 0; t < n_idx; t++) {
+      const SeedGeom &g = idx[t].g;
+      const int per_query = g.q == 0 ? 1 : (k + 1) * (2 * k + 1);
+      size_t n_probe = (size_t)(q_end - q_begin) * per_query;
+      // persistent grid: a multiple of the SM count, blocks of probes handed out by counters[3]
+      unsigned n_cta = (unsigned)ctx->sm_count * 8u;
+      unsigned need = grid_for((n_probe + 31) / 32, PROBE_WARPS);
+      if (need < n_cta) n_cta = need;
+      if (t > 0) PCB_CUDA(cudaMemsetAsync(counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
+      if (wide)
+        PCB_LAUNCH(ctx, probe_kernel<true>, n_cta, PROBE_WARPS * 32, 0, bc.planes.p, bc.len.p, q_begin, q_end, g,
+                   idx[t].bin_off.p, idx[t].ent.p, hk0.p, hv0.p, cap, key_shift, counters.p, idx[t].len_lo, idx[t].len_hi);
+      else
+        PCB_LAUNCH(ctx, probe_kernel<false>, n_cta, PROBE_WARPS * 32, 0, bc.planes.p, bc.len.p, q_begin, q_end, g,
+                   idx[t].bin_off.p, idx[t].ent.p, hk0.p, hv0.p, cap, key_shift, counters.p, idx[t].len_lo, idx[t].len_hi);
+    }
     PCB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     PCB_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));
     PCB_CUDA(cudaStreamSynchronize(ctx->stream));

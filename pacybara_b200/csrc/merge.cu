@@ -213,13 +213,14 @@ __global__ void comp_scratch_kernel(const int32_t *__restrict__ comp_ptr, const 
 }
 
 // Two launch shapes for the replay (merge_core.h / merge_warp.cuh):
-//  * component_kernel_thread (default): one THREAD per component running the host-testable
+//  * component_kernel_thread: one THREAD per component running the host-testable
 //    process_component().  Divergent lanes serialise, so only every (32 / per_warp)-th lane is used.
 //    Components are numbered heaviest first, so the long ones start first.
-//  * component_kernel_warp (PCB_REPLAY=warp): one WARP per component, uniform control flow, lanes share
-//    the order-independent work (merge_warp.cuh).  Measured on cfg 2 (r01f) it is instruction-fetch bound
-//    (6.7 k SASS instructions, no_instruction is the top stall) and slower than the thread kernel for the
-//    10-read components that dominate there; it is the shape that scales to components of thousands of reads.
+//  * component_kernel_warp: one WARP per component, uniform control flow, lanes share the order-independent
+//    work (merge_warp.cuh), mutable state of small components in shared memory.  Instruction-fetch bound
+//    (5.3 k SASS instructions, no_instruction is the top stall in profiles/r01f), so it loses to the thread
+//    kernel on the 10-read components of cfg 2 and wins wherever components carry more work.
+// merge_dev() picks by mean bucket size; PCB_REPLAY=thread|warp overrides.
 constexpr int COMP_BLOCK = 128;
 
 // Mutable working set of one small component in shared memory: cluster lists, union-find, scratch table,
@@ -441,8 +442,14 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   c.call_mut = out.call_mut; c.status = status.p;
   c.prm.maxDiff = in.max_diff; c.prm.minQual = in.min_qual; c.prm.minMatches = in.min_matches; c.prm.minJaccard = in.min_jaccard;
   stage_end(ctx, PCB_STAT_T_PREP_NS);
+  // Which launch shape: measured (profiles/r01_replay_shapes.md) the thread kernel wins when buckets are small
+  // (cfg 2: 5 reads per bucket, 1.55 vs 2.65 ms), the warp kernel when reads concentrate in big buckets (cfg 4:
+  // 8 reads per bucket, 1.1 vs 4.6 ms) -- and it is the only shape that copes with components of thousands of reads.
   const char *mode = getenv("PCB_REPLAY");
-  if (!(mode && strcmp(mode, "warp") == 0)) {
+  bool use_warp = (double)R / (double)U >= 7.0;
+  if (mode && strcmp(mode, "warp") == 0) use_warp = true;
+  if (mode && strcmp(mode, "thread") == 0) use_warp = false;
+  if (!use_warp) {
     int per_warp = 4;
     if (const char *e = getenv("PCB_COMP_PER_WARP")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) per_warp = v; }
     size_t n_threads = ((size_t)n_comp + per_warp - 1) / per_warp * 32;

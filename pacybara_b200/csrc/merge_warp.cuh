@@ -119,7 +119,7 @@ __device__ __noinline__ bool w_seed_pair_ok(const MergeCtx &c, const WTable &t, 
 }
 
 // SEED CLUSTERING of one bucket (:385-400)
-__device__ __noinline__ void w_seed_bucket(const MergeCtx &c, const MergeState &st, const WTable &t, int32_t b, int lane) {
+__device__ __forceinline__ void w_seed_bucket(const MergeCtx &c, const MergeState &st, const WTable &t, int32_t b, int lane) {
   const int32_t lo = c.bucket_ptr[b], n = c.bucket_ptr[b + 1] - lo;
   if (n < 2) return;
   const int32_t *rids = c.bucket_reads ? c.bucket_reads + lo : nullptr;
@@ -178,7 +178,7 @@ __device__ __noinline__ void w_seed_bucket(const MergeCtx &c, const MergeState &
 }
 
 // one visit of the main loop body (:419-455); uniform across the warp.  Returns 1 if linked.
-__device__ __noinline__ int w_visit_pair(const MergeCtx &c, const MergeState &st, const WTable &t, int32_t *runs, int32_t rid1,
+__device__ __forceinline__ int w_visit_pair(const MergeCtx &c, const MergeState &st, const WTable &t, int32_t *runs, int32_t rid1,
                                             int32_t rid2, int32_t ed, int32_t c1, int32_t c2, int32_t &cache_root, int lane) {
   const int32_t size1 = c1 >= 0 ? st.sl_size[c1 - st.r0] : 1, size2 = c2 >= 0 ? st.sl_size[c2 - st.r0] : 1;
   const int32_t mx = size1 > size2 ? size1 : size2, mn = size1 > size2 ? size2 : size1;
@@ -269,7 +269,7 @@ __device__ __noinline__ int32_t w_consensus_id(const MergeCtx &c, const MergeSta
   return PCB_NEEDS_ALIGNMENT;
 }
 
-__device__ __noinline__ void process_component_warp(const MergeCtx &c, const MergeState &st, int32_t comp, int lane) {
+__device__ __forceinline__ void process_component_warp(const MergeCtx &c, const MergeState &st, int32_t comp, int lane) {
   WTable t;
   t.slots = st.slots; t.mask = st.slot_mask;
   { int32_t bits = 0; while ((1 << bits) <= st.slot_mask) bits++; t.shift = 32 - bits; }
