@@ -240,7 +240,7 @@ def main():
     launches = ctx.stat("kernel_launches") - launches0
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     stats = ctx.stats()
-    stage_ms = {k.replace("t_", "").replace("_ns", ""): statistics.mean(v) for k, v in stage_acc.items()}
+    stage_ms = {(k[2:] if k.startswith("t_") else k)[:-3]: statistics.mean(v) for k, v in stage_acc.items()}
     # e2e: same call, pinned host inputs, host outputs
     timed(pinned, False, 1)
     e2e_ms, _, out_h = timed(pinned, False, args.steps)
@@ -270,10 +270,26 @@ def main():
     kk = (2 if args.full_table else 1) * params["max_diff"]
     per_query = (kk + 1) * (2 * kk + 1)
     algo_bytes = U * per_query * 20 + pairs * 24 + E * 12
-    roof = dict(bound="hbm", achieved=algo_bytes / probe_s / 1e9, peak=hbm_peak, unit="GB/s",
-                frac=algo_bytes / probe_s / 1e9 / hbm_peak, traffic=None, kernel="probe_kernel<false>",
+    roof_probe = dict(bound="hbm", achieved=algo_bytes / probe_s / 1e9, peak=hbm_peak, unit="GB/s",
+                      frac=algo_bytes / probe_s / 1e9 / hbm_peak, traffic=None, kernel="probe_kernel<false>",
+                      note="integer-ALU bound kernel: the HBM fraction is small by construction, see roofline_alu")
+    # the kernel that takes the largest share of the step: the per-component replay (merge.cu).  Algorithmic bytes
+    # (DESIGN.md 4.4): per read 16 B of inputs (lexrank, barcode id, bucket, genotype offset) + 28 B of cluster state
+    # written and read back + 12 B of per-read outputs; 8 B per genotype entry; 32 B per output row; 4 B per call.
+    replay_s = stage_ms.get("replay", 0.0) * 1e-3
+    if replay_s <= 0:                       # sharded runs call the stages one by one: no fused stage clock
+        replay_s = float("nan")
+    n_rows = int((np.asarray(out["row_size"].cpu() if hasattr(out["row_size"], "cpu") else out["row_size"]) > 0).sum())
+    nnz = int(ra.geno_mut.shape[0])
+    replay_bytes = R * (16 + 2 * 28 + 12) + nnz * 8 + n_rows * 32 + nnz * 4
+    roof = dict(bound="hbm", achieved=replay_bytes / replay_s / 1e9, peak=hbm_peak, unit="GB/s",
+                frac=replay_bytes / replay_s / 1e9 / hbm_peak, traffic=91.5e6 if args.config == "cfg2" and world == 1 else None,
+                kernel="component_kernel_thread" if R / max(U, 1) < 7 else "component_kernel_warp", ms=replay_s * 1e3,
+                share_of_step=replay_s * 1e3 / ms_per_step,
                 peak_source="measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback",
-                note="integer-ALU bound kernel: the HBM fraction is small by construction, see roofline_alu")
+                note="latency-bound sequential replay of the reference's greedy merge, one thread (or warp) per connected "
+                     "component: DRAM traffic ~ algorithmic bytes (ncu r01e: 72 MB read + 19 MB written), the time goes to "
+                     "dependent loads (long_scoreboard / wait stalls), not to bandwidth; traffic = ncu dram bytes at cfg 2")
     alu = None
     try:
         al = C.CDLL(os.path.join(ROOT, "bench_aux", "_alu_peak.so"))
@@ -303,7 +319,7 @@ def main():
                             l2="flushed between steps (512 MiB write)", parallelism=f"query-shard x{world}" if world > 1 else "1 GPU"),
                 e2e=dict(value=R / (e2e_ms / args.steps * 1e-3), unit="reads/s", h2d_bytes_per_step=h2d_bytes,
                          d2h_bytes_per_step=d2h_bytes, ms_per_step=e2e_ms / args.steps),
-                gpu_launches=launches, clocks=clocks, roofline=roof, roofline_alu=alu,
+                gpu_launches=launches, clocks=clocks, roofline=roof, roofline_probe=roof_probe, roofline_alu=alu,
                 edit_distance_gcups=(cells / probe_s / 1e9) if probe_s == probe_s else None,
                 kernel_ms=dict(probe=probe_s * 1e3), stage_ms=stage_ms)
     if world == 1 and not args.no_cpu_baseline:

@@ -90,5 +90,18 @@ def cluster_reads_sharded(ctx: Context, arrs: Dict, params: Dict, rank: int, wor
     out["n_edges"] = int(ei.numel())
     out["local_stats"] = local_stats
     if not on_device:
-        out = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}
+        # results to page-locked host buffers (reused by the next call, like Context(pinned_outputs=True))
+        host = {}
+        for k, v in out.items():
+            if hasattr(v, "is_cuda") and v.is_cuda:
+                key = ("mg_" + k, tuple(v.shape), str(v.dtype))
+                buf = ctx._pinned.get(key)
+                if buf is None:
+                    buf = ctx._pinned[key] = torch.empty(v.shape, dtype=v.dtype).pin_memory()
+                buf.copy_(v, non_blocking=True)
+                host[k] = buf
+            else:
+                host[k] = v
+        torch.cuda.current_stream(ctx.device).synchronize()
+        out = {k: (v.numpy() if hasattr(v, "numpy") and not isinstance(v, (int, dict)) else v) for k, v in host.items()}
     return out
