@@ -182,8 +182,13 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(const ulonglong
 }
 
 __global__ void len_hist_kernel(const int32_t *__restrict__ len, int32_t U, uint32_t *__restrict__ hist) {
-  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < U) atomicAdd(&hist[len[i]], 1u);        // lengths were validated to 1..64 when packing
+  __shared__ uint32_t sh[66];
+  if (threadIdx.x < 66) sh[threadIdx.x] = 0;
+  __syncthreads();
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < U; i += gridDim.x * blockDim.x)
+    atomicAdd(&sh[len[i]], 1u);                   // lengths were validated to 1..64 when packing
+  __syncthreads();
+  if (threadIdx.x < 66 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
 __global__ void flag_unique_kernel(const uint64_t *__restrict__ key, size_t n, uint32_t *__restrict__ flag) {
@@ -229,7 +234,7 @@ void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q
   // long enough for it, q_lo for the rest.  Either way every pair is found through its query side.
   DevBuf<uint32_t> d_hist(ctx, 66);
   PCB_CUDA(cudaMemsetAsync(d_hist.p, 0, 66 * sizeof(uint32_t), ctx->stream));
-  PCB_LAUNCH(ctx, len_hist_kernel, grid_for(U, 256), 256, 0, bc.len.p, U, d_hist.p);
+  PCB_LAUNCH(ctx, len_hist_kernel, (unsigned)ctx->sm_count, 256, 0, bc.len.p, U, d_hist.p);
   uint32_t h_hist[66];
   PCB_CUDA(cudaMemcpyAsync(h_hist, d_hist.p, sizeof(h_hist), cudaMemcpyDeviceToHost, ctx->stream));
   PCB_CUDA(cudaStreamSynchronize(ctx->stream));

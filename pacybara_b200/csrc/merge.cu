@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(COMP_BLOCK) component_kernel_warp(MergeCtx c, 
   process_component_warp(c, st, comp, lane);        // one call site: the same code runs on either memory
 }
 
+template <int PHASE>
 __global__ void __launch_bounds__(COMP_BLOCK) component_kernel_thread(MergeCtx c, int32_t n_comp, int32_t shard_rank, int32_t shard_count,
                                                                       int32_t per_warp) {
   const int32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -271,7 +272,10 @@ __global__ void __launch_bounds__(COMP_BLOCK) component_kernel_thread(MergeCtx c
   const int32_t comp = (tid >> 5) * per_warp + (tid & 31) / stride;
   if (comp >= n_comp) return;
   if (comp % shard_count != shard_rank) return;
-  process_component(c, global_state(c, comp), comp);
+  const MergeState st = global_state(c, comp);
+  if (PHASE == 1) component_seed(c, st, comp);
+  if (PHASE == 2) component_main(c, st, comp);
+  if (PHASE == 3) component_consensus(c, st, comp);
 }
 
 __global__ void init_outputs_kernel(int32_t R, int64_t nnz, int32_t *t_root, int32_t *t_pos, int32_t *t_size, int64_t *t_key,
@@ -453,8 +457,13 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
     int per_warp = 4;
     if (const char *e = getenv("PCB_COMP_PER_WARP")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) per_warp = v; }
     size_t n_threads = ((size_t)n_comp + per_warp - 1) / per_warp * 32;
-    PCB_LAUNCH(ctx, component_kernel_thread, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_comp, in.shard_rank, in.shard_count,
-               per_warp);
+    // three launches, one per phase: each kernel's code fits the instruction cache and its threads share a loop nest
+    PCB_LAUNCH(ctx, component_kernel_thread<1>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_comp, in.shard_rank,
+               in.shard_count, per_warp);
+    PCB_LAUNCH(ctx, component_kernel_thread<2>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_comp, in.shard_rank,
+               in.shard_count, per_warp);
+    PCB_LAUNCH(ctx, component_kernel_thread<3>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_comp, in.shard_rank,
+               in.shard_count, per_warp);
   } else {
     PCB_LAUNCH(ctx, component_kernel_warp, grid_for((size_t)n_comp * 32, COMP_BLOCK), COMP_BLOCK, 0, c, n_comp, in.shard_rank,
                in.shard_count);

@@ -366,16 +366,24 @@ PCB_HD int32_t consensus_id(const MergeCtx &c, const MergeState &st, Table &tab,
   return PCB_NEEDS_ALIGNMENT;
 }
 
-PCB_HD void process_component(const MergeCtx &c, const MergeState &st, int32_t comp) {
+// The replay of one component in three phases.  They only communicate through the cluster state (MergeState),
+// so they can run back to back in one thread (process_component, host emulation) or as three kernels whose
+// code each fits the instruction cache and whose threads are all in the same loop nest (merge.cu).
+
+// ---- phase 1: seed clustering, bucket by bucket
+PCB_HD void component_seed(const MergeCtx &c, const MergeState &st, int32_t comp) {
   Table tab;
   table_init(tab, st.slots, st.slot_mask, st.lists);     // lists: first half touched slots, second half bucket runs
-  int32_t *runs = st.lists + st.list_cap;
   int32_t b_lo = c.comp_ptr[comp], b_hi = c.comp_ptr[comp + 1];
-
-  // ---- seed clustering, bucket by bucket
   for (int32_t bi = b_lo; bi < b_hi; bi++) seed_bucket(c, st, c.comp_buckets ? c.comp_buckets[bi] : bi, tab);
+}
 
-  // ---- main clustering: the component's rows, pass by pass, in visiting order
+// ---- phase 2: main clustering: the component's rows, pass by pass, in visiting order
+PCB_HD void component_main(const MergeCtx &c, const MergeState &st, int32_t comp) {
+  if (c.cpair_ptr[comp] == c.cpair_ptr[comp + 1]) return;
+  Table tab;
+  table_init(tab, st.slots, st.slot_mask, st.lists);
+  int32_t *runs = st.lists + st.list_cap;
   int32_t n_links = 0, n_tests = 0, cache_root = -1;
   int32_t memo_a[4], memo_b[4], memo_n = 0, memo_w = 0;
   for (int32_t p = c.cpair_ptr[comp]; p < c.cpair_ptr[comp + 1]; p++) {
@@ -400,8 +408,20 @@ PCB_HD void process_component(const MergeCtx &c, const MergeState &st, int32_t c
     memo_n = 0; memo_w = 0;   // ids of a failed pair are only compared within one row
   }
 
-  // ---- consensus + rows (:464-477, :515-537, :546-567)
   table_clear(tab);                                    // drop whatever the main loop left cached
+#if defined(__CUDA_ARCH__)
+  if (n_links) atomicAdd(&c.status[2], n_links);
+  if (n_tests) atomicAdd(&c.status[3], n_tests);
+#else
+  c.status[2] += n_links; c.status[3] += n_tests;
+#endif
+}
+
+// ---- phase 3: consensus + rows (:464-477, :515-537, :546-567)
+PCB_HD void component_consensus(const MergeCtx &c, const MergeState &st, int32_t comp) {
+  Table tab;
+  table_init(tab, st.slots, st.slot_mask, st.lists);
+  int32_t b_lo = c.comp_ptr[comp], b_hi = c.comp_ptr[comp + 1];
   int64_t call_pos = c.call_off[comp];
   int32_t err = 0;
   for (int32_t bi = b_lo; bi < b_hi; bi++) {
@@ -451,12 +471,12 @@ PCB_HD void process_component(const MergeCtx &c, const MergeState &st, int32_t c
       if (uerr) { c.status[0] = 3; c.status[1] = head; }     // clustered read without uptag: KeyError in the reference
     }
   }
-#if defined(__CUDA_ARCH__)
-  if (n_links) atomicAdd(&c.status[2], n_links);
-  if (n_tests) atomicAdd(&c.status[3], n_tests);
-#else
-  c.status[2] += n_links; c.status[3] += n_tests;
-#endif
+}
+
+PCB_HD void process_component(const MergeCtx &c, const MergeState &st, int32_t comp) {
+  component_seed(c, st, comp);
+  component_main(c, st, comp);
+  component_consensus(c, st, comp);
 }
 
 }  // namespace pcb
