@@ -15,12 +15,19 @@ template <typename T>
 struct InArr {
   const T *p = nullptr;
   DevBuf<T> own;
-  InArr(pcb_ctx *ctx, int mem, const T *src, size_t n) {
+  const T *src_ = nullptr;
+  size_t n_ = 0;
+  // late = true: allocate now (on the main stream) but leave the copy to copy_late()
+  InArr(pcb_ctx *ctx, int mem, const T *src, size_t n, bool late = false) {
     if (!src) return;
     if (mem == PCB_MEM_DEVICE) { p = src; return; }
     own.alloc(ctx, n);
-    if (n) PCB_CUDA(cudaMemcpyAsync(own.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
     p = own.p;
+    if (late) { src_ = src; n_ = n; return; }
+    if (n) PCB_CUDA(cudaMemcpyAsync(own.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  void copy_late(cudaStream_t s) {
+    if (src_ && n_) PCB_CUDA(cudaMemcpyAsync(own.p, src_, n_ * sizeof(T), cudaMemcpyHostToDevice, s));
   }
 };
 
@@ -52,11 +59,13 @@ int guarded(pcb_ctx *ctx, F f) {
     return PCB_OK;
   } catch (const Error &e) {
     ctx->err = e.what();
+    cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->stream);
     cudaGetLastError();
     return e.code;
   } catch (const std::exception &e) {
     ctx->err = e.what();
+    cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->stream);
     return PCB_E_CUDA;
   }
@@ -106,6 +115,9 @@ int pcb_ctx_create(int device, pcb_ctx **out) {
     ctx->device = device;
     PCB_CUDA(cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device));
     PCB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    PCB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    PCB_CUDA(cudaEventCreateWithFlags(&ctx->ev_alloc, cudaEventDisableTiming));
+    PCB_CUDA(cudaEventCreateWithFlags(&ctx->ev_copied, cudaEventDisableTiming));
     PCB_CUDA(cudaEventCreate(&ctx->ev0));
     PCB_CUDA(cudaEventCreate(&ctx->ev1));
     for (int k = 0; k < 8; k++) PCB_CUDA(cudaEventCreate(&ctx->stage_ev[k]));
@@ -133,6 +145,9 @@ void pcb_ctx_destroy(pcb_ctx *ctx) {
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   for (int k = 0; k < 8; k++) if (ctx->stage_ev[k]) cudaEventDestroy(ctx->stage_ev[k]);
+  if (ctx->ev_alloc) cudaEventDestroy(ctx->ev_alloc);
+  if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
+  if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -267,9 +282,18 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
     size_t cells = (size_t)R * stride;
     (void)qual;   // qualities only feed the per-bucket sums of pcb_bucket; the clustering never reads them
     InArr<uint8_t> d_seq(ctx, mem, seq, cells);
-    InArr<int32_t> d_len(ctx, mem, len, R), d_lex(ctx, mem, lexrank, R), d_up(ctx, mem, up_id, R),
-        d_gptr(ctx, mem, geno_ptr, (size_t)R + 1), d_gmut(ctx, mem, geno_mut, nnz), d_gq(ctx, mem, geno_q, nnz),
-        d_rank(ctx, mem, mut_rank, n_mut);
+    InArr<int32_t> d_len(ctx, mem, len, R);
+    // what only the merge reads is copied on a second stream while bucketing and the pair search run
+    InArr<int32_t> d_lex(ctx, mem, lexrank, R, true), d_up(ctx, mem, up_id, R, true),
+        d_gptr(ctx, mem, geno_ptr, (size_t)R + 1, true), d_gmut(ctx, mem, geno_mut, nnz, true), d_gq(ctx, mem, geno_q, nnz, true),
+        d_rank(ctx, mem, mut_rank, n_mut, true);
+    if (mem == PCB_MEM_HOST) {
+      PCB_CUDA(cudaEventRecord(ctx->ev_alloc, ctx->stream));                  // the buffers exist from here on
+      PCB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_alloc, 0));
+      d_lex.copy_late(ctx->copy_stream); d_up.copy_late(ctx->copy_stream); d_gptr.copy_late(ctx->copy_stream);
+      d_gmut.copy_late(ctx->copy_stream); d_gq.copy_late(ctx->copy_stream); d_rank.copy_late(ctx->copy_stream);
+      PCB_CUDA(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+    }
     OutArr<int32_t> o_bor(ctx, mem, bucket_of_read, R), o_root(ctx, mem, read_root, R), o_pos(ctx, mem, read_pos, R),
         o_size(ctx, mem, row_size, R), o_bc(ctx, mem, row_bc, R), o_up(ctx, mem, row_up, R),
         o_calln(ctx, mem, row_call_n, R), o_call(ctx, mem, call_mut, nnz);
@@ -292,6 +316,7 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
     if (n_edges) *n_edges = E;
     DevBuf<int32_t> ped(ctx, (size_t)E);
     if (E) PCB_LAUNCH(ctx, pairs_from_edges_kernel, grid_for(E, 256), 256, 0, ctx->edges.ed, E, max_diff, ped.p);
+    if (mem == PCB_MEM_HOST) PCB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
     // a4..a13: merge; the barcode id of a read is its bucket
     MergeIn in{R, U, n_mut, bptr.p, breads.p, d_lex.p, bor, d_up.p, d_gptr.p, d_gmut.p, d_gq.p, d_rank.p,
                E, ctx->edges.ei, ctx->edges.ej, ctx->edges.ed, ped.p, max_diff, min_qual, min_matches, min_jaccard, 0, 1};

@@ -37,6 +37,8 @@ struct pcb_ctx {
   int device = 0;
   int sm_count = 148;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;      // host -> device copies that overlap the first stages (abi.cu)
+  cudaEvent_t ev_alloc = nullptr, ev_copied = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t stage_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   int stage_id[8] = {0};      // stat index the interval ENDING at mark k is charged to

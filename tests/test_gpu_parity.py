@@ -3,6 +3,7 @@
 Bit-exact is the bar everywhere (integer and index work; the one float compare is the same
 IEEE fp64 divide the reference does)."""
 import io
+import os
 
 import numpy as np
 import pytest
@@ -278,3 +279,61 @@ def test_fused_cfg2_full_size_properties(ctx):
     # most clones come back as one dominant cluster
     top = rows.row_members[rows.row_ptr[:-1]]
     assert rows.n_clusters > 0.9 * lib.params["n_clones"]
+
+
+# ----------------------------------------------------------------------------- many small random libraries
+def _rows_equal(a, b):
+    for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+
+
+@pytest.mark.parametrize("shape", ["thread", "warp"])
+def test_many_small_random_libraries_both_replay_shapes(ctx, shape, monkeypatch):
+    """120 tiny libraries with extreme settings (dense neighbours, collisions, short barcodes, d = 1..3,
+    minMatches 1..3, minJaccard 0.1..0.9, low/high minQual, skewed clone sizes): the fused path must give the
+    oracle's rows exactly -- row order, member order, consensus -- with either replay kernel."""
+    from oracle import orc
+    from pacybara_b200 import pipeline
+    monkeypatch.setenv("PCB_REPLAY", shape)
+    rng = np.random.default_rng(2024)
+    n_alignment = 0
+    for case in range(120):
+        kw = dict(n_clones=int(rng.integers(1, 40)), n_reads=int(rng.integers(1, 400)), bc_len=int(rng.choice([8, 12, 25])),
+                  p_err=float(rng.choice([0.0, 0.01, 0.05])), p_near=float(rng.choice([0.0, 0.3, 0.8])),
+                  p_collide=float(rng.choice([0.0, 0.3])), p_private=float(rng.choice([0.0, 0.15, 0.6])),
+                  p_private_hq=float(rng.choice([0.0, 0.2])), p_dropout=float(rng.choice([0.0, 0.3])),
+                  skew=float(rng.choice([0.0, 1.5])), seed=1000 + case, id_style=str(rng.choice(["padded", "plain"])))
+        params = dict(max_diff=int(rng.integers(0, 4)), min_qual=int(rng.choice([5, 32, 60])),
+                      min_jaccard=float(rng.choice([0.1, 0.2, 0.5, 0.9])), min_matches=int(rng.integers(1, 4)))
+        lib = synth.make_library(**kw)
+        ra, names = pipeline.arrays_from_library(lib, ctx)
+        reads = hostdata.FastqReads(names["ids"], lib.seq, lib.qual, lib.length)
+        b = util.oracle_buckets(reads)
+        ei, ej, ed = orc.edit_pairs(b["bucket_seq"], b["bucket_len"], 2 * params["max_diff"], method="brute")
+        q, r, d = hostdata.canonical_rows(ei, ej, ed)
+        prob = hostdata.MergeProblem(n_reads=lib.n_reads, n_buckets=b["n_buckets"], bucket_ptr=b["bucket_ptr"],
+                                     bucket_reads=b["bucket_reads"], lexrank=ra.lexrank, bc_id=b["bucket_of_read"], up_id=None,
+                                     geno_ptr=ra.geno_ptr, geno_mut=ra.geno_mut, geno_q=ra.geno_q, mut_rank=ra.mut_rank, **params)
+        ref = orc.cluster(prob, q, r, d)
+        n_alignment += int((ref.row_bc == hostdata.NEEDS_ALIGNMENT).any())
+        for full in (False, True):
+            out = pipeline.cluster_reads(ctx, ra, full_table=full, **params)
+            try:
+                _rows_equal(hostdata.rows_from_merge_outputs(out), ref)
+            except AssertionError as e:
+                raise AssertionError(f"case {case} full={full} {kw} {params}: {e}") from None
+    assert n_alignment < 60
+
+
+def test_big_buckets_with_collisions(ctx):
+    """A few clones with a hundred or more reads each, half of them sharing barcodes with disjoint genotypes: buckets
+    of several hundred reads that do NOT collapse into one seed cluster (the quadratic case of the seed step).
+    (Sized for the oracle: its literal restatement is quadratic in the product of two adjacent bucket sizes.)"""
+    lib = synth.make_library(n_clones=24, n_reads=3000, p_err=0.004, p_near=0.2, p_collide=0.5, skew=0.5, seed=77)
+    for shape in ("thread", "warp"):
+        os.environ["PCB_REPLAY"] = shape
+        try:
+            _fused_vs_oracle(ctx, lib, max_diff=2)
+        finally:
+            os.environ.pop("PCB_REPLAY", None)
+    assert lib.n_reads / ctx.stat("buckets") > 7

@@ -111,3 +111,36 @@ def test_replay_vs_oracle_on_fresh_random_libraries(seed, kw):
     for rows in (full, fast):
         for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
             assert np.array_equal(getattr(rows, f), getattr(ref, f)), f
+
+
+def test_many_small_random_libraries_host():
+    """The same 120 extreme tiny libraries the GPU test uses, through the host-compiled replay."""
+    from pacybara_b200 import pipeline
+    rng = np.random.default_rng(2024)
+    for case in range(120):
+        kw = dict(n_clones=int(rng.integers(1, 40)), n_reads=int(rng.integers(1, 400)), bc_len=int(rng.choice([8, 12, 25])),
+                  p_err=float(rng.choice([0.0, 0.01, 0.05])), p_near=float(rng.choice([0.0, 0.3, 0.8])),
+                  p_collide=float(rng.choice([0.0, 0.3])), p_private=float(rng.choice([0.0, 0.15, 0.6])),
+                  p_private_hq=float(rng.choice([0.0, 0.2])), p_dropout=float(rng.choice([0.0, 0.3])),
+                  skew=float(rng.choice([0.0, 1.5])), seed=1000 + case, id_style=str(rng.choice(["padded", "plain"])))
+        params = dict(max_diff=int(rng.integers(0, 4)), min_qual=int(rng.choice([5, 32, 60])),
+                      min_jaccard=float(rng.choice([0.1, 0.2, 0.5, 0.9])), min_matches=int(rng.integers(1, 4)))
+        lib = synth.make_library(**kw)
+        ids = lib.read_ids()
+        b = util.oracle_buckets(hostdata.FastqReads(ids, lib.seq, lib.qual, lib.length))
+        md = params["max_diff"]
+        ei, ej, ed = orc.edit_pairs(b["bucket_seq"], b["bucket_len"], 2 * md, method="brute")
+        q, r, d = hostdata.canonical_rows(ei, ej, ed)
+        prob = hostdata.MergeProblem(n_reads=lib.n_reads, n_buckets=b["n_buckets"], bucket_ptr=b["bucket_ptr"],
+                                     bucket_reads=b["bucket_reads"], lexrank=hostdata.lexrank_of(ids), bc_id=b["bucket_of_read"],
+                                     up_id=None, geno_ptr=lib.geno_ptr.astype(np.int32), geno_mut=lib.geno_mut, geno_q=lib.geno_q,
+                                     mut_rank=pipeline.mut_rank_of(lib.mut_strings()), **params)
+        ref = orc.cluster(prob, q, r, d)
+        keep = ed <= md
+        runs = [util.emul_merge(prob, hostdata.pairs_from_edges(ei, ej, ed, md)),
+                util.emul_merge(prob, hostdata.pairs_from_edges(ei[keep], ej[keep], ed[keep], md),
+                                planes=util.pack_planes(b["bucket_seq"], b["bucket_len"]), blen=b["bucket_len"], compute_k=2 * md)]
+        for out in runs:
+            rows = hostdata.rows_from_merge_outputs(out)
+            for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
+                assert np.array_equal(getattr(rows, f), getattr(ref, f)), (case, f, kw, params)
