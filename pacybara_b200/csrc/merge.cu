@@ -29,6 +29,7 @@
 namespace pcb {
 
 constexpr uint32_t WORK_CAP = 1023;     // component work classes used for ordering (10 bits)
+constexpr int HEAVY_READS = 64;         // components of at least this many reads always get a whole warp
 
 __device__ __forceinline__ int32_t uf_find(int32_t *parent, int32_t x) {
   for (;;) {
@@ -88,10 +89,12 @@ __global__ void comp_flag_kernel(const uint64_t *__restrict__ key, int32_t U, ui
 __global__ void comp_assign_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ val, const uint32_t *__restrict__ rank,
                                    const int32_t *__restrict__ bucket_ptr, int32_t U, int32_t n_comp,
                                    int32_t *__restrict__ old_of_new_b, int32_t *__restrict__ new_of_old_b,
-                                   int32_t *__restrict__ comp_ptr, int32_t *__restrict__ comp_of_new_b, uint32_t *__restrict__ nb_cnt) {
+                                   int32_t *__restrict__ comp_ptr, int32_t *__restrict__ comp_of_new_b, uint32_t *__restrict__ nb_cnt,
+                                   int bbits, uint32_t heavy_reads, uint32_t *__restrict__ n_heavy) {
   int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= U) return;
   bool head = i == 0 || key[i] != key[i - 1];
+  if (head && WORK_CAP - (uint32_t)(key[i] >> bbits) >= heavy_reads) atomicAdd(n_heavy, 1u);   // components come heaviest first
   int32_t c = (int32_t)rank[i] + (head ? 1 : 0) - 1;
   int32_t b = (int32_t)val[i];
   old_of_new_b[i] = b;
@@ -239,9 +242,10 @@ struct __align__(16) CompSmem {
   int32_t rd_slot[SM_READS], rd_next[SM_READS], sl_parent[SM_READS], sl_head[SM_READS], sl_tail[SM_READS], sl_size[SM_READS];
 };
 
-__global__ void __launch_bounds__(COMP_BLOCK) component_kernel_warp(MergeCtx c, int32_t n_comp, int32_t shard_rank, int32_t shard_count) {
+__global__ void __launch_bounds__(COMP_BLOCK) component_kernel_warp(MergeCtx c, int32_t comp_lo, int32_t n_comp, int32_t shard_rank,
+                                                                    int32_t shard_count) {
   __shared__ CompSmem sm_all[COMP_BLOCK / 32];
-  const int32_t comp = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  const int32_t comp = comp_lo + (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (comp >= n_comp) return;
   if (comp % shard_count != shard_rank) return;
@@ -264,12 +268,12 @@ __global__ void __launch_bounds__(COMP_BLOCK) component_kernel_warp(MergeCtx c, 
 }
 
 template <int PHASE>
-__global__ void __launch_bounds__(COMP_BLOCK) component_kernel_thread(MergeCtx c, int32_t n_comp, int32_t shard_rank, int32_t shard_count,
-                                                                      int32_t per_warp) {
+__global__ void __launch_bounds__(COMP_BLOCK) component_kernel_thread(MergeCtx c, int32_t comp_lo, int32_t n_comp, int32_t shard_rank,
+                                                                      int32_t shard_count, int32_t per_warp) {
   const int32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int32_t stride = 32 / per_warp;
   if ((tid & 31) % stride != 0) return;
-  const int32_t comp = (tid >> 5) * per_warp + (tid & 31) / stride;
+  const int32_t comp = comp_lo + (tid >> 5) * per_warp + (tid & 31) / stride;
   if (comp >= n_comp) return;
   if (comp % shard_count != shard_rank) return;
   const MergeState st = global_state(c, comp);
@@ -327,6 +331,7 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   DevBuf<int32_t> label(ctx, U), old_of_new_b(ctx, U), new_of_old_b(ctx, U), comp_of_new_b(ctx, U), comp_ptr(ctx, (size_t)U + 1);
   DevBuf<uint32_t> nb_ptr(ctx, (size_t)U + 1);
   int32_t n_comp = 0;
+  DevBuf<uint32_t> d_n_heavy(ctx, 1);
   {
     DevBuf<int32_t> parent(ctx, U);
     DevBuf<uint32_t> work(ctx, U), rank(ctx, U);
@@ -344,8 +349,9 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
     uint32_t last_flag = read_scalar(ctx, rank.p + (U - 1));
     exclusive_scan_u32(ctx, rank.p, rank.p, U);
     n_comp = (int32_t)(read_scalar(ctx, rank.p + (U - 1)) + last_flag);
+    PCB_CUDA(cudaMemsetAsync(d_n_heavy.p, 0, sizeof(uint32_t), ctx->stream));
     PCB_LAUNCH(ctx, comp_assign_kernel, grid_for(U, 256), 256, 0, sk, sv, rank.p, in.bucket_ptr, U, n_comp, old_of_new_b.p,
-               new_of_old_b.p, comp_ptr.p, comp_of_new_b.p, nb_ptr.p);
+               new_of_old_b.p, comp_ptr.p, comp_of_new_b.p, nb_ptr.p, bbits, (uint32_t)HEAVY_READS, d_n_heavy.p);
     exclusive_scan_u32(ctx, nb_ptr.p, nb_ptr.p, (size_t)U + 1);
   }
   ctx->stats[PCB_STAT_COMPONENTS] = n_comp;
@@ -447,26 +453,27 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   c.prm.maxDiff = in.max_diff; c.prm.minQual = in.min_qual; c.prm.minMatches = in.min_matches; c.prm.minJaccard = in.min_jaccard;
   stage_end(ctx, PCB_STAT_T_PREP_NS);
   // Which launch shape: measured (profiles/r01_replay_shapes.md) the thread kernel wins when buckets are small
-  // (cfg 2: 5 reads per bucket, 1.55 vs 2.65 ms), the warp kernel when reads concentrate in big buckets (cfg 4:
-  // 8 reads per bucket, 1.1 vs 4.6 ms) -- and it is the only shape that copes with components of thousands of reads.
+  // (cfg 2: 5 reads per bucket, 1.4 vs 2.65 ms), the warp kernel when reads concentrate in big buckets (cfg 4:
+  // 8 reads per bucket, 1.1 vs 4.6 ms).  Components of HEAVY_READS reads or more (they come first) always get a warp:
+  // one thread would crawl through them while the rest of the chip idles.
   const char *mode = getenv("PCB_REPLAY");
-  bool use_warp = (double)R / (double)U >= 7.0;
-  if (mode && strcmp(mode, "warp") == 0) use_warp = true;
-  if (mode && strcmp(mode, "thread") == 0) use_warp = false;
-  if (!use_warp) {
+  int32_t n_warp = (double)R / (double)U >= 7.0 ? n_comp : (int32_t)read_scalar(ctx, d_n_heavy.p);
+  if (mode && strcmp(mode, "warp") == 0) n_warp = n_comp;
+  if (mode && strcmp(mode, "thread") == 0) n_warp = 0;
+  if (n_warp > 0)
+    PCB_LAUNCH(ctx, component_kernel_warp, grid_for((size_t)n_warp * 32, COMP_BLOCK), COMP_BLOCK, 0, c, 0, n_warp, in.shard_rank,
+               in.shard_count);
+  if (n_warp < n_comp) {
     int per_warp = 4;
     if (const char *e = getenv("PCB_COMP_PER_WARP")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) per_warp = v; }
-    size_t n_threads = ((size_t)n_comp + per_warp - 1) / per_warp * 32;
+    size_t n_threads = ((size_t)(n_comp - n_warp) + per_warp - 1) / per_warp * 32;
     // three launches, one per phase: each kernel's code fits the instruction cache and its threads share a loop nest
-    PCB_LAUNCH(ctx, component_kernel_thread<1>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_comp, in.shard_rank,
+    PCB_LAUNCH(ctx, component_kernel_thread<1>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_warp, n_comp, in.shard_rank,
                in.shard_count, per_warp);
-    PCB_LAUNCH(ctx, component_kernel_thread<2>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_comp, in.shard_rank,
+    PCB_LAUNCH(ctx, component_kernel_thread<2>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_warp, n_comp, in.shard_rank,
                in.shard_count, per_warp);
-    PCB_LAUNCH(ctx, component_kernel_thread<3>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_comp, in.shard_rank,
+    PCB_LAUNCH(ctx, component_kernel_thread<3>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_warp, n_comp, in.shard_rank,
                in.shard_count, per_warp);
-  } else {
-    PCB_LAUNCH(ctx, component_kernel_warp, grid_for((size_t)n_comp * 32, COMP_BLOCK), COMP_BLOCK, 0, c, n_comp, in.shard_rank,
-               in.shard_count);
   }
   stage_end(ctx, PCB_STAT_T_REPLAY_NS);
   PCB_LAUNCH(ctx, scatter_outputs_kernel, grid_for(R, 256), 256, 0, R, old_of_new_r.p, old_of_new_b.p, t_root.p, t_pos.p, t_size.p,

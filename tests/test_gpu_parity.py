@@ -337,3 +337,11 @@ def test_big_buckets_with_collisions(ctx):
         finally:
             os.environ.pop("PCB_REPLAY", None)
     assert lib.n_reads / ctx.stat("buckets") > 7
+
+
+def test_mixed_light_and_heavy_components(ctx):
+    """Mean bucket size below the warp-kernel threshold, but a few clones with hundreds of reads: the heavy
+    components (>= 64 reads, numbered first) go to the warp kernel, the rest to the thread kernels."""
+    lib = synth.make_library(n_clones=1500, n_reads=12000, p_err=0.01, p_near=0.1, skew=2.2, seed=5)
+    _fused_vs_oracle(ctx, lib, max_diff=2)
+    assert lib.n_reads / ctx.stat("buckets") < 7
