@@ -190,6 +190,20 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
                       int32_t *row_bc, int32_t *row_up, int64_t *row_call_off, int32_t *row_call_n,
                       int32_t *call_mut);
 
+/*
+ * f1 (first row after the hot path) -- barcode-collision tags and the dominance test of the
+ * soft filter, on a cluster table given as per-row ids:
+ *   collision[i]     = the virtual barcode of row i occurs in more than one row   (tagDups, src/pacybara_translate.R:58-68)
+ *   up_collision[i]  = the uptag barcode of row i occurs in more than one row     (same, on upBarcode)
+ *   usable[i]        = size_i / (sum of the sizes of all rows with the same uptag) > min_ratio  and  size_i > 1
+ *                                                                                 (src/pacybara_softfilter.R:46-63)
+ * row_bc / row_up: ids of the barcode strings (0 <= id < n_bc_ids / n_up_ids); a negative id stands for a string
+ * that occurs nowhere else.  The ratio is the same fp64 divide and strict > as in R.  Outputs are bytes (0/1).
+ */
+int pcb_tag_rows(pcb_ctx *ctx, int mem, int32_t n_rows, const int32_t *row_bc, const int32_t *row_up,
+                 const int32_t *row_size, int32_t n_bc_ids, int32_t n_up_ids, double min_ratio,
+                 uint8_t *collision, uint8_t *up_collision, uint8_t *usable);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,7 +19,7 @@ STAT = dict(pairs_scored=0, cells=1, edges=2, seed_len=3, kernel_launches=4, com
 
 # every symbol include/pacybara_b200.h declares
 SYMBOLS = ["pcb_abi_version", "pcb_last_error", "pcb_ctx_create", "pcb_ctx_destroy", "pcb_stat", "pcb_sync",
-           "pcb_stream", "pcb_bucket", "pcb_edit_pairs", "pcb_edit_pairs_fetch", "pcb_sort_edges", "pcb_merge", "pcb_cluster_reads"]
+           "pcb_stream", "pcb_bucket", "pcb_edit_pairs", "pcb_edit_pairs_fetch", "pcb_sort_edges", "pcb_merge", "pcb_cluster_reads", "pcb_tag_rows"]
 
 
 class PcbError(RuntimeError):
@@ -59,5 +59,6 @@ def load():
                                   [i32, i32, dbl, i32, vp, vp, i32, i32, i32, i32] + [vp] * 9)
         lib.pcb_cluster_reads.argtypes = ([vp, C.c_int, vp, vp, vp, i32, i32] + [vp] * 6 + [i32, i32, i32, dbl, i32, i32] +
                                           [vp, C.POINTER(i32), C.POINTER(i64)] + [vp] * 9)
+        lib.pcb_tag_rows.argtypes = [vp, C.c_int, i32, vp, vp, vp, i32, i32, dbl, vp, vp, vp]
         _lib = lib
     return _lib

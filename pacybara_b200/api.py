@@ -206,6 +206,23 @@ class Context:
         out["call_mut"] = outs["call_mut"][:nnz]
         return out
 
+    # ------------------------------------------------------------------ f1
+    def tag_rows(self, row_bc, row_up, row_size, n_bc_ids: int, n_up_ids: int, min_ratio: float = 0.666) -> Dict:
+        """Collision tags + soft-filter dominance test on a cluster table (pcb_tag_rows)."""
+        if _is_dev(row_bc):
+            _torch()
+        mem = self._kind(row_bc, row_up, row_size)
+        n = int(row_bc.shape[0])
+        keep: list = []
+        outs = {}
+        ptrs = []
+        for name in ("collision", "up_collision", "usable"):
+            outs[name], ptr = self._out(mem, (max(n, 1),), np.uint8)
+            ptrs.append(ptr)
+        self._check(self.lib.pcb_tag_rows(self.h, mem, n, self._in(row_bc, np.int32, keep), self._in(row_up, np.int32, keep),
+                                          self._in(row_size, np.int32, keep), int(n_bc_ids), int(n_up_ids), float(min_ratio), *ptrs))
+        return {k: v[:n] for k, v in outs.items()}
+
     # ------------------------------------------------------------------ the whole path
     def cluster_reads(self, seq, qual, length, lexrank, up_id, geno_ptr, geno_mut, geno_q, mut_rank,
                       max_diff: int = 2, min_qual: int = 32, min_jaccard: float = 0.2, min_matches: int = 1,

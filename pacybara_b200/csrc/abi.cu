@@ -330,4 +330,17 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
   });
 }
 
+int pcb_tag_rows(pcb_ctx *ctx, int mem, int32_t n_rows, const int32_t *row_bc, const int32_t *row_up, const int32_t *row_size,
+                 int32_t n_bc_ids, int32_t n_up_ids, double min_ratio, uint8_t *collision, uint8_t *up_collision, uint8_t *usable) {
+  return guarded(ctx, [&] {
+    if (n_rows < 0 || n_bc_ids < 0 || n_up_ids < 0) throw Error(PCB_E_INPUT, "bad shape");
+    if (!(min_ratio >= 0.5 && min_ratio <= 1.0)) throw Error(PCB_E_INPUT, "minRatio must be between 0.5 and 1 (pacybara_softfilter.R:36-39)");
+    InArr<int32_t> d_bc(ctx, mem, row_bc, n_rows), d_up(ctx, mem, row_up, n_rows), d_size(ctx, mem, row_size, n_rows);
+    OutArr<uint8_t> o_c(ctx, mem, collision, n_rows), o_u(ctx, mem, up_collision, n_rows), o_ok(ctx, mem, usable, n_rows);
+    tag_rows_dev(ctx, n_rows, d_bc.p, d_up.p, d_size.p, n_bc_ids, n_up_ids, min_ratio, o_c.p, o_u.p, o_ok.p);
+    o_c.commit(n_rows); o_u.commit(n_rows); o_ok.commit(n_rows);
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
 }  // extern "C"

@@ -177,5 +177,7 @@ struct MergeOut {            // device pointers, caller-owned
   int32_t *row_call_n, *call_mut;
 };
 void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out);
+void tag_rows_dev(pcb_ctx *ctx, int32_t n_rows, const int32_t *row_bc, const int32_t *row_up, const int32_t *row_size,
+                  int32_t n_bc_ids, int32_t n_up_ids, double min_ratio, uint8_t *collision, uint8_t *up_collision, uint8_t *usable);
 
 }  // namespace pcb

@@ -345,3 +345,24 @@ def test_mixed_light_and_heavy_components(ctx):
     lib = synth.make_library(n_clones=1500, n_reads=12000, p_err=0.01, p_near=0.1, skew=2.2, seed=5)
     _fused_vs_oracle(ctx, lib, max_diff=2)
     assert lib.n_reads / ctx.stat("buckets") < 7
+
+
+# ----------------------------------------------------------------------------- f1: collision tags + soft filter
+@pytest.mark.parametrize("name", ["rand_collide", "rand_dense_d2", "rand_d3_combo", "kat1", "kat5a"])
+def test_tag_rows_on_cluster_tables(ctx, name):
+    from oracle import f1
+    from pacybara_b200 import tagging
+    case = util.load_golden(name)
+    table = [(r[1], r[2], r[0], r[3], r[4]) for r in util.golden_table(case)]     # canonical rows: members first
+    for ratio in (0.5, 0.666, 0.9):
+        assert tagging.tag_table(ctx, table, ratio) == f1.tag_table(table, ratio)
+    if name in ("rand_collide", "kat1", "kat5a"):
+        assert any(r[5] == "collision" for r in tagging.tag_table(ctx, table))     # the collision rule is exercised
+
+
+def test_tag_rows_random(ctx):
+    from oracle import f1
+    from pacybara_b200 import tagging
+    rng = np.random.default_rng(3)
+    table = [(f"B{rng.integers(0, 3000)}", f"U{rng.integers(0, 1500)}", f"r{i}", int(rng.integers(1, 40)), "=") for i in range(20000)]
+    assert tagging.tag_table(ctx, table, 0.666) == f1.tag_table(table, 0.666)
