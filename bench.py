@@ -182,7 +182,7 @@ def main():
     lib = synth.make_config(args.config, seed=args.seed, scale=scale)
     if world > 1:
         workload += f"; x{world} for {world} GPUs = {lib.params['n_clones']} clones / {lib.n_reads} reads, one library"
-    ra, names = pipeline.arrays_from_library(lib, ctx)
+    ra, names = pipeline.arrays_from_library(lib, ctx, with_names=False)
     R = ra.n_reads
     dev = f"cuda:{local_rank}"
     host = {k: v for k, v in vars(ra).items() if v is not None}

@@ -40,10 +40,16 @@ def mut_rank_of(mut_strings: List[str]) -> np.ndarray:
     return rank
 
 
-def arrays_from_library(lib, ctx: Optional[Context] = None) -> Tuple[ReadArrays, Dict]:
+def arrays_from_library(lib, ctx: Optional[Context] = None, with_names: bool = True) -> Tuple[ReadArrays, Dict]:
     """ReadArrays of a synth.Library plus the string tables the writer needs.  For combo
-    libraries the uptag ids come from bucketing the uptag strings (needs `ctx`)."""
-    ids = lib.read_ids()
+    libraries the uptag ids come from bucketing the uptag strings (needs `ctx`).
+    with_names=False skips building the R read-id strings (zero-padded ids sort like their index)."""
+    if not with_names and lib.id_style == "padded":
+        ids = None
+        lexrank = np.arange(lib.n_reads, dtype=np.int32)
+    else:
+        ids = lib.read_ids()
+        lexrank = hostdata.lexrank_of(ids)
     names = dict(ids=ids, mut_names=lib.mut_strings(), up_names=None)
     up_id = None
     if lib.uptag_len is not None:
@@ -54,7 +60,7 @@ def arrays_from_library(lib, ctx: Optional[Context] = None) -> Tuple[ReadArrays,
         up_id = b["bucket_of_read"].astype(np.int32)
         names["up_names"] = hostdata.matrix_to_strings(b["bucket_seq"], b["bucket_len"])
     ra = ReadArrays(seq=lib.seq, qual=lib.qual, length=lib.length.astype(np.int32),
-                    lexrank=hostdata.lexrank_of(ids), geno_ptr=lib.geno_ptr.astype(np.int32),
+                    lexrank=lexrank, geno_ptr=lib.geno_ptr.astype(np.int32),
                     geno_mut=lib.geno_mut.astype(np.int32), geno_q=lib.geno_q.astype(np.int32),
                     mut_rank=mut_rank_of(names["mut_names"]), up_id=up_id)
     return ra, names
