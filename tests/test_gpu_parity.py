@@ -366,3 +366,33 @@ def test_tag_rows_random(ctx):
     rng = np.random.default_rng(3)
     table = [(f"B{rng.integers(0, 3000)}", f"U{rng.integers(0, 1500)}", f"r{i}", int(rng.integers(1, 40)), "=") for i in range(20000)]
     assert tagging.tag_table(ctx, table, 0.666) == f1.tag_table(table, 0.666)
+
+
+# ----------------------------------------------------------------------------- degenerate shapes through the fused call
+def _tiny(ctx, seqs, genos, **params):
+    mat, lens = hostdata.strings_to_matrix([s.encode() for s in seqs]) if seqs else (np.zeros((0, 8), np.uint8), np.zeros(0, np.int32))
+    R = len(seqs)
+    ptr = np.zeros(R + 1, dtype=np.int32)
+    mut, q = [], []
+    for i, g in enumerate(genos):
+        for m, qq in g:
+            mut.append(m); q.append(qq)
+        ptr[i + 1] = len(mut)
+    out = ctx.cluster_reads(mat, None, lens, np.arange(R, dtype=np.int32), None, ptr, np.asarray(mut, dtype=np.int32),
+                            np.asarray(q, dtype=np.int32), np.arange(8, dtype=np.int32), **params)
+    return out
+
+
+def test_degenerate_inputs(ctx):
+    out = _tiny(ctx, [], [])                                   # no reads at all
+    assert out["n_buckets"] == 0 and out["n_edges"] == 0 and len(out["read_root"]) == 0
+    out = _tiny(ctx, ["ACGTACGT"], [[(0, 50)]])                 # one read: a singleton row with its high-quality call
+    assert out["n_buckets"] == 1 and out["read_root"].tolist() == [0] and out["row_size"].tolist() == [1]
+    assert out["row_call_n"].tolist() == [1] and out["call_mut"][out["row_call_off"][0]] == 0
+    out = _tiny(ctx, ["ACGTACGT"] * 3, [[], [], []])            # one bucket, wild type: one cluster [r1, r0, r2]
+    rows = hostdata.rows_from_merge_outputs(out)
+    assert rows.n_clusters == 1 and rows.row_members.tolist() == [1, 0, 2]
+    out = _tiny(ctx, ["ACGTACGT", "ACGTACGA"], [[], []])        # two singletons one edit apart never merge (1 v 1)
+    assert out["n_edges"] == 1 and sorted(out["row_size"].tolist()) == [1, 1]
+    out = _tiny(ctx, ["ACGTACGT", "ACGTACGT", "ACGTACGA"], [[], [], []], max_diff=0)   # maxDiff 0: no pair search at all
+    assert out["n_edges"] == 0 and hostdata.rows_from_merge_outputs(out).n_clusters == 1
