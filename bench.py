@@ -127,6 +127,7 @@ def cpu_pass(lib, params):
 
 def cpu_baseline(args, params, steps=1, warmup=0):
     from oracle import orc
+    orc.set_threads(os.cpu_count() or 1)      # torchrun pins OMP_NUM_THREADS=1; the CPU arm uses every host core
     base = synth.CONFIGS[args.config]["gen"]
     scale = min(1.0, args.cpu_sample_reads / base["n_reads"])
     lib = synth.make_config(args.config, seed=args.seed, scale=scale)

@@ -45,6 +45,10 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def set_threads(n: int) -> None:
+    lib().orc_set_threads(C.c_int32(int(n)))
+
+
 def precluster(seq: np.ndarray, qual: np.ndarray, length: np.ndarray):
     seq, qual, length = _c(seq, np.uint8), _c(qual, np.uint8), _c(length, np.int32)
     R, stride = seq.shape

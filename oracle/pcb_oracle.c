@@ -535,6 +535,15 @@ int32_t orc_cluster(int32_t R, int32_t U, const int32_t *bucket_ptr, const int32
   return err ? err : n_rows;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the reference arm wants every host core it can use */
+void orc_set_threads(int32_t n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 int32_t orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();
