@@ -168,45 +168,47 @@ void exclusive_scan_i64(pcb_ctx *ctx, const int64_t *in, int64_t *out, size_t n)
 // [digit][block] table -> scatter kernel that ranks with __match_any_sync.
 constexpr int SORT_BLOCK = 256;
 constexpr int SORT_WARPS = SORT_BLOCK / 32;
-constexpr int SORT_ROWS = 16;
-constexpr int SORT_TILE = SORT_BLOCK * SORT_ROWS;
-
+// Rows of 32 items per warp and tile: 16 (tile 4096) keeps the [digit][block] table small for big inputs; small
+// inputs take 4 (tile 1024) so that a 150 k-item sort still spreads over the whole chip instead of 37 blocks.
+template <int ROWS>
 __device__ __forceinline__ void sort_count_tile(const uint64_t *__restrict__ keys, size_t n, int shift,
                                                 uint32_t (*cnt)[256]) {
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int d = threadIdx.x; d < SORT_WARPS * 256; d += SORT_BLOCK) (&cnt[0][0])[d] = 0;
   __syncthreads();
-  size_t base = (size_t)blockIdx.x * SORT_TILE + (size_t)warp * (32 * SORT_ROWS);
+  size_t base = (size_t)blockIdx.x * (SORT_BLOCK * ROWS) + (size_t)warp * (32 * ROWS);
 #pragma unroll 4
-  for (int r = 0; r < SORT_ROWS; r++) {
+  for (int r = 0; r < ROWS; r++) {
     size_t idx = base + r * 32 + lane;
     if (idx < n) atomicAdd(&cnt[warp][(keys[idx] >> shift) & 0xFF], 1u);
   }
   __syncthreads();
 }
 
+template <int ROWS>
 __global__ void __launch_bounds__(SORT_BLOCK) sort_hist(const uint64_t *__restrict__ keys, size_t n, int shift,
                                                         uint32_t *__restrict__ ghist, uint32_t nblocks) {
   __shared__ uint32_t cnt[SORT_WARPS][256];
-  sort_count_tile(keys, n, shift, cnt);
+  sort_count_tile<ROWS>(keys, n, shift, cnt);
   uint32_t t = 0;
   for (int w = 0; w < SORT_WARPS; w++) t += cnt[w][threadIdx.x];
   ghist[(size_t)threadIdx.x * nblocks + blockIdx.x] = t;
 }
 
+template <int ROWS>
 __global__ void __launch_bounds__(SORT_BLOCK) sort_scatter(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                                            uint64_t *__restrict__ okeys, uint32_t *__restrict__ ovals, size_t n,
                                                            int shift, const uint32_t *__restrict__ goff, uint32_t nblocks) {
   __shared__ uint32_t cnt[SORT_WARPS][256];
-  sort_count_tile(keys, n, shift, cnt);
+  sort_count_tile<ROWS>(keys, n, shift, cnt);
   {
     uint32_t run = goff[(size_t)threadIdx.x * nblocks + blockIdx.x];
     for (int w = 0; w < SORT_WARPS; w++) { uint32_t c = cnt[w][threadIdx.x]; cnt[w][threadIdx.x] = run; run += c; }
   }
   __syncthreads();
   int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  size_t base = (size_t)blockIdx.x * SORT_TILE + (size_t)warp * (32 * SORT_ROWS);
-  for (int r = 0; r < SORT_ROWS; r++) {
+  size_t base = (size_t)blockIdx.x * (SORT_BLOCK * ROWS) + (size_t)warp * (32 * ROWS);
+  for (int r = 0; r < ROWS; r++) {
     size_t idx = base + r * 32 + lane;
     bool valid = idx < n;
     uint64_t key = valid ? keys[idx] : 0;
@@ -222,20 +224,27 @@ __global__ void __launch_bounds__(SORT_BLOCK) sort_scatter(const uint64_t *__res
   }
 }
 
-int radix_sort_pairs(pcb_ctx *ctx, uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, size_t n, int bits) {
-  if (n == 0) return 0;
-  uint32_t nblocks = (uint32_t)((n + SORT_TILE - 1) / SORT_TILE);
+template <int ROWS>
+static int radix_sort_rows(pcb_ctx *ctx, uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, size_t n, int bits) {
+  const size_t tile = (size_t)SORT_BLOCK * ROWS;
+  uint32_t nblocks = (uint32_t)((n + tile - 1) / tile);
   DevBuf<uint32_t> ghist(ctx, (size_t)256 * nblocks);
   int cur = 0;
   for (int shift = 0; shift < bits; shift += 8) {
     uint64_t *ki = cur ? k1 : k0, *ko = cur ? k0 : k1;
     uint32_t *vi = cur ? v1 : v0, *vo = cur ? v0 : v1;
-    PCB_LAUNCH(ctx, sort_hist, nblocks, SORT_BLOCK, 0, ki, n, shift, ghist.p, nblocks);
+    PCB_LAUNCH(ctx, sort_hist<ROWS>, nblocks, SORT_BLOCK, 0, ki, n, shift, ghist.p, nblocks);
     exclusive_scan_u32(ctx, ghist.p, ghist.p, (size_t)256 * nblocks);
-    PCB_LAUNCH(ctx, sort_scatter, nblocks, SORT_BLOCK, 0, ki, vi, ko, vo, n, shift, ghist.p, nblocks);
+    PCB_LAUNCH(ctx, sort_scatter<ROWS>, nblocks, SORT_BLOCK, 0, ki, vi, ko, vo, n, shift, ghist.p, nblocks);
     cur ^= 1;
   }
   return cur;
+}
+
+int radix_sort_pairs(pcb_ctx *ctx, uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, size_t n, int bits) {
+  if (n == 0) return 0;
+  if (n <= ((size_t)1 << 21)) return radix_sort_rows<4>(ctx, k0, v0, k1, v1, n, bits);
+  return radix_sort_rows<16>(ctx, k0, v0, k1, v1, n, bits);
 }
 
 // ------------------------------------------------------------------------------------ small
