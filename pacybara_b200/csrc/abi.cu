@@ -251,6 +251,7 @@ int pcb_merge(pcb_ctx *ctx, int mem, int32_t R, int32_t U, const int32_t *bucket
     MergeIn in{R, U, n_mut, d_bptr.p, d_breads.p, d_lex.p, d_bc.p, d_up.p, d_gptr.p, d_gmut.p, d_gq.p, d_rank.p,
                n_pairs, d_pq.p, d_pr.p, d_pd.p, d_pe.p, max_diff, min_qual, min_matches, min_jaccard, shard_rank, shard_count};
     MergeOut out{o_root.p, o_pos.p, o_size.p, o_key.p, o_bc.p, o_up.p, o_calloff.p, o_calln.p, o_call.p};
+    in.nnz = nnz;
     PackedBarcodes bc;
     if (bucket_seq && bucket_len && on_demand_k >= 0 && U > 0) {
       InArr<uint8_t> d_bseq(ctx, mem, bucket_seq, (size_t)U * stride);
@@ -321,6 +322,7 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
     MergeIn in{R, U, n_mut, bptr.p, breads.p, d_lex.p, bor, d_up.p, d_gptr.p, d_gmut.p, d_gq.p, d_rank.p,
                E, ctx->edges.ei, ctx->edges.ej, ctx->edges.ed, ped.p, max_diff, min_qual, min_matches, min_jaccard, 0, 1};
     if (!full) { in.planes = uniq.planes.p; in.blen = uniq.len.p; in.compute_k = 2 * max_diff; in.wide = uniq.max_len > 32; }
+    in.nnz = nnz;
     MergeOut out{o_root.p, o_pos.p, o_size.p, o_key.p, o_bc.p, o_up.p, o_calloff.p, o_calln.p, o_call.p};
     merge_dev(ctx, in, out);
     stage_collect(ctx);

@@ -156,17 +156,17 @@ int32_t bucket_reads_dev(pcb_ctx *ctx, const uint8_t *seq, const uint8_t *qual, 
   uint32_t cap = 64;
   while (cap < 2u * (uint32_t)R) cap <<= 1;
   DevBuf<int32_t> owner(ctx, cap), first(ctx, cap), slot_of_read(ctx, R);
-  DevBuf<uint32_t> count(ctx, cap), rank(ctx, R), bucket_cnt(ctx, (size_t)R + 1);
+  DevBuf<uint32_t> count(ctx, cap), rank(ctx, (size_t)R + 1), bucket_cnt(ctx, (size_t)R + 1);
   PCB_CUDA(cudaMemsetAsync(owner.p, 0xFF, cap * sizeof(int32_t), ctx->stream));
   fill_i32(ctx, first.p, cap, INT32_MAX);
   PCB_CUDA(cudaMemsetAsync(count.p, 0, cap * sizeof(uint32_t), ctx->stream));
   PCB_LAUNCH(ctx, bucket_insert_kernel, grid_for(R, 256), 256, 0, pk.planes.p, pk.len.p, R, owner.p, first.p, count.p,
              cap - 1, slot_of_read.p);
   PCB_LAUNCH(ctx, bucket_flag_first_kernel, grid_for(R, 256), 256, 0, slot_of_read.p, first.p, R, rank.p);
-  // U = number of first reads = rank[R-1] (exclusive) + is_first[R-1]
-  uint32_t last_flag = read_scalar(ctx, rank.p + (R - 1));
-  exclusive_scan_u32(ctx, rank.p, rank.p, R);
-  int32_t U = (int32_t)(read_scalar(ctx, rank.p + (R - 1)) + last_flag);
+  // U = number of first reads: scan one element past the end (a zero) and read the total there
+  PCB_CUDA(cudaMemsetAsync(rank.p + R, 0, sizeof(uint32_t), ctx->stream));
+  exclusive_scan_u32(ctx, rank.p, rank.p, (size_t)R + 1);
+  int32_t U = (int32_t)read_scalar(ctx, rank.p + R);
   DevBuf<uint64_t> k0(ctx, R), k1(ctx, R);
   DevBuf<uint32_t> v0(ctx, R), v1(ctx, R);
   PCB_CUDA(cudaMemsetAsync(bucket_cnt.p, 0, ((size_t)R + 1) * sizeof(uint32_t), ctx->stream));

@@ -168,6 +168,7 @@ struct MergeIn {             // device pointers
   const ulonglong2 *planes = nullptr;
   const int32_t *blen = nullptr;
   int32_t compute_k = -1, wide = 0;
+  int64_t nnz = -1;            // number of genotype entries if the caller already knows it (saves a round trip)
 };
 struct MergeOut {            // device pointers, caller-owned
   int32_t *read_root, *read_pos, *row_size;

@@ -325,11 +325,11 @@ void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q
   int where = radix_sort_pairs(ctx, hk0.p, hv0.p, hk1.p, hv1.p, n_hits, 2 * key_shift);
   uint64_t *sk = where ? hk1.p : hk0.p;
   uint32_t *sv = where ? hv1.p : hv0.p;
-  DevBuf<uint32_t> rank(ctx, n_hits);
+  DevBuf<uint32_t> rank(ctx, n_hits + 1);
   PCB_LAUNCH(ctx, flag_unique_kernel, grid_for(n_hits, 256), 256, 0, sk, n_hits, rank.p);
-  uint32_t last_flag = read_scalar(ctx, rank.p + (n_hits - 1));
-  exclusive_scan_u32(ctx, rank.p, rank.p, n_hits);
-  size_t n_edges = (size_t)read_scalar(ctx, rank.p + (n_hits - 1)) + last_flag;
+  PCB_CUDA(cudaMemsetAsync(rank.p + n_hits, 0, sizeof(uint32_t), ctx->stream));
+  exclusive_scan_u32(ctx, rank.p, rank.p, n_hits + 1);                  // one past the end: the total
+  size_t n_edges = (size_t)read_scalar(ctx, rank.p + n_hits);
   PCB_CUDA(cudaMallocAsync((void **)&res.ei, n_edges * sizeof(int32_t), ctx->stream));
   PCB_CUDA(cudaMallocAsync((void **)&res.ej, n_edges * sizeof(int32_t), ctx->stream));
   PCB_CUDA(cudaMallocAsync((void **)&res.ed, n_edges * sizeof(int32_t), ctx->stream));

@@ -323,7 +323,7 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   if (in.min_qual < 1) throw Error(PCB_E_INPUT, "minQual must be a positive integer");
   if (in.shard_count < 1 || in.shard_rank < 0 || in.shard_rank >= in.shard_count) throw Error(PCB_E_INPUT, "bad shard");
   if (R == 0 || U == 0) return;
-  const int64_t nnz = (int64_t)read_scalar(ctx, in.geno_ptr + R);
+  const int64_t nnz = in.nnz >= 0 ? in.nnz : (int64_t)read_scalar(ctx, in.geno_ptr + R);
   const int bbits = bits_for((uint64_t)(U > 1 ? U - 1 : 1));
   const bool on_demand = in.planes != nullptr && in.compute_k >= 0;
 
@@ -334,7 +334,7 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   DevBuf<uint32_t> d_n_heavy(ctx, 1);
   {
     DevBuf<int32_t> parent(ctx, U);
-    DevBuf<uint32_t> work(ctx, U), rank(ctx, U);
+    DevBuf<uint32_t> work(ctx, U), rank(ctx, (size_t)U + 1);
     DevBuf<uint64_t> k0(ctx, U), k1(ctx, U);
     DevBuf<uint32_t> v0(ctx, U), v1(ctx, U);
     PCB_CUDA(cudaMemsetAsync(work.p, 0, (size_t)U * sizeof(uint32_t), ctx->stream));
@@ -346,9 +346,9 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
     uint64_t *sk = w ? k1.p : k0.p;
     uint32_t *sv = w ? v1.p : v0.p;
     PCB_LAUNCH(ctx, comp_flag_kernel, grid_for(U, 256), 256, 0, sk, U, rank.p);
-    uint32_t last_flag = read_scalar(ctx, rank.p + (U - 1));
-    exclusive_scan_u32(ctx, rank.p, rank.p, U);
-    n_comp = (int32_t)(read_scalar(ctx, rank.p + (U - 1)) + last_flag);
+    PCB_CUDA(cudaMemsetAsync(rank.p + U, 0, sizeof(uint32_t), ctx->stream));
+    exclusive_scan_u32(ctx, rank.p, rank.p, (size_t)U + 1);              // one past the end: the total
+    n_comp = (int32_t)read_scalar(ctx, rank.p + U);
     PCB_CUDA(cudaMemsetAsync(d_n_heavy.p, 0, sizeof(uint32_t), ctx->stream));
     PCB_LAUNCH(ctx, comp_assign_kernel, grid_for(U, 256), 256, 0, sk, sv, rank.p, in.bucket_ptr, U, n_comp, old_of_new_b.p,
                new_of_old_b.p, comp_ptr.p, comp_of_new_b.p, nb_ptr.p, bbits, (uint32_t)HEAVY_READS, d_n_heavy.p);
@@ -414,8 +414,12 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   exclusive_scan_i64(ctx, slot_off.p, slot_off.p, (size_t)n_comp + 1);
   exclusive_scan_i64(ctx, list_off.p, list_off.p, (size_t)n_comp + 1);
   exclusive_scan_i64(ctx, call_off.p, call_off.p, (size_t)n_comp + 1);
-  int64_t n_slots = read_scalar(ctx, slot_off.p + n_comp);
-  int64_t n_list = read_scalar(ctx, list_off.p + n_comp);
+  int64_t n_slots = 0, n_list = 0;
+  uint32_t h_n_heavy = 0;                                               // three scalars, one round trip
+  PCB_CUDA(cudaMemcpyAsync(&n_slots, slot_off.p + n_comp, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PCB_CUDA(cudaMemcpyAsync(&n_list, list_off.p + n_comp, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PCB_CUDA(cudaMemcpyAsync(&h_n_heavy, d_n_heavy.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PCB_CUDA(cudaStreamSynchronize(ctx->stream));
   DevBuf<GenoSlot> slots(ctx, (size_t)n_slots);
   DevBuf<int32_t> lists(ctx, (size_t)n_list + 1);
   PCB_CUDA(cudaMemsetAsync(slots.p, 0, (size_t)n_slots * sizeof(GenoSlot), ctx->stream));     // all-zero = empty
@@ -457,7 +461,7 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   // 8 reads per bucket, 1.1 vs 4.6 ms).  Components of HEAVY_READS reads or more (they come first) always get a warp:
   // one thread would crawl through them while the rest of the chip idles.
   const char *mode = getenv("PCB_REPLAY");
-  int32_t n_warp = (double)R / (double)U >= 7.0 ? n_comp : (int32_t)read_scalar(ctx, d_n_heavy.p);
+  int32_t n_warp = (double)R / (double)U >= 7.0 ? n_comp : (int32_t)h_n_heavy;
   if (mode && strcmp(mode, "warp") == 0) n_warp = n_comp;
   if (mode && strcmp(mode, "thread") == 0) n_warp = 0;
   if (n_warp > 0)
