@@ -144,3 +144,22 @@ def test_clustering_section_of_the_driver(tmp_path, name, mode):
     assert got == util.golden_table(case)
     for qc in ("bcPreclust_distr.txt", "edDistr.txt", "clusters_distr.txt"):
         assert os.path.getsize(os.path.join(clu, "qc", qc)) > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,extra", [("rand_dense_d2", []), ("rand_collide", ["--full-table"]), ("rand_d3_combo", [])])
+def test_fused_cli(tmp_path, name, extra):
+    """bin/pacybara_b200_cluster: reads + genotypes in, the reference's cluster table out, one GPU call."""
+    case = util.load_golden(name)
+    ext = str(tmp_path / "extract")
+    _write_extract_dir(case, ext)
+    p = case["params"]
+    out = str(tmp_path / "clusters.csv.gz")
+    bc = "bcExtract_combo.fastq.gz" if name == "rand_d3_combo" else "bcExtract_1.fastq.gz"
+    cmd = [sys.executable, os.path.join(BIN, "pacybara_b200_cluster"), "-u", os.path.join(ext, "bcExtract_1.fastq.gz"), "-o", out,
+           "-j", repr(p["min_jaccard"]), "-m", str(p["min_matches"]), "-d", str(p["max_diff"]), "-q", str(p["min_qual"])] + extra + \
+          [os.path.join(ext, bc), os.path.join(ext, "genoExtract.csv.gz")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = canon.canon_table(canon.read_clusters_csv(out))
+    assert got == util.golden_table(case)
