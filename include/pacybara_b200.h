@@ -140,8 +140,9 @@ int pcb_sort_edges(pcb_ctx *ctx, int mem, int32_t *ei, int32_t *ej, int32_t *ed,
  *                   list complete up to max_diff and on_demand_k = 2*max_diff this gives exactly the
  *                   clusters of the full table (lookups never leave a connected component).  The
  *                   drop-in pacybara_cluster.py never sets it: there the EDFILE is the only authority.
- *   shard_rank / shard_count  components are dealt round-robin; entries of components owned by
- *                   other shards are left at PCB_FILL (combine shards with an element-wise max)
+ *   shard_rank / shard_count  a connected component belongs to shard (smallest bucket of the component mod
+ *                   shard_count); entries of reads owned by other shards are left at PCB_FILL, the call regions are
+ *                   laid out identically on every shard (combine shards with an element-wise max)
  * outputs (all [R] unless noted; a "row" is a cluster or an unclustered read and is named by
  * its representative read = first member)
  *   read_root       representative read of the row the read belongs to

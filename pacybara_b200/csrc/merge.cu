@@ -3,7 +3,8 @@
 // the reference's sequential algorithm (merge_core.h).
 //
 //   components    lock-free union-find over the pairs a pass visits (1 <= ed <= maxDiff);
-//                 label = smallest bucket of the component
+//                 label = smallest bucket of the component; a component belongs to shard (label mod shard_count)
+//                 and everything below only touches this shard's buckets, reads and pairs
 //   renumbering   buckets are sorted by (component work descending, component label), reads by
 //                 (new bucket, arrival order), and every per-read / per-bucket array the replay touches
 //                 is gathered into that order: a component's working set becomes a handful of
@@ -70,14 +71,35 @@ __global__ void uf_label_kernel(int32_t *parent, const int32_t *__restrict__ buc
   atomicAdd(&work[l], (uint32_t)(bucket_ptr[b + 1] - bucket_ptr[b]));
 }
 
+// lab_nnz[root] = genotype entries of the whole component: the call region of a component is laid out by its label,
+// which every shard computes identically (so shards can be combined element-wise)
+__global__ void label_nnz_kernel(const int32_t *__restrict__ bucket_ptr, const int32_t *__restrict__ bucket_reads,
+                                 const int32_t *__restrict__ geno_ptr, const int32_t *__restrict__ label, int32_t U,
+                                 uint32_t *__restrict__ lab_nnz) {
+  int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= U) return;
+  uint32_t nnz = 0;
+  for (int32_t x = bucket_ptr[b]; x < bucket_ptr[b + 1]; x++) {
+    int32_t r = bucket_reads[x];
+    nnz += (uint32_t)(geno_ptr[r + 1] - geno_ptr[r]);
+  }
+  if (nnz) atomicAdd(&lab_nnz[label[b]], nnz);
+}
+
+// counters: [0] buckets of this shard, [1] components of this shard, [2] heavy components of this shard, [3] reads of this shard
+// A component belongs to shard (label mod shard_count); the buckets of other shards sort behind everything and are
+// ignored from here on, so the preprocessing below only touches this shard's part of the library.
 __global__ void comp_keys_kernel(const int32_t *__restrict__ label, const uint32_t *__restrict__ work, int32_t U, int bbits,
-                                 uint64_t *__restrict__ key, uint32_t *__restrict__ val) {
+                                 int32_t shard_rank, int32_t shard_count, uint64_t *__restrict__ key, uint32_t *__restrict__ val,
+                                 uint32_t *__restrict__ counters) {
   int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= U) return;
   uint32_t l = (uint32_t)label[b];
   uint32_t w = work[l] < WORK_CAP ? work[l] : WORK_CAP;
-  key[b] = ((uint64_t)(WORK_CAP - w) << bbits) | l;          // heavy components first
+  bool mine = (int32_t)(l % (uint32_t)shard_count) == shard_rank;
+  key[b] = ((uint64_t)(mine ? 0 : 1) << (bbits + 10)) | ((uint64_t)(WORK_CAP - w) << bbits) | l;   // mine first, heavy first
   val[b] = (uint32_t)b;
+  if (mine) atomicAdd(&counters[0], 1u);
 }
 
 __global__ void comp_flag_kernel(const uint64_t *__restrict__ key, int32_t U, uint32_t *__restrict__ flag) {
@@ -85,24 +107,38 @@ __global__ void comp_flag_kernel(const uint64_t *__restrict__ key, int32_t U, ui
   if (i < U) flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1u : 0u;
 }
 
-// sorted position i = new bucket id.  rank = exclusive scan of the head flags.
+// sorted position i = new bucket id (this shard's buckets come first).  rank = exclusive scan of the head flags.
 __global__ void comp_assign_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ val, const uint32_t *__restrict__ rank,
                                    const int32_t *__restrict__ bucket_ptr, int32_t U, int32_t n_comp,
                                    int32_t *__restrict__ old_of_new_b, int32_t *__restrict__ new_of_old_b,
                                    int32_t *__restrict__ comp_ptr, int32_t *__restrict__ comp_of_new_b, uint32_t *__restrict__ nb_cnt,
-                                   int bbits, uint32_t heavy_reads, uint32_t *__restrict__ n_heavy) {
+                                   int32_t *__restrict__ comp_label, int bbits, uint32_t heavy_reads, uint32_t *__restrict__ counters) {
   int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= U) return;
-  bool head = i == 0 || key[i] != key[i - 1];
-  if (head && WORK_CAP - (uint32_t)(key[i] >> bbits) >= heavy_reads) atomicAdd(n_heavy, 1u);   // components come heaviest first
-  int32_t c = (int32_t)rank[i] + (head ? 1 : 0) - 1;
-  int32_t b = (int32_t)val[i];
-  old_of_new_b[i] = b;
-  new_of_old_b[b] = i;
-  comp_of_new_b[i] = c;
-  nb_cnt[i] = (uint32_t)(bucket_ptr[b + 1] - bucket_ptr[b]);
-  if (head) comp_ptr[c] = i;
+  const bool head = i == 0 || key[i] != key[i - 1];
+  const bool mine = (key[i] >> (bbits + 10)) == 0;
+  const int32_t c = (int32_t)rank[i] + (head ? 1 : 0) - 1;
+  const int32_t b = (int32_t)val[i];
+  if (head) comp_ptr[c] = i;                     // the first bucket of another shard closes this shard's last component
+  if (mine) {
+    old_of_new_b[i] = b;
+    new_of_old_b[b] = i;
+    comp_of_new_b[i] = c;
+    nb_cnt[i] = (uint32_t)(bucket_ptr[b + 1] - bucket_ptr[b]);
+    if (head) {
+      comp_label[c] = (int32_t)(key[i] & ((1ull << bbits) - 1ull));
+      atomicAdd(&counters[1], 1u);
+      if (WORK_CAP - (uint32_t)((key[i] >> bbits) & WORK_CAP) >= heavy_reads) atomicAdd(&counters[2], 1u);   // heaviest first
+    }
+  } else {
+    new_of_old_b[b] = -1;
+    nb_cnt[i] = 0;
+  }
   if (i == U - 1) { comp_ptr[n_comp] = U; nb_cnt[U] = 0; }
+}
+
+__global__ void shard_reads_kernel(const uint32_t *__restrict__ nb_ptr, uint32_t *__restrict__ counters) {
+  counters[3] = nb_ptr[counters[0]];
 }
 
 // one thread per position x of the caller's bucket_reads: where does that read go?
@@ -120,6 +156,7 @@ __global__ void read_renumber_kernel(const int32_t *__restrict__ bucket_ptr, con
     if (bucket_ptr[mid] <= x) lo = mid; else hi = mid;
   }
   int32_t nb = new_of_old_b[lo];
+  if (nb < 0) return;                            // a bucket of another shard
   int32_t nr = (int32_t)nb_ptr[nb] + (x - bucket_ptr[lo]);
   int32_t r = bucket_reads[x];
   old_of_new_r[nr] = r;
@@ -128,14 +165,14 @@ __global__ void read_renumber_kernel(const int32_t *__restrict__ bucket_ptr, con
   n_bc[nr] = bc_id[r];
   if (up_id) n_up[nr] = up_id[r];
   n_gcnt[nr] = (uint32_t)(geno_ptr[r + 1] - geno_ptr[r]);
-  if (x == R - 1) n_gcnt[R] = 0;
 }
 
 __global__ void geno_gather_kernel(const int32_t *__restrict__ old_of_new_r, const int32_t *__restrict__ geno_ptr,
                                    const int32_t *__restrict__ geno_mut, const int32_t *__restrict__ geno_q, int32_t R,
-                                   const uint32_t *__restrict__ n_gptr, int32_t *__restrict__ n_gmut, int32_t *__restrict__ n_gq) {
+                                   const uint32_t *__restrict__ n_gptr, int32_t *__restrict__ n_gmut, int32_t *__restrict__ n_gq,
+                                   const uint32_t *__restrict__ counters) {
   int32_t nr = blockIdx.x * blockDim.x + threadIdx.x;
-  if (nr >= R) return;
+  if (nr >= R || (uint32_t)nr >= counters[3]) return;
   int32_t r = old_of_new_r[nr];
   int32_t src = geno_ptr[r], n = geno_ptr[r + 1] - src;
   uint32_t dst = n_gptr[nr];
@@ -144,22 +181,40 @@ __global__ void geno_gather_kernel(const int32_t *__restrict__ old_of_new_r, con
 
 __global__ void planes_gather_kernel(const int32_t *__restrict__ old_of_new_b, const ulonglong2 *__restrict__ planes,
                                      const int32_t *__restrict__ blen, int32_t U, ulonglong2 *__restrict__ n_planes,
-                                     int32_t *__restrict__ n_blen) {
+                                     int32_t *__restrict__ n_blen, const uint32_t *__restrict__ counters) {
   int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= U) return;
+  if (i >= U || (uint32_t)i >= counters[0]) return;
   n_planes[i] = planes[old_of_new_b[i]];
   n_blen[i] = blen[old_of_new_b[i]];
 }
 
-__global__ void adj_keys_kernel(const int32_t *__restrict__ pq, const int32_t *__restrict__ pr, const int32_t *__restrict__ pd,
-                                int64_t n_pairs, const int32_t *__restrict__ new_of_old_b, int shift,
-                                uint64_t *__restrict__ key, uint32_t *__restrict__ val, uint32_t *__restrict__ adj_cnt) {
+// the pairs whose two buckets belong to this shard, in their original order, in the new bucket numbering
+__global__ void pair_flag_kernel(const int32_t *__restrict__ pq, const int32_t *__restrict__ pr, int64_t n_pairs,
+                                 const int32_t *__restrict__ new_of_old_b, uint32_t *__restrict__ flag) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n_pairs) flag[p] = (new_of_old_b[pq[p]] >= 0 && new_of_old_b[pr[p]] >= 0) ? 1u : 0u;
+}
+__global__ void pair_compact_kernel(const int32_t *__restrict__ pq, const int32_t *__restrict__ pr, const int32_t *__restrict__ pd,
+                                    const int32_t *__restrict__ ped, int64_t n_pairs, const int32_t *__restrict__ new_of_old_b,
+                                    const uint32_t *__restrict__ pos, int32_t *__restrict__ mq, int32_t *__restrict__ mr,
+                                    int32_t *__restrict__ md, int32_t *__restrict__ me) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_pairs) return;
-  uint32_t a = (uint32_t)new_of_old_b[pq[p]], b = (uint32_t)new_of_old_b[pr[p]];
+  int32_t a = new_of_old_b[pq[p]], b = new_of_old_b[pr[p]];
+  if (a < 0 || b < 0) return;
+  uint32_t at = pos[p];
+  mq[at] = a; mr[at] = b; md[at] = pd[p]; me[at] = ped[p];
+}
+
+__global__ void adj_keys_kernel(const int32_t *__restrict__ mq, const int32_t *__restrict__ mr, const int32_t *__restrict__ md,
+                                int64_t n_pairs, int shift, uint64_t *__restrict__ key, uint32_t *__restrict__ val,
+                                uint32_t *__restrict__ adj_cnt) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  uint32_t a = (uint32_t)mq[p], b = (uint32_t)mr[p];
   key[2 * p] = ((uint64_t)a << shift) | b;
   key[2 * p + 1] = ((uint64_t)b << shift) | a;
-  val[2 * p] = val[2 * p + 1] = (uint32_t)pd[p];
+  val[2 * p] = val[2 * p + 1] = (uint32_t)md[p];
   atomicAdd(&adj_cnt[a], 1u);
   atomicAdd(&adj_cnt[b], 1u);
 }
@@ -172,37 +227,37 @@ __global__ void adj_unpack_kernel(const uint64_t *__restrict__ key, const uint32
   d[i] = (int32_t)val[i];
 }
 
-__global__ void cpair_keys_kernel(const int32_t *__restrict__ pq, const int32_t *__restrict__ ped, int64_t n_pairs,
-                                  const int32_t *__restrict__ new_of_old_b, const int32_t *__restrict__ comp_of_new_b,
-                                  int32_t n_comp, int32_t max_diff,
+__global__ void cpair_keys_kernel(const int32_t *__restrict__ mq, const int32_t *__restrict__ me, int64_t n_pairs,
+                                  const int32_t *__restrict__ comp_of_new_b, int32_t n_comp, int32_t max_diff,
                                   uint64_t *__restrict__ key, uint32_t *__restrict__ val, uint32_t *__restrict__ cnt) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n_pairs) return;
-  int32_t ed = ped[p];
+  int32_t ed = me[p];
   bool visit = ed >= 1 && ed <= max_diff;
-  uint32_t c = visit ? (uint32_t)comp_of_new_b[new_of_old_b[pq[p]]] : (uint32_t)n_comp;
+  uint32_t c = visit ? (uint32_t)comp_of_new_b[mq[p]] : (uint32_t)n_comp;
   key[p] = ((uint64_t)c << 2) | (uint64_t)(visit ? ed : 0);
   val[p] = (uint32_t)p;
   if (visit) atomicAdd(&cnt[c], 1u);
 }
 
-__global__ void cpair_gather_kernel(const uint32_t *__restrict__ order, int64_t n, const int32_t *__restrict__ pq,
-                                    const int32_t *__restrict__ pr, const int32_t *__restrict__ ped,
-                                    const int32_t *__restrict__ new_of_old_b,
+__global__ void cpair_gather_kernel(const uint32_t *__restrict__ order, int64_t n, const int32_t *__restrict__ mq,
+                                    const int32_t *__restrict__ mr, const int32_t *__restrict__ me,
                                     int32_t *__restrict__ cq, int32_t *__restrict__ cr, int32_t *__restrict__ ce) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint32_t p = order[i];
-  cq[i] = new_of_old_b[pq[p]]; cr[i] = new_of_old_b[pr[p]]; ce[i] = ped[p];
+  cq[i] = mq[p]; cr[i] = mr[p]; ce[i] = me[p];
 }
 
-// components are contiguous in the new numbering: sizes come straight from the prefix arrays
+// components are contiguous in the new numbering: sizes come straight from the prefix arrays; the call region of a
+// component sits where its label puts it (label_nnz_kernel)
 __global__ void comp_scratch_kernel(const int32_t *__restrict__ comp_ptr, const uint32_t *__restrict__ nb_ptr,
-                                    const uint32_t *__restrict__ n_gptr, int32_t n_comp, int32_t *__restrict__ slot_cap,
-                                    int64_t *__restrict__ slot_sz, int64_t *__restrict__ list_sz, int64_t *__restrict__ call_sz) {
+                                    const uint32_t *__restrict__ n_gptr, int32_t n_comp, const int32_t *__restrict__ comp_label,
+                                    const uint32_t *__restrict__ lab_call_off, int32_t *__restrict__ slot_cap,
+                                    int64_t *__restrict__ slot_sz, int64_t *__restrict__ list_sz, int64_t *__restrict__ call_off) {
   int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c > n_comp) return;
-  if (c == n_comp) { slot_sz[c] = list_sz[c] = call_sz[c] = 0; return; }
+  if (c == n_comp) { slot_sz[c] = list_sz[c] = 0; call_off[c] = 0; return; }
   uint32_t r_lo = nb_ptr[comp_ptr[c]], r_hi = nb_ptr[comp_ptr[c + 1]];
   unsigned long long reads = r_hi - r_lo, nnz = n_gptr[r_hi] - n_gptr[r_lo];
   unsigned long long need = 2ull * (reads > nnz ? reads : nnz);
@@ -212,7 +267,7 @@ __global__ void comp_scratch_kernel(const int32_t *__restrict__ comp_ptr, const 
   slot_cap[c] = (int32_t)cap;
   slot_sz[c] = (int64_t)cap;
   list_sz[c] = (int64_t)(2ull * (reads + nnz) + 8);      // 4 counters, touched list, run list (merge_warp.cuh)
-  call_sz[c] = (int64_t)nnz;
+  call_off[c] = (int64_t)lab_call_off[comp_label[c]];
 }
 
 // Two launch shapes for the replay (merge_core.h / merge_warp.cuh):
@@ -299,7 +354,7 @@ __global__ void scatter_outputs_kernel(int32_t R, const int32_t *__restrict__ ol
                                        const int32_t *__restrict__ t_bc, const int32_t *__restrict__ t_up,
                                        const int64_t *__restrict__ t_calloff, const int32_t *__restrict__ t_calln, MergeOut out) {
   int32_t nr = blockIdx.x * blockDim.x + threadIdx.x;
-  if (nr >= R) return;
+  if (nr >= R) return;                              // R = reads of this shard
   int32_t r = old_of_new_r[nr];
   int32_t root = t_root[nr];
   out.read_root[r] = root == PCB_FILL ? PCB_FILL : old_of_new_r[root];
@@ -327,61 +382,88 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   const int bbits = bits_for((uint64_t)(U > 1 ? U - 1 : 1));
   const bool on_demand = in.planes != nullptr && in.compute_k >= 0;
 
-  // ---- components of the link graph, ordered by work
-  DevBuf<int32_t> label(ctx, U), old_of_new_b(ctx, U), new_of_old_b(ctx, U), comp_of_new_b(ctx, U), comp_ptr(ctx, (size_t)U + 1);
-  DevBuf<uint32_t> nb_ptr(ctx, (size_t)U + 1);
-  int32_t n_comp = 0;
-  DevBuf<uint32_t> d_n_heavy(ctx, 1);
+  // ---- components of the link graph; this shard's components first, heaviest first
+  DevBuf<int32_t> label(ctx, U), old_of_new_b(ctx, U), new_of_old_b(ctx, U), comp_of_new_b(ctx, U), comp_ptr(ctx, (size_t)U + 2),
+      comp_label(ctx, (size_t)U + 1);
+  DevBuf<uint32_t> nb_ptr(ctx, (size_t)U + 1), lab_call_off(ctx, (size_t)U + 1), counters(ctx, 4);
+  int32_t n_comp_all = 0;
   {
     DevBuf<int32_t> parent(ctx, U);
     DevBuf<uint32_t> work(ctx, U), rank(ctx, (size_t)U + 1);
     DevBuf<uint64_t> k0(ctx, U), k1(ctx, U);
     DevBuf<uint32_t> v0(ctx, U), v1(ctx, U);
     PCB_CUDA(cudaMemsetAsync(work.p, 0, (size_t)U * sizeof(uint32_t), ctx->stream));
+    PCB_CUDA(cudaMemsetAsync(counters.p, 0, 4 * sizeof(uint32_t), ctx->stream));
+    PCB_CUDA(cudaMemsetAsync(lab_call_off.p, 0, ((size_t)U + 1) * sizeof(uint32_t), ctx->stream));
     PCB_LAUNCH(ctx, uf_init_kernel, grid_for(U, 256), 256, 0, parent.p, U);
     if (P > 0) PCB_LAUNCH(ctx, uf_union_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_r, in.pair_ed, P, in.max_diff, parent.p);
     PCB_LAUNCH(ctx, uf_label_kernel, grid_for(U, 256), 256, 0, parent.p, in.bucket_ptr, U, label.p, work.p);
-    PCB_LAUNCH(ctx, comp_keys_kernel, grid_for(U, 256), 256, 0, label.p, work.p, U, bbits, k0.p, v0.p);
-    int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, U, bbits + 10);
+    PCB_LAUNCH(ctx, label_nnz_kernel, grid_for(U, 256), 256, 0, in.bucket_ptr, in.bucket_reads, in.geno_ptr, label.p, U, lab_call_off.p);
+    exclusive_scan_u32(ctx, lab_call_off.p, lab_call_off.p, (size_t)U + 1);
+    PCB_LAUNCH(ctx, comp_keys_kernel, grid_for(U, 256), 256, 0, label.p, work.p, U, bbits, in.shard_rank, in.shard_count, k0.p, v0.p,
+               counters.p);
+    int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, U, bbits + 11);
     uint64_t *sk = w ? k1.p : k0.p;
     uint32_t *sv = w ? v1.p : v0.p;
     PCB_LAUNCH(ctx, comp_flag_kernel, grid_for(U, 256), 256, 0, sk, U, rank.p);
     PCB_CUDA(cudaMemsetAsync(rank.p + U, 0, sizeof(uint32_t), ctx->stream));
     exclusive_scan_u32(ctx, rank.p, rank.p, (size_t)U + 1);              // one past the end: the total
-    n_comp = (int32_t)read_scalar(ctx, rank.p + U);
-    PCB_CUDA(cudaMemsetAsync(d_n_heavy.p, 0, sizeof(uint32_t), ctx->stream));
-    PCB_LAUNCH(ctx, comp_assign_kernel, grid_for(U, 256), 256, 0, sk, sv, rank.p, in.bucket_ptr, U, n_comp, old_of_new_b.p,
-               new_of_old_b.p, comp_ptr.p, comp_of_new_b.p, nb_ptr.p, bbits, (uint32_t)HEAVY_READS, d_n_heavy.p);
+    n_comp_all = (int32_t)read_scalar(ctx, rank.p + U);
+    PCB_LAUNCH(ctx, comp_assign_kernel, grid_for(U, 256), 256, 0, sk, sv, rank.p, in.bucket_ptr, U, n_comp_all, old_of_new_b.p,
+               new_of_old_b.p, comp_ptr.p, comp_of_new_b.p, nb_ptr.p, comp_label.p, bbits, (uint32_t)HEAVY_READS, counters.p);
     exclusive_scan_u32(ctx, nb_ptr.p, nb_ptr.p, (size_t)U + 1);
+    PCB_LAUNCH(ctx, shard_reads_kernel, 1, 1, 0, nb_ptr.p, counters.p);
   }
-  ctx->stats[PCB_STAT_COMPONENTS] = n_comp;
+  ctx->stats[PCB_STAT_COMPONENTS] = n_comp_all;
 
-  // ---- reads and genotypes gathered into component order
+  // ---- this shard's pairs, compacted (original order kept) and renumbered
+  DevBuf<uint32_t> ppos(ctx, (size_t)P + 1);
+  PCB_CUDA(cudaMemsetAsync(ppos.p, 0, ((size_t)P + 1) * sizeof(uint32_t), ctx->stream));
+  if (P > 0) {
+    PCB_LAUNCH(ctx, pair_flag_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_r, P, new_of_old_b.p, ppos.p);
+    exclusive_scan_u32(ctx, ppos.p, ppos.p, (size_t)P + 1);
+  }
+  uint32_t h_counters[4], h_pm = 0;                                     // one round trip for all the shard sizes
+  PCB_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));
+  PCB_CUDA(cudaMemcpyAsync(&h_pm, ppos.p + P, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int32_t Um = (int32_t)h_counters[0], n_comp = (int32_t)h_counters[1], Rm = (int32_t)h_counters[3];
+  const uint32_t h_n_heavy = h_counters[2];
+  const int64_t Pm = (int64_t)h_pm;
+  (void)Um;
+  DevBuf<int32_t> mq(ctx, (size_t)Pm), mr(ctx, (size_t)Pm), md(ctx, (size_t)Pm), me(ctx, (size_t)Pm);
+  if (Pm > 0)
+    PCB_LAUNCH(ctx, pair_compact_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_r, in.pair_d, in.pair_ed, P, new_of_old_b.p,
+               ppos.p, mq.p, mr.p, md.p, me.p);
+
+  // ---- reads and genotypes of this shard gathered into component order
   DevBuf<int32_t> old_of_new_r(ctx, R), n_bor(ctx, R), n_lex(ctx, R), n_bc(ctx, R), n_up(ctx, in.up_id ? R : 1);
   DevBuf<uint32_t> n_gptr(ctx, (size_t)R + 1);
   DevBuf<int32_t> n_gmut(ctx, (size_t)nnz), n_gq(ctx, (size_t)nnz);
+  PCB_CUDA(cudaMemsetAsync(n_gptr.p, 0, ((size_t)R + 1) * sizeof(uint32_t), ctx->stream));
   PCB_LAUNCH(ctx, read_renumber_kernel, grid_for(R, 256), 256, 0, in.bucket_ptr, in.bucket_reads, R, U, new_of_old_b.p, nb_ptr.p,
              in.lexrank, in.bc_id, in.up_id, in.geno_ptr, old_of_new_r.p, n_bor.p, n_lex.p, n_bc.p, n_up.p, n_gptr.p);
-  exclusive_scan_u32(ctx, n_gptr.p, n_gptr.p, (size_t)R + 1);
-  PCB_LAUNCH(ctx, geno_gather_kernel, grid_for(R, 256), 256, 0, old_of_new_r.p, in.geno_ptr, in.geno_mut, in.geno_q, R, n_gptr.p,
-             n_gmut.p, n_gq.p);
+  exclusive_scan_u32(ctx, n_gptr.p, n_gptr.p, (size_t)Rm + 1);
+  if (Rm > 0)
+    PCB_LAUNCH(ctx, geno_gather_kernel, grid_for(Rm, 256), 256, 0, old_of_new_r.p, in.geno_ptr, in.geno_mut, in.geno_q, Rm, n_gptr.p,
+               n_gmut.p, n_gq.p, counters.p);
   DevBuf<ulonglong2> n_planes(ctx, on_demand ? U : 1);
   DevBuf<int32_t> n_blen(ctx, on_demand ? U : 1);
   if (on_demand)
-    PCB_LAUNCH(ctx, planes_gather_kernel, grid_for(U, 256), 256, 0, old_of_new_b.p, in.planes, in.blen, U, n_planes.p, n_blen.p);
+    PCB_LAUNCH(ctx, planes_gather_kernel, grid_for(U, 256), 256, 0, old_of_new_b.p, in.planes, in.blen, U, n_planes.p, n_blen.p,
+               counters.p);
 
   // ---- adjacency (new bucket ids)
-  DevBuf<int32_t> adj_ptr(ctx, (size_t)U + 1), adj_nbr(ctx, (size_t)(2 * P)), adj_d(ctx, (size_t)(2 * P));
+  DevBuf<int32_t> adj_ptr(ctx, (size_t)U + 1), adj_nbr(ctx, (size_t)(2 * Pm)), adj_d(ctx, (size_t)(2 * Pm));
   {
     DevBuf<uint32_t> cnt(ctx, (size_t)U + 1);
     PCB_CUDA(cudaMemsetAsync(cnt.p, 0, ((size_t)U + 1) * sizeof(uint32_t), ctx->stream));
-    if (P > 0) {
-      DevBuf<uint64_t> k0(ctx, 2 * P), k1(ctx, 2 * P);
-      DevBuf<uint32_t> v0(ctx, 2 * P), v1(ctx, 2 * P);
-      PCB_LAUNCH(ctx, adj_keys_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_r, in.pair_d, P, new_of_old_b.p, bbits,
-                 k0.p, v0.p, cnt.p);
-      int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, 2 * P, 2 * bbits);
-      PCB_LAUNCH(ctx, adj_unpack_kernel, grid_for(2 * P, 256), 256, 0, w ? k1.p : k0.p, w ? v1.p : v0.p, 2 * P, bbits,
+    if (Pm > 0) {
+      DevBuf<uint64_t> k0(ctx, 2 * Pm), k1(ctx, 2 * Pm);
+      DevBuf<uint32_t> v0(ctx, 2 * Pm), v1(ctx, 2 * Pm);
+      PCB_LAUNCH(ctx, adj_keys_kernel, grid_for(Pm, 256), 256, 0, mq.p, mr.p, md.p, Pm, bbits, k0.p, v0.p, cnt.p);
+      int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, 2 * Pm, 2 * bbits);
+      PCB_LAUNCH(ctx, adj_unpack_kernel, grid_for(2 * Pm, 256), 256, 0, w ? k1.p : k0.p, w ? v1.p : v0.p, 2 * Pm, bbits,
                  adj_nbr.p, adj_d.p);
     }
     exclusive_scan_u32(ctx, cnt.p, cnt.p, (size_t)U + 1);
@@ -389,18 +471,17 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   }
 
   // ---- visiting pairs per component (stable: the caller's visiting order survives inside a component)
-  DevBuf<int32_t> cpair_ptr(ctx, (size_t)n_comp + 2), cq(ctx, (size_t)P), cr(ctx, (size_t)P), ce(ctx, (size_t)P);
+  DevBuf<int32_t> cpair_ptr(ctx, (size_t)n_comp + 2), cq(ctx, (size_t)Pm), cr(ctx, (size_t)Pm), ce(ctx, (size_t)Pm);
   {
     DevBuf<uint32_t> cnt(ctx, (size_t)n_comp + 2);
     PCB_CUDA(cudaMemsetAsync(cnt.p, 0, ((size_t)n_comp + 2) * sizeof(uint32_t), ctx->stream));
-    if (P > 0) {
-      DevBuf<uint64_t> k0(ctx, P), k1(ctx, P);
-      DevBuf<uint32_t> v0(ctx, P), v1(ctx, P);
-      PCB_LAUNCH(ctx, cpair_keys_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_ed, P, new_of_old_b.p, comp_of_new_b.p,
-                 n_comp, in.max_diff, k0.p, v0.p, cnt.p);
-      int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, P, bits_for((uint64_t)n_comp) + 2);
-      PCB_LAUNCH(ctx, cpair_gather_kernel, grid_for(P, 256), 256, 0, w ? v1.p : v0.p, P, in.pair_q, in.pair_r, in.pair_ed,
-                 new_of_old_b.p, cq.p, cr.p, ce.p);
+    if (Pm > 0) {
+      DevBuf<uint64_t> k0(ctx, Pm), k1(ctx, Pm);
+      DevBuf<uint32_t> v0(ctx, Pm), v1(ctx, Pm);
+      PCB_LAUNCH(ctx, cpair_keys_kernel, grid_for(Pm, 256), 256, 0, mq.p, me.p, Pm, comp_of_new_b.p, n_comp, in.max_diff, k0.p, v0.p,
+                 cnt.p);
+      int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, Pm, bits_for((uint64_t)n_comp) + 2);
+      PCB_LAUNCH(ctx, cpair_gather_kernel, grid_for(Pm, 256), 256, 0, w ? v1.p : v0.p, Pm, mq.p, mr.p, me.p, cq.p, cr.p, ce.p);
     }
     exclusive_scan_u32(ctx, cnt.p, cnt.p, (size_t)n_comp + 2);
     PCB_CUDA(cudaMemcpyAsync(cpair_ptr.p, cnt.p, ((size_t)n_comp + 2) * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
@@ -409,16 +490,13 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   // ---- scratch
   DevBuf<int32_t> slot_cap(ctx, (size_t)n_comp + 1);
   DevBuf<int64_t> slot_off(ctx, (size_t)n_comp + 1), list_off(ctx, (size_t)n_comp + 1), call_off(ctx, (size_t)n_comp + 1);
-  PCB_LAUNCH(ctx, comp_scratch_kernel, grid_for((size_t)n_comp + 1, 256), 256, 0, comp_ptr.p, nb_ptr.p, n_gptr.p, n_comp, slot_cap.p,
-             slot_off.p, list_off.p, call_off.p);
+  PCB_LAUNCH(ctx, comp_scratch_kernel, grid_for((size_t)n_comp + 1, 256), 256, 0, comp_ptr.p, nb_ptr.p, n_gptr.p, n_comp, comp_label.p,
+             lab_call_off.p, slot_cap.p, slot_off.p, list_off.p, call_off.p);
   exclusive_scan_i64(ctx, slot_off.p, slot_off.p, (size_t)n_comp + 1);
   exclusive_scan_i64(ctx, list_off.p, list_off.p, (size_t)n_comp + 1);
-  exclusive_scan_i64(ctx, call_off.p, call_off.p, (size_t)n_comp + 1);
   int64_t n_slots = 0, n_list = 0;
-  uint32_t h_n_heavy = 0;                                               // three scalars, one round trip
   PCB_CUDA(cudaMemcpyAsync(&n_slots, slot_off.p + n_comp, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
   PCB_CUDA(cudaMemcpyAsync(&n_list, list_off.p + n_comp, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  PCB_CUDA(cudaMemcpyAsync(&h_n_heavy, d_n_heavy.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   PCB_CUDA(cudaStreamSynchronize(ctx->stream));
   DevBuf<GenoSlot> slots(ctx, (size_t)n_slots);
   DevBuf<int32_t> lists(ctx, (size_t)n_list + 1);
@@ -432,9 +510,13 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   PCB_CUDA(cudaMemsetAsync(rd_slot.p, 0xFF, (size_t)R * sizeof(int32_t), ctx->stream));
   PCB_CUDA(cudaMemsetAsync(rd_next.p, 0xFF, (size_t)R * sizeof(int32_t), ctx->stream));
   PCB_CUDA(cudaMemsetAsync(status.p, 0, 4 * sizeof(int32_t), ctx->stream));
-  // everything starts as "not mine" (rows of components another shard owns, per-row fields of non-representative reads)
-  PCB_LAUNCH(ctx, init_outputs_kernel, grid_for((size_t)(R > nnz ? R : nnz), 256), 256, 0, R, nnz, t_root.p, t_pos.p, t_size.p,
+  // everything starts as "not mine": the per-row fields of non-representative reads (new numbering, this shard's reads),
+  // the call array, and -- when the library is sharded -- the caller's arrays for the reads other shards own
+  PCB_LAUNCH(ctx, init_outputs_kernel, grid_for((size_t)(Rm > nnz ? Rm : nnz) + 1, 256), 256, 0, Rm, nnz, t_root.p, t_pos.p, t_size.p,
              t_key.p, t_bc.p, t_up.p, t_calloff.p, t_calln.p, out.call_mut);
+  if (in.shard_count > 1)
+    PCB_LAUNCH(ctx, init_outputs_kernel, grid_for((size_t)R, 256), 256, 0, R, (int64_t)0, out.read_root, out.read_pos, out.row_size,
+               out.row_key, out.row_bc, out.row_up, out.row_call_off, out.row_call_n, out.call_mut);
 
   MergeCtx c;
   memset(&c, 0, sizeof(c));
@@ -465,23 +547,20 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   if (mode && strcmp(mode, "warp") == 0) n_warp = n_comp;
   if (mode && strcmp(mode, "thread") == 0) n_warp = 0;
   if (n_warp > 0)
-    PCB_LAUNCH(ctx, component_kernel_warp, grid_for((size_t)n_warp * 32, COMP_BLOCK), COMP_BLOCK, 0, c, 0, n_warp, in.shard_rank,
-               in.shard_count);
+    PCB_LAUNCH(ctx, component_kernel_warp, grid_for((size_t)n_warp * 32, COMP_BLOCK), COMP_BLOCK, 0, c, 0, n_warp, 0, 1);
   if (n_warp < n_comp) {
     int per_warp = 4;
     if (const char *e = getenv("PCB_COMP_PER_WARP")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) per_warp = v; }
     size_t n_threads = ((size_t)(n_comp - n_warp) + per_warp - 1) / per_warp * 32;
     // three launches, one per phase: each kernel's code fits the instruction cache and its threads share a loop nest
-    PCB_LAUNCH(ctx, component_kernel_thread<1>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_warp, n_comp, in.shard_rank,
-               in.shard_count, per_warp);
-    PCB_LAUNCH(ctx, component_kernel_thread<2>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_warp, n_comp, in.shard_rank,
-               in.shard_count, per_warp);
-    PCB_LAUNCH(ctx, component_kernel_thread<3>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_warp, n_comp, in.shard_rank,
-               in.shard_count, per_warp);
+    PCB_LAUNCH(ctx, component_kernel_thread<1>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_warp, n_comp, 0, 1, per_warp);
+    PCB_LAUNCH(ctx, component_kernel_thread<2>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_warp, n_comp, 0, 1, per_warp);
+    PCB_LAUNCH(ctx, component_kernel_thread<3>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_warp, n_comp, 0, 1, per_warp);
   }
   stage_end(ctx, PCB_STAT_T_REPLAY_NS);
-  PCB_LAUNCH(ctx, scatter_outputs_kernel, grid_for(R, 256), 256, 0, R, old_of_new_r.p, old_of_new_b.p, t_root.p, t_pos.p, t_size.p,
-             t_key.p, t_bc.p, t_up.p, t_calloff.p, t_calln.p, out);
+  if (Rm > 0)
+    PCB_LAUNCH(ctx, scatter_outputs_kernel, grid_for(Rm, 256), 256, 0, Rm, old_of_new_r.p, old_of_new_b.p, t_root.p, t_pos.p, t_size.p,
+               t_key.p, t_bc.p, t_up.p, t_calloff.p, t_calln.p, out);
   stage_end(ctx, PCB_STAT_T_SCATTER_NS);
 
   int32_t h_status[4];

@@ -118,6 +118,6 @@ extern "C" int emul_merge(int32_t R, int32_t U, const int32_t *bucket_ptr, const
   c.call_mut = call_mut; c.status = status;
   c.prm.maxDiff = max_diff; c.prm.minQual = min_qual; c.prm.minMatches = min_matches; c.prm.minJaccard = min_jaccard;
   for (int32_t comp = 0; comp < n_comp; comp++)
-    if (comp % shard_count == shard_rank) process_component(c, global_state(c, comp), comp);
+    if (label[comp_buckets[comp_ptr[comp]]] % shard_count == shard_rank) process_component(c, global_state(c, comp), comp);
   return n_comp;
 }
