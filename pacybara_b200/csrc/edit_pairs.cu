@@ -25,6 +25,7 @@ struct SeedGeom {
   int32_t npos;      // target positions indexed: 0 .. npos-1
   int32_t k;
   uint32_t nbins;
+  uint64_t pos_mask; // positions a probe can ask for (piece start + shift of some query length): only those are indexed
 };
 
 __device__ __forceinline__ uint32_t seed_bin(const SeedGeom g, uint64_t L, uint64_t H, int src_pos, int bin_pos) {
@@ -37,7 +38,7 @@ __global__ void seed_count_kernel(const ulonglong2 *__restrict__ planes, const i
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)U * g.npos) return;
   int32_t j = (int32_t)(i / g.npos), p = (int32_t)(i % g.npos);
-  if (g.q > 0 && p + g.q > len[j]) return;
+  if (g.q > 0 && (p + g.q > len[j] || !((g.pos_mask >> p) & 1ull))) return;
   ulonglong2 pl = planes[j];
   atomicAdd(&bin_cnt[seed_bin(g, pl.x, pl.y, p, p)], 1u);
 }
@@ -47,7 +48,7 @@ __global__ void seed_fill_kernel(const ulonglong2 *__restrict__ planes, const in
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)U * g.npos) return;
   int32_t j = (int32_t)(i / g.npos), p = (int32_t)(i % g.npos);
-  if (g.q > 0 && p + g.q > len[j]) return;
+  if (g.q > 0 && (p + g.q > len[j] || !((g.pos_mask >> p) & 1ull))) return;
   ulonglong2 pl = planes[j];
   uint32_t at = atomicAdd(&cursor[seed_bin(g, pl.x, pl.y, p, p)], 1u);
   ent[at] = j;
@@ -247,7 +248,22 @@ void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q
     while (g.q > 0 && ((uint64_t)(bc.max_len - g.q + 1) << (2 * g.q)) > (1ull << 26)) g.q--;
     g.npos = g.q == 0 ? 1 : bc.max_len - g.q + 1;
     g.nbins = g.q == 0 ? 1u : (uint32_t)g.npos << (2 * g.q);
+    g.pos_mask = ~0ull;
     return g;
+  };
+  // the positions the probes of query lengths [lo, hi] can ask for: start of piece t (t * m / (k+1)) plus a shift in [-k, k]
+  auto probe_positions = [&](const SeedGeom &g, int32_t lo, int32_t hi) -> uint64_t {
+    if (g.q == 0) return ~0ull;
+    uint64_t mask = 0;
+    if (lo < bc.min_len) lo = bc.min_len;
+    if (hi > bc.max_len) hi = bc.max_len;
+    for (int32_t m = lo; m <= hi; m++)
+      for (int32_t t = 0; t <= k; t++)
+        for (int32_t sft = -k; sft <= k; sft++) {
+          int32_t pp = (int32_t)((int64_t)t * m / (k + 1)) + sft;
+          if (pp >= 0 && pp < g.npos) mask |= 1ull << pp;
+        }
+    return mask;
   };
   struct SeedIndex { SeedGeom g; DevBuf<uint32_t> bin_off; DevBuf<int32_t> ent; int32_t len_lo, len_hi; };
   SeedIndex idx[2];
@@ -263,6 +279,7 @@ void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q
   }
   ctx->stats[PCB_STAT_SEED_LEN] = idx[0].g.q;
   for (int t = 0; t < n_idx; t++) {
+    idx[t].g.pos_mask = probe_positions(idx[t].g, idx[t].len_lo, idx[t].len_hi);
     const SeedGeom &g = idx[t].g;
     DevBuf<uint32_t> cursor(ctx, (size_t)g.nbins + 1);
     idx[t].bin_off.alloc(ctx, (size_t)g.nbins + 1);
