@@ -205,6 +205,55 @@ int pcb_tag_rows(pcb_ctx *ctx, int mem, int32_t n_rows, const int32_t *row_bc, c
                  const int32_t *row_size, int32_t n_bc_ids, int32_t n_up_ids, double min_ratio,
                  uint8_t *collision, uint8_t *up_collision, uint8_t *usable);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * f2 -- tokenizers for the text files either side of the path (csrc/ingest.cu).
+ *
+ * They replace the reference's Python line loops
+ *     extracted-barcode FASTQ   src/pacybara_precluster.py:47-63
+ *     genoExtract.csv           src/pacybara_cluster.py:302-313
+ *     uptag FASTQ               src/pacybara_cluster.py:318-331
+ *     read-id string order      src/pacybara_cluster.py:152-157 (makePID)
+ * with passes over the decompressed bytes on the device.  A pcb_text owns (or borrows, PCB_MEM_DEVICE) the bytes
+ * of one file plus its newline index; it must be closed before its context is destroyed.  Whatever the passes do
+ * not model exactly (non-ASCII or NUL bytes, a lone CR, text before the first header, malformed fields, duplicate
+ * read ids, a mutation named twice in one read, a 64-bit hash collision) is counted in the n_exotic / n_bad /
+ * counters outputs and the result must then be discarded in favour of a line parser: nothing is guessed.
+ * `mem` describes the array arguments of each call (the bytes given to pcb_text_open included).
+ */
+typedef struct pcb_text pcb_text;
+
+int pcb_text_open(pcb_ctx *ctx, int mem, const uint8_t *bytes, int64_t n_bytes, pcb_text **out, int64_t *n_lines,
+                  int64_t *n_exotic);
+void pcb_text_close(pcb_ctx *ctx, pcb_text *text);
+
+/* FASTQ records as the reference's state machine finds them.  n_bad counts records whose quality and sequence
+ * lengths differ or whose header holds no id, plus text before the first header. */
+int pcb_fastq_records(pcb_ctx *ctx, pcb_text *fastq, int32_t *n_records, int32_t *max_len, int32_t *max_id_len,
+                      int64_t *n_bad);
+/* seq, qual: [n_records, stride] zero padded (stride a multiple of 4, >= max_len); id_off/id_len: the read id inside
+ * the file's bytes. */
+int pcb_fastq_fetch(pcb_ctx *ctx, pcb_text *fastq, int mem, int32_t stride, uint8_t *seq, uint8_t *qual, int32_t *length,
+                    int64_t *id_off, int32_t *id_len);
+/* rank[i] = position of string i (bytes off[i] .. off[i]+len[i] of `text`) in byte-wise string order; equal strings
+ * keep their index order. */
+int pcb_rank_strings(pcb_ctx *ctx, const pcb_text *text, int mem, const int64_t *off, const int32_t *len, int32_t n,
+                     int32_t max_len, int32_t *rank);
+/* Genotypes of the R reads whose ids are (id_off, id_len) in `fastq`, from the genoExtract text `geno`.
+ * counters[0] malformed lines, [1] reads without a record (the reference's KeyError), [2] reads naming a mutation
+ * twice, [3] duplicate read ids / hash collisions. */
+int pcb_geno_join(pcb_ctx *ctx, pcb_text *geno, const pcb_text *fastq, int mem, const int64_t *id_off, const int32_t *id_len,
+                  int32_t R, int64_t *nnz, int32_t *n_mut, int64_t counters[4]);
+/* geno_ptr [R+1], geno_mut / geno_q [nnz] (mutation ids are dense, 0 <= id < n_mut), mut_off / mut_len [n_mut]:
+ * where each mutation's name stands in the genoExtract bytes. */
+int pcb_geno_fetch(pcb_ctx *ctx, pcb_text *geno, int mem, int32_t *geno_ptr, int32_t *geno_mut, int32_t *geno_q,
+                   int64_t *mut_off, int32_t *mut_len);
+/* Uptags: n_records = (id, tag) records in the file, n_tags = distinct tags among the R reads.  counters as above
+ * ([0]: tags longer than 65535). */
+int pcb_uptag_join(pcb_ctx *ctx, pcb_text *uptag, const pcb_text *fastq, int mem, const int64_t *id_off,
+                   const int32_t *id_len, int32_t R, int64_t *n_records, int32_t *n_tags, int64_t counters[4]);
+/* up_id [R] (-1: the read has no uptag record), tag_off / tag_len [n_tags] into the uptag bytes. */
+int pcb_uptag_fetch(pcb_ctx *ctx, pcb_text *uptag, int mem, int32_t *up_id, int64_t *tag_off, int32_t *tag_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -257,3 +257,117 @@ class Context:
         out["n_buckets"] = int(nb.value)
         out["n_edges"] = int(ne.value)
         return out
+
+
+class Text:
+    """The bytes of one text file on the device plus its newline index (pcb_text; f2 tokenizers).
+
+    `data`: bytes / bytearray / numpy uint8 (copied to the device) or a torch CUDA uint8 tensor (used in place and kept
+    alive).  `device=True` in the fetch methods returns torch CUDA tensors, else numpy arrays."""
+
+    def __init__(self, ctx: Context, data):
+        self.ctx = ctx
+        self.h = None
+        self._keep = data
+        if _is_dev(data):
+            _torch()
+            mem = ctx._kind(data)
+            if data.dtype != _NP2TORCH[np.dtype(np.uint8)]:
+                raise TypeError("device text must be a uint8 tensor")
+            n, ptr = int(data.numel()), C.c_void_p(data.data_ptr())
+        else:
+            mem = _lib.MEM_HOST
+            arr = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, dtype=np.uint8)
+            self._keep = arr
+            n, ptr = int(arr.shape[0]), arr.ctypes.data_as(C.c_void_p)
+        h, nl, ex = C.c_void_p(), C.c_int64(0), C.c_int64(0)
+        ctx._check(ctx.lib.pcb_text_open(ctx.h, mem, ptr, n, C.byref(h), C.byref(nl), C.byref(ex)))
+        self.h = h
+        self.n_bytes, self.n_lines, self.n_exotic = n, int(nl.value), int(ex.value)
+        if mem == _lib.MEM_HOST:
+            self._keep = None          # the library holds its own copy
+
+    def close(self):
+        if self.h is not None and getattr(self.ctx, "h", None):
+            self.ctx.lib.pcb_text_close(self.ctx.h, self.h)
+        self.h = None
+        self._keep = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _mem(self, device: bool) -> int:
+        if device:
+            _torch()
+        return _lib.MEM_DEVICE if device else _lib.MEM_HOST
+
+    def fastq_records(self) -> Dict:
+        n, ml, mi, bad = C.c_int32(0), C.c_int32(0), C.c_int32(0), C.c_int64(0)
+        self.ctx._check(self.ctx.lib.pcb_fastq_records(self.ctx.h, self.h, C.byref(n), C.byref(ml), C.byref(mi), C.byref(bad)))
+        self.n_records = int(n.value)
+        return dict(n_records=int(n.value), max_len=int(ml.value), max_id_len=int(mi.value), n_bad=int(bad.value))
+
+    def fastq_fetch(self, stride: int, device: bool = True) -> Dict:
+        mem, R, o = self._mem(device), self.n_records, self.ctx._out
+        seq, p_seq = o(mem, (R, stride), np.uint8)
+        qual, p_qual = o(mem, (R, stride), np.uint8)
+        length, p_len = o(mem, (R,), np.int32)
+        id_off, p_off = o(mem, (R,), np.int64)
+        id_len, p_idl = o(mem, (R,), np.int32)
+        self.ctx._check(self.ctx.lib.pcb_fastq_fetch(self.ctx.h, self.h, mem, int(stride), p_seq, p_qual, p_len, p_off, p_idl))
+        return dict(seq=seq, qual=qual, length=length, id_off=id_off, id_len=id_len)
+
+    def rank_strings(self, off, length, max_len: int):
+        mem = self.ctx._kind(off, length)
+        keep: list = []
+        n = int(off.shape[0])
+        rank, p_rank = self.ctx._out(mem, (n,), np.int32)
+        self.ctx._check(self.ctx.lib.pcb_rank_strings(self.ctx.h, self.h, mem, self.ctx._in(off, np.int64, keep),
+                                                      self.ctx._in(length, np.int32, keep), n, int(max_len), p_rank))
+        return rank
+
+    def _join(self, fn, fastq: "Text", id_off, id_len):
+        mem = self.ctx._kind(id_off, id_len)
+        keep: list = []
+        R = int(id_off.shape[0])
+        a, b = C.c_int64(0), C.c_int32(0)
+        counters = (C.c_int64 * 4)()
+        self.ctx._check(fn(self.ctx.h, self.h, fastq.h, mem, self.ctx._in(id_off, np.int64, keep), self.ctx._in(id_len, np.int32, keep),
+                           R, C.byref(a), C.byref(b), counters))
+        self.n_reads = R
+        return int(a.value), int(b.value), [int(c) for c in counters]
+
+    def geno_join(self, fastq: "Text", id_off, id_len) -> Dict:
+        self.nnz, self.n_distinct, c = self._join(self.ctx.lib.pcb_geno_join, fastq, id_off, id_len)
+        return dict(nnz=self.nnz, n_mut=self.n_distinct, malformed=c[0], missing=c[1], repeated=c[2], collisions=c[3])
+
+    def geno_fetch(self, device: bool = True) -> Dict:
+        mem, o = self._mem(device), self.ctx._out
+        gp, p_gp = o(mem, (self.n_reads + 1,), np.int32)
+        gm, p_gm = o(mem, (self.nnz,), np.int32)
+        gq, p_gq = o(mem, (self.nnz,), np.int32)
+        mo, p_mo = o(mem, (self.n_distinct,), np.int64)
+        ml, p_ml = o(mem, (self.n_distinct,), np.int32)
+        self.ctx._check(self.ctx.lib.pcb_geno_fetch(self.ctx.h, self.h, mem, p_gp, p_gm, p_gq, p_mo, p_ml))
+        return dict(geno_ptr=gp, geno_mut=gm, geno_q=gq, mut_off=mo, mut_len=ml)
+
+    def uptag_join(self, fastq: "Text", id_off, id_len) -> Dict:
+        n_rec, self.n_distinct, c = self._join(self.ctx.lib.pcb_uptag_join, fastq, id_off, id_len)
+        return dict(n_records=n_rec, n_tags=self.n_distinct, too_long=c[0], collisions=c[3])
+
+    def uptag_fetch(self, device: bool = True) -> Dict:
+        mem, o = self._mem(device), self.ctx._out
+        up, p_up = o(mem, (self.n_reads,), np.int32)
+        to, p_to = o(mem, (self.n_distinct,), np.int64)
+        tl, p_tl = o(mem, (self.n_distinct,), np.int32)
+        self.ctx._check(self.ctx.lib.pcb_uptag_fetch(self.ctx.h, self.h, mem, p_up, p_to, p_tl))
+        return dict(up_id=up, tag_off=to, tag_len=tl)

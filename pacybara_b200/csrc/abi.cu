@@ -345,4 +345,132 @@ int pcb_tag_rows(pcb_ctx *ctx, int mem, int32_t n_rows, const int32_t *row_bc, c
   });
 }
 
+// ---- f2: tokenizers (ingest.cu)
+
+int pcb_text_open(pcb_ctx *ctx, int mem, const uint8_t *bytes, int64_t n_bytes, pcb_text **out, int64_t *n_lines, int64_t *n_exotic) {
+  if (out) *out = nullptr;
+  return guarded(ctx, [&] {
+    if (!out || n_bytes < 0 || (n_bytes && !bytes)) throw Error(PCB_E_INPUT, "bad arguments");
+    DevBuf<uint8_t> own;
+    if (mem != PCB_MEM_DEVICE) {
+      own.alloc(ctx, (size_t)n_bytes);
+      if (n_bytes) PCB_CUDA(cudaMemcpyAsync(own.p, bytes, (size_t)n_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    int64_t exotic = 0;
+    pcb_text *x = text_open_dev(ctx, bytes, std::move(own), n_bytes, &exotic);
+    int64_t nl, nnz; int32_t a, b, c;
+    text_sizes(x, &nl, &a, &nnz, &b, &c);
+    if (n_lines) *n_lines = nl;
+    if (n_exotic) *n_exotic = exotic;
+    *out = x;
+  });
+}
+
+void pcb_text_close(pcb_ctx *ctx, pcb_text *text) {
+  if (!ctx || !text) return;
+  cudaSetDevice(ctx->device);
+  text_free(text);
+}
+
+int pcb_fastq_records(pcb_ctx *ctx, pcb_text *fastq, int32_t *n_records, int32_t *max_len, int32_t *max_id_len, int64_t *n_bad) {
+  return guarded(ctx, [&] {
+    if (!fastq) throw Error(PCB_E_INPUT, "no text");
+    int32_t n = 0, ml = 0, mi = 0; int64_t bad = 0;
+    fastq_records_dev(ctx, fastq, &n, &ml, &mi, &bad);
+    if (n_records) *n_records = n;
+    if (max_len) *max_len = ml;
+    if (max_id_len) *max_id_len = mi;
+    if (n_bad) *n_bad = bad;
+  });
+}
+
+int pcb_fastq_fetch(pcb_ctx *ctx, pcb_text *fastq, int mem, int32_t stride, uint8_t *seq, uint8_t *qual, int32_t *length,
+                    int64_t *id_off, int32_t *id_len) {
+  return guarded(ctx, [&] {
+    if (!fastq) throw Error(PCB_E_INPUT, "no text");
+    int64_t nl, nnz; int32_t R, b, c;
+    text_sizes(fastq, &nl, &R, &nnz, &b, &c);
+    if (R < 0) throw Error(PCB_E_STATE, "pcb_fastq_fetch before pcb_fastq_records");
+    if (stride <= 0) throw Error(PCB_E_INPUT, "bad stride");
+    size_t cells = (size_t)R * stride;
+    OutArr<uint8_t> o_seq(ctx, mem, seq, cells), o_qual(ctx, mem, qual, cells);
+    OutArr<int32_t> o_len(ctx, mem, length, R), o_idl(ctx, mem, id_len, R);
+    OutArr<int64_t> o_ido(ctx, mem, id_off, R);
+    if (R > 0 && (!o_seq.p || !o_qual.p || !o_len.p || !o_idl.p || !o_ido.p)) throw Error(PCB_E_INPUT, "all five outputs are required");
+    fastq_fetch_dev(ctx, fastq, stride, o_seq.p, o_qual.p, o_len.p, o_ido.p, o_idl.p);
+    o_seq.commit(cells); o_qual.commit(cells); o_len.commit(R); o_idl.commit(R); o_ido.commit(R);
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int pcb_rank_strings(pcb_ctx *ctx, const pcb_text *text, int mem, const int64_t *off, const int32_t *len, int32_t n, int32_t max_len,
+                     int32_t *rank) {
+  return guarded(ctx, [&] {
+    if (!text || n < 0 || max_len < 0) throw Error(PCB_E_INPUT, "bad arguments");
+    InArr<int64_t> d_off(ctx, mem, off, n);
+    InArr<int32_t> d_len(ctx, mem, len, n);
+    OutArr<int32_t> o_rank(ctx, mem, rank, n);
+    rank_strings_dev(ctx, text, d_off.p, d_len.p, n, max_len, o_rank.p);
+    o_rank.commit(n);
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int pcb_geno_join(pcb_ctx *ctx, pcb_text *geno, const pcb_text *fastq, int mem, const int64_t *id_off, const int32_t *id_len, int32_t R,
+                  int64_t *nnz, int32_t *n_mut, int64_t counters[4]) {
+  return guarded(ctx, [&] {
+    if (!geno || !fastq || R < 0 || !counters) throw Error(PCB_E_INPUT, "bad arguments");
+    InArr<int64_t> d_off(ctx, mem, id_off, R);
+    InArr<int32_t> d_len(ctx, mem, id_len, R);
+    int64_t z = 0; int32_t m = 0;
+    geno_join_dev(ctx, geno, fastq, d_off.p, d_len.p, R, &z, &m, counters);
+    if (nnz) *nnz = z;
+    if (n_mut) *n_mut = m;
+  });
+}
+
+int pcb_geno_fetch(pcb_ctx *ctx, pcb_text *geno, int mem, int32_t *geno_ptr, int32_t *geno_mut, int32_t *geno_q, int64_t *mut_off,
+                   int32_t *mut_len) {
+  return guarded(ctx, [&] {
+    if (!geno) throw Error(PCB_E_INPUT, "no text");
+    int64_t nl, nnz; int32_t a, M, R;
+    text_sizes(geno, &nl, &a, &nnz, &M, &R);
+    if (nnz < 0 || R < 0) throw Error(PCB_E_STATE, "pcb_geno_fetch before pcb_geno_join");
+    OutArr<int32_t> o_ptr(ctx, mem, geno_ptr, (size_t)R + 1), o_mut(ctx, mem, geno_mut, nnz), o_q(ctx, mem, geno_q, nnz), o_ml(ctx, mem, mut_len, M);
+    OutArr<int64_t> o_mo(ctx, mem, mut_off, M);
+    if (!o_ptr.p || (nnz > 0 && (!o_mut.p || !o_q.p)) || (M > 0 && (!o_ml.p || !o_mo.p))) throw Error(PCB_E_INPUT, "all five outputs are required");
+    geno_fetch_dev(ctx, geno, o_ptr.p, o_mut.p, o_q.p, o_mo.p, o_ml.p);
+    o_ptr.commit((size_t)R + 1); o_mut.commit(nnz); o_q.commit(nnz); o_ml.commit(M); o_mo.commit(M);
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int pcb_uptag_join(pcb_ctx *ctx, pcb_text *uptag, const pcb_text *fastq, int mem, const int64_t *id_off, const int32_t *id_len,
+                   int32_t R, int64_t *n_records, int32_t *n_tags, int64_t counters[4]) {
+  return guarded(ctx, [&] {
+    if (!uptag || !fastq || R < 0 || !counters) throw Error(PCB_E_INPUT, "bad arguments");
+    InArr<int64_t> d_off(ctx, mem, id_off, R);
+    InArr<int32_t> d_len(ctx, mem, id_len, R);
+    int64_t nr = 0; int32_t nt = 0;
+    uptag_join_dev(ctx, uptag, fastq, d_off.p, d_len.p, R, &nr, &nt, counters);
+    if (n_records) *n_records = nr;
+    if (n_tags) *n_tags = nt;
+  });
+}
+
+int pcb_uptag_fetch(pcb_ctx *ctx, pcb_text *uptag, int mem, int32_t *up_id, int64_t *tag_off, int32_t *tag_len) {
+  return guarded(ctx, [&] {
+    if (!uptag) throw Error(PCB_E_INPUT, "no text");
+    int64_t nl, nnz; int32_t a, M, R;
+    text_sizes(uptag, &nl, &a, &nnz, &M, &R);
+    if (R < 0 || M < 0) throw Error(PCB_E_STATE, "pcb_uptag_fetch before pcb_uptag_join");
+    OutArr<int32_t> o_up(ctx, mem, up_id, R), o_tl(ctx, mem, tag_len, M);
+    OutArr<int64_t> o_to(ctx, mem, tag_off, M);
+    if ((R > 0 && !o_up.p) || (M > 0 && (!o_tl.p || !o_to.p))) throw Error(PCB_E_INPUT, "all three outputs are required");
+    uptag_fetch_dev(ctx, uptag, o_up.p, o_to.p, o_tl.p);
+    o_up.commit(R); o_tl.commit(M); o_to.commit(M);
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
 }  // extern "C"

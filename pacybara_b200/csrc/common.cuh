@@ -33,6 +33,8 @@ struct pcb_edges {
   bool valid = false;
 };
 
+struct pcb_text;     // a text file on the device (ingest.cu)
+
 struct pcb_ctx {
   int device = 0;
   int sm_count = 148;
@@ -180,5 +182,21 @@ struct MergeOut {            // device pointers, caller-owned
 void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out);
 void tag_rows_dev(pcb_ctx *ctx, int32_t n_rows, const int32_t *row_bc, const int32_t *row_up, const int32_t *row_size,
                   int32_t n_bc_ids, int32_t n_up_ids, double min_ratio, uint8_t *collision, uint8_t *up_collision, uint8_t *usable);
+
+
+// ---- f2: text tokenizers (ingest.cu); all array arguments are device pointers
+pcb_text *text_open_dev(pcb_ctx *ctx, const uint8_t *bytes, DevBuf<uint8_t> &&own, int64_t n, int64_t *n_exotic);
+void fastq_records_dev(pcb_ctx *ctx, pcb_text *x, int32_t *n_records, int32_t *max_len, int32_t *max_id_len, int64_t *n_bad);
+void fastq_fetch_dev(pcb_ctx *ctx, pcb_text *x, int32_t stride, uint8_t *seq, uint8_t *qual, int32_t *length, int64_t *id_off,
+                     int32_t *id_len);
+void rank_strings_dev(pcb_ctx *ctx, const pcb_text *x, const int64_t *off, const int32_t *len, int32_t n, int32_t max_len, int32_t *rank);
+void geno_join_dev(pcb_ctx *ctx, pcb_text *g, const pcb_text *fq, const int64_t *id_off, const int32_t *id_len, int32_t R,
+                   int64_t *nnz, int32_t *n_mut, int64_t counters_out[4]);
+void geno_fetch_dev(pcb_ctx *ctx, pcb_text *g, int32_t *geno_ptr, int32_t *geno_mut, int32_t *geno_q, int64_t *mut_off, int32_t *mut_len);
+void uptag_join_dev(pcb_ctx *ctx, pcb_text *u, const pcb_text *fq, const int64_t *id_off, const int32_t *id_len, int32_t R,
+                    int64_t *n_records, int32_t *n_tags, int64_t counters_out[4]);
+void uptag_fetch_dev(pcb_ctx *ctx, pcb_text *u, int32_t *up_id, int64_t *tag_off, int32_t *tag_len);
+void text_sizes(const pcb_text *x, int64_t *n_lines, int32_t *n_rec, int64_t *nnz, int32_t *n_distinct, int32_t *n_reads);
+void text_free(pcb_text *x);
 
 }  // namespace pcb

@@ -31,13 +31,8 @@ def main(argv=None) -> int:
     bc_file, geno_file = o["ed"], o["geno"]
     from .api import Context
     ctx = Context(0)
-    with hostdata.open_text(bc_file) as fq, hostdata.open_text(geno_file) as ge:
-        up = hostdata.open_text(o["uptag"]) if o["uptag"] else None
-        try:
-            ra, names = pipeline.arrays_from_text(fq, ge, up, ctx)
-        finally:
-            if up is not None:
-                up.close()
+    from . import ingest
+    ra, names = ingest.arrays_from_files(ctx, bc_file, geno_file, o["uptag"] or None, log=cluster_cli.log)
     bad = [r for r in names["ids"] if "-" in r]
     if bad:
         cluster_cli.log(f"ERROR: read id {bad[0]!r} contains '-'", file=sys.stderr)

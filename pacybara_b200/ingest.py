@@ -1,0 +1,140 @@
+"""f2: from the gzip files of the clustering section to device-resident ReadArrays without a Python line loop.
+
+    bcExtract_*.fastq.gz, genoExtract.csv.gz [, uptag FASTQ]  --gunzip-->  bytes  --H2D-->  pcb_text tokenizers
+
+The tokenizers (csrc/ingest.cu) restate the reference's loaders (pacybara_precluster.py:47-63,
+pacybara_cluster.py:302-331) as data-parallel passes and COUNT everything they do not model exactly; when any
+such counter is non-zero this module hands the same files to the line parsers of hostdata.py (which mirror the
+reference line by line and raise its errors).  What stays on the host: gunzip (zlib, one thread per file), the
+names of the M distinct mutations and their (digit key, string) order, and the id strings the writer prints.
+"""
+from __future__ import annotations
+
+import gzip
+import threading
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+
+from . import hostdata, pipeline
+from .api import Context, Text
+
+
+class NeedsLineParser(Exception):
+    """The device tokenizers met something only the line parser models (message says what)."""
+
+
+def read_bytes(path: str) -> bytes:
+    if path == "-":
+        import sys
+        return sys.stdin.buffer.read()
+    with open(path, "rb") as fh:
+        head = fh.read(2)
+    if head == b"\x1f\x8b":
+        with gzip.open(path, "rb") as fh:
+            return fh.read()
+    with open(path, "rb") as fh:
+        return fh.read()
+
+
+def read_all(paths: List[Optional[str]]) -> List[Optional[bytes]]:
+    """Decompress the files concurrently (zlib releases the GIL)."""
+    out: List[Optional[bytes]] = [None] * len(paths)
+    errs: List[BaseException] = []
+
+    def work(i):
+        try:
+            out[i] = read_bytes(paths[i])
+        except BaseException as e:       # noqa: BLE001 - re-raised below
+            errs.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i, p in enumerate(paths) if p is not None]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errs:
+        raise errs[0]
+    return out
+
+
+def _slices(raw: bytes, off: np.ndarray, length: np.ndarray) -> List[str]:
+    txt = raw.decode("ascii")
+    return [txt[o:o + n] for o, n in zip(off.tolist(), length.tolist())]
+
+
+def arrays_from_bytes(ctx: Context, fastq: bytes, geno: bytes, uptag: Optional[bytes] = None
+                      ) -> Tuple[pipeline.ReadArrays, Dict]:
+    """Device-resident ReadArrays (torch CUDA tensors) + the string tables of the writer.
+    Raises NeedsLineParser when the tokenizers decline."""
+    import torch
+    dev = f"cuda:{ctx.device}"
+
+    def decline(what: str, n):
+        raise NeedsLineParser(f"{what}: {n}")
+
+    with Text(ctx, fastq) as fq:
+        if fq.n_exotic:
+            decline("barcode FASTQ has bytes outside plain ASCII text", fq.n_exotic)
+        rec = fq.fastq_records()
+        if rec["n_bad"]:
+            decline("barcode FASTQ records the tokenizer does not model", rec["n_bad"])
+        if rec["max_len"] > hostdata.MAX_BARCODE:
+            raise hostdata.FormatError(f"barcode of length {rec['max_len']} exceeds {hostdata.MAX_BARCODE}")
+        stride = max(4, (rec["max_len"] + 3) // 4 * 4)
+        f = fq.fastq_fetch(stride)
+        R = rec["n_records"]
+        lexrank = fq.rank_strings(f["id_off"], f["id_len"], rec["max_id_len"])
+        with Text(ctx, geno) as ge:
+            if ge.n_exotic:
+                decline("genoExtract has bytes outside plain ASCII text", ge.n_exotic)
+            j = ge.geno_join(fq, f["id_off"], f["id_len"])
+            if j["collisions"]:
+                decline("duplicate read ids (or a hash collision)", j["collisions"])
+            if j["malformed"]:
+                decline("genoExtract lines the tokenizer does not model", j["malformed"])
+            if j["repeated"]:
+                decline("reads naming a mutation twice", j["repeated"])
+            if j["missing"]:
+                raise KeyError(f"{j['missing']} bucketed read(s) have no genotype record")
+            g = ge.geno_fetch()
+            mut_names = _slices(geno, g["mut_off"].cpu().numpy(), g["mut_len"].cpu().numpy())
+        up_id, up_names = None, None
+        if uptag is not None:
+            up = fq if uptag is fastq else Text(ctx, uptag)                # the same file: one copy, one index
+            try:
+                if up.n_exotic:
+                    decline("uptag FASTQ has bytes outside plain ASCII text", up.n_exotic)
+                uj = up.uptag_join(fq, f["id_off"], f["id_len"])
+                if uj["collisions"] or uj["too_long"]:
+                    decline("uptag records the tokenizer does not model", uj["collisions"] + uj["too_long"])
+                if uj["n_records"] > 0:                      # `if len(tags) > 0`, pacybara_cluster.py:376
+                    u = up.uptag_fetch()
+                    up_id = u["up_id"]
+                    up_names = _slices(uptag, u["tag_off"].cpu().numpy(), u["tag_len"].cpu().numpy())
+            finally:
+                if up is not fq:
+                    up.close()
+    ids = _slices(fastq, f["id_off"].cpu().numpy(), f["id_len"].cpu().numpy())
+    mut_rank = torch.from_numpy(pipeline.mut_rank_of(mut_names)).to(dev)
+    ra = pipeline.ReadArrays(seq=f["seq"], qual=f["qual"], length=f["length"], lexrank=lexrank, geno_ptr=g["geno_ptr"],
+                             geno_mut=g["geno_mut"], geno_q=g["geno_q"], mut_rank=mut_rank, up_id=up_id)
+    assert ra.n_reads == R
+    return ra, dict(ids=ids, mut_names=mut_names, up_names=up_names)
+
+
+def arrays_from_files(ctx: Context, bc_file: str, geno_file: str, uptag_file: Optional[str] = None, log=None
+                      ) -> Tuple[pipeline.ReadArrays, Dict]:
+    """The tokenizer path with the line parsers behind it."""
+    same = uptag_file is not None and uptag_file == bc_file
+    raw = read_all([bc_file, geno_file, None if same else uptag_file])
+    if same:
+        raw[2] = raw[0]
+    try:
+        return arrays_from_bytes(ctx, raw[0], raw[1], raw[2])
+    except NeedsLineParser as e:
+        if log:
+            log(f" - tokenizer declined ({e}); using the line parser")
+    import io
+    streams = [io.TextIOWrapper(io.BytesIO(b)) if b is not None else None for b in raw]     # as hostdata.open_text reads them
+    return pipeline.arrays_from_text(streams[0], streams[1], streams[2], ctx)

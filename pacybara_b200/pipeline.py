@@ -74,7 +74,11 @@ def cluster_reads(ctx: Context, ra: ReadArrays, max_diff: int = 2, min_qual: int
 
 
 def table_from_outputs(out: Dict, ra: ReadArrays, names: Dict):
-    """Rows (virtualBarcode, upBarcode, reads, size, geno) of a fused run on host arrays."""
+    """Rows (virtualBarcode, upBarcode, reads, size, geno) of a fused run (device results are brought to the host)."""
+    host = lambda a: a.cpu().numpy() if hasattr(a, "data_ptr") else a
+    out = {k: host(v) for k, v in out.items()}
+    ra = ReadArrays(**{k: host(getattr(ra, k)) for k in ("seq", "qual", "length", "lexrank", "geno_ptr", "geno_mut", "geno_q",
+                                                        "mut_rank", "up_id")})
     rows = hostdata.rows_from_merge_outputs(out)
     bor = np.asarray(out["bucket_of_read"])
     U = int(out["n_buckets"])

@@ -1,0 +1,172 @@
+"""f2: the device tokenizers (csrc/ingest.cu) against the line parsers of hostdata.py, which mirror the reference's
+loaders (pacybara_precluster.py:47-63, pacybara_cluster.py:302-331) and are themselves pinned to the reference by
+tests/test_cli.py.  Bit-exact: same reads, same bytes, same id order, same genotypes, same uptags."""
+import gzip
+import io
+import os
+
+import numpy as np
+import pytest
+
+from pacybara_b200 import hostdata, pipeline, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from pacybara_b200.api import Context
+    c = Context(0)
+    yield c
+    c.close()
+
+
+def host_view(ra, names):
+    """ReadArrays + names -> plain Python values that do not depend on id numbering or strides."""
+    h = lambda a: a.cpu().numpy() if hasattr(a, "data_ptr") else np.asarray(a)
+    seq, qual, length = h(ra.seq), h(ra.qual), h(ra.length)
+    gp, gm, gq = h(ra.geno_ptr), h(ra.geno_mut), h(ra.geno_q)
+    R = length.shape[0]
+    reads = [(seq[i, :length[i]].tobytes(), qual[i, :length[i]].tobytes()) for i in range(R)]
+    assert not seq[np.arange(seq.shape[1])[None, :] >= length[:, None]].any()        # zero padded
+    geno = [[(names["mut_names"][m], int(q)) for m, q in zip(gm[gp[i]:gp[i + 1]], gq[gp[i]:gp[i + 1]])] for i in range(R)]
+    rank = h(ra.mut_rank)
+    used = sorted(set(gm.tolist()))
+    mut_order = [names["mut_names"][m] for m in sorted(used, key=lambda m: rank[m])]
+    up = None
+    if ra.up_id is not None:
+        up = [names["up_names"][u] if u >= 0 else None for u in h(ra.up_id).tolist()]
+    return dict(ids=list(names["ids"]), reads=reads, lexrank=h(ra.lexrank).tolist(), geno=geno, mut_order=mut_order, up=up)
+
+
+def both(ctx, fastq: str, geno: str, uptag=None):
+    from pacybara_b200 import ingest
+    fb, gb = fastq.encode(), geno.encode()
+    ub = fb if uptag is fastq else (uptag.encode() if uptag is not None else None)
+    dev = host_view(*ingest.arrays_from_bytes(ctx, fb, gb, ub))
+    wrap = lambda b: io.TextIOWrapper(io.BytesIO(b)) if b is not None else None
+    ref = host_view(*pipeline.arrays_from_text(wrap(fb), wrap(gb), wrap(ub), ctx))
+    return dev, ref
+
+
+def assert_same(dev, ref):
+    for k in ref:
+        assert dev[k] == ref[k], k
+
+
+FQ = ("@r10 pos=17 len=8\nACGTACGT\n+\nIIIIIIII\n"
+      "@r9 pos=17\nACGTACGA\n+\nIIII#III\n"
+      "@r100\nTTTT\n+\n@III\n"                       # quality starting with '@': the reference drops the read
+      "@r11 x\nACGTACGT  \r\n+\r\nIIIIII!I\t\n"       # CRLF, trailing blanks
+      "@q/7/ccs\nGGGGGGGGGGGG\n+\nIIIIIIIIIIII")      # no newline at the end
+GE = ('"r10","A5C:40;T7G:33"\n'
+      '"zzz","A1C:1"\n'                               # not a read: ignored
+      'r9,=\n'                                        # no quotes
+      '"r11","A5C:12"\n'
+      '"r11","G9T:50;A5C:2"\r\n'                      # the last record of a read wins
+      '"q/7/ccs","100_101insAAC:+7;A5C:0",extra\n'
+      '"r100","T1A:5"\n')
+
+
+def test_small_with_quirks(ctx):
+    dev, ref = both(ctx, FQ, GE)
+    assert_same(dev, ref)
+    assert dev["ids"] == ["r10", "r9", "r11", "q/7/ccs"]
+    assert dev["geno"][2] == [("G9T", 50), ("A5C", 2)]
+    assert dev["lexrank"] == [1, 3, 2, 0]               # string order: q/7/ccs < r10 < r11 < r9
+
+
+def test_uptags(ctx):
+    up = ("@r10 a\nAAAA\n+\nIIII\n"
+          "@r9\nCCCC \n+\nIIII\n"
+          "@r10\nGGGG\n+\nIIII\n"                     # later record wins
+          "@nobody\nTTTT\n+\nIIII\n"
+          "@q/7/ccs\n@r11\nCCCC\n+\nIIII\n")           # a header right after a header: q/7/ccs gets no tag
+    dev, ref = both(ctx, FQ, GE, up)
+    assert_same(dev, ref)
+    assert dev["up"] == ["GGGG", "CCCC", "CCCC", None]
+    dev, ref = both(ctx, FQ, GE, FQ)                   # the barcode file as its own uptag file (non-combo libraries)
+    assert_same(dev, ref)
+    dev, ref = both(ctx, FQ, GE, "")                   # no records: uptags stay off
+    assert_same(dev, ref)
+    assert dev["up"] is None
+
+
+@pytest.mark.parametrize("cfg,scale,style", [("cfg1", 1.0, "plain"), ("cfg3", 0.01, "padded"), ("cfg2", 0.05, "plain")])
+def test_synthetic_files(ctx, tmp_path, cfg, scale, style):
+    from pacybara_b200 import ingest
+    lib = synth.make_config(cfg, seed=5, scale=scale, id_style=style)
+    paths = lib.write_files(str(tmp_path))
+    ra, names = ingest.arrays_from_files(ctx, paths["bc"], paths["geno"], paths["uptag"])
+    assert hasattr(ra.seq, "data_ptr")                 # the tokenizers ran (no fallback)
+    with hostdata.open_text(paths["bc"]) as fq, hostdata.open_text(paths["geno"]) as ge, hostdata.open_text(paths["uptag"]) as up:
+        ref = pipeline.arrays_from_text(fq, ge, up, ctx)
+    assert_same(host_view(ra, names), host_view(*ref))
+    # and the clusters of the two loaders are the same table
+    a = pipeline.table_from_outputs(pipeline.cluster_reads(ctx, ra), ra, names)
+    b = pipeline.table_from_outputs(pipeline.cluster_reads(ctx, ref[0]), *ref)
+    assert a == b and len(a) > 0
+
+
+@pytest.mark.parametrize("what,fastq,geno", [
+    ("non-ascii", FQ.replace("pos=17 len=8", "pos=17 lén"), GE),
+    ("lone CR", FQ.replace("@r9 pos=17\n", "@r9 pos=17\r"), GE),
+    ("text before the first header", "junk\n" + FQ, GE),
+    ("quality shorter than sequence", FQ.replace("IIII#III", "IIII#II"), GE),
+    ("header without id", FQ.replace("@r9 pos=17", "@ r9"), GE),
+    ("duplicate read id", FQ.replace("@r9 pos=17", "@r10"), GE),
+    ("genotype without quality", FQ, GE.replace("A5C:12", "A5C")),
+    ("quality not a number", FQ, GE.replace("A5C:12", "A5C:1e3")),
+    ("line without comma", FQ, GE + "oops\n"),
+    ("mutation twice in a read", FQ, GE.replace("G9T:50;A5C:2", "A5C:50;A5C:2")),
+])
+def test_declines_what_it_does_not_model(ctx, what, fastq, geno):
+    from pacybara_b200 import ingest
+    with pytest.raises(ingest.NeedsLineParser):
+        ingest.arrays_from_bytes(ctx, fastq.encode(), geno.encode())
+
+
+def test_missing_genotype_is_the_references_keyerror(ctx):
+    from pacybara_b200 import ingest
+    with pytest.raises(KeyError):
+        ingest.arrays_from_bytes(ctx, FQ.encode(), GE.replace('"r10",', '"r1O",').encode())
+    wrap = lambda s: io.StringIO(s)
+    with pytest.raises(KeyError):
+        pipeline.arrays_from_text(wrap(FQ), wrap(GE.replace('"r10",', '"r1O",')), None, ctx)
+
+
+def test_fallback_gives_the_line_parsers_answer(ctx, tmp_path):
+    from pacybara_b200 import ingest
+    fq, ge = tmp_path / "bc.fastq.gz", tmp_path / "geno.csv"
+    with gzip.open(fq, "wt") as fh:
+        fh.write(FQ)
+    ge.write_text(GE.replace("G9T:50;A5C:2", "A5C:50;A5C:2"))           # dict semantics: A5C -> 2
+    said = []
+    ra, names = ingest.arrays_from_files(ctx, str(fq), str(ge), None, log=said.append)
+    assert said and "line parser" in said[0]
+    assert host_view(ra, names)["geno"][2] == [("A5C", 2)]
+
+
+def test_empty_and_tiny(ctx):
+    from pacybara_b200 import ingest
+    ra, names = ingest.arrays_from_bytes(ctx, b"", b"")
+    assert ra.n_reads == 0 and names["ids"] == []
+    dev, ref = both(ctx, "@a\nA\n+\nI\n", "a,=\n")
+    assert_same(dev, ref)
+    assert dev["geno"] == [[]]
+
+
+def test_rank_strings_long_ids(ctx):
+    from pacybara_b200.api import Text
+    rng = np.random.default_rng(3)
+    ids = []
+    for i in range(5000):
+        n = int(rng.integers(1, 40))
+        ids.append("m64012_190920_173625/" + "".join(rng.choice(list("0123456789/abc_"), n)))
+    ids = sorted(set(ids), key=lambda s: rng.random())
+    raw = "\n".join(ids).encode()
+    off = np.cumsum([0] + [len(s) + 1 for s in ids[:-1]]).astype(np.int64)
+    ln = np.array([len(s) for s in ids], dtype=np.int32)
+    with Text(ctx, raw) as t:
+        rank = t.rank_strings(off, ln, int(ln.max()))
+    assert np.array_equal(rank, hostdata.lexrank_of(ids))
