@@ -442,14 +442,33 @@ def rows_to_table(rows: ClusterRows, ids: Sequence[str], bc_names: Sequence[str]
     return out
 
 
+def gzip_members(data: bytes, chunk: int = 8 << 20, level: int = 6) -> List[bytes]:
+    """`data` as a sequence of gzip members compressed concurrently (zlib releases the GIL); their
+    concatenation is one valid gzip file (RFC 1952 2.2), which gzip.open, zcat and R's gzfile read as a whole."""
+    import zlib
+    from concurrent.futures import ThreadPoolExecutor
+
+    def one(i):
+        c = zlib.compressobj(level, zlib.DEFLATED, 31)
+        return c.compress(data[i:i + chunk]) + c.flush()
+
+    starts = list(range(0, max(len(data), 1), chunk))
+    if len(starts) == 1:
+        return [one(0)]
+    import os
+    with ThreadPoolExecutor(max_workers=min(len(starts), os.cpu_count() or 1)) as ex:
+        return list(ex.map(one, starts))
+
+
 def write_clusters_csv(path: str, table: Sequence[Tuple[str, str, str, int, str]]) -> None:
     """pacybara_cluster.py:549-567: gzip, unquoted, fixed header."""
-    with gzip.open(path, "wb") as fh:
-        fh.write(b"virtualBarcode,upBarcode,reads,size,geno\n")
-        buf = io.StringIO()
-        for vbc, ubc, reads, size, geno in table:
-            buf.write(f"{vbc},{ubc},{reads},{size},{geno}\n")
-        fh.write(buf.getvalue().encode("utf-8"))
+    buf = io.StringIO()
+    buf.write("virtualBarcode,upBarcode,reads,size,geno\n")
+    for vbc, ubc, reads, size, geno in table:
+        buf.write(f"{vbc},{ubc},{reads},{size},{geno}\n")
+    with open(path, "wb") as fh:
+        for member in gzip_members(buf.getvalue().encode("utf-8")):
+            fh.write(member)
 
 
 # --------------------------------------------------------------------------- loading a cluster-stage job

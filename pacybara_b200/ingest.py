@@ -63,12 +63,20 @@ def _slices(raw: bytes, off: np.ndarray, length: np.ndarray) -> List[str]:
     return [txt[o:o + n] for o, n in zip(off.tolist(), length.tolist())]
 
 
-def arrays_from_bytes(ctx: Context, fastq: bytes, geno: bytes, uptag: Optional[bytes] = None
+def arrays_from_bytes(ctx: Context, fastq: bytes, geno: bytes, uptag: Optional[bytes] = None, laps: Optional[Dict] = None
                       ) -> Tuple[pipeline.ReadArrays, Dict]:
     """Device-resident ReadArrays (torch CUDA tensors) + the string tables of the writer.
-    Raises NeedsLineParser when the tokenizers decline."""
+    Raises NeedsLineParser when the tokenizers decline.  laps: filled with seconds per step."""
+    import time
     import torch
     dev = f"cuda:{ctx.device}"
+    t_last = [time.perf_counter()]
+
+    def lap(name):
+        if laps is not None:
+            now = time.perf_counter()
+            laps[name] = laps.get(name, 0.0) + round(now - t_last[0], 4)
+            t_last[0] = now
 
     def decline(what: str, n):
         raise NeedsLineParser(f"{what}: {n}")
@@ -76,6 +84,7 @@ def arrays_from_bytes(ctx: Context, fastq: bytes, geno: bytes, uptag: Optional[b
     with Text(ctx, fastq) as fq:
         if fq.n_exotic:
             decline("barcode FASTQ has bytes outside plain ASCII text", fq.n_exotic)
+        lap("open_fastq")
         rec = fq.fastq_records()
         if rec["n_bad"]:
             decline("barcode FASTQ records the tokenizer does not model", rec["n_bad"])
@@ -84,8 +93,11 @@ def arrays_from_bytes(ctx: Context, fastq: bytes, geno: bytes, uptag: Optional[b
         stride = max(4, (rec["max_len"] + 3) // 4 * 4)
         f = fq.fastq_fetch(stride)
         R = rec["n_records"]
+        lap("fastq_records")
         lexrank = fq.rank_strings(f["id_off"], f["id_len"], rec["max_id_len"])
+        lap("rank_ids")
         with Text(ctx, geno) as ge:
+            lap("open_geno")
             if ge.n_exotic:
                 decline("genoExtract has bytes outside plain ASCII text", ge.n_exotic)
             j = ge.geno_join(fq, f["id_off"], f["id_len"])
@@ -98,7 +110,9 @@ def arrays_from_bytes(ctx: Context, fastq: bytes, geno: bytes, uptag: Optional[b
             if j["missing"]:
                 raise KeyError(f"{j['missing']} bucketed read(s) have no genotype record")
             g = ge.geno_fetch()
+            lap("geno_join")
             mut_names = _slices(geno, g["mut_off"].cpu().numpy(), g["mut_len"].cpu().numpy())
+        lap("mut_names")
         up_id, up_names = None, None
         if uptag is not None:
             up = fq if uptag is fastq else Text(ctx, uptag)                # the same file: one copy, one index
@@ -115,11 +129,14 @@ def arrays_from_bytes(ctx: Context, fastq: bytes, geno: bytes, uptag: Optional[b
             finally:
                 if up is not fq:
                     up.close()
+    lap("uptags")
     ids = _slices(fastq, f["id_off"].cpu().numpy(), f["id_len"].cpu().numpy())
+    lap("id_strings")
     mut_rank = torch.from_numpy(pipeline.mut_rank_of(mut_names)).to(dev)
     ra = pipeline.ReadArrays(seq=f["seq"], qual=f["qual"], length=f["length"], lexrank=lexrank, geno_ptr=g["geno_ptr"],
                              geno_mut=g["geno_mut"], geno_q=g["geno_q"], mut_rank=mut_rank, up_id=up_id)
     assert ra.n_reads == R
+    lap("mut_rank")
     return ra, dict(ids=ids, mut_names=mut_names, up_names=up_names)
 
 

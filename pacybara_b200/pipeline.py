@@ -73,8 +73,10 @@ def cluster_reads(ctx: Context, ra: ReadArrays, max_diff: int = 2, min_qual: int
                              min_matches=min_matches, full_table=full_table)
 
 
-def table_from_outputs(out: Dict, ra: ReadArrays, names: Dict):
-    """Rows (virtualBarcode, upBarcode, reads, size, geno) of a fused run (device results are brought to the host)."""
+def table_from_outputs(out: Dict, ra: ReadArrays, names: Dict, consensus=None):
+    """Rows (virtualBarcode, upBarcode, reads, size, geno) of a fused run (device results are brought to the host).
+    consensus(list of barcode strings) -> string resolves the rows whose barcode vote is tied among >= 3 reads; the
+    default is the reference's own `muscle` alignment (pacybara_cluster.py:484-511)."""
     host = lambda a: a.cpu().numpy() if hasattr(a, "data_ptr") else a
     out = {k: host(v) for k, v in out.items()}
     ra = ReadArrays(**{k: host(getattr(ra, k)) for k in ("seq", "qual", "length", "lexrank", "geno_ptr", "geno_mut", "geno_q",
@@ -85,7 +87,19 @@ def table_from_outputs(out: Dict, ra: ReadArrays, names: Dict):
     first = np.full(U, np.iinfo(np.int64).max, dtype=np.int64)
     np.minimum.at(first, bor, np.arange(bor.shape[0]))
     bc_names = hostdata.matrix_to_strings(np.asarray(ra.seq)[first], np.asarray(ra.length)[first])
-    return hostdata.rows_to_table(rows, names["ids"], bc_names, names["up_names"], names["mut_names"])
+    if consensus is None:
+        from .cluster import alignment_consensus as consensus
+    up_names = names["up_names"] if names["up_names"] is not None else bc_names
+    up_of = ra.up_id if ra.up_id is not None else bor
+
+    def on_alignment(i, members, b, u):
+        if b == hostdata.NEEDS_ALIGNMENT:
+            b = consensus([bc_names[bor[r]] for r in members])
+        if u == hostdata.NEEDS_ALIGNMENT:
+            u = consensus([up_names[up_of[r]] for r in members])
+        return b, u
+
+    return hostdata.rows_to_table(rows, names["ids"], bc_names, names["up_names"], names["mut_names"], on_alignment=on_alignment)
 
 
 def arrays_from_text(fastq_stream, geno_stream, uptag_stream=None, ctx: Optional[Context] = None
