@@ -199,8 +199,10 @@ def main():
             return multigpu.cluster_reads_sharded(ctx, arrs, params, rank, world, on_device=on_device,
                                                   full_table=args.full_table)
         a = arrs if on_device else {k: v.numpy() for k, v in arrs.items()}
+        # host buffers: ask for one entry per ROW of the cluster table, so only the rows cross the bus
         return ctx.cluster_reads(a["seq"], a["qual"], a["length"], a["lexrank"], a.get("up_id"), a["geno_ptr"],
-                                 a["geno_mut"], a["geno_q"], a["mut_rank"], full_table=args.full_table, **params)
+                                 a["geno_mut"], a["geno_q"], a["mut_rank"], full_table=args.full_table,
+                                 compact_rows=not on_device, **params)
 
     STAGES = ("t_bucket_ns", "t_index_ns", "probe_ns", "t_hits_ns", "t_prep_ns", "t_replay_ns", "t_scatter_ns")
     stage_acc = {}

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PCB_ABI_VERSION 1
+#define PCB_ABI_VERSION 2
 
 enum {
   PCB_OK = 0,
@@ -71,7 +71,9 @@ enum {
   PCB_STAT_T_PREP_NS = 13,     /* merge preprocessing: components, renumbering, adjacency, visiting lists, scratch */
   PCB_STAT_T_REPLAY_NS = 14,   /* component_kernel */
   PCB_STAT_T_SCATTER_NS = 15,  /* outputs back to the caller's numbering */
-  PCB_STAT_COUNT = 16
+  PCB_STAT_ROWS = 16,          /* rows of the last pcb_cluster_reads with PCB_CLUSTER_COMPACT_ROWS */
+  PCB_STAT_CALLS = 17,         /* consensus genotype entries of those rows */
+  PCB_STAT_COUNT = 18
 };
 
 typedef struct pcb_ctx pcb_ctx;
@@ -179,8 +181,14 @@ int pcb_merge(pcb_ctx *ctx, int mem, int32_t R, int32_t U,
  *   candidates.
  * flags = PCB_CLUSTER_FULL_TABLE: the pair search runs at k = 2*max_diff, i.e. the table
  *   pacybara.sh:466-468 asks of calcEdits.R is materialised (fetch it with pcb_edit_pairs_fetch).
+ * flags |= PCB_CLUSTER_COMPACT_ROWS: the row_* outputs hold one entry per ROW instead of one per read: the
+ *   n_rows = pcb_stat(PCB_STAT_ROWS) rows in ascending order of their representative read, which row_rep[i]
+ *   names (required with this flag, NULL otherwise); row_call_off[i] points into a call_mut that holds only the
+ *   pcb_stat(PCB_STAT_CALLS) consensus entries, row after row.  read_root / read_pos / bucket_of_read stay per read.
+ *   With host memory only those entries cross the bus (a cluster table has far fewer rows than reads).
  */
 #define PCB_CLUSTER_FULL_TABLE 1
+#define PCB_CLUSTER_COMPACT_ROWS 2
 int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *qual, const int32_t *len,
                       int32_t R, int32_t stride, const int32_t *lexrank, const int32_t *up_id,
                       const int32_t *geno_ptr, const int32_t *geno_mut, const int32_t *geno_q,
@@ -189,7 +197,7 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
                       int32_t *bucket_of_read, int32_t *n_buckets, int64_t *n_edges,
                       int32_t *read_root, int32_t *read_pos, int32_t *row_size, int64_t *row_key,
                       int32_t *row_bc, int32_t *row_up, int64_t *row_call_off, int32_t *row_call_n,
-                      int32_t *call_mut);
+                      int32_t *call_mut, int32_t *row_rep);
 
 /*
  * f1 (first row after the hot path) -- barcode-collision tags and the dominance test of the

@@ -13,9 +13,10 @@ MEM_HOST, MEM_DEVICE = 0, 1
 FILL = -(1 << 31)
 NEEDS_ALIGNMENT = -2
 CLUSTER_FULL_TABLE = 1
+CLUSTER_COMPACT_ROWS = 2
 STAT = dict(pairs_scored=0, cells=1, edges=2, seed_len=3, kernel_launches=4, components=5, links=6, tests=7,
             buckets=8, probe_ns=9, t_bucket_ns=10, t_index_ns=11, t_hits_ns=12, t_prep_ns=13, t_replay_ns=14,
-            t_scatter_ns=15)
+            t_scatter_ns=15, rows=16, calls=17)
 
 # every symbol include/pacybara_b200.h declares
 SYMBOLS = ["pcb_abi_version", "pcb_last_error", "pcb_ctx_create", "pcb_ctx_destroy", "pcb_stat", "pcb_sync",
@@ -60,7 +61,7 @@ def load():
         lib.pcb_merge.argtypes = ([vp, C.c_int, i32, i32] + [vp] * 9 + [i32, i64] + [vp] * 4 +
                                   [i32, i32, dbl, i32, vp, vp, i32, i32, i32, i32] + [vp] * 9)
         lib.pcb_cluster_reads.argtypes = ([vp, C.c_int, vp, vp, vp, i32, i32] + [vp] * 6 + [i32, i32, i32, dbl, i32, i32] +
-                                          [vp, C.POINTER(i32), C.POINTER(i64)] + [vp] * 9)
+                                          [vp, C.POINTER(i32), C.POINTER(i64)] + [vp] * 10)
         lib.pcb_tag_rows.argtypes = [vp, C.c_int, i32, vp, vp, vp, i32, i32, dbl, vp, vp, vp]
         p32, p64 = C.POINTER(i32), C.POINTER(i64)
         lib.pcb_text_open.argtypes = [vp, C.c_int, vp, i64, C.POINTER(vp), p64, p64]

@@ -226,10 +226,13 @@ class Context:
     # ------------------------------------------------------------------ the whole path
     def cluster_reads(self, seq, qual, length, lexrank, up_id, geno_ptr, geno_mut, geno_q, mut_rank,
                       max_diff: int = 2, min_qual: int = 32, min_jaccard: float = 0.2, min_matches: int = 1,
-                      full_table: bool = False) -> Dict:
+                      full_table: bool = False, compact_rows: bool = False) -> Dict:
         """Bucketing -> distances -> merge on the device (pcb_cluster_reads).  full_table=True
         materialises every pair up to 2*max_diff (the calcEdits table) instead of scoring the
-        transitive-rule distances on demand; the clusters are the same."""
+        transitive-rule distances on demand; the clusters are the same.  compact_rows=True returns the
+        row_* arrays with one entry per row (plus `row_rep`, the representative read of each row, and a
+        call_mut holding only the rows' calls) instead of one per read: with host arrays only the rows
+        cross the bus."""
         arrays = [seq, qual, length, lexrank, up_id, geno_ptr, geno_mut, geno_q, mut_rank]
         if any(_is_dev(a) for a in arrays):
             _torch()
@@ -246,13 +249,20 @@ class Context:
             ptrs.append(ptr)
         outs["call_mut"], p_call = self._out(mem, (max(nnz, 1),), np.int32, "c_call_mut")
         nb, ne = C.c_int32(0), C.c_int64(0)
+        rep, p_rep = self._out(mem, (max(R, 1),), np.int32, "c_row_rep") if compact_rows else (None, None)
+        flags = (_lib.CLUSTER_FULL_TABLE if full_table else 0) | (_lib.CLUSTER_COMPACT_ROWS if compact_rows else 0)
         self._check(self.lib.pcb_cluster_reads(self.h, mem, ins[0], ins[1], ins[2], R, stride, *ins[3:],
                                                int(mut_rank.shape[0]), int(max_diff), int(min_qual),
-                                               float(min_jaccard), int(min_matches),
-                                               _lib.CLUSTER_FULL_TABLE if full_table else 0, p_bor, C.byref(nb), C.byref(ne),
-                                               *ptrs, p_call))
-        out = {k: v[:R] for k, v in outs.items() if k != "call_mut"}
-        out["call_mut"] = outs["call_mut"][:nnz]
+                                               float(min_jaccard), int(min_matches), flags, p_bor, C.byref(nb), C.byref(ne),
+                                               *ptrs, p_call, p_rep))
+        if compact_rows:
+            n_rows, n_calls = self.stat("rows"), self.stat("calls")
+            out = {k: v[:(R if k in ("read_root", "read_pos") else n_rows)] for k, v in outs.items() if k != "call_mut"}
+            out["call_mut"] = outs["call_mut"][:n_calls]
+            out["row_rep"] = rep[:n_rows]
+        else:
+            out = {k: v[:R] for k, v in outs.items() if k != "call_mut"}
+            out["call_mut"] = outs["call_mut"][:nnz]
         out["bucket_of_read"] = bor[:R]
         out["n_buckets"] = int(nb.value)
         out["n_edges"] = int(ne.value)

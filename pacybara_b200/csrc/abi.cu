@@ -91,6 +91,36 @@ __global__ void edge_unpack_kernel(const uint64_t *__restrict__ key, const uint3
   }
 }
 
+// PCB_CLUSTER_COMPACT_ROWS: per-read row arrays -> one entry per row, in ascending order of the representative
+__global__ void row_flag_kernel(const int32_t *__restrict__ row_size, const int32_t *__restrict__ row_call_n, int32_t R,
+                                uint32_t *__restrict__ flag, uint32_t *__restrict__ ncall) {
+  int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > R) return;
+  bool rep = r < R && row_size[r] > 0;
+  flag[r] = rep ? 1u : 0u;
+  ncall[r] = rep && row_call_n[r] > 0 ? (uint32_t)row_call_n[r] : 0u;
+}
+__global__ void row_compact_kernel(int32_t R, const uint32_t *__restrict__ row_of, const uint32_t *__restrict__ call_at,
+                                   const int32_t *__restrict__ t_size, const int64_t *__restrict__ t_key, const int32_t *__restrict__ t_bc,
+                                   const int32_t *__restrict__ t_up, const int64_t *__restrict__ t_calloff, const int32_t *__restrict__ t_calln,
+                                   const int32_t *__restrict__ t_call, int32_t *__restrict__ o_rep, int32_t *__restrict__ o_size,
+                                   int64_t *__restrict__ o_key, int32_t *__restrict__ o_bc, int32_t *__restrict__ o_up,
+                                   int64_t *__restrict__ o_calloff, int32_t *__restrict__ o_calln, int32_t *__restrict__ o_call) {
+  int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R || row_of[r + 1] == row_of[r]) return;
+  uint32_t i = row_of[r];
+  o_rep[i] = r;
+  o_size[i] = t_size[r];
+  o_key[i] = t_key[r];
+  o_bc[i] = t_bc[r];
+  o_up[i] = t_up[r];
+  o_calln[i] = t_calln[r];
+  uint32_t at = call_at[r];
+  o_calloff[i] = (int64_t)at;
+  int64_t from = t_calloff[r];
+  for (int32_t k = 0; k < t_calln[r]; k++) o_call[at + k] = t_call[from + k];
+}
+
 }  // namespace
 
 extern "C" {
@@ -272,10 +302,12 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
                       int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches, int32_t flags,
                       int32_t *bucket_of_read, int32_t *n_buckets, int64_t *n_edges, int32_t *read_root,
                       int32_t *read_pos, int32_t *row_size, int64_t *row_key, int32_t *row_bc, int32_t *row_up,
-                      int64_t *row_call_off, int32_t *row_call_n, int32_t *call_mut) {
+                      int64_t *row_call_off, int32_t *row_call_n, int32_t *call_mut, int32_t *row_rep) {
   return guarded(ctx, [&] {
     if (R < 0 || stride < 1) throw Error(PCB_E_INPUT, "bad shape");
     if (max_diff < 0 || max_diff > 3) throw Error(PCB_E_INPUT, "maxDiff must be between 0 and 3");
+    const bool compact = (flags & PCB_CLUSTER_COMPACT_ROWS) != 0;
+    if (compact && !row_rep) throw Error(PCB_E_INPUT, "PCB_CLUSTER_COMPACT_ROWS needs row_rep");
     int64_t nnz = 0;
     if (R > 0) {
       if (mem == PCB_MEM_DEVICE) nnz = read_scalar(ctx, geno_ptr + R); else nnz = geno_ptr[R];
@@ -323,11 +355,37 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
                E, ctx->edges.ei, ctx->edges.ej, ctx->edges.ed, ped.p, max_diff, min_qual, min_matches, min_jaccard, 0, 1};
     if (!full) { in.planes = uniq.planes.p; in.blen = uniq.len.p; in.compute_k = 2 * max_diff; in.wide = uniq.max_len > 32; }
     in.nnz = nnz;
-    MergeOut out{o_root.p, o_pos.p, o_size.p, o_key.p, o_bc.p, o_up.p, o_calloff.p, o_calln.p, o_call.p};
-    merge_dev(ctx, in, out);
-    stage_collect(ctx);
-    o_bor.commit(R); o_root.commit(R); o_pos.commit(R); o_size.commit(R); o_bc.commit(R); o_up.commit(R);
-    o_calln.commit(R); o_call.commit(nnz); o_key.commit(R); o_calloff.commit(R);
+    if (!compact) {
+      MergeOut out{o_root.p, o_pos.p, o_size.p, o_key.p, o_bc.p, o_up.p, o_calloff.p, o_calln.p, o_call.p};
+      merge_dev(ctx, in, out);
+      stage_collect(ctx);
+      o_bor.commit(R); o_root.commit(R); o_pos.commit(R); o_size.commit(R); o_bc.commit(R); o_up.commit(R);
+      o_calln.commit(R); o_call.commit(nnz); o_key.commit(R); o_calloff.commit(R);
+    } else {
+      // per-read row arrays stay on the device; only the rows travel
+      DevBuf<int32_t> t_size(ctx, R), t_bc(ctx, R), t_up(ctx, R), t_calln(ctx, R), t_call(ctx, (size_t)nnz);
+      DevBuf<int64_t> t_key(ctx, R), t_calloff(ctx, R);
+      MergeOut out{o_root.p, o_pos.p, t_size.p, t_key.p, t_bc.p, t_up.p, t_calloff.p, t_calln.p, t_call.p};
+      merge_dev(ctx, in, out);
+      OutArr<int32_t> o_rep(ctx, mem, row_rep, R);
+      DevBuf<uint32_t> row_of(ctx, (size_t)R + 1), call_at(ctx, (size_t)R + 1);
+      PCB_LAUNCH(ctx, row_flag_kernel, grid_for((size_t)R + 1, 256), 256, 0, t_size.p, t_calln.p, R, row_of.p, call_at.p);
+      exclusive_scan_u32(ctx, row_of.p, row_of.p, (size_t)R + 1);
+      exclusive_scan_u32(ctx, call_at.p, call_at.p, (size_t)R + 1);
+      if (R) PCB_LAUNCH(ctx, row_compact_kernel, grid_for((size_t)R, 256), 256, 0, R, row_of.p, call_at.p, t_size.p, t_key.p, t_bc.p,
+                        t_up.p, t_calloff.p, t_calln.p, t_call.p, o_rep.p, o_size.p, o_key.p, o_bc.p, o_up.p, o_calloff.p, o_calln.p,
+                        o_call.p);
+      uint32_t h_rows = 0, h_calls = 0;
+      PCB_CUDA(cudaMemcpyAsync(&h_rows, row_of.p + R, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      PCB_CUDA(cudaMemcpyAsync(&h_calls, call_at.p + R, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      o_bor.commit(R); o_root.commit(R); o_pos.commit(R);
+      PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+      stage_collect(ctx);
+      ctx->stats[PCB_STAT_ROWS] = h_rows;
+      ctx->stats[PCB_STAT_CALLS] = h_calls;
+      o_rep.commit(h_rows); o_size.commit(h_rows); o_bc.commit(h_rows); o_up.commit(h_rows); o_calln.commit(h_rows);
+      o_key.commit(h_rows); o_calloff.commit(h_rows); o_call.commit(h_calls);
+    }
     PCB_CUDA(cudaStreamSynchronize(ctx->stream));
   });
 }

@@ -523,6 +523,16 @@ def rows_from_merge_outputs(out: Dict[str, np.ndarray]) -> ClusterRows:
     """Per-read / per-representative arrays of pcb_merge -> the table layout of
     pacybara_cluster.py:546-567: clusters in creation order of the surviving cluster id, then
     the unclustered reads (the reference emits those in `set` order; read order here)."""
+    if "row_rep" in out:            # PCB_CLUSTER_COMPACT_ROWS: one entry per row already; same code on the expanded view
+        rep0 = np.asarray(out["row_rep"]).astype(np.int64)
+        R = out["read_root"].shape[0]
+        full = {}
+        for name, dt in MERGE_OUTPUTS[2:]:
+            a = np.full(R, -1 if name != "row_size" else 0, dtype=dt)
+            a[rep0] = out[name]
+            full[name] = a
+        out = dict(out, **full)
+        del out["row_rep"]
     row_size = out["row_size"]
     rep = np.nonzero(row_size > 0)[0]
     key = out["row_key"][rep]

@@ -67,10 +67,10 @@ def arrays_from_library(lib, ctx: Optional[Context] = None, with_names: bool = T
 
 
 def cluster_reads(ctx: Context, ra: ReadArrays, max_diff: int = 2, min_qual: int = 32, min_jaccard: float = 0.2,
-                  min_matches: int = 1, full_table: bool = False) -> Dict:
+                  min_matches: int = 1, full_table: bool = False, compact_rows: bool = False) -> Dict:
     return ctx.cluster_reads(ra.seq, ra.qual, ra.length, ra.lexrank, ra.up_id, ra.geno_ptr, ra.geno_mut, ra.geno_q,
                              ra.mut_rank, max_diff=max_diff, min_qual=min_qual, min_jaccard=min_jaccard,
-                             min_matches=min_matches, full_table=full_table)
+                             min_matches=min_matches, full_table=full_table, compact_rows=compact_rows)
 
 
 def table_from_outputs(out: Dict, ra: ReadArrays, names: Dict, consensus=None):

@@ -213,6 +213,32 @@ def test_fused_cfg1_device_memory(ctx):
     _fused_vs_oracle(ctx, synth.make_config("cfg1", seed=4), device=True)
 
 
+@pytest.mark.parametrize("device", [False, True])
+@pytest.mark.parametrize("cfg,scale", [("cfg1", 1.0), ("cfg3", 0.01), ("cfg2", 0.1)])
+def test_fused_compact_rows(ctx, cfg, scale, device):
+    """PCB_CLUSTER_COMPACT_ROWS: one entry per row instead of one per read -- the same rows, member order and calls."""
+    from pacybara_b200 import pipeline
+    lib = synth.make_config(cfg, seed=6, scale=scale)
+    ra, names = pipeline.arrays_from_library(lib, ctx)
+    if device:
+        import torch
+        ra = pipeline.ReadArrays(**{k: (torch.from_numpy(np.ascontiguousarray(v)).cuda() if v is not None else None)
+                                    for k, v in vars(ra).items()})
+    host = lambda d: {k: (v.cpu().numpy() if hasattr(v, "data_ptr") else v) for k, v in d.items()}
+    per_read = host(pipeline.cluster_reads(ctx, ra))
+    compact = host(pipeline.cluster_reads(ctx, ra, compact_rows=True))
+    n_rows = int((per_read["row_size"] > 0).sum())
+    assert ctx.stat("rows") == n_rows == compact["row_rep"].shape[0] == compact["row_size"].shape[0]
+    assert np.array_equal(compact["row_rep"], np.nonzero(per_read["row_size"] > 0)[0])
+    assert compact["call_mut"].shape[0] == ctx.stat("calls") == int(per_read["row_call_n"][compact["row_rep"]].clip(0).sum())
+    for k in ("read_root", "read_pos", "bucket_of_read"):
+        assert np.array_equal(compact[k], per_read[k]), k
+    a, b = hostdata.rows_from_merge_outputs(per_read), hostdata.rows_from_merge_outputs(compact)
+    for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    assert a.n_clusters == b.n_clusters
+
+
 def test_fused_cfg1_golden_digest(ctx):
     """The committed digest of the reference's own cfg-1 table (tests/golden/cfg1_seed1)."""
     import hashlib
