@@ -196,8 +196,9 @@ def main():
 
     def run(arrs, on_device):
         if world > 1:
+            # results stay sharded by component (north star: only the merge-edge lists are exchanged)
             return multigpu.cluster_reads_sharded(ctx, arrs, params, rank, world, on_device=on_device,
-                                                  full_table=args.full_table)
+                                                  full_table=args.full_table, combine=False)
         a = arrs if on_device else {k: v.numpy() for k, v in arrs.items()}
         # host buffers: ask for one entry per ROW of the cluster table, so only the rows cross the bus
         return ctx.cluster_reads(a["seq"], a["qual"], a["length"], a["lexrank"], a.get("up_id"), a["geno_ptr"],
@@ -248,6 +249,12 @@ def main():
     timed(pinned, False, 1)
     e2e_ms, _, out_h = timed(pinned, False, args.steps)
     d2h_bytes = sum(np.asarray(v).nbytes for k, v in out_h.items() if hasattr(v, "nbytes"))
+    if dist is not None:
+        # whole job: every rank uploads its chunk of the reads (+ the small mutation table) and ships its own rows
+        t = torch.tensor([d2h_bytes], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        d2h_bytes = int(t.item())
+        h2d_bytes += (world - 1) * pinned["mut_rank"].numel() * pinned["mut_rank"].element_size()
 
     if rank != 0:
         if dist is not None:
@@ -319,7 +326,8 @@ def main():
                             max_diff=params["max_diff"], pair_search_k=(2 if args.full_table else 1) * params["max_diff"],
                             distance_table="full (<= 2*maxDiff)" if args.full_table else "<= maxDiff + on-demand in merge",
                             seed_len=stats["seed_len"],
-                            l2="flushed between steps (512 MiB write)", parallelism=f"query-shard x{world}" if world > 1 else "1 GPU"),
+                            l2="flushed between steps (512 MiB write)", parallelism=(f"x{world}: pairs sharded by query bucket, edge all-gather, merge and results sharded by component"
+                                         if world > 1 else "1 GPU")),
                 e2e=dict(value=R / (e2e_ms / args.steps * 1e-3), unit="reads/s", h2d_bytes_per_step=h2d_bytes,
                          d2h_bytes_per_step=d2h_bytes, ms_per_step=e2e_ms / args.steps),
                 gpu_launches=launches, clocks=clocks, roofline=roof, roofline_probe=roof_probe, roofline_alu=alu,

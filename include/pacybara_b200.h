@@ -200,6 +200,25 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
                       int32_t *call_mut, int32_t *row_rep);
 
 /*
+ * The part of a merge result that belongs to this shard, compacted (multi-GPU: every rank keeps and ships only its own
+ * components; N = 1: all reads are owned).  Inputs: the per-read outputs of pcb_merge / pcb_cluster_reads, in `mem_in`.
+ * Outputs, in `mem_out` (buffers of R entries, c_call_mut of nnz):
+ *   own_read / own_root / own_pos [n_own]   the reads whose read_root is not PCB_FILL, ascending, with their row and position
+ *   own_bucket [n_own]                      bucket_of_read of those reads (both NULL to skip): row_bc names buckets, and
+ *                                           the consensus barcode of a row is the barcode of one of its own members
+ *   row_rep, c_* [n_rows]                   one entry per row in ascending order of the representative read; c_call_off
+ *                                           points into c_call_mut [n_calls], which holds the rows' calls back to back
+ * With mem_in = PCB_MEM_DEVICE and mem_out = PCB_MEM_HOST only the compacted entries cross the bus.
+ */
+int pcb_compact_shard(pcb_ctx *ctx, int mem_in, int mem_out, int32_t R, int64_t nnz,
+                      const int32_t *read_root, const int32_t *read_pos, const int32_t *row_size, const int64_t *row_key,
+                      const int32_t *row_bc, const int32_t *row_up, const int64_t *row_call_off, const int32_t *row_call_n,
+                      const int32_t *call_mut, const int32_t *bucket_of_read,
+                      int32_t *n_own, int32_t *own_read, int32_t *own_root, int32_t *own_pos, int32_t *own_bucket,
+                      int32_t *n_rows, int64_t *n_calls, int32_t *row_rep, int32_t *c_size, int64_t *c_key, int32_t *c_bc,
+                      int32_t *c_up, int64_t *c_call_off, int32_t *c_call_n, int32_t *c_call_mut);
+
+/*
  * f1 (first row after the hot path) -- barcode-collision tags and the dominance test of the
  * soft filter, on a cluster table given as per-row ids:
  *   collision[i]     = the virtual barcode of row i occurs in more than one row   (tagDups, src/pacybara_translate.R:58-68)

@@ -268,6 +268,40 @@ class Context:
         out["n_edges"] = int(ne.value)
         return out
 
+    def compact_shard(self, out: Dict, to_host: bool = True) -> Dict:
+        """The reads this shard owns and their rows, compacted (pcb_compact_shard).  `out`: per-read outputs of
+        merge() / cluster_reads() (numpy or torch CUDA).  to_host=True returns numpy arrays (page-locked and reused when
+        the context has pinned_outputs): from device inputs only the compacted entries cross the bus."""
+        names = [n for n, _ in MERGE_OUTPUTS] + ["call_mut"]
+        arrays = [out[n] for n in names]
+        mem_in = self._kind(*arrays)
+        mem_out = _lib.MEM_HOST if to_host else _lib.MEM_DEVICE
+        if not to_host:
+            _torch()
+        R, nnz = int(out["read_root"].shape[0]), int(out["call_mut"].shape[0])
+        keep: list = []
+        dts = dict(MERGE_OUTPUTS)
+        ins = [self._in(out[n], dts.get(n, np.int32), keep) for n in names]
+        bor = out.get("bucket_of_read")
+        if bor is not None and self._kind(bor) != mem_in:
+            raise TypeError("bucket_of_read must live where the other arrays do")
+        ins.append(self._in(bor, np.int32, keep))
+        res, ptrs = {}, {}
+        for n, dt, size in (("own_read", np.int32, R), ("own_root", np.int32, R), ("own_pos", np.int32, R), ("own_bucket", np.int32, R),
+                            ("row_rep", np.int32, R),
+                            ("row_size", np.int32, R), ("row_key", np.int64, R), ("row_bc", np.int32, R), ("row_up", np.int32, R),
+                            ("row_call_off", np.int64, R), ("row_call_n", np.int32, R), ("call_mut", np.int32, nnz)):
+            res[n], ptrs[n] = self._out(mem_out, (max(size, 1),), dt, "s_" + n)
+        n_own, n_rows, n_calls = C.c_int32(0), C.c_int32(0), C.c_int64(0)
+        self._check(self.lib.pcb_compact_shard(self.h, mem_in, mem_out, R, nnz, *ins, C.byref(n_own), ptrs["own_read"], ptrs["own_root"],
+                                               ptrs["own_pos"], ptrs["own_bucket"] if bor is not None else None, C.byref(n_rows), C.byref(n_calls), ptrs["row_rep"], ptrs["row_size"],
+                                               ptrs["row_key"], ptrs["row_bc"], ptrs["row_up"], ptrs["row_call_off"], ptrs["row_call_n"],
+                                               ptrs["call_mut"]))
+        cut = dict(own_read=n_own.value, own_root=n_own.value, own_pos=n_own.value, own_bucket=n_own.value, call_mut=n_calls.value)
+        res = {k: v[:cut.get(k, n_rows.value)] for k, v in res.items() if not (k == "own_bucket" and bor is None)}
+        res["n_reads"] = R
+        return res
+
 
 class Text:
     """The bytes of one text file on the device plus its newline index (pcb_text; f2 tokenizers).

@@ -121,6 +121,36 @@ __global__ void row_compact_kernel(int32_t R, const uint32_t *__restrict__ row_o
   for (int32_t k = 0; k < t_calln[r]; k++) o_call[at + k] = t_call[from + k];
 }
 
+__global__ void own_flag_kernel(const int32_t *__restrict__ read_root, int32_t R, uint32_t *__restrict__ flag) {
+  int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > R) return;
+  flag[r] = (r < R && read_root[r] != PCB_FILL) ? 1u : 0u;
+}
+__global__ void own_compact_kernel(int32_t R, const uint32_t *__restrict__ at, const int32_t *__restrict__ read_root,
+                                   const int32_t *__restrict__ read_pos, const int32_t *__restrict__ bucket_of_read,
+                                   int32_t *__restrict__ o_read, int32_t *__restrict__ o_root, int32_t *__restrict__ o_pos,
+                                   int32_t *__restrict__ o_bucket) {
+  int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R || at[r + 1] == at[r]) return;
+  o_read[at[r]] = r; o_root[at[r]] = read_root[r]; o_pos[at[r]] = read_pos[r];
+  if (o_bucket) o_bucket[at[r]] = bucket_of_read[r];
+}
+
+struct RowArrays {           // device pointers
+  int32_t *size; int64_t *key; int32_t *bc, *up; int64_t *calloff; int32_t *calln, *call;
+};
+// per-read row arrays -> one entry per row (ascending representative); returns after the counts have arrived
+void compact_rows(pcb_ctx *ctx, int32_t R, const RowArrays &t, int32_t *o_rep, const RowArrays &o, uint32_t *n_rows, uint32_t *n_calls) {
+  DevBuf<uint32_t> row_of(ctx, (size_t)R + 1), call_at(ctx, (size_t)R + 1);
+  PCB_LAUNCH(ctx, row_flag_kernel, grid_for((size_t)R + 1, 256), 256, 0, t.size, t.calln, R, row_of.p, call_at.p);
+  exclusive_scan_u32(ctx, row_of.p, row_of.p, (size_t)R + 1);
+  exclusive_scan_u32(ctx, call_at.p, call_at.p, (size_t)R + 1);
+  if (R) PCB_LAUNCH(ctx, row_compact_kernel, grid_for((size_t)R, 256), 256, 0, R, row_of.p, call_at.p, t.size, t.key, t.bc, t.up,
+                    t.calloff, t.calln, t.call, o_rep, o.size, o.key, o.bc, o.up, o.calloff, o.calln, o.call);
+  PCB_CUDA(cudaMemcpyAsync(n_rows, row_of.p + R, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PCB_CUDA(cudaMemcpyAsync(n_calls, call_at.p + R, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+}
+
 }  // namespace
 
 extern "C" {
@@ -368,16 +398,9 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
       MergeOut out{o_root.p, o_pos.p, t_size.p, t_key.p, t_bc.p, t_up.p, t_calloff.p, t_calln.p, t_call.p};
       merge_dev(ctx, in, out);
       OutArr<int32_t> o_rep(ctx, mem, row_rep, R);
-      DevBuf<uint32_t> row_of(ctx, (size_t)R + 1), call_at(ctx, (size_t)R + 1);
-      PCB_LAUNCH(ctx, row_flag_kernel, grid_for((size_t)R + 1, 256), 256, 0, t_size.p, t_calln.p, R, row_of.p, call_at.p);
-      exclusive_scan_u32(ctx, row_of.p, row_of.p, (size_t)R + 1);
-      exclusive_scan_u32(ctx, call_at.p, call_at.p, (size_t)R + 1);
-      if (R) PCB_LAUNCH(ctx, row_compact_kernel, grid_for((size_t)R, 256), 256, 0, R, row_of.p, call_at.p, t_size.p, t_key.p, t_bc.p,
-                        t_up.p, t_calloff.p, t_calln.p, t_call.p, o_rep.p, o_size.p, o_key.p, o_bc.p, o_up.p, o_calloff.p, o_calln.p,
-                        o_call.p);
       uint32_t h_rows = 0, h_calls = 0;
-      PCB_CUDA(cudaMemcpyAsync(&h_rows, row_of.p + R, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-      PCB_CUDA(cudaMemcpyAsync(&h_calls, call_at.p + R, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      compact_rows(ctx, R, RowArrays{t_size.p, t_key.p, t_bc.p, t_up.p, t_calloff.p, t_calln.p, t_call.p}, o_rep.p,
+                   RowArrays{o_size.p, o_key.p, o_bc.p, o_up.p, o_calloff.p, o_calln.p, o_call.p}, &h_rows, &h_calls);
       o_bor.commit(R); o_root.commit(R); o_pos.commit(R);
       PCB_CUDA(cudaStreamSynchronize(ctx->stream));
       stage_collect(ctx);
@@ -386,6 +409,46 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
       o_rep.commit(h_rows); o_size.commit(h_rows); o_bc.commit(h_rows); o_up.commit(h_rows); o_calln.commit(h_rows);
       o_key.commit(h_rows); o_calloff.commit(h_rows); o_call.commit(h_calls);
     }
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int pcb_compact_shard(pcb_ctx *ctx, int mem_in, int mem_out, int32_t R, int64_t nnz, const int32_t *read_root, const int32_t *read_pos,
+                      const int32_t *row_size, const int64_t *row_key, const int32_t *row_bc, const int32_t *row_up,
+                      const int64_t *row_call_off, const int32_t *row_call_n, const int32_t *call_mut, const int32_t *bucket_of_read,
+                      int32_t *n_own, int32_t *own_read, int32_t *own_root, int32_t *own_pos, int32_t *own_bucket,
+                      int32_t *n_rows, int64_t *n_calls, int32_t *row_rep, int32_t *c_size, int64_t *c_key, int32_t *c_bc,
+                      int32_t *c_up, int64_t *c_call_off, int32_t *c_call_n, int32_t *c_call_mut) {
+  return guarded(ctx, [&] {
+    if (R < 0 || nnz < 0) throw Error(PCB_E_INPUT, "bad shape");
+    if ((bucket_of_read == nullptr) != (own_bucket == nullptr)) throw Error(PCB_E_INPUT, "bucket_of_read and own_bucket go together");
+    InArr<int32_t> i_bor(ctx, mem_in, bucket_of_read, R);
+    OutArr<int32_t> o_bucket(ctx, mem_out, own_bucket, R);
+    InArr<int32_t> i_root(ctx, mem_in, read_root, R), i_pos(ctx, mem_in, read_pos, R), i_size(ctx, mem_in, row_size, R),
+        i_bc(ctx, mem_in, row_bc, R), i_up(ctx, mem_in, row_up, R), i_calln(ctx, mem_in, row_call_n, R), i_call(ctx, mem_in, call_mut, nnz);
+    InArr<int64_t> i_key(ctx, mem_in, row_key, R), i_calloff(ctx, mem_in, row_call_off, R);
+    OutArr<int32_t> o_read(ctx, mem_out, own_read, R), o_root(ctx, mem_out, own_root, R), o_pos(ctx, mem_out, own_pos, R),
+        o_rep(ctx, mem_out, row_rep, R), o_size(ctx, mem_out, c_size, R), o_bc(ctx, mem_out, c_bc, R), o_up(ctx, mem_out, c_up, R),
+        o_calln(ctx, mem_out, c_call_n, R), o_call(ctx, mem_out, c_call_mut, nnz);
+    OutArr<int64_t> o_key(ctx, mem_out, c_key, R), o_calloff(ctx, mem_out, c_call_off, R);
+    DevBuf<uint32_t> own_at(ctx, (size_t)R + 1);
+    PCB_LAUNCH(ctx, own_flag_kernel, grid_for((size_t)R + 1, 256), 256, 0, i_root.p, R, own_at.p);
+    exclusive_scan_u32(ctx, own_at.p, own_at.p, (size_t)R + 1);
+    if (R) PCB_LAUNCH(ctx, own_compact_kernel, grid_for((size_t)R, 256), 256, 0, R, own_at.p, i_root.p, i_pos.p, i_bor.p, o_read.p, o_root.p,
+                      o_pos.p, o_bucket.p);
+    uint32_t h_own = 0, h_rows = 0, h_calls = 0;
+    PCB_CUDA(cudaMemcpyAsync(&h_own, own_at.p + R, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    compact_rows(ctx, R, RowArrays{const_cast<int32_t *>(i_size.p), const_cast<int64_t *>(i_key.p), const_cast<int32_t *>(i_bc.p),
+                                   const_cast<int32_t *>(i_up.p), const_cast<int64_t *>(i_calloff.p), const_cast<int32_t *>(i_calln.p),
+                                   const_cast<int32_t *>(i_call.p)},
+                 o_rep.p, RowArrays{o_size.p, o_key.p, o_bc.p, o_up.p, o_calloff.p, o_calln.p, o_call.p}, &h_rows, &h_calls);
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n_own) *n_own = (int32_t)h_own;
+    if (n_rows) *n_rows = (int32_t)h_rows;
+    if (n_calls) *n_calls = (int64_t)h_calls;
+    o_read.commit(h_own); o_root.commit(h_own); o_pos.commit(h_own); o_bucket.commit(h_own);
+    o_rep.commit(h_rows); o_size.commit(h_rows); o_bc.commit(h_rows); o_up.commit(h_rows); o_calln.commit(h_rows);
+    o_key.commit(h_rows); o_calloff.commit(h_rows); o_call.commit(h_calls);
     PCB_CUDA(cudaStreamSynchronize(ctx->stream));
   });
 }

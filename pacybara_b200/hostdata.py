@@ -519,6 +519,31 @@ MERGE_OUTPUTS = (("read_root", np.int32), ("read_pos", np.int32), ("row_size", n
                  ("row_bc", np.int32), ("row_up", np.int32), ("row_call_off", np.int64), ("row_call_n", np.int32))
 
 
+def merge_outputs_from_shards(shards: Sequence[Dict], n_reads: int) -> Dict[str, np.ndarray]:
+    """Per-read merge outputs from the compacted results of all shards (Context.compact_shard): every read is owned
+    by exactly one shard, rows are named by their representative read."""
+    out = {name: np.full(n_reads, 0 if name == "row_size" else -1, dtype=dt) for name, dt in MERGE_OUTPUTS}
+    if all("own_bucket" in s for s in shards):
+        out["bucket_of_read"] = np.full(n_reads, -1, dtype=np.int32)
+    calls, base = [], 0
+    for s in shards:
+        own = np.asarray(s["own_read"]).astype(np.int64)
+        out["read_root"][own] = s["own_root"]
+        out["read_pos"][own] = s["own_pos"]
+        if "bucket_of_read" in out:
+            out["bucket_of_read"][own] = s["own_bucket"]
+        rep = np.asarray(s["row_rep"]).astype(np.int64)
+        for name in ("row_size", "row_key", "row_bc", "row_up", "row_call_n"):
+            out[name][rep] = s[name]
+        out["row_call_off"][rep] = np.asarray(s["row_call_off"]) + base
+        calls.append(np.asarray(s["call_mut"]))
+        base += int(calls[-1].shape[0])
+    if (out["read_root"] < 0).any():
+        raise RuntimeError("some reads belong to no shard")
+    out["call_mut"] = np.concatenate(calls) if calls else np.zeros(0, dtype=np.int32)
+    return out
+
+
 def rows_from_merge_outputs(out: Dict[str, np.ndarray]) -> ClusterRows:
     """Per-read / per-representative arrays of pcb_merge -> the table layout of
     pacybara_cluster.py:546-567: clusters in creation order of the surviving cluster id, then

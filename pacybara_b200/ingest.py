@@ -63,6 +63,19 @@ def _slices(raw: bytes, off: np.ndarray, length: np.ndarray) -> List[str]:
     return [txt[o:o + n] for o, n in zip(off.tolist(), length.tolist())]
 
 
+def fastq_from_bytes(ctx: Context, fastq: bytes) -> hostdata.FastqReads:
+    """The reads pacybara_precluster.py:47-63 would keep, as device matrices (torch CUDA tensors) + id strings."""
+    with Text(ctx, fastq) as fq:
+        if fq.n_exotic:
+            raise NeedsLineParser(f"FASTQ has bytes outside plain ASCII text: {fq.n_exotic}")
+        rec = fq.fastq_records()
+        if rec["n_bad"]:
+            raise NeedsLineParser(f"FASTQ records the tokenizer does not model: {rec['n_bad']}")
+        f = fq.fastq_fetch(max(4, (rec["max_len"] + 3) // 4 * 4))
+    ids = _slices(fastq, f["id_off"].cpu().numpy(), f["id_len"].cpu().numpy())
+    return hostdata.FastqReads(ids, f["seq"], f["qual"], f["length"])
+
+
 def arrays_from_bytes(ctx: Context, fastq: bytes, geno: bytes, uptag: Optional[bytes] = None, laps: Optional[Dict] = None
                       ) -> Tuple[pipeline.ReadArrays, Dict]:
     """Device-resident ReadArrays (torch CUDA tensors) + the string tables of the writer.

@@ -10,8 +10,12 @@ What shards and what is exchanged:
                           canonical row order;
   4. merge                SHARDED by connected component (round-robin, pcb_merge shard_rank/count):
                           components are independent units of the reference's sequential algorithm;
-  5. table exchange       element-wise MAX all-reduce of the per-read outputs (entries a rank does not
-                          own are PCB_FILL = INT32_MIN).
+  5. result               stays SHARDED by default (combine=False): every rank holds the rows of its own
+                          components (entries of reads it does not own are PCB_FILL = INT32_MIN) and, with host
+                          buffers, ships only those (pcb_compact_shard).  combine=True replicates the whole result
+                          on every rank with an element-wise MAX all-reduce of the per-read outputs.
+With host buffers (on_device=False) every rank uploads 1/N of the reads and the ranks all-gather them over NVLink
+(upload_sharded), instead of N full copies crossing PCIe.
 """
 from __future__ import annotations
 
@@ -48,14 +52,67 @@ def gather_edges(ei, ej, ed, world: int):
     return cat[0].contiguous(), cat[1].contiguous(), cat[2].contiguous()
 
 
+def read_chunk(n: int, rank: int, world: int):
+    """Equal chunks (the last ones may be short or empty): rank r uploads reads [lo, hi)."""
+    chunk = (n + world - 1) // world
+    return chunk, min(n, rank * chunk), min(n, (rank + 1) * chunk)
+
+
+def upload_sharded(arrs: Dict, rank: int, world: int, dev) -> Dict:
+    """Host arrays (the full read set, identical on every rank) -> full device arrays on every rank, with every rank
+    copying only its chunk of the reads over PCIe and the chunks all-gathered between the GPUs.  The genotype CSR
+    travels as it is: geno_ptr holds global offsets, so the concatenation of the chunks IS the pointer array."""
+    import torch
+    import torch.distributed as dist
+    R = int(arrs["length"].shape[0])
+    chunk, lo, hi = read_chunk(R, rank, world)
+    out = {}
+
+    def gather_rows(src, extra_tail=0):
+        shape = (chunk,) + tuple(src.shape[1:])
+        mine = torch.zeros(shape, dtype=src.dtype, device=dev)
+        if hi > lo:
+            mine[: hi - lo].copy_(src[lo:hi], non_blocking=True)
+        full = torch.empty((world * chunk + extra_tail,) + tuple(src.shape[1:]), dtype=src.dtype, device=dev)
+        dist.all_gather_into_tensor(full[: world * chunk], mine)
+        return full
+
+    for k in ("seq", "length", "lexrank", "up_id"):
+        if arrs.get(k) is not None:
+            out[k] = gather_rows(arrs[k])[:R]
+    gptr = arrs["geno_ptr"]
+    nnz = int(gptr[R])
+    full = gather_rows(gptr[:R], extra_tail=1)
+    full[R] = nnz
+    out["geno_ptr"] = full[: R + 1]
+    # genotype entries of my reads: [ptr[lo], ptr[hi]); the counts of all ranks follow from the (replicated) host pointer
+    bounds = [int(gptr[min(R, r * chunk)]) for r in range(world + 1)]
+    m = max(1, max(bounds[r + 1] - bounds[r] for r in range(world)))
+    for k in ("geno_mut", "geno_q"):
+        mine = torch.zeros(m, dtype=arrs[k].dtype, device=dev)
+        n = bounds[rank + 1] - bounds[rank]
+        if n:
+            mine[:n].copy_(arrs[k][bounds[rank]: bounds[rank + 1]], non_blocking=True)
+        allbuf = torch.empty(world * m, dtype=arrs[k].dtype, device=dev)
+        dist.all_gather_into_tensor(allbuf, mine)
+        parts = [allbuf[r * m: r * m + bounds[r + 1] - bounds[r]] for r in range(world)]
+        out[k] = torch.cat(parts) if world > 1 else parts[0]
+        assert out[k].numel() == nnz
+    out["mut_rank"] = arrs["mut_rank"].to(dev, non_blocking=True)
+    return out
+
+
 def cluster_reads_sharded(ctx: Context, arrs: Dict, params: Dict, rank: int, world: int, on_device: bool = True,
-                          full_table: bool = False) -> Dict:
+                          full_table: bool = False, combine: bool = False) -> Dict:
     """`arrs`: dict of torch tensors (seq, qual, length, lexrank, geno_ptr, geno_mut, geno_q, mut_rank[, up_id]),
-    CUDA tensors when on_device else pinned host tensors (copied in here; results copied back)."""
+    CUDA tensors when on_device else pinned host tensors holding the full read set on every rank.
+    Result: on_device -> per-read device arrays (combine=False: entries of reads other ranks own are PCB_FILL);
+    host buffers -> combine=False: this rank's reads and rows, compacted (Context.compact_shard; put the ranks' parts
+    together with hostdata.merge_outputs_from_shards); combine=True: the full per-read arrays on every rank."""
     import torch
     import torch.distributed as dist
     dev = f"cuda:{ctx.device}"
-    a = arrs if on_device else {k: v.to(dev, non_blocking=True) for k, v in arrs.items() if k != "qual"}
+    a = arrs if on_device else upload_sharded(arrs, rank, world, dev)
     max_diff = int(params["max_diff"])
     R = int(a["length"].shape[0])
     # 1. buckets (replicated)
@@ -81,14 +138,18 @@ def cluster_reads_sharded(ctx: Context, arrs: Dict, params: Dict, rank: int, wor
     else:
         out = ctx.merge(prob, PairList(ei, ej, ed, ped), shard=(rank, world), bucket_seq=bseq, bucket_len=blen,
                         on_demand_k=2 * max_diff)
-    # 5. combine
-    for name in list(out.keys()):
-        dist.all_reduce(out[name], op=dist.ReduceOp.MAX)
-    torch.cuda.current_stream(ctx.device).synchronize()
-    out["bucket_of_read"] = b["bucket_of_read"]
-    out["n_buckets"] = U
-    out["n_edges"] = int(ei.numel())
-    out["local_stats"] = local_stats
+    # 5. result
+    if combine:
+        for name in list(out.keys()):
+            dist.all_reduce(out[name], op=dist.ReduceOp.MAX)
+        torch.cuda.current_stream(ctx.device).synchronize()
+    extra = dict(bucket_of_read=b["bucket_of_read"], n_buckets=U, n_edges=int(ei.numel()), local_stats=local_stats)
+    if not on_device and not combine:
+        # bucket ids travel for my reads only (row_bc names buckets; the barcode of a bucket is that of any of its reads)
+        shard = ctx.compact_shard(dict(out, bucket_of_read=b["bucket_of_read"]), to_host=True)
+        shard.update(n_buckets=U, n_edges=extra["n_edges"], local_stats=local_stats)
+        return shard
+    out.update(extra)
     if not on_device:
         # results to page-locked host buffers (reused by the next call, like Context(pinned_outputs=True))
         host = {}

@@ -14,13 +14,21 @@ from . import hostdata
 
 
 def main(argv=None) -> int:
+    import io
+    from . import ingest
     from .api import Context
-    reads = hostdata.parse_fastq_for_precluster(sys.stdin)
+    raw = sys.stdin.buffer.read()
     out = sys.stdout
-    if len(reads.ids) == 0:
-        return 0
     ctx = Context(0)
+    try:                                   # device tokenizer (csrc/ingest.cu) ...
+        reads = ingest.fastq_from_bytes(ctx, raw)
+    except ingest.NeedsLineParser:         # ... or, for anything it only counts, the reference's line loop
+        reads = hostdata.parse_fastq_for_precluster(io.TextIOWrapper(io.BytesIO(raw)))
+    if len(reads.ids) == 0:
+        ctx.close()
+        return 0
     res = ctx.bucket(reads.seq, reads.qual, reads.length)
+    res = {k: (v.cpu().numpy() if hasattr(v, "data_ptr") else v) for k, v in res.items()}
     hostdata.write_preclust_fastq(out, reads.ids, res["bucket_ptr"], res["bucket_reads"], res["bucket_seq"],
                                   res["bucket_len"], res["bucket_qsum"])
     out.flush()

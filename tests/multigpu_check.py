@@ -31,7 +31,7 @@ def main():
     params = dict(max_diff=lib.params["max_diff"], min_qual=lib.params["min_qual"], min_jaccard=0.2, min_matches=1)
     dev = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in vars(ra).items() if v is not None}
     full = os.environ.get("PCB_FULL_TABLE", "0") == "1"
-    out = multigpu.cluster_reads_sharded(ctx, dev, params, rank, world, on_device=True, full_table=full)
+    out = multigpu.cluster_reads_sharded(ctx, dev, params, rank, world, on_device=True, full_table=full, combine=True)
     single = ctx.cluster_reads(dev["seq"], dev["qual"], dev["length"], dev["lexrank"], dev.get("up_id"), dev["geno_ptr"],
                                dev["geno_mut"], dev["geno_q"], dev["mut_rank"], full_table=full, **params)
     bad = [k for k in ("read_root", "read_pos", "row_size", "row_key", "row_bc", "row_up", "row_call_n", "bucket_of_read")
@@ -49,6 +49,30 @@ def main():
         assert digest == canon.table_digest(want), "sharded table differs from the oracle"
         print(f"multigpu_check ok: {world} ranks, {lib.n_reads} reads, {out['n_buckets']} buckets, {out['n_edges']} edges, "
               f"rank-0 share of scored pairs {out['local_stats']['pairs_scored']}")
+    # results left sharded on the devices: the element-wise max over the ranks is the single-GPU result
+    names = ("read_root", "read_pos", "row_size", "row_key", "row_bc", "row_up", "row_call_off", "row_call_n", "call_mut")
+    part = multigpu.cluster_reads_sharded(ctx, dev, params, rank, world, on_device=True, full_table=full, combine=False)
+    owned = int((part["read_root"] != -(1 << 31)).sum())
+    for k in names:
+        t = part[k].clone()
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert torch.equal(t, single[k]), f"rank {rank}: max over shards != single-GPU in {k}"
+    # host buffers: every rank uploads its chunk of the reads and gets its own reads and rows back, compacted
+    from pacybara_b200 import hostdata
+    pinned = {k: v.cpu().pin_memory() for k, v in dev.items()}
+    shard = multigpu.cluster_reads_sharded(ctx, pinned, params, rank, world, on_device=False, full_table=full, combine=False)
+    assert shard["own_read"].shape[0] == owned
+    mine = {k: (np.array(v) if hasattr(v, "shape") else v) for k, v in shard.items()}
+    parts = [None] * world
+    dist.all_gather_object(parts, mine)
+    whole = hostdata.merge_outputs_from_shards(parts, lib.n_reads)
+    ref = {k: single[k].cpu().numpy() for k in names + ("bucket_of_read",)}
+    assert np.array_equal(whole["bucket_of_read"], ref["bucket_of_read"])
+    a, b = hostdata.rows_from_merge_outputs(ref), hostdata.rows_from_merge_outputs(whole)
+    for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f"rank {rank}: host shards != single-GPU in {f}"
+    if rank == 0:
+        print(f"multigpu_check sharded results ok: rank 0 owns {owned} of {lib.n_reads} reads, {shard['row_rep'].shape[0]} rows")
     dist.barrier()
     dist.destroy_process_group()
 
