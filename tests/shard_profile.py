@@ -31,6 +31,7 @@ def main():
         bseq, blen = b["bucket_seq"].contiguous(), b["bucket_len"].contiguous()
         lo, hi = multigpu.shard_range(U, 0, N)
         (ei, ej, ed), t_pairs_shard = timed(lambda: ctx.edit_pairs(bseq, blen, 2, q_range=(lo, hi)))
+        st_pairs = {k: round(ctx.stat(k) * 1e-6, 3) for k in ("t_index_ns", "probe_ns", "t_hits_ns")}
         (fi, fj, fd), t_pairs_all = timed(lambda: ctx.edit_pairs(bseq, blen, 2))
         fi, fj, fd = fi.clone(), fj.clone(), fd.clone()
         _, t_sort = timed(lambda: ctx.sort_edges(fi, fj, fd, U))
@@ -39,9 +40,12 @@ def main():
                             lexrank=a["lexrank"], bc_id=b["bucket_of_read"].contiguous(), up_id=None, geno_ptr=a["geno_ptr"],
                             geno_mut=a["geno_mut"], geno_q=a["geno_q"], mut_rank=a["mut_rank"], max_diff=2, min_qual=32)
         out, t_merge = timed(lambda: ctx.merge(prob, PairList(fi, fj, fd, ped), shard=(0, N), bucket_seq=bseq, bucket_len=blen, on_demand_k=4))
+        st_merge = {k: round(ctx.stat(k) * 1e-6, 3) for k in ("t_prep_ns", "t_replay_ns", "t_scatter_ns")}
+        _, t_compact = timed(lambda: ctx.compact_shard(dict(out, bucket_of_read=b["bucket_of_read"]), to_host=True))
         nbytes = sum(v.numel() * v.element_size() for v in out.values())
     print(f"N={N} reads={R} U={U} edges={fi.numel()}: bucket {t_bucket:.2f} ms, pairs(shard 1/{N}) {t_pairs_shard:.2f} ms "
-          f"(all: {t_pairs_all:.2f}), sort_edges {t_sort:.2f}, merge(shard) {t_merge:.2f} ms, all-reduce payload {nbytes / 1e6:.0f} MB")
+          f"(all: {t_pairs_all:.2f}), sort_edges {t_sort:.2f}, merge(shard) {t_merge:.2f} ms, compact+D2H {t_compact:.2f} ms, all-reduce payload {nbytes / 1e6:.0f} MB; "
+          f"pair stages {st_pairs}, merge stages {st_merge}")
 
 
 if __name__ == "__main__":
