@@ -219,6 +219,23 @@ int pcb_compact_shard(pcb_ctx *ctx, int mem_in, int mem_out, int32_t R, int64_t 
                       int32_t *c_up, int64_t *c_call_off, int32_t *c_call_n, int32_t *c_call_mut);
 
 /*
+ * f3 -- barcode -> library matching with maxErr: what barseq_caller.R asks of
+ * yogiseq::new.bc.matcher(bcRef$barcode, errCutoff = maxErr)$findMatches (src/barseq_caller.R:57,242).  yogiseq is
+ * not vendored in the reference, so its matcher is restated from that call site -- per read: the library rows at the
+ * smallest distance, that distance, and how many rows share it -- with the distance of this library (unit-cost
+ * Levenshtein, the same Myers kernel and seed index as pcb_edit_pairs): parity unpinned, see DESIGN.md.
+ *   library: lib_seq [L, lib_stride], lib_len [L];  queries: q_seq [Q, q_stride], q_len [Q]  (ACGT, 1..64 nt)
+ *   best_d [Q]     smallest distance <= max_err to any library row, -1 if there is none
+ *   n_best [Q]     library rows at that distance (duplicated library barcodes count once per row), 0 if none
+ *   first_hit [Q]  the smallest such row, -1 if none
+ *   n_pairs        all (query, row) pairs within max_err; fetch them with pcb_edit_pairs_fetch as (query, row, d),
+ *                  sorted by (query, row)
+ */
+int pcb_match_barcodes(pcb_ctx *ctx, int mem, const uint8_t *lib_seq, const int32_t *lib_len, int32_t L, int32_t lib_stride,
+                       const uint8_t *q_seq, const int32_t *q_len, int32_t Q, int32_t q_stride, int32_t max_err,
+                       int32_t *best_d, int32_t *n_best, int32_t *first_hit, int64_t *n_pairs);
+
+/*
  * f1 (first row after the hot path) -- barcode-collision tags and the dominance test of the
  * soft filter, on a cluster table given as per-row ids:
  *   collision[i]     = the virtual barcode of row i occurs in more than one row   (tagDups, src/pacybara_translate.R:58-68)

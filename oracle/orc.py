@@ -4,7 +4,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
-from typing import Optional, Tuple
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 
@@ -82,6 +82,18 @@ def edit_pairs(seq: np.ndarray, length: np.ndarray, k: int, method: str = "seede
         if n <= cap:
             return oi[:n].copy(), oj[:n].copy(), od[:n].copy()
         cap = n
+
+
+def match_barcodes(lib_seq: np.ndarray, lib_len: np.ndarray, q_seq: np.ndarray, q_len: np.ndarray, k: int) -> Dict[str, np.ndarray]:
+    """f3: per query the smallest Levenshtein distance <= k to a library row (-1: none), the number of rows at that
+    distance and the first of them; exhaustive DP."""
+    lib_seq, lib_len, q_seq, q_len = _c(lib_seq, np.uint8), _c(lib_len, np.int32), _c(q_seq, np.uint8), _c(q_len, np.int32)
+    L, Q = lib_len.shape[0], q_len.shape[0]
+    best, nb, first = (np.empty(max(Q, 1), dtype=np.int32) for _ in range(3))
+    lib().orc_match_brute(_p(lib_seq), _p(lib_len), C.c_int32(L), C.c_int32(lib_seq.shape[1] if L else 1),
+                          _p(q_seq), _p(q_len), C.c_int32(Q), C.c_int32(q_seq.shape[1] if Q else 1), C.c_int32(k),
+                          _p(best), _p(nb), _p(first))
+    return dict(best_d=best[:Q], n_best=nb[:Q], first_hit=first[:Q])
 
 
 def cluster(p: MergeProblem, ed_q: np.ndarray, ed_r: np.ndarray, ed_d: np.ndarray) -> ClusterRows:

@@ -174,6 +174,28 @@ int64_t orc_edit_pairs_brute(const uint8_t *seq, const int32_t *len, int32_t U, 
   return n;
 }
 
+/* f3: nearest library barcodes of every query (what src/barseq_caller.R:57,242 asks of yogiseq's bc.matcher, restated
+ * from the call site: the rows at the smallest Levenshtein distance <= k, that distance, their number).  Exhaustive:
+ * every (query, row) pair goes through the full DP. */
+void orc_match_brute(const uint8_t *lib, const int32_t *lib_len, int32_t L, int32_t lib_stride,
+                     const uint8_t *qs, const int32_t *q_len, int32_t Q, int32_t q_stride, int32_t k,
+                     int32_t *best_d, int32_t *n_best, int32_t *first_hit) {
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 64)
+#endif
+  for (int32_t q = 0; q < Q; q++) {
+    int32_t best = -1, cnt = 0, first = -1;
+    for (int32_t j = 0; j < L; j++) {
+      if (abs(q_len[q] - lib_len[j]) > k) continue;
+      int32_t d = orc_lev(qs + (int64_t)q * q_stride, q_len[q], lib + (int64_t)j * lib_stride, lib_len[j]);
+      if (d > k) continue;
+      if (best < 0 || d < best) { best = d; cnt = 1; first = j; }
+      else if (d == best) cnt++;
+    }
+    best_d[q] = best; n_best[q] = cnt; first_hit[q] = first;
+  }
+}
+
 typedef struct { uint64_t key; int32_t j; } SeedEnt;
 static int seedent_cmp(const void *a, const void *b) {
   const SeedEnt *x = (const SeedEnt *)a, *y = (const SeedEnt *)b;

@@ -268,6 +268,33 @@ class Context:
         out["n_edges"] = int(ne.value)
         return out
 
+    # ------------------------------------------------------------------ f3
+    def match_barcodes(self, lib_seq, lib_len, q_seq, q_len, max_err: int, want_pairs: bool = False) -> Dict:
+        """Nearest library barcodes of every query within max_err (pcb_match_barcodes).  want_pairs=True also returns
+        every (query, row, d) within max_err, sorted by (query, row)."""
+        arrays = [lib_seq, lib_len, q_seq, q_len]
+        if any(_is_dev(a) for a in arrays):
+            _torch()
+        mem = self._kind(*arrays)
+        L, Q = int(lib_len.shape[0]), int(q_len.shape[0])
+        ls = int(lib_seq.shape[1]) if L else 1
+        qs = int(q_seq.shape[1]) if Q else 1
+        keep: list = []
+        best, p_best = self._out(mem, (max(Q, 1),), np.int32)
+        nb, p_nb = self._out(mem, (max(Q, 1),), np.int32)
+        first, p_first = self._out(mem, (max(Q, 1),), np.int32)
+        n_pairs = C.c_int64(0)
+        self._check(self.lib.pcb_match_barcodes(self.h, mem, self._in(lib_seq, np.uint8, keep), self._in(lib_len, np.int32, keep), L, ls,
+                                                self._in(q_seq, np.uint8, keep), self._in(q_len, np.int32, keep), Q, qs, int(max_err),
+                                                p_best, p_nb, p_first, C.byref(n_pairs)))
+        out = dict(best_d=best[:Q], n_best=nb[:Q], first_hit=first[:Q], n_pairs=int(n_pairs.value))
+        if want_pairs:
+            n = out["n_pairs"]
+            bufs = [self._out(mem, (max(n, 1),), np.int32) for _ in range(3)]
+            self._check(self.lib.pcb_edit_pairs_fetch(self.h, mem, bufs[0][1], bufs[1][1], bufs[2][1], n))
+            out["pair_q"], out["pair_row"], out["pair_d"] = (b[0][:n] for b in bufs)
+        return out
+
     def compact_shard(self, out: Dict, to_host: bool = True) -> Dict:
         """The reads this shard owns and their rows, compacted (pcb_compact_shard).  `out`: per-read outputs of
         merge() / cluster_reads() (numpy or torch CUDA).  to_host=True returns numpy arrays (page-locked and reused when

@@ -453,6 +453,26 @@ int pcb_compact_shard(pcb_ctx *ctx, int mem_in, int mem_out, int32_t R, int64_t 
   });
 }
 
+int pcb_match_barcodes(pcb_ctx *ctx, int mem, const uint8_t *lib_seq, const int32_t *lib_len, int32_t L, int32_t lib_stride,
+                       const uint8_t *q_seq, const int32_t *q_len, int32_t Q, int32_t q_stride, int32_t max_err,
+                       int32_t *best_d, int32_t *n_best, int32_t *first_hit, int64_t *n_pairs) {
+  return guarded(ctx, [&] {
+    if (L < 0 || Q < 0 || lib_stride < 1 || q_stride < 1) throw Error(PCB_E_INPUT, "bad shape");
+    InArr<uint8_t> d_lseq(ctx, mem, lib_seq, (size_t)L * lib_stride), d_qseq(ctx, mem, q_seq, (size_t)Q * q_stride);
+    InArr<int32_t> d_llen(ctx, mem, lib_len, L), d_qlen(ctx, mem, q_len, Q);
+    OutArr<int32_t> o_best(ctx, mem, best_d, Q), o_n(ctx, mem, n_best, Q), o_first(ctx, mem, first_hit, Q);
+    if (Q > 0 && (!o_best.p || !o_n.p || !o_first.p)) throw Error(PCB_E_INPUT, "all three outputs are required");
+    PackedBarcodes lib, qs;
+    lib.n = 0; qs.n = 0;
+    if (L) pack_barcodes(ctx, d_lseq.p, d_llen.p, nullptr, L, lib_stride, lib);
+    if (Q) pack_barcodes(ctx, d_qseq.p, d_qlen.p, nullptr, Q, q_stride, qs);
+    match_barcodes_dev(ctx, lib, qs, max_err, o_best.p, o_n.p, o_first.p);
+    if (n_pairs) *n_pairs = ctx->edges.n;
+    o_best.commit(Q); o_n.commit(Q); o_first.commit(Q);
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
 int pcb_tag_rows(pcb_ctx *ctx, int mem, int32_t n_rows, const int32_t *row_bc, const int32_t *row_up, const int32_t *row_size,
                  int32_t n_bc_ids, int32_t n_up_ids, double min_ratio, uint8_t *collision, uint8_t *up_collision, uint8_t *usable) {
   return guarded(ctx, [&] {

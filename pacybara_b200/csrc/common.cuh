@@ -156,6 +156,9 @@ int32_t bucket_reads_dev(pcb_ctx *ctx, const uint8_t *seq, const uint8_t *qual, 
                          int32_t stride, const BucketOut &out, PackedBarcodes *unique_out);
 
 void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q_begin, int32_t q_end);
+// f3: nearest library barcodes of every query within k; the (query, row, d) rows stay in ctx->edges
+void match_barcodes_dev(pcb_ctx *ctx, const PackedBarcodes &library, const PackedBarcodes &queries, int32_t k, int32_t *best_d,
+                        int32_t *n_best, int32_t *first_hit);
 
 struct MergeIn {             // device pointers
   int32_t R, U, n_mut;

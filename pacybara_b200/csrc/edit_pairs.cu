@@ -91,31 +91,35 @@ __device__ __forceinline__ int myers32_dev(uint32_t pL, uint32_t pH, int m, uint
 // counters: [0] hits emitted, [1] pairs scored, [2] cells (sum len_i * len_j), [3] next block of probes.
 constexpr int PROBE_WARPS = 8;
 
-template <bool WIDE>
-__device__ __forceinline__ void score_pair(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int2 pr,
+// SELF: queries and targets are the same set (the clustering path); otherwise query i comes from (qplanes, qlen)
+// and the hit key is (query, target) as it stands (f3: barcode -> library matching).
+template <bool WIDE, bool SELF>
+__device__ __forceinline__ void score_pair(const ulonglong2 *__restrict__ qplanes, const int32_t *__restrict__ qlen,
+                                           const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int2 pr,
                                            int k, uint64_t *__restrict__ hit_key, uint32_t *__restrict__ hit_d,
                                            unsigned long long cap, int key_shift, unsigned long long *counters,
                                            unsigned long long &scored, unsigned long long &cells) {
   int32_t i = pr.x, j = pr.y;
-  int32_t m = len[i], n = len[j];
+  int32_t m = qlen[i], n = len[j];
   int32_t dl = m - n;
   if (dl > k || -dl > k) return;
-  ulonglong2 a = planes[i], b = planes[j];
+  ulonglong2 a = qplanes[i], b = planes[j];
   int d = WIDE ? myers64(a.x, a.y, m, b.x, b.y, n)
                : myers32_dev((uint32_t)a.x, (uint32_t)a.y, m, (uint32_t)b.x, (uint32_t)b.y, n);
   scored++; cells += (unsigned long long)(m * n);
   if (d <= k) {
     unsigned long long at = atomicAdd(&counters[0], 1ull);
     if (at < cap) {
-      uint32_t x = i < j ? i : j, y = i < j ? j : i;
+      uint32_t x = (SELF && j < i) ? j : i, y = (SELF && j < i) ? i : j;
       hit_key[at] = ((uint64_t)x << key_shift) | y;
       hit_d[at] = (uint32_t)d;
     }
   }
 }
 
-template <bool WIDE>
-__global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len,
+template <bool WIDE, bool SELF>
+__global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(const ulonglong2 *__restrict__ qplanes, const int32_t *__restrict__ qlen,
+                                                                  const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len,
                                                                   int32_t q_begin, int32_t q_end, SeedGeom g,
                                                                   const uint32_t *__restrict__ bin_off, const int32_t *__restrict__ ent,
                                                                   uint64_t *__restrict__ hit_key, uint32_t *__restrict__ hit_d,
@@ -142,11 +146,11 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(const ulonglong
       qi = q_begin + (int32_t)(pid / per_query);
       int32_t rem = (int32_t)(pid % per_query);
       int32_t t = rem / n_shift, s = rem % n_shift - (g.q == 0 ? 0 : g.k);
-      int32_t m = len[qi];
+      int32_t m = qlen[qi];
       int32_t st = g.q == 0 ? 0 : (int32_t)((int64_t)t * m / (g.k + 1));
       int32_t p = st + s;
       if (p >= 0 && p < g.npos && m >= len_lo && m <= len_hi) {     // queries of other lengths use the other index
-        ulonglong2 a = planes[qi];
+        ulonglong2 a = qplanes[qi];
         uint32_t bin = seed_bin(g, a.x, a.y, st, p);
         lo = bin_off[bin]; hi = bin_off[bin + 1];
       }
@@ -156,14 +160,14 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(const ulonglong
       int32_t j = 0;
       if (lo < hi) {
         j = ent[lo++];
-        keep = j != qi && is_query_side(qi, j);
+        keep = !SELF || (j != qi && is_query_side(qi, j));
       }
       uint32_t mask = __ballot_sync(0xFFFFFFFFu, keep);
       if (keep) queue[warp][cnt + __popc(mask & lt_mask)] = make_int2(qi, j);
       cnt += __popc(mask);
       __syncwarp();
       if (cnt >= 32) {
-        score_pair<WIDE>(planes, len, queue[warp][lane], g.k, hit_key, hit_d, cap, key_shift, counters, scored, cells);
+        score_pair<WIDE, SELF>(qplanes, qlen, planes, len, queue[warp][lane], g.k, hit_key, hit_d, cap, key_shift, counters, scored, cells);
         int rest = cnt - 32;
         int2 carry = make_int2(0, 0);
         if (lane < rest) carry = queue[warp][32 + lane];
@@ -174,7 +178,7 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(const ulonglong
       }
     }
   }
-  if (lane < cnt) score_pair<WIDE>(planes, len, queue[warp][lane], g.k, hit_key, hit_d, cap, key_shift, counters, scored, cells);
+  if (lane < cnt) score_pair<WIDE, SELF>(qplanes, qlen, planes, len, queue[warp][lane], g.k, hit_key, hit_d, cap, key_shift, counters, scored, cells);
   for (int o = 16; o > 0; o >>= 1) {
     scored += __shfl_down_sync(0xFFFFFFFFu, scored, o);
     cells += __shfl_down_sync(0xFFFFFFFFu, cells, o);
@@ -218,16 +222,54 @@ static void free_edges(pcb_ctx *ctx) {
   e = pcb_edges();
 }
 
+// best match of every query among the (query, target, d) rows sorted by (query, target)
+__global__ void match_reduce_kernel(const int32_t *__restrict__ eq, const int32_t *__restrict__ et, const int32_t *__restrict__ ed,
+                                    int64_t n, int32_t Q, int32_t *__restrict__ best_d, int32_t *__restrict__ n_best,
+                                    int32_t *__restrict__ first_hit) {
+  int32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= Q) return;
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (eq[mid] < q) lo = mid + 1; else hi = mid;
+  }
+  int32_t best = -1, cnt = 0, first = -1;
+  for (int64_t x = lo; x < n && eq[x] == q; x++) {
+    int32_t d = ed[x];
+    if (best < 0 || d < best) { best = d; cnt = 1; first = et[x]; }
+    else if (d == best) cnt++;
+  }
+  best_d[q] = best; n_best[q] = cnt; first_hit[q] = first;
+}
+
+static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarcodes *queries, int32_t k, int32_t q_begin, int32_t q_end);
+
 void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q_begin, int32_t q_end) {
+  pair_search(ctx, bc, nullptr, k, q_begin, q_end);
+}
+
+void match_barcodes_dev(pcb_ctx *ctx, const PackedBarcodes &library, const PackedBarcodes &queries, int32_t k, int32_t *best_d,
+                        int32_t *n_best, int32_t *first_hit) {
+  pair_search(ctx, library, &queries, k, 0, queries.n);
+  const pcb_edges &e = ctx->edges;
+  if (queries.n)
+    PCB_LAUNCH(ctx, match_reduce_kernel, grid_for((size_t)queries.n, 256), 256, 0, e.ei, e.ej, e.ed, e.n, queries.n, best_d, n_best, first_hit);
+}
+
+// Pairs (query, target) within k.  queries == nullptr: the self-join of the clustering path (every unordered pair
+// once, through its query side); otherwise the rows are (query index, target index) as they stand.
+static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarcodes *queries, int32_t k, int32_t q_begin, int32_t q_end) {
   free_edges(ctx);
+  const bool self = queries == nullptr;
+  const PackedBarcodes &qs = self ? bc : *queries;
   const int32_t U = bc.n;
   ctx->stats[PCB_STAT_PAIRS_SCORED] = ctx->stats[PCB_STAT_CELLS] = ctx->stats[PCB_STAT_EDGES] = 0;
   ctx->stats[PCB_STAT_PROBE_NS] = 0;
   if (k < 0 || k > 8) throw Error(PCB_E_INPUT, "k must be in 0..8");
-  if (q_begin < 0 || q_end > U || q_begin > q_end) throw Error(PCB_E_INPUT, "query range outside [0, U)");
+  if (q_begin < 0 || q_end > qs.n || q_begin > q_end) throw Error(PCB_E_INPUT, "query range outside [0, U)");
   pcb_edges &res = ctx->edges;
   res.valid = true;
-  if (U < 2 || q_begin == q_end) return;
+  if (U < (self ? 2 : 1) || q_begin == q_end) return;
 
   // ---- seed lengths.  A query of length m splits into k+1 pieces of at least floor(m/(k+1)) bases, so it can
   // probe an index of q-grams with q up to that.  Most barcodes share one length; the few shorter ones (deletions)
@@ -235,11 +277,11 @@ void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q
   // long enough for it, q_lo for the rest.  Either way every pair is found through its query side.
   DevBuf<uint32_t> d_hist(ctx, 66);
   PCB_CUDA(cudaMemsetAsync(d_hist.p, 0, 66 * sizeof(uint32_t), ctx->stream));
-  PCB_LAUNCH(ctx, len_hist_kernel, (unsigned)ctx->sm_count, 256, 0, bc.len.p, U, d_hist.p);
+  PCB_LAUNCH(ctx, len_hist_kernel, (unsigned)ctx->sm_count, 256, 0, qs.len.p, qs.n, d_hist.p);
   uint32_t h_hist[66];
   PCB_CUDA(cudaMemcpyAsync(h_hist, d_hist.p, sizeof(h_hist), cudaMemcpyDeviceToHost, ctx->stream));
   PCB_CUDA(cudaStreamSynchronize(ctx->stream));
-  int32_t mode_len = bc.min_len;
+  int32_t mode_len = qs.min_len;
   for (int32_t l = 1; l <= 64; l++) if (h_hist[l] > h_hist[mode_len]) mode_len = l;
   auto make_geom = [&](int32_t q) {
     SeedGeom g;
@@ -255,8 +297,8 @@ void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q
   auto probe_positions = [&](const SeedGeom &g, int32_t lo, int32_t hi) -> uint64_t {
     if (g.q == 0) return ~0ull;
     uint64_t mask = 0;
-    if (lo < bc.min_len) lo = bc.min_len;
-    if (hi > bc.max_len) hi = bc.max_len;
+    if (lo < qs.min_len) lo = qs.min_len;
+    if (hi > qs.max_len) hi = qs.max_len;
     for (int32_t m = lo; m <= hi; m++)
       for (int32_t t = 0; t <= k; t++)
         for (int32_t sft = -k; sft <= k; sft++) {
@@ -270,8 +312,8 @@ void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q
   int n_idx = 1;
   idx[0].g = make_geom(mode_len / (k + 1));
   idx[0].len_lo = idx[0].g.q * (k + 1); idx[0].len_hi = 64;
-  if (bc.min_len < idx[0].len_lo) {
-    idx[1].g = make_geom(bc.min_len / (k + 1));
+  if (qs.min_len < idx[0].len_lo) {
+    idx[1].g = make_geom(qs.min_len / (k + 1));
     idx[1].len_lo = 0; idx[1].len_hi = idx[0].len_lo - 1;
     if (idx[1].g.q == idx[0].g.q) idx[0].len_lo = 0; else n_idx = 2;
   } else {
@@ -294,13 +336,17 @@ void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q
 
   stage_end(ctx, PCB_STAT_T_INDEX_NS);
   // ---- probe (re-run with a larger hit buffer if the first guess overflows)
-  const int key_shift = bits_for((uint64_t)(U - 1));
+  const int key_shift = bits_for((uint64_t)(U > 1 ? U - 1 : 1));
   unsigned long long cap = 8ull * (unsigned long long)(q_end - q_begin) + (1ull << 16);
   DevBuf<unsigned long long> counters(ctx, 4);
   DevBuf<uint64_t> hk0, hk1;
   DevBuf<uint32_t> hv0, hv1;
   unsigned long long h_counters[4];
-  const bool wide = bc.max_len > 32;
+  const bool wide = bc.max_len > 32 || qs.max_len > 32;
+  auto launch = [&](auto kernel, unsigned n_cta, const SeedIndex &ix) {
+    PCB_LAUNCH(ctx, kernel, n_cta, PROBE_WARPS * 32, 0, qs.planes.p, qs.len.p, bc.planes.p, bc.len.p, q_begin, q_end, ix.g,
+               ix.bin_off.p, ix.ent.p, hk0.p, hv0.p, cap, key_shift, counters.p, ix.len_lo, ix.len_hi);
+  };
   for (int attempt = 0;; attempt++) {
     hk0.alloc(ctx, cap); hv0.alloc(ctx, cap);
     PCB_CUDA(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
@@ -314,12 +360,10 @@ void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q
       unsigned need = grid_for((n_probe + 31) / 32, PROBE_WARPS);
       if (need < n_cta) n_cta = need;
       if (t > 0) PCB_CUDA(cudaMemsetAsync(counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
-      if (wide)
-        PCB_LAUNCH(ctx, probe_kernel<true>, n_cta, PROBE_WARPS * 32, 0, bc.planes.p, bc.len.p, q_begin, q_end, g,
-                   idx[t].bin_off.p, idx[t].ent.p, hk0.p, hv0.p, cap, key_shift, counters.p, idx[t].len_lo, idx[t].len_hi);
-      else
-        PCB_LAUNCH(ctx, probe_kernel<false>, n_cta, PROBE_WARPS * 32, 0, bc.planes.p, bc.len.p, q_begin, q_end, g,
-                   idx[t].bin_off.p, idx[t].ent.p, hk0.p, hv0.p, cap, key_shift, counters.p, idx[t].len_lo, idx[t].len_hi);
+      if (wide && self) launch(probe_kernel<true, true>, n_cta, idx[t]);
+      else if (wide) launch(probe_kernel<true, false>, n_cta, idx[t]);
+      else if (self) launch(probe_kernel<false, true>, n_cta, idx[t]);
+      else launch(probe_kernel<false, false>, n_cta, idx[t]);
     }
     PCB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     PCB_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));
@@ -339,7 +383,7 @@ void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q
 
   // ---- canonical order, duplicates removed
   hk1.alloc(ctx, n_hits); hv1.alloc(ctx, n_hits);
-  int where = radix_sort_pairs(ctx, hk0.p, hv0.p, hk1.p, hv1.p, n_hits, 2 * key_shift);
+  int where = radix_sort_pairs(ctx, hk0.p, hv0.p, hk1.p, hv1.p, n_hits, key_shift + bits_for((uint64_t)(qs.n > 1 ? qs.n - 1 : 1)));
   uint64_t *sk = where ? hk1.p : hk0.p;
   uint32_t *sv = where ? hv1.p : hv0.p;
   DevBuf<uint32_t> rank(ctx, n_hits + 1);
