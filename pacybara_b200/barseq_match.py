@@ -8,7 +8,7 @@
 `yogiseq` (where new.bc.matcher lives) is not part of the reference tree, so the matcher is restated from this call
 site and its comment: per read the library rows at the smallest distance <= errCutoff, that distance, their number.
 The distance is unit-cost Levenshtein, computed by the same bit-parallel kernel and seed index as the clustering
-path (pcb_match_barcodes).  Parity is pinned to the brute-force oracle (oracle/pcb_oracle.c:orc_match_brute), not to
+path (pcb_match_barcodes).  Parity is pinned to an exhaustive-DP checker in the test tree (orc_match_brute), not to
 yogiseq: "parity unpinned" in the sense of DESIGN.md section 2.
 
 Reads are matched once per distinct barcode (exact duplicates are bucketed on the GPU first).  A barcode that is

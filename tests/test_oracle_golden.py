@@ -69,3 +69,35 @@ def test_cfg1_full_size_digest():
     assert len(got) == case["n_rows"]
     assert [list(r) for r in got[:20]] == case["table_head"]
     assert canon.table_digest(got) == case["digest"]
+
+
+def test_oracle_matcher_against_plain_dp():
+    """f3 oracle (orc_match_brute) against a pure-Python Levenshtein on small random cases."""
+    import numpy as np
+    from oracle import orc
+    from pacybara_b200 import hostdata
+
+    def lev(a, b):
+        prev = list(range(len(b) + 1))
+        for i, ca in enumerate(a, 1):
+            cur = [i]
+            for j, cb in enumerate(b, 1):
+                cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+            prev = cur
+        return prev[-1]
+
+    rng = np.random.default_rng(5)
+    lib = ["".join(rng.choice(list("ACGT"), int(rng.integers(5, 9)))) for _ in range(60)]
+    lib[10] = lib[3]
+    qs = ["".join(rng.choice(list("ACGT"), int(rng.integers(5, 9)))) for _ in range(80)] + lib[:5]
+    lm, ll = hostdata.strings_to_matrix([s.encode() for s in lib])
+    qm, ql = hostdata.strings_to_matrix([s.encode() for s in qs])
+    for k in (0, 1, 3):
+        got = orc.match_barcodes(lm, ll, qm, ql, k)
+        for i, q in enumerate(qs):
+            ds = [lev(q, t) for t in lib]
+            ok = [d for d in ds if d <= k]
+            best = min(ok) if ok else -1
+            assert got["best_d"][i] == best
+            assert got["n_best"][i] == (sum(d == best for d in ds) if ok else 0)
+            assert got["first_hit"][i] == (ds.index(best) if ok else -1)
