@@ -281,7 +281,7 @@ def main():
     per_query = (kk + 1) * (2 * kk + 1)
     algo_bytes = U * per_query * 20 + pairs * 24 + E * 12
     roof_probe = dict(bound="hbm", achieved=algo_bytes / probe_s / 1e9, peak=hbm_peak, unit="GB/s",
-                      frac=algo_bytes / probe_s / 1e9 / hbm_peak, traffic=None, kernel="probe_kernel<false>",
+                      frac=algo_bytes / probe_s / 1e9 / hbm_peak, traffic=None, kernel="probe_kernel<false, true>",
                       note="integer-ALU bound kernel: the HBM fraction is small by construction, see roofline_alu")
     # the kernel that takes the largest share of the step: the per-component replay (merge.cu).  Algorithmic bytes
     # (DESIGN.md 4.4): per read 16 B of inputs (lexrank, barcode id, bucket, genotype offset) + 28 B of cluster state
