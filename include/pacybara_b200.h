@@ -224,7 +224,8 @@ int pcb_compact_shard(pcb_ctx *ctx, int mem_in, int mem_out, int32_t R, int64_t 
  * not vendored in the reference, so its matcher is restated from that call site -- per read: the library rows at the
  * smallest distance, that distance, and how many rows share it -- with the distance of this library (unit-cost
  * Levenshtein, the same Myers kernel and seed index as pcb_edit_pairs): parity unpinned, see DESIGN.md.
- *   library: lib_seq [L, lib_stride], lib_len [L];  queries: q_seq [Q, q_stride], q_len [Q]  (ACGT, 1..64 nt)
+ *   library: lib_seq [L, lib_stride], lib_len [L]  (ACGT, 1..64 nt);  queries: q_seq [Q, q_stride], q_len [Q]  (1..64
+ *   characters; any character outside ACGT, e.g. N, equals nothing and costs one edit like in a DP over the strings)
  *   best_d [Q]     smallest distance <= max_err to any library row, -1 if there is none
  *   n_best [Q]     library rows at that distance (duplicated library barcodes count once per row), 0 if none
  *   first_hit [Q]  the smallest such row, -1 if none

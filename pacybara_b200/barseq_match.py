@@ -11,10 +11,11 @@ The distance is unit-cost Levenshtein, computed by the same bit-parallel kernel 
 path (pcb_match_barcodes).  Parity is pinned to an exhaustive-DP checker in the test tree (orc_match_brute), not to
 yogiseq: "parity unpinned" in the sense of DESIGN.md section 2.
 
-Reads are matched once per distinct barcode (exact duplicates are bucketed on the GPU first).  A barcode that is
-missing (None / NA: failed extraction, :139-195) or that holds anything but 1..64 ACGT bases is reported unmatched
-and never reaches the GPU.  With a second read (paired-end) the read with the smaller distance decides; on equal
-distance the rows of both count.
+Reads are matched once per distinct barcode (exact duplicates are bucketed on the GPU first).  A read barcode may hold
+characters outside ACGT (N): such a character equals nothing and costs one edit, as in a DP over the strings.  A
+barcode that is missing (None / NA: failed extraction, :139-195), empty or longer than 64 is reported unmatched;
+library rows that are not 1..64 ACGT bases can never be hit.  With a second read (paired-end) the read with the
+smaller distance decides; on equal distance the rows of both count.
 """
 from __future__ import annotations
 
@@ -29,10 +30,13 @@ _OK = np.zeros(256, dtype=bool)
 _OK[[ord(c) for c in "ACGT"]] = True
 
 
+def _scorable(bc: Optional[str]) -> bool:
+    return isinstance(bc, str) and 1 <= len(bc) <= hostdata.MAX_BARCODE
+
+
 def _valid(bc: Optional[str]) -> bool:
-    if bc is None or not isinstance(bc, str) or not (1 <= len(bc) <= hostdata.MAX_BARCODE):
-        return False
-    return bool(_OK[np.frombuffer(bc.encode("latin-1", "replace"), dtype=np.uint8)].all())
+    """1..64 bases over ACGT (what a library row must be, and what the exact-duplicate bucketing takes)."""
+    return _scorable(bc) and bool(_OK[np.frombuffer(bc.encode("latin-1", "replace"), dtype=np.uint8)].all())
 
 
 class BcMatcher:
@@ -50,22 +54,33 @@ class BcMatcher:
     def match_arrays(self, barcodes: Sequence[Optional[str]]) -> Dict:
         """Per read: best distance (-1: none), number of rows at it, and the CSR list of those rows (0-based)."""
         n = len(barcodes)
-        ok = np.array([_valid(b) for b in barcodes], dtype=bool)
+        ok = np.array([_scorable(b) for b in barcodes], dtype=bool)
         best = np.full(n, -1, dtype=np.int32)
         nhits = np.zeros(n, dtype=np.int32)
         ptr = np.zeros(n + 1, dtype=np.int64)
         hits = np.zeros(0, dtype=np.int64)
         idx = np.nonzero(ok)[0]
         if idx.shape[0] and self.rows.shape[0]:
-            seq, length = hostdata.strings_to_matrix([barcodes[i].encode() for i in idx])
-            b = self.ctx.bucket(seq, None, length, want_qsum=False)            # one query per distinct barcode
-            u = self.ctx.match_barcodes(self.lib_seq, self.lib_len, b["bucket_seq"], b["bucket_len"], self.err_cutoff,
-                                        want_pairs=True)
+            enc = [barcodes[i].encode("latin-1", "replace") for i in idx]
+            seq, length = hostdata.strings_to_matrix(enc)
+            # one query per distinct barcode: plain ACGT barcodes are bucketed on the GPU, the few others go as they are
+            clean = _OK[seq].all(axis=1, where=np.arange(seq.shape[1])[None, :] < length[:, None])
+            ci, oi = np.nonzero(clean)[0], np.nonzero(~clean)[0]
+            bor = np.empty(idx.shape[0], dtype=np.int64)
+            n_u = 0
+            useq, ulen = seq[:0], length[:0]
+            if ci.shape[0]:
+                b = self.ctx.bucket(seq[ci], None, length[ci], want_qsum=False)
+                n_u, useq, ulen = b["n_buckets"], b["bucket_seq"], b["bucket_len"]
+                bor[ci] = b["bucket_of_read"]
+            bor[oi] = n_u + np.arange(oi.shape[0])
+            useq, ulen = np.concatenate([useq, seq[oi]]), np.concatenate([ulen, length[oi]])
+            n_u += oi.shape[0]
+            u = self.ctx.match_barcodes(self.lib_seq, self.lib_len, useq, ulen, self.err_cutoff, want_pairs=True)
             keep = u["pair_d"] == u["best_d"][u["pair_q"]]                     # the equidistant best rows
             pq, prow = u["pair_q"][keep], self.rows[u["pair_row"][keep]]
-            uptr = np.zeros(b["n_buckets"] + 1, dtype=np.int64)
-            np.cumsum(np.bincount(pq, minlength=b["n_buckets"]), out=uptr[1:])
-            bor = b["bucket_of_read"]
+            uptr = np.zeros(n_u + 1, dtype=np.int64)
+            np.cumsum(np.bincount(pq, minlength=n_u), out=uptr[1:])
             best[idx] = u["best_d"][bor]
             nhits[idx] = u["n_best"][bor]
             np.cumsum(nhits, out=ptr[1:])

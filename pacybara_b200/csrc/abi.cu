@@ -465,7 +465,7 @@ int pcb_match_barcodes(pcb_ctx *ctx, int mem, const uint8_t *lib_seq, const int3
     PackedBarcodes lib, qs;
     lib.n = 0; qs.n = 0;
     if (L) pack_barcodes(ctx, d_lseq.p, d_llen.p, nullptr, L, lib_stride, lib);
-    if (Q) pack_barcodes(ctx, d_qseq.p, d_qlen.p, nullptr, Q, q_stride, qs);
+    if (Q) pack_barcodes(ctx, d_qseq.p, d_qlen.p, nullptr, Q, q_stride, qs, true);       // N and friends: characters that match nothing
     match_barcodes_dev(ctx, lib, qs, max_err, o_best.p, o_n.p, o_first.p);
     if (n_pairs) *n_pairs = ctx->edges.n;
     o_best.commit(Q); o_n.commit(Q); o_first.commit(Q);

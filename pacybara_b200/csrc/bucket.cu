@@ -15,23 +15,25 @@ namespace pcb {
 // flags[0] = first offending row + 1 (0: none), flags[1] = min length, flags[2] = max length
 __global__ void pack_kernel(const uint8_t *__restrict__ seq, const int32_t *__restrict__ len,
                             const int32_t *__restrict__ rows, int32_t n, int32_t stride,
-                            ulonglong2 *__restrict__ planes, int32_t *__restrict__ out_len, int32_t *flags) {
+                            ulonglong2 *__restrict__ planes, int32_t *__restrict__ out_len, int32_t *flags,
+                            uint64_t *__restrict__ other) {
   int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   int32_t row = rows ? rows[i] : i;
   int32_t m = len[row];
   bool bad = m < 1 || m > 64 || m > stride;
-  uint64_t L = 0, H = 0;
+  uint64_t L = 0, H = 0, X = 0;
   if (!bad) {
     const uint8_t *s = seq + (size_t)row * stride;
     for (int32_t t = 0; t < m; t++) {
       uint32_t c = base_code(s[t]);
-      bad |= c > 3u;
+      if (c > 3u) { bad |= other == nullptr; X |= 1ull << t; c = 0u; }
       L |= (uint64_t)(c & 1u) << t;
       H |= (uint64_t)((c >> 1) & 1u) << t;
     }
   }
   planes[i] = make_ulonglong2(L, H);
+  if (other) other[i] = X;
   out_len[i] = m;
   if (bad) { atomicMin((uint32_t *)&flags[0], (uint32_t)i + 1u); return; }
   atomicMin(&flags[1], m);
@@ -39,20 +41,22 @@ __global__ void pack_kernel(const uint8_t *__restrict__ seq, const int32_t *__re
 }
 
 void pack_barcodes(pcb_ctx *ctx, const uint8_t *seq, const int32_t *len, const int32_t *rows, int32_t n,
-                   int32_t stride, PackedBarcodes &out) {
+                   int32_t stride, PackedBarcodes &out, bool allow_other) {
   out.planes.alloc(ctx, (size_t)n);
   out.len.alloc(ctx, (size_t)n);
+  if (allow_other) out.other.alloc(ctx, (size_t)n);
   out.n = n;
   DevBuf<int32_t> flags(ctx, 4);
   int32_t init[4] = {-1, 1 << 30, 0, 0};     // flags[0] as unsigned: 0xFFFFFFFF = none
   PCB_CUDA(cudaMemcpyAsync(flags.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-  if (n > 0) PCB_LAUNCH(ctx, pack_kernel, grid_for(n, 128), 128, 0, seq, len, rows, n, stride, out.planes.p, out.len.p, flags.p);
+  if (n > 0) PCB_LAUNCH(ctx, pack_kernel, grid_for(n, 128), 128, 0, seq, len, rows, n, stride, out.planes.p, out.len.p, flags.p,
+                        allow_other ? out.other.p : nullptr);
   int32_t h[4];
   PCB_CUDA(cudaMemcpyAsync(h, flags.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
   PCB_CUDA(cudaStreamSynchronize(ctx->stream));
   if (h[0] != -1)
     throw Error(PCB_E_INPUT, "barcode " + std::to_string((uint32_t)h[0] - 1u) +
-                                 " is not 1..64 bases over ACGT (no side path exists for such barcodes)");
+                                 (allow_other ? " is not 1..64 characters long" : " is not 1..64 bases over ACGT (no side path exists for such barcodes)"));
   out.min_len = n ? h[1] : 0;
   out.max_len = n ? h[2] : 0;
 }

@@ -142,11 +142,13 @@ inline int bits_for(uint64_t max_value) {
 struct PackedBarcodes {      // planes of n barcodes: x = plane L (bit 0 of each base), y = plane H
   DevBuf<ulonglong2> planes;
   DevBuf<int32_t> len;
+  DevBuf<uint64_t> other;    // optional: positions holding a character that is no base (f3 queries); planes are 0 there
   int32_t n = 0, min_len = 0, max_len = 0;
 };
 // ASCII rows (optionally gathered through `rows`) -> planes; throws PCB_E_INPUT on bad input
+// allow_other: characters outside ACGT are recorded in out.other instead of being refused
 void pack_barcodes(pcb_ctx *ctx, const uint8_t *seq, const int32_t *len, const int32_t *rows, int32_t n,
-                   int32_t stride, PackedBarcodes &out);
+                   int32_t stride, PackedBarcodes &out, bool allow_other = false);
 
 struct BucketOut {           // all device pointers, caller-owned
   int32_t *bucket_of_read, *bucket_ptr, *bucket_reads;

@@ -59,14 +59,14 @@ __global__ void seed_fill_kernel(const ulonglong2 *__restrict__ planes, const in
 // arithmetic shift gives the all-ones/all-zero mask, one add moves to the next column), and the
 // two carries-in are written as adds so that ptxas can place them on the FMA pipe (IMAD.IADD).
 // Same recurrence and same result as pcb::myers32 (myers.cuh), which the host tests pin to the DP.
-__device__ __forceinline__ int myers32_dev(uint32_t pL, uint32_t pH, int m, uint32_t tL, uint32_t tH, int n) {
+__device__ __forceinline__ int myers32_dev(uint32_t pL, uint32_t pH, int m, uint32_t tL, uint32_t tH, int n, uint32_t other = 0u) {
   uint32_t Pv = 0xFFFFFFFFu, Mv = 0u;
   uint32_t rl = __brev(tL), rh = __brev(tH);
 #pragma unroll 5
   for (int j = 0; j < n; j++) {
     uint32_t cl = (uint32_t)((int32_t)rl >> 31), ch = (uint32_t)((int32_t)rh >> 31);
     rl += rl; rh += rh;
-    uint32_t Eq = ~((pL ^ cl) | (pH ^ ch));
+    uint32_t Eq = ~((pL ^ cl) | (pH ^ ch)) & ~other;
     uint32_t Xv = Eq | Mv;
     uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
     uint32_t Ph = Mv | ~(Xh | Pv);
@@ -95,7 +95,7 @@ constexpr int PROBE_WARPS = 8;
 // and the hit key is (query, target) as it stands (f3: barcode -> library matching).
 template <bool WIDE, bool SELF>
 __device__ __forceinline__ void score_pair(const ulonglong2 *__restrict__ qplanes, const int32_t *__restrict__ qlen,
-                                           const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int2 pr,
+                                           const uint64_t *__restrict__ qother, const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int2 pr,
                                            int k, uint64_t *__restrict__ hit_key, uint32_t *__restrict__ hit_d,
                                            unsigned long long cap, int key_shift, unsigned long long *counters,
                                            unsigned long long &scored, unsigned long long &cells) {
@@ -104,8 +104,9 @@ __device__ __forceinline__ void score_pair(const ulonglong2 *__restrict__ qplane
   int32_t dl = m - n;
   if (dl > k || -dl > k) return;
   ulonglong2 a = qplanes[i], b = planes[j];
-  int d = WIDE ? myers64(a.x, a.y, m, b.x, b.y, n)
-               : myers32_dev((uint32_t)a.x, (uint32_t)a.y, m, (uint32_t)b.x, (uint32_t)b.y, n);
+  const uint64_t x = (!SELF && qother) ? qother[i] : 0ull;                // query characters that are no base never match
+  int d = WIDE ? myers64(a.x, a.y, m, b.x, b.y, n, x)
+               : myers32_dev((uint32_t)a.x, (uint32_t)a.y, m, (uint32_t)b.x, (uint32_t)b.y, n, (uint32_t)x);
   scored++; cells += (unsigned long long)(m * n);
   if (d <= k) {
     unsigned long long at = atomicAdd(&counters[0], 1ull);
@@ -119,6 +120,7 @@ __device__ __forceinline__ void score_pair(const ulonglong2 *__restrict__ qplane
 
 template <bool WIDE, bool SELF>
 __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(const ulonglong2 *__restrict__ qplanes, const int32_t *__restrict__ qlen,
+                                                                  const uint64_t *__restrict__ qother,
                                                                   const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len,
                                                                   int32_t q_begin, int32_t q_end, SeedGeom g,
                                                                   const uint32_t *__restrict__ bin_off, const int32_t *__restrict__ ent,
@@ -152,7 +154,9 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(const ulonglong
       if (p >= 0 && p < g.npos && m >= len_lo && m <= len_hi) {     // queries of other lengths use the other index
         ulonglong2 a = qplanes[qi];
         uint32_t bin = seed_bin(g, a.x, a.y, st, p);
-        lo = bin_off[bin]; hi = bin_off[bin + 1];
+        // a seed that holds a non-base cannot occur in a target; the error-free piece the pigeonhole promises has none
+        bool clean = SELF || !qother || g.q == 0 || ((qother[qi] >> st) & ((1ull << g.q) - 1ull)) == 0ull;
+        if (clean) { lo = bin_off[bin]; hi = bin_off[bin + 1]; }
       }
     }
     while (__any_sync(0xFFFFFFFFu, lo < hi)) {
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(const ulonglong
       cnt += __popc(mask);
       __syncwarp();
       if (cnt >= 32) {
-        score_pair<WIDE, SELF>(qplanes, qlen, planes, len, queue[warp][lane], g.k, hit_key, hit_d, cap, key_shift, counters, scored, cells);
+        score_pair<WIDE, SELF>(qplanes, qlen, qother, planes, len, queue[warp][lane], g.k, hit_key, hit_d, cap, key_shift, counters, scored, cells);
         int rest = cnt - 32;
         int2 carry = make_int2(0, 0);
         if (lane < rest) carry = queue[warp][32 + lane];
@@ -178,7 +182,7 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(const ulonglong
       }
     }
   }
-  if (lane < cnt) score_pair<WIDE, SELF>(qplanes, qlen, planes, len, queue[warp][lane], g.k, hit_key, hit_d, cap, key_shift, counters, scored, cells);
+  if (lane < cnt) score_pair<WIDE, SELF>(qplanes, qlen, qother, planes, len, queue[warp][lane], g.k, hit_key, hit_d, cap, key_shift, counters, scored, cells);
   for (int o = 16; o > 0; o >>= 1) {
     scored += __shfl_down_sync(0xFFFFFFFFu, scored, o);
     cells += __shfl_down_sync(0xFFFFFFFFu, cells, o);
@@ -344,7 +348,7 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
   unsigned long long h_counters[4];
   const bool wide = bc.max_len > 32 || qs.max_len > 32;
   auto launch = [&](auto kernel, unsigned n_cta, const SeedIndex &ix) {
-    PCB_LAUNCH(ctx, kernel, n_cta, PROBE_WARPS * 32, 0, qs.planes.p, qs.len.p, bc.planes.p, bc.len.p, q_begin, q_end, ix.g,
+    PCB_LAUNCH(ctx, kernel, n_cta, PROBE_WARPS * 32, 0, qs.planes.p, qs.len.p, (const uint64_t *)(self ? nullptr : qs.other.p), bc.planes.p, bc.len.p, q_begin, q_end, ix.g,
                ix.bin_off.p, ix.ent.p, hk0.p, hv0.p, cap, key_shift, counters.p, ix.len_lo, ix.len_hi);
   };
   for (int attempt = 0;; attempt++) {

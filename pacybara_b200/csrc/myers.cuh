@@ -69,12 +69,13 @@ PCB_HD int myers32(uint32_t pL, uint32_t pH, int m, uint32_t tL, uint32_t tH, in
 }
 
 // Same for barcodes of up to 64 nt.
-PCB_HD int myers64(uint64_t pL, uint64_t pH, int m, uint64_t tL, uint64_t tH, int n) {
+// `other`: pattern rows holding a character that equals no base (N, ...): they never match (f3 queries)
+PCB_HD int myers64(uint64_t pL, uint64_t pH, int m, uint64_t tL, uint64_t tH, int n, uint64_t other = 0ull) {
   uint64_t Pv = ~0ull, Mv = 0ull;
 #pragma unroll 1
   for (int j = 0; j < n; j++) {
     uint64_t cl = 0ull - ((tL >> j) & 1ull), ch = 0ull - ((tH >> j) & 1ull);
-    uint64_t Eq = ~((pL ^ cl) | (pH ^ ch));
+    uint64_t Eq = ~((pL ^ cl) | (pH ^ ch)) & ~other;
     uint64_t Xv = Eq | Mv;
     uint64_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
     uint64_t Ph = Mv | ~(Xh | Pv);

@@ -98,15 +98,34 @@ def test_bc_matcher_mirrors_the_call_site(ctx):
     reads = ["ACGTACGTACGTACGTACGTACGTA",       # exact: rows 1 and 5
              "ACGTACGTACGTACGTACGTACGTG",       # one substitution away from rows 1, 2, 5
              None,                              # failed extraction
-             "ACGTNCGTACGTACGTACGTACGTA",       # N: not scored
+             "ACGTNCGTACGTACGTACGTACGTA",       # N costs one edit: rows 1 and 5 at distance 1 (row 2 would be 2)
              "GGGGGGGGGGGGGGGGGGGGGGGGG",       # nothing within 2
              "TTTTTTTTTTTTTTTTTTTTTTTT",        # one deletion away from row 4
              "ACGTACGTACGTACGTACGTACGTA"]       # duplicate read
     r = m.find_matches(reads)
-    assert r["hits"] == [[1, 5], [1, 2, 5], [], [], [], [4], [1, 5]]
-    assert r["diffs"] == [0, 1, None, None, None, 1, 0]
-    assert r["nhits"] == [2, 3, 0, 0, 0, 1, 2]
+    assert r["hits"] == [[1, 5], [1, 2, 5], [], [1, 5], [], [4], [1, 5]]
+    assert r["diffs"] == [0, 1, None, 1, None, 1, 0]
+    assert r["nhits"] == [2, 3, 0, 2, 0, 1, 2]
     # paired reads: the closer read decides, equal distances pool their rows
     r2 = m.find_matches(reads, ["TTTTTTTTTTTTTTTTTTTTTTTTT", None, "ACGTACGTACGTACGTACGTACGTC", None, None, "TTTTTTTTTTTTTTTTTTTTTTTTT", None])
-    assert r2["hits"] == [[1, 4, 5], [1, 2, 5], [2], [], [], [4], [1, 5]]
-    assert r2["diffs"] == [0, 1, 0, None, None, 0, 0]
+    assert r2["hits"] == [[1, 4, 5], [1, 2, 5], [2], [1, 5], [], [4], [1, 5]]
+    assert r2["diffs"] == [0, 1, 0, 1, None, 0, 0]
+
+
+@pytest.mark.parametrize("bc_len,k", [(25, 2), (50, 3), (12, 1)])
+def test_match_queries_with_n(ctx, bc_len, k):
+    """Query characters outside ACGT equal nothing: same answer as the DP over the raw strings."""
+    from oracle import orc
+    lib, qs = make_case(300 + bc_len, 800, 3000, bc_len, 1)
+    rng = np.random.default_rng(2)
+    qs = ["".join(("N" if rng.random() < 0.04 else c) for c in q) for q in qs]
+    qs[0] = "N" * bc_len
+    assert sum("N" in q for q in qs) > 1000
+    lm, ll = hostdata.strings_to_matrix([s.encode() for s in lib])
+    qm, ql = hostdata.strings_to_matrix([s.encode() for s in qs])
+    got = ctx.match_barcodes(lm, ll, qm, ql, k)
+    ref = orc.match_barcodes(lm, ll, qm, ql, k)
+    for f in ("best_d", "n_best", "first_hit"):
+        assert np.array_equal(got[f], ref[f]), f
+    with pytest.raises(Exception):                       # the library itself must be plain ACGT
+        ctx.match_barcodes(qm, ql, qm, ql, k)
