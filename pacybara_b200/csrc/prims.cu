@@ -195,14 +195,61 @@ __global__ void __launch_bounds__(SORT_BLOCK) sort_hist(const uint64_t *__restri
   ghist[(size_t)threadIdx.x * nblocks + blockIdx.x] = t;
 }
 
+// The [digit][block] table needs no general scan: one block per digit turns its row into exclusive prefixes over the
+// tiles and leaves the digit's total; the scatter kernel adds the (256-entry) prefix over the digits itself.
+constexpr int ROWSCAN_BLOCK = 256;
+__global__ void __launch_bounds__(ROWSCAN_BLOCK) sort_rowscan(uint32_t *__restrict__ ghist, uint32_t nblocks,
+                                                              uint32_t *__restrict__ digit_total) {
+  __shared__ uint32_t warp_tot[ROWSCAN_BLOCK / 32];
+  uint32_t *row = ghist + (size_t)blockIdx.x * nblocks;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t running = 0;
+  for (uint32_t base = 0; base < nblocks; base += ROWSCAN_BLOCK) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = i < nblocks ? row[i] : 0u, inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < ROWSCAN_BLOCK / 32; w++) { uint32_t t = warp_tot[w]; if (w < warp) before += t; all += t; }
+    if (i < nblocks) row[i] = running + before + inc - v;
+    running += all;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) digit_total[blockIdx.x] = running;
+}
+
 template <int ROWS>
 __global__ void __launch_bounds__(SORT_BLOCK) sort_scatter(const uint64_t *__restrict__ keys, const uint32_t *__restrict__ vals,
                                                            uint64_t *__restrict__ okeys, uint32_t *__restrict__ ovals, size_t n,
-                                                           int shift, const uint32_t *__restrict__ goff, uint32_t nblocks) {
+                                                           int shift, const uint32_t *__restrict__ goff, uint32_t nblocks,
+                                                           const uint32_t *__restrict__ digit_total) {
   __shared__ uint32_t cnt[SORT_WARPS][256];
+  __shared__ uint32_t dig_warp[SORT_WARPS];
+  // exclusive prefix of the digit totals: thread d owns digit d (SORT_BLOCK == 256)
+  uint32_t dig_base;
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t v = digit_total[threadIdx.x], inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    if (lane == 31) dig_warp[warp] = inc;
+    __syncthreads();
+    uint32_t before = 0;
+    for (int w = 0; w < warp; w++) before += dig_warp[w];
+    dig_base = before + inc - v;
+  }
   sort_count_tile<ROWS>(keys, n, shift, cnt);
   {
-    uint32_t run = goff[(size_t)threadIdx.x * nblocks + blockIdx.x];
+    uint32_t run = dig_base + goff[(size_t)threadIdx.x * nblocks + blockIdx.x];
     for (int w = 0; w < SORT_WARPS; w++) { uint32_t c = cnt[w][threadIdx.x]; cnt[w][threadIdx.x] = run; run += c; }
   }
   __syncthreads();
@@ -228,14 +275,15 @@ template <int ROWS>
 static int radix_sort_rows(pcb_ctx *ctx, uint64_t *k0, uint32_t *v0, uint64_t *k1, uint32_t *v1, size_t n, int bits) {
   const size_t tile = (size_t)SORT_BLOCK * ROWS;
   uint32_t nblocks = (uint32_t)((n + tile - 1) / tile);
-  DevBuf<uint32_t> ghist(ctx, (size_t)256 * nblocks);
+  static_assert(SORT_BLOCK == 256, "one thread per digit");
+  DevBuf<uint32_t> ghist(ctx, (size_t)256 * nblocks), digit_total(ctx, 256);
   int cur = 0;
   for (int shift = 0; shift < bits; shift += 8) {
     uint64_t *ki = cur ? k1 : k0, *ko = cur ? k0 : k1;
     uint32_t *vi = cur ? v1 : v0, *vo = cur ? v0 : v1;
     PCB_LAUNCH(ctx, sort_hist<ROWS>, nblocks, SORT_BLOCK, 0, ki, n, shift, ghist.p, nblocks);
-    exclusive_scan_u32(ctx, ghist.p, ghist.p, (size_t)256 * nblocks);
-    PCB_LAUNCH(ctx, sort_scatter<ROWS>, nblocks, SORT_BLOCK, 0, ki, vi, ko, vo, n, shift, ghist.p, nblocks);
+    PCB_LAUNCH(ctx, sort_rowscan, 256, ROWSCAN_BLOCK, 0, ghist.p, nblocks, digit_total.p);
+    PCB_LAUNCH(ctx, sort_scatter<ROWS>, nblocks, SORT_BLOCK, 0, ki, vi, ko, vo, n, shift, ghist.p, nblocks, digit_total.p);
     cur ^= 1;
   }
   return cur;
