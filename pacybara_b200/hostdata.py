@@ -425,21 +425,37 @@ def rows_to_table(rows: ClusterRows, ids: Sequence[str], bc_names: Sequence[str]
                   on_alignment=None) -> List[Tuple[str, str, str, int, str]]:
     """(virtualBarcode, upBarcode, reads, size, geno) per row, as the reference writes them."""
     up_names = bc_names if up_names is None else up_names
+    # gather once, slice per row: the id and mutation strings in member / call order
+    member_ids = np.asarray(ids, dtype=object)[rows.row_members].tolist() if len(ids) else []
+    call_names = np.asarray(mut_names, dtype=object)[rows.call_mut].tolist() if len(mut_names) else []
+    row_ptr, call_ptr = rows.row_ptr.tolist(), rows.call_ptr.tolist()
+    row_bc, row_up = rows.row_bc.tolist(), rows.row_up.tolist()
     out = []
+    import gc
+    gc_was_on = gc.isenabled()
+    gc.disable()                 # millions of live strings: the cyclic collector would rescan them for every batch of rows
+    try:
+        _rows_to_table_loop(rows, out, row_ptr, call_ptr, row_bc, row_up, member_ids, call_names, bc_names, up_names, on_alignment)
+    finally:
+        if gc_was_on:
+            gc.enable()
+    return out
+
+
+def _rows_to_table_loop(rows, out, row_ptr, call_ptr, row_bc, row_up, member_ids, call_names, bc_names, up_names, on_alignment):
     for i in range(rows.n_rows):
-        mem = rows.row_members[rows.row_ptr[i]: rows.row_ptr[i + 1]]
-        calls = rows.call_mut[rows.call_ptr[i]: rows.call_ptr[i + 1]]
-        b, u = int(rows.row_bc[i]), int(rows.row_up[i])
+        lo, hi = row_ptr[i], row_ptr[i + 1]
+        b, u = row_bc[i], row_up[i]
         if b == NEEDS_ALIGNMENT or u == NEEDS_ALIGNMENT:
             if on_alignment is None:
                 raise RuntimeError("a cluster of >= 3 reads has tied barcode counts: the reference resolves "
                                    "this with an external `muscle` alignment (pacybara_cluster.py:484-511,530)")
-            b, u = on_alignment(i, mem, b, u)
+            b, u = on_alignment(i, rows.row_members[lo:hi], b, u)
         vbc = b if isinstance(b, str) else bc_names[b]
         ubc = u if isinstance(u, str) else ("None" if u < 0 else up_names[u])
-        geno = ";".join(mut_names[m] for m in calls) if len(calls) else "="
-        out.append((vbc, ubc, "|".join(ids[r] for r in mem), int(len(mem)), geno))
-    return out
+        clo, chi = call_ptr[i], call_ptr[i + 1]
+        geno = ";".join(call_names[clo:chi]) if chi > clo else "="
+        out.append((vbc, ubc, "|".join(member_ids[lo:hi]), hi - lo, geno))
 
 
 def gzip_members(data: bytes, chunk: int = 8 << 20, level: int = 6) -> List[bytes]:
