@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "_pcb.so")
+SO = os.environ.get("PCB_LIB") or os.path.join(HERE, "_pcb.so")     # PCB_LIB: a differently built library (experiments)
 
 PCB_OK, PCB_E_CUDA, PCB_E_INPUT, PCB_E_CAPACITY, PCB_E_STATE, PCB_E_UPTAG = range(6)
 MEM_HOST, MEM_DEVICE = 0, 1

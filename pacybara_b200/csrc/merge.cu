@@ -322,8 +322,14 @@ __global__ void __launch_bounds__(COMP_BLOCK) component_kernel_warp(MergeCtx c, 
   process_component_warp(c, st, comp, lane);        // one call site: the same code runs on either memory
 }
 
+// Block size of the thread kernels: warps of one block finish at very different times, and a block keeps its
+// registers until its slowest warp is done.
+#ifndef PCB_THREAD_BLOCK
+#define PCB_THREAD_BLOCK 128
+#endif
+constexpr int THREAD_BLOCK = PCB_THREAD_BLOCK;
 template <int PHASE>
-__global__ void __launch_bounds__(COMP_BLOCK) component_kernel_thread(MergeCtx c, int32_t comp_lo, int32_t n_comp, int32_t shard_rank,
+__global__ void __launch_bounds__(THREAD_BLOCK) component_kernel_thread(MergeCtx c, int32_t comp_lo, int32_t n_comp, int32_t shard_rank,
                                                                       int32_t shard_count, int32_t per_warp) {
   const int32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int32_t stride = 32 / per_warp;
@@ -553,9 +559,9 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
     if (const char *e = getenv("PCB_COMP_PER_WARP")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) per_warp = v; }
     size_t n_threads = ((size_t)(n_comp - n_warp) + per_warp - 1) / per_warp * 32;
     // three launches, one per phase: each kernel's code fits the instruction cache and its threads share a loop nest
-    PCB_LAUNCH(ctx, component_kernel_thread<1>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_warp, n_comp, 0, 1, per_warp);
-    PCB_LAUNCH(ctx, component_kernel_thread<2>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_warp, n_comp, 0, 1, per_warp);
-    PCB_LAUNCH(ctx, component_kernel_thread<3>, grid_for(n_threads, COMP_BLOCK), COMP_BLOCK, 0, c, n_warp, n_comp, 0, 1, per_warp);
+    PCB_LAUNCH(ctx, component_kernel_thread<1>, grid_for(n_threads, THREAD_BLOCK), THREAD_BLOCK, 0, c, n_warp, n_comp, 0, 1, per_warp);
+    PCB_LAUNCH(ctx, component_kernel_thread<2>, grid_for(n_threads, THREAD_BLOCK), THREAD_BLOCK, 0, c, n_warp, n_comp, 0, 1, per_warp);
+    PCB_LAUNCH(ctx, component_kernel_thread<3>, grid_for(n_threads, THREAD_BLOCK), THREAD_BLOCK, 0, c, n_warp, n_comp, 0, 1, per_warp);
   }
   stage_end(ctx, PCB_STAT_T_REPLAY_NS);
   if (Rm > 0)

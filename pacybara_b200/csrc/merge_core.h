@@ -218,6 +218,36 @@ PCB_HD void seed_bucket(const MergeCtx &c, const MergeState &st, int32_t b, Tabl
   if (n < 2) return;
   const int32_t *rids = c.bucket_reads ? c.bucket_reads + lo : nullptr;     // null: reads are numbered lo, lo+1, ...
 #define PCB_RID(i) (rids ? rids[i] : lo + (i))
+  // The usual bucket: every read carries the same calls (same mutations, same order, all Q > 0).  Then every
+  // mutation is kept (seen in n > 1 reads), every pair has Jaccard g/g, and the loop below would link (r1, r0),
+  // then (r2, r0), (r3, r0), ...: one cluster r1 -> r0 -> r2 -> ... -> r(n-1), created first in this bucket.
+  {
+    const int32_t r0 = PCB_RID(0);
+    const int32_t g0 = c.geno_ptr[r0], g = c.geno_ptr[r0 + 1] - g0;
+    bool uniform = true;
+    for (int32_t e = 0; e < g && uniform; e++) uniform = c.geno_q[g0 + e] > 0;
+    for (int32_t i = 1; i < n && uniform; i++) {
+      const int32_t ri = PCB_RID(i), gi = c.geno_ptr[ri];
+      uniform = c.geno_ptr[ri + 1] - gi == g;
+      for (int32_t e = 0; e < g && uniform; e++) uniform = c.geno_mut[gi + e] == c.geno_mut[g0 + e] && c.geno_q[gi + e] > 0;
+    }
+    if (uniform) {
+      if (!(g == 0 || (1.0 > c.prm.minJaccard && g >= c.prm.minMatches))) return;     // no pair of this bucket links
+      const int32_t r1 = PCB_RID(1), s = r1;
+      int32_t prev = r0;
+      st.rd_next[(r1) - st.r0] = r0;
+      st.rd_slot[(r0) - st.r0] = s; st.rd_slot[(r1) - st.r0] = s;
+      for (int32_t i = 2; i < n; i++) {
+        const int32_t ri = PCB_RID(i);
+        st.rd_next[(prev) - st.r0] = ri; st.rd_slot[(ri) - st.r0] = s;
+        prev = ri;
+      }
+      st.rd_next[(prev) - st.r0] = -1;
+      st.sl_parent[(s) - st.r0] = s; st.sl_head[(s) - st.r0] = r1; st.sl_tail[(s) - st.r0] = prev; st.sl_size[(s) - st.r0] = n;
+      st.sl_key[(s) - st.r0] = (int64_t)b << 32;
+      return;
+    }
+  }
   // varMatrix + filterSeqError (:338-356): per mutation #reads with Q>0 and sum of Q over the bucket
   for (int32_t i = 0; i < n; i++)
     for (int32_t e = c.geno_ptr[PCB_RID(i)]; e < c.geno_ptr[PCB_RID(i) + 1]; e++) {
