@@ -58,9 +58,21 @@ def read_all(paths: List[Optional[str]]) -> List[Optional[bytes]]:
     return out
 
 
+_decoded: Dict[int, tuple] = {}
+
+
+def _text(raw: bytes) -> str:
+    """ASCII text of a file's bytes, decoded once per buffer (the uptag file is often the barcode file itself)."""
+    hit = _decoded.get(id(raw))
+    if hit is None or hit[0] is not raw:
+        _decoded.clear()
+        hit = _decoded[id(raw)] = (raw, raw.decode("ascii"))
+    return hit[1]
+
+
 def _slices(raw: bytes, off: np.ndarray, length: np.ndarray) -> List[str]:
     import gc
-    txt = raw.decode("ascii")
+    txt = _text(raw)
     on = gc.isenabled()
     gc.disable()                 # a million fresh strings: keep the cyclic collector from rescanning them as the list grows
     try:
@@ -156,6 +168,7 @@ def arrays_from_bytes(ctx: Context, fastq: bytes, geno: bytes, uptag: Optional[b
     ra = pipeline.ReadArrays(seq=f["seq"], qual=f["qual"], length=f["length"], lexrank=lexrank, geno_ptr=g["geno_ptr"],
                              geno_mut=g["geno_mut"], geno_q=g["geno_q"], mut_rank=mut_rank, up_id=up_id)
     assert ra.n_reads == R
+    _decoded.clear()
     lap("mut_rank")
     return ra, dict(ids=ids, mut_names=mut_names, up_names=up_names)
 
