@@ -92,6 +92,7 @@ def fastq_from_bytes(ctx: Context, fastq: bytes) -> hostdata.FastqReads:
             raise NeedsLineParser(f"FASTQ records the tokenizer does not model: {rec['n_bad']}")
         f = fq.fastq_fetch(max(4, (rec["max_len"] + 3) // 4 * 4))
     ids = _slices(fastq, f["id_off"].cpu().numpy(), f["id_len"].cpu().numpy())
+    _decoded.clear()
     return hostdata.FastqReads(ids, f["seq"], f["qual"], f["length"])
 
 
