@@ -13,7 +13,8 @@
 //   * joins by read id go through an open-addressing table of 64-bit string hashes, every match verified
 //     byte by byte; "last record wins" is an atomicMax over line numbers;
 //   * mutation and uptag strings are interned the same way (first occurrence = representative), ids are
-//     dense in table order, and a verification pass proves that no two different strings share an id;
+//     dense in order of first occurrence (deterministic: every rank of a multi-GPU job numbers them alike), and a
+//     verification pass proves that no two different strings share an id;
 //   * the string order of the read ids is a stable LSD radix sort over big-endian 8-byte words.
 //
 // Anything the line passes do not model exactly (bytes >= 0x80 or NUL, a lone '\r', text before the first
@@ -247,12 +248,24 @@ __global__ void intern_flag_kernel(const unsigned long long *__restrict__ keys, 
   uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s < cap) flag[s] = keys[s] != 0ull;
 }
-__global__ void intern_reps_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ rep, uint64_t cap,
-                                   const uint32_t *__restrict__ id_of_slot, int64_t *__restrict__ rep_off, int32_t *__restrict__ rep_len) {
+// ids are dense in order of FIRST OCCURRENCE (the representative's offset): independent of which thread won which
+// slot, so every run -- and every rank of a multi-GPU job -- numbers the strings alike
+__global__ void intern_keys_kernel(const unsigned long long *__restrict__ keys, const unsigned long long *__restrict__ rep, uint64_t cap,
+                                   const uint32_t *__restrict__ at, uint64_t *__restrict__ skey, uint32_t *__restrict__ sval) {
   uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= cap || keys[s] == 0ull) return;
-  rep_off[id_of_slot[s]] = (int64_t)(rep[s] >> 16);
-  rep_len[id_of_slot[s]] = (int32_t)(rep[s] & 0xffff);
+  skey[at[s]] = rep[s] >> 16;
+  sval[at[s]] = (uint32_t)s;
+}
+__global__ void intern_reps_kernel(const uint64_t *__restrict__ skey, const uint32_t *__restrict__ sval, const unsigned long long *__restrict__ rep,
+                                   int32_t n_distinct, uint32_t *__restrict__ id_of_slot, int64_t *__restrict__ rep_off,
+                                   int32_t *__restrict__ rep_len) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_distinct) return;
+  uint32_t s = sval[i];
+  id_of_slot[s] = (uint32_t)i;
+  rep_off[i] = (int64_t)skey[i];
+  rep_len[i] = (int32_t)(rep[s] & 0xffff);
 }
 // slot -> dense id, and the proof that the string really is its representative
 __global__ void intern_remap_kernel(const uint8_t *__restrict__ t, const int64_t *__restrict__ off, const int32_t *__restrict__ len,
@@ -445,8 +458,8 @@ struct Interned {
   DevBuf<int32_t> rep_len;
 };
 // items (off, len; len < 0: none) -> ids in `ids_out` (-1: none), representatives, mismatch count added to *mismatch
-Interned intern_strings(pcb_ctx *ctx, const uint8_t *t, const int64_t *off, const int32_t *len, int64_t n, int32_t *ids_out,
-                        unsigned long long *mismatch) {
+Interned intern_strings(pcb_ctx *ctx, const uint8_t *t, int64_t text_bytes, const int64_t *off, const int32_t *len, int64_t n,
+                        int32_t *ids_out, unsigned long long *mismatch) {
   Interned out;
   uint64_t cap = table_capacity((size_t)n);
   DevBuf<unsigned long long> keys(ctx, cap), rep(ctx, cap);
@@ -460,7 +473,15 @@ Interned intern_strings(pcb_ctx *ctx, const uint8_t *t, const int64_t *off, cons
   out.n_distinct = (int32_t)read_scalar(ctx, id_of_slot.p + cap);
   out.rep_off.alloc(ctx, (size_t)out.n_distinct);
   out.rep_len.alloc(ctx, (size_t)out.n_distinct);
-  PCB_LAUNCH(ctx, intern_reps_kernel, grid_for(cap, 256), 256, 0, keys.p, rep.p, cap, id_of_slot.p, out.rep_off.p, out.rep_len.p);
+  if (out.n_distinct) {
+    const size_t M = (size_t)out.n_distinct;
+    DevBuf<uint64_t> k0(ctx, M), k1(ctx, M);
+    DevBuf<uint32_t> v0(ctx, M), v1(ctx, M);
+    PCB_LAUNCH(ctx, intern_keys_kernel, grid_for(cap, 256), 256, 0, keys.p, rep.p, cap, id_of_slot.p, k0.p, v0.p);
+    int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, M, bits_for((uint64_t)(text_bytes > 1 ? text_bytes - 1 : 1)));
+    PCB_LAUNCH(ctx, intern_reps_kernel, grid_for(M, 256), 256, 0, w ? k1.p : k0.p, w ? v1.p : v0.p, rep.p, out.n_distinct,
+               id_of_slot.p, out.rep_off.p, out.rep_len.p);
+  }
   if (n) PCB_LAUNCH(ctx, intern_remap_kernel, grid_for((size_t)n, 256), 256, 0, t, off, len, n, id_of_slot.p, out.rep_off.p,
                     out.rep_len.p, ids_out, mismatch);
   return out;
@@ -603,7 +624,7 @@ void geno_join_dev(pcb_ctx *ctx, pcb_text *g, const pcb_text *fq, const int64_t 
   DevBuf<int32_t> piece_len(ctx, (size_t)g->nnz);
   PCB_LAUNCH(ctx, geno_fill_kernel, grid_for((size_t)R + 1, 256), 256, 0, g->t, line_of_read.p, field_b.p, field_len.p, ptr.p, R,
              g->g_ptr.p, piece_off.p, piece_len.p, g->g_q.p);
-  Interned in = intern_strings(ctx, g->t, piece_off.p, piece_len.p, g->nnz, g->g_mut.p, counters.p + GC_MISMATCH);
+  Interned in = intern_strings(ctx, g->t, g->n, piece_off.p, piece_len.p, g->nnz, g->g_mut.p, counters.p + GC_MISMATCH);
   if (R) PCB_LAUNCH(ctx, geno_dup_kernel, grid_for((size_t)R, 256), 256, 0, g->g_ptr.p, g->g_mut.p, R, counters.p);
   g->n_distinct = in.n_distinct;
   g->rep_off = std::move(in.rep_off);
@@ -651,7 +672,7 @@ void uptag_join_dev(pcb_ctx *ctx, pcb_text *u, const pcb_text *fq, const int64_t
   if (u->n_lines) PCB_LAUNCH(ctx, uptag_line_kernel, grid_for((size_t)u->n_lines, 256), 256, 0, v, ids, line_of_read.p, counters.p);
   if (R) PCB_LAUNCH(ctx, uptag_items_kernel, grid_for((size_t)R, 256), 256, 0, v, line_of_read.p, R, off.p, len.p, counters.p);
   u->up_id.alloc(ctx, (size_t)R);
-  Interned in = intern_strings(ctx, u->t, off.p, len.p, R, u->up_id.p, counters.p + GC_MISMATCH);
+  Interned in = intern_strings(ctx, u->t, u->n, off.p, len.p, R, u->up_id.p, counters.p + GC_MISMATCH);
   u->n_distinct = in.n_distinct;
   u->rep_off = std::move(in.rep_off);
   u->rep_len = std::move(in.rep_len);

@@ -7,6 +7,13 @@ Does what precluster -> (bowtie2 + calcEdits) -> cluster do together (src/pacyba
 options as pacybara_cluster.py and the same output file, through a single pcb_cluster_reads call: nothing but the
 reads goes to the GPU and nothing but the cluster table comes back.  Intermediate files are not written; use the
 three drop-ins in bin/ when bcPreclust.fastq.gz / editDistance.csv.gz are wanted.
+
+Several GPUs of one box: launch it under torchrun, one process per GPU --
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 bin/pacybara_b200_cluster ...
+
+every rank tokenizes the files on its own GPU, the pair search is sharded by query bucket, the merge by connected
+component (pacybara_b200/multigpu.py), and rank 0 collects the ranks' rows and writes the one table.
 """
 from __future__ import annotations
 
@@ -29,23 +36,63 @@ def main(argv=None) -> int:
         print(__doc__)
         return 0
     bc_file, geno_file = o["ed"], o["geno"]
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    log = cluster_cli.log if rank == 0 else (lambda *a, **k: None)
     from .api import Context
-    ctx = Context(0)
     from . import ingest
-    ra, names = ingest.arrays_from_files(ctx, bc_file, geno_file, o["uptag"] or None, log=cluster_cli.log)
-    bad = [r for r in names["ids"] if "-" in r]
-    if bad:
-        cluster_cli.log(f"ERROR: read id {bad[0]!r} contains '-'", file=sys.stderr)
-        return 1
-    cluster_cli.log(f"Clustering {ra.n_reads} reads on the GPU...")
-    out = pipeline.cluster_reads(ctx, ra, max_diff=o["max_diff"], min_qual=o["min_qual"], min_jaccard=o["min_jaccard"],
-                                 min_matches=o["min_matches"], full_table=full)
-    table = pipeline.table_from_outputs(out, ra, names)
-    cluster_cli.log(f" - {out['n_buckets']} barcode groups, {out['n_edges']} barcode pairs, {len(table)} rows")
-    hostdata.write_clusters_csv(o["out"], table)
-    cluster_cli.log("Done!")
-    ctx.close()
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    ctx = Context(local)
+    try:
+        ra, names = ingest.arrays_from_files(ctx, bc_file, geno_file, o["uptag"] or None, log=log)
+        bad = [r for r in names["ids"] if "-" in r]
+        if bad:
+            log(f"ERROR: read id {bad[0]!r} contains '-'", file=sys.stderr)
+            return 1
+        params = dict(max_diff=o["max_diff"], min_qual=o["min_qual"], min_jaccard=o["min_jaccard"], min_matches=o["min_matches"])
+        if world == 1:
+            log(f"Clustering {ra.n_reads} reads on the GPU...")
+            out = pipeline.cluster_reads(ctx, ra, full_table=full, **params)
+        else:
+            log(f"Clustering {ra.n_reads} reads on {world} GPUs...")
+            out = _cluster_sharded(ctx, ra, params, rank, world, full)
+        if rank == 0:
+            table = pipeline.table_from_outputs(out, ra, names)
+            log(f" - {out['n_buckets']} barcode groups, {out['n_edges']} barcode pairs, {len(table)} rows")
+            hostdata.write_clusters_csv(o["out"], table)
+            log("Done!")
+    finally:
+        ctx.close()
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
     return 0
+
+
+def _cluster_sharded(ctx, ra, params, rank: int, world: int, full: bool):
+    """The sharded path; rank 0 gets the whole result as per-read host arrays, the others None."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from . import multigpu
+    dev = f"cuda:{ctx.device}"
+    arrs = {k: (v if hasattr(v, "data_ptr") else torch.from_numpy(np.ascontiguousarray(v)).to(dev))
+            for k, v in vars(ra).items() if v is not None}            # line-parser route: host arrays
+    part = multigpu.cluster_reads_sharded(ctx, arrs, params, rank, world, on_device=True, full_table=full, combine=False)
+    shard = ctx.compact_shard(part, to_host=True)                      # my reads and rows only
+    shard = {k: (np.array(v) if hasattr(v, "shape") else v) for k, v in shard.items()}
+    parts = [None] * world
+    dist.all_gather_object(parts, shard)
+    if rank != 0:
+        return None
+    out = hostdata.merge_outputs_from_shards(parts, ra.n_reads)
+    out.update(n_buckets=part["n_buckets"], n_edges=part["n_edges"])
+    return out
 
 
 if __name__ == "__main__":

@@ -163,3 +163,30 @@ def test_fused_cli(tmp_path, name, extra):
     assert r.returncode == 0, r.stderr[-2000:]
     got = canon.canon_table(canon.read_clusters_csv(out))
     assert got == util.golden_table(case)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["rand_dense_d2", "rand_d3_combo"])
+def test_fused_cli_two_gpus(tmp_path, name):
+    """The same command under torchrun on 2 GPUs: sharded pair search and merge, rank 0 writes the one table."""
+    import socket
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    case = util.load_golden(name)
+    ext = str(tmp_path / "extract")
+    _write_extract_dir(case, ext)
+    p = case["params"]
+    out = str(tmp_path / "clusters.csv.gz")
+    bc = "bcExtract_combo.fastq.gz" if name == "rand_d3_combo" else "bcExtract_1.fastq.gz"
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(BIN, "pacybara_b200_cluster"), "-u", os.path.join(ext, "bcExtract_1.fastq.gz"),
+           "-o", out, "-j", repr(p["min_jaccard"]), "-m", str(p["min_matches"]), "-d", str(p["max_diff"]), "-q", str(p["min_qual"]),
+           os.path.join(ext, bc), os.path.join(ext, "genoExtract.csv.gz")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    got = canon.canon_table(canon.read_clusters_csv(out))
+    assert got == util.golden_table(case)
