@@ -12,6 +12,13 @@
  *   pcb_merge         <- src/pacybara_cluster.py:385-477,515-537  (seed + main clustering,
  *                        consensus genotype / barcode)
  *   pcb_cluster_reads <- the three of them back to back, nothing leaving the device
+ *   pcb_compact_shard <- (multi-GPU) the part of a merge result one rank owns, compacted
+ * and, either side of the path:
+ *   pcb_tag_rows       <- src/pacybara_translate.R:58-68, src/pacybara_softfilter.R:46-63      (f1)
+ *   pcb_text_open, pcb_fastq_*, pcb_geno_*, pcb_uptag_*, pcb_rank_strings
+ *                      <- the line loops of src/pacybara_precluster.py:47-63 and
+ *                         src/pacybara_cluster.py:302-331, makePID's string order :152-157      (f2)
+ *   pcb_match_barcodes <- src/barseq_caller.R:57,242 (yogiseq::new.bc.matcher)                 (f3)
  *
  * Conventions
  *   - every function returns 0 on success or a PCB_E_* code; pcb_last_error() gives the text;
