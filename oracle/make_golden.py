@@ -164,7 +164,58 @@ RANDOM_CASES = [
 ]
 
 
+def textquirks_texts():
+    """A small library whose files are formatted the way real tools sometimes leave them: CRLF records, trailing
+    blanks, a quality string starting with '@', no newline at the end, unquoted and CRLF genotype lines, a third
+    column, records of reads that were never extracted, a read recorded twice (the later record counts) -- everything
+    the reference's line loops accept (src/pacybara_precluster.py:47-63, src/pacybara_cluster.py:302-331)."""
+    lib = synth.make_library(name="x_textquirks", n_clones=40, n_reads=320, p_err=0.03, p_near=0.4, seed=23)
+    ids, muts = lib.read_ids(), lib.mut_strings()
+    fq, ge, up = [], [], []
+    for i in range(lib.n_reads):
+        n = int(lib.length[i])
+        seq, qual = lib.seq[i, :n].tobytes().decode(), lib.qual[i, :n].tobytes().decode()
+        if i % 37 == 5:
+            qual = "@" + qual[1:]                                  # Phred 31 first: the reference drops this read
+        eol = "\r\n" if i % 5 == 0 else "\n"
+        pad = "  " if i % 7 == 0 else ""
+        fq.append(f"@{ids[i]} pos=17 len={n}{eol}{seq}{pad}{eol}+{eol}{qual}{eol}")
+        g = lib.geno_str(i, muts)
+        if i % 11 == 3:
+            ge.append(f"\"{ids[i]}\",\"999A>C:55\"\n")                  # an earlier record of the same read: overwritten below
+        quote = "" if i % 4 == 1 else "\""
+        tail = ",extra" if i % 9 == 2 else ""
+        ge.append(f"{quote}{ids[i]}{quote},{quote}{g}{quote}{tail}" + ("\r\n" if i % 6 == 0 else "\n"))
+        if i % 50 == 0:
+            ge.append(f"\"ghost/{i}/ccs\",\"5A>T:40\"\n")                  # a read that is not in the FASTQ
+        if i % 13 == 4:
+            up.append(f"@{ids[i]} pos=1 len={n}\n{'T' * n}\n+\n{'I' * n}\n")   # an earlier uptag record of this read
+        up.append(f"@{ids[i]} pos=17 len={n}{eol}{seq}{pad}{eol}+{eol}{'I' * n}{eol}")
+    fastq, uptag = "".join(fq), "".join(up)
+    return fastq[:-1] if fastq.endswith("\n") and not fastq.endswith("\r\n") else fastq, "".join(ge), uptag
+
+
+def add_textquirks():
+    """Adds tests/golden/x_textquirks.json.gz (and its INDEX entry) without touching the other fixtures."""
+    fastq, geno, uptag = textquirks_texts()
+    case = run_case("x_textquirks", fastq, geno, uptag, "canonical", _params({}), note="oracle.make_golden.textquirks_texts()")
+    assert case["exit_code"] == 0, case["stderr_tail"]
+    with gzip.GzipFile(os.path.join(GOLDEN_DIR, "x_textquirks.json.gz"), "wb", mtime=0) as fh:
+        fh.write(json.dumps(case, indent=0).encode())
+    ipath = os.path.join(GOLDEN_DIR, "INDEX.json")
+    with open(ipath) as fh:
+        index = [e for e in json.load(fh) if e["name"] != "x_textquirks"]
+    index.append(dict(name="x_textquirks", exit_code=case["exit_code"], n_rows=case["n_rows"], digest=case["digest"]))
+    with open(ipath, "w") as fh:
+        json.dump(index, fh, indent=1)
+    print(f"x_textquirks exit={case['exit_code']} rows={case['n_rows']}")
+
+
 def main():
+    if "--add-textquirks" in sys.argv:
+        if not ref_runner.available():
+            sys.exit("reference scripts not found")
+        return add_textquirks()
     if not ref_runner.available():
         sys.exit("reference scripts not found; golden vectors can only be generated in the build container")
     os.makedirs(GOLDEN_DIR, exist_ok=True)

@@ -170,3 +170,28 @@ def test_rank_strings_long_ids(ctx):
     with Text(ctx, raw) as t:
         rank = t.rank_strings(off, ln, int(ln.max()))
     assert np.array_equal(rank, hostdata.lexrank_of(ids))
+
+
+def test_quirky_files_against_the_reference_itself(ctx):
+    """tests/golden/x_textquirks: CRLF records, trailing blanks, an '@' quality, no final newline, unquoted / CRLF /
+    three-column genotype lines, ghost reads, reads recorded twice -- run through the UNMODIFIED reference
+    (oracle/make_golden.py --add-textquirks).  The tokenizers must take these files as they are (no line parser) and the
+    clusters must be the reference's table."""
+    from pacybara_b200 import canon, ingest
+    from tests import util
+    case = util.load_golden("x_textquirks")
+    ra, names = ingest.arrays_from_bytes(ctx, case["fastq"].encode(), case["geno"].encode(), case["uptag"].encode())
+    assert hasattr(ra.seq, "data_ptr")
+    reads = hostdata.parse_fastq_for_precluster(io.StringIO(case["fastq"]))
+    assert names["ids"] == reads.ids and len(reads.ids) < case["fastq"].count("\n+")        # the '@' qualities dropped reads
+    for full in (True, False):
+        out = pipeline.cluster_reads(ctx, ra, full_table=full, **case["params"])
+        got = canon.canon_table(pipeline.table_from_outputs(out, ra, names))
+        assert got == util.golden_table(case)
+    # and the bucketing text the reference printed, from the tokenizer's matrices
+    fq = ingest.fastq_from_bytes(ctx, case["fastq"].encode())
+    res = ctx.bucket(fq.seq, fq.qual, fq.length)
+    res = {k: (v.cpu().numpy() if hasattr(v, "data_ptr") else v) for k, v in res.items()}
+    buf = io.StringIO()
+    hostdata.write_preclust_fastq(buf, fq.ids, res["bucket_ptr"], res["bucket_reads"], res["bucket_seq"], res["bucket_len"], res["bucket_qsum"])
+    assert buf.getvalue() == case["preclust"]
