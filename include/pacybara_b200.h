@@ -4,7 +4,7 @@
  * The reference (rothlab/pacybara) has no FFI: its boundary for this path is three
  * processes connected by files.  Each entry point below replaces the
  * compute of one of those processes; the file parsing/writing stays in the host layer
- * (pacybara_b200/*.py), which binds this header with ctypes.
+ * (the Python modules of pacybara_b200), which binds this header with ctypes.
  *
  *   pcb_bucket        <- src/pacybara_precluster.py:28-39,68-76   (addRecord + output order)
  *   pcb_edit_pairs    <- src/pacybara.sh:448-468                  (seqret + bowtie2-build +

@@ -70,3 +70,46 @@ def test_product_code_never_touches_the_oracle():
                     if re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M) or "libpcb_oracle" in text or "pcb_oracle.c" in text:
                         offenders.append(os.path.relpath(path, ROOT))
     assert not offenders, offenders
+
+
+C_CALLER = r'''
+#include <stdio.h>
+#include <string.h>
+#include "pacybara_b200.h"
+/* a C (not C++) caller: the header must be plain C and the library must link without torch or the C++ runtime in sight */
+int main(void) {
+  pcb_ctx *ctx = NULL;
+  int rc;
+  if (pcb_abi_version() != PCB_ABI_VERSION) return 2;
+  rc = pcb_ctx_create(0, &ctx);
+  if (rc == PCB_OK) {                       /* a GPU is there: one tiny call through the boundary */
+    const uint8_t seq[8] = {'A','C','G','T','A','C','G','T'};
+    const int32_t len[2] = {4, 4};
+    int32_t bor[2], ptr[3], reads[2], U = 0;
+    rc = pcb_bucket(ctx, PCB_MEM_HOST, seq, NULL, len, 2, 4, bor, &U, ptr, reads, NULL);
+    printf("gpu: rc=%d buckets=%d\n", rc, (int)U);
+    pcb_ctx_destroy(ctx);
+    return (rc == PCB_OK && U == 1) ? 0 : 3;
+  }
+  printf("no gpu: rc=%d (%s)\n", rc, pcb_last_error(NULL));
+  return (rc == PCB_E_CUDA && strstr(pcb_last_error(NULL), "no CPU implementation")) ? 0 : 4;
+}
+'''
+
+
+def test_a_c_program_can_include_the_header_and_link_the_library(tmp_path):
+    """C99, -Wall -Wextra -pedantic -Werror on the header; without a GPU the library must say so, not compute."""
+    import shutil
+    import subprocess
+    from pacybara_b200 import _lib as L
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else shutil.which("gcc")
+    if cc is None or not os.path.exists(L.SO):
+        pytest.skip("no C compiler or library not built")
+    src = tmp_path / "caller.c"
+    src.write_text(C_CALLER)
+    exe = str(tmp_path / "caller")
+    so_dir = os.path.dirname(L.SO)
+    subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe,
+                    L.SO, f"-Wl,-rpath,{so_dir}"], check=True, capture_output=True, text=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
