@@ -1,0 +1,86 @@
+#!/usr/bin/env python3
+"""CPU fuzz: the replay the GPU threads execute (csrc/merge_core.h, compiled for the host by tests/host_emul) against the
+literal restatement of pacybara_cluster.py (oracle/pcb_oracle.c:orc_cluster) on many small random libraries with harsh
+parameters.  Not collected by pytest (it runs as long as you let it):
+
+    python tests/fuzz_replay_host.py [seconds] [first_seed]
+"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from oracle import orc  # noqa: E402
+from pacybara_b200 import hostdata, synth  # noqa: E402
+from tests import util  # noqa: E402
+
+
+def one(seed: int) -> str:
+    rng = np.random.default_rng(seed)
+    combo = bool(rng.random() < 0.2)
+    kw = dict(n_clones=int(rng.integers(3, 60)), n_reads=int(rng.integers(20, 500)), bc_len=int(rng.choice([8, 12, 25])),
+              p_err=float(rng.choice([0.0, 0.02, 0.06])), p_near=float(rng.choice([0.0, 0.3, 0.7])),
+              p_collide=float(rng.choice([0.0, 0.2, 0.5])), seed=seed, combo=combo,
+              id_style=str(rng.choice(["padded", "plain"])), skew=float(rng.choice([0.0, 1.0, 2.0])))
+    if rng.random() < 0.5:
+        kw.update(p_private=float(rng.choice([0.1, 0.5])), p_private_hq=float(rng.choice([0.0, 0.3])), p_dropout=float(rng.choice([0.0, 0.3])))
+    params = dict(max_diff=int(rng.integers(0, 4)), min_qual=int(rng.choice([1, 20, 32, 60])),
+                  min_jaccard=float(rng.choice([0.05, 0.2, 0.5, 1.0])), min_matches=int(rng.choice([1, 1, 2, 3])))
+    lib = synth.make_library(**kw)
+    ids = lib.read_ids()
+    reads = hostdata.FastqReads(ids, lib.seq, lib.qual, lib.length)
+    b = util.oracle_buckets(reads)
+    up_id = None
+    if combo:
+        ub = orc.precluster(lib.uptag_seq(), lib.qual, lib.uptag_len)
+        up_id = ub["bucket_of_read"].astype(np.int32)
+        if rng.random() < 0.3:
+            up_id[rng.integers(0, lib.n_reads, 2)] = -1              # reads without uptag record: KeyError if clustered
+    mut_names = lib.mut_strings()
+    from pacybara_b200.pipeline import mut_rank_of
+    prob = hostdata.MergeProblem(n_reads=lib.n_reads, n_buckets=b["n_buckets"], bucket_ptr=b["bucket_ptr"], bucket_reads=b["bucket_reads"],
+                                 lexrank=hostdata.lexrank_of(ids), bc_id=b["bucket_of_read"], up_id=up_id,
+                                 geno_ptr=lib.geno_ptr.astype(np.int32), geno_mut=lib.geno_mut.astype(np.int32),
+                                 geno_q=lib.geno_q.astype(np.int32), mut_rank=mut_rank_of(mut_names), **params)
+    ei, ej, ed = orc.edit_pairs(b["bucket_seq"], b["bucket_len"], 2 * params["max_diff"], method="brute")
+    q, r, d = hostdata.canonical_rows(ei, ej, ed)
+    if rng.random() < 0.3 and len(q):                                  # arbitrary row order / duplicates, like a foreign EDFILE
+        perm = rng.permutation(len(q))
+        q, r, d = q[perm], r[perm], d[perm]
+    try:
+        want = orc.cluster(prob, q, r, d)
+        want_err = None
+    except Exception as e:        # the reference's KeyError (read without uptag in a cluster)
+        want, want_err = None, type(e).__name__
+    pairs = hostdata.dedupe_ed_rows(q, r, d, prob.n_buckets, prob.max_diff)
+    out = util.emul_merge(prob, pairs)
+    if int(out["status"][0]) == 3 or want_err is not None:
+        return "" if (int(out["status"][0]) == 3) == (want_err is not None) else f"error behaviour differs: emul status {out['status'][:2]}, oracle {want_err}"
+    got = hostdata.rows_from_merge_outputs(out)
+    for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
+        if not np.array_equal(getattr(got, f), getattr(want, f)):
+            return f"{f} differs ({kw}, {params})"
+    return ""
+
+
+def main():
+    budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
+    seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+    t0, n, bad = time.time(), 0, []
+    while time.time() - t0 < budget:
+        msg = one(seed)
+        if msg:
+            bad.append((seed, msg))
+            print(f"seed {seed}: {msg}", flush=True)
+        seed += 1
+        n += 1
+    print(f"{n} libraries, {len(bad)} discrepancies, seeds {seed - n}..{seed - 1}")
+    return 1 if bad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
