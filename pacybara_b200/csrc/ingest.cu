@@ -115,6 +115,11 @@ __global__ void fastq_flag_kernel(TextView v, uint32_t *__restrict__ flag, unsig
   bool rec = L >= 3 && is_header(v, L - 3) && !is_header(v, L - 2) && !is_header(v, L - 1) && !is_header(v, L);
   flag[L] = rec ? 1u : 0u;
   if (L == 0 && !is_header(v, 0)) atomicAdd(exotic, 1ull);       // text before the first header: host parser
+  // the reference extracts the id of EVERY line that starts with '@' and raises if there is none (:52-57),
+  // whether or not a record follows
+  int64_t b, e;
+  span(v, L, b, e);
+  if (e > b && v.t[b] == '@' && (e - b == 1 || v.t[b + 1] == ' ')) atomicAdd(exotic, 1ull);
 }
 
 enum { META_MAX_LEN = 0, META_MAX_ID = 1, META_BAD = 2, META_COUNT = 4 };

@@ -64,6 +64,22 @@ def one(seed: int) -> str:
     for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
         if not np.array_equal(getattr(got, f), getattr(want, f)):
             return f"{f} differs ({kw}, {params})"
+    # on-demand distances: only the pairs a pass can visit are listed, the transitive rule scores the rest on the spot,
+    # and two shards put together are the whole (canonical row order only: that is what the fused call produces)
+    keep = ed <= params["max_diff"]
+    q2, r2, d2 = hostdata.canonical_rows(ei[keep], ej[keep], ed[keep])
+    qf, rf, df = hostdata.canonical_rows(ei, ej, ed)
+    full = hostdata.rows_from_merge_outputs(util.emul_merge(prob, hostdata.dedupe_ed_rows(qf, rf, df, prob.n_buckets, prob.max_diff)))
+    planes = util.pack_planes(b["bucket_seq"], b["bucket_len"])
+    pairs2 = hostdata.dedupe_ed_rows(q2, r2, d2, prob.n_buckets, prob.max_diff)
+    parts = [util.emul_merge(prob, pairs2, shard=(s, 2), planes=planes, blen=b["bucket_len"], compute_k=2 * params["max_diff"]) for s in range(2)]
+    if any(int(o["status"][0]) == 3 for o in parts):
+        return "on-demand run raised the uptag error where the full table did not"
+    merged = {k: np.maximum(parts[0][k], parts[1][k]) for k in [n for n, _ in hostdata.MERGE_OUTPUTS] + ["call_mut"]}
+    lazy = hostdata.rows_from_merge_outputs(merged)
+    for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
+        if not np.array_equal(getattr(lazy, f), getattr(full, f)):
+            return f"on-demand + 2 shards: {f} differs ({kw}, {params})"
     return ""
 
 

@@ -115,6 +115,7 @@ def test_synthetic_files(ctx, tmp_path, cfg, scale, style):
     ("quality shorter than sequence", FQ.replace("IIII#III", "IIII#II"), GE),
     ("header without id", FQ.replace("@r9 pos=17", "@ r9"), GE),
     ("duplicate read id", FQ.replace("@r9 pos=17", "@r10"), GE),
+    ("a lone '@' line after the last record", FQ + "\n@\n", GE),
     ("genotype without quality", FQ, GE.replace("A5C:12", "A5C")),
     ("quality not a number", FQ, GE.replace("A5C:12", "A5C:1e3")),
     ("line without comma", FQ, GE + "oops\n"),
