@@ -57,6 +57,31 @@ def ours(text: str):
         return None, type(e).__name__
 
 
+def mangle(rng, geno: str, uptag: str):
+    """Formatting the reference's loaders accept (src/pacybara_cluster.py:302-331): quotes or none, CRLF, extra columns,
+    records of unknown reads, a read recorded twice (the later one counts), trailing blanks; uptag records likewise."""
+    out = []
+    for line in geno.splitlines():
+        rid, g = [f.strip('"') for f in line.split(",")[:2]]
+        if rng.random() < 0.1:
+            out.append(f'"{rid}","77A>C:{int(rng.integers(1, 90))}"\n')            # overwritten by the real record below
+        q = '"' if rng.random() < 0.7 else ""
+        tail = ",x,y" if rng.random() < 0.1 else ""
+        pad = rng.choice(["", "", " ", "\t"])
+        out.append(f"{q}{rid}{q},{q}{g}{q}{tail}{pad}" + ("\r\n" if rng.random() < 0.2 else "\n"))
+        if rng.random() < 0.05:
+            out.append(f"ghost{int(rng.integers(99))},5A>T:40\n")
+    up = []
+    lines = uptag.split("\n")
+    for k in range(0, len(lines) - 3, 4):                       # lib_texts writes plain 4-line records
+        head, seq, _, qual = lines[k: k + 4]
+        if rng.random() < 0.1:
+            up.append(f"{head}\n{'A' * len(seq)}\n+\n{qual}\n")                    # an earlier record of the same read
+        eol = "\r\n" if rng.random() < 0.2 else "\n"
+        up.append(f"{head}{eol}{seq}{rng.choice(['', ' '])}{eol}+{eol}{qual}{eol}")
+    return "".join(out), "".join(up)
+
+
 def cluster_fuzz(budget: float, seed: int) -> int:
     """Random small libraries through the reference's precluster + cluster scripts and through the oracle."""
     from oracle import make_golden, orc
@@ -74,6 +99,8 @@ def cluster_fuzz(budget: float, seed: int) -> int:
                    m=int(rng.choice([1, 1, 2])))
         lib = synth.make_library(name=f"fuzz{seed}", **kw)
         fastq, geno, uptag = make_golden.lib_texts(lib)
+        if rng.random() < 0.6:
+            geno, uptag = mangle(rng, geno, uptag)
         case = make_golden.run_case(f"fuzz{seed}", fastq, geno, uptag, "canonical", make_golden._params(par))
         job = util.job_from_golden(case)
         rows = orc.cluster(job.problem, job.ed_q, job.ed_r, job.ed_d)
