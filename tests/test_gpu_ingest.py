@@ -196,3 +196,72 @@ def test_quirky_files_against_the_reference_itself(ctx):
     buf = io.StringIO()
     hostdata.write_preclust_fastq(buf, fq.ids, res["bucket_ptr"], res["bucket_reads"], res["bucket_seq"], res["bucket_len"], res["bucket_qsum"])
     assert buf.getvalue() == case["preclust"]
+
+
+def random_odd_texts(rng):
+    """A small FASTQ + genoExtract pair with the formatting accidents the loaders tolerate (and a few they do not)."""
+    n = int(rng.integers(1, 30))
+    pool = ["".join(rng.choice(list("ACGT"), int(rng.integers(1, 12)))) for _ in range(int(rng.integers(1, 5)))]
+    muts = [f"{int(rng.integers(1, 3000))}{a}>{b}" for a, b in zip(rng.choice(list("ACGT"), 6), rng.choice(list("ACGT"), 6))]
+    fq, ge = [], []
+    for i in range(n):
+        rid = f"m{int(rng.integers(100))}/{i}/ccs"
+        seq = pool[int(rng.integers(len(pool)))]
+        qual = "".join(chr(int(c)) for c in rng.integers(33, 127, len(seq)))
+        if rng.random() < 0.08:
+            qual = "@" + qual[1:]
+        eol = "\r\n" if rng.random() < 0.2 else "\n"
+        pad = str(rng.choice(["", "", " ", "\t", "  "]))
+        head = f"@{rid}" + str(rng.choice(["", " pos=17", " pos=NA len=3"] * 100 + ["\tx"]))     # a tab belongs to the id
+        rec = f"{head}{pad}{eol}{seq}{pad}{eol}+{eol}{qual}{eol}"
+        if rng.random() < 0.05:
+            rec += eol
+        if rng.random() < 0.02:
+            rec = rec.replace("+", "", 1)
+        fq.append(rec)
+        if rng.random() < 0.004:
+            continue                                          # a read without genotype record
+        k = int(rng.integers(0, 4))
+        g = ";".join(f"{m}:{int(rng.integers(0, 93))}" for m in rng.choice(muts, k, replace=False)) if k else "="
+        if rng.random() < 0.1:
+            ge.append(f'"{rid}","1A>C:7"\n')
+        q = '"' if rng.random() < 0.7 else ""
+        tail = ",x" if rng.random() < 0.1 else ""
+        ge.append(f"{q}{rid}{q},{q}{g}{q}{tail}" + str(rng.choice(["", " ", "\t"])) + ("\r\n" if rng.random() < 0.2 else "\n"))
+        if rng.random() < 0.05:
+            ge.append(f"ghost{i},5A>T:40\n")
+    fastq = "".join(fq)
+    if rng.random() < 0.3:
+        fastq = fastq.rstrip("\r\n")
+    return fastq, "".join(ge)
+
+
+def test_random_odd_texts_match_the_line_parser(ctx):
+    """Whatever the tokenizers accept they must read exactly as the line parser does (which oracle/fuzz_against_reference.py
+    pins to the reference); whatever they do not model they must decline, never guess."""
+    from pacybara_b200 import ingest
+    rng = np.random.default_rng(17)
+    taken = declined = failed_alike = 0
+    for _ in range(250):
+        fastq, geno = random_odd_texts(rng)
+        fb, gb = fastq.encode(), geno.encode()
+        wrap = lambda b: io.TextIOWrapper(io.BytesIO(b))
+        try:
+            ref, ref_err = host_view(*pipeline.arrays_from_text(wrap(fb), wrap(gb), wrap(fb), ctx)), None
+        except Exception as e:                                # noqa: BLE001
+            ref, ref_err = None, type(e)
+        try:
+            dev, dev_err = host_view(*ingest.arrays_from_bytes(ctx, fb, gb, fb)), None
+        except ingest.NeedsLineParser:
+            declined += 1
+            continue
+        except Exception as e:                                # noqa: BLE001
+            dev, dev_err = None, type(e)
+        if ref_err is not None or dev_err is not None:
+            assert ref_err is dev_err, (ref_err, dev_err, fastq, geno)
+            failed_alike += 1
+            continue
+        for k in ref:
+            assert dev[k] == ref[k], (k, fastq, geno)
+        taken += 1
+    assert taken > 100, (taken, declined, failed_alike)
