@@ -330,6 +330,16 @@ class Context:
         return res
 
 
+def open_context_or_exit(device: int = 0, **kw) -> Context:
+    """For the command-line programs: a Context, or one line on stderr and exit status 1 (there is no CPU path)."""
+    import sys
+    try:
+        return Context(device, **kw)
+    except _lib.PcbError as e:
+        print(f"ERROR: {e}", file=sys.stderr)
+        sys.exit(1)
+
+
 class Text:
     """The bytes of one text file on the device plus its newline index (pcb_text; f2 tokenizers).
 

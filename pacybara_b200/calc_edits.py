@@ -26,11 +26,11 @@ def main(argv=None) -> int:
     ap.add_argument("--maxErr", type=int, default=3, help="Maximum allowed number of errors in barcode")
     ap.add_argument("--chunkSize", type=int, default=1000, help="accepted for compatibility; unused")
     args = ap.parse_args(argv)
-    from .api import Context
+    from .api import open_context_or_exit
     with hostdata.open_text(args.preclustFASTQ) as fh:
         pc = hostdata.parse_preclust(fh)
     mat, lens = hostdata.strings_to_matrix([s.encode("ascii") for s in pc.seqs])
-    ctx = Context(0)
+    ctx = open_context_or_exit(0)
     ei, ej, ed = ctx.edit_pairs(mat, lens, args.maxErr) if pc.n_buckets > 1 else ([], [], [])
     import numpy as np
     ei, ej, ed = (np.asarray(x, dtype=np.int32) for x in (ei, ej, ed))

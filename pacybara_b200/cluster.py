@@ -52,13 +52,18 @@ class Die(Exception):
     pass
 
 
+_usage_text = None        # a caller with other positionals (fused_cli) shows its own usage
+
+
 def usage_and_die(err):
     log(err, file=sys.stderr)
-    print(USAGE)
+    print(USAGE if _usage_text is None else _usage_text)
     raise Die()
 
 
-def parse_args(argv):
+def parse_args(argv, usage=None):
+    global _usage_text
+    _usage_text = usage
     try:
         opts, args = getopt.getopt(argv, "u:j:m:d:q:o:",
                                    ["uptagBarcodeFile=", "minJaccard=", "minMatches=", "maxDiff=", "minQual=", "out=", "help"])
@@ -144,7 +149,7 @@ def main(argv=None) -> int:
     if o["help"]:
         print(USAGE)
         return 0
-    from .api import Context
+    from .api import open_context_or_exit
     log("Loading data...")
     with hostdata.open_text(o["ed"]) as ed, hostdata.open_text(o["geno"]) as ge, hostdata.open_text(o["preclust"]) as pc:
         up = hostdata.open_text(o["uptag"]) if o["uptag"] is not None else None
@@ -162,7 +167,7 @@ def main(argv=None) -> int:
     p = job.problem
     pairs = hostdata.dedupe_ed_rows(job.ed_q, job.ed_r, job.ed_d, p.n_buckets, p.max_diff)
     log(f"Clustering {p.n_reads} reads in {p.n_buckets} barcode groups, {len(pairs.q)} barcode pairs on the GPU...")
-    ctx = Context(0)
+    ctx = open_context_or_exit(0)
     out = ctx.merge(p, pairs)
     rows = hostdata.rows_from_merge_outputs(out)
     log(f" - {ctx.stat('components')} components, {ctx.stat('tests')} cluster tests, {ctx.stat('links')} links")

@@ -22,32 +22,36 @@ import sys
 from . import cluster as cluster_cli
 from . import hostdata, pipeline
 
+USAGE = ("Usage: pacybara_b200_cluster [-u|--uptagBarcodeFile <FASTQFILE>] [-j|--minJaccard <FLOAT>] [-m|--minMatches <INT>]\n"
+         "  [-d|--maxDiff <INT>] [-q|--minQual <INT>] [-o|--out <FILE>] [--full-table] [--help] <BARCODES.fastq.gz> <GENOEXTRACT.csv.gz>")
+
 
 def main(argv=None) -> int:
     argv = list(sys.argv[1:] if argv is None else argv)
-    full = "--full-table" in argv
-    argv = [a for a in argv if a != "--full-table"]
-    # same option parsing / validation as the drop-in; the first positional slot is unused here
-    try:
-        o = cluster_cli.parse_args(argv[:-2] + [argv[-2], argv[-1], argv[-2]] if len(argv) >= 2 else argv)
-    except cluster_cli.Die:
-        return 1
-    if o["help"]:
+    if "--help" in argv or "-h" in argv:
         print(__doc__)
         return 0
+    full = "--full-table" in argv
+    argv = [a for a in argv if a != "--full-table"]
+    # same option parsing / validation as the drop-in (its messages name the option at fault); the first
+    # positional slot is unused here
+    try:
+        o = cluster_cli.parse_args(argv[:-2] + [argv[-2], argv[-1], argv[-2]] if len(argv) >= 2 else argv, usage=USAGE)
+    except cluster_cli.Die:
+        return 1
     bc_file, geno_file = o["ed"], o["geno"]
     import os
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank, local = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     log = cluster_cli.log if rank == 0 else (lambda *a, **k: None)
-    from .api import Context
+    from .api import open_context_or_exit
     from . import ingest
     if world > 1:
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
-    ctx = Context(local)
+    ctx = open_context_or_exit(local)
     try:
         ra, names = ingest.arrays_from_files(ctx, bc_file, geno_file, o["uptag"] or None, log=log)
         bad = [r for r in names["ids"] if "-" in r]

@@ -16,10 +16,10 @@ from . import hostdata
 def main(argv=None) -> int:
     import io
     from . import ingest
-    from .api import Context
+    from .api import open_context_or_exit
     raw = sys.stdin.buffer.read()
     out = sys.stdout
-    ctx = Context(0)
+    ctx = open_context_or_exit(0)
     try:                                   # device tokenizer (csrc/ingest.cu) ...
         reads = ingest.fastq_from_bytes(ctx, raw)
     except ingest.NeedsLineParser:         # ... or, for anything it only counts, the reference's line loop

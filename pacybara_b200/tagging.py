@@ -42,9 +42,9 @@ def main(argv=None) -> int:
     if not (0.5 <= args.minRatio <= 1):
         print("minRatio must be between 0.5 and 1", file=sys.stderr)
         return 1
-    from .api import Context
+    from .api import open_context_or_exit
     rows = canon.read_clusters_csv(args.infile)
-    ctx = Context(0)
+    ctx = open_context_or_exit(0)
     tagged = tag_table(ctx, rows, args.minRatio)
     with gzip.open(args.out, "wt") as fh:
         fh.write("virtualBarcode,upBarcode,reads,size,geno,collision,upTagCollision,usable\n")
