@@ -145,3 +145,72 @@ def oracle_table_for_library(lib, ra, names, max_diff=2, min_qual=32, min_jaccar
     rows = orc.cluster(prob, q, r, d)
     bc_names = hostdata.matrix_to_strings(b["bucket_seq"], b["bucket_len"])
     return hostdata.rows_to_table(rows, names["ids"], bc_names, names["up_names"], names["mut_names"])
+
+
+# ---------------------------------------------------------------------------------------------
+# parity at sizes where the oracle's own pair search is out of reach (BASELINE cfg 2 / 4 / 5 at full size)
+
+def library_arrays(lib, ctx):
+    """Array inputs of Context.cluster_reads for a synth.Library without building R id strings
+    (padded ids sort like their index)."""
+    up_id = None
+    if lib.uptag_len is not None:
+        b = ctx.bucket(lib.uptag_seq(), None, lib.uptag_len, want_qsum=False)
+        up_id = b["bucket_of_read"].astype(np.int32)
+    R = lib.n_reads
+    return (lib.seq, None, lib.length.astype(np.int32), np.arange(R, dtype=np.int32), up_id, lib.geno_ptr.astype(np.int32),
+            lib.geno_mut, lib.geno_q, np.arange(len(lib.mut_codes), dtype=np.int32))
+
+
+def rows_equal(a, b, what=""):
+    for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), (what, f)
+
+
+def check_full_size_against_oracle_merge(ctx, lib, n_spot=20_000, seed=0):
+    """The GPU's full distance table (every pair <= 2*maxDiff) is (i) spot-checked pair by pair against the textbook DP,
+    edges and random non-edges alike, (ii) fed to the oracle's literal restatement of pacybara_cluster.py
+    (:385-455, :464-477, :515-537, :546-567), whose rows must equal the GPU's rows -- row order, member order, consensus
+    barcode, calls -- for BOTH the full-table run and the on-demand-distance run.  Returns a few counts."""
+    import ctypes as C
+    from oracle import orc
+    p = dict(max_diff=lib.params["max_diff"], min_qual=lib.params["min_qual"], min_jaccard=0.2, min_matches=1)
+    args = library_arrays(lib, ctx)
+    R = lib.n_reads
+    out_full = ctx.cluster_reads(*args, full_table=True, **p)
+    E = out_full["n_edges"]
+    ei, ej, ed = (np.empty(max(E, 1), dtype=np.int32) for _ in range(3))
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert ctx.lib.pcb_edit_pairs_fetch(ctx.h, 0, ptr(ei), ptr(ej), ptr(ed), E) == 0
+    ei, ej, ed = ei[:E], ej[:E], ed[:E]
+    bor = out_full["bucket_of_read"]
+    U = out_full["n_buckets"]
+    first = np.full(U, R, dtype=np.int64)
+    np.minimum.at(first, bor, np.arange(R))
+    bseq, blen = lib.seq[first], lib.length[first]
+    rng = np.random.default_rng(seed)
+    lev = lambda a, b: orc.lev(bseq[a, :blen[a]].tobytes(), bseq[b, :blen[b]].tobytes())
+    for k in rng.choice(E, size=min(E, n_spot), replace=False):
+        assert lev(ei[k], ej[k]) == ed[k], ("distance", int(ei[k]), int(ej[k]))
+    assert (ei < ej).all() and (ed >= 0).all() and (ed <= 2 * p["max_diff"]).all()
+    key = ei.astype(np.int64) * U + ej
+    assert (np.diff(key) > 0).all()                      # sorted by (i, j), no duplicate
+    ra_, rb_ = rng.integers(0, U, n_spot), rng.integers(0, U, n_spot)
+    probe = np.minimum(ra_, rb_).astype(np.int64) * U + np.maximum(ra_, rb_)
+    is_edge = key[np.clip(np.searchsorted(key, probe), 0, max(E - 1, 0))] == probe if E else np.zeros(n_spot, dtype=bool)
+    for a, b, e_ in zip(ra_, rb_, is_edge):
+        if a != b and not e_:
+            assert lev(a, b) > 2 * p["max_diff"], ("missing pair", int(a), int(b))
+    order = np.argsort(bor, kind="stable").astype(np.int32)
+    bptr = np.zeros(U + 1, dtype=np.int32)
+    np.cumsum(np.bincount(bor, minlength=U), out=bptr[1:])
+    q, r, d = hostdata.canonical_rows(ei, ej, ed)
+    prob = hostdata.MergeProblem(n_reads=R, n_buckets=U, bucket_ptr=bptr, bucket_reads=order, lexrank=args[3], bc_id=bor,
+                                 up_id=args[4], geno_ptr=args[5], geno_mut=args[6], geno_q=args[7], mut_rank=args[8], **p)
+    ref = orc.cluster(prob, q, r, d)
+    rows_equal(hostdata.rows_from_merge_outputs(out_full), ref, "full table")
+    out = ctx.cluster_reads(*args, **p)
+    rows_equal(hostdata.rows_from_merge_outputs(out), ref, "on-demand distances")
+    assert np.array_equal(np.sort(ref.row_members), np.arange(R))
+    return dict(reads=R, buckets=U, edges_full=int(E), edges_on_demand=int(out["n_edges"]), rows=ref.n_rows,
+                clusters=ref.n_clusters, links=ctx.stat("links"))
