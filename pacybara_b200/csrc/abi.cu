@@ -235,10 +235,13 @@ int pcb_bucket(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *qual, c
     OutArr<uint8_t> o_qsum(ctx, mem, bucket_qsum, cells);
     if (bucket_qsum && !qual) throw Error(PCB_E_INPUT, "quality sums requested without qualities");
     BucketOut bo{o_bor.p, o_ptr.p, o_reads.p, o_qsum.p};
+    stage_begin(ctx, PCB_STAT_T_BUCKET_NS, PCB_STAT_T_BUCKET_NS);
     int32_t U = bucket_reads_dev(ctx, d_seq.p, d_qual.p, d_len.p, R, stride, bo, nullptr);
+    stage_end(ctx, PCB_STAT_T_BUCKET_NS);
     if (n_buckets) *n_buckets = U;
     o_bor.commit(R); o_ptr.commit((size_t)U + 1); o_reads.commit(R); o_qsum.commit((size_t)U * stride);
     PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    stage_collect(ctx);
   });
 }
 
@@ -250,9 +253,11 @@ int pcb_edit_pairs(pcb_ctx *ctx, int mem, const uint8_t *seq, const int32_t *len
     InArr<int32_t> d_len(ctx, mem, len, U);
     PackedBarcodes bc;
     pack_barcodes(ctx, d_seq.p, d_len.p, nullptr, U, stride, bc);
+    stage_begin(ctx, PCB_STAT_T_INDEX_NS, PCB_STAT_T_HITS_NS);
     edit_pairs_dev(ctx, bc, k, q_begin, q_end);
     if (n_edges) *n_edges = ctx->edges.n;
     PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    stage_collect(ctx);
   });
 }
 
@@ -319,7 +324,9 @@ int pcb_merge(pcb_ctx *ctx, int mem, int32_t R, int32_t U, const int32_t *bucket
       pack_barcodes(ctx, d_bseq.p, d_blen.p, nullptr, U, stride, bc);
       in.planes = bc.planes.p; in.blen = bc.len.p; in.compute_k = on_demand_k; in.wide = bc.max_len > 32;
     }
+    stage_begin(ctx, PCB_STAT_T_PREP_NS, PCB_STAT_T_SCATTER_NS);
     merge_dev(ctx, in, out);
+    stage_collect(ctx);
     o_root.commit(R); o_pos.commit(R); o_size.commit(R); o_bc.commit(R); o_up.commit(R); o_calln.commit(R);
     o_call.commit(nnz); o_key.commit(R); o_calloff.commit(R);
     PCB_CUDA(cudaStreamSynchronize(ctx->stream));

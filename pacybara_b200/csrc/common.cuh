@@ -95,9 +95,9 @@ inline unsigned grid_for(size_t n, unsigned block) {
 
 // Stage timing: stage_begin() once, stage_end(stat) after each stage; stage_collect() after the stream
 // has drained turns the event intervals into stats[stat] (ns).
-inline void stage_begin(pcb_ctx *ctx) {
+inline void stage_begin(pcb_ctx *ctx, int first = PCB_STAT_T_BUCKET_NS, int last = PCB_STAT_T_SCATTER_NS) {
   ctx->n_marks = 0;
-  for (int s = PCB_STAT_T_BUCKET_NS; s <= PCB_STAT_T_SCATTER_NS; s++) ctx->stats[s] = 0;
+  for (int s = first; s <= last; s++) ctx->stats[s] = 0;      // the stages this call is going to time
   if (ctx->stage_ev[0]) { cudaEventRecord(ctx->stage_ev[0], ctx->stream); ctx->n_marks = 1; }
 }
 inline void stage_end(pcb_ctx *ctx, int stat) {

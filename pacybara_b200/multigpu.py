@@ -112,21 +112,41 @@ def cluster_reads_sharded(ctx: Context, arrs: Dict, params: Dict, rank: int, wor
     import torch
     import torch.distributed as dist
     dev = f"cuda:{ctx.device}"
-    a = arrs if on_device else upload_sharded(arrs, rank, world, dev)
+    stage_ms: Dict[str, float] = {}
+
+    def lib_stages(*names):
+        for n in names:                                   # device time of the library's own stages (CUDA events on its stream)
+            stage_ms[n] = stage_ms.get(n, 0.0) + ctx.stat(("t_" if n != "probe" else "") + n + "_ns") * 1e-6
+
+    def torch_stage(name, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = fn()
+        e1.record()
+        e1.synchronize()
+        stage_ms[name] = stage_ms.get(name, 0.0) + e0.elapsed_time(e1)
+        return res
+
+    a = arrs if on_device else torch_stage("upload_allgather", lambda: upload_sharded(arrs, rank, world, dev))
     max_diff = int(params["max_diff"])
     R = int(a["length"].shape[0])
     # 1. buckets (replicated)
     b = ctx.bucket(a["seq"], None, a["length"], want_qsum=False)      # qualities are not needed for clustering
+    lib_stages("bucket")
     U = b["n_buckets"]
     # 2. my slice of the query buckets
     lo, hi = shard_range(U, rank, world)
     bseq, blen = b["bucket_seq"].contiguous(), b["bucket_len"].contiguous()
     ei, ej, ed = ctx.edit_pairs(bseq, blen, (2 if full_table else 1) * max_diff, q_range=(lo, hi))
+    lib_stages("index", "probe", "hits")
     local_stats = dict(pairs_scored=ctx.stat("pairs_scored"), cells=ctx.stat("cells"), probe_ns=ctx.stat("probe_ns"))
     # 3. exchange edges
-    ei, ej, ed = gather_edges(ei, ej, ed, world)
-    ctx.sort_edges(ei, ej, ed, U)
-    ped = torch.where((ed >= 1) & (ed <= max_diff), ed, torch.zeros_like(ed))
+    ei, ej, ed = torch_stage("edge_allgather", lambda: gather_edges(ei, ej, ed, world))
+
+    def order_edges():
+        ctx.sort_edges(ei, ej, ed, U)
+        return torch.where((ed >= 1) & (ed <= max_diff), ed, torch.zeros_like(ed))
+    ped = torch_stage("edge_sort", order_edges)
     # 4. my components
     prob = MergeProblem(n_reads=R, n_buckets=U, bucket_ptr=b["bucket_ptr"].contiguous(), bucket_reads=b["bucket_reads"].contiguous(),
                         lexrank=a["lexrank"], bc_id=b["bucket_of_read"].contiguous(), up_id=a.get("up_id"), geno_ptr=a["geno_ptr"],
@@ -138,16 +158,18 @@ def cluster_reads_sharded(ctx: Context, arrs: Dict, params: Dict, rank: int, wor
     else:
         out = ctx.merge(prob, PairList(ei, ej, ed, ped), shard=(rank, world), bucket_seq=bseq, bucket_len=blen,
                         on_demand_k=2 * max_diff)
+    lib_stages("prep", "replay", "scatter")
+    local_stats.update(links=ctx.stat("links"), tests=ctx.stat("tests"), components=ctx.stat("components"))
     # 5. result
     if combine:
         for name in list(out.keys()):
             dist.all_reduce(out[name], op=dist.ReduceOp.MAX)
         torch.cuda.current_stream(ctx.device).synchronize()
-    extra = dict(bucket_of_read=b["bucket_of_read"], n_buckets=U, n_edges=int(ei.numel()), local_stats=local_stats)
+    extra = dict(bucket_of_read=b["bucket_of_read"], n_buckets=U, n_edges=int(ei.numel()), local_stats=local_stats, stage_ms=stage_ms)
     if not on_device and not combine:
         # bucket ids travel for my reads only (row_bc names buckets; the barcode of a bucket is that of any of its reads)
         shard = ctx.compact_shard(dict(out, bucket_of_read=b["bucket_of_read"]), to_host=True)
-        shard.update(n_buckets=U, n_edges=extra["n_edges"], local_stats=local_stats)
+        shard.update(n_buckets=U, n_edges=extra["n_edges"], local_stats=local_stats, stage_ms=stage_ms)
         return shard
     out.update(extra)
     if not on_device:

@@ -97,8 +97,7 @@ int main(void) {
 '''
 
 
-def test_a_c_program_can_include_the_header_and_link_the_library(tmp_path):
-    """C99, -Wall -Wextra -pedantic -Werror on the header; without a GPU the library must say so, not compute."""
+def _run_c_caller(tmp_path):
     import shutil
     import subprocess
     from pacybara_b200 import _lib as L
@@ -111,5 +110,17 @@ def test_a_c_program_can_include_the_header_and_link_the_library(tmp_path):
     so_dir = os.path.dirname(L.SO)
     subprocess.run([cc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe,
                     L.SO, f"-Wl,-rpath,{so_dir}"], check=True, capture_output=True, text=True)
-    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    return subprocess.run([exe], capture_output=True, text=True, timeout=120)
+
+
+def test_a_c_program_can_include_the_header_and_link_the_library(tmp_path):
+    """C99, -Wall -Wextra -pedantic -Werror on the header; without a GPU the library must say so, not compute."""
+    r = _run_c_caller(tmp_path)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.gpu
+def test_the_c_program_computes_on_the_gpu(tmp_path):
+    """The same plain-C caller on the GPU box: its pcb_bucket call must go through (the driver's -m gpu run sees this)."""
+    r = _run_c_caller(tmp_path)
+    assert r.returncode == 0 and r.stdout.startswith("gpu: rc=0 buckets=1"), r.stdout + r.stderr
