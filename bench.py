@@ -49,7 +49,7 @@ def parse_args():
     ap.add_argument("--config", default=os.environ.get("PCB_BENCH_CONFIG", "cfg2"))
     ap.add_argument("--scale", type=float, default=float(os.environ.get("PCB_BENCH_SCALE", "1.0")))
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--cpu-sample-reads", type=int, default=400_000,
+    ap.add_argument("--cpu-sample-reads", type=int, default=600_000,
                     help="reads of the bounded sample the cpu_baseline leg of the default run clusters on the host cores")
     ap.add_argument("--cpu-budget-s", type=float, default=float(os.environ.get("PCB_CPU_BUDGET_S", "240")),
                     help="--impl reference: wall-clock budget for the timed full-size passes (at least one pass is always timed)")

@@ -1,0 +1,342 @@
+// merge_small.cuh -- the per-component replay for components of at most 32 reads: ONE WARP per component,
+// one LANE per read, the whole cluster state in registers.
+//
+// Same algorithm, same visiting order and the same rows as process_component() in merge_core.h (seed step
+// src/pacybara_cluster.py:385-400, main loop :408-455, consensus :464-477,:515-537), reformulated so that the
+// lanes of a warp do data-parallel work instead of one lane chasing pointers:
+//
+//   cluster state    per read (= lane): cid (row of its cluster, -1 = in no cluster), pos (place in the member
+//                    list), key (creation key of the surviving cluster id).  "Relabel every member and append
+//                    its list" (:193-202) is one predicated update: lanes of c2 add size(c1) to pos and take
+//                    c1's cid and key.  Sizes and member sets are ballots.
+//   genotype sums    a dense matrix in shared memory: row = cluster (or lone read), column = one of the <= 32
+//                    distinct mutations of the component, LANE m OWNS COLUMN m.  cell = (sum of Q, #reads with
+//                    Q > 0, #reads naming the mutation).  A merge adds two rows; the genotype rule (:447-452) is
+//                    two row reads, one filterSeqError test per lane and two ballots -- no hash table, no
+//                    accumulate-per-test.  After the fill pass a lane only ever touches its own column, so no
+//                    further synchronisation is needed.
+//   seed step        per bucket: the bucket-wide filter (:350-356) is a column sum; presence masks of the reads
+//                    come out of the same loop (one ballot per read); row i of the pair loop (:391-400) is ONE
+//                    parallel Jaccard test of read i against every j < i (its verdict depends on the filter and
+//                    the two reads only, not on link order), then addLink is replayed over the set bits.
+//   main loop        a row's read pairs (x, y) are screened 32 at a time (same cluster / already failed since the
+//                    last merge), the first live one is visited, then the rest are screened again.
+//   transitive rule  the buckets within 2e of each bucket of the component as bit masks (one lookup per bucket
+//                    pair, spread over the lanes, on-demand Myers included); the rule (:442) is then
+//                    "no bucket of cluster 1 has a bucket of cluster 2 outside its mask".
+//   consensus        vote per column from the cluster's row; order of the calls by counting smaller ranks;
+//                    barcode majority with match_any.
+//
+// Eligibility: <= 32 reads, <= 32 distinct mutations, |Q| <= 2^24.  Anything else returns 1 before a single
+// output is written and is replayed by the generic kernel (merge_warp.cuh).
+// Written against simt.h so that tests/host_emul runs this very source on the CPU (unit tests only).
+#pragma once
+#include "merge_core.h"
+#include "simt.h"
+
+namespace pcb {
+
+constexpr int SMALL_READS = 32;     // one lane per read
+constexpr int SMALL_MUTS = 32;      // one matrix column per lane
+constexpr int SMALL_STRIDE = 33;    // row stride: conflict-free along a row (lane = column) and down a column (lane = row)
+constexpr int SMALL_TAB = 64;       // open-addressing table that numbers the component's mutations
+
+struct SmallSmem {
+  int32_t sum[SMALL_READS * SMALL_STRIDE];    // sum of Q
+  uint16_t cnt[SMALL_READS * SMALL_STRIDE];   // low byte: #reads with Q > 0; high byte: #reads naming the mutation
+  int32_t tab[SMALL_TAB];                     // mutation id + 1, 0 = empty
+  int32_t colmut[SMALL_MUTS];                 // column -> mutation id
+  uint32_t near[3][32];                       // near[e-1][a]: buckets b of the component with dist(a, b) <= 2e
+};
+
+SIMT_FN uint32_t small_hash(int32_t mut) { return ((uint32_t)mut * 0x9E3779B1u) >> 26; }      // 6 bits
+
+// Returns 0 when the component was replayed, 1 when it is not eligible (nothing written).
+SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, SmallSmem *sm) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t lt = (1u << lane) - 1u;
+  const int32_t b_lo = c.comp_ptr[comp], b_hi = c.comp_ptr[comp + 1];
+  const int32_t r_lo = c.bucket_ptr[b_lo], r_hi = c.bucket_ptr[b_hi];
+  const int32_t n = r_hi - r_lo, B = b_hi - b_lo;
+  if (n > SMALL_READS) return 1;
+  const bool has = lane < n;
+  const int32_t r = r_lo + lane;
+  const int32_t minQual = c.prm.minQual, minMatches = c.prm.minMatches;
+  const double minJaccard = c.prm.minJaccard;
+  int32_t lex = 0, bc = 0, up = 0, bkt = 0, g0 = 0, g1 = 0;
+  if (has) {
+    lex = c.lexrank[r]; bc = c.bc_id[r]; up = c.up_id ? c.up_id[r] : 0;
+    bkt = c.bucket_of_read[r] - b_lo; g0 = c.geno_ptr[r]; g1 = c.geno_ptr[r + 1];
+  }
+
+  // ---- number the mutations of the component (column = rank of the table slot), fill the matrix
+  for (int32_t i = lane; i < n * SMALL_STRIDE; i += 32) { sm->sum[i] = 0; sm->cnt[i] = 0; }
+  sm->tab[lane] = 0; sm->tab[lane + 32] = 0;
+  simt::sync(FULL);
+  bool bad = false;
+  for (int32_t e = g0; e < g1; e++) {
+    const int32_t mut = c.geno_mut[e], q = c.geno_q[e];
+    if (q > (1 << 24) || q < -(1 << 24)) bad = true;
+    uint32_t h = small_hash(mut);
+    for (int probes = 0;; probes++) {
+      if (probes == SMALL_TAB) { bad = true; break; }
+      const int32_t old = simt::atomic_cas(&sm->tab[h], 0, mut + 1);
+      if (old == 0 || old == mut + 1) break;
+      h = (h + 1) & (SMALL_TAB - 1);
+    }
+  }
+  simt::sync(FULL);
+  const uint32_t occ_lo = simt::ballot(FULL, sm->tab[lane] != 0), occ_hi = simt::ballot(FULL, sm->tab[lane + 32] != 0);
+  const int32_t n_lo = simt::popc(occ_lo), M = n_lo + simt::popc(occ_hi);
+  if (simt::ballot(FULL, bad) != 0u || M > SMALL_MUTS) return 1;
+  {
+    const int32_t t0 = sm->tab[lane], t1 = sm->tab[lane + 32];
+    if (t0) sm->colmut[simt::popc(occ_lo & lt)] = t0 - 1;
+    if (t1) sm->colmut[n_lo + simt::popc(occ_hi & lt)] = t1 - 1;
+  }
+  for (int32_t e = g0; e < g1; e++) {
+    const int32_t mut = c.geno_mut[e], q = c.geno_q[e];
+    uint32_t h = small_hash(mut);
+    while (sm->tab[h] != mut + 1) h = (h + 1) & (SMALL_TAB - 1);
+    const int32_t col = h < 32 ? simt::popc(occ_lo & ((1u << h) - 1u)) : n_lo + simt::popc(occ_hi & ((1u << (h - 32)) - 1u));
+    sm->sum[lane * SMALL_STRIDE + col] = q;                                      // mutation ids are distinct within a read
+    sm->cnt[lane * SMALL_STRIDE + col] = (uint16_t)(0x100 | (q > 0 ? 1 : 0));
+  }
+  simt::sync(FULL);
+  const int32_t mymut = lane < M ? sm->colmut[lane] : -1;
+  const int32_t myrank = lane < M ? c.mut_rank[mymut] : 0x7fffffff;
+
+  // ---- transitive rule: which buckets lie within 2e of each bucket (only components that have rows to visit)
+  const int32_t p_lo = c.cpair_ptr[comp], p_hi = c.cpair_ptr[comp + 1];
+  uint32_t near1 = 0, near2 = 0, near3 = 0;
+  if (p_hi > p_lo) {
+    if (lane < B) { sm->near[0][lane] = 1u << lane; sm->near[1][lane] = 1u << lane; sm->near[2][lane] = 1u << lane; }
+    simt::sync(FULL);
+    const int32_t n_bp = B * (B - 1) / 2;
+    for (int32_t t = lane; t < n_bp; t += 32) {
+      int32_t b = (int32_t)((1.0f + simt::sqrt_f(1.0f + 8.0f * (float)t)) * 0.5f);       // t = b(b-1)/2 + a, a < b
+      while (b * (b - 1) / 2 > t) b--;
+      while ((b + 1) * b / 2 <= t) b++;
+      const int32_t a = t - b * (b - 1) / 2;
+      const int32_t d = lookup_dist(c, b_lo + a, b_lo + b);
+      if (d >= 0)
+        for (int32_t e = 1; e <= 3; e++)
+          if (d <= 2 * e) { simt::atomic_or(&sm->near[e - 1][a], 1u << b); simt::atomic_or(&sm->near[e - 1][b], 1u << a); }
+    }
+    simt::sync(FULL);
+    if (lane < B) { near1 = sm->near[0][lane]; near2 = sm->near[1][lane]; near3 = sm->near[2][lane]; }
+  }
+
+  // ---- cluster state
+  int32_t cid = -1, pos = 0, keyb = -1, keyn = -1;
+
+#define PCB_ROW_ADD(dst, src)                                                                   \
+  do {                                                                                          \
+    sm->sum[(dst) * SMALL_STRIDE + lane] += sm->sum[(src) * SMALL_STRIDE + lane];               \
+    sm->cnt[(dst) * SMALL_STRIDE + lane] = (uint16_t)(sm->cnt[(dst) * SMALL_STRIDE + lane] + sm->cnt[(src) * SMALL_STRIDE + lane]); \
+  } while (0)
+  // addLink(R1, R2) (:185-220) with uniform arguments: C1, C2 the clusters of the two reads (-1: none);
+  // (NKB, NKN) the creation key if a new cluster is opened
+#define PCB_LINK(R1, R2, C1, C2, NKB, NKN)                                                      \
+  do {                                                                                          \
+    if ((C1) >= 0 && (C2) >= 0) {                                                               \
+      const uint32_t m1_ = simt::ballot(FULL, cid == (C1));                                     \
+      const int src_ = simt::ffs(m1_) - 1;                                                      \
+      const int32_t kb_ = simt::shfl(FULL, keyb, src_), kn_ = simt::shfl(FULL, keyn, src_);     \
+      if (cid == (C2)) { pos += simt::popc(m1_); cid = (C1); keyb = kb_; keyn = kn_; }          \
+      PCB_ROW_ADD((C1), (C2));                                                                  \
+    } else if ((C1) >= 0) {                                                                     \
+      const uint32_t m1_ = simt::ballot(FULL, cid == (C1));                                     \
+      const int src_ = simt::ffs(m1_) - 1;                                                      \
+      const int32_t kb_ = simt::shfl(FULL, keyb, src_), kn_ = simt::shfl(FULL, keyn, src_);     \
+      if (lane == (R2)) { pos = simt::popc(m1_); cid = (C1); keyb = kb_; keyn = kn_; }          \
+      PCB_ROW_ADD((C1), (R2));                                                                  \
+    } else if ((C2) >= 0) {                                                                     \
+      const uint32_t m2_ = simt::ballot(FULL, cid == (C2));                                     \
+      const int src_ = simt::ffs(m2_) - 1;                                                      \
+      const int32_t kb_ = simt::shfl(FULL, keyb, src_), kn_ = simt::shfl(FULL, keyn, src_);     \
+      if (lane == (R1)) { pos = simt::popc(m2_); cid = (C2); keyb = kb_; keyn = kn_; }          \
+      PCB_ROW_ADD((C2), (R1));                                                                  \
+    } else {                                                                                    \
+      if (lane == (R1)) { cid = (R1); pos = 0; keyb = (NKB); keyn = (NKN); }                    \
+      if (lane == (R2)) { cid = (R1); pos = 1; keyb = (NKB); keyn = (NKN); }                    \
+      PCB_ROW_ADD((R1), (R2));                                                                  \
+    }                                                                                           \
+  } while (0)
+
+  // ---- seed clustering, bucket by bucket (:385-400)
+  for (int32_t bi = 0; bi < B; bi++) {
+    const int32_t lo = c.bucket_ptr[b_lo + bi] - r_lo, hi = c.bucket_ptr[b_lo + bi + 1] - r_lo;
+    if (hi - lo < 2) continue;
+    int32_t colcnt = 0, colsum = 0;
+    uint32_t mymask = 0;
+    for (int32_t x = lo; x < hi; x++) {
+      const uint32_t cv = sm->cnt[x * SMALL_STRIDE + lane] & 0xFFu;
+      colcnt += (int32_t)cv; colsum += sm->sum[x * SMALL_STRIDE + lane];
+      const uint32_t pm = simt::ballot(FULL, cv != 0u);           // mutations read x carries with Q > 0
+      if (lane == x) mymask = pm;
+    }
+    const uint32_t kept = simt::ballot(FULL, colcnt > 1 || colsum > minQual);     // filterSeqError over the bucket (:350-356)
+    mymask &= kept;
+    int32_t n_created = 0;
+    for (int32_t ri = lo + 1; ri < hi; ri++) {
+      const uint32_t mi = simt::shfl(FULL, mymask, ri);
+      bool ok = false;
+      if (lane >= lo && lane < ri) {                               // calcJaccard of (read i, read j) on presence (:358-367)
+        const int32_t inters = simt::popc(mi & mymask), uni = simt::popc(mi | mymask);
+        ok = uni == 0 || ((double)inters / (double)uni > minJaccard && inters >= minMatches);
+      }
+      uint32_t J = simt::ballot(FULL, ok);
+      int32_t ci = -1;                                             // read i is in no cluster when its row of pairs starts
+      while (J) {
+        const uint32_t live = ci < 0 ? J : (J & simt::ballot(FULL, cid != ci));   // addLink inside one cluster is a no-op
+        if (!live) break;
+        const int j = simt::ffs(live) - 1;
+        J &= ~((2u << j) - 1u);
+        const int32_t cj = simt::shfl(FULL, cid, j);
+        const bool fresh = ci < 0 && cj < 0;
+        PCB_LINK(ri, j, ci, cj, b_lo + bi, n_created);
+        if (fresh) n_created++;
+        ci = simt::shfl(FULL, cid, ri);
+      }
+    }
+  }
+
+  // ---- main clustering: the component's rows in visiting order (:408-455)
+  int32_t n_links = 0, n_tests = 0;
+  for (int32_t p = p_lo; p < p_hi; p++) {
+    const int32_t ba = c.cpair_q[p], bb = c.cpair_r[p], ed = c.cpair_ed[p];
+    const int32_t xlo = c.bucket_ptr[ba] - r_lo, nx = c.bucket_ptr[ba + 1] - c.bucket_ptr[ba];
+    const int32_t ylo = c.bucket_ptr[bb] - r_lo, ny = c.bucket_ptr[bb + 1] - c.bucket_ptr[bb];
+    const uint32_t nearE = ed == 1 ? near1 : ed == 2 ? near2 : near3;
+    // cluster pairs that failed since the last merge (within this row): the last four, -1 never matches an id pair
+    int32_t ma0 = 0, mb0 = 0, ma1 = 0, mb1 = 0, ma2 = 0, mb2 = 0, ma3 = 0, mb3 = 0, memo_n = 0;
+    const int32_t total = nx * ny;
+    for (int32_t base = 0; base < total; base += 32) {
+      const int32_t t = base + lane;
+      const bool valid = t < total;
+      const int32_t x = valid ? xlo + t / ny : 0, y = valid ? ylo + t % ny : 0;
+      const int32_t lx = simt::shfl(FULL, lex, x), ly = simt::shfl(FULL, lex, y);
+      int32_t rid1 = x, rid2 = y;                                  // makePID order (:152-157)
+      if (!(lx < ly)) { rid1 = y; rid2 = x; }
+      int cursor = 0;
+      for (;;) {
+        const int32_t c1 = simt::shfl(FULL, cid, rid1), c2 = simt::shfl(FULL, cid, rid2);
+        const int32_t ida = c1 >= 0 ? c1 : ~rid1, idb = c2 >= 0 ? c2 : ~rid2;
+        bool live = valid && lane >= cursor && !(c1 >= 0 && c1 == c2);            // :424
+        if ((memo_n > 0 && ma0 == ida && mb0 == idb) || (memo_n > 1 && ma1 == ida && mb1 == idb) ||
+            (memo_n > 2 && ma2 == ida && mb2 == idb) || (memo_n > 3 && ma3 == ida && mb3 == idb)) live = false;
+        const uint32_t L = simt::ballot(FULL, live);
+        if (!L) break;
+        const int l = simt::ffs(L) - 1;
+        cursor = l + 1;
+        const int32_t R1 = simt::shfl(FULL, rid1, l), R2 = simt::shfl(FULL, rid2, l);
+        const int32_t C1 = simt::shfl(FULL, c1, l), C2 = simt::shfl(FULL, c2, l);
+        n_tests++;
+        // one visit of the loop body (:419-455)
+        bool linked = false;
+        do {
+          const uint32_t m1 = C1 >= 0 ? simt::ballot(FULL, cid == C1) : (1u << R1);
+          const uint32_t m2 = C2 >= 0 ? simt::ballot(FULL, cid == C2) : (1u << R2);
+          const int32_t s1 = simt::popc(m1), s2 = simt::popc(m2);
+          const int32_t mx = s1 > s2 ? s1 : s2, mn = s1 > s2 ? s2 : s1;
+          if (mx < (mn << ed)) break;                                            // size rule (:435-440)
+          const uint32_t S1 = simt::reduce_or(FULL, ((m1 >> lane) & 1u) ? (1u << bkt) : 0u);
+          const uint32_t S2 = simt::reduce_or(FULL, ((m2 >> lane) & 1u) ? (1u << bkt) : 0u);
+          const bool far = lane < B && ((S1 >> lane) & 1u) && (S2 & ~nearE) != 0u;
+          if (simt::ballot(FULL, far) != 0u) break;                              // transitive rule (:442-445)
+          const int32_t row1 = C1 >= 0 ? C1 : R1, row2 = C2 >= 0 ? C2 : R2;
+          const int32_t v1 = sm->sum[row1 * SMALL_STRIDE + lane], v2 = sm->sum[row2 * SMALL_STRIDE + lane];
+          const int32_t o1 = sm->cnt[row1 * SMALL_STRIDE + lane] & 0xFF, o2 = sm->cnt[row2 * SMALL_STRIDE + lane] & 0xFF;
+          const bool keep = o1 + o2 > 1 || v1 + v2 > minQual;                    // filterSeqError across both clusters
+          const int32_t inters = simt::popc(simt::ballot(FULL, keep && v1 > 0 && v2 > 0));
+          const int32_t uni = simt::popc(simt::ballot(FULL, keep && (v1 > 0 || v2 > 0)));
+          if (!(uni == 0 || (double)inters / (double)uni > minJaccard)) break;   // genotype rule (:447-452)
+          PCB_LINK(R1, R2, C1, C2, -1, -1);
+          linked = true;
+        } while (0);
+        if (linked) { n_links++; memo_n = 0; }
+        else {
+          ma3 = ma2; mb3 = mb2; ma2 = ma1; mb2 = mb1; ma1 = ma0; mb1 = mb0;
+          ma0 = C1 >= 0 ? C1 : ~R1; mb0 = C2 >= 0 ? C2 : ~R2;
+          if (memo_n < 4) memo_n++;
+        }
+      }
+    }
+  }
+
+  // ---- consensus and rows (:464-477, :515-537, :546-567)
+  int64_t call_base = c.call_off[comp];
+  int32_t up_err_head = -1;
+  uint32_t heads = simt::ballot(FULL, cid >= 0 && pos == 0);
+  while (heads) {
+    const int h = simt::ffs(heads) - 1;
+    heads &= heads - 1u;
+    const int32_t ch = simt::shfl(FULL, cid, h);
+    const uint32_t mem = simt::ballot(FULL, cid == ch);
+    const int32_t size = simt::popc(mem);
+    const bool in = ((mem >> lane) & 1u) != 0u;
+    if (in) { c.read_root[r] = r_lo + h; c.read_pos[r] = pos; if (lane != h) c.row_size[r] = 0; }
+    // genotype vote (:468-470): Q where a member names the mutation, -minQual where it does not
+    const int32_t sv = sm->sum[ch * SMALL_STRIDE + lane], any = sm->cnt[ch * SMALL_STRIDE + lane] >> 8;
+    const bool called = lane < M && (int64_t)sv - (int64_t)minQual * (int64_t)(size - any) > 0;
+    const uint32_t cm = simt::ballot(FULL, called);
+    int32_t at = 0;                                               // calls ordered by the (digit key, string) rank (:475)
+    for (uint32_t tm = cm; tm; tm &= tm - 1u) {
+      const int s = simt::ffs(tm) - 1;
+      const int32_t rk = simt::shfl(FULL, myrank, s);
+      if (rk < myrank || (rk == myrank && s < lane)) at++;
+    }
+    if (called) c.call_mut[call_base + at] = mymut;
+    // majority barcode / uptag (:515-532)
+    int32_t cons[2] = {0, 0};
+    for (int w = 0; w < 2; w++) {
+      if (w == 1 && !c.up_id) { cons[1] = cons[0]; break; }
+      const int32_t id = w == 0 ? bc : up;
+      if (w == 1 && simt::ballot(FULL, in && id < 0) != 0u) up_err_head = r_lo + h;     // clustered read without uptag: KeyError (:519)
+      const int32_t v = id < 0 ? 0x7ffffffe : id;
+      int32_t votes = 0;
+      if (in) votes = simt::popc(simt::match_any(mem, v));
+      const int32_t best = simt::reduce_max(FULL, votes);
+      const uint32_t top = simt::ballot(FULL, in && votes == best);
+      if (simt::popc(top) == best) cons[w] = simt::shfl(FULL, v, simt::ffs(top) - 1);      // one barcode holds all the top votes
+      else if (size == 2) cons[w] = simt::shfl(FULL, id, h);
+      else cons[w] = PCB_NEEDS_ALIGNMENT;
+    }
+    if (lane == h) {
+      c.row_size[r] = size; c.row_key[r] = ((int64_t)keyb << 32) | (int64_t)keyn;
+      c.row_call_off[r] = call_base; c.row_call_n[r] = simt::popc(cm);
+      c.row_bc[r] = cons[0]; c.row_up[r] = cons[1];
+    }
+    call_base += simt::popc(cm);
+  }
+  {
+    // unclustered reads (:560-567): calls with Q >= minQual in input order
+    const bool single = has && cid < 0;
+    int32_t ncs = 0;
+    if (single) for (int32_t e = g0; e < g1; e++) if (c.geno_q[e] >= minQual) ncs++;
+    int32_t incl = ncs;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t tv = simt::shfl(FULL, incl, lane >= o ? lane - o : lane);
+      if (lane >= o) incl += tv;
+    }
+    if (single) {
+      const int64_t off = call_base + (int64_t)(incl - ncs);
+      c.read_root[r] = r; c.read_pos[r] = 0; c.row_size[r] = 1; c.row_key[r] = -1;
+      c.row_bc[r] = bc; c.row_up[r] = c.up_id ? up : bc;
+      c.row_call_off[r] = off; c.row_call_n[r] = ncs;
+      int32_t k = 0;
+      for (int32_t e = g0; e < g1; e++) if (c.geno_q[e] >= minQual) c.call_mut[off + k++] = c.geno_mut[e];
+    }
+  }
+  if (lane == 0) {
+    if (n_links) simt::atomic_add(&c.status[2], n_links);
+    if (n_tests) simt::atomic_add(&c.status[3], n_tests);
+    if (up_err_head >= 0) { c.status[0] = 3; c.status[1] = up_err_head; }
+  }
+#undef PCB_LINK
+#undef PCB_ROW_ADD
+  return 0;
+}
+
+}  // namespace pcb

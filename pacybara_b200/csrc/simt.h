@@ -1,0 +1,52 @@
+// simt.h -- the warp-collective vocabulary of the warp-synchronous kernels (merge_small.cuh).
+//
+// Under nvcc these are the sm_100a intrinsics, one instruction each.  Under a plain host compiler
+// (tests/host_emul only -- a unit-test harness, never a product path) they are declared here and
+// implemented by tests/host_emul/simt_emul.cpp, which runs the 32 lanes of a warp as coroutines that
+// meet at every collective.  That way the very source the GPU executes is exercised against the oracle
+// in the GPU-less build container, with the lane interleaving randomised so that a missing
+// __syncwarp shows up as a failing test rather than as a rare flake on the device.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SIMT_FN __device__ __forceinline__
+
+namespace simt {
+SIMT_FN uint32_t ballot(uint32_t mask, bool p) { return __ballot_sync(mask, p); }
+SIMT_FN int32_t shfl(uint32_t mask, int32_t v, int src) { return __shfl_sync(mask, v, src); }
+SIMT_FN uint32_t shfl(uint32_t mask, uint32_t v, int src) { return __shfl_sync(mask, v, src); }
+SIMT_FN uint32_t match_any(uint32_t mask, int32_t v) { return __match_any_sync(mask, v); }
+SIMT_FN uint32_t reduce_or(uint32_t mask, uint32_t v) { return __reduce_or_sync(mask, v); }
+SIMT_FN int32_t reduce_max(uint32_t mask, int32_t v) { return __reduce_max_sync(mask, v); }
+SIMT_FN void sync(uint32_t mask) { __syncwarp(mask); }
+SIMT_FN int32_t atomic_cas(int32_t *p, int32_t cmp, int32_t v) { return atomicCAS(p, cmp, v); }
+SIMT_FN uint32_t atomic_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
+SIMT_FN int32_t atomic_add(int32_t *p, int32_t v) { return atomicAdd(p, v); }
+SIMT_FN int popc(uint32_t x) { return __popc(x); }
+SIMT_FN int ffs(uint32_t x) { return __ffs((int)x); }      // 1-based, 0 when x == 0
+SIMT_FN float sqrt_f(float x) { return sqrtf(x); }
+}  // namespace simt
+
+#else
+#include <math.h>
+#define SIMT_FN inline
+
+namespace simt {
+// implemented by tests/host_emul/simt_emul.cpp; `lane` is implicit (the coroutine that is running)
+uint32_t ballot(uint32_t mask, bool p);
+int32_t shfl(uint32_t mask, int32_t v, int src);
+uint32_t shfl(uint32_t mask, uint32_t v, int src);
+uint32_t match_any(uint32_t mask, int32_t v);
+uint32_t reduce_or(uint32_t mask, uint32_t v);
+int32_t reduce_max(uint32_t mask, int32_t v);
+void sync(uint32_t mask);
+// lanes run one at a time between collectives, so plain read-modify-writes are atomic
+inline int32_t atomic_cas(int32_t *p, int32_t cmp, int32_t v) { int32_t o = *p; if (o == cmp) *p = v; return o; }
+inline uint32_t atomic_or(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
+inline int32_t atomic_add(int32_t *p, int32_t v) { int32_t o = *p; *p = o + v; return o; }
+inline int popc(uint32_t x) { return __builtin_popcount(x); }
+inline int ffs(uint32_t x) { return __builtin_ffs((int)x); }
+inline float sqrt_f(float x) { return sqrtf(x); }
+}  // namespace simt
+#endif

@@ -19,6 +19,9 @@ from pacybara_b200 import hostdata, synth  # noqa: E402
 from tests import util  # noqa: E402
 
 
+STATS = dict(small=0, components=0)
+
+
 def one(seed: int) -> str:
     rng = np.random.default_rng(seed)
     combo = bool(rng.random() < 0.2)
@@ -64,6 +67,15 @@ def one(seed: int) -> str:
     for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
         if not np.array_equal(getattr(got, f), getattr(want, f)):
             return f"{f} differs ({kw}, {params})"
+    # the warp kernel for small components (csrc/merge_small.cuh) on an emulated warp, lanes interleaved at random
+    small = util.emul_merge_small(prob, pairs, seed=seed)
+    STATS["small"] += small["n_small"]; STATS["components"] += small["n_components"]
+    if int(small["status"][0]) == 3:
+        return "small-component kernel reports a missing uptag, the oracle does not"
+    got = hostdata.rows_from_merge_outputs(small)
+    for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
+        if not np.array_equal(getattr(got, f), getattr(want, f)):
+            return f"small-component kernel: {f} differs ({kw}, {params})"
     # on-demand distances: only the pairs a pass can visit are listed, the transitive rule scores the rest on the spot,
     # and two shards put together are the whole (canonical row order only: that is what the fused call produces)
     keep = ed <= params["max_diff"]
@@ -72,6 +84,7 @@ def one(seed: int) -> str:
     full_out = util.emul_merge(prob, hostdata.dedupe_ed_rows(qf, rf, df, prob.n_buckets, prob.max_diff))
     planes = util.pack_planes(b["bucket_seq"], b["bucket_len"])
     pairs2 = hostdata.dedupe_ed_rows(q2, r2, d2, prob.n_buckets, prob.max_diff)
+    small2 = util.emul_merge_small(prob, pairs2, planes=planes, blen=b["bucket_len"], compute_k=2 * params["max_diff"], seed=seed + 7)
     parts = [util.emul_merge(prob, pairs2, shard=(s, 2), planes=planes, blen=b["bucket_len"], compute_k=2 * params["max_diff"]) for s in range(2)]
     # (the rows above may have been shuffled, which is a different problem: the canonical order decides here)
     if (int(full_out["status"][0]) == 3) != any(int(o["status"][0]) == 3 for o in parts):
@@ -84,6 +97,10 @@ def one(seed: int) -> str:
     for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
         if not np.array_equal(getattr(lazy, f), getattr(full, f)):
             return f"on-demand + 2 shards: {f} differs ({kw}, {params})"
+    lazy_small = hostdata.rows_from_merge_outputs(small2)
+    for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
+        if not np.array_equal(getattr(lazy_small, f), getattr(full, f)):
+            return f"small-component kernel, on-demand distances: {f} differs ({kw}, {params})"
     return ""
 
 
@@ -98,7 +115,8 @@ def main():
             print(f"seed {seed}: {msg}", flush=True)
         seed += 1
         n += 1
-    print(f"{n} libraries, {len(bad)} discrepancies, seeds {seed - n}..{seed - 1}")
+    print(f"{n} libraries, {len(bad)} discrepancies, seeds {seed - n}..{seed - 1}; "
+          f"{STATS['small']} of {STATS['components']} components went through the small-component warp kernel")
     return 1 if bad else 0
 
 
