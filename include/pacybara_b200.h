@@ -43,7 +43,7 @@
 extern "C" {
 #endif
 
-#define PCB_ABI_VERSION 2
+#define PCB_ABI_VERSION 3
 
 enum {
   PCB_OK = 0,
@@ -91,6 +91,16 @@ const char *pcb_last_error(const pcb_ctx *ctx);
 int pcb_ctx_create(int device, pcb_ctx **out);
 void pcb_ctx_destroy(pcb_ctx *ctx);
 int64_t pcb_stat(const pcb_ctx *ctx, int which);
+/*
+ * Options of a context.  PCB_OPT_REPLAY_SHAPE: which launch shape replays the components in pcb_merge /
+ * pcb_cluster_reads -- PCB_REPLAY_AUTO (default: one warp per component with one lane per read for components of
+ * at most 32 reads, the generic warp kernel for the rest), PCB_REPLAY_THREAD (one thread per component) or
+ * PCB_REPLAY_WARP (the generic warp kernel for everything).  All shapes give identical results; the knob exists
+ * for measurements and for the parity tests, which run every shape.
+ */
+enum { PCB_OPT_REPLAY_SHAPE = 0 };
+enum { PCB_REPLAY_AUTO = 0, PCB_REPLAY_THREAD = 1, PCB_REPLAY_WARP = 2 };
+int pcb_set_option(pcb_ctx *ctx, int option, int64_t value);
 /* Block until everything queued on the context's stream has finished. */
 int pcb_sync(pcb_ctx *ctx);
 /* The context's cudaStream_t, for callers that time with their own CUDA events. */

@@ -19,7 +19,10 @@ STAT = dict(pairs_scored=0, cells=1, edges=2, seed_len=3, kernel_launches=4, com
             t_scatter_ns=15, rows=16, calls=17)
 
 # every symbol include/pacybara_b200.h declares
-SYMBOLS = ["pcb_abi_version", "pcb_last_error", "pcb_ctx_create", "pcb_ctx_destroy", "pcb_stat", "pcb_sync",
+REPLAY_SHAPES = dict(auto=0, small=0, thread=1, warp=2)
+OPT_REPLAY_SHAPE = 0
+
+SYMBOLS = ["pcb_abi_version", "pcb_last_error", "pcb_ctx_create", "pcb_ctx_destroy", "pcb_stat", "pcb_set_option", "pcb_sync",
            "pcb_stream", "pcb_bucket", "pcb_edit_pairs", "pcb_edit_pairs_fetch", "pcb_sort_edges", "pcb_merge", "pcb_cluster_reads", "pcb_compact_shard", "pcb_match_barcodes", "pcb_tag_rows",
            "pcb_text_open", "pcb_text_close", "pcb_fastq_records", "pcb_fastq_fetch", "pcb_rank_strings", "pcb_geno_join",
            "pcb_geno_fetch", "pcb_uptag_join", "pcb_uptag_fetch"]
@@ -51,6 +54,7 @@ def load():
         lib.pcb_ctx_destroy.restype = None
         lib.pcb_stat.restype = i64
         lib.pcb_stat.argtypes = [vp, C.c_int]
+        lib.pcb_set_option.argtypes = [vp, C.c_int, i64]
         lib.pcb_sync.argtypes = [vp]
         lib.pcb_stream.restype = vp
         lib.pcb_stream.argtypes = [vp]

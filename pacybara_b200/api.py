@@ -70,6 +70,15 @@ class Context:
     def sync(self):
         self._check(self.lib.pcb_sync(self.h))
 
+    def set_replay_shape(self, shape: Optional[str] = None):
+        """'auto' (default), 'thread' or 'warp' (pcb_set_option).  None: what the environment variable PCB_REPLAY
+        says -- read here on the host, per call, so that tests and measurements can switch shapes on a live context."""
+        import os
+        shape = shape or os.environ.get("PCB_REPLAY") or "auto"
+        if shape not in _lib.REPLAY_SHAPES:
+            raise ValueError(f"unknown replay shape {shape!r}")
+        self._check(self.lib.pcb_set_option(self.h, _lib.OPT_REPLAY_SHAPE, _lib.REPLAY_SHAPES[shape]))
+
     def stream_handle(self) -> int:
         return int(self.lib.pcb_stream(self.h) or 0)
 
@@ -197,6 +206,7 @@ class Context:
             outs[name], ptr = self._out(mem, (max(R, 1),), dt, "m_" + name)
             ptrs.append(ptr)
         outs["call_mut"], p_call = self._out(mem, (max(nnz, 1),), np.int32, "m_call_mut")
+        self.set_replay_shape()
         self._check(self.lib.pcb_merge(self.h, mem, R, int(p.n_buckets), *ins[:9], int(p.mut_rank.shape[0]),
                                        int(pairs.q.shape[0]), *ins[9:], int(p.max_diff), int(p.min_qual),
                                        float(p.min_jaccard), int(p.min_matches), p_bseq, p_blen, stride,
@@ -251,6 +261,7 @@ class Context:
         nb, ne = C.c_int32(0), C.c_int64(0)
         rep, p_rep = self._out(mem, (max(R, 1),), np.int32, "c_row_rep") if compact_rows else (None, None)
         flags = (_lib.CLUSTER_FULL_TABLE if full_table else 0) | (_lib.CLUSTER_COMPACT_ROWS if compact_rows else 0)
+        self.set_replay_shape()
         self._check(self.lib.pcb_cluster_reads(self.h, mem, ins[0], ins[1], ins[2], R, stride, *ins[3:],
                                                int(mut_rank.shape[0]), int(max_diff), int(min_qual),
                                                float(min_jaccard), int(min_matches), flags, p_bor, C.byref(nb), C.byref(ne),

@@ -217,6 +217,16 @@ int64_t pcb_stat(const pcb_ctx *ctx, int which) {
   return ctx->stats[which];
 }
 
+int pcb_set_option(pcb_ctx *ctx, int option, int64_t value) {
+  if (!ctx) return PCB_E_STATE;
+  if (option == PCB_OPT_REPLAY_SHAPE && value >= PCB_REPLAY_AUTO && value <= PCB_REPLAY_WARP) {
+    ctx->replay_shape = (int)value;
+    return PCB_OK;
+  }
+  ctx->err = "pcb_set_option: unknown option or value";
+  return PCB_E_INPUT;
+}
+
 int pcb_sync(pcb_ctx *ctx) {
   return guarded(ctx, [&] {});
 }

@@ -47,6 +47,7 @@ struct pcb_ctx {
   int n_marks = 0;
   std::string err;
   int64_t stats[PCB_STAT_COUNT] = {0};
+  int replay_shape = PCB_REPLAY_AUTO;      // pcb_set_option(PCB_OPT_REPLAY_SHAPE)
   pcb_edges edges;
 };
 

@@ -25,12 +25,13 @@
 
 #include "common.cuh"
 #include "merge_core.h"
+#include "merge_small.cuh"
 #include "merge_warp.cuh"
 
 namespace pcb {
 
 constexpr uint32_t WORK_CAP = 1023;     // component work classes used for ordering (10 bits)
-constexpr int HEAVY_READS = 64;         // components of at least this many reads always get a whole warp
+constexpr int HEAVY_READS = SMALL_READS + 1;   // components too big for the one-lane-per-read kernel (they are numbered first)
 
 __device__ __forceinline__ int32_t uf_find(int32_t *parent, int32_t x) {
   for (;;) {
@@ -297,19 +298,12 @@ struct __align__(16) CompSmem {
   int32_t rd_slot[SM_READS], rd_next[SM_READS], sl_parent[SM_READS], sl_head[SM_READS], sl_tail[SM_READS], sl_size[SM_READS];
 };
 
-__global__ void __launch_bounds__(COMP_BLOCK) component_kernel_warp(MergeCtx c, int32_t comp_lo, int32_t n_comp, int32_t shard_rank,
-                                                                    int32_t shard_count) {
-  __shared__ CompSmem sm_all[COMP_BLOCK / 32];
-  const int32_t comp = comp_lo + (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-  const int lane = threadIdx.x & 31;
-  if (comp >= n_comp) return;
-  if (comp % shard_count != shard_rank) return;
+__device__ __forceinline__ void replay_component_warp(const MergeCtx &c, int32_t comp, int lane, CompSmem *sm) {
   const int32_t r_lo = c.bucket_ptr[c.comp_ptr[comp]];
   const int32_t reads = c.bucket_ptr[c.comp_ptr[comp + 1]] - r_lo;
   const int32_t nnz = c.geno_ptr[r_lo + reads] - c.geno_ptr[r_lo];
   MergeState st = global_state(c, comp);
   if (reads <= SM_READS && nnz <= SM_READS) {
-    CompSmem *sm = &sm_all[threadIdx.x >> 5];
     for (int32_t i = lane; i < SM_SLOTS; i += 32) { GenoSlot z; z.key = 0; z.obs1 = z.obs2 = z.pad = 0; z.sum1 = z.sum2 = 0; sm->slots[i] = z; }
     for (int32_t i = lane; i < reads; i += 32) { sm->rd_slot[i] = -1; sm->rd_next[i] = -1; }
     __syncwarp();
@@ -320,6 +314,38 @@ __global__ void __launch_bounds__(COMP_BLOCK) component_kernel_warp(MergeCtx c, 
     st.lists = sm->lists; st.list_cap = 2 * SM_READS;
   }
   process_component_warp(c, st, comp, lane);        // one call site: the same code runs on either memory
+}
+
+__global__ void __launch_bounds__(COMP_BLOCK) component_kernel_warp(MergeCtx c, int32_t comp_lo, int32_t n_comp) {
+  __shared__ CompSmem sm_all[COMP_BLOCK / 32];
+  const int32_t comp = comp_lo + (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (comp >= n_comp) return;
+  replay_component_warp(c, comp, threadIdx.x & 31, &sm_all[threadIdx.x >> 5]);
+}
+
+// the components the small-component kernel declined (list filled on the device, its length known only there):
+// a fixed grid of warps walks the list
+__global__ void __launch_bounds__(COMP_BLOCK) component_kernel_warp_list(MergeCtx c, const int32_t *__restrict__ list,
+                                                                         const int32_t *__restrict__ n_list) {
+  __shared__ CompSmem sm_all[COMP_BLOCK / 32];
+  const int32_t n = *n_list;
+  const int32_t n_warps = (int32_t)(gridDim.x * (blockDim.x >> 5));
+  for (int32_t i = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5); i < n; i += n_warps) {
+    replay_component_warp(c, list[i], threadIdx.x & 31, &sm_all[threadIdx.x >> 5]);
+    __syncwarp();
+  }
+}
+
+// One warp per component of at most 32 reads, one lane per read (merge_small.cuh).  A component it is not
+// eligible for (more than 32 distinct mutations, huge qualities) goes on the list for the generic kernel.
+constexpr int SMALL_BLOCK = 128;
+__global__ void __launch_bounds__(SMALL_BLOCK) component_kernel_small(MergeCtx c, int32_t comp_lo, int32_t n_comp,
+                                                                      int32_t *__restrict__ declined, int32_t *__restrict__ n_declined) {
+  __shared__ SmallSmem sm_all[SMALL_BLOCK / 32];
+  const int32_t comp = comp_lo + (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (comp >= n_comp) return;
+  const int lane = threadIdx.x & 31;
+  if (process_component_small(c, comp, lane, &sm_all[threadIdx.x >> 5]) != 0 && lane == 0) declined[atomicAdd(n_declined, 1)] = comp;
 }
 
 // Block size of the thread kernels: warps of one block finish at very different times, and a block keeps its
@@ -524,6 +550,7 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
     PCB_LAUNCH(ctx, init_outputs_kernel, grid_for((size_t)R, 256), 256, 0, R, (int64_t)0, out.read_root, out.read_pos, out.row_size,
                out.row_key, out.row_bc, out.row_up, out.row_call_off, out.row_call_n, out.call_mut);
 
+  DevBuf<int32_t> declined(ctx, (size_t)n_comp + 1), n_declined(ctx, 1);
   MergeCtx c;
   memset(&c, 0, sizeof(c));
   c.R = R; c.U = U;
@@ -544,24 +571,26 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   c.call_mut = out.call_mut; c.status = status.p;
   c.prm.maxDiff = in.max_diff; c.prm.minQual = in.min_qual; c.prm.minMatches = in.min_matches; c.prm.minJaccard = in.min_jaccard;
   stage_end(ctx, PCB_STAT_T_PREP_NS);
-  // Which launch shape: measured (profiles/r01_replay_shapes.md) the thread kernel wins when buckets are small
-  // (cfg 2: 5 reads per bucket, 1.4 vs 2.65 ms), the warp kernel when reads concentrate in big buckets (cfg 4:
-  // 8 reads per bucket, 1.1 vs 4.6 ms).  Components of HEAVY_READS reads or more (they come first) always get a warp:
-  // one thread would crawl through them while the rest of the chip idles.
-  const char *mode = getenv("PCB_REPLAY");
-  int32_t n_warp = (double)R / (double)U >= 7.0 ? n_comp : (int32_t)h_n_heavy;
-  if (mode && strcmp(mode, "warp") == 0) n_warp = n_comp;
-  if (mode && strcmp(mode, "thread") == 0) n_warp = 0;
+  // Launch shapes (profiles/r01_replay_shapes.md, r02_replay.md).  Default: components of at most 32 reads -- all but a
+  // handful on every BASELINE config -- go to the one-lane-per-read kernel; the bigger ones (numbered first) and
+  // whatever that kernel declines go to the generic warp kernel.  ctx->replay_shape forces the round-1 shapes
+  // (one thread per component / the generic warp kernel for everything), which the parity tests keep exercising.
+  int32_t n_warp = (int32_t)h_n_heavy;
+  if (ctx->replay_shape == PCB_REPLAY_WARP) n_warp = n_comp;
   if (n_warp > 0)
-    PCB_LAUNCH(ctx, component_kernel_warp, grid_for((size_t)n_warp * 32, COMP_BLOCK), COMP_BLOCK, 0, c, 0, n_warp, 0, 1);
-  if (n_warp < n_comp) {
-    int per_warp = 4;
-    if (const char *e = getenv("PCB_COMP_PER_WARP")) { int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8 || v == 16 || v == 32) per_warp = v; }
+    PCB_LAUNCH(ctx, component_kernel_warp, grid_for((size_t)n_warp * 32, COMP_BLOCK), COMP_BLOCK, 0, c, 0, n_warp);
+  if (n_warp < n_comp && ctx->replay_shape == PCB_REPLAY_THREAD) {
+    const int per_warp = 4;               // best of a 1..32 sweep (divergent lanes serialise)
     size_t n_threads = ((size_t)(n_comp - n_warp) + per_warp - 1) / per_warp * 32;
     // three launches, one per phase: each kernel's code fits the instruction cache and its threads share a loop nest
     PCB_LAUNCH(ctx, component_kernel_thread<1>, grid_for(n_threads, THREAD_BLOCK), THREAD_BLOCK, 0, c, n_warp, n_comp, 0, 1, per_warp);
     PCB_LAUNCH(ctx, component_kernel_thread<2>, grid_for(n_threads, THREAD_BLOCK), THREAD_BLOCK, 0, c, n_warp, n_comp, 0, 1, per_warp);
     PCB_LAUNCH(ctx, component_kernel_thread<3>, grid_for(n_threads, THREAD_BLOCK), THREAD_BLOCK, 0, c, n_warp, n_comp, 0, 1, per_warp);
+  } else if (n_warp < n_comp) {
+    PCB_CUDA(cudaMemsetAsync(n_declined.p, 0, sizeof(int32_t), ctx->stream));
+    PCB_LAUNCH(ctx, component_kernel_small, grid_for((size_t)(n_comp - n_warp) * 32, SMALL_BLOCK), SMALL_BLOCK, 0, c, n_warp, n_comp,
+               declined.p, n_declined.p);
+    PCB_LAUNCH(ctx, component_kernel_warp_list, (unsigned)ctx->sm_count * 2u, COMP_BLOCK, 0, c, declined.p, n_declined.p);
   }
   stage_end(ctx, PCB_STAT_T_REPLAY_NS);
   if (Rm > 0)

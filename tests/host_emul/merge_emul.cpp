@@ -142,3 +142,23 @@ extern "C" int emul_merge(int32_t R, int32_t U, const int32_t *bucket_ptr, const
   if (use_small && status[0] == 0) status[1] = n_small;
   return n_comp;
 }
+
+// ---- self test of the emulator (tests/test_merge_small_host.py): neighbour exchange through a shared array
+static int selftest(bool with_sync) {
+  int wrong = 0;
+  for (unsigned seed = 1; seed <= 20; seed++) {
+    static int32_t buf[32];
+    int got[32];
+    for (int l = 0; l < 32; l++) buf[l] = -1;
+    simt_emul::run_warp([&](int lane) {
+      buf[lane] = lane * 7;
+      if (with_sync) simt::sync(0xFFFFFFFFu);
+      got[lane] = buf[(lane + 1) & 31];
+      simt::sync(0xFFFFFFFFu);
+    }, seed);
+    for (int l = 0; l < 32; l++) if (got[l] != ((l + 1) & 31) * 7) wrong = 1;
+  }
+  return wrong;
+}
+extern "C" int emul_selftest_missing_sync() { return selftest(false); }
+extern "C" int emul_selftest_with_sync() { return selftest(true); }

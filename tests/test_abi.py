@@ -33,7 +33,7 @@ def test_header_symbols_are_exported(lib):
 
 
 def test_abi_version_and_constants(lib):
-    assert lib.pcb_abi_version() == 2
+    assert lib.pcb_abi_version() == 3
     text = open(HEADER).read()
     for name, value in (("PCB_STAT_PAIRS_SCORED", _lib.STAT["pairs_scored"]), ("PCB_STAT_T_REPLAY_NS", _lib.STAT["t_replay_ns"]),
                         ("PCB_STAT_PROBE_NS", _lib.STAT["probe_ns"])):
