@@ -75,9 +75,9 @@ enum {
   PCB_STAT_T_BUCKET_NS = 10,   /* pack + table + numbering + read grouping */
   PCB_STAT_T_INDEX_NS = 11,    /* seed index (count, scan, fill) */
   PCB_STAT_T_HITS_NS = 12,     /* hit sort + de-duplication */
-  PCB_STAT_T_PREP_NS = 13,     /* merge preprocessing: components, renumbering, adjacency, visiting lists, scratch */
-  PCB_STAT_T_REPLAY_NS = 14,   /* component_kernel */
-  PCB_STAT_T_SCATTER_NS = 15,  /* outputs back to the caller's numbering */
+  PCB_STAT_T_PREP_NS = 13,     /* merge preprocessing: components, grouping, adjacency rows, visiting lists */
+  PCB_STAT_T_REPLAY_NS = 14,   /* the replay kernels (they write the outputs in the caller's numbering themselves) */
+  PCB_STAT_T_SCATTER_NS = 15,  /* what follows the replay: status round trip, late components */
   PCB_STAT_ROWS = 16,          /* rows of the last pcb_cluster_reads with PCB_CLUSTER_COMPACT_ROWS */
   PCB_STAT_CALLS = 17,         /* consensus genotype entries of those rows */
   PCB_STAT_COUNT = 18
@@ -148,7 +148,8 @@ int pcb_sort_edges(pcb_ctx *ctx, int mem, int32_t *ei, int32_t *ej, int32_t *ed,
  *   bc_id [R]       id of the read's barcode string;  up_id [R] id of its uptag string, -1 if the
  *                   read has none, or NULL when no uptag file is given (:537)
  *   geno_ptr [R+1], geno_mut, geno_q [nnz]  genotype calls per read, distinct mutation ids within
- *                   a read, input order;  mut_rank [n_mut] rank in (digit key, string) order (:475)
+ *                   a read, input order (nnz = geno_ptr[R], passed so that device arrays need no round trip);
+ *                   mut_rank [n_mut] rank in (digit key, string) order (:475), a permutation of 0..n_mut-1
  *   pair_q, pair_r, pair_d, pair_ed [n_pairs]  unique unordered bucket pairs in visiting order:
  *                   (q, r) direction of the row that introduced the pair in the pass that visits it,
  *                   d = distance the lookup table ends with (:266), ed = visiting pass 1..maxDiff or 0
@@ -160,8 +161,13 @@ int pcb_sort_edges(pcb_ctx *ctx, int mem, int32_t *ei, int32_t *ej, int32_t *ed,
  *                   clusters of the full table (lookups never leave a connected component).  The
  *                   drop-in pacybara_cluster.py never sets it: there the EDFILE is the only authority.
  *   shard_rank / shard_count  a connected component belongs to shard (smallest bucket of the component mod
- *                   shard_count); entries of reads owned by other shards are left at PCB_FILL, the call regions are
- *                   laid out identically on every shard (combine shards with an element-wise max)
+ *                   shard_count); entries of reads owned by other shards are left at PCB_FILL
+ *   flags           PCB_MERGE_PAIRS_SORTED: pair_q < pair_r everywhere and the pairs ascend by (q, r) -- the order
+ *                   pcb_edit_pairs delivers and pcb_sort_edges restores; the adjacency and the visiting lists then need
+ *                   no sort.  PCB_MERGE_SHARD_LAYOUT: lay the call regions out by component label, identically on
+ *                   every shard, so that shards can be combined with an element-wise max (costs a pass over all reads;
+ *                   without it a row's calls sit wherever the component found room: row_call_off / row_call_n / the
+ *                   calls are reproducible, the layout of call_mut is not)
  * outputs (all [R] unless noted; a "row" is a cluster or an unclustered read and is named by
  * its representative read = first member)
  *   read_root       representative read of the row the read belongs to
@@ -171,16 +177,18 @@ int pcb_sort_edges(pcb_ctx *ctx, int mem, int32_t *ei, int32_t *ej, int32_t *ed,
  *   row_bc, row_up  consensus barcode / uptag id, or PCB_NEEDS_ALIGNMENT
  *   row_call_off (int64), row_call_n, call_mut [nnz]  consensus / singleton genotype
  */
+#define PCB_MERGE_PAIRS_SORTED 1
+#define PCB_MERGE_SHARD_LAYOUT 2
 int pcb_merge(pcb_ctx *ctx, int mem, int32_t R, int32_t U,
               const int32_t *bucket_ptr, const int32_t *bucket_reads, const int32_t *lexrank,
               const int32_t *bc_id, const int32_t *up_id,
-              const int32_t *geno_ptr, const int32_t *geno_mut, const int32_t *geno_q,
+              const int32_t *geno_ptr, const int32_t *geno_mut, const int32_t *geno_q, int64_t nnz,
               const int32_t *mut_rank, int32_t n_mut,
               int64_t n_pairs, const int32_t *pair_q, const int32_t *pair_r, const int32_t *pair_d,
               const int32_t *pair_ed,
               int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches,
               const uint8_t *bucket_seq, const int32_t *bucket_len, int32_t stride, int32_t on_demand_k,
-              int32_t shard_rank, int32_t shard_count,
+              int32_t shard_rank, int32_t shard_count, int32_t flags,
               int32_t *read_root, int32_t *read_pos, int32_t *row_size, int64_t *row_key,
               int32_t *row_bc, int32_t *row_up, int64_t *row_call_off, int32_t *row_call_n,
               int32_t *call_mut);
@@ -208,7 +216,7 @@ int pcb_merge(pcb_ctx *ctx, int mem, int32_t R, int32_t U,
 #define PCB_CLUSTER_COMPACT_ROWS 2
 int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *qual, const int32_t *len,
                       int32_t R, int32_t stride, const int32_t *lexrank, const int32_t *up_id,
-                      const int32_t *geno_ptr, const int32_t *geno_mut, const int32_t *geno_q,
+                      const int32_t *geno_ptr, const int32_t *geno_mut, const int32_t *geno_q, int64_t nnz,
                       const int32_t *mut_rank, int32_t n_mut,
                       int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches, int32_t flags,
                       int32_t *bucket_of_read, int32_t *n_buckets, int64_t *n_edges,

@@ -14,6 +14,8 @@ FILL = -(1 << 31)
 NEEDS_ALIGNMENT = -2
 CLUSTER_FULL_TABLE = 1
 CLUSTER_COMPACT_ROWS = 2
+MERGE_PAIRS_SORTED = 1
+MERGE_SHARD_LAYOUT = 2
 STAT = dict(pairs_scored=0, cells=1, edges=2, seed_len=3, kernel_launches=4, components=5, links=6, tests=7,
             buckets=8, probe_ns=9, t_bucket_ns=10, t_index_ns=11, t_hits_ns=12, t_prep_ns=13, t_replay_ns=14,
             t_scatter_ns=15, rows=16, calls=17)
@@ -62,9 +64,9 @@ def load():
         lib.pcb_edit_pairs.argtypes = [vp, C.c_int, vp, vp, i32, i32, i32, i32, i32, C.POINTER(i64)]
         lib.pcb_edit_pairs_fetch.argtypes = [vp, C.c_int, vp, vp, vp, i64]
         lib.pcb_sort_edges.argtypes = [vp, C.c_int, vp, vp, vp, i64, i32]
-        lib.pcb_merge.argtypes = ([vp, C.c_int, i32, i32] + [vp] * 9 + [i32, i64] + [vp] * 4 +
-                                  [i32, i32, dbl, i32, vp, vp, i32, i32, i32, i32] + [vp] * 9)
-        lib.pcb_cluster_reads.argtypes = ([vp, C.c_int, vp, vp, vp, i32, i32] + [vp] * 6 + [i32, i32, i32, dbl, i32, i32] +
+        lib.pcb_merge.argtypes = ([vp, C.c_int, i32, i32] + [vp] * 8 + [i64, vp, i32, i64] + [vp] * 4 +
+                                  [i32, i32, dbl, i32, vp, vp, i32, i32, i32, i32, i32] + [vp] * 9)
+        lib.pcb_cluster_reads.argtypes = ([vp, C.c_int, vp, vp, vp, i32, i32] + [vp] * 5 + [i64, vp, i32, i32, i32, dbl, i32, i32] +
                                           [vp, C.POINTER(i32), C.POINTER(i64)] + [vp] * 10)
         lib.pcb_compact_shard.argtypes = ([vp, C.c_int, C.c_int, i32, i64] + [vp] * 10 + [C.POINTER(i32), vp, vp, vp, vp] +
                                           [C.POINTER(i32), C.POINTER(i64)] + [vp] * 8)

@@ -185,10 +185,13 @@ class Context:
 
     # ------------------------------------------------------------------ a4..a13
     def merge(self, p: MergeProblem, pairs: PairList, shard: Tuple[int, int] = (0, 1), bucket_seq=None,
-              bucket_len=None, on_demand_k: int = -1) -> Dict:
+              bucket_len=None, on_demand_k: int = -1, pairs_sorted: bool = False, shard_layout: Optional[bool] = None) -> Dict:
         """Seed clustering + greedy merge + consensus (pcb_merge).  Arrays inside `p` and `pairs`
         may be numpy or torch CUDA tensors.  bucket_seq/bucket_len/on_demand_k: score distances the
-        pair list lacks on demand (see the header); never used for an EDFILE-driven run."""
+        pair list lacks on demand (see the header); never used for an EDFILE-driven run.
+        pairs_sorted: q < r everywhere and ascending by (q, r) (pcb_edit_pairs / pcb_sort_edges order).
+        shard_layout: call regions laid out identically on every shard, so that the shards' outputs can be combined
+        with an element-wise max (default: only when shard[1] > 1)."""
         arrays = [p.bucket_ptr, p.bucket_reads, p.lexrank, p.bc_id, p.up_id, p.geno_ptr, p.geno_mut, p.geno_q,
                   p.mut_rank, pairs.q, pairs.r, pairs.d, pairs.ed]
         extra = [bucket_seq, bucket_len]
@@ -207,10 +210,13 @@ class Context:
             ptrs.append(ptr)
         outs["call_mut"], p_call = self._out(mem, (max(nnz, 1),), np.int32, "m_call_mut")
         self.set_replay_shape()
-        self._check(self.lib.pcb_merge(self.h, mem, R, int(p.n_buckets), *ins[:9], int(p.mut_rank.shape[0]),
+        if shard_layout is None:
+            shard_layout = int(shard[1]) > 1
+        flags = (_lib.MERGE_PAIRS_SORTED if pairs_sorted else 0) | (_lib.MERGE_SHARD_LAYOUT if shard_layout else 0)
+        self._check(self.lib.pcb_merge(self.h, mem, R, int(p.n_buckets), *ins[:8], nnz, ins[8], int(p.mut_rank.shape[0]),
                                        int(pairs.q.shape[0]), *ins[9:], int(p.max_diff), int(p.min_qual),
                                        float(p.min_jaccard), int(p.min_matches), p_bseq, p_blen, stride,
-                                       int(on_demand_k) if bucket_seq is not None else -1, int(shard[0]), int(shard[1]),
+                                       int(on_demand_k) if bucket_seq is not None else -1, int(shard[0]), int(shard[1]), flags,
                                        *ptrs, p_call))
         out = {k: v[:R] for k, v in outs.items() if k != "call_mut"}
         out["call_mut"] = outs["call_mut"][:nnz]
@@ -262,7 +268,7 @@ class Context:
         rep, p_rep = self._out(mem, (max(R, 1),), np.int32, "c_row_rep") if compact_rows else (None, None)
         flags = (_lib.CLUSTER_FULL_TABLE if full_table else 0) | (_lib.CLUSTER_COMPACT_ROWS if compact_rows else 0)
         self.set_replay_shape()
-        self._check(self.lib.pcb_cluster_reads(self.h, mem, ins[0], ins[1], ins[2], R, stride, *ins[3:],
+        self._check(self.lib.pcb_cluster_reads(self.h, mem, ins[0], ins[1], ins[2], R, stride, *ins[3:8], nnz, ins[8],
                                                int(mut_rank.shape[0]), int(max_diff), int(min_qual),
                                                float(min_jaccard), int(min_matches), flags, p_bor, C.byref(nb), C.byref(ne),
                                                *ptrs, p_call, p_rep))

@@ -303,18 +303,15 @@ int pcb_sort_edges(pcb_ctx *ctx, int mem, int32_t *ei, int32_t *ej, int32_t *ed,
 
 int pcb_merge(pcb_ctx *ctx, int mem, int32_t R, int32_t U, const int32_t *bucket_ptr, const int32_t *bucket_reads,
               const int32_t *lexrank, const int32_t *bc_id, const int32_t *up_id, const int32_t *geno_ptr,
-              const int32_t *geno_mut, const int32_t *geno_q, const int32_t *mut_rank, int32_t n_mut, int64_t n_pairs,
+              const int32_t *geno_mut, const int32_t *geno_q, int64_t nnz, const int32_t *mut_rank, int32_t n_mut, int64_t n_pairs,
               const int32_t *pair_q, const int32_t *pair_r, const int32_t *pair_d, const int32_t *pair_ed,
               int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches,
               const uint8_t *bucket_seq, const int32_t *bucket_len, int32_t stride, int32_t on_demand_k,
-              int32_t shard_rank, int32_t shard_count, int32_t *read_root, int32_t *read_pos, int32_t *row_size, int64_t *row_key,
-              int32_t *row_bc, int32_t *row_up, int64_t *row_call_off, int32_t *row_call_n, int32_t *call_mut) {
+              int32_t shard_rank, int32_t shard_count, int32_t flags, int32_t *read_root, int32_t *read_pos, int32_t *row_size,
+              int64_t *row_key, int32_t *row_bc, int32_t *row_up, int64_t *row_call_off, int32_t *row_call_n, int32_t *call_mut) {
   return guarded(ctx, [&] {
-    if (R < 0 || U < 0 || n_pairs < 0) throw Error(PCB_E_INPUT, "bad shape");
-    int64_t nnz = 0;
-    if (R > 0) {
-      if (mem == PCB_MEM_DEVICE) nnz = read_scalar(ctx, geno_ptr + R); else nnz = geno_ptr[R];
-    }
+    if (R < 0 || U < 0 || n_pairs < 0 || nnz < 0) throw Error(PCB_E_INPUT, "bad shape");
+    if (mem == PCB_MEM_HOST && R > 0 && geno_ptr[R] != nnz) throw Error(PCB_E_INPUT, "nnz is not geno_ptr[R]");
     InArr<int32_t> d_bptr(ctx, mem, bucket_ptr, (size_t)U + 1), d_breads(ctx, mem, bucket_reads, R), d_lex(ctx, mem, lexrank, R),
         d_bc(ctx, mem, bc_id, R), d_up(ctx, mem, up_id, R), d_gptr(ctx, mem, geno_ptr, (size_t)R + 1),
         d_gmut(ctx, mem, geno_mut, nnz), d_gq(ctx, mem, geno_q, nnz), d_rank(ctx, mem, mut_rank, n_mut),
@@ -327,6 +324,8 @@ int pcb_merge(pcb_ctx *ctx, int mem, int32_t R, int32_t U, const int32_t *bucket
                n_pairs, d_pq.p, d_pr.p, d_pd.p, d_pe.p, max_diff, min_qual, min_matches, min_jaccard, shard_rank, shard_count};
     MergeOut out{o_root.p, o_pos.p, o_size.p, o_key.p, o_bc.p, o_up.p, o_calloff.p, o_calln.p, o_call.p};
     in.nnz = nnz;
+    in.pairs_sorted = (flags & PCB_MERGE_PAIRS_SORTED) != 0;
+    in.shard_layout = (flags & PCB_MERGE_SHARD_LAYOUT) != 0;
     PackedBarcodes bc;
     if (bucket_seq && bucket_len && on_demand_k >= 0 && U > 0) {
       InArr<uint8_t> d_bseq(ctx, mem, bucket_seq, (size_t)U * stride);
@@ -345,7 +344,7 @@ int pcb_merge(pcb_ctx *ctx, int mem, int32_t R, int32_t U, const int32_t *bucket
 
 int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *qual, const int32_t *len, int32_t R,
                       int32_t stride, const int32_t *lexrank, const int32_t *up_id, const int32_t *geno_ptr,
-                      const int32_t *geno_mut, const int32_t *geno_q, const int32_t *mut_rank, int32_t n_mut,
+                      const int32_t *geno_mut, const int32_t *geno_q, int64_t nnz, const int32_t *mut_rank, int32_t n_mut,
                       int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches, int32_t flags,
                       int32_t *bucket_of_read, int32_t *n_buckets, int64_t *n_edges, int32_t *read_root,
                       int32_t *read_pos, int32_t *row_size, int64_t *row_key, int32_t *row_bc, int32_t *row_up,
@@ -355,10 +354,7 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
     if (max_diff < 0 || max_diff > 3) throw Error(PCB_E_INPUT, "maxDiff must be between 0 and 3");
     const bool compact = (flags & PCB_CLUSTER_COMPACT_ROWS) != 0;
     if (compact && !row_rep) throw Error(PCB_E_INPUT, "PCB_CLUSTER_COMPACT_ROWS needs row_rep");
-    int64_t nnz = 0;
-    if (R > 0) {
-      if (mem == PCB_MEM_DEVICE) nnz = read_scalar(ctx, geno_ptr + R); else nnz = geno_ptr[R];
-    }
+    if (nnz < 0 || (mem == PCB_MEM_HOST && R > 0 && geno_ptr[R] != nnz)) throw Error(PCB_E_INPUT, "nnz is not geno_ptr[R]");
     size_t cells = (size_t)R * stride;
     (void)qual;   // qualities only feed the per-bucket sums of pcb_bucket; the clustering never reads them
     InArr<uint8_t> d_seq(ctx, mem, seq, cells);
@@ -402,6 +398,8 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
                E, ctx->edges.ei, ctx->edges.ej, ctx->edges.ed, ped.p, max_diff, min_qual, min_matches, min_jaccard, 0, 1};
     if (!full) { in.planes = uniq.planes.p; in.blen = uniq.len.p; in.compute_k = 2 * max_diff; in.wide = uniq.max_len > 32; }
     in.nnz = nnz;
+    in.pairs_sorted = true;            // the pair search delivers q < r, ascending by (q, r)
+    in.bucket_of_read = bor;
     if (!compact) {
       MergeOut out{o_root.p, o_pos.p, o_size.p, o_key.p, o_bc.p, o_up.p, o_calloff.p, o_calln.p, o_call.p};
       merge_dev(ctx, in, out);

@@ -48,6 +48,7 @@ struct pcb_ctx {
   std::string err;
   int64_t stats[PCB_STAT_COUNT] = {0};
   int replay_shape = PCB_REPLAY_AUTO;      // pcb_set_option(PCB_OPT_REPLAY_SHAPE)
+  bool medium_attr_set = false;            // the medium replay kernel's shared-memory opt-in (merge.cu)
   pcb_edges edges;
 };
 
@@ -177,6 +178,9 @@ struct MergeIn {             // device pointers
   const int32_t *blen = nullptr;
   int32_t compute_k = -1, wide = 0;
   int64_t nnz = -1;            // number of genotype entries if the caller already knows it (saves a round trip)
+  bool pairs_sorted = false;   // pair_q < pair_r everywhere and the pairs ascend by (q, r): how the pair search delivers them
+  const int32_t *bucket_of_read = nullptr;   // [R], if the caller has it (it is derived from the CSR otherwise)
+  bool shard_layout = false;   // call regions laid out by component label, identically on every shard
 };
 struct MergeOut {            // device pointers, caller-owned
   int32_t *read_root, *read_pos, *row_size;

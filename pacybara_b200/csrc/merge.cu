@@ -1,25 +1,28 @@
-// merge.cu -- cluster merge on the device (rows a4..a13): preprocessing kernels that turn the
-// bucket-pair list into per-component work, then one thread per connected component replaying
-// the reference's sequential algorithm (merge_core.h).
+// merge.cu -- cluster merge on the device (rows a4..a13): a few streaming kernels that turn the bucket-pair list
+// into per-component work, then the replay of the reference's sequential algorithm, one connected component per
+// warp (merge_small.cuh for components of at most 32 reads, merge_warp.cuh / merge_core.h for the rest).
 //
-//   components    lock-free union-find over the pairs a pass visits (1 <= ed <= maxDiff);
-//                 label = smallest bucket of the component; a component belongs to shard (label mod shard_count)
-//                 and everything below only touches this shard's buckets, reads and pairs
-//   renumbering   buckets are sorted by (component work descending, component label), reads by
-//                 (new bucket, arrival order), and every per-read / per-bucket array the replay touches
-//                 is gathered into that order: a component's working set becomes a handful of
-//                 contiguous cache lines instead of one sector per read scattered over HBM, and
-//                 neighbouring threads (= neighbouring components of similar size) follow similar
-//                 control flow.  The renumbering is an identity relabelling: nothing in the algorithm
-//                 depends on the numeric value of a read or bucket id (string order of read ids comes
-//                 in through `lexrank`, creation keys are mapped back to the old bucket numbers).
-//   adjacency     symmetric (a, nbr, d) sorted by (a, nbr) in the new numbering: the lookup table of :236,:266
-//   visiting      pairs a pass visits, grouped per component by a STABLE sort on (component, ed),
-//                 which keeps the reference's visiting order inside every component
-//   replay        process_component(): seed step, greedy merge, consensus
-//   scatter       outputs back to the caller's read numbering
-// Everything except the replay is HBM-bound streaming; the replay is latency-bound pointer work
-// whose parallelism is the number of components (about 10^5 at cfg 2).
+// Nothing is renumbered or gathered: the replay kernels read the caller's arrays through two small indirections
+// (component -> its buckets, bucket -> its reads) and write the caller's output arrays directly.
+//
+//   components    lock-free union-find over the pairs a pass visits (1 <= ed <= maxDiff); label = smallest bucket of
+//                 the component; a component belongs to shard (label mod shard_count)
+//   grouping      buckets sorted by (not mine, label) -- ONE radix sort over the U bucket labels: comp_buckets
+//                 (ascending bucket id inside a component, the sort is stable) and comp_ptr
+//   adjacency     the pair list itself when the caller's pairs are sorted by (q < r) -- which is how the pair search
+//                 delivers them -- plus row pointers; a sorted copy otherwise.  Every pair is held once, in the row of
+//                 its smaller bucket (MergeCtx::adj_forward); this is the lookup table of :236,:266
+//   visiting      the pairs a pass visits, per component, in the reference's order: pass by pass, rows in the caller's
+//                 order.  Sorted pairs: a count + one walk per component over the rows of its buckets (no sort);
+//                 otherwise a STABLE sort on (component, ed)
+//   tiers         <= 32 reads: component_kernel_small.  33..128 reads: component_kernel_medium -- the generic warp
+//                 replay on a LOCAL copy of the component in shared memory (reads, calls, state, scratch), the
+//                 handful of such components of a library would otherwise be the tail of the step; it runs on a
+//                 second stream beside the small kernel, and takes whatever that kernel declines afterwards.
+//                 Bigger: the generic replay on global state (scratch sized per component).
+//   call regions  a component's rows put their calls into a region as long as its reads' call lists, taken from a
+//                 shared cursor as components come by: the layout of call_mut is not reproducible from run to
+//                 run, the rows (row_call_off / row_call_n / the calls themselves) are.
 #include <cstdlib>
 #include <cstring>
 
@@ -30,9 +33,7 @@
 
 namespace pcb {
 
-constexpr uint32_t WORK_CAP = 1023;     // component work classes used for ordering (10 bits)
-constexpr int HEAVY_READS = SMALL_READS + 1;   // components too big for the one-lane-per-read kernel (they are numbered first)
-
+// ------------------------------------------------------------------------------------------ components
 __device__ __forceinline__ int32_t uf_find(int32_t *parent, int32_t x) {
   for (;;) {
     int32_t p = ((volatile int32_t *)parent)[x];
@@ -62,18 +63,50 @@ __global__ void uf_union_kernel(const int32_t *__restrict__ pq, const int32_t *_
   }
 }
 
-// label[b] = root; work[root] += reads of b
-__global__ void uf_label_kernel(int32_t *parent, const int32_t *__restrict__ bucket_ptr, int32_t U,
-                                int32_t *__restrict__ label, uint32_t *__restrict__ work) {
+// counters: [0] buckets of this shard, [1] components of this shard, [2] medium list, [3] large list, [4] visiting pairs
+// of this shard, [5] components the small kernel declined, [6] declined components too big for the medium kernel
+enum { CNT_BUCKETS = 0, CNT_COMPS, CNT_MEDIUM, CNT_LARGE, CNT_VISITS, CNT_DECLINED, CNT_LATE, CNT_N };
+
+// key = (not mine, label): this shard's components first, buckets of a component together in ascending order
+__global__ void comp_keys_kernel(int32_t *parent, int32_t U, int bbits, int32_t shard_rank, int32_t shard_count,
+                                 int32_t *__restrict__ label, uint64_t *__restrict__ key, uint32_t *__restrict__ val,
+                                 int32_t *__restrict__ counters) {
   int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= U) return;
-  int32_t l = uf_find(parent, b);
-  label[b] = l;
-  atomicAdd(&work[l], (uint32_t)(bucket_ptr[b + 1] - bucket_ptr[b]));
+  const uint32_t l = (uint32_t)uf_find(parent, b);
+  label[b] = (int32_t)l;
+  const bool mine = (int32_t)(l % (uint32_t)shard_count) == shard_rank;
+  key[b] = ((uint64_t)(mine ? 0 : 1) << bbits) | l;
+  val[b] = (uint32_t)b;
+  if (mine) atomicAdd(&counters[CNT_BUCKETS], 1);
 }
 
-// lab_nnz[root] = genotype entries of the whole component: the call region of a component is laid out by its label,
-// which every shard computes identically (so shards can be combined element-wise)
+__global__ void comp_flag_kernel(const uint64_t *__restrict__ key, int32_t U, uint32_t *__restrict__ flag) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= U) flag[i] = (i < U && (i == 0 || key[i] != key[i - 1])) ? 1u : 0u;
+}
+
+// sorted position i: bucket val[i] of component rank[i] (rank = exclusive scan of the head flags; rank[U] = #components)
+__global__ void comp_assign_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ val, const uint32_t *__restrict__ rank,
+                                   int32_t U, int bbits, int32_t *__restrict__ comp_buckets, int32_t *__restrict__ comp_ptr,
+                                   int32_t *__restrict__ comp_of_b, int32_t *__restrict__ counters) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= U) return;
+  const bool head = i == 0 || key[i] != key[i - 1];
+  const bool mine = (key[i] >> bbits) == 0;
+  const int32_t c = (int32_t)rank[i] + (head ? 1 : 0) - 1;
+  const int32_t b = (int32_t)val[i];
+  comp_buckets[i] = b;
+  comp_of_b[b] = mine ? c : -1;
+  if (head) {
+    comp_ptr[c] = i;                             // the first bucket of another shard closes this shard's last component
+    if (mine) atomicAdd(&counters[CNT_COMPS], 1);
+  }
+  if (i == U - 1) comp_ptr[rank[U]] = U;
+}
+
+// PCB_MERGE_SHARD_LAYOUT: lab_nnz[label] = genotype entries of the whole component, so that the call region of a
+// component sits where its label puts it -- which every shard computes identically
 __global__ void label_nnz_kernel(const int32_t *__restrict__ bucket_ptr, const int32_t *__restrict__ bucket_reads,
                                  const int32_t *__restrict__ geno_ptr, const int32_t *__restrict__ label, int32_t U,
                                  uint32_t *__restrict__ lab_nnz) {
@@ -86,69 +119,100 @@ __global__ void label_nnz_kernel(const int32_t *__restrict__ bucket_ptr, const i
   }
   if (nnz) atomicAdd(&lab_nnz[label[b]], nnz);
 }
-
-// counters: [0] buckets of this shard, [1] components of this shard, [2] heavy components of this shard, [3] reads of this shard
-// A component belongs to shard (label mod shard_count); the buckets of other shards sort behind everything and are
-// ignored from here on, so the preprocessing below only touches this shard's part of the library.
-__global__ void comp_keys_kernel(const int32_t *__restrict__ label, const uint32_t *__restrict__ work, int32_t U, int bbits,
-                                 int32_t shard_rank, int32_t shard_count, uint64_t *__restrict__ key, uint32_t *__restrict__ val,
-                                 uint32_t *__restrict__ counters) {
-  int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= U) return;
-  uint32_t l = (uint32_t)label[b];
-  uint32_t w = work[l] < WORK_CAP ? work[l] : WORK_CAP;
-  bool mine = (int32_t)(l % (uint32_t)shard_count) == shard_rank;
-  key[b] = ((uint64_t)(mine ? 0 : 1) << (bbits + 10)) | ((uint64_t)(WORK_CAP - w) << bbits) | l;   // mine first, heavy first
-  val[b] = (uint32_t)b;
-  if (mine) atomicAdd(&counters[0], 1u);
+__global__ void comp_call_off_kernel(const int32_t *__restrict__ comp_ptr, const int32_t *__restrict__ comp_buckets,
+                                     const int32_t *__restrict__ counters, const uint32_t *__restrict__ lab_off, int64_t *__restrict__ call_off) {
+  const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < counters[1]) call_off[c] = (int64_t)lab_off[comp_buckets[comp_ptr[c]]];      // a component's label is its smallest bucket
 }
 
-__global__ void comp_flag_kernel(const uint64_t *__restrict__ key, int32_t U, uint32_t *__restrict__ flag) {
-  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < U) flag[i] = (i == 0 || key[i] != key[i - 1]) ? 1u : 0u;
+// ------------------------------------------------------------------------------------------ adjacency
+// row pointers of pairs sorted by q: ptr[b] = first pair with q >= b
+__global__ void row_ptr_kernel(const int32_t *__restrict__ q, int64_t n, int32_t U, int32_t *__restrict__ ptr) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p > n) return;
+  const int32_t lo = p == 0 ? 0 : q[p - 1] + 1, hi = p == n ? U : q[p];
+  for (int32_t b = lo; b <= hi; b++) ptr[b] = (int32_t)p;
 }
 
-// sorted position i = new bucket id (this shard's buckets come first).  rank = exclusive scan of the head flags.
-__global__ void comp_assign_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ val, const uint32_t *__restrict__ rank,
-                                   const int32_t *__restrict__ bucket_ptr, int32_t U, int32_t n_comp,
-                                   int32_t *__restrict__ old_of_new_b, int32_t *__restrict__ new_of_old_b,
-                                   int32_t *__restrict__ comp_ptr, int32_t *__restrict__ comp_of_new_b, uint32_t *__restrict__ nb_cnt,
-                                   int32_t *__restrict__ comp_label, int bbits, uint32_t heavy_reads, uint32_t *__restrict__ counters) {
-  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= U) return;
-  const bool head = i == 0 || key[i] != key[i - 1];
-  const bool mine = (key[i] >> (bbits + 10)) == 0;
-  const int32_t c = (int32_t)rank[i] + (head ? 1 : 0) - 1;
-  const int32_t b = (int32_t)val[i];
-  if (head) comp_ptr[c] = i;                     // the first bucket of another shard closes this shard's last component
-  if (mine) {
-    old_of_new_b[i] = b;
-    new_of_old_b[b] = i;
-    comp_of_new_b[i] = c;
-    nb_cnt[i] = (uint32_t)(bucket_ptr[b + 1] - bucket_ptr[b]);
-    if (head) {
-      comp_label[c] = (int32_t)(key[i] & ((1ull << bbits) - 1ull));
-      atomicAdd(&counters[1], 1u);
-      if (WORK_CAP - (uint32_t)((key[i] >> bbits) & WORK_CAP) >= heavy_reads) atomicAdd(&counters[2], 1u);   // heaviest first
+__global__ void pair_keys_kernel(const int32_t *__restrict__ pq, const int32_t *__restrict__ pr, int64_t n, int shift,
+                                 uint64_t *__restrict__ key, uint32_t *__restrict__ val) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const uint32_t a = (uint32_t)pq[p], b = (uint32_t)pr[p];
+  key[p] = a < b ? ((uint64_t)a << shift) | b : ((uint64_t)b << shift) | a;
+  val[p] = (uint32_t)p;
+}
+__global__ void pair_unpack_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ order, const int32_t *__restrict__ pd,
+                                   int64_t n, int shift, int32_t *__restrict__ sq, int32_t *__restrict__ sr, int32_t *__restrict__ sd) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  sq[i] = (int32_t)(key[i] >> shift);
+  sr[i] = (int32_t)(key[i] & ((1ull << shift) - 1ull));
+  sd[i] = pd[order[i]];
+}
+
+// ------------------------------------------------------------------------------------------ visiting lists
+// cnt[4 * comp + ed] = pairs pass `ed` visits in this shard's component comp
+__global__ void visit_count_kernel(const int32_t *__restrict__ pq, const int32_t *__restrict__ ped, int64_t n, int32_t max_diff,
+                                   const int32_t *__restrict__ comp_of_b, uint32_t *__restrict__ cnt, int32_t *__restrict__ counters) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  const int32_t ed = ped[p];
+  if (ed < 1 || ed > max_diff) return;
+  const int32_t c = comp_of_b[pq[p]];
+  if (c < 0) return;
+  atomicAdd(&cnt[4 * (size_t)c + ed], 1u);
+  atomicAdd(&counters[CNT_VISITS], 1);
+}
+
+// Pairs sorted by (q, r): the rows a component's passes visit, in order, are the visiting pairs found by walking the
+// adjacency rows of its buckets in ascending bucket order -- once per pass.  One thread per component.
+__global__ void visit_walk_kernel(const int32_t *__restrict__ comp_ptr, const int32_t *__restrict__ comp_buckets, const int32_t *__restrict__ counters,
+                                  const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ pr, const int32_t *__restrict__ ped,
+                                  int32_t max_diff, const uint32_t *__restrict__ off, int32_t *__restrict__ cpair_ptr,
+                                  int32_t *__restrict__ cq, int32_t *__restrict__ cr, int32_t *__restrict__ ce) {
+  const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t n_comp = counters[CNT_COMPS];
+  if (c > n_comp) return;
+  cpair_ptr[c] = (int32_t)off[4 * (size_t)c];
+  if (c == n_comp || off[4 * (size_t)c] == off[4 * (size_t)c + 4]) return;
+  for (int32_t ed = 1; ed <= max_diff; ed++) {
+    uint32_t at = off[4 * (size_t)c + ed];
+    if (at == off[4 * (size_t)c + ed + 1]) continue;
+    for (int32_t bi = comp_ptr[c]; bi < comp_ptr[c + 1]; bi++) {
+      const int32_t a = comp_buckets[bi];
+      for (int32_t e = row_ptr[a]; e < row_ptr[a + 1]; e++)
+        if (ped[e] == ed) { cq[at] = a; cr[at] = pr[e]; ce[at] = ed; at++; }
     }
-  } else {
-    new_of_old_b[b] = -1;
-    nb_cnt[i] = 0;
   }
-  if (i == U - 1) { comp_ptr[n_comp] = U; nb_cnt[U] = 0; }
 }
 
-__global__ void shard_reads_kernel(const uint32_t *__restrict__ nb_ptr, uint32_t *__restrict__ counters) {
-  counters[3] = nb_ptr[counters[0]];
+// pairs in arbitrary order (pcb_merge on a caller's pair list): stable sort on (component, ed)
+__global__ void cpair_keys_kernel(const int32_t *__restrict__ pq, const int32_t *__restrict__ ped, int64_t n_pairs,
+                                  const int32_t *__restrict__ comp_of_b, int32_t U, int32_t max_diff,
+                                  uint64_t *__restrict__ key, uint32_t *__restrict__ val) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  const int32_t ed = ped[p];
+  const int32_t c = (ed >= 1 && ed <= max_diff) ? comp_of_b[pq[p]] : -1;
+  key[p] = c >= 0 ? (((uint64_t)(uint32_t)c << 2) | (uint64_t)ed) : (((uint64_t)(uint32_t)U << 2) | 3ull);      // others sort behind
+  val[p] = (uint32_t)p;
+}
+__global__ void cpair_gather_kernel(const uint32_t *__restrict__ order, const int32_t *__restrict__ counters, const int32_t *__restrict__ pq,
+                                    const int32_t *__restrict__ pr, const int32_t *__restrict__ ped,
+                                    int32_t *__restrict__ cq, int32_t *__restrict__ cr, int32_t *__restrict__ ce, int64_t n_pairs) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pairs || i >= (int64_t)counters[CNT_VISITS]) return;
+  const uint32_t p = order[i];
+  cq[i] = pq[p]; cr[i] = pr[p]; ce[i] = ped[p];
+}
+__global__ void cpair_ptr_kernel(const uint32_t *__restrict__ off, const int32_t *__restrict__ counters, int32_t *__restrict__ cpair_ptr) {
+  const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c <= counters[CNT_COMPS]) cpair_ptr[c] = (int32_t)off[4 * (size_t)c];
 }
 
-// one thread per position x of the caller's bucket_reads: where does that read go?
-__global__ void read_renumber_kernel(const int32_t *__restrict__ bucket_ptr, const int32_t *__restrict__ bucket_reads, int32_t R, int32_t U,
-                                     const int32_t *__restrict__ new_of_old_b, const uint32_t *__restrict__ nb_ptr,
-                                     const int32_t *__restrict__ lexrank, const int32_t *__restrict__ bc_id, const int32_t *__restrict__ up_id,
-                                     const int32_t *__restrict__ geno_ptr,
-                                     int32_t *__restrict__ old_of_new_r, int32_t *__restrict__ n_bor, int32_t *__restrict__ n_lex,
-                                     int32_t *__restrict__ n_bc, int32_t *__restrict__ n_up, uint32_t *__restrict__ n_gcnt) {
+__global__ void bucket_of_read_kernel(const int32_t *__restrict__ bucket_ptr, const int32_t *__restrict__ bucket_reads, int32_t R, int32_t U,
+                                      int32_t *__restrict__ bor) {
   int32_t x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= R) return;
   int32_t lo = 0, hi = U;                       // last b with bucket_ptr[b] <= x
@@ -156,250 +220,283 @@ __global__ void read_renumber_kernel(const int32_t *__restrict__ bucket_ptr, con
     int32_t mid = (lo + hi) >> 1;
     if (bucket_ptr[mid] <= x) lo = mid; else hi = mid;
   }
-  int32_t nb = new_of_old_b[lo];
-  if (nb < 0) return;                            // a bucket of another shard
-  int32_t nr = (int32_t)nb_ptr[nb] + (x - bucket_ptr[lo]);
-  int32_t r = bucket_reads[x];
-  old_of_new_r[nr] = r;
-  n_bor[nr] = nb;
-  n_lex[nr] = lexrank[r];
-  n_bc[nr] = bc_id[r];
-  if (up_id) n_up[nr] = up_id[r];
-  n_gcnt[nr] = (uint32_t)(geno_ptr[r + 1] - geno_ptr[r]);
+  bor[bucket_reads[x]] = lo;
 }
 
-__global__ void geno_gather_kernel(const int32_t *__restrict__ old_of_new_r, const int32_t *__restrict__ geno_ptr,
-                                   const int32_t *__restrict__ geno_mut, const int32_t *__restrict__ geno_q, int32_t R,
-                                   const uint32_t *__restrict__ n_gptr, int32_t *__restrict__ n_gmut, int32_t *__restrict__ n_gq,
-                                   const uint32_t *__restrict__ counters) {
-  int32_t nr = blockIdx.x * blockDim.x + threadIdx.x;
-  if (nr >= R || (uint32_t)nr >= counters[3]) return;
-  int32_t r = old_of_new_r[nr];
-  int32_t src = geno_ptr[r], n = geno_ptr[r + 1] - src;
-  uint32_t dst = n_gptr[nr];
-  for (int32_t e = 0; e < n; e++) { n_gmut[dst + e] = geno_mut[src + e]; n_gq[dst + e] = geno_q[src + e]; }
+// ------------------------------------------------------------------------------------------ tiers
+constexpr int MED_READS = 128, MED_BUCKETS = 128, MED_CALLS = 256, MED_PAIRS = 256;
+
+// Components of more than 32 reads: medium if a local copy fits the medium kernel's shared memory, else large.
+// force_large: every component goes on the large list (the PCB_REPLAY_THREAD / PCB_REPLAY_WARP shapes).
+__global__ void classify_kernel(MergeCtx c, int32_t force_large, int32_t *__restrict__ counters, int32_t *__restrict__ medium,
+                                int32_t *__restrict__ large) {
+  const int32_t comp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (comp >= counters[CNT_COMPS]) return;
+  const int32_t b_lo = c.comp_ptr[comp], b_hi = c.comp_ptr[comp + 1];
+  int32_t reads = 0;
+  if (!force_large) {
+    for (int32_t bi = b_lo; bi < b_hi && reads <= MED_READS; bi++) {
+      const int32_t b = c.comp_buckets[bi];
+      reads += c.bucket_ptr[b + 1] - c.bucket_ptr[b];
+    }
+    if (reads <= SMALL_READS) return;
+  }
+  bool fits = !force_large && reads <= MED_READS && b_hi - b_lo <= MED_BUCKETS &&
+              c.cpair_ptr[comp + 1] - c.cpair_ptr[comp] <= MED_PAIRS;
+  if (fits) {
+    int32_t nnz = 0;
+    for (int32_t bi = b_lo; bi < b_hi && nnz <= MED_CALLS; bi++) {
+      const int32_t b = c.comp_buckets[bi];
+      for (int32_t x = c.bucket_ptr[b]; x < c.bucket_ptr[b + 1]; x++) {
+        const int32_t r = c.bucket_reads[x];
+        nnz += c.geno_ptr[r + 1] - c.geno_ptr[r];
+      }
+    }
+    fits = nnz <= MED_CALLS;
+  }
+  if (fits) medium[atomicAdd(&counters[CNT_MEDIUM], 1)] = comp;
+  else large[atomicAdd(&counters[CNT_LARGE], 1)] = comp;
 }
 
-__global__ void planes_gather_kernel(const int32_t *__restrict__ old_of_new_b, const ulonglong2 *__restrict__ planes,
-                                     const int32_t *__restrict__ blen, int32_t U, ulonglong2 *__restrict__ n_planes,
-                                     int32_t *__restrict__ n_blen, const uint32_t *__restrict__ counters) {
-  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= U || (uint32_t)i >= counters[0]) return;
-  n_planes[i] = planes[old_of_new_b[i]];
-  n_blen[i] = blen[old_of_new_b[i]];
-}
-
-// the pairs whose two buckets belong to this shard, in their original order, in the new bucket numbering
-__global__ void pair_flag_kernel(const int32_t *__restrict__ pq, const int32_t *__restrict__ pr, int64_t n_pairs,
-                                 const int32_t *__restrict__ new_of_old_b, uint32_t *__restrict__ flag) {
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < n_pairs) flag[p] = (new_of_old_b[pq[p]] >= 0 && new_of_old_b[pr[p]] >= 0) ? 1u : 0u;
-}
-__global__ void pair_compact_kernel(const int32_t *__restrict__ pq, const int32_t *__restrict__ pr, const int32_t *__restrict__ pd,
-                                    const int32_t *__restrict__ ped, int64_t n_pairs, const int32_t *__restrict__ new_of_old_b,
-                                    const uint32_t *__restrict__ pos, int32_t *__restrict__ mq, int32_t *__restrict__ mr,
-                                    int32_t *__restrict__ md, int32_t *__restrict__ me) {
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pairs) return;
-  int32_t a = new_of_old_b[pq[p]], b = new_of_old_b[pr[p]];
-  if (a < 0 || b < 0) return;
-  uint32_t at = pos[p];
-  mq[at] = a; mr[at] = b; md[at] = pd[p]; me[at] = ped[p];
-}
-
-__global__ void adj_keys_kernel(const int32_t *__restrict__ mq, const int32_t *__restrict__ mr, const int32_t *__restrict__ md,
-                                int64_t n_pairs, int shift, uint64_t *__restrict__ key, uint32_t *__restrict__ val,
-                                uint32_t *__restrict__ adj_cnt) {
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pairs) return;
-  uint32_t a = (uint32_t)mq[p], b = (uint32_t)mr[p];
-  key[2 * p] = ((uint64_t)a << shift) | b;
-  key[2 * p + 1] = ((uint64_t)b << shift) | a;
-  val[2 * p] = val[2 * p + 1] = (uint32_t)md[p];
-  atomicAdd(&adj_cnt[a], 1u);
-  atomicAdd(&adj_cnt[b], 1u);
-}
-
-__global__ void adj_unpack_kernel(const uint64_t *__restrict__ key, const uint32_t *__restrict__ val, int64_t n, int shift,
-                                  int32_t *__restrict__ nbr, int32_t *__restrict__ d) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  nbr[i] = (int32_t)(key[i] & ((1ull << shift) - 1ull));
-  d[i] = (int32_t)val[i];
-}
-
-__global__ void cpair_keys_kernel(const int32_t *__restrict__ mq, const int32_t *__restrict__ me, int64_t n_pairs,
-                                  const int32_t *__restrict__ comp_of_new_b, int32_t n_comp, int32_t max_diff,
-                                  uint64_t *__restrict__ key, uint32_t *__restrict__ val, uint32_t *__restrict__ cnt) {
-  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= n_pairs) return;
-  int32_t ed = me[p];
-  bool visit = ed >= 1 && ed <= max_diff;
-  uint32_t c = visit ? (uint32_t)comp_of_new_b[mq[p]] : (uint32_t)n_comp;
-  key[p] = ((uint64_t)c << 2) | (uint64_t)(visit ? ed : 0);
-  val[p] = (uint32_t)p;
-  if (visit) atomicAdd(&cnt[c], 1u);
-}
-
-__global__ void cpair_gather_kernel(const uint32_t *__restrict__ order, int64_t n, const int32_t *__restrict__ mq,
-                                    const int32_t *__restrict__ mr, const int32_t *__restrict__ me,
-                                    int32_t *__restrict__ cq, int32_t *__restrict__ cr, int32_t *__restrict__ ce) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  uint32_t p = order[i];
-  cq[i] = mq[p]; cr[i] = mr[p]; ce[i] = me[p];
-}
-
-// components are contiguous in the new numbering: sizes come straight from the prefix arrays; the call region of a
-// component sits where its label puts it (label_nnz_kernel)
-__global__ void comp_scratch_kernel(const int32_t *__restrict__ comp_ptr, const uint32_t *__restrict__ nb_ptr,
-                                    const uint32_t *__restrict__ n_gptr, int32_t n_comp, const int32_t *__restrict__ comp_label,
-                                    const uint32_t *__restrict__ lab_call_off, int32_t *__restrict__ slot_cap,
-                                    int64_t *__restrict__ slot_sz, int64_t *__restrict__ list_sz, int64_t *__restrict__ call_off) {
-  int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c > n_comp) return;
-  if (c == n_comp) { slot_sz[c] = list_sz[c] = 0; call_off[c] = 0; return; }
-  uint32_t r_lo = nb_ptr[comp_ptr[c]], r_hi = nb_ptr[comp_ptr[c + 1]];
-  unsigned long long reads = r_hi - r_lo, nnz = n_gptr[r_hi] - n_gptr[r_lo];
+// scratch of the large components (one thread each): table capacity, list length
+__global__ void large_scratch_kernel(MergeCtx c, const int32_t *__restrict__ list, int32_t n, int32_t *__restrict__ slot_cap,
+                                     int64_t *__restrict__ slot_sz, int64_t *__restrict__ list_sz) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  if (i == n) { slot_sz[i] = 0; list_sz[i] = 0; return; }
+  const int32_t comp = list[i];
+  unsigned long long reads = 0, nnz = 0;
+  for (int32_t bi = c.comp_ptr[comp]; bi < c.comp_ptr[comp + 1]; bi++) {
+    const int32_t b = c.comp_buckets[bi];
+    reads += (unsigned long long)(c.bucket_ptr[b + 1] - c.bucket_ptr[b]);
+    for (int32_t x = c.bucket_ptr[b]; x < c.bucket_ptr[b + 1]; x++) {
+      const int32_t r = c.bucket_reads[x];
+      nnz += (unsigned long long)(c.geno_ptr[r + 1] - c.geno_ptr[r]);
+    }
+  }
   unsigned long long need = 2ull * (reads > nnz ? reads : nnz);
   if (need < 2) need = 2;
   unsigned long long cap = 2;
   while (cap < need) cap <<= 1;
-  slot_cap[c] = (int32_t)cap;
-  slot_sz[c] = (int64_t)cap;
-  list_sz[c] = (int64_t)(2ull * (reads + nnz) + 8);      // 4 counters, touched list, run list (merge_warp.cuh)
-  call_off[c] = (int64_t)lab_call_off[comp_label[c]];
+  slot_cap[i] = (int32_t)cap;
+  slot_sz[i] = (int64_t)cap;
+  list_sz[i] = (int64_t)(2ull * (reads + nnz) + 8);      // 4 counters, touched list, run list (merge_warp.cuh)
 }
 
-// Two launch shapes for the replay (merge_core.h / merge_warp.cuh):
-//  * component_kernel_thread: one THREAD per component running the host-testable
-//    process_component().  Divergent lanes serialise, so only every (32 / per_warp)-th lane is used.
-//    Components are numbered heaviest first, so the long ones start first.
-//  * component_kernel_warp: one WARP per component, uniform control flow, lanes share the order-independent
-//    work (merge_warp.cuh), mutable state of small components in shared memory.  Instruction-fetch bound
-//    (5.3 k SASS instructions, no_instruction is the top stall in profiles/r01f), so it loses to the thread
-//    kernel on the 10-read components of cfg 2 and wins wherever components carry more work.
-// merge_dev() picks by mean bucket size; PCB_REPLAY=thread|warp overrides.
-constexpr int COMP_BLOCK = 128;
-
-// Mutable working set of one small component in shared memory: cluster lists, union-find, scratch table,
-// lists.  Every read-modify-write of the replay then costs a shared-memory round trip (~30 cycles) instead
-// of an L2 one; at one component per warp this fits at full occupancy (8 blocks x 4 warps x 3.6 KB per SM).
-#ifndef PCB_SM_READS
-#define PCB_SM_READS 32
-#endif
-constexpr int SM_READS = PCB_SM_READS;
-constexpr int SM_SLOTS = 2 * SM_READS;
-static_assert((SM_SLOTS & (SM_SLOTS - 1)) == 0, "the scratch table size must be a power of two");
-struct __align__(16) CompSmem {
-  GenoSlot slots[SM_SLOTS];
-  int64_t sl_key[SM_READS];
-  int32_t lists[8 + 4 * SM_READS];
-  int32_t rd_slot[SM_READS], rd_next[SM_READS], sl_parent[SM_READS], sl_head[SM_READS], sl_tail[SM_READS], sl_size[SM_READS];
-};
-
-__device__ __forceinline__ void replay_component_warp(const MergeCtx &c, int32_t comp, int lane, CompSmem *sm) {
-  const int32_t r_lo = c.bucket_ptr[c.comp_ptr[comp]];
-  const int32_t reads = c.bucket_ptr[c.comp_ptr[comp + 1]] - r_lo;
-  const int32_t nnz = c.geno_ptr[r_lo + reads] - c.geno_ptr[r_lo];
-  MergeState st = global_state(c, comp);
-  if (reads <= SM_READS && nnz <= SM_READS) {
-    for (int32_t i = lane; i < SM_SLOTS; i += 32) { GenoSlot z; z.key = 0; z.obs1 = z.obs2 = z.pad = 0; z.sum1 = z.sum2 = 0; sm->slots[i] = z; }
-    for (int32_t i = lane; i < reads; i += 32) { sm->rd_slot[i] = -1; sm->rd_next[i] = -1; }
-    __syncwarp();
-    st.r0 = r_lo;
-    st.rd_slot = sm->rd_slot; st.rd_next = sm->rd_next; st.sl_parent = sm->sl_parent; st.sl_head = sm->sl_head;
-    st.sl_tail = sm->sl_tail; st.sl_size = sm->sl_size; st.sl_key = sm->sl_key;
-    st.slots = sm->slots; st.slot_mask = SM_SLOTS - 1;
-    st.lists = sm->lists; st.list_cap = 2 * SM_READS;
-  }
-  process_component_warp(c, st, comp, lane);        // one call site: the same code runs on either memory
-}
-
-__global__ void __launch_bounds__(COMP_BLOCK) component_kernel_warp(MergeCtx c, int32_t comp_lo, int32_t n_comp) {
-  __shared__ CompSmem sm_all[COMP_BLOCK / 32];
-  const int32_t comp = comp_lo + (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-  if (comp >= n_comp) return;
-  replay_component_warp(c, comp, threadIdx.x & 31, &sm_all[threadIdx.x >> 5]);
-}
-
-// the components the small-component kernel declined (list filled on the device, its length known only there):
-// a fixed grid of warps walks the list
-__global__ void __launch_bounds__(COMP_BLOCK) component_kernel_warp_list(MergeCtx c, const int32_t *__restrict__ list,
-                                                                         const int32_t *__restrict__ n_list) {
-  __shared__ CompSmem sm_all[COMP_BLOCK / 32];
-  const int32_t n = *n_list;
-  const int32_t n_warps = (int32_t)(gridDim.x * (blockDim.x >> 5));
-  for (int32_t i = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5); i < n; i += n_warps) {
-    replay_component_warp(c, list[i], threadIdx.x & 31, &sm_all[threadIdx.x >> 5]);
-    __syncwarp();
-  }
-}
-
-// One warp per component of at most 32 reads, one lane per read (merge_small.cuh).  A component it is not
-// eligible for (more than 32 distinct mutations, huge qualities) goes on the list for the generic kernel.
+// ------------------------------------------------------------------------------------------ replay kernels
 constexpr int SMALL_BLOCK = 128;
-__global__ void __launch_bounds__(SMALL_BLOCK) component_kernel_small(MergeCtx c, int32_t comp_lo, int32_t n_comp,
-                                                                      int32_t *__restrict__ declined, int32_t *__restrict__ n_declined) {
+// One warp per component of at most 32 reads, one lane per read (merge_small.cuh).  A component it is not eligible
+// for (more than 32 live mutations, huge qualities) goes on the declined list -- or, when a local copy would not fit
+// the medium kernel either, on the late list the host looks at after the step.
+__global__ void __launch_bounds__(SMALL_BLOCK) component_kernel_small(MergeCtx c, int32_t n_comp, int32_t *__restrict__ counters,
+                                                                      int32_t *__restrict__ declined, int32_t *__restrict__ late) {
   __shared__ SmallSmem sm_all[SMALL_BLOCK / 32];
-  const int32_t comp = comp_lo + (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  const int32_t comp = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   if (comp >= n_comp) return;
   const int lane = threadIdx.x & 31;
-  if (process_component_small(c, comp, lane, &sm_all[threadIdx.x >> 5]) != 0 && lane == 0) declined[atomicAdd(n_declined, 1)] = comp;
+  const int rc = process_component_small(c, comp, lane, &sm_all[threadIdx.x >> 5], MED_CALLS, MED_PAIRS);
+  if (lane == 0 && rc == 1) declined[atomicAdd(&counters[CNT_DECLINED], 1)] = comp;
+  if (lane == 0 && rc == 2) late[atomicAdd(&counters[CNT_LATE], 1)] = comp;
 }
 
-// Block size of the thread kernels: warps of one block finish at very different times, and a block keeps its
-// registers until its slowest warp is done.
-#ifndef PCB_THREAD_BLOCK
-#define PCB_THREAD_BLOCK 128
-#endif
-constexpr int THREAD_BLOCK = PCB_THREAD_BLOCK;
+// The generic warp replay (merge_warp.cuh) on a LOCAL copy of one component: reads, calls, buckets and visiting pairs
+// are numbered 0.. inside the component and live in shared memory together with the cluster state and the scratch
+// table, so the pointer chasing of the replay costs shared-memory round trips; rows are written out through the map
+// back to the caller's read numbers.  One warp per block.
+struct __align__(16) MediumSmem {
+  GenoSlot slots[2 * MED_CALLS];
+  int64_t sl_key[MED_READS], o_key[MED_READS], o_calloff[MED_READS];
+  int32_t lists[8 + 2 * (MED_READS + MED_CALLS)];
+  int32_t rd_slot[MED_READS], rd_next[MED_READS], sl_parent[MED_READS], sl_head[MED_READS], sl_tail[MED_READS], sl_size[MED_READS];
+  int32_t rid[MED_READS], lex[MED_READS], bc[MED_READS], up[MED_READS], bor[MED_READS], gptr[MED_READS + 1];
+  int32_t gmut[MED_CALLS], gq[MED_CALLS];
+  int32_t bptr[MED_BUCKETS + 1], gid[MED_BUCKETS];
+  int32_t cq[MED_PAIRS], cr[MED_PAIRS], ce[MED_PAIRS];
+  int32_t o_root[MED_READS], o_pos[MED_READS], o_size[MED_READS], o_bc[MED_READS], o_up[MED_READS], o_calln[MED_READS];
+  int32_t comp_ptr[2], cpair_ptr[2];
+  int64_t call_off[1];
+};
+
+__global__ void __launch_bounds__(32) component_kernel_medium(MergeCtx c, const int32_t *__restrict__ list, const int32_t *__restrict__ n_list) {
+  extern __shared__ __align__(16) unsigned char medium_raw[];
+  MediumSmem *sm = (MediumSmem *)medium_raw;
+  const int lane = threadIdx.x;
+  const int32_t n = *n_list;
+  for (int32_t it = (int32_t)blockIdx.x; it < n; it += (int32_t)gridDim.x) {
+    const int32_t comp = list[it];
+    const int32_t b_lo = c.comp_ptr[comp], B = c.comp_ptr[comp + 1] - b_lo;
+    // buckets and reads
+    int32_t n_reads = 0;
+    for (int32_t bi = 0; bi < B; bi++) {                      // (B <= 128: a short uniform loop)
+      const int32_t b = c.comp_buckets[b_lo + bi];
+      const int32_t x0 = c.bucket_ptr[b], sz = c.bucket_ptr[b + 1] - x0;
+      if (lane == 0) { sm->bptr[bi] = n_reads; sm->gid[bi] = b; }
+      for (int32_t k = lane; k < sz; k += 32) {
+        const int32_t r = c.bucket_reads[x0 + k], i = n_reads + k;
+        sm->rid[i] = r; sm->lex[i] = c.lexrank[r]; sm->bc[i] = c.bc_id[r]; sm->up[i] = c.up_id ? c.up_id[r] : 0; sm->bor[i] = bi;
+        sm->rd_slot[i] = -1; sm->rd_next[i] = -1;
+        sm->o_size[i] = PCB_FILL; sm->o_key[i] = INT64_MIN; sm->o_bc[i] = PCB_FILL; sm->o_up[i] = PCB_FILL;
+        sm->o_calloff[i] = INT64_MIN; sm->o_calln[i] = PCB_FILL;
+      }
+      n_reads += sz;
+    }
+    if (lane == 0) { sm->bptr[B] = n_reads; sm->comp_ptr[0] = 0; sm->comp_ptr[1] = B; }
+    __syncwarp();
+    // calls: prefix of the per-read counts, then the entries
+    int32_t run = 0;
+    for (int32_t i0 = 0; i0 < n_reads; i0 += 32) {
+      const int32_t i = i0 + lane;
+      int32_t cnt = 0;
+      if (i < n_reads) { const int32_t r = sm->rid[i]; cnt = c.geno_ptr[r + 1] - c.geno_ptr[r]; }
+      int32_t inc = cnt;
+      for (int o = 1; o < 32; o <<= 1) { const int32_t t = __shfl_up_sync(PCB_FULL, inc, o); if (lane >= o) inc += t; }
+      if (i < n_reads) sm->gptr[i] = run + inc - cnt;
+      run += __shfl_sync(PCB_FULL, inc, 31);
+    }
+    if (lane == 0) sm->gptr[n_reads] = run;
+    __syncwarp();
+    for (int32_t i = 0; i < n_reads; i++) {
+      const int32_t r = sm->rid[i], g0 = c.geno_ptr[r], cnt = sm->gptr[i + 1] - sm->gptr[i];
+      for (int32_t e = lane; e < cnt; e += 32) { sm->gmut[sm->gptr[i] + e] = c.geno_mut[g0 + e]; sm->gq[sm->gptr[i] + e] = c.geno_q[g0 + e]; }
+    }
+    // visiting pairs in local bucket numbers
+    const int32_t p_lo = c.cpair_ptr[comp], P = c.cpair_ptr[comp + 1] - p_lo;
+    for (int32_t p = lane; p < P; p += 32) {
+      const int32_t ga = c.cpair_q[p_lo + p], gb = c.cpair_r[p_lo + p];
+      int32_t la = 0, lb = 0;
+      for (int32_t bi = 0; bi < B; bi++) { if (sm->gid[bi] == ga) la = bi; if (sm->gid[bi] == gb) lb = bi; }
+      sm->cq[p] = la; sm->cr[p] = lb; sm->ce[p] = c.cpair_ed[p_lo + p];
+    }
+    for (int32_t i = lane; i < 2 * MED_CALLS; i += 32) { GenoSlot z; z.key = 0; z.obs1 = z.obs2 = z.pad = 0; z.sum1 = z.sum2 = 0; sm->slots[i] = z; }
+    if (lane == 0) {
+      sm->cpair_ptr[0] = 0; sm->cpair_ptr[1] = P;
+      sm->call_off[0] = (int64_t)atomicAdd((unsigned long long *)c.call_cursor, (unsigned long long)run);
+    }
+    __syncwarp();
+    MergeCtx lc = c;
+    lc.bucket_ptr = sm->bptr; lc.bucket_reads = nullptr; lc.bucket_of_read = sm->bor; lc.lexrank = sm->lex; lc.bc_id = sm->bc;
+    lc.up_id = c.up_id ? sm->up : nullptr;
+    lc.geno_ptr = sm->gptr; lc.geno_mut = sm->gmut; lc.geno_q = sm->gq;
+    lc.comp_ptr = sm->comp_ptr; lc.comp_buckets = nullptr;
+    lc.cpair_ptr = sm->cpair_ptr; lc.cpair_q = sm->cq; lc.cpair_r = sm->cr; lc.cpair_ed = sm->ce;
+    lc.call_off = sm->call_off; lc.bucket_gid = sm->gid;
+    lc.read_root = sm->o_root; lc.read_pos = sm->o_pos; lc.row_size = sm->o_size; lc.row_key = sm->o_key;
+    lc.row_bc = sm->o_bc; lc.row_up = sm->o_up; lc.row_call_off = sm->o_calloff; lc.row_call_n = sm->o_calln;
+    MergeState st;
+    st.r0 = 0;
+    st.rd_slot = sm->rd_slot; st.rd_next = sm->rd_next; st.sl_parent = sm->sl_parent; st.sl_head = sm->sl_head;
+    st.sl_tail = sm->sl_tail; st.sl_size = sm->sl_size; st.sl_key = sm->sl_key;
+    st.slots = sm->slots; st.slot_mask = 2 * MED_CALLS - 1;
+    st.lists = sm->lists; st.list_cap = MED_READS + MED_CALLS;
+    process_component_warp(lc, st, 0, lane);
+    __syncwarp();
+    // rows out, through the map back to the caller's numbering (creation keys name local buckets)
+    for (int32_t i = lane; i < n_reads; i += 32) {
+      const int32_t r = sm->rid[i];
+      c.read_root[r] = sm->rid[sm->o_root[i]];
+      c.read_pos[r] = sm->o_pos[i];
+      c.row_size[r] = sm->o_size[i];
+      int64_t key = sm->o_key[i];
+      if (key >= 0) key = ((int64_t)sm->gid[(int32_t)(key >> 32)] << 32) | (key & 0xFFFFFFFFll);
+      c.row_key[r] = key;
+      c.row_bc[r] = sm->o_bc[i]; c.row_up[r] = sm->o_up[i];
+      c.row_call_off[r] = sm->o_calloff[i]; c.row_call_n[r] = sm->o_calln[i];
+    }
+    __syncwarp();
+  }
+}
+
+// scratch of large component i of a list (global memory)
+struct LargeScratch {
+  const int32_t *list;
+  const int32_t *slot_cap;
+  const int64_t *slot_off, *list_off;
+};
+__device__ __forceinline__ MergeState large_state(const MergeCtx &c, const LargeScratch &s, int32_t i) {
+  MergeState st;
+  st.r0 = 0;
+  st.rd_slot = c.rd_slot; st.rd_next = c.rd_next; st.sl_parent = c.sl_parent; st.sl_head = c.sl_head;
+  st.sl_tail = c.sl_tail; st.sl_size = c.sl_size; st.sl_key = c.sl_key;
+  st.slots = c.slots + s.slot_off[i];
+  st.slot_mask = s.slot_cap[i] - 1;
+  st.lists = c.lists + s.list_off[i];
+  st.list_cap = (s.list_off[i + 1] - s.list_off[i]) / 2 - 4;     // region = 8 + 2 * list_cap ints
+  return st;
+}
+
+constexpr int COMP_BLOCK = 128;
+// the generic warp replay on global state, the caller's numbering: one warp per listed component
+__global__ void __launch_bounds__(COMP_BLOCK) component_kernel_large(MergeCtx c, LargeScratch s, int32_t n) {
+  const int32_t i = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (i >= n) return;
+  process_component_warp(c, large_state(c, s, i), s.list[i], threadIdx.x & 31);
+}
+
+// PCB_REPLAY_THREAD: one THREAD per component running the host-testable process_component() phases
+// (merge_core.h); divergent lanes serialise, so only every (32 / per_warp)-th lane is used.
+constexpr int THREAD_BLOCK = 128;
 template <int PHASE>
-__global__ void __launch_bounds__(THREAD_BLOCK) component_kernel_thread(MergeCtx c, int32_t comp_lo, int32_t n_comp, int32_t shard_rank,
-                                                                      int32_t shard_count, int32_t per_warp) {
+__global__ void __launch_bounds__(THREAD_BLOCK) component_kernel_thread(MergeCtx c, LargeScratch s, int32_t n, int32_t per_warp) {
   const int32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int32_t stride = 32 / per_warp;
   if ((tid & 31) % stride != 0) return;
-  const int32_t comp = comp_lo + (tid >> 5) * per_warp + (tid & 31) / stride;
-  if (comp >= n_comp) return;
-  if (comp % shard_count != shard_rank) return;
-  const MergeState st = global_state(c, comp);
-  if (PHASE == 1) component_seed(c, st, comp);
-  if (PHASE == 2) component_main(c, st, comp);
-  if (PHASE == 3) component_consensus(c, st, comp);
+  const int32_t i = (tid >> 5) * per_warp + (tid & 31) / stride;
+  if (i >= n) return;
+  const MergeState st = large_state(c, s, i);
+  if (PHASE == 1) component_seed(c, st, s.list[i]);
+  if (PHASE == 2) component_main(c, st, s.list[i]);
+  if (PHASE == 3) component_consensus(c, st, s.list[i]);
 }
 
-__global__ void init_outputs_kernel(int32_t R, int64_t nnz, int32_t *t_root, int32_t *t_pos, int32_t *t_size, int64_t *t_key,
-                                    int32_t *t_bc, int32_t *t_up, int64_t *t_calloff, int32_t *t_calln, int32_t *call_mut) {
+__global__ void init_outputs_kernel(int32_t R, int64_t nnz, MergeOut out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < R) {
-    t_root[i] = t_pos[i] = t_size[i] = t_bc[i] = t_up[i] = t_calln[i] = PCB_FILL;
-    t_key[i] = INT64_MIN; t_calloff[i] = INT64_MIN;
+    out.read_root[i] = out.read_pos[i] = out.row_size[i] = out.row_bc[i] = out.row_up[i] = out.row_call_n[i] = PCB_FILL;
+    out.row_key[i] = INT64_MIN; out.row_call_off[i] = INT64_MIN;
   }
-  if (i < nnz) call_mut[i] = PCB_FILL;
+  if (i < nnz) out.call_mut[i] = PCB_FILL;
 }
 
-// new numbering -> the caller's numbering.  Rows of components another shard owns stay PCB_FILL.
-__global__ void scatter_outputs_kernel(int32_t R, const int32_t *__restrict__ old_of_new_r, const int32_t *__restrict__ old_of_new_b,
-                                       const int32_t *__restrict__ t_root, const int32_t *__restrict__ t_pos,
-                                       const int32_t *__restrict__ t_size, const int64_t *__restrict__ t_key,
-                                       const int32_t *__restrict__ t_bc, const int32_t *__restrict__ t_up,
-                                       const int64_t *__restrict__ t_calloff, const int32_t *__restrict__ t_calln, MergeOut out) {
-  int32_t nr = blockIdx.x * blockDim.x + threadIdx.x;
-  if (nr >= R) return;                              // R = reads of this shard
-  int32_t r = old_of_new_r[nr];
-  int32_t root = t_root[nr];
-  out.read_root[r] = root == PCB_FILL ? PCB_FILL : old_of_new_r[root];
-  out.read_pos[r] = t_pos[nr];
-  out.row_size[r] = t_size[nr];
-  int64_t key = t_key[nr];
-  if (key >= 0) key = ((int64_t)old_of_new_b[(int32_t)(key >> 32)] << 32) | (key & 0xFFFFFFFFll);   // creation order is by caller bucket
-  out.row_key[r] = key;
-  out.row_bc[r] = t_bc[nr];
-  out.row_up[r] = t_up[nr];
-  out.row_call_off[r] = t_calloff[nr];
-  out.row_call_n[r] = t_calln[nr];
+// ------------------------------------------------------------------------------------------ host
+namespace {
+
+// The generic replay on global state for a list of components (the large tier; every component under the forced shapes).
+void run_large(pcb_ctx *ctx, MergeCtx c, const int32_t *list, int32_t n, int32_t R, int shape) {
+  if (n <= 0) return;
+  DevBuf<int32_t> slot_cap(ctx, (size_t)n + 1);
+  DevBuf<int64_t> slot_off(ctx, (size_t)n + 1), list_off(ctx, (size_t)n + 1);
+  PCB_LAUNCH(ctx, large_scratch_kernel, grid_for((size_t)n + 1, 128), 128, 0, c, list, n, slot_cap.p, slot_off.p, list_off.p);
+  exclusive_scan_i64(ctx, slot_off.p, slot_off.p, (size_t)n + 1);
+  exclusive_scan_i64(ctx, list_off.p, list_off.p, (size_t)n + 1);
+  int64_t n_slots = 0, n_list = 0;
+  PCB_CUDA(cudaMemcpyAsync(&n_slots, slot_off.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PCB_CUDA(cudaMemcpyAsync(&n_list, list_off.p + n, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  DevBuf<GenoSlot> slots(ctx, (size_t)n_slots);
+  DevBuf<int32_t> lists(ctx, (size_t)n_list + 1);
+  PCB_CUDA(cudaMemsetAsync(slots.p, 0, (size_t)n_slots * sizeof(GenoSlot), ctx->stream));     // all-zero = empty
+  DevBuf<int32_t> rd_slot(ctx, R), rd_next(ctx, R), sl_parent(ctx, R), sl_head(ctx, R), sl_tail(ctx, R), sl_size(ctx, R);
+  DevBuf<int64_t> sl_key(ctx, R);
+  PCB_CUDA(cudaMemsetAsync(rd_slot.p, 0xFF, (size_t)R * sizeof(int32_t), ctx->stream));
+  PCB_CUDA(cudaMemsetAsync(rd_next.p, 0xFF, (size_t)R * sizeof(int32_t), ctx->stream));
+  c.slots = slots.p; c.lists = lists.p;
+  c.rd_slot = rd_slot.p; c.rd_next = rd_next.p; c.sl_parent = sl_parent.p; c.sl_head = sl_head.p;
+  c.sl_tail = sl_tail.p; c.sl_size = sl_size.p; c.sl_key = sl_key.p;
+  LargeScratch s{list, slot_cap.p, slot_off.p, list_off.p};
+  if (shape == PCB_REPLAY_THREAD) {
+    const int per_warp = 4;               // best of a 1..32 sweep (divergent lanes serialise)
+    size_t n_threads = ((size_t)n + per_warp - 1) / per_warp * 32;
+    // three launches, one per phase: each kernel's code fits the instruction cache and its threads share a loop nest
+    PCB_LAUNCH(ctx, component_kernel_thread<1>, grid_for(n_threads, THREAD_BLOCK), THREAD_BLOCK, 0, c, s, n, per_warp);
+    PCB_LAUNCH(ctx, component_kernel_thread<2>, grid_for(n_threads, THREAD_BLOCK), THREAD_BLOCK, 0, c, s, n, per_warp);
+    PCB_LAUNCH(ctx, component_kernel_thread<3>, grid_for(n_threads, THREAD_BLOCK), THREAD_BLOCK, 0, c, s, n, per_warp);
+  } else {
+    PCB_LAUNCH(ctx, component_kernel_large, grid_for((size_t)n * 32, COMP_BLOCK), COMP_BLOCK, 0, c, s, n);
+  }
+  PCB_CUDA(cudaStreamSynchronize(ctx->stream));          // the scratch above is released when this returns
 }
+
+}  // namespace
 
 void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   const int32_t R = in.R, U = in.U;
@@ -413,194 +510,149 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   const int64_t nnz = in.nnz >= 0 ? in.nnz : (int64_t)read_scalar(ctx, in.geno_ptr + R);
   const int bbits = bits_for((uint64_t)(U > 1 ? U - 1 : 1));
   const bool on_demand = in.planes != nullptr && in.compute_k >= 0;
+  const int shape = ctx->replay_shape;
+  if (!ctx->medium_attr_set) {
+    PCB_CUDA(cudaFuncSetAttribute(component_kernel_medium, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(MediumSmem)));
+    ctx->medium_attr_set = true;
+  }
 
-  // ---- components of the link graph; this shard's components first, heaviest first
-  DevBuf<int32_t> label(ctx, U), old_of_new_b(ctx, U), new_of_old_b(ctx, U), comp_of_new_b(ctx, U), comp_ptr(ctx, (size_t)U + 2),
-      comp_label(ctx, (size_t)U + 1);
-  DevBuf<uint32_t> nb_ptr(ctx, (size_t)U + 1), lab_call_off(ctx, (size_t)U + 1), counters(ctx, 4);
-  int32_t n_comp_all = 0;
+  // ---- components of the link graph; this shard's components first
+  DevBuf<int32_t> counters(ctx, CNT_N + 1), label(ctx, U), comp_buckets(ctx, U), comp_ptr(ctx, (size_t)U + 2), comp_of_b(ctx, U);
+  DevBuf<int64_t> cursor(ctx, 1);
+  PCB_CUDA(cudaMemsetAsync(counters.p, 0, (CNT_N + 1) * sizeof(int32_t), ctx->stream));
+  PCB_CUDA(cudaMemsetAsync(cursor.p, 0, sizeof(int64_t), ctx->stream));
   {
     DevBuf<int32_t> parent(ctx, U);
-    DevBuf<uint32_t> work(ctx, U), rank(ctx, (size_t)U + 1);
+    DevBuf<uint32_t> rank(ctx, (size_t)U + 1);
     DevBuf<uint64_t> k0(ctx, U), k1(ctx, U);
     DevBuf<uint32_t> v0(ctx, U), v1(ctx, U);
-    PCB_CUDA(cudaMemsetAsync(work.p, 0, (size_t)U * sizeof(uint32_t), ctx->stream));
-    PCB_CUDA(cudaMemsetAsync(counters.p, 0, 4 * sizeof(uint32_t), ctx->stream));
-    PCB_CUDA(cudaMemsetAsync(lab_call_off.p, 0, ((size_t)U + 1) * sizeof(uint32_t), ctx->stream));
     PCB_LAUNCH(ctx, uf_init_kernel, grid_for(U, 256), 256, 0, parent.p, U);
     if (P > 0) PCB_LAUNCH(ctx, uf_union_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_r, in.pair_ed, P, in.max_diff, parent.p);
-    PCB_LAUNCH(ctx, uf_label_kernel, grid_for(U, 256), 256, 0, parent.p, in.bucket_ptr, U, label.p, work.p);
-    PCB_LAUNCH(ctx, label_nnz_kernel, grid_for(U, 256), 256, 0, in.bucket_ptr, in.bucket_reads, in.geno_ptr, label.p, U, lab_call_off.p);
-    exclusive_scan_u32(ctx, lab_call_off.p, lab_call_off.p, (size_t)U + 1);
-    PCB_LAUNCH(ctx, comp_keys_kernel, grid_for(U, 256), 256, 0, label.p, work.p, U, bbits, in.shard_rank, in.shard_count, k0.p, v0.p,
+    PCB_LAUNCH(ctx, comp_keys_kernel, grid_for(U, 256), 256, 0, parent.p, U, bbits, in.shard_rank, in.shard_count, label.p, k0.p, v0.p,
                counters.p);
-    int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, U, bbits + 11);
+    int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, U, bbits + (in.shard_count > 1 ? 1 : 0));
     uint64_t *sk = w ? k1.p : k0.p;
     uint32_t *sv = w ? v1.p : v0.p;
-    PCB_LAUNCH(ctx, comp_flag_kernel, grid_for(U, 256), 256, 0, sk, U, rank.p);
-    PCB_CUDA(cudaMemsetAsync(rank.p + U, 0, sizeof(uint32_t), ctx->stream));
+    PCB_LAUNCH(ctx, comp_flag_kernel, grid_for((size_t)U + 1, 256), 256, 0, sk, U, rank.p);
     exclusive_scan_u32(ctx, rank.p, rank.p, (size_t)U + 1);              // one past the end: the total
-    n_comp_all = (int32_t)read_scalar(ctx, rank.p + U);
-    PCB_LAUNCH(ctx, comp_assign_kernel, grid_for(U, 256), 256, 0, sk, sv, rank.p, in.bucket_ptr, U, n_comp_all, old_of_new_b.p,
-               new_of_old_b.p, comp_ptr.p, comp_of_new_b.p, nb_ptr.p, comp_label.p, bbits, (uint32_t)HEAVY_READS, counters.p);
-    exclusive_scan_u32(ctx, nb_ptr.p, nb_ptr.p, (size_t)U + 1);
-    PCB_LAUNCH(ctx, shard_reads_kernel, 1, 1, 0, nb_ptr.p, counters.p);
-  }
-  ctx->stats[PCB_STAT_COMPONENTS] = n_comp_all;
-
-  // ---- this shard's pairs, compacted (original order kept) and renumbered
-  DevBuf<uint32_t> ppos(ctx, (size_t)P + 1);
-  PCB_CUDA(cudaMemsetAsync(ppos.p, 0, ((size_t)P + 1) * sizeof(uint32_t), ctx->stream));
-  if (P > 0) {
-    PCB_LAUNCH(ctx, pair_flag_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_r, P, new_of_old_b.p, ppos.p);
-    exclusive_scan_u32(ctx, ppos.p, ppos.p, (size_t)P + 1);
-  }
-  uint32_t h_counters[4], h_pm = 0;                                     // one round trip for all the shard sizes
-  PCB_CUDA(cudaMemcpyAsync(h_counters, counters.p, sizeof(h_counters), cudaMemcpyDeviceToHost, ctx->stream));
-  PCB_CUDA(cudaMemcpyAsync(&h_pm, ppos.p + P, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-  PCB_CUDA(cudaStreamSynchronize(ctx->stream));
-  const int32_t Um = (int32_t)h_counters[0], n_comp = (int32_t)h_counters[1], Rm = (int32_t)h_counters[3];
-  const uint32_t h_n_heavy = h_counters[2];
-  const int64_t Pm = (int64_t)h_pm;
-  (void)Um;
-  DevBuf<int32_t> mq(ctx, (size_t)Pm), mr(ctx, (size_t)Pm), md(ctx, (size_t)Pm), me(ctx, (size_t)Pm);
-  if (Pm > 0)
-    PCB_LAUNCH(ctx, pair_compact_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_r, in.pair_d, in.pair_ed, P, new_of_old_b.p,
-               ppos.p, mq.p, mr.p, md.p, me.p);
-
-  // ---- reads and genotypes of this shard gathered into component order
-  DevBuf<int32_t> old_of_new_r(ctx, R), n_bor(ctx, R), n_lex(ctx, R), n_bc(ctx, R), n_up(ctx, in.up_id ? R : 1);
-  DevBuf<uint32_t> n_gptr(ctx, (size_t)R + 1);
-  DevBuf<int32_t> n_gmut(ctx, (size_t)nnz), n_gq(ctx, (size_t)nnz);
-  PCB_CUDA(cudaMemsetAsync(n_gptr.p, 0, ((size_t)R + 1) * sizeof(uint32_t), ctx->stream));
-  PCB_LAUNCH(ctx, read_renumber_kernel, grid_for(R, 256), 256, 0, in.bucket_ptr, in.bucket_reads, R, U, new_of_old_b.p, nb_ptr.p,
-             in.lexrank, in.bc_id, in.up_id, in.geno_ptr, old_of_new_r.p, n_bor.p, n_lex.p, n_bc.p, n_up.p, n_gptr.p);
-  exclusive_scan_u32(ctx, n_gptr.p, n_gptr.p, (size_t)Rm + 1);
-  if (Rm > 0)
-    PCB_LAUNCH(ctx, geno_gather_kernel, grid_for(Rm, 256), 256, 0, old_of_new_r.p, in.geno_ptr, in.geno_mut, in.geno_q, Rm, n_gptr.p,
-               n_gmut.p, n_gq.p, counters.p);
-  DevBuf<ulonglong2> n_planes(ctx, on_demand ? U : 1);
-  DevBuf<int32_t> n_blen(ctx, on_demand ? U : 1);
-  if (on_demand)
-    PCB_LAUNCH(ctx, planes_gather_kernel, grid_for(U, 256), 256, 0, old_of_new_b.p, in.planes, in.blen, U, n_planes.p, n_blen.p,
+    PCB_LAUNCH(ctx, comp_assign_kernel, grid_for(U, 256), 256, 0, sk, sv, rank.p, U, bbits, comp_buckets.p, comp_ptr.p, comp_of_b.p,
                counters.p);
-
-  // ---- adjacency (new bucket ids)
-  DevBuf<int32_t> adj_ptr(ctx, (size_t)U + 1), adj_nbr(ctx, (size_t)(2 * Pm)), adj_d(ctx, (size_t)(2 * Pm));
-  {
-    DevBuf<uint32_t> cnt(ctx, (size_t)U + 1);
-    PCB_CUDA(cudaMemsetAsync(cnt.p, 0, ((size_t)U + 1) * sizeof(uint32_t), ctx->stream));
-    if (Pm > 0) {
-      DevBuf<uint64_t> k0(ctx, 2 * Pm), k1(ctx, 2 * Pm);
-      DevBuf<uint32_t> v0(ctx, 2 * Pm), v1(ctx, 2 * Pm);
-      PCB_LAUNCH(ctx, adj_keys_kernel, grid_for(Pm, 256), 256, 0, mq.p, mr.p, md.p, Pm, bbits, k0.p, v0.p, cnt.p);
-      int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, 2 * Pm, 2 * bbits);
-      PCB_LAUNCH(ctx, adj_unpack_kernel, grid_for(2 * Pm, 256), 256, 0, w ? k1.p : k0.p, w ? v1.p : v0.p, 2 * Pm, bbits,
-                 adj_nbr.p, adj_d.p);
-    }
-    exclusive_scan_u32(ctx, cnt.p, cnt.p, (size_t)U + 1);
-    PCB_CUDA(cudaMemcpyAsync(adj_ptr.p, cnt.p, ((size_t)U + 1) * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
   }
 
-  // ---- visiting pairs per component (stable: the caller's visiting order survives inside a component)
-  DevBuf<int32_t> cpair_ptr(ctx, (size_t)n_comp + 2), cq(ctx, (size_t)Pm), cr(ctx, (size_t)Pm), ce(ctx, (size_t)Pm);
+  // ---- adjacency: every pair once, in the row of its smaller bucket
+  DevBuf<int32_t> adj_ptr(ctx, (size_t)U + 1), sq, sr, sd;
+  const int32_t *adj_nbr = in.pair_r, *adj_d = in.pair_d;
+  if (!in.pairs_sorted && P > 0) {
+    DevBuf<uint64_t> k0(ctx, P), k1(ctx, P);
+    DevBuf<uint32_t> v0(ctx, P), v1(ctx, P);
+    sq.alloc(ctx, P); sr.alloc(ctx, P); sd.alloc(ctx, P);
+    PCB_LAUNCH(ctx, pair_keys_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_r, P, bbits, k0.p, v0.p);
+    int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, P, 2 * bbits);
+    PCB_LAUNCH(ctx, pair_unpack_kernel, grid_for(P, 256), 256, 0, w ? k1.p : k0.p, w ? v1.p : v0.p, in.pair_d, P, bbits, sq.p, sr.p, sd.p);
+    adj_nbr = sr.p; adj_d = sd.p;
+  }
+  PCB_LAUNCH(ctx, row_ptr_kernel, grid_for((size_t)P + 1, 256), 256, 0, (in.pairs_sorted || P == 0) ? in.pair_q : sq.p, P, U, adj_ptr.p);
+
+  // ---- visiting pairs per component
+  DevBuf<int32_t> cpair_ptr(ctx, (size_t)U + 2), cq(ctx, (size_t)P), cr(ctx, (size_t)P), ce(ctx, (size_t)P);
   {
-    DevBuf<uint32_t> cnt(ctx, (size_t)n_comp + 2);
-    PCB_CUDA(cudaMemsetAsync(cnt.p, 0, ((size_t)n_comp + 2) * sizeof(uint32_t), ctx->stream));
-    if (Pm > 0) {
-      DevBuf<uint64_t> k0(ctx, Pm), k1(ctx, Pm);
-      DevBuf<uint32_t> v0(ctx, Pm), v1(ctx, Pm);
-      PCB_LAUNCH(ctx, cpair_keys_kernel, grid_for(Pm, 256), 256, 0, mq.p, me.p, Pm, comp_of_new_b.p, n_comp, in.max_diff, k0.p, v0.p,
-                 cnt.p);
-      int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, Pm, bits_for((uint64_t)n_comp) + 2);
-      PCB_LAUNCH(ctx, cpair_gather_kernel, grid_for(Pm, 256), 256, 0, w ? v1.p : v0.p, Pm, mq.p, mr.p, me.p, cq.p, cr.p, ce.p);
+    DevBuf<uint32_t> cnt(ctx, 4 * ((size_t)U + 1) + 1);
+    PCB_CUDA(cudaMemsetAsync(cnt.p, 0, (4 * ((size_t)U + 1) + 1) * sizeof(uint32_t), ctx->stream));
+    if (P > 0)
+      PCB_LAUNCH(ctx, visit_count_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_ed, P, in.max_diff, comp_of_b.p, cnt.p, counters.p);
+    exclusive_scan_u32(ctx, cnt.p, cnt.p, 4 * ((size_t)U + 1) + 1);
+    if (in.pairs_sorted || P == 0) {
+      PCB_LAUNCH(ctx, visit_walk_kernel, grid_for((size_t)U + 1, 128), 128, 0, comp_ptr.p, comp_buckets.p, counters.p, adj_ptr.p, in.pair_r,
+                 in.pair_ed, in.max_diff, cnt.p, cpair_ptr.p, cq.p, cr.p, ce.p);
+    } else {
+      DevBuf<uint64_t> k0(ctx, P), k1(ctx, P);
+      DevBuf<uint32_t> v0(ctx, P), v1(ctx, P);
+      PCB_LAUNCH(ctx, cpair_keys_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_ed, P, comp_of_b.p, U, in.max_diff, k0.p, v0.p);
+      int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, P, bbits + 3);
+      PCB_LAUNCH(ctx, cpair_gather_kernel, grid_for(P, 256), 256, 0, w ? v1.p : v0.p, counters.p, in.pair_q, in.pair_r, in.pair_ed, cq.p,
+                 cr.p, ce.p, P);
+      PCB_LAUNCH(ctx, cpair_ptr_kernel, grid_for((size_t)U + 1, 256), 256, 0, cnt.p, counters.p, cpair_ptr.p);
     }
-    exclusive_scan_u32(ctx, cnt.p, cnt.p, (size_t)n_comp + 2);
-    PCB_CUDA(cudaMemcpyAsync(cpair_ptr.p, cnt.p, ((size_t)n_comp + 2) * sizeof(int32_t), cudaMemcpyDeviceToDevice, ctx->stream));
   }
 
-  // ---- scratch
-  DevBuf<int32_t> slot_cap(ctx, (size_t)n_comp + 1);
-  DevBuf<int64_t> slot_off(ctx, (size_t)n_comp + 1), list_off(ctx, (size_t)n_comp + 1), call_off(ctx, (size_t)n_comp + 1);
-  PCB_LAUNCH(ctx, comp_scratch_kernel, grid_for((size_t)n_comp + 1, 256), 256, 0, comp_ptr.p, nb_ptr.p, n_gptr.p, n_comp, comp_label.p,
-             lab_call_off.p, slot_cap.p, slot_off.p, list_off.p, call_off.p);
-  exclusive_scan_i64(ctx, slot_off.p, slot_off.p, (size_t)n_comp + 1);
-  exclusive_scan_i64(ctx, list_off.p, list_off.p, (size_t)n_comp + 1);
-  int64_t n_slots = 0, n_list = 0;
-  PCB_CUDA(cudaMemcpyAsync(&n_slots, slot_off.p + n_comp, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  PCB_CUDA(cudaMemcpyAsync(&n_list, list_off.p + n_comp, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-  PCB_CUDA(cudaStreamSynchronize(ctx->stream));
-  DevBuf<GenoSlot> slots(ctx, (size_t)n_slots);
-  DevBuf<int32_t> lists(ctx, (size_t)n_list + 1);
-  PCB_CUDA(cudaMemsetAsync(slots.p, 0, (size_t)n_slots * sizeof(GenoSlot), ctx->stream));     // all-zero = empty
-
-  // ---- cluster state and outputs in the new numbering
-  DevBuf<int32_t> rd_slot(ctx, R), rd_next(ctx, R), sl_parent(ctx, R), sl_head(ctx, R), sl_tail(ctx, R), sl_size(ctx, R), status(ctx, 4);
-  DevBuf<int64_t> sl_key(ctx, R);
-  DevBuf<int32_t> t_root(ctx, R), t_pos(ctx, R), t_size(ctx, R), t_bc(ctx, R), t_up(ctx, R), t_calln(ctx, R);
-  DevBuf<int64_t> t_key(ctx, R), t_calloff(ctx, R);
-  PCB_CUDA(cudaMemsetAsync(rd_slot.p, 0xFF, (size_t)R * sizeof(int32_t), ctx->stream));
-  PCB_CUDA(cudaMemsetAsync(rd_next.p, 0xFF, (size_t)R * sizeof(int32_t), ctx->stream));
+  // ---- what the replay reads
+  DevBuf<int32_t> bor_own;
+  const int32_t *bor = in.bucket_of_read;
+  if (!bor) {
+    bor_own.alloc(ctx, R);
+    PCB_LAUNCH(ctx, bucket_of_read_kernel, grid_for(R, 256), 256, 0, in.bucket_ptr, in.bucket_reads, R, U, bor_own.p);
+    bor = bor_own.p;
+  }
+  DevBuf<int32_t> status(ctx, 4), medium(ctx, (size_t)U + 1), large(ctx, (size_t)U + 1), declined(ctx, (size_t)U + 1), late(ctx, (size_t)U + 1);
   PCB_CUDA(cudaMemsetAsync(status.p, 0, 4 * sizeof(int32_t), ctx->stream));
-  // everything starts as "not mine": the per-row fields of non-representative reads (new numbering, this shard's reads),
-  // the call array, and -- when the library is sharded -- the caller's arrays for the reads other shards own
-  PCB_LAUNCH(ctx, init_outputs_kernel, grid_for((size_t)(Rm > nnz ? Rm : nnz) + 1, 256), 256, 0, Rm, nnz, t_root.p, t_pos.p, t_size.p,
-             t_key.p, t_bc.p, t_up.p, t_calloff.p, t_calln.p, out.call_mut);
-  if (in.shard_count > 1)
-    PCB_LAUNCH(ctx, init_outputs_kernel, grid_for((size_t)R, 256), 256, 0, R, (int64_t)0, out.read_root, out.read_pos, out.row_size,
-               out.row_key, out.row_bc, out.row_up, out.row_call_off, out.row_call_n, out.call_mut);
-
-  DevBuf<int32_t> declined(ctx, (size_t)n_comp + 1), n_declined(ctx, 1);
   MergeCtx c;
   memset(&c, 0, sizeof(c));
   c.R = R; c.U = U;
-  c.bucket_ptr = (const int32_t *)nb_ptr.p; c.bucket_reads = nullptr; c.bucket_of_read = n_bor.p;
-  c.lexrank = n_lex.p; c.bc_id = n_bc.p; c.up_id = in.up_id ? n_up.p : nullptr;
-  c.geno_ptr = (const int32_t *)n_gptr.p; c.geno_mut = n_gmut.p; c.geno_q = n_gq.p; c.mut_rank = in.mut_rank;
-  c.adj_ptr = adj_ptr.p; c.adj_nbr = adj_nbr.p; c.adj_d = adj_d.p;
-  c.planes = on_demand ? (const uint64_t *)n_planes.p : nullptr; c.blen = on_demand ? n_blen.p : nullptr;
+  c.bucket_ptr = in.bucket_ptr; c.bucket_reads = in.bucket_reads; c.bucket_of_read = bor;
+  c.lexrank = in.lexrank; c.bc_id = in.bc_id; c.up_id = in.up_id;
+  c.geno_ptr = in.geno_ptr; c.geno_mut = in.geno_mut; c.geno_q = in.geno_q; c.mut_rank = in.mut_rank;
+  c.adj_ptr = adj_ptr.p; c.adj_nbr = adj_nbr; c.adj_d = adj_d; c.adj_forward = 1;
+  c.planes = on_demand ? (const uint64_t *)in.planes : nullptr; c.blen = on_demand ? in.blen : nullptr;
   c.compute_k = on_demand ? in.compute_k : -1; c.wide = in.wide;
-  c.comp_ptr = comp_ptr.p; c.comp_buckets = nullptr;
+  c.comp_ptr = comp_ptr.p; c.comp_buckets = comp_buckets.p;
   c.cpair_ptr = cpair_ptr.p; c.cpair_q = cq.p; c.cpair_r = cr.p; c.cpair_ed = ce.p;
-  c.scr_slot_off = slot_off.p; c.scr_slot_cap = slot_cap.p; c.scr_list_off = list_off.p; c.call_off = call_off.p;
-  c.slots = slots.p; c.lists = lists.p;
-  c.rd_slot = rd_slot.p; c.rd_next = rd_next.p; c.sl_parent = sl_parent.p; c.sl_head = sl_head.p;
-  c.sl_tail = sl_tail.p; c.sl_size = sl_size.p; c.sl_key = sl_key.p;
-  c.read_root = t_root.p; c.read_pos = t_pos.p; c.row_size = t_size.p; c.row_key = t_key.p;
-  c.row_bc = t_bc.p; c.row_up = t_up.p; c.row_call_off = t_calloff.p; c.row_call_n = t_calln.p;
+  c.call_off = nullptr; c.call_cursor = cursor.p;
+  DevBuf<int64_t> call_off;
+  if (in.shard_layout) {
+    DevBuf<uint32_t> lab_off(ctx, (size_t)U + 1);
+    call_off.alloc(ctx, (size_t)U + 1);
+    PCB_CUDA(cudaMemsetAsync(lab_off.p, 0, ((size_t)U + 1) * sizeof(uint32_t), ctx->stream));
+    PCB_LAUNCH(ctx, label_nnz_kernel, grid_for(U, 256), 256, 0, in.bucket_ptr, in.bucket_reads, in.geno_ptr, label.p, U, lab_off.p);
+    exclusive_scan_u32(ctx, lab_off.p, lab_off.p, (size_t)U + 1);
+    PCB_LAUNCH(ctx, comp_call_off_kernel, grid_for(U, 256), 256, 0, comp_ptr.p, comp_buckets.p, counters.p, lab_off.p, call_off.p);
+    c.call_off = call_off.p;
+  }
+  c.read_root = out.read_root; c.read_pos = out.read_pos; c.row_size = out.row_size; c.row_key = out.row_key;
+  c.row_bc = out.row_bc; c.row_up = out.row_up; c.row_call_off = out.row_call_off; c.row_call_n = out.row_call_n;
   c.call_mut = out.call_mut; c.status = status.p;
   c.prm.maxDiff = in.max_diff; c.prm.minQual = in.min_qual; c.prm.minMatches = in.min_matches; c.prm.minJaccard = in.min_jaccard;
-  stage_end(ctx, PCB_STAT_T_PREP_NS);
-  // Launch shapes (profiles/r01_replay_shapes.md, r02_replay.md).  Default: components of at most 32 reads -- all but a
-  // handful on every BASELINE config -- go to the one-lane-per-read kernel; the bigger ones (numbered first) and
-  // whatever that kernel declines go to the generic warp kernel.  ctx->replay_shape forces the round-1 shapes
-  // (one thread per component / the generic warp kernel for everything), which the parity tests keep exercising.
-  int32_t n_warp = (int32_t)h_n_heavy;
-  if (ctx->replay_shape == PCB_REPLAY_WARP) n_warp = n_comp;
-  if (n_warp > 0)
-    PCB_LAUNCH(ctx, component_kernel_warp, grid_for((size_t)n_warp * 32, COMP_BLOCK), COMP_BLOCK, 0, c, 0, n_warp);
-  if (n_warp < n_comp && ctx->replay_shape == PCB_REPLAY_THREAD) {
-    const int per_warp = 4;               // best of a 1..32 sweep (divergent lanes serialise)
-    size_t n_threads = ((size_t)(n_comp - n_warp) + per_warp - 1) / per_warp * 32;
-    // three launches, one per phase: each kernel's code fits the instruction cache and its threads share a loop nest
-    PCB_LAUNCH(ctx, component_kernel_thread<1>, grid_for(n_threads, THREAD_BLOCK), THREAD_BLOCK, 0, c, n_warp, n_comp, 0, 1, per_warp);
-    PCB_LAUNCH(ctx, component_kernel_thread<2>, grid_for(n_threads, THREAD_BLOCK), THREAD_BLOCK, 0, c, n_warp, n_comp, 0, 1, per_warp);
-    PCB_LAUNCH(ctx, component_kernel_thread<3>, grid_for(n_threads, THREAD_BLOCK), THREAD_BLOCK, 0, c, n_warp, n_comp, 0, 1, per_warp);
-  } else if (n_warp < n_comp) {
-    PCB_CUDA(cudaMemsetAsync(n_declined.p, 0, sizeof(int32_t), ctx->stream));
-    PCB_LAUNCH(ctx, component_kernel_small, grid_for((size_t)(n_comp - n_warp) * 32, SMALL_BLOCK), SMALL_BLOCK, 0, c, n_warp, n_comp,
-               declined.p, n_declined.p);
-    PCB_LAUNCH(ctx, component_kernel_warp_list, (unsigned)ctx->sm_count * 2u, COMP_BLOCK, 0, c, declined.p, n_declined.p);
-  }
-  stage_end(ctx, PCB_STAT_T_REPLAY_NS);
-  if (Rm > 0)
-    PCB_LAUNCH(ctx, scatter_outputs_kernel, grid_for(Rm, 256), 256, 0, Rm, old_of_new_r.p, old_of_new_b.p, t_root.p, t_pos.p, t_size.p,
-               t_key.p, t_bc.p, t_up.p, t_calloff.p, t_calln.p, out);
-  stage_end(ctx, PCB_STAT_T_SCATTER_NS);
-
-  int32_t h_status[4];
-  PCB_CUDA(cudaMemcpyAsync(h_status, status.p, sizeof(h_status), cudaMemcpyDeviceToHost, ctx->stream));
+  const int32_t force_large = shape != PCB_REPLAY_AUTO ? 1 : 0;
+  PCB_LAUNCH(ctx, classify_kernel, grid_for((size_t)U, 128), 128, 0, c, force_large, counters.p, medium.p, large.p);
+  // every output starts as "not produced": entries of reads other shards own, the row fields of non-representative reads
+  PCB_LAUNCH(ctx, init_outputs_kernel, grid_for((size_t)(R > nnz ? R : nnz) + 1, 256), 256, 0, R, nnz, out);
+  int32_t h_cnt[CNT_N];                                                 // the one round trip of the preprocessing
+  PCB_CUDA(cudaMemcpyAsync(h_cnt, counters.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
   PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int32_t n_comp = h_cnt[CNT_COMPS], n_medium = h_cnt[CNT_MEDIUM], n_large = h_cnt[CNT_LARGE];
+  ctx->stats[PCB_STAT_COMPONENTS] = n_comp;
+  stage_end(ctx, PCB_STAT_T_PREP_NS);
+
+  // ---- replay
+  const unsigned medium_grid = (unsigned)ctx->sm_count * 4u;
+  if (n_medium > 0) {                     // the few components of 33..128 reads on a second stream, beside everything else
+    PCB_CUDA(cudaEventRecord(ctx->ev_alloc, ctx->stream));
+    PCB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_alloc, 0));
+    component_kernel_medium<<<(unsigned)n_medium < medium_grid ? (unsigned)n_medium : medium_grid, 32, sizeof(MediumSmem), ctx->copy_stream>>>(
+        c, medium.p, counters.p + CNT_MEDIUM);
+    ctx->stats[PCB_STAT_KERNEL_LAUNCHES]++;
+    PCB_CUDA(cudaGetLastError());
+    PCB_CUDA(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
+  }
+  if (shape == PCB_REPLAY_AUTO && n_comp > 0) {
+    PCB_LAUNCH(ctx, component_kernel_small, grid_for((size_t)n_comp * 32, SMALL_BLOCK), SMALL_BLOCK, 0, c, n_comp, counters.p, declined.p,
+               late.p);
+    // whatever it declined (the count is only known on the device): a fixed grid walks the list
+    PCB_LAUNCH(ctx, component_kernel_medium, medium_grid / 4u, 32, sizeof(MediumSmem), c, declined.p, counters.p + CNT_DECLINED);
+  }
+  if (n_medium > 0) PCB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
+  run_large(ctx, c, large.p, n_large, R, shape);
+  stage_end(ctx, PCB_STAT_T_REPLAY_NS);
+
+  int32_t h_status[4], h_late = 0;
+  PCB_CUDA(cudaMemcpyAsync(h_status, status.p, sizeof(h_status), cudaMemcpyDeviceToHost, ctx->stream));
+  PCB_CUDA(cudaMemcpyAsync(&h_late, counters.p + CNT_LATE, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (h_late > 0) {                       // <= 32 reads, but too many calls or rows for either warp kernel's shared memory
+    run_large(ctx, c, late.p, h_late, R, PCB_REPLAY_WARP);
+    PCB_CUDA(cudaMemcpyAsync(h_status, status.p, sizeof(h_status), cudaMemcpyDeviceToHost, ctx->stream));
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  stage_end(ctx, PCB_STAT_T_SCATTER_NS);
   ctx->stats[PCB_STAT_LINKS] = h_status[2];
   ctx->stats[PCB_STAT_TESTS] = h_status[3];
   if (h_status[0] == 3)

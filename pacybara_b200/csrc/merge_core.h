@@ -67,7 +67,10 @@ struct MergeCtx {
   const int64_t *scr_slot_off;   // into slots[]  (capacity = scr_slot_cap[c], a power of two)
   const int32_t *scr_slot_cap;
   const int64_t *scr_list_off;   // into lists[]  (capacity 2 * (#reads + #geno entries) of the component)
-  const int64_t *call_off;       // into call_mut[] (capacity = #geno entries of the component)
+  const int64_t *call_off;       // into call_mut[] (capacity = #geno entries of the component); nullptr: regions are taken from
+  int64_t *call_cursor;          //   this shared cursor as the components come by (merge_small.cuh, merge.cu)
+  const int32_t *bucket_gid;     // optional: bucket number -> bucket id in the adjacency (components replayed on a local copy)
+  int32_t adj_forward;           // the adjacency holds every pair once, in the row of its smaller bucket id
   GenoSlot *slots;
   int32_t *lists;
   // cluster state in global memory (size R)
@@ -196,6 +199,8 @@ PCB_HD void table_clear(Table &t) {
 // distance between two buckets as edistLookup holds it (:236,:266,:294); -1 = absent (inf)
 PCB_HD int32_t lookup_dist(const MergeCtx &c, int32_t a, int32_t b) {
   if (a == b) return 0;
+  if (c.bucket_gid) { a = c.bucket_gid[a]; b = c.bucket_gid[b]; }
+  if (c.adj_forward && a > b) { const int32_t t = a; a = b; b = t; }
   int32_t lo = c.adj_ptr[a], hi = c.adj_ptr[a + 1];
   while (lo < hi) {
     int32_t mid = (lo + hi) >> 1;
@@ -447,12 +452,33 @@ PCB_HD void component_main(const MergeCtx &c, const MergeState &st, int32_t comp
 #endif
 }
 
+// Where the calls of a component's rows go: its fixed region (call_off), or as many entries as its reads carry -- an
+// upper bound of its calls -- taken from the shared cursor (regions are then laid out in the order the components finish).
+PCB_HD int64_t component_call_base(const MergeCtx &c, int32_t comp) {
+  if (c.call_off) return c.call_off[comp];
+  int64_t ne = 0;
+  for (int32_t bi = c.comp_ptr[comp]; bi < c.comp_ptr[comp + 1]; bi++) {
+    const int32_t b = c.comp_buckets ? c.comp_buckets[bi] : bi;
+    for (int32_t x = c.bucket_ptr[b]; x < c.bucket_ptr[b + 1]; x++) {
+      const int32_t r = c.bucket_reads ? c.bucket_reads[x] : x;
+      ne += c.geno_ptr[r + 1] - c.geno_ptr[r];
+    }
+  }
+#if defined(__CUDA_ARCH__)
+  return (int64_t)atomicAdd((unsigned long long *)c.call_cursor, (unsigned long long)ne);
+#else
+  const int64_t at = *c.call_cursor;
+  *c.call_cursor = at + ne;
+  return at;
+#endif
+}
+
 // ---- phase 3: consensus + rows (:464-477, :515-537, :546-567)
 PCB_HD void component_consensus(const MergeCtx &c, const MergeState &st, int32_t comp) {
   Table tab;
   table_init(tab, st.slots, st.slot_mask, st.lists);
   int32_t b_lo = c.comp_ptr[comp], b_hi = c.comp_ptr[comp + 1];
-  int64_t call_pos = c.call_off[comp];
+  int64_t call_pos = component_call_base(c, comp);
   int32_t err = 0;
   for (int32_t bi = b_lo; bi < b_hi; bi++) {
     int32_t b = c.comp_buckets ? c.comp_buckets[bi] : bi;

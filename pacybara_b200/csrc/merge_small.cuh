@@ -27,8 +27,10 @@
 //   consensus        vote per column from the cluster's row; order of the calls by counting smaller ranks;
 //                    barcode majority with match_any.
 //
-// Eligibility: <= 32 reads, <= 32 distinct mutations, |Q| <= 2^24.  Anything else returns 1 before a single
-// output is written and is replayed by the generic kernel (merge_warp.cuh).
+// Eligibility: <= 32 reads, <= 32 LIVE mutations (a mutation only one read of the component names, with Q <= minQual,
+// is dead: it can pass no filter and win no vote, and gets no column), <= 128 distinct mutations, |Q| <= 2^24.
+// Anything else returns non-zero before a single output is written and is replayed by the generic kernel.
+// The caller's numbering is read in place: component -> comp_buckets -> bucket_ptr / bucket_reads -> read.
 // Written against simt.h so that tests/host_emul runs this very source on the CPU (unit tests only).
 #pragma once
 #include "merge_core.h"
@@ -39,40 +41,82 @@ namespace pcb {
 constexpr int SMALL_READS = 32;     // one lane per read
 constexpr int SMALL_MUTS = 32;      // one matrix column per lane
 constexpr int SMALL_STRIDE = 33;    // row stride: conflict-free along a row (lane = column) and down a column (lane = row)
-constexpr int SMALL_TAB = 64;       // open-addressing table that numbers the component's mutations
+constexpr int SMALL_TAB = 128;      // open-addressing table over the component's mutations (live ones get a column)
 
-struct SmallSmem {
+struct alignas(16) SmallSmem {
   int32_t sum[SMALL_READS * SMALL_STRIDE];    // sum of Q
   uint16_t cnt[SMALL_READS * SMALL_STRIDE];   // low byte: #reads with Q > 0; high byte: #reads naming the mutation
   int32_t tab[SMALL_TAB];                     // mutation id + 1, 0 = empty
+  uint32_t tflag[SMALL_TAB];                  // 2: named by two reads or more; 4: some Q > minQual
   int32_t colmut[SMALL_MUTS];                 // column -> mutation id
   uint32_t near[3][32];                       // near[e-1][a]: buckets b of the component with dist(a, b) <= 2e
+  int32_t bid[32];                            // local bucket -> bucket id
 };
 
-SIMT_FN uint32_t small_hash(int32_t mut) { return ((uint32_t)mut * 0x9E3779B1u) >> 26; }      // 6 bits
+SIMT_FN uint32_t small_hash(int32_t mut) { return ((uint32_t)mut * 0x9E3779B1u) >> 25; }      // 7 bits
 
-// Returns 0 when the component was replayed, 1 when it is not eligible (nothing written).
-SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, SmallSmem *sm) {
+// Returns 0 when the component was replayed; otherwise nothing was written: 3 = more than 32 reads (not this kernel's
+// tier), 1 = not eligible (more than 32 live mutations, huge qualities), 2 = not eligible AND more than med_calls
+// genotype entries or med_pairs rows (too big for the medium kernel's local copy as well).
+SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, SmallSmem *sm, int32_t med_calls, int32_t med_pairs) {
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t lt = (1u << lane) - 1u;
+  // The component's buckets are comp_buckets[b_lo .. b_hi) (ascending bucket id), bucket b's reads are
+  // bucket_reads[bucket_ptr[b] .. bucket_ptr[b + 1]) in arrival order -- the caller's numbering, nothing is gathered
+  // beforehand.  Lane L is the L-th read of that sequence; lane bi < B also keeps bucket bi (id, first lane, size).
   const int32_t b_lo = c.comp_ptr[comp], b_hi = c.comp_ptr[comp + 1];
-  const int32_t r_lo = c.bucket_ptr[b_lo], r_hi = c.bucket_ptr[b_hi];
-  const int32_t n = r_hi - r_lo, B = b_hi - b_lo;
-  if (n > SMALL_READS) return 1;
+  const int32_t B = b_hi - b_lo;
+  if (B > SMALL_READS) return 3;
+  int32_t myb = -1, mysz = 0, myx0 = 0;
+  if (lane < B) {
+    myb = c.comp_buckets ? c.comp_buckets[b_lo + lane] : b_lo + lane;
+    myx0 = c.bucket_ptr[myb]; mysz = c.bucket_ptr[myb + 1] - myx0;
+  }
+  int32_t incl = mysz;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int32_t tv = simt::shfl(FULL, incl, lane >= o ? lane - o : lane);
+    if (lane >= o) incl += tv;
+  }
+  const int32_t n = simt::shfl(FULL, incl, 31);
+  if (n > SMALL_READS) return 3;
+  const int32_t mystart = incl - mysz;
   const bool has = lane < n;
-  const int32_t r = r_lo + lane;
   const int32_t minQual = c.prm.minQual, minMatches = c.prm.minMatches;
   const double minJaccard = c.prm.minJaccard;
-  int32_t lex = 0, bc = 0, up = 0, bkt = 0, g0 = 0, g1 = 0;
+  const uint32_t starts = simt::reduce_or(FULL, lane < B ? (1u << mystart) : 0u);       // buckets are never empty
+  const int32_t bkt = simt::popc(starts & (2u * (1u << lane) - 1u)) - 1;              // my bucket: last start <= lane
+  const int32_t bsrc = has ? bkt : 0;
+  const int32_t k_in_b = lane - simt::shfl(FULL, mystart, bsrc), x0_of_b = simt::shfl(FULL, myx0, bsrc);
+  int32_t r = 0, lex = 0, bc = 0, up = 0, g0 = 0, g1 = 0;
   if (has) {
+    r = c.bucket_reads ? c.bucket_reads[x0_of_b + k_in_b] : x0_of_b + k_in_b;
     lex = c.lexrank[r]; bc = c.bc_id[r]; up = c.up_id ? c.up_id[r] : 0;
-    bkt = c.bucket_of_read[r] - b_lo; g0 = c.geno_ptr[r]; g1 = c.geno_ptr[r + 1];
+    g0 = c.geno_ptr[r]; g1 = c.geno_ptr[r + 1];
   }
+  sm->bid[lane] = myb;
 
   // ---- number the mutations of the component (column = rank of the table slot), fill the matrix
-  for (int32_t i = lane; i < n * SMALL_STRIDE; i += 32) { sm->sum[i] = 0; sm->cnt[i] = 0; }
-  sm->tab[lane] = 0; sm->tab[lane + 32] = 0;
+  {
+    struct alignas(16) Q16 { int32_t a, b, c, d; };             // 16-byte stores: rows 0..n-1 of both matrices
+    const Q16 zero = {0, 0, 0, 0};
+    Q16 *zs = (Q16 *)sm->sum, *zc = (Q16 *)sm->cnt;
+    for (int32_t i = lane; i < (n * SMALL_STRIDE + 3) / 4; i += 32) zs[i] = zero;
+    for (int32_t i = lane; i < (n * SMALL_STRIDE + 7) / 8; i += 32) zc[i] = zero;
+  }
+  for (int32_t i = lane; i < SMALL_TAB; i += 32) { sm->tab[i] = 0; sm->tflag[i] = 0u; }
+  // Jaccard as an integer threshold: lane u holds the smallest `inters` with (double)inters / (double)u > minJaccard
+  // (u + 1 if there is none; lane 0 holds the entry for u = 32).  The quotient grows with inters, so
+  // "inters / uni > minJaccard" (:358-367, :447-452) is exactly "inters >= thr[uni]" -- the same IEEE divide, done once.
+  int32_t thr;
+  {
+    const int32_t u = lane == 0 ? 32 : lane;
+    thr = u + 1;
+    for (int32_t i = u; i >= 0; i--) if ((double)i / (double)u > minJaccard) thr = i; else break;
+  }
   simt::sync(FULL);
+  // A mutation that a single read of the whole component names, with Q <= minQual, can never pass filterSeqError
+  // (:350-356: it is seen once and its sum stays <= minQual in any pair of clusters) nor be called in a cluster
+  // (Q - minQual * (size - 1) <= 0): such DEAD mutations -- the private sequencing-error calls -- get no column.
   bool bad = false;
   for (int32_t e = g0; e < g1; e++) {
     const int32_t mut = c.geno_mut[e], q = c.geno_q[e];
@@ -81,24 +125,44 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
     for (int probes = 0;; probes++) {
       if (probes == SMALL_TAB) { bad = true; break; }
       const int32_t old = simt::atomic_cas(&sm->tab[h], 0, mut + 1);
-      if (old == 0 || old == mut + 1) break;
+      if (old == 0 || old == mut + 1) {
+        const uint32_t f = (old != 0 ? 2u : 0u) | (q > minQual ? 4u : 0u);
+        if (f) simt::atomic_or(&sm->tflag[h], f);
+        break;
+      }
       h = (h + 1) & (SMALL_TAB - 1);
     }
   }
   simt::sync(FULL);
-  const uint32_t occ_lo = simt::ballot(FULL, sm->tab[lane] != 0), occ_hi = simt::ballot(FULL, sm->tab[lane + 32] != 0);
-  const int32_t n_lo = simt::popc(occ_lo), M = n_lo + simt::popc(occ_hi);
-  if (simt::ballot(FULL, bad) != 0u || M > SMALL_MUTS) return 1;
+  uint32_t live[SMALL_TAB / 32];
+  int32_t M = 0;
+#pragma unroll
+  for (int w = 0; w < SMALL_TAB / 32; w++) { live[w] = simt::ballot(FULL, sm->tflag[32 * w + lane] != 0u); M += simt::popc(live[w]); }
+  if (simt::ballot(FULL, bad) != 0u || M > SMALL_MUTS) {
+    int32_t ne = g1 - g0;
+    for (int o = 16; o > 0; o >>= 1) ne += simt::shfl(FULL, ne, lane ^ o);
+    return (ne > med_calls || c.cpair_ptr[comp + 1] - c.cpair_ptr[comp] > med_pairs) ? 2 : 1;
+  }
   {
-    const int32_t t0 = sm->tab[lane], t1 = sm->tab[lane + 32];
-    if (t0) sm->colmut[simt::popc(occ_lo & lt)] = t0 - 1;
-    if (t1) sm->colmut[n_lo + simt::popc(occ_hi & lt)] = t1 - 1;
+    int32_t base = 0;
+#pragma unroll
+    for (int w = 0; w < SMALL_TAB / 32; w++) {
+      if ((live[w] >> lane) & 1u) sm->colmut[base + simt::popc(live[w] & lt)] = sm->tab[32 * w + lane] - 1;
+      base += simt::popc(live[w]);
+    }
   }
   for (int32_t e = g0; e < g1; e++) {
     const int32_t mut = c.geno_mut[e], q = c.geno_q[e];
     uint32_t h = small_hash(mut);
     while (sm->tab[h] != mut + 1) h = (h + 1) & (SMALL_TAB - 1);
-    const int32_t col = h < 32 ? simt::popc(occ_lo & ((1u << h) - 1u)) : n_lo + simt::popc(occ_hi & ((1u << (h - 32)) - 1u));
+    int32_t col = 0;
+    bool alive = false;
+#pragma unroll
+    for (int w = 0; w < SMALL_TAB / 32; w++) {
+      if ((int)(h >> 5) == w) { alive = ((live[w] >> (h & 31u)) & 1u) != 0u; col += simt::popc(live[w] & ((1u << (h & 31u)) - 1u)); }
+      else if ((int)(h >> 5) > w) col += simt::popc(live[w]);
+    }
+    if (!alive) continue;
     sm->sum[lane * SMALL_STRIDE + col] = q;                                      // mutation ids are distinct within a read
     sm->cnt[lane * SMALL_STRIDE + col] = (uint16_t)(0x100 | (q > 0 ? 1 : 0));
   }
@@ -118,7 +182,7 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
       while (b * (b - 1) / 2 > t) b--;
       while ((b + 1) * b / 2 <= t) b++;
       const int32_t a = t - b * (b - 1) / 2;
-      const int32_t d = lookup_dist(c, b_lo + a, b_lo + b);
+      const int32_t d = lookup_dist(c, sm->bid[a], sm->bid[b]);
       if (d >= 0)
         for (int32_t e = 1; e <= 3; e++)
           if (d <= 2 * e) { simt::atomic_or(&sm->near[e - 1][a], 1u << b); simt::atomic_or(&sm->near[e - 1][b], 1u << a); }
@@ -166,26 +230,39 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
 
   // ---- seed clustering, bucket by bucket (:385-400)
   for (int32_t bi = 0; bi < B; bi++) {
-    const int32_t lo = c.bucket_ptr[b_lo + bi] - r_lo, hi = c.bucket_ptr[b_lo + bi + 1] - r_lo;
+    const int32_t lo = simt::shfl(FULL, mystart, bi), hi = lo + simt::shfl(FULL, mysz, bi);
+    const int32_t bucket = simt::shfl(FULL, myb, bi);
     if (hi - lo < 2) continue;
     int32_t colcnt = 0, colsum = 0;
-    uint32_t mymask = 0;
+    uint32_t colall = 0, mymask = 0;
     for (int32_t x = lo; x < hi; x++) {
-      const uint32_t cv = sm->cnt[x * SMALL_STRIDE + lane] & 0xFFu;
-      colcnt += (int32_t)cv; colsum += sm->sum[x * SMALL_STRIDE + lane];
-      const uint32_t pm = simt::ballot(FULL, cv != 0u);           // mutations read x carries with Q > 0
+      const uint32_t cv = sm->cnt[x * SMALL_STRIDE + lane];
+      colall += cv; colcnt += (int32_t)(cv & 0xFFu); colsum += sm->sum[x * SMALL_STRIDE + lane];
+      const uint32_t pm = simt::ballot(FULL, (cv & 0xFFu) != 0u);           // mutations read x carries with Q > 0
       if (lane == x) mymask = pm;
     }
     const uint32_t kept = simt::ballot(FULL, colcnt > 1 || colsum > minQual);     // filterSeqError over the bucket (:350-356)
     mymask &= kept;
+    const bool inb = lane >= lo && lane < hi;
+    const uint32_t m0 = simt::shfl(FULL, mymask, lo);
+    if (simt::ballot(FULL, inb && mymask != m0) == 0u) {
+      // Every read of the bucket carries the same kept calls: every pair has Jaccard g/g, so either no pair links or
+      // the loop below links (r1, r0), then appends r2, r3, ...: one cluster r1, r0, r2, ..., created first in this bucket,
+      // whose sums are the column sums just taken.
+      const int32_t g = simt::popc(m0);
+      const int32_t tg = simt::shfl(FULL, thr, g & 31);
+      if (!(g == 0 || (g >= tg && g >= minMatches))) continue;
+      if (inb) { cid = lo + 1; pos = lane == lo + 1 ? 0 : lane == lo ? 1 : lane - lo; keyb = bucket; keyn = 0; }
+      sm->sum[(lo + 1) * SMALL_STRIDE + lane] = colsum;
+      sm->cnt[(lo + 1) * SMALL_STRIDE + lane] = (uint16_t)colall;
+      continue;
+    }
     int32_t n_created = 0;
     for (int32_t ri = lo + 1; ri < hi; ri++) {
       const uint32_t mi = simt::shfl(FULL, mymask, ri);
-      bool ok = false;
-      if (lane >= lo && lane < ri) {                               // calcJaccard of (read i, read j) on presence (:358-367)
-        const int32_t inters = simt::popc(mi & mymask), uni = simt::popc(mi | mymask);
-        ok = uni == 0 || ((double)inters / (double)uni > minJaccard && inters >= minMatches);
-      }
+      const int32_t inters = simt::popc(mi & mymask), uni = simt::popc(mi | mymask);        // calcJaccard on presence (:358-367)
+      const int32_t tu = simt::shfl(FULL, thr, uni & 31);
+      const bool ok = lane >= lo && lane < ri && (uni == 0 || (inters >= tu && inters >= minMatches));
       uint32_t J = simt::ballot(FULL, ok);
       int32_t ci = -1;                                             // read i is in no cluster when its row of pairs starts
       while (J) {
@@ -195,7 +272,7 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
         J &= ~((2u << j) - 1u);
         const int32_t cj = simt::shfl(FULL, cid, j);
         const bool fresh = ci < 0 && cj < 0;
-        PCB_LINK(ri, j, ci, cj, b_lo + bi, n_created);
+        PCB_LINK(ri, j, ci, cj, bucket, n_created);
         if (fresh) n_created++;
         ci = simt::shfl(FULL, cid, ri);
       }
@@ -206,8 +283,9 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
   int32_t n_links = 0, n_tests = 0;
   for (int32_t p = p_lo; p < p_hi; p++) {
     const int32_t ba = c.cpair_q[p], bb = c.cpair_r[p], ed = c.cpair_ed[p];
-    const int32_t xlo = c.bucket_ptr[ba] - r_lo, nx = c.bucket_ptr[ba + 1] - c.bucket_ptr[ba];
-    const int32_t ylo = c.bucket_ptr[bb] - r_lo, ny = c.bucket_ptr[bb + 1] - c.bucket_ptr[bb];
+    const int ia = simt::ffs(simt::ballot(FULL, myb == ba)) - 1, ib = simt::ffs(simt::ballot(FULL, myb == bb)) - 1;
+    const int32_t xlo = simt::shfl(FULL, mystart, ia), nx = simt::shfl(FULL, mysz, ia);
+    const int32_t ylo = simt::shfl(FULL, mystart, ib), ny = simt::shfl(FULL, mysz, ib);
     const uint32_t nearE = ed == 1 ? near1 : ed == 2 ? near2 : near3;
     // cluster pairs that failed since the last merge (within this row): the last four, -1 never matches an id pair
     int32_t ma0 = 0, mb0 = 0, ma1 = 0, mb1 = 0, ma2 = 0, mb2 = 0, ma3 = 0, mb3 = 0, memo_n = 0;
@@ -251,7 +329,7 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
           const bool keep = o1 + o2 > 1 || v1 + v2 > minQual;                    // filterSeqError across both clusters
           const int32_t inters = simt::popc(simt::ballot(FULL, keep && v1 > 0 && v2 > 0));
           const int32_t uni = simt::popc(simt::ballot(FULL, keep && (v1 > 0 || v2 > 0)));
-          if (!(uni == 0 || (double)inters / (double)uni > minJaccard)) break;   // genotype rule (:447-452)
+          if (!(uni == 0 || inters >= simt::shfl(FULL, thr, uni & 31))) break;    // genotype rule (:447-452)
           PCB_LINK(R1, R2, C1, C2, -1, -1);
           linked = true;
         } while (0);
@@ -266,7 +344,18 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
   }
 
   // ---- consensus and rows (:464-477, :515-537, :546-567)
-  int64_t call_base = c.call_off[comp];
+  // call region: as many entries as the component's reads carry (an upper bound of its calls), taken from the shared
+  // cursor when the caller lays regions out dynamically (call_off == nullptr)
+  int64_t call_base = 0;
+  if (c.call_off) call_base = c.call_off[comp];
+  else {
+    int32_t ne = g1 - g0;
+    for (int o = 16; o > 0; o >>= 1) ne += simt::shfl(FULL, ne, lane ^ o);
+    int32_t lo32 = 0, hi32 = 0;
+    if (lane == 0) { const int64_t at = simt::atomic_add64(c.call_cursor, (int64_t)ne); lo32 = (int32_t)(at & 0xFFFFFFFFll); hi32 = (int32_t)(at >> 32); }
+    lo32 = simt::shfl(FULL, lo32, 0); hi32 = simt::shfl(FULL, hi32, 0);
+    call_base = ((int64_t)hi32 << 32) | (int64_t)(uint32_t)lo32;
+  }
   int32_t up_err_head = -1;
   uint32_t heads = simt::ballot(FULL, cid >= 0 && pos == 0);
   while (heads) {
@@ -276,7 +365,8 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
     const uint32_t mem = simt::ballot(FULL, cid == ch);
     const int32_t size = simt::popc(mem);
     const bool in = ((mem >> lane) & 1u) != 0u;
-    if (in) { c.read_root[r] = r_lo + h; c.read_pos[r] = pos; if (lane != h) c.row_size[r] = 0; }
+    const int32_t r_head = simt::shfl(FULL, r, h);
+    if (in) { c.read_root[r] = r_head; c.read_pos[r] = pos; if (lane != h) c.row_size[r] = 0; }
     // genotype vote (:468-470): Q where a member names the mutation, -minQual where it does not
     const int32_t sv = sm->sum[ch * SMALL_STRIDE + lane], any = sm->cnt[ch * SMALL_STRIDE + lane] >> 8;
     const bool called = lane < M && (int64_t)sv - (int64_t)minQual * (int64_t)(size - any) > 0;
@@ -293,7 +383,7 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
     for (int w = 0; w < 2; w++) {
       if (w == 1 && !c.up_id) { cons[1] = cons[0]; break; }
       const int32_t id = w == 0 ? bc : up;
-      if (w == 1 && simt::ballot(FULL, in && id < 0) != 0u) up_err_head = r_lo + h;     // clustered read without uptag: KeyError (:519)
+      if (w == 1 && simt::ballot(FULL, in && id < 0) != 0u) up_err_head = r_head;     // clustered read without uptag: KeyError (:519)
       const int32_t v = id < 0 ? 0x7ffffffe : id;
       int32_t votes = 0;
       if (in) votes = simt::popc(simt::match_any(mem, v));

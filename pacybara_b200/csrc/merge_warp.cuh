@@ -326,7 +326,13 @@ __device__ __forceinline__ void process_component_warp(const MergeCtx &c, const 
 
   // ---- consensus + rows (:464-477, :515-537, :546-567)
   w_table_clear(t, lane);
-  int64_t call_pos = c.call_off[comp];
+  int64_t call_pos = 0;
+  {
+    int32_t lo32 = 0, hi32 = 0;
+    if (lane == 0) { const int64_t at = component_call_base(c, comp); lo32 = (int32_t)(at & 0xFFFFFFFFll); hi32 = (int32_t)(at >> 32); }
+    lo32 = __shfl_sync(PCB_FULL, lo32, 0); hi32 = __shfl_sync(PCB_FULL, hi32, 0);
+    call_pos = ((int64_t)hi32 << 32) | (int64_t)(uint32_t)lo32;
+  }
   int32_t err = 0;
   for (int32_t bi = b_lo; bi < b_hi; bi++) {
     const int32_t b = c.comp_buckets ? c.comp_buckets[bi] : bi;

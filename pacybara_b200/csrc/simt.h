@@ -23,6 +23,7 @@ SIMT_FN void sync(uint32_t mask) { __syncwarp(mask); }
 SIMT_FN int32_t atomic_cas(int32_t *p, int32_t cmp, int32_t v) { return atomicCAS(p, cmp, v); }
 SIMT_FN uint32_t atomic_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
 SIMT_FN int32_t atomic_add(int32_t *p, int32_t v) { return atomicAdd(p, v); }
+SIMT_FN int64_t atomic_add64(int64_t *p, int64_t v) { return (int64_t)atomicAdd((unsigned long long *)p, (unsigned long long)v); }
 SIMT_FN int popc(uint32_t x) { return __popc(x); }
 SIMT_FN int ffs(uint32_t x) { return __ffs((int)x); }      // 1-based, 0 when x == 0
 SIMT_FN float sqrt_f(float x) { return sqrtf(x); }
@@ -45,6 +46,7 @@ void sync(uint32_t mask);
 inline int32_t atomic_cas(int32_t *p, int32_t cmp, int32_t v) { int32_t o = *p; if (o == cmp) *p = v; return o; }
 inline uint32_t atomic_or(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
 inline int32_t atomic_add(int32_t *p, int32_t v) { int32_t o = *p; *p = o + v; return o; }
+inline int64_t atomic_add64(int64_t *p, int64_t v) { int64_t o = *p; *p = o + v; return o; }
 inline int popc(uint32_t x) { return __builtin_popcount(x); }
 inline int ffs(uint32_t x) { return __builtin_ffs((int)x); }
 inline float sqrt_f(float x) { return sqrtf(x); }

@@ -154,10 +154,10 @@ def cluster_reads_sharded(ctx: Context, arrs: Dict, params: Dict, rank: int, wor
                         min_qual=int(params["min_qual"]), min_jaccard=float(params["min_jaccard"]),
                         min_matches=int(params["min_matches"]))
     if full_table:
-        out = ctx.merge(prob, PairList(ei, ej, ed, ped), shard=(rank, world))
+        out = ctx.merge(prob, PairList(ei, ej, ed, ped), shard=(rank, world), pairs_sorted=True, shard_layout=combine)
     else:
         out = ctx.merge(prob, PairList(ei, ej, ed, ped), shard=(rank, world), bucket_seq=bseq, bucket_len=blen,
-                        on_demand_k=2 * max_diff)
+                        on_demand_k=2 * max_diff, pairs_sorted=True, shard_layout=combine)
     lib_stages("prep", "replay", "scatter")
     local_stats.update(links=ctx.stat("links"), tests=ctx.stat("tests"), components=ctx.stat("components"))
     # 5. result

@@ -31,9 +31,8 @@ extern "C" int emul_merge(int32_t R, int32_t U, const int32_t *bucket_ptr, const
                           int32_t *row_bc, int32_t *row_up, int64_t *row_call_off, int32_t *row_call_n,
                           int32_t *call_mut, int32_t *status,
                           const uint64_t *planes, const int32_t *blen, int32_t compute_k, int32_t wide, int32_t use_small) {
-  // use_small != 0: the caller numbered buckets and reads in component order (as csrc/merge.cu does before the replay);
-  // every component then goes through process_component_small() on an emulated warp first (use_small = lane-order
-  // seed), and through process_component() only if that declines.  status[1] returns how many components it took.
+  // use_small != 0: every component goes through process_component_small() on an emulated warp first (use_small =
+  // lane-order seed), and through process_component() only if that declines.  status[1] returns how many it took.
   std::vector<int32_t> bucket_of_read(R);
   for (int32_t b = 0; b < U; b++)
     for (int32_t x = bucket_ptr[b]; x < bucket_ptr[b + 1]; x++) bucket_of_read[bucket_reads[x]] = b;
@@ -123,17 +122,14 @@ extern "C" int emul_merge(int32_t R, int32_t U, const int32_t *bucket_ptr, const
   c.call_mut = call_mut; c.status = status;
   c.prm.maxDiff = max_diff; c.prm.minQual = min_qual; c.prm.minMatches = min_matches; c.prm.minJaccard = min_jaccard;
   int32_t n_small = 0;
-  if (use_small) {
-    for (int32_t i = 0; i < U; i++) if (comp_buckets[i] != i) return -1;
-    for (int32_t x = 0; x < R; x++) if (bucket_reads[x] != x) return -1;
-    c.comp_buckets = nullptr; c.bucket_reads = nullptr;
-  }
+  int64_t call_cursor = 0;
+  if (use_small) { c.call_off = nullptr; c.call_cursor = &call_cursor; }     // regions from the shared cursor, like csrc/merge.cu
   static SmallSmem smem;
   for (int32_t comp = 0; comp < n_comp; comp++) {
     if (label[comp_buckets[comp_ptr[comp]]] % shard_count != shard_rank) continue;
     if (use_small) {
       int rc[32];
-      simt_emul::run_warp([&](int lane) { rc[lane] = process_component_small(c, comp, lane, &smem); }, (unsigned)(use_small + comp));
+      simt_emul::run_warp([&](int lane) { rc[lane] = process_component_small(c, comp, lane, &smem, 1 << 30, 1 << 30); }, (unsigned)(use_small + comp));
       for (int l = 1; l < 32; l++) if (rc[l] != rc[0]) return -2;
       if (rc[0] == 0) { n_small++; continue; }
     }

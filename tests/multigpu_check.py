@@ -36,10 +36,12 @@ def main():
                                dev["geno_mut"], dev["geno_q"], dev["mut_rank"], full_table=full, **params)
     bad = [k for k in ("read_root", "read_pos", "row_size", "row_key", "row_bc", "row_up", "row_call_n", "bucket_of_read")
            if not torch.equal(out[k], single[k])]
-    # call_mut offsets are component-relative in both runs, so the arrays must agree too
-    if not torch.equal(out["call_mut"], single["call_mut"]) or not torch.equal(out["row_call_off"], single["row_call_off"]):
-        bad.append("calls")
     assert not bad, f"rank {rank}: sharded != single-GPU in {bad}"
+    # where a row's calls sit in call_mut depends on the run (regions are handed out as components come by): compare rows
+    from pacybara_b200 import hostdata as _hd
+    ra_, rb_ = (_hd.rows_from_merge_outputs({k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in o.items()}) for o in (out, single))
+    for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
+        assert np.array_equal(getattr(ra_, f), getattr(rb_, f)), f"rank {rank}: sharded != single-GPU in {f}"
     assert out["n_edges"] == single["n_edges"]
     host = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in out.items()}
     digest = canon.table_digest(canon.canon_table(pipeline.table_from_outputs(host, ra, names)))
@@ -54,6 +56,8 @@ def main():
     part = multigpu.cluster_reads_sharded(ctx, dev, params, rank, world, on_device=True, full_table=full, combine=False)
     owned = int((part["read_root"] != -(1 << 31)).sum())
     for k in names:
+        if k in ("row_call_off", "call_mut"):
+            continue                       # run-dependent layout without PCB_MERGE_SHARD_LAYOUT; the compacted shards below carry the calls
         t = part[k].clone()
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         assert torch.equal(t, single[k]), f"rank {rank}: max over shards != single-GPU in {k}"

@@ -106,59 +106,11 @@ def pack_planes(seq: np.ndarray, length: np.ndarray) -> np.ndarray:
     return np.ascontiguousarray(np.stack([L, H], axis=1))
 
 
-def renumber_in_component_order(p: hostdata.MergeProblem, pairs: hostdata.PairList, planes=None, blen=None):
-    """What csrc/merge.cu does before the replay, in numpy: buckets grouped by connected component of the rows a pass
-    visits, reads grouped by bucket in arrival order.  Returns the renumbered problem and pairs plus the maps back."""
-    from scipy.sparse import coo_matrix
-    from scipy.sparse.csgraph import connected_components
-    U, R = p.n_buckets, p.n_reads
-    vis = np.asarray(pairs.ed) >= 1
-    g = coo_matrix((np.ones(int(vis.sum()), dtype=np.int8), (np.asarray(pairs.q)[vis], np.asarray(pairs.r)[vis])), shape=(U, U))
-    _, lab = connected_components(g, directed=False)
-    first = np.full(lab.max() + 1 if U else 0, U, dtype=np.int64)
-    np.minimum.at(first, lab, np.arange(U))
-    old_of_new_b = np.lexsort((np.arange(U), first[lab])).astype(np.int32)
-    new_of_old_b = np.empty(U, dtype=np.int32)
-    new_of_old_b[old_of_new_b] = np.arange(U, dtype=np.int32)
-    sizes = np.diff(p.bucket_ptr)[old_of_new_b]
-    nb_ptr = np.zeros(U + 1, dtype=np.int32)
-    np.cumsum(sizes, out=nb_ptr[1:])
-    old_of_new_r = np.concatenate([p.bucket_reads[p.bucket_ptr[b]:p.bucket_ptr[b + 1]] for b in old_of_new_b]).astype(np.int32) \
-        if U else np.zeros(0, dtype=np.int32)
-    gcnt = np.diff(p.geno_ptr)[old_of_new_r]
-    n_gptr = np.zeros(R + 1, dtype=np.int32)
-    np.cumsum(gcnt, out=n_gptr[1:])
-    src = np.repeat(p.geno_ptr[:-1][old_of_new_r] - n_gptr[:-1], gcnt) + np.arange(int(n_gptr[-1]))
-    q = hostdata.MergeProblem(n_reads=R, n_buckets=U, bucket_ptr=nb_ptr, bucket_reads=np.arange(R, dtype=np.int32),
-                              lexrank=p.lexrank[old_of_new_r], bc_id=p.bc_id[old_of_new_r],
-                              up_id=None if p.up_id is None else p.up_id[old_of_new_r], geno_ptr=n_gptr,
-                              geno_mut=p.geno_mut[src], geno_q=p.geno_q[src], mut_rank=p.mut_rank, max_diff=p.max_diff,
-                              min_qual=p.min_qual, min_jaccard=p.min_jaccard, min_matches=p.min_matches)
-    npairs = hostdata.PairList(new_of_old_b[pairs.q], new_of_old_b[pairs.r], np.asarray(pairs.d), np.asarray(pairs.ed))
-    nplanes = None if planes is None else np.ascontiguousarray(planes[old_of_new_b])
-    nblen = None if blen is None else np.ascontiguousarray(np.asarray(blen)[old_of_new_b])
-    return q, npairs, nplanes, nblen, old_of_new_r, old_of_new_b
-
-
-def emul_merge_small(p: hostdata.MergeProblem, pairs: hostdata.PairList, planes=None, blen=None, compute_k=-1, seed=1):
-    """The warp kernel for small components (csrc/merge_small.cuh) on an emulated warp, generic replay for the rest;
-    outputs in the caller's numbering (the scatter of csrc/merge.cu).  out['n_small'] = components it replayed."""
-    q, npairs, nplanes, nblen, old_r, old_b = renumber_in_component_order(p, pairs, planes, blen)
-    o = emul_merge(q, npairs, planes=nplanes, blen=nblen, compute_k=compute_k, use_small=seed)
-    out = {}
-    for k, dt in hostdata.MERGE_OUTPUTS:
-        a = np.empty_like(o[k])
-        a[old_r] = o[k]
-        out[k] = a
-    root = out["read_root"]
-    out["read_root"] = np.where(root >= 0, old_r[np.clip(root, 0, None)], root).astype(np.int32)
-    key = out["row_key"]
-    pos_key = key >= 0
-    out["row_key"] = np.where(pos_key, (old_b[np.clip(key >> 32, 0, None)].astype(np.int64) << 32) | (key & 0xFFFFFFFF), key)
-    out["call_mut"] = o["call_mut"]
-    out["status"] = o["status"]
-    out["n_components"] = o["n_components"]
-    out["n_small"] = int(o["status"][1]) if o["status"][0] == 0 else 0
+def emul_merge_small(p: hostdata.MergeProblem, pairs: hostdata.PairList, planes=None, blen=None, compute_k=-1, seed=1, shard=(0, 1)):
+    """The warp kernel for small components (csrc/merge_small.cuh) on an emulated warp, generic replay for the rest.
+    out['n_small'] = components it replayed."""
+    out = emul_merge(p, pairs, shard=shard, planes=planes, blen=blen, compute_k=compute_k, use_small=seed)
+    out["n_small"] = int(out["status"][1]) if out["status"][0] == 0 else 0
     return out
 
 
