@@ -381,9 +381,18 @@ int pcb_cluster_reads(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *
     stage_begin(ctx);
     PackedBarcodes uniq;
     BucketOut bo{bor, bptr.p, breads.p, nullptr};
-    int32_t U = bucket_reads_dev(ctx, d_seq.p, nullptr, d_len.p, R, stride, bo, &uniq);
+    int32_t U = 0;
+    if (R > 0) {
+      BucketPending pending;
+      bucket_launch(ctx, d_seq.p, d_len.p, R, stride, bo, &uniq, pending);
+      stage_end(ctx, PCB_STAT_T_BUCKET_NS);
+      PCB_CUDA(cudaStreamSynchronize(ctx->stream));           // round trip 1 of the call: U, input errors, lengths seen
+      U = bucket_finish(ctx, bo, &uniq, pending);
+    } else {
+      uniq.n = 0; uniq.planes.alloc(ctx, 0); uniq.len.alloc(ctx, 0);
+      stage_end(ctx, PCB_STAT_T_BUCKET_NS);
+    }
     if (n_buckets) *n_buckets = U;
-    stage_end(ctx, PCB_STAT_T_BUCKET_NS);
     // a2+a3: either the full table up to 2*maxDiff (what pacybara.sh:466-468 asks of calcEdits.R), or only
     // the pairs a pass can visit (<= maxDiff) with the transitive-rule distances scored on demand
     const bool full = (flags & PCB_CLUSTER_FULL_TABLE) != 0;

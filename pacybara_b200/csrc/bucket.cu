@@ -2,63 +2,90 @@
 //
 // Replaces the dictionary of src/pacybara_precluster.py:28-39 and its first-seen output
 // order (:68-76).  Reads are packed to 2-bit planes, inserted into an open-addressing table
-// keyed by (planes, length), buckets are numbered by the smallest read index they contain
-// (= first-seen order), reads are grouped by a stable radix sort (= arrival order inside each
-// bucket), and the per-position qualities are summed with the reference's cap of 93.
-// All of it is HBM-bound: per read W+4 bytes in (planes + length), 8 bytes out, plus
-// 2 * stride bytes of quality traffic.
+// keyed by (planes, length) whose 8-byte slots hold (smallest read index, count); buckets are
+// numbered by the smallest read index they contain (= first-seen order); every read takes a place
+// in its bucket's segment with one atomic and the segments are then put into ascending read order
+// (= arrival order) bucket by bucket -- no sort over all reads; the per-position qualities are
+// summed with the reference's cap of 93.  The whole stage is launched without a host round trip.
+// HBM-bound, and at the 2*10^7-read size bound by RANDOM sector accesses: about 6 per read
+// (slot, the slot owner's planes and length, slot again for the bucket number, the bucket's cursor
+// and pointer, the place) against 15 with the three-array table and the radix sort of round 1.
 #include "common.cuh"
 #include "myers.cuh"
 
 namespace pcb {
 
-// flags[0] = first offending row + 1 (0: none), flags[1] = min length, flags[2] = max length
-__global__ void pack_kernel(const uint8_t *__restrict__ seq, const int32_t *__restrict__ len,
-                            const int32_t *__restrict__ rows, int32_t n, int32_t stride,
-                            ulonglong2 *__restrict__ planes, int32_t *__restrict__ out_len, int32_t *flags,
-                            uint64_t *__restrict__ other) {
+// flags[0] = first offending row + 1 (0xFFFFFFFF: none), flags[1] = min length, flags[2] = max length,
+// flags[4 + m] = barcodes of length m (m = 1..64): the pair search picks its seed lengths from that histogram
+constexpr int PACK_FLAGS = 4 + 66;
+__global__ void __launch_bounds__(128) pack_kernel(const uint8_t *__restrict__ seq, const int32_t *__restrict__ len,
+                                                   const int32_t *__restrict__ rows, int32_t n, int32_t stride,
+                                                   ulonglong2 *__restrict__ planes, int32_t *__restrict__ out_len, int32_t *flags,
+                                                   uint64_t *__restrict__ other) {
+  __shared__ uint32_t sh_hist[66];
+  if (threadIdx.x < 66) sh_hist[threadIdx.x] = 0;
+  __syncthreads();
   int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int32_t row = rows ? rows[i] : i;
-  int32_t m = len[row];
-  bool bad = m < 1 || m > 64 || m > stride;
-  uint64_t L = 0, H = 0, X = 0;
-  if (!bad) {
-    const uint8_t *s = seq + (size_t)row * stride;
-    for (int32_t t = 0; t < m; t++) {
-      uint32_t c = base_code(s[t]);
-      if (c > 3u) { bad |= other == nullptr; X |= 1ull << t; c = 0u; }
-      L |= (uint64_t)(c & 1u) << t;
-      H |= (uint64_t)((c >> 1) & 1u) << t;
+  if (i < n) {
+    int32_t row = rows ? rows[i] : i;
+    int32_t m = len[row];
+    bool bad = m < 1 || m > 64 || m > stride;
+    uint64_t L = 0, H = 0, X = 0;
+    if (!bad) {
+      const uint8_t *s = seq + (size_t)row * stride;
+      for (int32_t t = 0; t < m; t++) {
+        uint32_t c = base_code(s[t]);
+        if (c > 3u) { bad |= other == nullptr; X |= 1ull << t; c = 0u; }
+        L |= (uint64_t)(c & 1u) << t;
+        H |= (uint64_t)((c >> 1) & 1u) << t;
+      }
     }
+    planes[i] = make_ulonglong2(L, H);
+    if (other) other[i] = X;
+    out_len[i] = m;
+    if (bad) atomicMin((uint32_t *)&flags[0], (uint32_t)i + 1u);
+    else atomicAdd(&sh_hist[m], 1u);
   }
-  planes[i] = make_ulonglong2(L, H);
-  if (other) other[i] = X;
-  out_len[i] = m;
-  if (bad) { atomicMin((uint32_t *)&flags[0], (uint32_t)i + 1u); return; }
-  atomicMin(&flags[1], m);
-  atomicMax(&flags[2], m);
+  __syncthreads();
+  if (threadIdx.x >= 1 && threadIdx.x <= 64 && sh_hist[threadIdx.x]) {
+    atomicAdd((uint32_t *)&flags[4 + threadIdx.x], sh_hist[threadIdx.x]);
+    atomicMin(&flags[1], (int32_t)threadIdx.x);
+    atomicMax(&flags[2], (int32_t)threadIdx.x);
+  }
 }
 
-void pack_barcodes(pcb_ctx *ctx, const uint8_t *seq, const int32_t *len, const int32_t *rows, int32_t n,
-                   int32_t stride, PackedBarcodes &out, bool allow_other) {
+// launches the packing; the flags stay on the device until pack_finish() has them (after a stream synchronisation)
+void pack_launch(pcb_ctx *ctx, const uint8_t *seq, const int32_t *len, const int32_t *rows, int32_t n, int32_t stride,
+                 PackedBarcodes &out, bool allow_other, DevBuf<int32_t> &flags) {
   out.planes.alloc(ctx, (size_t)n);
   out.len.alloc(ctx, (size_t)n);
   if (allow_other) out.other.alloc(ctx, (size_t)n);
   out.n = n;
-  DevBuf<int32_t> flags(ctx, 4);
-  int32_t init[4] = {-1, 1 << 30, 0, 0};     // flags[0] as unsigned: 0xFFFFFFFF = none
-  PCB_CUDA(cudaMemcpyAsync(flags.p, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
+  flags.alloc(ctx, PACK_FLAGS);
+  PCB_CUDA(cudaMemsetAsync(flags.p, 0, PACK_FLAGS * sizeof(int32_t), ctx->stream));
+  PCB_CUDA(cudaMemsetAsync(flags.p, 0xFF, sizeof(int32_t), ctx->stream));                 // flags[0] as unsigned: 0xFFFFFFFF = none
+  PCB_CUDA(cudaMemsetAsync(flags.p + 1, 0x7F, sizeof(int32_t), ctx->stream));             // min length: a large value
   if (n > 0) PCB_LAUNCH(ctx, pack_kernel, grid_for(n, 128), 128, 0, seq, len, rows, n, stride, out.planes.p, out.len.p, flags.p,
                         allow_other ? out.other.p : nullptr);
-  int32_t h[4];
-  PCB_CUDA(cudaMemcpyAsync(h, flags.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
-  PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+}
+void pack_finish(PackedBarcodes &out, const int32_t *h, bool allow_other) {
   if (h[0] != -1)
     throw Error(PCB_E_INPUT, "barcode " + std::to_string((uint32_t)h[0] - 1u) +
                                  (allow_other ? " is not 1..64 characters long" : " is not 1..64 bases over ACGT (no side path exists for such barcodes)"));
-  out.min_len = n ? h[1] : 0;
-  out.max_len = n ? h[2] : 0;
+  out.min_len = out.n ? h[1] : 0;
+  out.max_len = out.n ? h[2] : 0;
+  for (int m = 0; m < 66; m++) out.len_hist[m] = (uint32_t)h[4 + m];
+  out.has_hist = true;
+}
+
+void pack_barcodes(pcb_ctx *ctx, const uint8_t *seq, const int32_t *len, const int32_t *rows, int32_t n,
+                   int32_t stride, PackedBarcodes &out, bool allow_other) {
+  DevBuf<int32_t> flags;
+  pack_launch(ctx, seq, len, rows, n, stride, out, allow_other, flags);
+  int32_t h[PACK_FLAGS];
+  PCB_CUDA(cudaMemcpyAsync(h, flags.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  pack_finish(out, h, allow_other);
 }
 
 __device__ __forceinline__ uint32_t hash_barcode(ulonglong2 p, int32_t m) {
@@ -67,56 +94,126 @@ __device__ __forceinline__ uint32_t hash_barcode(ulonglong2 p, int32_t m) {
   return (uint32_t)x;
 }
 
-// Every read finds (or claims) the table slot of its barcode; the slot remembers the smallest
-// read index that landed in it and how many did.
+// Open-addressing table over the barcodes.  A slot is 8 bytes: the smallest read index that landed in it so far -- which
+// also names the slot's barcode, any read of a bucket does -- and how many reads did.  One 32-byte sector per probe.
+struct BucketSlot { int32_t first; uint32_t count; };
+constexpr int32_t SLOT_EMPTY = 0x7F7F7F7F;          // what cudaMemset(0x7F) leaves; larger than any read index
+
 __global__ void bucket_insert_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int32_t R,
-                                     int32_t *owner, int32_t *first, uint32_t *count, uint32_t mask,
-                                     int32_t *__restrict__ slot_of_read) {
+                                     BucketSlot *slot, uint32_t mask, int32_t *__restrict__ slot_of_read) {
   int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
-  ulonglong2 p = planes[r];
-  int32_t m = len[r];
+  const ulonglong2 p = planes[r];
+  const int32_t m = len[r];
   uint32_t s = hash_barcode(p, m) & mask;
   for (;;) {
-    int32_t o = owner[s];
-    if (o < 0) {
-      o = atomicCAS(&owner[s], -1, r);
-      if (o < 0) o = r;
+    int32_t f = *(volatile int32_t *)&slot[s].first;
+    if (f == SLOT_EMPTY) {
+      const int32_t old = atomicCAS(&slot[s].first, SLOT_EMPTY, r);
+      f = old == SLOT_EMPTY ? r : old;
     }
-    if (o == r) break;
-    ulonglong2 po = planes[o];
-    if (po.x == p.x && po.y == p.y && len[o] == m) break;
+    if (f == r) break;
+    const ulonglong2 po = planes[f];
+    if (po.x == p.x && po.y == p.y && len[f] == m) { if (r < f) atomicMin(&slot[s].first, r); break; }
     s = (s + 1) & mask;
   }
-  atomicMin(&first[s], r);
-  atomicAdd(&count[s], 1u);
+  atomicAdd(&slot[s].count, 1u);
   slot_of_read[r] = (int32_t)s;
 }
 
-__global__ void bucket_flag_first_kernel(const int32_t *__restrict__ slot_of_read, const int32_t *__restrict__ first, int32_t R,
-                                         uint32_t *__restrict__ is_first) {
-  int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < R) is_first[r] = first[slot_of_read[r]] == r ? 1u : 0u;
+// first reads of the buckets (= first-seen order of the barcodes)
+__global__ void bucket_flag_first_kernel(const BucketSlot *__restrict__ slot, uint32_t cap, uint32_t *__restrict__ is_first) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= cap) return;
+  const int32_t f = slot[s].first;
+  if (f != SLOT_EMPTY) is_first[f] = 1u;
 }
 
-// rank[r] = number of first reads before r: for a first read that is its bucket index
-__global__ void bucket_number_kernel(const int32_t *__restrict__ slot_of_read, const int32_t *__restrict__ first,
-                                     const uint32_t *__restrict__ rank, const uint32_t *__restrict__ count, int32_t R,
-                                     int32_t *__restrict__ bucket_of_read, uint32_t *__restrict__ bucket_cnt,
-                                     uint64_t *__restrict__ sort_key) {
+// rank[r] = number of first reads before r: for a first read that is its bucket index.  Per occupied slot: the bucket
+// number replaces `first` in the slot; the bucket's size, packed barcode and length go to the bucket arrays.
+__global__ void bucket_number_kernel(BucketSlot *__restrict__ slot, uint32_t cap, const uint32_t *__restrict__ rank,
+                                     const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len,
+                                     uint32_t *__restrict__ bucket_cnt, ulonglong2 *__restrict__ uplanes, int32_t *__restrict__ ulen) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= cap) return;
+  const int32_t f = slot[s].first;
+  if (f == SLOT_EMPTY) return;
+  const uint32_t b = rank[f];
+  slot[s].first = (int32_t)b;
+  bucket_cnt[b] = slot[s].count - 0x7F7F7F7Fu;          // the table was filled with 0x7F bytes: counts started there
+  if (uplanes) { uplanes[b] = planes[f]; ulen[b] = len[f]; }
+}
+
+// every read takes a place in its bucket's segment (in whatever order the atomics resolve; bucket_order_kernel fixes it)
+__global__ void bucket_place_kernel(const int32_t *__restrict__ slot_of_read, const BucketSlot *__restrict__ slot, int32_t R,
+                                    const int32_t *__restrict__ bucket_ptr, uint32_t *__restrict__ cursor,
+                                    int32_t *__restrict__ bucket_of_read, int32_t *__restrict__ bucket_reads) {
   int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= R) return;
-  int32_t s = slot_of_read[r];
-  int32_t f = first[s];
-  uint32_t b = rank[f];
-  bucket_of_read[r] = (int32_t)b;
-  sort_key[r] = b;
-  if (f == r) bucket_cnt[b] = count[s];
+  const int32_t b = slot[slot_of_read[r]].first;
+  bucket_of_read[r] = b;
+  bucket_reads[bucket_ptr[b] + (int32_t)atomicAdd(&cursor[b], 1u)] = r;
 }
 
-__global__ void copy_u32_to_i32_kernel(const uint32_t *__restrict__ in, int32_t *__restrict__ out, size_t n) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = (int32_t)in[i];
+// Arrival order inside a bucket = ascending read index.  Buckets of up to 32 reads (nearly all): one thread sorts its
+// segment; up to 4096: on the `mid` list for one block each; more: on the `big` list, sorted by the host with the radix sort.
+constexpr int ORDER_THREAD = 32, ORDER_BLOCK = 4096;
+// counters: [0] = U (number of buckets), [1] = mid buckets, [2] = big buckets
+__global__ void bucket_order_kernel(const uint32_t *__restrict__ rank, int32_t R, const int32_t *__restrict__ bucket_ptr,
+                                    int32_t *__restrict__ bucket_reads, int32_t *__restrict__ counters, int32_t *__restrict__ mid,
+                                    int32_t *__restrict__ big) {
+  int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int32_t U = (int32_t)rank[R];
+  if (b == 0) counters[0] = U;
+  if (b >= U) return;
+  const int32_t lo = bucket_ptr[b], n = bucket_ptr[b + 1] - lo;
+  if (n <= 1) return;
+  if (n > ORDER_BLOCK) { big[atomicAdd(&counters[2], 1)] = b; return; }
+  if (n > ORDER_THREAD) { mid[atomicAdd(&counters[1], 1)] = b; return; }
+  int32_t v[ORDER_THREAD];
+  for (int32_t i = 0; i < n; i++) {                      // insertion sort
+    const int32_t x = bucket_reads[lo + i];
+    int32_t k = i - 1;
+    while (k >= 0 && v[k] > x) { v[k + 1] = v[k]; k--; }
+    v[k + 1] = x;
+  }
+  for (int32_t i = 0; i < n; i++) bucket_reads[lo + i] = v[i];
+}
+
+__global__ void __launch_bounds__(256) bucket_order_mid_kernel(const int32_t *__restrict__ bucket_ptr, int32_t *__restrict__ bucket_reads,
+                                                              const int32_t *__restrict__ counters, const int32_t *__restrict__ mid) {
+  __shared__ int32_t sh[ORDER_BLOCK];
+  const int32_t n_mid = counters[1];
+  for (int32_t it = blockIdx.x; it < n_mid; it += gridDim.x) {
+    const int32_t b = mid[it], lo = bucket_ptr[b], n = bucket_ptr[b + 1] - lo;
+    int32_t m = 64;
+    while (m < n) m <<= 1;
+    for (int32_t i = threadIdx.x; i < m; i += blockDim.x) sh[i] = i < n ? bucket_reads[lo + i] : INT32_MAX;
+    __syncthreads();
+    for (int32_t k = 2; k <= m; k <<= 1)                 // bitonic sort
+      for (int32_t j = k >> 1; j > 0; j >>= 1) {
+        for (int32_t i = threadIdx.x; i < m; i += blockDim.x) {
+          const int32_t l = i ^ j;
+          if (l > i) {
+            const int32_t a = sh[i], c = sh[l];
+            const bool up = (i & k) == 0;
+            if ((a > c) == up) { sh[i] = c; sh[l] = a; }
+          }
+        }
+        __syncthreads();
+      }
+    for (int32_t i = threadIdx.x; i < n; i += blockDim.x) bucket_reads[lo + i] = sh[i];
+    __syncthreads();
+  }
+}
+
+__global__ void u32_keys_kernel(const int32_t *__restrict__ v, int64_t n, uint64_t *__restrict__ key, uint32_t *__restrict__ val) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { key[i] = (uint64_t)(uint32_t)v[i]; val[i] = 0u; }
+}
+__global__ void u32_unkeys_kernel(const uint64_t *__restrict__ key, int64_t n, int32_t *__restrict__ v) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = (int32_t)key[i];
 }
 
 // One thread per (bucket, position): min(93, sum of Phred) -- the running min(93, old + new) of
@@ -138,14 +235,69 @@ __global__ void bucket_qsum_kernel(const uint8_t *__restrict__ qual, const int32
   qsum[i] = (uint8_t)acc;
 }
 
-__global__ void gather_first_kernel(const int32_t *__restrict__ bucket_ptr, const int32_t *__restrict__ bucket_reads, int32_t U,
-                                    const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len,
-                                    ulonglong2 *__restrict__ uplanes, int32_t *__restrict__ ulen) {
-  int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= U) return;
-  int32_t r = bucket_reads[bucket_ptr[b]];
-  uplanes[b] = planes[r];
-  ulen[b] = len[r];
+// Launches the bucketing of R reads; nothing is synchronised.  What the host has to know -- the packing flags and the
+// counters (number of buckets, buckets left for the block / radix orderings) -- stays in st until bucket_finish().
+void bucket_launch(pcb_ctx *ctx, const uint8_t *seq, const int32_t *len, int32_t R, int32_t stride, const BucketOut &out,
+                   PackedBarcodes *unique_out, BucketPending &st) {
+  st.R = R;
+  pack_launch(ctx, seq, len, nullptr, R, stride, st.pk, false, st.flags);
+  uint32_t cap = 64;
+  while (cap < 2u * (uint32_t)R) cap <<= 1;
+  DevBuf<BucketSlot> slot(ctx, cap);
+  DevBuf<int32_t> slot_of_read(ctx, R);
+  DevBuf<uint32_t> rank(ctx, (size_t)R + 1), bucket_cnt(ctx, (size_t)R + 2), cursor(ctx, (size_t)R + 1);
+  st.counters.alloc(ctx, 4); st.mid.alloc(ctx, (size_t)R / ORDER_THREAD + 1); st.big.alloc(ctx, (size_t)R / ORDER_BLOCK + 1);
+  PCB_CUDA(cudaMemsetAsync(slot.p, 0x7F, (size_t)cap * sizeof(BucketSlot), ctx->stream));
+  PCB_CUDA(cudaMemsetAsync(rank.p, 0, ((size_t)R + 1) * sizeof(uint32_t), ctx->stream));
+  PCB_CUDA(cudaMemsetAsync(bucket_cnt.p, 0, ((size_t)R + 2) * sizeof(uint32_t), ctx->stream));
+  PCB_CUDA(cudaMemsetAsync(cursor.p, 0, ((size_t)R + 1) * sizeof(uint32_t), ctx->stream));
+  PCB_CUDA(cudaMemsetAsync(st.counters.p, 0, 4 * sizeof(int32_t), ctx->stream));
+  PCB_LAUNCH(ctx, bucket_insert_kernel, grid_for(R, 256), 256, 0, st.pk.planes.p, st.pk.len.p, R, slot.p, cap - 1, slot_of_read.p);
+  PCB_LAUNCH(ctx, bucket_flag_first_kernel, grid_for(cap, 256), 256, 0, slot.p, cap, rank.p);
+  exclusive_scan_u32(ctx, rank.p, rank.p, (size_t)R + 1);               // rank[R] = U
+  if (unique_out) { unique_out->planes.alloc(ctx, (size_t)R); unique_out->len.alloc(ctx, (size_t)R); }
+  PCB_LAUNCH(ctx, bucket_number_kernel, grid_for(cap, 256), 256, 0, slot.p, cap, rank.p, st.pk.planes.p, st.pk.len.p, bucket_cnt.p,
+             unique_out ? unique_out->planes.p : nullptr, unique_out ? unique_out->len.p : nullptr);
+  exclusive_scan_u32(ctx, bucket_cnt.p, (uint32_t *)out.bucket_ptr, (size_t)R + 1);      // entries past U all hold R
+  PCB_LAUNCH(ctx, bucket_place_kernel, grid_for(R, 256), 256, 0, slot_of_read.p, slot.p, R, out.bucket_ptr, cursor.p, out.bucket_of_read,
+             out.bucket_reads);
+  PCB_LAUNCH(ctx, bucket_order_kernel, grid_for(R, 128), 128, 0, rank.p, R, out.bucket_ptr, out.bucket_reads, st.counters.p, st.mid.p,
+             st.big.p);
+  PCB_LAUNCH(ctx, bucket_order_mid_kernel, (unsigned)ctx->sm_count, 256, 0, out.bucket_ptr, out.bucket_reads, st.counters.p, st.mid.p);
+  PCB_CUDA(cudaMemcpyAsync(st.h_flags, st.flags.p, sizeof(st.h_flags), cudaMemcpyDeviceToHost, ctx->stream));
+  PCB_CUDA(cudaMemcpyAsync(st.h_counters, st.counters.p, sizeof(st.h_counters), cudaMemcpyDeviceToHost, ctx->stream));
+}
+
+// After the stream has been synchronised: input errors, U, and the (rare) buckets of more than 4096 reads, whose
+// segments go through the radix sort one by one.
+int32_t bucket_finish(pcb_ctx *ctx, const BucketOut &out, PackedBarcodes *unique_out, BucketPending &st) {
+  pack_finish(st.pk, st.h_flags, false);
+  const int32_t U = st.h_counters[0], n_big = st.h_counters[2];
+  if (n_big > 0) {
+    std::vector<int32_t> h_big((size_t)n_big), h_ptr(2);
+    PCB_CUDA(cudaMemcpyAsync(h_big.data(), st.big.p, (size_t)n_big * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int32_t b : h_big) {
+      PCB_CUDA(cudaMemcpyAsync(h_ptr.data(), out.bucket_ptr + b, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+      const int64_t n = h_ptr[1] - h_ptr[0];
+      DevBuf<uint64_t> k0(ctx, n), k1(ctx, n);
+      DevBuf<uint32_t> v0(ctx, n), v1(ctx, n);
+      PCB_LAUNCH(ctx, u32_keys_kernel, grid_for(n, 256), 256, 0, out.bucket_reads + h_ptr[0], n, k0.p, v0.p);
+      int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, n, bits_for((uint64_t)(st.R > 1 ? st.R - 1 : 1)));
+      PCB_LAUNCH(ctx, u32_unkeys_kernel, grid_for(n, 256), 256, 0, w ? k1.p : k0.p, n, out.bucket_reads + h_ptr[0]);
+    }
+  }
+  if (unique_out) {
+    unique_out->n = U;
+    unique_out->min_len = st.pk.min_len; unique_out->max_len = st.pk.max_len;
+    // the histogram counts reads, not unique barcodes: same set of lengths, and only the choice of the usual length
+    // (a performance matter for the pair search) looks at the counts
+    for (int m = 0; m < 66; m++) unique_out->len_hist[m] = st.pk.len_hist[m];
+    unique_out->has_hist = true;
+  }
+  ctx->stats[PCB_STAT_BUCKETS] = U;
+  return U;
 }
 
 int32_t bucket_reads_dev(pcb_ctx *ctx, const uint8_t *seq, const uint8_t *qual, const int32_t *len, int32_t R,
@@ -155,45 +307,13 @@ int32_t bucket_reads_dev(pcb_ctx *ctx, const uint8_t *seq, const uint8_t *qual, 
     if (unique_out) { unique_out->n = 0; unique_out->planes.alloc(ctx, 0); unique_out->len.alloc(ctx, 0); }
     return 0;
   }
-  PackedBarcodes pk;
-  pack_barcodes(ctx, seq, len, nullptr, R, stride, pk);
-  uint32_t cap = 64;
-  while (cap < 2u * (uint32_t)R) cap <<= 1;
-  DevBuf<int32_t> owner(ctx, cap), first(ctx, cap), slot_of_read(ctx, R);
-  DevBuf<uint32_t> count(ctx, cap), rank(ctx, (size_t)R + 1), bucket_cnt(ctx, (size_t)R + 1);
-  PCB_CUDA(cudaMemsetAsync(owner.p, 0xFF, cap * sizeof(int32_t), ctx->stream));
-  fill_i32(ctx, first.p, cap, INT32_MAX);
-  PCB_CUDA(cudaMemsetAsync(count.p, 0, cap * sizeof(uint32_t), ctx->stream));
-  PCB_LAUNCH(ctx, bucket_insert_kernel, grid_for(R, 256), 256, 0, pk.planes.p, pk.len.p, R, owner.p, first.p, count.p,
-             cap - 1, slot_of_read.p);
-  PCB_LAUNCH(ctx, bucket_flag_first_kernel, grid_for(R, 256), 256, 0, slot_of_read.p, first.p, R, rank.p);
-  // U = number of first reads: scan one element past the end (a zero) and read the total there
-  PCB_CUDA(cudaMemsetAsync(rank.p + R, 0, sizeof(uint32_t), ctx->stream));
-  exclusive_scan_u32(ctx, rank.p, rank.p, (size_t)R + 1);
-  int32_t U = (int32_t)read_scalar(ctx, rank.p + R);
-  DevBuf<uint64_t> k0(ctx, R), k1(ctx, R);
-  DevBuf<uint32_t> v0(ctx, R), v1(ctx, R);
-  PCB_CUDA(cudaMemsetAsync(bucket_cnt.p, 0, ((size_t)R + 1) * sizeof(uint32_t), ctx->stream));
-  PCB_LAUNCH(ctx, bucket_number_kernel, grid_for(R, 256), 256, 0, slot_of_read.p, first.p, rank.p, count.p, R,
-             out.bucket_of_read, bucket_cnt.p, k0.p);
-  exclusive_scan_u32(ctx, bucket_cnt.p, bucket_cnt.p, (size_t)U + 1);
-  PCB_LAUNCH(ctx, copy_u32_to_i32_kernel, grid_for((size_t)U + 1, 256), 256, 0, bucket_cnt.p, out.bucket_ptr, (size_t)U + 1);
-  iota_u32(ctx, v0.p, R);
-  int where = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, R, bits_for((uint64_t)(U > 1 ? U - 1 : 1)));
-  PCB_LAUNCH(ctx, copy_u32_to_i32_kernel, grid_for(R, 256), 256, 0, where ? v1.p : v0.p, out.bucket_reads, (size_t)R);
+  BucketPending st;
+  bucket_launch(ctx, seq, len, R, stride, out, unique_out, st);
+  PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  const int32_t U = bucket_finish(ctx, out, unique_out, st);
   if (out.bucket_qsum)
     PCB_LAUNCH(ctx, bucket_qsum_kernel, grid_for((size_t)U * stride, 256), 256, 0, qual, len, out.bucket_ptr,
                out.bucket_reads, U, stride, out.bucket_qsum);
-  if (unique_out) {
-    unique_out->planes.alloc(ctx, (size_t)U);
-    unique_out->len.alloc(ctx, (size_t)U);
-    unique_out->n = U;
-    unique_out->min_len = pk.min_len;
-    unique_out->max_len = pk.max_len;
-    PCB_LAUNCH(ctx, gather_first_kernel, grid_for(U, 256), 256, 0, out.bucket_ptr, out.bucket_reads, U, pk.planes.p,
-               pk.len.p, unique_out->planes.p, unique_out->len.p);
-  }
-  ctx->stats[PCB_STAT_BUCKETS] = U;
   return U;
 }
 

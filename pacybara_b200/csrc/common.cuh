@@ -146,7 +146,12 @@ struct PackedBarcodes {      // planes of n barcodes: x = plane L (bit 0 of each
   DevBuf<int32_t> len;
   DevBuf<uint64_t> other;    // optional: positions holding a character that is no base (f3 queries); planes are 0 there
   int32_t n = 0, min_len = 0, max_len = 0;
+  uint32_t len_hist[66] = {0};   // barcodes per length, when the packing counted them (has_hist)
+  bool has_hist = false;
 };
+void pack_launch(pcb_ctx *ctx, const uint8_t *seq, const int32_t *len, const int32_t *rows, int32_t n, int32_t stride,
+                 PackedBarcodes &out, bool allow_other, DevBuf<int32_t> &flags);
+void pack_finish(PackedBarcodes &out, const int32_t *h_flags, bool allow_other);
 // ASCII rows (optionally gathered through `rows`) -> planes; throws PCB_E_INPUT on bad input
 // allow_other: characters outside ACGT are recorded in out.other instead of being refused
 void pack_barcodes(pcb_ctx *ctx, const uint8_t *seq, const int32_t *len, const int32_t *rows, int32_t n,
@@ -158,6 +163,17 @@ struct BucketOut {           // all device pointers, caller-owned
 };
 int32_t bucket_reads_dev(pcb_ctx *ctx, const uint8_t *seq, const uint8_t *qual, const int32_t *len, int32_t R,
                          int32_t stride, const BucketOut &out, PackedBarcodes *unique_out);
+// the same in two halves, for callers that have more to launch before they synchronise the stream
+struct BucketPending {
+  int32_t R = 0;
+  PackedBarcodes pk;
+  DevBuf<int32_t> flags, counters, mid, big;
+  int32_t h_flags[4 + 66];
+  int32_t h_counters[4];
+};
+void bucket_launch(pcb_ctx *ctx, const uint8_t *seq, const int32_t *len, int32_t R, int32_t stride, const BucketOut &out,
+                   PackedBarcodes *unique_out, BucketPending &st);
+int32_t bucket_finish(pcb_ctx *ctx, const BucketOut &out, PackedBarcodes *unique_out, BucketPending &st);
 
 void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q_begin, int32_t q_end);
 // f3: nearest library barcodes of every query within k; the (query, row, d) rows stay in ctx->edges

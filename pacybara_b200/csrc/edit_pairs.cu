@@ -279,12 +279,16 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
   // probe an index of q-grams with q up to that.  Most barcodes share one length; the few shorter ones (deletions)
   // would force the short q on everybody, so there are up to two indexes over all targets: q_hi for the queries
   // long enough for it, q_lo for the rest.  Either way every pair is found through its query side.
-  DevBuf<uint32_t> d_hist(ctx, 66);
-  PCB_CUDA(cudaMemsetAsync(d_hist.p, 0, 66 * sizeof(uint32_t), ctx->stream));
-  PCB_LAUNCH(ctx, len_hist_kernel, (unsigned)ctx->sm_count, 256, 0, qs.len.p, qs.n, d_hist.p);
   uint32_t h_hist[66];
-  PCB_CUDA(cudaMemcpyAsync(h_hist, d_hist.p, sizeof(h_hist), cudaMemcpyDeviceToHost, ctx->stream));
-  PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (qs.has_hist) {                                          // counted while packing: no round trip
+    for (int l = 0; l < 66; l++) h_hist[l] = qs.len_hist[l];
+  } else {
+    DevBuf<uint32_t> d_hist(ctx, 66);
+    PCB_CUDA(cudaMemsetAsync(d_hist.p, 0, 66 * sizeof(uint32_t), ctx->stream));
+    PCB_LAUNCH(ctx, len_hist_kernel, (unsigned)ctx->sm_count, 256, 0, qs.len.p, qs.n, d_hist.p);
+    PCB_CUDA(cudaMemcpyAsync(h_hist, d_hist.p, sizeof(h_hist), cudaMemcpyDeviceToHost, ctx->stream));
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   int32_t mode_len = qs.min_len;
   for (int32_t l = 1; l <= 64; l++) if (h_hist[l] > h_hist[mode_len]) mode_len = l;
   auto make_geom = [&](int32_t q) {
