@@ -61,8 +61,8 @@ enum { PCB_MEM_HOST = 0, PCB_MEM_DEVICE = 1 };
 
 /* counters readable after a call (pcb_stat) */
 enum {
-  PCB_STAT_PAIRS_SCORED = 0,   /* candidate pairs that went through the Myers kernel */
-  PCB_STAT_CELLS = 1,          /* sum over those pairs of len_i * len_j (GCUPS numerator) */
+  PCB_STAT_PAIRS_SCORED = 0,   /* candidate pairs that entered the Myers recurrence */
+  PCB_STAT_CELLS = 1,          /* DP cells the recurrence computed for them (rows x columns done; an early exit stops short) */
   PCB_STAT_EDGES = 2,          /* unique pairs with dist <= k */
   PCB_STAT_SEED_LEN = 3,       /* q of the pigeonhole seeds used */
   PCB_STAT_KERNEL_LAUNCHES = 4,/* kernels launched by this context so far */
@@ -80,7 +80,8 @@ enum {
   PCB_STAT_T_SCATTER_NS = 15,  /* what follows the replay: status round trip, late components */
   PCB_STAT_ROWS = 16,          /* rows of the last pcb_cluster_reads with PCB_CLUSTER_COMPACT_ROWS */
   PCB_STAT_CALLS = 17,         /* consensus genotype entries of those rows */
-  PCB_STAT_COUNT = 18
+  PCB_STAT_CANDIDATES = 18,    /* candidate pairs the seed index produced (before the composition / length filters) */
+  PCB_STAT_COUNT = 19
 };
 
 typedef struct pcb_ctx pcb_ctx;

@@ -18,7 +18,7 @@ MERGE_PAIRS_SORTED = 1
 MERGE_SHARD_LAYOUT = 2
 STAT = dict(pairs_scored=0, cells=1, edges=2, seed_len=3, kernel_launches=4, components=5, links=6, tests=7,
             buckets=8, probe_ns=9, t_bucket_ns=10, t_index_ns=11, t_hits_ns=12, t_prep_ns=13, t_replay_ns=14,
-            t_scatter_ns=15, rows=16, calls=17)
+            t_scatter_ns=15, rows=16, calls=17, candidates=18)
 
 # every symbol include/pacybara_b200.h declares
 REPLAY_SHAPES = dict(auto=0, small=0, thread=1, warp=2)

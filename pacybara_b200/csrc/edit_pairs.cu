@@ -17,21 +17,9 @@
 // planes of each scored target, mostly served by L2.  See DESIGN.md for the op and byte counts.
 #include "common.cuh"
 #include "myers.cuh"
+#include "probe.cuh"
 
 namespace pcb {
-
-struct SeedGeom {
-  int32_t q;         // seed length (0: single bin)
-  int32_t npos;      // target positions indexed: 0 .. npos-1
-  int32_t k;
-  uint32_t nbins;
-  uint64_t pos_mask; // positions a probe can ask for (piece start + shift of some query length): only those are indexed
-};
-
-__device__ __forceinline__ uint32_t seed_bin(const SeedGeom g, uint64_t L, uint64_t H, int src_pos, int bin_pos) {
-  if (g.q == 0) return 0u;
-  return ((uint32_t)bin_pos << (2 * g.q)) | qgram_key(L, H, src_pos, g.q);
-}
 
 __global__ void seed_count_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int32_t U,
                                   SeedGeom g, uint32_t *__restrict__ bin_cnt) {
@@ -190,6 +178,18 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(const ulonglong
   if (lane == 0 && scored) { atomicAdd(&counters[1], scored); atomicAdd(&counters[2], cells); }
 }
 
+// The clustering path's probe for barcodes of at most 32 nt (probe.cuh): composition filter on a 4-byte sketch, lanes
+// that each carry their own pair through the recurrence, Ukkonen cut-off at checkpoints.
+__global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel_lanes(ProbeArgs a) {
+  __shared__ ProbeQueue queue[PROBE_WARPS];
+  probe_warp(a, threadIdx.x & 31, &queue[threadIdx.x >> 5]);
+}
+
+__global__ void sketch_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int32_t U, uint32_t *__restrict__ sketch) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < U) sketch[i] = barcode_sketch((uint32_t)planes[i].x, (uint32_t)planes[i].y, len[i]);
+}
+
 __global__ void len_hist_kernel(const int32_t *__restrict__ len, int32_t U, uint32_t *__restrict__ hist) {
   __shared__ uint32_t sh[66];
   if (threadIdx.x < 66) sh[threadIdx.x] = 0;
@@ -267,7 +267,7 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
   const bool self = queries == nullptr;
   const PackedBarcodes &qs = self ? bc : *queries;
   const int32_t U = bc.n;
-  ctx->stats[PCB_STAT_PAIRS_SCORED] = ctx->stats[PCB_STAT_CELLS] = ctx->stats[PCB_STAT_EDGES] = 0;
+  ctx->stats[PCB_STAT_PAIRS_SCORED] = ctx->stats[PCB_STAT_CELLS] = ctx->stats[PCB_STAT_EDGES] = ctx->stats[PCB_STAT_CANDIDATES] = 0;
   ctx->stats[PCB_STAT_PROBE_NS] = 0;
   if (k < 0 || k > 8) throw Error(PCB_E_INPUT, "k must be in 0..8");
   if (q_begin < 0 || q_end > qs.n || q_begin > q_end) throw Error(PCB_E_INPUT, "query range outside [0, U)");
@@ -346,10 +346,16 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
   // ---- probe (re-run with a larger hit buffer if the first guess overflows)
   const int key_shift = bits_for((uint64_t)(U > 1 ? U - 1 : 1));
   unsigned long long cap = 8ull * (unsigned long long)(q_end - q_begin) + (1ull << 16);
-  DevBuf<unsigned long long> counters(ctx, 4);
+  DevBuf<unsigned long long> counters(ctx, 6);
+  const bool lanes = self && !(bc.max_len > 32);          // the clustering path on one-word barcodes: probe.cuh
+  DevBuf<uint32_t> sketch;
+  if (lanes) {
+    sketch.alloc(ctx, (size_t)U);
+    PCB_LAUNCH(ctx, sketch_kernel, grid_for(U, 256), 256, 0, bc.planes.p, bc.len.p, U, sketch.p);
+  }
   DevBuf<uint64_t> hk0, hk1;
   DevBuf<uint32_t> hv0, hv1;
-  unsigned long long h_counters[4];
+  unsigned long long h_counters[6];
   const bool wide = bc.max_len > 32 || qs.max_len > 32;
   auto launch = [&](auto kernel, unsigned n_cta, const SeedIndex &ix) {
     PCB_LAUNCH(ctx, kernel, n_cta, PROBE_WARPS * 32, 0, qs.planes.p, qs.len.p, (const uint64_t *)(self ? nullptr : qs.other.p), bc.planes.p, bc.len.p, q_begin, q_end, ix.g,
@@ -357,7 +363,7 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
   };
   for (int attempt = 0;; attempt++) {
     hk0.alloc(ctx, cap); hv0.alloc(ctx, cap);
-    PCB_CUDA(cudaMemsetAsync(counters.p, 0, 4 * sizeof(unsigned long long), ctx->stream));
+    PCB_CUDA(cudaMemsetAsync(counters.p, 0, 6 * sizeof(unsigned long long), ctx->stream));
     PCB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
     for (int t = 0; t < n_idx; t++) {
       const SeedGeom &g = idx[t].g;
@@ -368,7 +374,14 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
       unsigned need = grid_for((n_probe + 31) / 32, PROBE_WARPS);
       if (need < n_cta) n_cta = need;
       if (t > 0) PCB_CUDA(cudaMemsetAsync(counters.p + 3, 0, sizeof(unsigned long long), ctx->stream));
-      if (wide && self) launch(probe_kernel<true, true>, n_cta, idx[t]);
+      if (lanes) {
+        ProbeArgs a;
+        a.planes = (const Planes16 *)bc.planes.p; a.len = bc.len.p; a.sketch = sketch.p; a.q_begin = q_begin; a.q_end = q_end; a.g = g;
+        a.bin_off = idx[t].bin_off.p; a.ent = idx[t].ent.p; a.hit_key = hk0.p; a.hit_d = hv0.p; a.cap = cap; a.key_shift = key_shift;
+        a.counters = counters.p; a.len_lo = idx[t].len_lo; a.len_hi = idx[t].len_hi;
+        PCB_LAUNCH(ctx, probe_kernel_lanes, n_cta, PROBE_WARPS * 32, 0, a);
+      }
+      else if (wide && self) launch(probe_kernel<true, true>, n_cta, idx[t]);
       else if (wide) launch(probe_kernel<true, false>, n_cta, idx[t]);
       else if (self) launch(probe_kernel<false, true>, n_cta, idx[t]);
       else launch(probe_kernel<false, false>, n_cta, idx[t]);
@@ -386,6 +399,7 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
   stage_end(ctx, -1);      // the probe interval itself is PCB_STAT_PROBE_NS (ev0/ev1 above)
   ctx->stats[PCB_STAT_PAIRS_SCORED] = (int64_t)h_counters[1];
   ctx->stats[PCB_STAT_CELLS] = (int64_t)h_counters[2];
+  ctx->stats[PCB_STAT_CANDIDATES] = lanes ? (int64_t)h_counters[5] : (int64_t)h_counters[1];
   size_t n_hits = (size_t)h_counters[0];
   if (n_hits == 0) return;
 

@@ -1,0 +1,232 @@
+// probe.cuh -- the pair search's probe for barcodes of at most 32 nt within one set (the clustering path): candidate
+// generation from the seed index, two cheap exact filters, and the Myers/Hyyro bit-vector distance with an early exit,
+// organised so that the lanes of a warp are always busy with a pair of their own.
+//
+//   filter     every lane walks the bin of its probe (query i, piece t, shift s); a target j is kept when i is the
+//              pair's query side (every unordered pair has exactly one), the lengths differ by at most k, and the
+//              base-composition bound holds: an edit changes the count of at most two bases by one each, so
+//              dist >= max(surplus, deficit) of the four base counts (two popc-built 4-byte vectors, two SIMD
+//              subtractions on a 4-byte sketch of the target -- the one thing a candidate costs in memory).  Survivors
+//              go to a per-warp queue.
+//   scoring    a lane that has no pair pops one from the queue; all lanes then advance THEIR pair by a few text
+//              columns; at the checkpoint a finished pair emits its hit and a pair whose cell on the final diagonal
+//              already exceeds k is dropped (D[m][n] >= D[j + m - n][j], Ukkonen's cut-off) -- either way the lane is
+//              free for the next pair, so rejected pairs cost a few columns and the warp stays full.
+//   direction  the seed that produced the candidate matches exactly, so the errors sit on the other side of it: the
+//              recurrence runs over the reversed strings when the longer unseeded part is the tail (dist(x, y) =
+//              dist(rev x, rev y)), which puts the mismatches first and the cut-off early.
+// Same distances and the same hit set as the plain kernel (edit_pairs.cu), which stays for 33..64-nt barcodes and for
+// the two-set matcher.  Written against simt.h: tests/host_emul runs this source on an emulated warp (unit tests).
+#pragma once
+#include "myers.cuh"
+#include "simt.h"
+
+namespace pcb {
+
+struct Planes16 { uint64_t x, y; };       // layout of ulonglong2: plane L, plane H
+
+struct SeedGeom {
+  int32_t q;         // seed length (0: single bin)
+  int32_t npos;      // target positions indexed: 0 .. npos-1
+  int32_t k;
+  uint32_t nbins;
+  uint64_t pos_mask; // positions a probe can ask for (piece start + shift of some query length): only those are indexed
+};
+
+PCB_HD uint32_t seed_bin(const SeedGeom g, uint64_t L, uint64_t H, int src_pos, int bin_pos) {
+  if (g.q == 0) return 0u;
+  return ((uint32_t)bin_pos << (2 * g.q)) | qgram_key(L, H, src_pos, g.q);
+}
+
+struct ProbeArgs {
+  const Planes16 *planes;          // the barcodes (queries and targets are the same set)
+  const int32_t *len;
+  const uint32_t *sketch;          // per barcode: length << 24 | #T << 16 | #G << 8 | #C -- all the filters read (one sector)
+  int32_t q_begin, q_end;          // this call's queries
+  SeedGeom g;
+  const uint32_t *bin_off;
+  const int32_t *ent;
+  uint64_t *hit_key;
+  uint32_t *hit_d;
+  unsigned long long cap;
+  int key_shift;
+  unsigned long long *counters;    // [0] hits, [1] pairs that entered the recurrence, [2] cells computed, [3] next block of probes,
+                                   // [4] bin entries walked, [5] entries that passed the query-side rule (the filters' input)
+  int32_t len_lo, len_hi;          // query lengths this index serves
+};
+
+constexpr int PROBE_QUEUE = 96;    // survivors waiting for a lane (at most 63 + 32)
+constexpr int PROBE_CHUNK = 5;     // text columns between checkpoints
+struct ProbeQueue {
+  int32_t qi[PROBE_QUEUE], tj[PROBE_QUEUE];     // query, target (bit 31 of tj: run the recurrence over the reversed strings)
+};
+
+PCB_HD uint32_t barcode_sketch(uint32_t L, uint32_t H, int32_t n) {
+  return ((uint32_t)n << 24) | ((uint32_t)popc32(L & H) << 16) | ((uint32_t)popc32(~L & H) << 8) | (uint32_t)popc32(L & ~H);
+}
+// counts of A, C, G, T as four bytes, from a sketch
+SIMT_FN uint32_t sketch_counts(uint32_t sk) {
+  const uint32_t n = sk >> 24, nc = sk & 0xFFu, ng = (sk >> 8) & 0xFFu, nt = (sk >> 16) & 0xFFu;
+  return (n - nc - ng - nt) | ((sk & 0xFFFFFFu) << 8);
+}
+
+SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t lt = (1u << lane) - 1u;
+  const SeedGeom g = a.g;
+  const int k = g.k;
+  const int n_shift = g.q == 0 ? 1 : 2 * k + 1;
+  const int per_query = g.q == 0 ? 1 : (k + 1) * n_shift;
+  const unsigned long long n_probe = (unsigned long long)(a.q_end - a.q_begin) * per_query;
+  const unsigned long long n_blocks = (n_probe + 31) / 32;
+  unsigned long long n_started = 0, n_cells = 0, n_walked = 0, n_sided = 0;
+  int cnt = 0;                       // queued survivors (uniform)
+  bool exhausted = false;            // no more probe blocks (uniform)
+  // my probe
+  uint32_t lo = 0, hi = 0;
+  int32_t qi = -1, qm = 0;
+  uint32_t qcounts = 0, qrev = 0;
+  // my pair
+  bool active = false;
+  uint32_t Pv = 0, Mv = 0, rl = 0, rh = 0, pL = 0, pH = 0;
+  int32_t pj = 0, pn = 0, pm = 0, pi = 0, ptj = 0;
+  for (;;) {
+    // ---- filter: until a warp's worth of survivors waits (or the probes run out)
+    while (cnt < 32 && !exhausted) {
+      if (simt::ballot(FULL, lo < hi) == 0u) {
+        unsigned long long blk = 0;
+        if (lane == 0) blk = simt::atomic_add_u64(&a.counters[3], 1ull);
+        const uint32_t b_lo = simt::shfl(FULL, (uint32_t)(blk & 0xFFFFFFFFull), 0), b_hi = simt::shfl(FULL, (uint32_t)(blk >> 32), 0);
+        blk = ((unsigned long long)b_hi << 32) | b_lo;
+        if (blk >= n_blocks) { exhausted = true; break; }
+        const unsigned long long pid = blk * 32 + (unsigned)lane;
+        lo = hi = 0; qi = -1;
+        if (pid < n_probe) {
+          qi = a.q_begin + (int32_t)(pid / per_query);
+          const int32_t rem = (int32_t)(pid % per_query);
+          const int32_t t = rem / n_shift, s = rem % n_shift - (g.q == 0 ? 0 : k);
+          qm = a.len[qi];
+          const int32_t st = g.q == 0 ? 0 : (int32_t)((int64_t)t * qm / (k + 1));
+          const int32_t p = st + s;
+          if (p >= 0 && p < g.npos && qm >= a.len_lo && qm <= a.len_hi) {     // queries of other lengths use the other index
+            const Planes16 pl = a.planes[qi];
+            const uint32_t bin = seed_bin(g, pl.x, pl.y, st, p);
+            lo = a.bin_off[bin]; hi = a.bin_off[bin + 1];
+            qcounts = sketch_counts(a.sketch[qi]);
+            // the seed matches exactly: the errors are before it or after it -- start the recurrence on the longer side
+            qrev = (st < qm - (st + g.q)) ? 0x80000000u : 0u;
+          }
+        }
+        continue;
+      }
+      bool keep = false;
+      int32_t j = 0;
+      if (lo < hi) {
+        j = a.ent[lo++];
+        n_walked++;
+        if (j != qi && is_query_side(qi, j)) {
+          n_sided++;
+          const uint32_t sk = a.sketch[j];
+          const int32_t dl = qm - (int32_t)(sk >> 24);
+          if (dl <= k && -dl <= k) {
+            const uint32_t tc = sketch_counts(sk);
+            const uint32_t up = simt::surplus4(qcounts, tc), down = simt::surplus4(tc, qcounts);
+            keep = (int32_t)(up > down ? up : down) <= k;
+          }
+        }
+      }
+      const uint32_t mask = simt::ballot(FULL, keep);
+      if (keep) {
+        const int at = cnt + simt::popc(mask & lt);
+        qu->qi[at] = qi; qu->tj[at] = (int32_t)((uint32_t)j | qrev);
+      }
+      cnt += simt::popc(mask);
+      simt::sync(FULL);
+    }
+    // ---- lanes without a pair take one
+    {
+      const uint32_t idle = simt::ballot(FULL, !active);
+      const int n_pop = simt::popc(idle) < cnt ? simt::popc(idle) : cnt;
+      if (!active && simt::popc(idle & lt) < n_pop) {
+        const int at = cnt - 1 - simt::popc(idle & lt);
+        pi = qu->qi[at];
+        const uint32_t tj = (uint32_t)qu->tj[at];
+        ptj = (int32_t)(tj & 0x7FFFFFFFu);
+        const Planes16 tp = a.planes[ptj], pl = a.planes[pi];
+        const uint32_t tL = (uint32_t)tp.x, tH = (uint32_t)tp.y;
+        pn = a.len[ptj]; pm = a.len[pi];
+        if (tj & 0x80000000u) {              // reversed strings: text from its last base, pattern mirrored
+          rl = tL << (32 - pn); rh = tH << (32 - pn);
+          pL = simt::brev((uint32_t)pl.x) >> (32 - pm); pH = simt::brev((uint32_t)pl.y) >> (32 - pm);
+        } else {
+          rl = simt::brev(tL); rh = simt::brev(tH);
+          pL = (uint32_t)pl.x; pH = (uint32_t)pl.y;
+        }
+        Pv = 0xFFFFFFFFu; Mv = 0u; pj = 0;
+        active = true;
+        n_started++;
+      }
+      cnt -= n_pop;
+      simt::sync(FULL);
+      if (simt::ballot(FULL, active) == 0u) {
+        if (exhausted && cnt == 0) break;
+        continue;
+      }
+    }
+    // ---- a few columns of every lane's own pair (myers.cuh: the recurrence; the text column is the sign bit of rl / rh)
+    const int32_t pj_before = pj;
+#pragma unroll
+    for (int c = 0; c < PROBE_CHUNK; c++) {
+      if (active && pj < pn) {
+        const uint32_t cl = (uint32_t)((int32_t)rl >> 31), ch = (uint32_t)((int32_t)rh >> 31);
+        rl += rl; rh += rh;
+        const uint32_t Eq = ~((pL ^ cl) | (pH ^ ch));
+        const uint32_t Xv = Eq | Mv;
+        const uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
+        uint32_t Ph = Mv | ~(Xh | Pv);
+        uint32_t Mh = Pv & Xh;
+        Ph = Ph + Ph + 1u;
+        Mh = Mh + Mh;
+        Pv = Mh | ~(Xv | Ph);
+        Mv = Ph & Xv;
+        pj++;
+      }
+    }
+    // ---- checkpoint
+    if (active) {
+      n_cells += (unsigned long long)((pj - pj_before) * pm);
+      if (pj >= pn) {
+        const uint32_t rows = pm >= 32 ? 0xFFFFFFFFu : ((1u << pm) - 1u);
+        const int d = pn + simt::popc(Pv & rows) - simt::popc(Mv & rows);
+        if (d <= k) {
+          const unsigned long long at = simt::atomic_add_u64(&a.counters[0], 1ull);
+          if (at < a.cap) {
+            const uint32_t x = ptj < pi ? (uint32_t)ptj : (uint32_t)pi, y = ptj < pi ? (uint32_t)pi : (uint32_t)ptj;
+            a.hit_key[at] = ((uint64_t)x << a.key_shift) | y;
+            a.hit_d[at] = (uint32_t)d;
+          }
+        }
+        active = false;
+      } else {
+        // the cell of column pj on the diagonal that ends in (m, n) bounds the distance from below
+        int32_t i = pj + pm - pn, extra = 0;
+        if (i < 0) { extra = -i; i = 0; }
+        if (i > pm) { extra = i - pm; i = pm; }
+        const uint32_t below = i >= 32 ? 0xFFFFFFFFu : ((1u << i) - 1u);
+        if (pj + simt::popc(Pv & below) - simt::popc(Mv & below) + extra > k) active = false;
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    n_started += ((unsigned long long)simt::shfl(FULL, (uint32_t)(n_started >> 32), lane ^ o) << 32) | simt::shfl(FULL, (uint32_t)n_started, lane ^ o);
+    n_cells += ((unsigned long long)simt::shfl(FULL, (uint32_t)(n_cells >> 32), lane ^ o) << 32) | simt::shfl(FULL, (uint32_t)n_cells, lane ^ o);
+    n_walked += ((unsigned long long)simt::shfl(FULL, (uint32_t)(n_walked >> 32), lane ^ o) << 32) | simt::shfl(FULL, (uint32_t)n_walked, lane ^ o);
+    n_sided += ((unsigned long long)simt::shfl(FULL, (uint32_t)(n_sided >> 32), lane ^ o) << 32) | simt::shfl(FULL, (uint32_t)n_sided, lane ^ o);
+  }
+  if (lane == 0 && n_walked) {
+    simt::atomic_add_u64(&a.counters[1], n_started); simt::atomic_add_u64(&a.counters[2], n_cells);
+    simt::atomic_add_u64(&a.counters[4], n_walked); simt::atomic_add_u64(&a.counters[5], n_sided);
+  }
+}
+
+}  // namespace pcb

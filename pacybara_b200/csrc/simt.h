@@ -27,6 +27,10 @@ SIMT_FN int64_t atomic_add64(int64_t *p, int64_t v) { return (int64_t)atomicAdd(
 SIMT_FN int popc(uint32_t x) { return __popc(x); }
 SIMT_FN int ffs(uint32_t x) { return __ffs((int)x); }      // 1-based, 0 when x == 0
 SIMT_FN float sqrt_f(float x) { return sqrtf(x); }
+SIMT_FN uint32_t brev(uint32_t x) { return __brev(x); }
+SIMT_FN unsigned long long atomic_add_u64(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
+// sum over the four bytes of max(0, a_byte - b_byte)
+SIMT_FN uint32_t surplus4(uint32_t a, uint32_t b) { return __vsadu4(__vsubus4(a, b), 0u); }
 }  // namespace simt
 
 #else
@@ -50,5 +54,12 @@ inline int64_t atomic_add64(int64_t *p, int64_t v) { int64_t o = *p; *p = o + v;
 inline int popc(uint32_t x) { return __builtin_popcount(x); }
 inline int ffs(uint32_t x) { return __builtin_ffs((int)x); }
 inline float sqrt_f(float x) { return sqrtf(x); }
+inline uint32_t brev(uint32_t x) { uint32_t r = 0; for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i); return r; }
+inline unsigned long long atomic_add_u64(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+inline uint32_t surplus4(uint32_t a, uint32_t b) {
+  uint32_t s = 0;
+  for (int i = 0; i < 4; i++) { uint32_t x = (a >> (8 * i)) & 0xFFu, y = (b >> (8 * i)) & 0xFFu; if (x > y) s += x - y; }
+  return s;
+}
 }  // namespace simt
 #endif
