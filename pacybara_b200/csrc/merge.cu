@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(32) component_kernel_medium(MergeCtx c, const 
     for (int32_t i = lane; i < 2 * MED_CALLS; i += 32) { GenoSlot z; z.key = 0; z.obs1 = z.obs2 = z.pad = 0; z.sum1 = z.sum2 = 0; sm->slots[i] = z; }
     if (lane == 0) {
       sm->cpair_ptr[0] = 0; sm->cpair_ptr[1] = P;
-      sm->call_off[0] = (int64_t)atomicAdd((unsigned long long *)c.call_cursor, (unsigned long long)run);
+      sm->call_off[0] = c.call_off ? c.call_off[comp] : (int64_t)atomicAdd((unsigned long long *)c.call_cursor, (unsigned long long)run);
     }
     __syncwarp();
     MergeCtx lc = c;
