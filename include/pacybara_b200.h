@@ -126,14 +126,16 @@ int pcb_bucket(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *qual, c
  * a2+a3 -- every unordered pair of distinct barcodes with Levenshtein distance <= k
  * (replaces bowtie2 all-vs-all + pacybara_calcEdits.R; dist := unit-cost Levenshtein).
  *   seq [U, stride], len [U]: the unique barcodes;  0 <= k <= 8
- *   q_begin, q_end: this call scores the pairs whose "query" barcode lies in [q_begin, q_end);
- *     every unordered pair has exactly one query side, so disjoint ranges that cover [0, U)
- *     produce disjoint edge sets whose union is the full result (multi-GPU sharding).
+ *   q_begin, q_end / t_begin, t_end: every unordered pair has exactly one "query" side and one "target" side;
+ *     this call scores the pairs whose query lies in [q_begin, q_end) AND whose target lies in [t_begin, t_end).
+ *     Disjoint ranges that cover [0, U) on either side (the other left at [0, U)) produce disjoint edge sets whose
+ *     union is the full result (multi-GPU sharding).  Only the targets of the range are indexed, so sharding by
+ *     target also divides the index build.
  *   n_edges: host int64, number of pairs found.  The pairs stay in the context until
  *   pcb_edit_pairs_fetch copies them out: ei < ej, sorted by (ei, ej), ed = distance.
  */
 int pcb_edit_pairs(pcb_ctx *ctx, int mem, const uint8_t *seq, const int32_t *len, int32_t U, int32_t stride,
-                   int32_t k, int32_t q_begin, int32_t q_end, int64_t *n_edges);
+                   int32_t k, int32_t q_begin, int32_t q_end, int32_t t_begin, int32_t t_end, int64_t *n_edges);
 int pcb_edit_pairs_fetch(pcb_ctx *ctx, int mem, int32_t *ei, int32_t *ej, int32_t *ed, int64_t cap);
 /* Sort n edges in place by (ei, ej): puts the concatenation of several shards' edge lists
  * (after the all-gather) back into the canonical row order the merge visits them in. */

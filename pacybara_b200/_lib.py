@@ -61,7 +61,7 @@ def load():
         lib.pcb_stream.restype = vp
         lib.pcb_stream.argtypes = [vp]
         lib.pcb_bucket.argtypes = [vp, C.c_int, vp, vp, vp, i32, i32, vp, C.POINTER(i32), vp, vp, vp]
-        lib.pcb_edit_pairs.argtypes = [vp, C.c_int, vp, vp, i32, i32, i32, i32, i32, C.POINTER(i64)]
+        lib.pcb_edit_pairs.argtypes = [vp, C.c_int, vp, vp, i32, i32, i32, i32, i32, i32, i32, C.POINTER(i64)]
         lib.pcb_edit_pairs_fetch.argtypes = [vp, C.c_int, vp, vp, vp, i64]
         lib.pcb_sort_edges.argtypes = [vp, C.c_int, vp, vp, vp, i64, i32]
         lib.pcb_merge.argtypes = ([vp, C.c_int, i32, i32] + [vp] * 8 + [i64, vp, i32, i64] + [vp] * 4 +

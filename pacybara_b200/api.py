@@ -151,17 +151,21 @@ class Context:
                     bucket_len=length[first.long()] if mem == _lib.MEM_DEVICE else np.asarray(length)[first])
 
     # ------------------------------------------------------------------ a2+a3
-    def edit_pairs(self, seq, length, k: int, q_range: Optional[Tuple[int, int]] = None):
-        """All pairs i<j of the U barcodes with Levenshtein <= k, sorted by (i, j) (pcb_edit_pairs)."""
+    def edit_pairs(self, seq, length, k: int, q_range: Optional[Tuple[int, int]] = None,
+                   t_range: Optional[Tuple[int, int]] = None):
+        """All pairs i<j of the U barcodes with Levenshtein <= k, sorted by (i, j) (pcb_edit_pairs).  Every unordered pair
+        has one query side and one target side: q_range / t_range restrict the call to the pairs whose query / target
+        lies in the range (disjoint ranges that cover [0, U) give disjoint edge sets whose union is everything)."""
         if _is_dev(seq):
             _torch()
         mem = self._kind(seq, length)
         U, stride = int(seq.shape[0]), int(seq.shape[1])
         lo, hi = (0, U) if q_range is None else q_range
+        tlo, thi = (0, U) if t_range is None else t_range
         keep: list = []
         n = C.c_int64(0)
         self._check(self.lib.pcb_edit_pairs(self.h, mem, self._in(seq, np.uint8, keep), self._in(length, np.int32, keep),
-                                            U, stride, int(k), int(lo), int(hi), C.byref(n)))
+                                            U, stride, int(k), int(lo), int(hi), int(tlo), int(thi), C.byref(n)))
         E = int(n.value)
         ei, p_i = self._out(mem, (max(E, 1),), np.int32)
         ej, p_j = self._out(mem, (max(E, 1),), np.int32)

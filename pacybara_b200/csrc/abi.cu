@@ -256,7 +256,7 @@ int pcb_bucket(pcb_ctx *ctx, int mem, const uint8_t *seq, const uint8_t *qual, c
 }
 
 int pcb_edit_pairs(pcb_ctx *ctx, int mem, const uint8_t *seq, const int32_t *len, int32_t U, int32_t stride, int32_t k,
-                   int32_t q_begin, int32_t q_end, int64_t *n_edges) {
+                   int32_t q_begin, int32_t q_end, int32_t t_begin, int32_t t_end, int64_t *n_edges) {
   return guarded(ctx, [&] {
     if (U < 0 || stride < 1) throw Error(PCB_E_INPUT, "bad shape");
     InArr<uint8_t> d_seq(ctx, mem, seq, (size_t)U * stride);
@@ -264,7 +264,7 @@ int pcb_edit_pairs(pcb_ctx *ctx, int mem, const uint8_t *seq, const int32_t *len
     PackedBarcodes bc;
     pack_barcodes(ctx, d_seq.p, d_len.p, nullptr, U, stride, bc);
     stage_begin(ctx, PCB_STAT_T_INDEX_NS, PCB_STAT_T_HITS_NS);
-    edit_pairs_dev(ctx, bc, k, q_begin, q_end);
+    edit_pairs_dev(ctx, bc, k, q_begin, q_end, t_begin, t_end);
     if (n_edges) *n_edges = ctx->edges.n;
     PCB_CUDA(cudaStreamSynchronize(ctx->stream));
     stage_collect(ctx);

@@ -175,7 +175,7 @@ void bucket_launch(pcb_ctx *ctx, const uint8_t *seq, const int32_t *len, int32_t
                    PackedBarcodes *unique_out, BucketPending &st);
 int32_t bucket_finish(pcb_ctx *ctx, const BucketOut &out, PackedBarcodes *unique_out, BucketPending &st);
 
-void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q_begin, int32_t q_end);
+void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q_begin, int32_t q_end, int32_t t_begin = 0, int32_t t_end = -1);
 // f3: nearest library barcodes of every query within k; the (query, row, d) rows stay in ctx->edges
 void match_barcodes_dev(pcb_ctx *ctx, const PackedBarcodes &library, const PackedBarcodes &queries, int32_t k, int32_t *best_d,
                         int32_t *n_best, int32_t *first_hit);

@@ -21,21 +21,22 @@
 
 namespace pcb {
 
-__global__ void seed_count_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int32_t U,
+// the targets indexed are [t_begin, t_begin + U)
+__global__ void seed_count_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int32_t t_begin, int32_t U,
                                   SeedGeom g, uint32_t *__restrict__ bin_cnt) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)U * g.npos) return;
-  int32_t j = (int32_t)(i / g.npos), p = (int32_t)(i % g.npos);
+  int32_t j = t_begin + (int32_t)(i / g.npos), p = (int32_t)(i % g.npos);
   if (g.q > 0 && (p + g.q > len[j] || !((g.pos_mask >> p) & 1ull))) return;
   ulonglong2 pl = planes[j];
   atomicAdd(&bin_cnt[seed_bin(g, pl.x, pl.y, p, p)], 1u);
 }
 
-__global__ void seed_fill_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int32_t U,
+__global__ void seed_fill_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int32_t t_begin, int32_t U,
                                  SeedGeom g, uint32_t *__restrict__ cursor, int32_t *__restrict__ ent) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)U * g.npos) return;
-  int32_t j = (int32_t)(i / g.npos), p = (int32_t)(i % g.npos);
+  int32_t j = t_begin + (int32_t)(i / g.npos), p = (int32_t)(i % g.npos);
   if (g.q > 0 && (p + g.q > len[j] || !((g.pos_mask >> p) & 1ull))) return;
   ulonglong2 pl = planes[j];
   uint32_t at = atomicAdd(&cursor[seed_bin(g, pl.x, pl.y, p, p)], 1u);
@@ -246,15 +247,16 @@ __global__ void match_reduce_kernel(const int32_t *__restrict__ eq, const int32_
   best_d[q] = best; n_best[q] = cnt; first_hit[q] = first;
 }
 
-static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarcodes *queries, int32_t k, int32_t q_begin, int32_t q_end);
+static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarcodes *queries, int32_t k, int32_t q_begin, int32_t q_end,
+                        int32_t t_begin, int32_t t_end);
 
-void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q_begin, int32_t q_end) {
-  pair_search(ctx, bc, nullptr, k, q_begin, q_end);
+void edit_pairs_dev(pcb_ctx *ctx, const PackedBarcodes &bc, int32_t k, int32_t q_begin, int32_t q_end, int32_t t_begin, int32_t t_end) {
+  pair_search(ctx, bc, nullptr, k, q_begin, q_end, t_begin, t_end < 0 ? bc.n : t_end);
 }
 
 void match_barcodes_dev(pcb_ctx *ctx, const PackedBarcodes &library, const PackedBarcodes &queries, int32_t k, int32_t *best_d,
                         int32_t *n_best, int32_t *first_hit) {
-  pair_search(ctx, library, &queries, k, 0, queries.n);
+  pair_search(ctx, library, &queries, k, 0, queries.n, 0, library.n);
   const pcb_edges &e = ctx->edges;
   if (queries.n)
     PCB_LAUNCH(ctx, match_reduce_kernel, grid_for((size_t)queries.n, 256), 256, 0, e.ei, e.ej, e.ed, e.n, queries.n, best_d, n_best, first_hit);
@@ -262,7 +264,9 @@ void match_barcodes_dev(pcb_ctx *ctx, const PackedBarcodes &library, const Packe
 
 // Pairs (query, target) within k.  queries == nullptr: the self-join of the clustering path (every unordered pair
 // once, through its query side); otherwise the rows are (query index, target index) as they stand.
-static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarcodes *queries, int32_t k, int32_t q_begin, int32_t q_end) {
+// [t_begin, t_end): the targets that are indexed -- a pair is found by the call whose target range holds its target side.
+static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarcodes *queries, int32_t k, int32_t q_begin, int32_t q_end,
+                        int32_t t_begin, int32_t t_end) {
   free_edges(ctx);
   const bool self = queries == nullptr;
   const PackedBarcodes &qs = self ? bc : *queries;
@@ -271,9 +275,11 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
   ctx->stats[PCB_STAT_PROBE_NS] = 0;
   if (k < 0 || k > 8) throw Error(PCB_E_INPUT, "k must be in 0..8");
   if (q_begin < 0 || q_end > qs.n || q_begin > q_end) throw Error(PCB_E_INPUT, "query range outside [0, U)");
+  if (t_begin < 0 || t_end > bc.n || t_begin > t_end) throw Error(PCB_E_INPUT, "target range outside [0, U)");
+  const int32_t T = t_end - t_begin;
   pcb_edges &res = ctx->edges;
   res.valid = true;
-  if (U < (self ? 2 : 1) || q_begin == q_end) return;
+  if (U < (self ? 2 : 1) || q_begin == q_end || T == 0) return;
 
   // ---- seed lengths.  A query of length m splits into k+1 pieces of at least floor(m/(k+1)) bases, so it can
   // probe an index of q-grams with q up to that.  Most barcodes share one length; the few shorter ones (deletions)
@@ -333,13 +339,13 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
     const SeedGeom &g = idx[t].g;
     DevBuf<uint32_t> cursor(ctx, (size_t)g.nbins + 1);
     idx[t].bin_off.alloc(ctx, (size_t)g.nbins + 1);
-    idx[t].ent.alloc(ctx, (size_t)U * g.npos);
+    idx[t].ent.alloc(ctx, (size_t)T * g.npos);
     PCB_CUDA(cudaMemsetAsync(idx[t].bin_off.p, 0, ((size_t)g.nbins + 1) * sizeof(uint32_t), ctx->stream));
-    size_t n_slots = (size_t)U * g.npos;
-    PCB_LAUNCH(ctx, seed_count_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, U, g, idx[t].bin_off.p);
+    size_t n_slots = (size_t)T * g.npos;
+    PCB_LAUNCH(ctx, seed_count_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, t_begin, T, g, idx[t].bin_off.p);
     exclusive_scan_u32(ctx, idx[t].bin_off.p, idx[t].bin_off.p, (size_t)g.nbins + 1);
     PCB_CUDA(cudaMemcpyAsync(cursor.p, idx[t].bin_off.p, ((size_t)g.nbins + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    PCB_LAUNCH(ctx, seed_fill_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, U, g, cursor.p, idx[t].ent.p);
+    PCB_LAUNCH(ctx, seed_fill_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, t_begin, T, g, cursor.p, idx[t].ent.p);
   }
 
   stage_end(ctx, PCB_STAT_T_INDEX_NS);

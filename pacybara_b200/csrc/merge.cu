@@ -291,10 +291,13 @@ constexpr int SMALL_BLOCK = 128;
 __global__ void __launch_bounds__(SMALL_BLOCK) component_kernel_small(MergeCtx c, int32_t n_comp, int32_t *__restrict__ counters,
                                                                       int32_t *__restrict__ declined, int32_t *__restrict__ late) {
   __shared__ SmallSmem sm_all[SMALL_BLOCK / 32];
+  __shared__ int32_t jthr[33];
+  if (threadIdx.x < 33) jthr[threadIdx.x] = c.prm.jthr[threadIdx.x];
+  __syncthreads();
   const int32_t comp = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   if (comp >= n_comp) return;
   const int lane = threadIdx.x & 31;
-  const int rc = process_component_small(c, comp, lane, &sm_all[threadIdx.x >> 5], MED_CALLS, MED_PAIRS);
+  const int rc = process_component_small(c, comp, lane, &sm_all[threadIdx.x >> 5], jthr, MED_CALLS, MED_PAIRS);
   if (lane == 0 && rc == 1) declined[atomicAdd(&counters[CNT_DECLINED], 1)] = comp;
   if (lane == 0 && rc == 2) late[atomicAdd(&counters[CNT_LATE], 1)] = comp;
 }
@@ -611,6 +614,7 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   c.row_bc = out.row_bc; c.row_up = out.row_up; c.row_call_off = out.row_call_off; c.row_call_n = out.row_call_n;
   c.call_mut = out.call_mut; c.status = status.p;
   c.prm.maxDiff = in.max_diff; c.prm.minQual = in.min_qual; c.prm.minMatches = in.min_matches; c.prm.minJaccard = in.min_jaccard;
+  jaccard_thresholds(c.prm);
   const int32_t force_large = shape != PCB_REPLAY_AUTO ? 1 : 0;
   PCB_LAUNCH(ctx, classify_kernel, grid_for((size_t)U, 128), 128, 0, c, force_large, counters.p, medium.p, large.p);
   // every output starts as "not produced": entries of reads other shards own, the row fields of non-representative reads

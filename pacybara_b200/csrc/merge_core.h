@@ -40,7 +40,20 @@ struct GenoSlot {          // 32 bytes; an all-zero slot is empty, so a memset(0
 struct MergeParams {
   int32_t maxDiff, minQual, minMatches;
   double minJaccard;
+  // Jaccard as an integer threshold: jthr[u] = the smallest `inters` with (double)inters / (double)u > minJaccard
+  // (u + 1 if there is none), for a union of u = 1..32 mutations.  The quotient grows with inters, so
+  // "inters / uni > minJaccard" (:358-367, :447-452) is exactly "inters >= jthr[uni]" -- the same IEEE divide,
+  // done once per call on the host (jaccard_thresholds) instead of once per test.
+  int32_t jthr[33];
 };
+
+inline void jaccard_thresholds(MergeParams &p) {
+  p.jthr[0] = 0;
+  for (int32_t u = 1; u <= 32; u++) {
+    p.jthr[u] = u + 1;
+    for (int32_t i = u; i >= 0; i--) { if ((double)i / (double)u > p.minJaccard) p.jthr[u] = i; else break; }
+  }
+}
 
 #ifndef PCB_FILL                        // same values as include/pacybara_b200.h
 #define PCB_FILL INT32_MIN              // "not produced by this shard"
@@ -196,6 +209,21 @@ PCB_HD void table_clear(Table &t) {
   t.n_touched = 0;
 }
 
+// a distance the pair list does not hold, scored on the spot (kept out of line: it is rare and two Myers loops long)
+#if defined(__CUDACC__)
+__host__ __device__ __noinline__
+#else
+inline
+#endif
+int32_t on_demand_dist(const uint64_t *planes, const int32_t *blen, int32_t compute_k, int32_t wide, int32_t a, int32_t b) {
+  int32_t m = blen[a], n = blen[b];
+  int32_t dl = m > n ? m - n : n - m;
+  if (dl > compute_k) return -1;
+  int32_t d = wide ? myers64(planes[2 * a], planes[2 * a + 1], m, planes[2 * b], planes[2 * b + 1], n)
+                   : myers32((uint32_t)planes[2 * a], (uint32_t)planes[2 * a + 1], m, (uint32_t)planes[2 * b], (uint32_t)planes[2 * b + 1], n);
+  return d <= compute_k ? d : -1;
+}
+
 // distance between two buckets as edistLookup holds it (:236,:266,:294); -1 = absent (inf)
 PCB_HD int32_t lookup_dist(const MergeCtx &c, int32_t a, int32_t b) {
   if (a == b) return 0;
@@ -208,13 +236,7 @@ PCB_HD int32_t lookup_dist(const MergeCtx &c, int32_t a, int32_t b) {
   }
   if (lo < c.adj_ptr[a + 1] && c.adj_nbr[lo] == b) return c.adj_d[lo];
   if (c.compute_k < 0) return -1;
-  int32_t m = c.blen[a], n = c.blen[b];
-  int32_t dl = m > n ? m - n : n - m;
-  if (dl > c.compute_k) return -1;
-  int32_t d = c.wide ? myers64(c.planes[2 * a], c.planes[2 * a + 1], m, c.planes[2 * b], c.planes[2 * b + 1], n)
-                     : myers32((uint32_t)c.planes[2 * a], (uint32_t)c.planes[2 * a + 1], m,
-                               (uint32_t)c.planes[2 * b], (uint32_t)c.planes[2 * b + 1], n);
-  return d <= c.compute_k ? d : -1;
+  return on_demand_dist(c.planes, c.blen, c.compute_k, c.wide, a, b);
 }
 
 // SEED CLUSTERING of one bucket (:385-400)

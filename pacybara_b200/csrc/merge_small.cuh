@@ -47,7 +47,7 @@ struct alignas(16) SmallSmem {
   int32_t sum[SMALL_READS * SMALL_STRIDE];    // sum of Q
   uint16_t cnt[SMALL_READS * SMALL_STRIDE];   // low byte: #reads with Q > 0; high byte: #reads naming the mutation
   int32_t tab[SMALL_TAB];                     // mutation id + 1, 0 = empty
-  uint32_t tflag[SMALL_TAB];                  // 2: named by two reads or more; 4: some Q > minQual
+  uint32_t tflag[SMALL_TAB];                  // 2: named by two reads or more; 4: some Q > minQual; then: column + 1 (0 = dead)
   int32_t colmut[SMALL_MUTS];                 // column -> mutation id
   uint32_t near[3][32];                       // near[e-1][a]: buckets b of the component with dist(a, b) <= 2e
   int32_t bid[32];                            // local bucket -> bucket id
@@ -58,7 +58,8 @@ SIMT_FN uint32_t small_hash(int32_t mut) { return ((uint32_t)mut * 0x9E3779B1u) 
 // Returns 0 when the component was replayed; otherwise nothing was written: 3 = more than 32 reads (not this kernel's
 // tier), 1 = not eligible (more than 32 live mutations, huge qualities), 2 = not eligible AND more than med_calls
 // genotype entries or med_pairs rows (too big for the medium kernel's local copy as well).
-SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, SmallSmem *sm, int32_t med_calls, int32_t med_pairs) {
+// jthr: MergeParams::jthr somewhere a lane can index cheaply (shared memory on the device).
+SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, SmallSmem *sm, const int32_t *jthr, int32_t med_calls, int32_t med_pairs) {
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t lt = (1u << lane) - 1u;
   // The component's buckets are comp_buckets[b_lo .. b_hi) (ascending bucket id), bucket b's reads are
@@ -72,18 +73,18 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
     myb = c.comp_buckets ? c.comp_buckets[b_lo + lane] : b_lo + lane;
     myx0 = c.bucket_ptr[myb]; mysz = c.bucket_ptr[myb + 1] - myx0;
   }
-  int32_t incl = mysz;
-  for (int o = 1; o < 32; o <<= 1) {
-    const int32_t tv = simt::shfl(FULL, incl, lane >= o ? lane - o : lane);
-    if (lane >= o) incl += tv;
+  int32_t n = 0, mystart = 0;
+  uint32_t starts = 0;                     // bit L: a bucket starts at lane L (buckets are never empty)
+  for (int32_t bi = 0; bi < B; bi++) {
+    const int32_t sz = simt::shfl(FULL, mysz, bi);
+    if (lane == bi) mystart = n;
+    if (n < 32) starts |= 1u << n;
+    n += sz;
   }
-  const int32_t n = simt::shfl(FULL, incl, 31);
   if (n > SMALL_READS) return 3;
-  const int32_t mystart = incl - mysz;
   const bool has = lane < n;
   const int32_t minQual = c.prm.minQual, minMatches = c.prm.minMatches;
   const double minJaccard = c.prm.minJaccard;
-  const uint32_t starts = simt::reduce_or(FULL, lane < B ? (1u << mystart) : 0u);       // buckets are never empty
   const int32_t bkt = simt::popc(starts & (2u * (1u << lane) - 1u)) - 1;              // my bucket: last start <= lane
   const int32_t bsrc = has ? bkt : 0;
   const int32_t k_in_b = lane - simt::shfl(FULL, mystart, bsrc), x0_of_b = simt::shfl(FULL, myx0, bsrc);
@@ -104,15 +105,6 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
     for (int32_t i = lane; i < (n * SMALL_STRIDE + 7) / 8; i += 32) zc[i] = zero;
   }
   for (int32_t i = lane; i < SMALL_TAB; i += 32) { sm->tab[i] = 0; sm->tflag[i] = 0u; }
-  // Jaccard as an integer threshold: lane u holds the smallest `inters` with (double)inters / (double)u > minJaccard
-  // (u + 1 if there is none; lane 0 holds the entry for u = 32).  The quotient grows with inters, so
-  // "inters / uni > minJaccard" (:358-367, :447-452) is exactly "inters >= thr[uni]" -- the same IEEE divide, done once.
-  int32_t thr;
-  {
-    const int32_t u = lane == 0 ? 32 : lane;
-    thr = u + 1;
-    for (int32_t i = u; i >= 0; i--) if ((double)i / (double)u > minJaccard) thr = i; else break;
-  }
   simt::sync(FULL);
   // A mutation that a single read of the whole component names, with Q <= minQual, can never pass filterSeqError
   // (:350-356: it is seen once and its sum stays <= minQual in any pair of clusters) nor be called in a cluster
@@ -139,32 +131,30 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
 #pragma unroll
   for (int w = 0; w < SMALL_TAB / 32; w++) { live[w] = simt::ballot(FULL, sm->tflag[32 * w + lane] != 0u); M += simt::popc(live[w]); }
   if (simt::ballot(FULL, bad) != 0u || M > SMALL_MUTS) {
-    int32_t ne = g1 - g0;
-    for (int o = 16; o > 0; o >>= 1) ne += simt::shfl(FULL, ne, lane ^ o);
+    const int32_t ne = simt::reduce_add(FULL, g1 - g0);
     return (ne > med_calls || c.cpair_ptr[comp + 1] - c.cpair_ptr[comp] > med_pairs) ? 2 : 1;
   }
   {
-    int32_t base = 0;
+    int32_t base = 0;                      // live slots get the columns 0 .. M-1 in slot order
 #pragma unroll
     for (int w = 0; w < SMALL_TAB / 32; w++) {
-      if ((live[w] >> lane) & 1u) sm->colmut[base + simt::popc(live[w] & lt)] = sm->tab[32 * w + lane] - 1;
+      if ((live[w] >> lane) & 1u) {
+        const int32_t col = base + simt::popc(live[w] & lt);
+        sm->colmut[col] = sm->tab[32 * w + lane] - 1;
+        sm->tflag[32 * w + lane] = (uint32_t)col + 1u;
+      }
       base += simt::popc(live[w]);
     }
   }
+  simt::sync(FULL);
   for (int32_t e = g0; e < g1; e++) {
     const int32_t mut = c.geno_mut[e], q = c.geno_q[e];
     uint32_t h = small_hash(mut);
     while (sm->tab[h] != mut + 1) h = (h + 1) & (SMALL_TAB - 1);
-    int32_t col = 0;
-    bool alive = false;
-#pragma unroll
-    for (int w = 0; w < SMALL_TAB / 32; w++) {
-      if ((int)(h >> 5) == w) { alive = ((live[w] >> (h & 31u)) & 1u) != 0u; col += simt::popc(live[w] & ((1u << (h & 31u)) - 1u)); }
-      else if ((int)(h >> 5) > w) col += simt::popc(live[w]);
-    }
-    if (!alive) continue;
-    sm->sum[lane * SMALL_STRIDE + col] = q;                                      // mutation ids are distinct within a read
-    sm->cnt[lane * SMALL_STRIDE + col] = (uint16_t)(0x100 | (q > 0 ? 1 : 0));
+    const uint32_t col1 = sm->tflag[h];
+    if (col1 == 0u) continue;                                                    // dead
+    sm->sum[lane * SMALL_STRIDE + (col1 - 1u)] = q;                              // mutation ids are distinct within a read
+    sm->cnt[lane * SMALL_STRIDE + (col1 - 1u)] = (uint16_t)(0x100 | (q > 0 ? 1 : 0));
   }
   simt::sync(FULL);
   const int32_t mymut = lane < M ? sm->colmut[lane] : -1;
@@ -250,7 +240,7 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
       // the loop below links (r1, r0), then appends r2, r3, ...: one cluster r1, r0, r2, ..., created first in this bucket,
       // whose sums are the column sums just taken.
       const int32_t g = simt::popc(m0);
-      const int32_t tg = simt::shfl(FULL, thr, g & 31);
+      const int32_t tg = c.prm.jthr[g];
       if (!(g == 0 || (g >= tg && g >= minMatches))) continue;
       if (inb) { cid = lo + 1; pos = lane == lo + 1 ? 0 : lane == lo ? 1 : lane - lo; keyb = bucket; keyn = 0; }
       sm->sum[(lo + 1) * SMALL_STRIDE + lane] = colsum;
@@ -261,7 +251,7 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
     for (int32_t ri = lo + 1; ri < hi; ri++) {
       const uint32_t mi = simt::shfl(FULL, mymask, ri);
       const int32_t inters = simt::popc(mi & mymask), uni = simt::popc(mi | mymask);        // calcJaccard on presence (:358-367)
-      const int32_t tu = simt::shfl(FULL, thr, uni & 31);
+      const int32_t tu = jthr[uni];
       const bool ok = lane >= lo && lane < ri && (uni == 0 || (inters >= tu && inters >= minMatches));
       uint32_t J = simt::ballot(FULL, ok);
       int32_t ci = -1;                                             // read i is in no cluster when its row of pairs starts
@@ -329,7 +319,7 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
           const bool keep = o1 + o2 > 1 || v1 + v2 > minQual;                    // filterSeqError across both clusters
           const int32_t inters = simt::popc(simt::ballot(FULL, keep && v1 > 0 && v2 > 0));
           const int32_t uni = simt::popc(simt::ballot(FULL, keep && (v1 > 0 || v2 > 0)));
-          if (!(uni == 0 || inters >= simt::shfl(FULL, thr, uni & 31))) break;    // genotype rule (:447-452)
+          if (!(uni == 0 || inters >= c.prm.jthr[uni])) break;                      // genotype rule (:447-452)
           PCB_LINK(R1, R2, C1, C2, -1, -1);
           linked = true;
         } while (0);
@@ -349,8 +339,7 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
   int64_t call_base = 0;
   if (c.call_off) call_base = c.call_off[comp];
   else {
-    int32_t ne = g1 - g0;
-    for (int o = 16; o > 0; o >>= 1) ne += simt::shfl(FULL, ne, lane ^ o);
+    const int32_t ne = simt::reduce_add(FULL, g1 - g0);
     int32_t lo32 = 0, hi32 = 0;
     if (lane == 0) { const int64_t at = simt::atomic_add64(c.call_cursor, (int64_t)ne); lo32 = (int32_t)(at & 0xFFFFFFFFll); hi32 = (int32_t)(at >> 32); }
     lo32 = simt::shfl(FULL, lo32, 0); hi32 = simt::shfl(FULL, hi32, 0);

@@ -79,13 +79,17 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu) {
   const int per_query = g.q == 0 ? 1 : (k + 1) * n_shift;
   const unsigned long long n_probe = (unsigned long long)(a.q_end - a.q_begin) * per_query;
   const unsigned long long n_blocks = (n_probe + 31) / 32;
-  unsigned long long n_started = 0, n_cells = 0, n_walked = 0, n_sided = 0;
+  uint32_t n_started = 0, n_cells = 0, n_walked = 0, n_sided = 0;      // per lane; widened when the warp is done
   int cnt = 0;                       // queued survivors (uniform)
   bool exhausted = false;            // no more probe blocks (uniform)
-  // my probe
+  // my probe; and, when the block's bins are long, the probe the whole warp is walking together
   uint32_t lo = 0, hi = 0;
   int32_t qi = -1, qm = 0;
   uint32_t qcounts = 0, qrev = 0;
+  int mode = 0;                      // 0: fetch a block of probes; 1: every lane walks its own bin; 2: the warp walks bin after bin
+  int coop_p = -1;
+  uint32_t c_at = 0, c_hi = 0, c_counts = 0, c_rev = 0;
+  int32_t c_qi = 0, c_qm = 0;
   // my pair
   bool active = false;
   uint32_t Pv = 0, Mv = 0, rl = 0, rh = 0, pL = 0, pH = 0;
@@ -93,7 +97,7 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu) {
   for (;;) {
     // ---- filter: until a warp's worth of survivors waits (or the probes run out)
     while (cnt < 32 && !exhausted) {
-      if (simt::ballot(FULL, lo < hi) == 0u) {
+      if (mode == 0) {
         unsigned long long blk = 0;
         if (lane == 0) blk = simt::atomic_add_u64(&a.counters[3], 1ull);
         const uint32_t b_lo = simt::shfl(FULL, (uint32_t)(blk & 0xFFFFFFFFull), 0), b_hi = simt::shfl(FULL, (uint32_t)(blk >> 32), 0);
@@ -117,32 +121,68 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu) {
             qrev = (st < qm - (st + g.q)) ? 0x80000000u : 0u;
           }
         }
+        // long bins (a big library): the warp walks them one after the other, 32 entries per step, coalesced;
+        // short bins: every lane walks its own
+        mode = simt::reduce_add(FULL, (int32_t)(hi - lo)) >= 32 * 12 ? 2 : 1;
+        coop_p = -1; c_at = c_hi = 0;
         continue;
       }
       bool keep = false;
-      int32_t j = 0;
-      if (lo < hi) {
-        j = a.ent[lo++];
-        n_walked++;
-        if (j != qi && is_query_side(qi, j)) {
-          n_sided++;
-          const uint32_t sk = a.sketch[j];
-          const int32_t dl = qm - (int32_t)(sk >> 24);
-          if (dl <= k && -dl <= k) {
-            const uint32_t tc = sketch_counts(sk);
-            const uint32_t up = simt::surplus4(qcounts, tc), down = simt::surplus4(tc, qcounts);
-            keep = (int32_t)(up > down ? up : down) <= k;
+      int32_t j = 0, kq = 0;
+      uint32_t krev = 0;
+      if (mode == 1) {
+        if (simt::ballot(FULL, lo < hi) == 0u) { mode = 0; continue; }
+        if (lo < hi) {
+          j = simt::ld_stream(&a.ent[lo++]);
+          n_walked++;
+          if (j != qi && is_query_side(qi, j)) {
+            n_sided++;
+            const uint32_t sk = a.sketch[j];
+            const int32_t dl = qm - (int32_t)(sk >> 24);
+            if (dl <= k && -dl <= k) {
+              const uint32_t tc = sketch_counts(sk);
+              const uint32_t up = simt::surplus4(qcounts, tc), down = simt::surplus4(tc, qcounts);
+              keep = (int32_t)(up > down ? up : down) <= k;
+            }
           }
         }
+        kq = qi; krev = qrev;
+      } else {
+        if (c_at >= c_hi) {                                  // next probe of the block that has entries
+          const uint32_t left = simt::ballot(FULL, lo < hi);
+          if (left == 0u) { mode = 0; continue; }
+          coop_p = simt::ffs(left) - 1;
+          c_qi = simt::shfl(FULL, qi, coop_p); c_qm = simt::shfl(FULL, qm, coop_p);
+          c_at = simt::shfl(FULL, lo, coop_p); c_hi = simt::shfl(FULL, hi, coop_p);
+          c_counts = simt::shfl(FULL, qcounts, coop_p); c_rev = simt::shfl(FULL, qrev, coop_p);
+          if (lane == coop_p) lo = hi;
+        }
+        const uint32_t e = c_at + (uint32_t)lane;
+        if (e < c_hi) {
+          j = simt::ld_stream(&a.ent[e]);
+          n_walked++;
+          if (j != c_qi && is_query_side(c_qi, j)) {
+            n_sided++;
+            const uint32_t sk = a.sketch[j];
+            const int32_t dl = c_qm - (int32_t)(sk >> 24);
+            if (dl <= k && -dl <= k) {
+              const uint32_t tc = sketch_counts(sk);
+              const uint32_t up = simt::surplus4(c_counts, tc), down = simt::surplus4(tc, c_counts);
+              keep = (int32_t)(up > down ? up : down) <= k;
+            }
+          }
+        }
+        c_at += 32u;
+        kq = c_qi; krev = c_rev;
       }
       const uint32_t mask = simt::ballot(FULL, keep);
       if (keep) {
         const int at = cnt + simt::popc(mask & lt);
-        qu->qi[at] = qi; qu->tj[at] = (int32_t)((uint32_t)j | qrev);
+        qu->qi[at] = kq; qu->tj[at] = (int32_t)((uint32_t)j | krev);
       }
       cnt += simt::popc(mask);
-      simt::sync(FULL);
     }
+    simt::sync(FULL);
     // ---- lanes without a pair take one
     {
       const uint32_t idle = simt::ballot(FULL, !active);
@@ -194,7 +234,7 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu) {
     }
     // ---- checkpoint
     if (active) {
-      n_cells += (unsigned long long)((pj - pj_before) * pm);
+      n_cells += (uint32_t)((pj - pj_before) * pm);
       if (pj >= pn) {
         const uint32_t rows = pm >= 32 ? 0xFFFFFFFFu : ((1u << pm) - 1u);
         const int d = pn + simt::popc(Pv & rows) - simt::popc(Mv & rows);
@@ -217,13 +257,7 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu) {
       }
     }
   }
-  for (int o = 16; o > 0; o >>= 1) {
-    n_started += ((unsigned long long)simt::shfl(FULL, (uint32_t)(n_started >> 32), lane ^ o) << 32) | simt::shfl(FULL, (uint32_t)n_started, lane ^ o);
-    n_cells += ((unsigned long long)simt::shfl(FULL, (uint32_t)(n_cells >> 32), lane ^ o) << 32) | simt::shfl(FULL, (uint32_t)n_cells, lane ^ o);
-    n_walked += ((unsigned long long)simt::shfl(FULL, (uint32_t)(n_walked >> 32), lane ^ o) << 32) | simt::shfl(FULL, (uint32_t)n_walked, lane ^ o);
-    n_sided += ((unsigned long long)simt::shfl(FULL, (uint32_t)(n_sided >> 32), lane ^ o) << 32) | simt::shfl(FULL, (uint32_t)n_sided, lane ^ o);
-  }
-  if (lane == 0 && n_walked) {
+  if (n_walked) {
     simt::atomic_add_u64(&a.counters[1], n_started); simt::atomic_add_u64(&a.counters[2], n_cells);
     simt::atomic_add_u64(&a.counters[4], n_walked); simt::atomic_add_u64(&a.counters[5], n_sided);
   }

@@ -19,6 +19,7 @@ SIMT_FN uint32_t shfl(uint32_t mask, uint32_t v, int src) { return __shfl_sync(m
 SIMT_FN uint32_t match_any(uint32_t mask, int32_t v) { return __match_any_sync(mask, v); }
 SIMT_FN uint32_t reduce_or(uint32_t mask, uint32_t v) { return __reduce_or_sync(mask, v); }
 SIMT_FN int32_t reduce_max(uint32_t mask, int32_t v) { return __reduce_max_sync(mask, v); }
+SIMT_FN int32_t reduce_add(uint32_t mask, int32_t v) { return __reduce_add_sync(mask, v); }
 SIMT_FN void sync(uint32_t mask) { __syncwarp(mask); }
 SIMT_FN int32_t atomic_cas(int32_t *p, int32_t cmp, int32_t v) { return atomicCAS(p, cmp, v); }
 SIMT_FN uint32_t atomic_or(uint32_t *p, uint32_t v) { return atomicOr(p, v); }
@@ -28,6 +29,7 @@ SIMT_FN int popc(uint32_t x) { return __popc(x); }
 SIMT_FN int ffs(uint32_t x) { return __ffs((int)x); }      // 1-based, 0 when x == 0
 SIMT_FN float sqrt_f(float x) { return sqrtf(x); }
 SIMT_FN uint32_t brev(uint32_t x) { return __brev(x); }
+SIMT_FN int32_t ld_stream(const int32_t *p) { return __ldcs(p); }      // read once: do not keep it in the caches
 SIMT_FN unsigned long long atomic_add_u64(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
 // sum over the four bytes of max(0, a_byte - b_byte)
 SIMT_FN uint32_t surplus4(uint32_t a, uint32_t b) { return __vsadu4(__vsubus4(a, b), 0u); }
@@ -45,6 +47,7 @@ uint32_t shfl(uint32_t mask, uint32_t v, int src);
 uint32_t match_any(uint32_t mask, int32_t v);
 uint32_t reduce_or(uint32_t mask, uint32_t v);
 int32_t reduce_max(uint32_t mask, int32_t v);
+int32_t reduce_add(uint32_t mask, int32_t v);
 void sync(uint32_t mask);
 // lanes run one at a time between collectives, so plain read-modify-writes are atomic
 inline int32_t atomic_cas(int32_t *p, int32_t cmp, int32_t v) { int32_t o = *p; if (o == cmp) *p = v; return o; }
@@ -54,6 +57,7 @@ inline int64_t atomic_add64(int64_t *p, int64_t v) { int64_t o = *p; *p = o + v;
 inline int popc(uint32_t x) { return __builtin_popcount(x); }
 inline int ffs(uint32_t x) { return __builtin_ffs((int)x); }
 inline float sqrt_f(float x) { return sqrtf(x); }
+inline int32_t ld_stream(const int32_t *p) { return *p; }
 inline uint32_t brev(uint32_t x) { uint32_t r = 0; for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i); return r; }
 inline unsigned long long atomic_add_u64(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 inline uint32_t surplus4(uint32_t a, uint32_t b) {

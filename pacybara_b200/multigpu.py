@@ -3,8 +3,9 @@
 What shards and what is exchanged:
   1. bucketing            replicated -- every rank buckets the whole read set (HBM-bound, a few ms;
                           it yields the identical bucket numbering everywhere without an exchange);
-  2. distance pairs       SHARDED by query bucket: rank r scores the pairs whose query side lies in
-                          its slice of [0, U) (pcb_edit_pairs q_begin/q_end) -- the dominant kernel;
+  2. distance pairs       SHARDED by target bucket: rank r indexes its slice of [0, U) and scores the pairs
+                          whose target side lies in it (pcb_edit_pairs t_begin/t_end) -- the dominant kernel, and
+                          the index build divides with it;
   3. edge exchange        the one real collective: all-gather of the per-rank edge lists (counts, then
                           the padded (i, j, d) payload) over NVLink, then pcb_sort_edges restores the
                           canonical row order;
@@ -134,10 +135,10 @@ def cluster_reads_sharded(ctx: Context, arrs: Dict, params: Dict, rank: int, wor
     b = ctx.bucket(a["seq"], None, a["length"], want_qsum=False)      # qualities are not needed for clustering
     lib_stages("bucket")
     U = b["n_buckets"]
-    # 2. my slice of the query buckets
+    # 2. my slice of the target buckets (every pair has one query side and one target side)
     lo, hi = shard_range(U, rank, world)
     bseq, blen = b["bucket_seq"].contiguous(), b["bucket_len"].contiguous()
-    ei, ej, ed = ctx.edit_pairs(bseq, blen, (2 if full_table else 1) * max_diff, q_range=(lo, hi))
+    ei, ej, ed = ctx.edit_pairs(bseq, blen, (2 if full_table else 1) * max_diff, t_range=(lo, hi))
     lib_stages("index", "probe", "hits")
     local_stats = dict(pairs_scored=ctx.stat("pairs_scored"), cells=ctx.stat("cells"), probe_ns=ctx.stat("probe_ns"))
     # 3. exchange edges
@@ -188,3 +189,35 @@ def cluster_reads_sharded(ctx: Context, arrs: Dict, params: Dict, rank: int, wor
         torch.cuda.current_stream(ctx.device).synchronize()
         out = {k: (v.numpy() if hasattr(v, "numpy") and not isinstance(v, (int, dict)) else v) for k, v in host.items()}
     return out
+
+
+def cluster_reads_virtual(ctx: Context, arrs: Dict, params: Dict, world: int, full_table: bool = False) -> Dict:
+    """The sharded algorithm with `world` VIRTUAL ranks on ONE GPU, one after the other: what every rank computes in
+    cluster_reads_sharded (its slice of the pair search, its components of the merge, its compacted shard), with the
+    collectives replaced by concatenation.  No NCCL involved: this exists so that the decomposition itself -- target
+    slices that partition the pairs, components dealt to shards, shards reassembled -- is checked wherever one GPU is
+    available.  `arrs`: CUDA tensors as for cluster_reads_sharded(on_device=True).  Returns per-read host arrays."""
+    import torch
+    from . import hostdata
+    max_diff = int(params["max_diff"])
+    R = int(arrs["length"].shape[0])
+    b = ctx.bucket(arrs["seq"], None, arrs["length"], want_qsum=False)
+    U = b["n_buckets"]
+    bseq, blen = b["bucket_seq"].contiguous(), b["bucket_len"].contiguous()
+    parts = [ctx.edit_pairs(bseq, blen, (2 if full_table else 1) * max_diff, t_range=shard_range(U, r, world)) for r in range(world)]
+    ei, ej, ed = (torch.cat([p[t] for p in parts]).contiguous() for t in range(3))        # the all-gather
+    ctx.sort_edges(ei, ej, ed, U)
+    ped = torch.where((ed >= 1) & (ed <= max_diff), ed, torch.zeros_like(ed))
+    prob = MergeProblem(n_reads=R, n_buckets=U, bucket_ptr=b["bucket_ptr"].contiguous(), bucket_reads=b["bucket_reads"].contiguous(),
+                        lexrank=arrs["lexrank"], bc_id=b["bucket_of_read"].contiguous(), up_id=arrs.get("up_id"), geno_ptr=arrs["geno_ptr"],
+                        geno_mut=arrs["geno_mut"], geno_q=arrs["geno_q"], mut_rank=arrs["mut_rank"], max_diff=max_diff,
+                        min_qual=int(params["min_qual"]), min_jaccard=float(params["min_jaccard"]), min_matches=int(params["min_matches"]))
+    shards = []
+    for r in range(world):
+        kw = {} if full_table else dict(bucket_seq=bseq, bucket_len=blen, on_demand_k=2 * max_diff)
+        out = ctx.merge(prob, PairList(ei, ej, ed, ped), shard=(r, world), pairs_sorted=True, shard_layout=False, **kw)
+        shard = ctx.compact_shard(dict(out, bucket_of_read=b["bucket_of_read"]), to_host=True)
+        shards.append({k: (np.array(v) if hasattr(v, "shape") else v) for k, v in shard.items()})
+    whole = hostdata.merge_outputs_from_shards(shards, R)
+    whole.update(n_buckets=U, n_edges=int(ei.numel()), shard_rows=[int(s["row_rep"].shape[0]) for s in shards])
+    return whole

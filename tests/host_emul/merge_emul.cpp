@@ -121,6 +121,7 @@ extern "C" int emul_merge(int32_t R, int32_t U, const int32_t *bucket_ptr, const
   c.row_bc = row_bc; c.row_up = row_up; c.row_call_off = row_call_off; c.row_call_n = row_call_n;
   c.call_mut = call_mut; c.status = status;
   c.prm.maxDiff = max_diff; c.prm.minQual = min_qual; c.prm.minMatches = min_matches; c.prm.minJaccard = min_jaccard;
+  jaccard_thresholds(c.prm);
   int32_t n_small = 0;
   int64_t call_cursor = 0;
   if (use_small) { c.call_off = nullptr; c.call_cursor = &call_cursor; }     // regions from the shared cursor, like csrc/merge.cu
@@ -129,7 +130,7 @@ extern "C" int emul_merge(int32_t R, int32_t U, const int32_t *bucket_ptr, const
     if (label[comp_buckets[comp_ptr[comp]]] % shard_count != shard_rank) continue;
     if (use_small) {
       int rc[32];
-      simt_emul::run_warp([&](int lane) { rc[lane] = process_component_small(c, comp, lane, &smem, 1 << 30, 1 << 30); }, (unsigned)(use_small + comp));
+      simt_emul::run_warp([&](int lane) { rc[lane] = process_component_small(c, comp, lane, &smem, c.prm.jthr, 1 << 30, 1 << 30); }, (unsigned)(use_small + comp));
       for (int l = 1; l < 32; l++) if (rc[l] != rc[0]) return -2;
       if (rc[0] == 0) { n_small++; continue; }
     }

@@ -13,7 +13,7 @@
 
 namespace {
 
-enum Op { OP_BALLOT = 1, OP_SHFL, OP_MATCH, OP_OR, OP_MAX, OP_SYNC };
+enum Op { OP_BALLOT = 1, OP_SHFL, OP_MATCH, OP_OR, OP_MAX, OP_ADD, OP_SYNC };
 
 struct Rendezvous {          // one per distinct mask: disjoint or nested lane subsets meet independently, as on the device
   uint32_t mask = 0, arrived = 0;
@@ -67,6 +67,7 @@ uint32_t collective(int op, uint32_t mask, uint32_t v, uint32_t aux) {
         }
         case OP_MATCH: for (int t = 0; t < 32; t++) if (((mask >> t) & 1u) && rv.val[t] == rv.val[l]) out |= 1u << t; break;
         case OP_OR: for (int t = 0; t < 32; t++) if ((mask >> t) & 1u) out |= rv.val[t]; break;
+        case OP_ADD: for (int t = 0; t < 32; t++) if ((mask >> t) & 1u) out += rv.val[t]; break;
         case OP_MAX: {
           int32_t m = INT32_MIN;
           for (int t = 0; t < 32; t++) if (((mask >> t) & 1u) && (int32_t)rv.val[t] > m) m = (int32_t)rv.val[t];
@@ -95,6 +96,7 @@ uint32_t shfl(uint32_t mask, uint32_t v, int src) { return collective(OP_SHFL, m
 uint32_t match_any(uint32_t mask, int32_t v) { return collective(OP_MATCH, mask, (uint32_t)v, 0); }
 uint32_t reduce_or(uint32_t mask, uint32_t v) { return collective(OP_OR, mask, v, 0); }
 int32_t reduce_max(uint32_t mask, int32_t v) { return (int32_t)collective(OP_MAX, mask, (uint32_t)v, 0); }
+int32_t reduce_add(uint32_t mask, int32_t v) { return (int32_t)collective(OP_ADD, mask, (uint32_t)v, 0); }
 void sync(uint32_t mask) { collective(OP_SYNC, mask, 0, 0); }
 }  // namespace simt
 

@@ -307,6 +307,34 @@ def test_fused_cfg2_full_size_properties(ctx):
     assert rows.n_clusters > 0.9 * lib.params["n_clones"]
 
 
+# ----------------------------------------------------------------------------- the multi-GPU decomposition on one GPU
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("kw", [dict(cfg="cfg1"), dict(n_clones=300, n_reads=5000, p_err=0.03, p_near=0.4, p_collide=0.2, seed=41),
+                                dict(n_clones=200, n_reads=3000, combo=True, p_err=0.01, p_near=0.3, seed=42, max_diff=3)])
+def test_sharded_algorithm_with_virtual_ranks(ctx, kw, world):
+    """What N ranks compute in pacybara_b200.multigpu -- target slices of the pair search, components dealt to shards,
+    compacted shards put back together -- executed rank after rank on this GPU (no NCCL): the rows must be those of the
+    single call, which the other tests pin to the oracle.  (The collectives themselves run in bench.py --gpus N, whose
+    line carries the same comparison, and in tests/multigpu_check.py.)"""
+    import torch
+    from pacybara_b200 import multigpu, pipeline
+    kw = dict(kw)
+    md = kw.pop("max_diff", 2)
+    lib = synth.make_config(kw["cfg"], seed=5) if "cfg" in kw else synth.make_library(**kw)
+    ra, names = pipeline.arrays_from_library(lib, ctx)
+    params = dict(max_diff=md, min_qual=32, min_jaccard=0.2, min_matches=1)
+    dev = {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in vars(ra).items() if v is not None}
+    single = ctx.cluster_reads(dev["seq"], dev["qual"], dev["length"], dev["lexrank"], dev.get("up_id"), dev["geno_ptr"], dev["geno_mut"],
+                               dev["geno_q"], dev["mut_rank"], **params)
+    single = {k: (v.cpu().numpy() if hasattr(v, "cpu") else v) for k, v in single.items()}
+    want = hostdata.rows_from_merge_outputs(single)
+    for full in (False, True):
+        whole = multigpu.cluster_reads_virtual(ctx, dev, params, world, full_table=full)
+        assert np.array_equal(whole["bucket_of_read"], single["bucket_of_read"])
+        _rows_equal(hostdata.rows_from_merge_outputs(whole), want)
+        assert sum(whole["shard_rows"]) == want.n_rows and min(whole["shard_rows"]) > 0
+
+
 # ----------------------------------------------------------------------------- many small random libraries
 def _rows_equal(a, b):
     for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
