@@ -27,8 +27,12 @@
  *     context's device; nothing is copied, results stay there);
  *   - the caller owns every array and sizes it as documented; scalars returned through
  *     pointers are always host memory;
- *   - barcodes are ASCII over {A,C,G,T}, 1..64 nt, one per row of a [n, stride] uint8 matrix;
- *     anything else is refused with PCB_E_INPUT (no fallback path exists);
+ *   - barcodes are ASCII strings, one per row of a [n, stride] uint8 matrix, len[i] <= stride characters.  Those of
+ *     1..64 bases over {A,C,G,T} are packed into 2-bit planes and take part in everything.  Any other barcode (another
+ *     character such as N, more than 64 characters, or none) is kept as the opaque string the reference treats every
+ *     barcode as (src/pacybara_precluster.py:28-39): it is bucketed with its exact copies (by a 128-bit hash of its
+ *     bytes) and clusters like any bucket, but takes no part in the pair search -- no distance is reported for it.
+ *     Only a negative length or one beyond `stride` is refused (PCB_E_INPUT);
  *   - one context per GPU and per host thread; calls on one context are serialised.
  *
  * There is no CPU implementation behind this ABI: without a CUDA device every entry point
@@ -48,7 +52,7 @@ extern "C" {
 enum {
   PCB_OK = 0,
   PCB_E_CUDA = 1,      /* CUDA runtime / no device */
-  PCB_E_INPUT = 2,     /* malformed input (non-ACGT base, length 0 or > 64, bad ids, ...) */
+  PCB_E_INPUT = 2,     /* malformed input (a length outside the matrix, bad parameters, ...) */
   PCB_E_CAPACITY = 3,  /* caller buffer too small; the needed size is reported */
   PCB_E_STATE = 4,     /* call order (e.g. fetch before compute) */
   PCB_E_UPTAG = 5      /* a clustered read has no uptag (the reference's KeyError, :519) */
@@ -99,7 +103,7 @@ int64_t pcb_stat(const pcb_ctx *ctx, int which);
  * PCB_REPLAY_WARP (the generic warp kernel for everything).  All shapes give identical results; the knob exists
  * for measurements and for the parity tests, which run every shape.
  */
-enum { PCB_OPT_REPLAY_SHAPE = 0 };
+enum { PCB_OPT_REPLAY_SHAPE = 0, PCB_OPT_TRACE = 1 /* 1: host-side lap times of the stages on stderr (development aid) */ };
 enum { PCB_REPLAY_AUTO = 0, PCB_REPLAY_THREAD = 1, PCB_REPLAY_WARP = 2 };
 int pcb_set_option(pcb_ctx *ctx, int option, int64_t value);
 /* Block until everything queued on the context's stream has finished. */

@@ -195,6 +195,35 @@ def textquirks_texts():
     return fastq[:-1] if fastq.endswith("\n") and not fastq.endswith("\r\n") else fastq, "".join(ge), uptag
 
 
+def opaque_texts():
+    """A small library in which some barcodes do not fit 2-bit planes: a 70-nt insertion call (three reads), a barcode
+    with an N (two reads), one read with an N all of its own.  The reference treats them like any other string."""
+    long_ = "ACGTTGCA" * 8 + "ACGTAC"                      # 70 nt
+    n_bc = "TTGCANTGCATTGCATTGCATTGCA"
+    reads = [("r01", A, "10A>G:50"), ("r02", long_, "7C>T:60"), ("r03", A, "10A>G:55"), ("r04", n_bc, "="), ("r05", A1, "10A>G:45"),
+             ("r06", long_, "7C>T:58"), ("r07", B, "5A>T:90"), ("r08", n_bc, "="), ("r09", long_, "7C>T:61;99G>C:12"),
+             ("r10", B, "5A>T:88"), ("r11", "GGGGGCCCCCAAAAANTTTTGGGGG", "3A>C:70"), ("r12", B1, "=")]
+    return _fq(reads), _geno(reads), _fq(reads)
+
+
+def add_opaque():
+    """Adds tests/golden/x_opaque.json.gz (and its INDEX entry) without touching the other fixtures."""
+    fastq, geno, uptag = opaque_texts()
+    case = run_case("x_opaque", fastq, geno, uptag, "canonical", _params({}), note="oracle.make_golden.opaque_texts()")
+    assert case["exit_code"] == 0, case["stderr_tail"]
+    with gzip.GzipFile(os.path.join(GOLDEN_DIR, "x_opaque.json.gz"), "wb", mtime=0) as fh:
+        fh.write(json.dumps(case, indent=0).encode())
+    ipath = os.path.join(GOLDEN_DIR, "INDEX.json")
+    with open(ipath) as fh:
+        index = [e for e in json.load(fh) if e["name"] != "x_opaque"]
+    index.append(dict(name="x_opaque", exit_code=case["exit_code"], n_rows=case["n_rows"], digest=case["digest"]))
+    with open(ipath, "w") as fh:
+        json.dump(index, fh, indent=1)
+    print(f"x_opaque exit={case['exit_code']} rows={case['n_rows']}")
+    for row in case["table"]:
+        print("  ", row)
+
+
 def add_textquirks():
     """Adds tests/golden/x_textquirks.json.gz (and its INDEX entry) without touching the other fixtures."""
     fastq, geno, uptag = textquirks_texts()
@@ -212,6 +241,10 @@ def add_textquirks():
 
 
 def main():
+    if "--add-opaque" in sys.argv:
+        if not ref_runner.available():
+            sys.exit("reference scripts not found")
+        return add_opaque()
     if "--add-textquirks" in sys.argv:
         if not ref_runner.available():
             sys.exit("reference scripts not found")

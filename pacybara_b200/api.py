@@ -78,6 +78,8 @@ class Context:
         if shape not in _lib.REPLAY_SHAPES:
             raise ValueError(f"unknown replay shape {shape!r}")
         self._check(self.lib.pcb_set_option(self.h, _lib.OPT_REPLAY_SHAPE, _lib.REPLAY_SHAPES[shape]))
+        if os.environ.get("PCB_TRACE"):
+            self._check(self.lib.pcb_set_option(self.h, 1, 1))
 
     def stream_handle(self) -> int:
         return int(self.lib.pcb_stream(self.h) or 0)

@@ -223,6 +223,7 @@ int pcb_set_option(pcb_ctx *ctx, int option, int64_t value) {
     ctx->replay_shape = (int)value;
     return PCB_OK;
   }
+  if (option == PCB_OPT_TRACE) { ctx->trace = value != 0; return PCB_OK; }
   ctx->err = "pcb_set_option: unknown option or value";
   return PCB_E_INPUT;
 }

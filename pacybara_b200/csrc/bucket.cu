@@ -15,7 +15,7 @@
 
 namespace pcb {
 
-// flags[0] = first offending row + 1 (0xFFFFFFFF: none), flags[1] = min length, flags[2] = max length,
+// flags[0] = first offending row + 1 (0xFFFFFFFF: none), flags[1] = min length, flags[2] = max length, flags[3] = opaque barcodes,
 // flags[4 + m] = barcodes of length m (m = 1..64): the pair search picks its seed lengths from that histogram
 constexpr int PACK_FLAGS = 4 + 66;
 __global__ void __launch_bounds__(128) pack_kernel(const uint8_t *__restrict__ seq, const int32_t *__restrict__ len,
@@ -29,21 +29,36 @@ __global__ void __launch_bounds__(128) pack_kernel(const uint8_t *__restrict__ s
   if (i < n) {
     int32_t row = rows ? rows[i] : i;
     int32_t m = len[row];
-    bool bad = m < 1 || m > 64 || m > stride;
+    const uint8_t *s = seq + (size_t)row * stride;
+    bool bad = m < 0 || m > stride;
+    // The reference treats barcodes as opaque strings (src/pacybara_precluster.py:28-39).  One that does not fit the
+    // 2-bit planes -- a character outside ACGT, more than 64 bases, or none -- is kept as such: its planes hold a
+    // 128-bit hash of its bytes and its packed length the marker PCB_LEN_OPAQUE, so that it buckets with its exact
+    // copies and nothing else, and the pair search leaves it alone.
+    bool opaque = !bad && other == nullptr && (m < 1 || m > 64);
+    if (other != nullptr && (m < 1 || m > 64)) bad = true;
     uint64_t L = 0, H = 0, X = 0;
-    if (!bad) {
-      const uint8_t *s = seq + (size_t)row * stride;
+    if (!bad && !opaque) {
       for (int32_t t = 0; t < m; t++) {
         uint32_t c = base_code(s[t]);
-        if (c > 3u) { bad |= other == nullptr; X |= 1ull << t; c = 0u; }
+        if (c > 3u) { if (other == nullptr) { opaque = true; break; } X |= 1ull << t; c = 0u; }
         L |= (uint64_t)(c & 1u) << t;
         H |= (uint64_t)((c >> 1) & 1u) << t;
       }
     }
+    if (opaque) {
+      uint64_t h1 = 0x9E3779B97F4A7C15ull ^ (uint64_t)m, h2 = 0xC2B2AE3D27D4EB4Full + (uint64_t)m;
+      for (int32_t t = 0; t < m; t++) {
+        h1 = (h1 ^ s[t]) * 0x100000001B3ull; h1 ^= h1 >> 29;
+        h2 = (h2 + s[t]) * 0xD6E8FEB86659FD93ull; h2 ^= h2 >> 32;
+      }
+      L = h1; H = h2;
+    }
     planes[i] = make_ulonglong2(L, H);
     if (other) other[i] = X;
-    out_len[i] = m;
+    out_len[i] = opaque ? PCB_LEN_OPAQUE : m;
     if (bad) atomicMin((uint32_t *)&flags[0], (uint32_t)i + 1u);
+    else if (opaque) atomicAdd(&flags[3], 1);
     else atomicAdd(&sh_hist[m], 1u);
   }
   __syncthreads();
@@ -71,9 +86,10 @@ void pack_launch(pcb_ctx *ctx, const uint8_t *seq, const int32_t *len, const int
 void pack_finish(PackedBarcodes &out, const int32_t *h, bool allow_other) {
   if (h[0] != -1)
     throw Error(PCB_E_INPUT, "barcode " + std::to_string((uint32_t)h[0] - 1u) +
-                                 (allow_other ? " is not 1..64 characters long" : " is not 1..64 bases over ACGT (no side path exists for such barcodes)"));
-  out.min_len = out.n ? h[1] : 0;
-  out.max_len = out.n ? h[2] : 0;
+                                 (allow_other ? " is not 1..64 characters long" : " has a negative length or is longer than the rows of the matrix"));
+  out.max_len = out.n ? h[2] : 0;                      // over the barcodes that fit the planes; 0 if none does
+  out.min_len = out.max_len ? h[1] : 0;
+  out.n_opaque = h[3];
   for (int m = 0; m < 66; m++) out.len_hist[m] = (uint32_t)h[4 + m];
   out.has_hist = true;
 }
@@ -239,23 +255,29 @@ __global__ void bucket_qsum_kernel(const uint8_t *__restrict__ qual, const int32
 // counters (number of buckets, buckets left for the block / radix orderings) -- stays in st until bucket_finish().
 void bucket_launch(pcb_ctx *ctx, const uint8_t *seq, const int32_t *len, int32_t R, int32_t stride, const BucketOut &out,
                    PackedBarcodes *unique_out, BucketPending &st) {
+  HostTrace tr(ctx, "bucket_launch");
   st.R = R;
   pack_launch(ctx, seq, len, nullptr, R, stride, st.pk, false, st.flags);
   uint32_t cap = 64;
   while (cap < 2u * (uint32_t)R) cap <<= 1;
+  tr.lap("pack");
   DevBuf<BucketSlot> slot(ctx, cap);
   DevBuf<int32_t> slot_of_read(ctx, R);
   DevBuf<uint32_t> rank(ctx, (size_t)R + 1), bucket_cnt(ctx, (size_t)R + 2), cursor(ctx, (size_t)R + 1);
   st.counters.alloc(ctx, 4); st.mid.alloc(ctx, (size_t)R / ORDER_THREAD + 1); st.big.alloc(ctx, (size_t)R / ORDER_BLOCK + 1);
+  tr.lap("allocs");
   PCB_CUDA(cudaMemsetAsync(slot.p, 0x7F, (size_t)cap * sizeof(BucketSlot), ctx->stream));
   PCB_CUDA(cudaMemsetAsync(rank.p, 0, ((size_t)R + 1) * sizeof(uint32_t), ctx->stream));
   PCB_CUDA(cudaMemsetAsync(bucket_cnt.p, 0, ((size_t)R + 2) * sizeof(uint32_t), ctx->stream));
   PCB_CUDA(cudaMemsetAsync(cursor.p, 0, ((size_t)R + 1) * sizeof(uint32_t), ctx->stream));
   PCB_CUDA(cudaMemsetAsync(st.counters.p, 0, 4 * sizeof(int32_t), ctx->stream));
+  tr.lap("memsets");
   PCB_LAUNCH(ctx, bucket_insert_kernel, grid_for(R, 256), 256, 0, st.pk.planes.p, st.pk.len.p, R, slot.p, cap - 1, slot_of_read.p);
   PCB_LAUNCH(ctx, bucket_flag_first_kernel, grid_for(cap, 256), 256, 0, slot.p, cap, rank.p);
   exclusive_scan_u32(ctx, rank.p, rank.p, (size_t)R + 1);               // rank[R] = U
+  tr.lap("insert..scan");
   if (unique_out) { unique_out->planes.alloc(ctx, (size_t)R); unique_out->len.alloc(ctx, (size_t)R); }
+  tr.lap("unique allocs");
   PCB_LAUNCH(ctx, bucket_number_kernel, grid_for(cap, 256), 256, 0, slot.p, cap, rank.p, st.pk.planes.p, st.pk.len.p, bucket_cnt.p,
              unique_out ? unique_out->planes.p : nullptr, unique_out ? unique_out->len.p : nullptr);
   exclusive_scan_u32(ctx, bucket_cnt.p, (uint32_t *)out.bucket_ptr, (size_t)R + 1);      // entries past U all hold R
@@ -264,8 +286,10 @@ void bucket_launch(pcb_ctx *ctx, const uint8_t *seq, const int32_t *len, int32_t
   PCB_LAUNCH(ctx, bucket_order_kernel, grid_for(R, 128), 128, 0, rank.p, R, out.bucket_ptr, out.bucket_reads, st.counters.p, st.mid.p,
              st.big.p);
   PCB_LAUNCH(ctx, bucket_order_mid_kernel, (unsigned)ctx->sm_count, 256, 0, out.bucket_ptr, out.bucket_reads, st.counters.p, st.mid.p);
+  tr.lap("number..order");
   PCB_CUDA(cudaMemcpyAsync(st.h_flags, st.flags.p, sizeof(st.h_flags), cudaMemcpyDeviceToHost, ctx->stream));
   PCB_CUDA(cudaMemcpyAsync(st.h_counters, st.counters.p, sizeof(st.h_counters), cudaMemcpyDeviceToHost, ctx->stream));
+  tr.lap("d2h");
 }
 
 // After the stream has been synchronised: input errors, U, and the (rare) buckets of more than 4096 reads, whose

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <chrono>
+#include <cstdio>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -35,6 +37,10 @@ struct pcb_edges {
 
 struct pcb_text;     // a text file on the device (ingest.cu)
 
+// packed length of a barcode that does not fit the 2-bit planes (non-ACGT character, more than 64 bases, empty): it is
+// bucketed by the exact bytes (planes = 128-bit hash) and takes no part in the pair search
+#define PCB_LEN_OPAQUE 127
+
 struct pcb_ctx {
   int device = 0;
   int sm_count = 148;
@@ -49,6 +55,7 @@ struct pcb_ctx {
   int64_t stats[PCB_STAT_COUNT] = {0};
   int replay_shape = PCB_REPLAY_AUTO;      // pcb_set_option(PCB_OPT_REPLAY_SHAPE)
   bool medium_attr_set = false;            // the medium replay kernel's shared-memory opt-in (merge.cu)
+  int trace = 0;                           // pcb_set_option(PCB_OPT_TRACE): host-side lap times on stderr
   pcb_edges edges;
 };
 
@@ -81,6 +88,19 @@ struct DevBuf {
   T *detach() { T *q = p; p = nullptr; n = 0; return q; }
   ~DevBuf() { release(); }
   operator T *() const { return p; }
+};
+
+// development aid (PCB_OPT_TRACE): where the HOST spends its time inside a stage
+struct HostTrace {
+  pcb_ctx *ctx; const char *what;
+  std::chrono::steady_clock::time_point t;
+  HostTrace(pcb_ctx *c, const char *w) : ctx(c), what(w), t(std::chrono::steady_clock::now()) {}
+  void lap(const char *name) {
+    if (!ctx->trace) return;
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[pcb trace] %s / %s: %.3f ms\n", what, name, std::chrono::duration<double, std::milli>(now - t).count());
+    t = now;
+  }
 };
 
 inline unsigned grid_for(size_t n, unsigned block) {
@@ -145,7 +165,8 @@ struct PackedBarcodes {      // planes of n barcodes: x = plane L (bit 0 of each
   DevBuf<ulonglong2> planes;
   DevBuf<int32_t> len;
   DevBuf<uint64_t> other;    // optional: positions holding a character that is no base (f3 queries); planes are 0 there
-  int32_t n = 0, min_len = 0, max_len = 0;
+  int32_t n = 0, min_len = 0, max_len = 0;   // lengths over the barcodes that fit the planes (len <= 64)
+  int32_t n_opaque = 0;                      // barcodes kept as opaque strings (len == PCB_LEN_OPAQUE, planes = hash)
   uint32_t len_hist[66] = {0};   // barcodes per length, when the packing counted them (has_hist)
   bool has_hist = false;
 };

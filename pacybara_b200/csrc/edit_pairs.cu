@@ -27,6 +27,7 @@ __global__ void seed_count_kernel(const ulonglong2 *__restrict__ planes, const i
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)U * g.npos) return;
   int32_t j = t_begin + (int32_t)(i / g.npos), p = (int32_t)(i % g.npos);
+  if (len[j] > 64) return;                       // an opaque barcode: not a target
   if (g.q > 0 && (p + g.q > len[j] || !((g.pos_mask >> p) & 1ull))) return;
   ulonglong2 pl = planes[j];
   atomicAdd(&bin_cnt[seed_bin(g, pl.x, pl.y, p, p)], 1u);
@@ -37,10 +38,26 @@ __global__ void seed_fill_kernel(const ulonglong2 *__restrict__ planes, const in
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)U * g.npos) return;
   int32_t j = t_begin + (int32_t)(i / g.npos), p = (int32_t)(i % g.npos);
+  if (len[j] > 64) return;
   if (g.q > 0 && (p + g.q > len[j] || !((g.pos_mask >> p) & 1ull))) return;
   ulonglong2 pl = planes[j];
   uint32_t at = atomicAdd(&cursor[seed_bin(g, pl.x, pl.y, p, p)], 1u);
   ent[at] = j;
+}
+
+// the same with (target, sketch) entries: the index of the lane-per-pair probe (probe.cuh)
+__global__ void seed_fill8_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int32_t t_begin, int32_t U,
+                                  SeedGeom g, uint32_t *__restrict__ cursor, SeedEnt *__restrict__ ent) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)U * g.npos) return;
+  int32_t j = t_begin + (int32_t)(i / g.npos), p = (int32_t)(i % g.npos);
+  if (len[j] > 64) return;
+  if (g.q > 0 && (p + g.q > len[j] || !((g.pos_mask >> p) & 1ull))) return;
+  ulonglong2 pl = planes[j];
+  uint32_t at = atomicAdd(&cursor[seed_bin(g, pl.x, pl.y, p, p)], 1u);
+  SeedEnt e;
+  e.j = j; e.sk = barcode_sketch((uint32_t)pl.x, (uint32_t)pl.y, len[j]);
+  ent[at] = e;
 }
 
 // Device-side Myers for one-word barcodes, tuned for the ALU/FMA pipe split of sm_100a: the text
@@ -196,7 +213,7 @@ __global__ void len_hist_kernel(const int32_t *__restrict__ len, int32_t U, uint
   if (threadIdx.x < 66) sh[threadIdx.x] = 0;
   __syncthreads();
   for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < U; i += gridDim.x * blockDim.x)
-    atomicAdd(&sh[len[i]], 1u);                   // lengths were validated to 1..64 when packing
+    if (len[i] <= 64) atomicAdd(&sh[len[i]], 1u);   // (opaque barcodes carry the marker length and are not counted)
   __syncthreads();
   if (threadIdx.x < 66 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
@@ -280,6 +297,7 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
   pcb_edges &res = ctx->edges;
   res.valid = true;
   if (U < (self ? 2 : 1) || q_begin == q_end || T == 0) return;
+  if (bc.max_len == 0 || qs.max_len == 0) return;           // nothing but opaque barcodes
 
   // ---- seed lengths.  A query of length m splits into k+1 pieces of at least floor(m/(k+1)) bases, so it can
   // probe an index of q-grams with q up to that.  Most barcodes share one length; the few shorter ones (deletions)
@@ -321,7 +339,8 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
         }
     return mask;
   };
-  struct SeedIndex { SeedGeom g; DevBuf<uint32_t> bin_off; DevBuf<int32_t> ent; int32_t len_lo, len_hi; };
+  struct SeedIndex { SeedGeom g; DevBuf<uint32_t> bin_off; DevBuf<int32_t> ent; DevBuf<SeedEnt> ent8; int32_t len_lo, len_hi; };
+  const bool lanes = self && !(bc.max_len > 32);          // the clustering path on one-word barcodes: probe.cuh
   SeedIndex idx[2];
   int n_idx = 1;
   idx[0].g = make_geom(mode_len / (k + 1));
@@ -339,13 +358,14 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
     const SeedGeom &g = idx[t].g;
     DevBuf<uint32_t> cursor(ctx, (size_t)g.nbins + 1);
     idx[t].bin_off.alloc(ctx, (size_t)g.nbins + 1);
-    idx[t].ent.alloc(ctx, (size_t)T * g.npos);
+    if (lanes) idx[t].ent8.alloc(ctx, (size_t)T * g.npos); else idx[t].ent.alloc(ctx, (size_t)T * g.npos);
     PCB_CUDA(cudaMemsetAsync(idx[t].bin_off.p, 0, ((size_t)g.nbins + 1) * sizeof(uint32_t), ctx->stream));
     size_t n_slots = (size_t)T * g.npos;
     PCB_LAUNCH(ctx, seed_count_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, t_begin, T, g, idx[t].bin_off.p);
     exclusive_scan_u32(ctx, idx[t].bin_off.p, idx[t].bin_off.p, (size_t)g.nbins + 1);
     PCB_CUDA(cudaMemcpyAsync(cursor.p, idx[t].bin_off.p, ((size_t)g.nbins + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
-    PCB_LAUNCH(ctx, seed_fill_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, t_begin, T, g, cursor.p, idx[t].ent.p);
+    if (lanes) PCB_LAUNCH(ctx, seed_fill8_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, t_begin, T, g, cursor.p, idx[t].ent8.p);
+    else PCB_LAUNCH(ctx, seed_fill_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, t_begin, T, g, cursor.p, idx[t].ent.p);
   }
 
   stage_end(ctx, PCB_STAT_T_INDEX_NS);
@@ -353,7 +373,6 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
   const int key_shift = bits_for((uint64_t)(U > 1 ? U - 1 : 1));
   unsigned long long cap = 8ull * (unsigned long long)(q_end - q_begin) + (1ull << 16);
   DevBuf<unsigned long long> counters(ctx, 6);
-  const bool lanes = self && !(bc.max_len > 32);          // the clustering path on one-word barcodes: probe.cuh
   DevBuf<uint32_t> sketch;
   if (lanes) {
     sketch.alloc(ctx, (size_t)U);
@@ -383,7 +402,7 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
       if (lanes) {
         ProbeArgs a;
         a.planes = (const Planes16 *)bc.planes.p; a.len = bc.len.p; a.sketch = sketch.p; a.q_begin = q_begin; a.q_end = q_end; a.g = g;
-        a.bin_off = idx[t].bin_off.p; a.ent = idx[t].ent.p; a.hit_key = hk0.p; a.hit_d = hv0.p; a.cap = cap; a.key_shift = key_shift;
+        a.bin_off = idx[t].bin_off.p; a.ent = idx[t].ent8.p; a.hit_key = hk0.p; a.hit_d = hv0.p; a.cap = cap; a.key_shift = key_shift;
         a.counters = counters.p; a.len_lo = idx[t].len_lo; a.len_hi = idx[t].len_hi;
         PCB_LAUNCH(ctx, probe_kernel_lanes, n_cta, PROBE_WARPS * 32, 0, a);
       }

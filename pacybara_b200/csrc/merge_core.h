@@ -217,6 +217,7 @@ inline
 #endif
 int32_t on_demand_dist(const uint64_t *planes, const int32_t *blen, int32_t compute_k, int32_t wide, int32_t a, int32_t b) {
   int32_t m = blen[a], n = blen[b];
+  if (m > 64 || n > 64) return -1;               // an opaque barcode (csrc/common.cuh: PCB_LEN_OPAQUE) is near nothing
   int32_t dl = m > n ? m - n : n - m;
   if (dl > compute_k) return -1;
   int32_t d = wide ? myers64(planes[2 * a], planes[2 * a + 1], m, planes[2 * b], planes[2 * b + 1], n)

@@ -6,8 +6,8 @@
 //              pair's query side (every unordered pair has exactly one), the lengths differ by at most k, and the
 //              base-composition bound holds: an edit changes the count of at most two bases by one each, so
 //              dist >= max(surplus, deficit) of the four base counts (two popc-built 4-byte vectors, two SIMD
-//              subtractions on a 4-byte sketch of the target -- the one thing a candidate costs in memory).  Survivors
-//              go to a per-warp queue.
+//              subtractions on a 4-byte sketch of the target that sits in the index entry itself, so a candidate
+//              costs 8 streamed bytes and no gather).  Survivors go to a per-warp queue.
 //   scoring    a lane that has no pair pops one from the queue; all lanes then advance THEIR pair by a few text
 //              columns; at the checkpoint a finished pair emits its hit and a pair whose cell on the final diagonal
 //              already exceeds k is dropped (D[m][n] >= D[j + m - n][j], Ukkonen's cut-off) -- either way the lane is
@@ -38,14 +38,16 @@ PCB_HD uint32_t seed_bin(const SeedGeom g, uint64_t L, uint64_t H, int src_pos, 
   return ((uint32_t)bin_pos << (2 * g.q)) | qgram_key(L, H, src_pos, g.q);
 }
 
+struct alignas(8) SeedEnt { int32_t j; uint32_t sk; };      // an index entry: the target and its sketch (so the filters need no gather)
+
 struct ProbeArgs {
   const Planes16 *planes;          // the barcodes (queries and targets are the same set)
   const int32_t *len;
-  const uint32_t *sketch;          // per barcode: length << 24 | #T << 16 | #G << 8 | #C -- all the filters read (one sector)
+  const uint32_t *sketch;          // per barcode: length << 24 | #T << 16 | #G << 8 | #C -- all the filters read
   int32_t q_begin, q_end;          // this call's queries
   SeedGeom g;
   const uint32_t *bin_off;
-  const int32_t *ent;
+  const SeedEnt *ent;              // the bins: (target, its sketch), streamed
   uint64_t *hit_key;
   uint32_t *hit_d;
   unsigned long long cap;
@@ -133,11 +135,12 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu) {
       if (mode == 1) {
         if (simt::ballot(FULL, lo < hi) == 0u) { mode = 0; continue; }
         if (lo < hi) {
-          j = simt::ld_stream(&a.ent[lo++]);
+          const SeedEnt en = a.ent[lo++];
+          j = en.j;
           n_walked++;
           if (j != qi && is_query_side(qi, j)) {
             n_sided++;
-            const uint32_t sk = a.sketch[j];
+            const uint32_t sk = en.sk;
             const int32_t dl = qm - (int32_t)(sk >> 24);
             if (dl <= k && -dl <= k) {
               const uint32_t tc = sketch_counts(sk);
@@ -159,11 +162,12 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu) {
         }
         const uint32_t e = c_at + (uint32_t)lane;
         if (e < c_hi) {
-          j = simt::ld_stream(&a.ent[e]);
+          const SeedEnt en = simt::ld_stream(&a.ent[e]);
+          j = en.j;
           n_walked++;
           if (j != c_qi && is_query_side(c_qi, j)) {
             n_sided++;
-            const uint32_t sk = a.sketch[j];
+            const uint32_t sk = en.sk;
             const int32_t dl = c_qm - (int32_t)(sk >> 24);
             if (dl <= k && -dl <= k) {
               const uint32_t tc = sketch_counts(sk);

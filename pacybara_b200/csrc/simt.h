@@ -8,6 +8,7 @@
 // __syncwarp shows up as a failing test rather than as a rare flake on the device.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define SIMT_FN __device__ __forceinline__
@@ -29,7 +30,15 @@ SIMT_FN int popc(uint32_t x) { return __popc(x); }
 SIMT_FN int ffs(uint32_t x) { return __ffs((int)x); }      // 1-based, 0 when x == 0
 SIMT_FN float sqrt_f(float x) { return sqrtf(x); }
 SIMT_FN uint32_t brev(uint32_t x) { return __brev(x); }
-SIMT_FN int32_t ld_stream(const int32_t *p) { return __ldcs(p); }      // read once: do not keep it in the caches
+// read once: do not keep it in the caches (8-byte items)
+template <typename T>
+SIMT_FN T ld_stream(const T *p) {
+  static_assert(sizeof(T) == 8, "8-byte items");
+  const longlong1 v = {__ldcs((const long long *)p)};
+  T out;
+  memcpy(&out, &v, 8);
+  return out;
+}
 SIMT_FN unsigned long long atomic_add_u64(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
 // sum over the four bytes of max(0, a_byte - b_byte)
 SIMT_FN uint32_t surplus4(uint32_t a, uint32_t b) { return __vsadu4(__vsubus4(a, b), 0u); }
@@ -57,7 +66,7 @@ inline int64_t atomic_add64(int64_t *p, int64_t v) { int64_t o = *p; *p = o + v;
 inline int popc(uint32_t x) { return __builtin_popcount(x); }
 inline int ffs(uint32_t x) { return __builtin_ffs((int)x); }
 inline float sqrt_f(float x) { return sqrtf(x); }
-inline int32_t ld_stream(const int32_t *p) { return *p; }
+template <typename T> inline T ld_stream(const T *p) { return *p; }
 inline uint32_t brev(uint32_t x) { uint32_t r = 0; for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i); return r; }
 inline unsigned long long atomic_add_u64(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
 inline uint32_t surplus4(uint32_t a, uint32_t b) {

@@ -25,7 +25,7 @@ import numpy as np
 
 from .canon import mut_sort_key
 
-MAX_BARCODE = 64          # 2-bit planes in at most two 64-bit words
+MAX_BARCODE = 64          # 2-bit planes in at most two 64-bit words; longer barcodes are kept as opaque strings
 _RID = re.compile(r"@([^ ]+)")
 
 

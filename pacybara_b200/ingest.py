@@ -121,8 +121,8 @@ def arrays_from_bytes(ctx: Context, fastq: bytes, geno: bytes, uptag: Optional[b
         rec = fq.fastq_records()
         if rec["n_bad"]:
             decline("barcode FASTQ records the tokenizer does not model", rec["n_bad"])
-        if rec["max_len"] > hostdata.MAX_BARCODE:
-            raise hostdata.FormatError(f"barcode of length {rec['max_len']} exceeds {hostdata.MAX_BARCODE}")
+        if rec["max_len"] > 4 * hostdata.MAX_BARCODE:
+            decline("a barcode too long for the tokenizer's matrices", rec["max_len"])
         stride = max(4, (rec["max_len"] + 3) // 4 * 4)
         f = fq.fastq_fetch(stride)
         R = rec["n_records"]

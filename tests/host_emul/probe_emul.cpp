@@ -31,8 +31,12 @@ extern "C" int64_t emul_probe(const uint64_t *planes, const int32_t *len, int32_
       items.push_back({seed_bin(g, planes[2 * j], planes[2 * j + 1], p, p), j});
     }
   std::stable_sort(items.begin(), items.end(), [](auto &x, auto &y) { return x.first < y.first; });
-  std::vector<int32_t> ent(items.size() + 1);
-  for (size_t i = 0; i < items.size(); i++) { bin_off[items[i].first + 1]++; ent[i] = items[i].second; }
+  std::vector<SeedEnt> ent(items.size() + 1);
+  for (size_t i = 0; i < items.size(); i++) {
+    const int32_t j = items[i].second;
+    bin_off[items[i].first + 1]++;
+    ent[i].j = j; ent[i].sk = barcode_sketch((uint32_t)planes[2 * j], (uint32_t)planes[2 * j + 1], len[j]);
+  }
   for (uint32_t b = 0; b < g.nbins; b++) bin_off[b + 1] += bin_off[b];
   unsigned long long hit_cap = 64ull * (unsigned long long)U * (unsigned long long)U + 4096;      // a pair can be found through every piece and shift
   if (hit_cap > (1ull << 24)) hit_cap = 1ull << 24;

@@ -69,15 +69,37 @@ def test_bucket_edge_shapes(ctx):
     assert r["bucket_of_read"].tolist() == [0, 1, 0, 2, 1]
 
 
-def test_bad_input_is_refused(ctx):
+def test_barcodes_that_do_not_fit_the_planes_are_kept_as_opaque_strings(ctx):
+    """The reference treats barcodes as opaque strings: an N, a 70-nt insertion call or an empty barcode must not abort
+    the library.  They bucket with their exact copies, in first-seen order like everything else, and the pair search
+    leaves them alone."""
     from pacybara_b200._lib import PcbError, PCB_E_INPUT
-    bad = hostdata.strings_to_matrix([b"ACGT", b"ACNT"])
+    long_ = b"ACGT" * 17 + b"AC"                                   # 70 nt
+    seqs = [b"ACGTACGTAC", b"ACNTACGTAC", long_, b"ACGTACGTAC", b"ACNTACGTAC", b"", long_, b"ACGTACGTAA", b"", long_[:-1] + b"G"]
+    mat, lens = hostdata.strings_to_matrix(seqs)
+    r = ctx.bucket(mat, np.full_like(mat, 50), lens)
+    assert r["bucket_of_read"].tolist() == [0, 1, 2, 0, 1, 3, 2, 4, 3, 5]
+    assert r["n_buckets"] == 6 and np.diff(r["bucket_ptr"]).tolist() == [2, 2, 2, 2, 1, 1]
+    assert r["bucket_reads"].tolist() == [0, 3, 1, 4, 2, 6, 5, 8, 7, 9]
+    assert r["bucket_qsum"][2, :70].tolist() == [34] * 70 and r["bucket_qsum"][3].tolist() == [0] * mat.shape[1]
+    # pairs: only among the barcodes that fit the planes (ACGTACGTAC ~ ACGTACGTAA); the N barcode is one edit from
+    # bucket 0 as a string, but it is opaque here
+    ei, ej, ed = ctx.edit_pairs(r["bucket_seq"], r["bucket_len"], 2)
+    assert list(zip(ei.tolist(), ej.tolist(), ed.tolist())) == [(0, 4, 1)]
+    # the whole path: rows for everybody
+    R = len(seqs)
+    out = ctx.cluster_reads(mat, None, lens, np.arange(R, dtype=np.int32), None, np.zeros(R + 1, dtype=np.int32), np.zeros(0, dtype=np.int32),
+                            np.zeros(0, dtype=np.int32), np.zeros(1, dtype=np.int32), max_diff=2)
+    rows = hostdata.rows_from_merge_outputs(out)
+    members = sorted(sorted(rows.row_members[rows.row_ptr[i]:rows.row_ptr[i + 1]].tolist()) for i in range(rows.n_rows))
+    assert members == [[0, 3, 7], [1, 4], [2, 6], [5, 8], [9]]          # (7: one read against two, one edit away, no calls: it joins)
+    # what is still refused: a length the matrix cannot hold
     with pytest.raises(PcbError) as e:
-        ctx.bucket(bad[0], np.full_like(bad[0], 50), bad[1])
+        ctx.bucket(mat, np.full_like(mat, 50), np.where(np.arange(R) == 4, mat.shape[1] + 1, lens).astype(np.int32))
     assert e.value.code == PCB_E_INPUT
-    too_long = hostdata.strings_to_matrix([b"A" * 65])
-    with pytest.raises(PcbError):
-        ctx.edit_pairs(too_long[0], too_long[1], 2)
+    only_opaque = hostdata.strings_to_matrix([b"NNNN", b"NNNA", b"NNNN"])
+    assert ctx.bucket(only_opaque[0], np.full_like(only_opaque[0], 40), only_opaque[1])["bucket_of_read"].tolist() == [0, 1, 0]
+    assert len(ctx.edit_pairs(only_opaque[0][:2], only_opaque[1][:2], 2)[0]) == 0
 
 
 # ----------------------------------------------------------------------------- a2+a3 distances
