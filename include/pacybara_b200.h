@@ -19,6 +19,7 @@
  *                      <- the line loops of src/pacybara_precluster.py:47-63 and
  *                         src/pacybara_cluster.py:302-331, makePID's string order :152-157      (f2)
  *   pcb_match_barcodes <- src/barseq_caller.R:57,242 (yogiseq::new.bc.matcher)                 (f3)
+ *   pcb_merge_libraries <- src/pacybara_merge.R:48-101                                         (f4)
  *
  * Conventions
  *   - every function returns 0 on success or a PCB_E_* code; pcb_last_error() gives the text;
@@ -249,6 +250,23 @@ int pcb_compact_shard(pcb_ctx *ctx, int mem_in, int mem_out, int32_t R, int64_t 
                       int32_t *n_own, int32_t *own_read, int32_t *own_root, int32_t *own_pos, int32_t *own_bucket,
                       int32_t *n_rows, int64_t *n_calls, int32_t *row_rep, int32_t *c_size, int64_t *c_key, int32_t *c_bc,
                       int32_t *c_up, int64_t *c_call_off, int32_t *c_call_n, int32_t *c_call_mut);
+
+/*
+ * f4 -- merging two cluster libraries by virtual barcode and genotype (src/pacybara_merge.R:48-101).
+ *   vbc1/geno1/size1 [n1], vbc2/geno2/size2 [n2]: per row of the first / second translated cluster table the id of its
+ *   virtualBarcode (0 .. n_ids-1, one id space for both libraries), the id of its hgvsc genotype string, and its size.
+ * outputs
+ *   klass2 [n2]     PCB_LIBMERGE_NEW (barcode not in the first library: the row is appended), PCB_LIBMERGE_MERGE (a row
+ *                   of the first library has the same barcode and genotype: sizes add up, read lists are joined) or
+ *                   PCB_LIBMERGE_CONFLICT (the barcode is there with other genotypes only: appended, a collision)
+ *   target2 [n2]    for merges the row of the first library the row goes into -- when several rows share barcode and
+ *                   genotype, the one that is largest at that moment, first of equals (which.max) -- else -1
+ *   size1_out [n1]  sizes of the first library's rows after all merges
+ */
+enum { PCB_LIBMERGE_NEW = 0, PCB_LIBMERGE_MERGE = 1, PCB_LIBMERGE_CONFLICT = 2 };
+int pcb_merge_libraries(pcb_ctx *ctx, int mem, int32_t n1, const int32_t *vbc1, const int32_t *geno1, const int32_t *size1,
+                        int32_t n2, const int32_t *vbc2, const int32_t *geno2, const int32_t *size2, int32_t n_ids,
+                        int32_t *size1_out, int32_t *target2, int32_t *klass2);
 
 /*
  * f3 -- barcode -> library matching with maxErr: what barseq_caller.R asks of

@@ -245,6 +245,24 @@ class Context:
                                           self._in(row_size, np.int32, keep), int(n_bc_ids), int(n_up_ids), float(min_ratio), *ptrs))
         return {k: v[:n] for k, v in outs.items()}
 
+    # ------------------------------------------------------------------ f4
+    def merge_libraries(self, vbc1, geno1, size1, vbc2, geno2, size2, n_ids: int) -> Dict:
+        """Rows of a second cluster library against a first one (pcb_merge_libraries): per row of the second library its
+        class (0 new, 1 merge, 2 conflict) and the row of the first it merges into; the first library's sizes afterwards."""
+        arrays = [vbc1, geno1, size1, vbc2, geno2, size2]
+        if any(_is_dev(a) for a in arrays):
+            _torch()
+        mem = self._kind(*arrays)
+        n1, n2 = int(vbc1.shape[0]), int(vbc2.shape[0])
+        keep: list = []
+        ins = [self._in(a, np.int32, keep) for a in arrays]
+        size_out, p_s = self._out(mem, (max(n1, 1),), np.int32)
+        target, p_t = self._out(mem, (max(n2, 1),), np.int32)
+        klass, p_k = self._out(mem, (max(n2, 1),), np.int32)
+        self._check(self.lib.pcb_merge_libraries(self.h, mem, n1, ins[0], ins[1], ins[2], n2, ins[3], ins[4], ins[5], int(n_ids),
+                                                 p_s, p_t, p_k))
+        return dict(size1=size_out[:n1], target2=target[:n2], klass2=klass[:n2])
+
     # ------------------------------------------------------------------ the whole path
     def cluster_reads(self, seq, qual, length, lexrank, up_id, geno_ptr, geno_mut, geno_q, mut_rank,
                       max_diff: int = 2, min_qual: int = 32, min_jaccard: float = 0.2, min_matches: int = 1,

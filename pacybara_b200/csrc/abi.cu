@@ -48,13 +48,33 @@ struct OutArr {
   }
 };
 
+// After a call that used the workspace arena: drop everything; if the call needed more than the arena holds, make it
+// that large (plus a margin) for the next one.  The stream has been synchronised: nothing is in flight.
+void arena_end(pcb_ctx *ctx) {
+  ctx->arena_on = false;
+  ctx->arena_off = 0;
+  if (ctx->arena_need > ctx->arena_cap) {
+    const size_t want = ctx->arena_need + ctx->arena_need / 8 + (1 << 20);
+    if (ctx->arena) cudaFree(ctx->arena);
+    ctx->arena = nullptr; ctx->arena_cap = 0;
+    cudaMemPool_t pool;                                         // what the pool served this call is the arena's job from now on
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    if (cudaMalloc((void **)&ctx->arena, want) == cudaSuccess) ctx->arena_cap = want;
+    else { ctx->arena = nullptr; cudaGetLastError(); }          // no room for it: the stream-ordered pool keeps serving
+  }
+}
+
+// arena: the call's temporaries come from the context's workspace arena (not for calls that leave device objects behind)
 template <typename F>
-int guarded(pcb_ctx *ctx, F f) {
+int guarded(pcb_ctx *ctx, F f, bool arena = true) {
   if (!ctx) return PCB_E_STATE;
   try {
     PCB_CUDA(cudaSetDevice(ctx->device));
+    ctx->arena_on = arena; ctx->arena_off = 0; ctx->arena_need = 0;
     f();
     PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+    PCB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+    arena_end(ctx);
     ctx->err.clear();
     return PCB_OK;
   } catch (const Error &e) {
@@ -62,11 +82,13 @@ int guarded(pcb_ctx *ctx, F f) {
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->stream);
     cudaGetLastError();
+    arena_end(ctx);
     return e.code;
   } catch (const std::exception &e) {
     ctx->err = e.what();
     cudaStreamSynchronize(ctx->copy_stream);
     cudaStreamSynchronize(ctx->stream);
+    arena_end(ctx);
     return PCB_E_CUDA;
   }
 }
@@ -208,6 +230,7 @@ void pcb_ctx_destroy(pcb_ctx *ctx) {
   if (ctx->ev_alloc) cudaEventDestroy(ctx->ev_alloc);
   if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -511,6 +534,21 @@ int pcb_tag_rows(pcb_ctx *ctx, int mem, int32_t n_rows, const int32_t *row_bc, c
   });
 }
 
+int pcb_merge_libraries(pcb_ctx *ctx, int mem, int32_t n1, const int32_t *vbc1, const int32_t *geno1, const int32_t *size1,
+                        int32_t n2, const int32_t *vbc2, const int32_t *geno2, const int32_t *size2, int32_t n_ids,
+                        int32_t *size1_out, int32_t *target2, int32_t *klass2) {
+  return guarded(ctx, [&] {
+    if (n1 < 0 || n2 < 0 || n_ids < 0) throw Error(PCB_E_INPUT, "bad shape");
+    InArr<int32_t> d_v1(ctx, mem, vbc1, n1), d_g1(ctx, mem, geno1, n1), d_s1(ctx, mem, size1, n1), d_v2(ctx, mem, vbc2, n2),
+        d_g2(ctx, mem, geno2, n2), d_s2(ctx, mem, size2, n2);
+    OutArr<int32_t> o_s(ctx, mem, size1_out, n1), o_t(ctx, mem, target2, n2), o_k(ctx, mem, klass2, n2);
+    if ((n1 > 0 && !o_s.p) || (n2 > 0 && (!o_t.p || !o_k.p))) throw Error(PCB_E_INPUT, "all three outputs are required");
+    merge_libraries_dev(ctx, n1, d_v1.p, d_g1.p, d_s1.p, n2, d_v2.p, d_g2.p, d_s2.p, n_ids, o_s.p, o_t.p, o_k.p);
+    o_s.commit(n1); o_t.commit(n2); o_k.commit(n2);
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
 // ---- f2: tokenizers (ingest.cu)
 
 int pcb_text_open(pcb_ctx *ctx, int mem, const uint8_t *bytes, int64_t n_bytes, pcb_text **out, int64_t *n_lines, int64_t *n_exotic) {
@@ -529,7 +567,7 @@ int pcb_text_open(pcb_ctx *ctx, int mem, const uint8_t *bytes, int64_t n_bytes, 
     if (n_lines) *n_lines = nl;
     if (n_exotic) *n_exotic = exotic;
     *out = x;
-  });
+  }, false);       // text handles outlive the call: no workspace arena
 }
 
 void pcb_text_close(pcb_ctx *ctx, pcb_text *text) {
@@ -547,7 +585,7 @@ int pcb_fastq_records(pcb_ctx *ctx, pcb_text *fastq, int32_t *n_records, int32_t
     if (max_len) *max_len = ml;
     if (max_id_len) *max_id_len = mi;
     if (n_bad) *n_bad = bad;
-  });
+  }, false);       // text handles outlive the call: no workspace arena
 }
 
 int pcb_fastq_fetch(pcb_ctx *ctx, pcb_text *fastq, int mem, int32_t stride, uint8_t *seq, uint8_t *qual, int32_t *length,
@@ -566,7 +604,7 @@ int pcb_fastq_fetch(pcb_ctx *ctx, pcb_text *fastq, int mem, int32_t stride, uint
     fastq_fetch_dev(ctx, fastq, stride, o_seq.p, o_qual.p, o_len.p, o_ido.p, o_idl.p);
     o_seq.commit(cells); o_qual.commit(cells); o_len.commit(R); o_idl.commit(R); o_ido.commit(R);
     PCB_CUDA(cudaStreamSynchronize(ctx->stream));
-  });
+  }, false);       // text handles outlive the call: no workspace arena
 }
 
 int pcb_rank_strings(pcb_ctx *ctx, const pcb_text *text, int mem, const int64_t *off, const int32_t *len, int32_t n, int32_t max_len,
@@ -579,7 +617,7 @@ int pcb_rank_strings(pcb_ctx *ctx, const pcb_text *text, int mem, const int64_t 
     rank_strings_dev(ctx, text, d_off.p, d_len.p, n, max_len, o_rank.p);
     o_rank.commit(n);
     PCB_CUDA(cudaStreamSynchronize(ctx->stream));
-  });
+  }, false);       // text handles outlive the call: no workspace arena
 }
 
 int pcb_geno_join(pcb_ctx *ctx, pcb_text *geno, const pcb_text *fastq, int mem, const int64_t *id_off, const int32_t *id_len, int32_t R,
@@ -592,7 +630,7 @@ int pcb_geno_join(pcb_ctx *ctx, pcb_text *geno, const pcb_text *fastq, int mem, 
     geno_join_dev(ctx, geno, fastq, d_off.p, d_len.p, R, &z, &m, counters);
     if (nnz) *nnz = z;
     if (n_mut) *n_mut = m;
-  });
+  }, false);       // text handles outlive the call: no workspace arena
 }
 
 int pcb_geno_fetch(pcb_ctx *ctx, pcb_text *geno, int mem, int32_t *geno_ptr, int32_t *geno_mut, int32_t *geno_q, int64_t *mut_off,
@@ -608,7 +646,7 @@ int pcb_geno_fetch(pcb_ctx *ctx, pcb_text *geno, int mem, int32_t *geno_ptr, int
     geno_fetch_dev(ctx, geno, o_ptr.p, o_mut.p, o_q.p, o_mo.p, o_ml.p);
     o_ptr.commit((size_t)R + 1); o_mut.commit(nnz); o_q.commit(nnz); o_ml.commit(M); o_mo.commit(M);
     PCB_CUDA(cudaStreamSynchronize(ctx->stream));
-  });
+  }, false);       // text handles outlive the call: no workspace arena
 }
 
 int pcb_uptag_join(pcb_ctx *ctx, pcb_text *uptag, const pcb_text *fastq, int mem, const int64_t *id_off, const int32_t *id_len,
@@ -621,7 +659,7 @@ int pcb_uptag_join(pcb_ctx *ctx, pcb_text *uptag, const pcb_text *fastq, int mem
     uptag_join_dev(ctx, uptag, fastq, d_off.p, d_len.p, R, &nr, &nt, counters);
     if (n_records) *n_records = nr;
     if (n_tags) *n_tags = nt;
-  });
+  }, false);       // text handles outlive the call: no workspace arena
 }
 
 int pcb_uptag_fetch(pcb_ctx *ctx, pcb_text *uptag, int mem, int32_t *up_id, int64_t *tag_off, int32_t *tag_len) {
@@ -636,7 +674,7 @@ int pcb_uptag_fetch(pcb_ctx *ctx, pcb_text *uptag, int mem, int32_t *up_id, int6
     uptag_fetch_dev(ctx, uptag, o_up.p, o_to.p, o_tl.p);
     o_up.commit(R); o_tl.commit(M); o_to.commit(M);
     PCB_CUDA(cudaStreamSynchronize(ctx->stream));
-  });
+  }, false);       // text handles outlive the call: no workspace arena
 }
 
 }  // extern "C"

@@ -56,6 +56,13 @@ struct pcb_ctx {
   int replay_shape = PCB_REPLAY_AUTO;      // pcb_set_option(PCB_OPT_REPLAY_SHAPE)
   bool medium_attr_set = false;            // the medium replay kernel's shared-memory opt-in (merge.cu)
   int trace = 0;                           // pcb_set_option(PCB_OPT_TRACE): host-side lap times on stderr
+  // Workspace arena: the temporaries of one call are carved out of one long-lived allocation with a bump pointer and
+  // all dropped when the call returns.  The stream-ordered pool is fast on average, but its occasional slow paths
+  // (a block that has to be split, remapped or grown: 10..50 ms for the 0.5 GB buffers of a 2*10^7-read call, seen in
+  // profiles/r02f) sit on the critical path of a step; the arena has none once it has seen the largest call.
+  char *arena = nullptr;
+  size_t arena_cap = 0, arena_off = 0, arena_need = 0;
+  bool arena_on = false;
   pcb_edges edges;
 };
 
@@ -68,22 +75,35 @@ struct DevBuf {
   T *p = nullptr;
   size_t n = 0;
   cudaStream_t s = nullptr;
+  bool in_arena = false;
   DevBuf() {}
   DevBuf(pcb_ctx *ctx, size_t count) { alloc(ctx, count); }
   DevBuf(const DevBuf &) = delete;
   DevBuf &operator=(const DevBuf &) = delete;
-  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+  DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), s(o.s), in_arena(o.in_arena) { o.p = nullptr; o.n = 0; }
   DevBuf &operator=(DevBuf &&o) noexcept {
-    if (this != &o) { release(); p = o.p; n = o.n; s = o.s; o.p = nullptr; o.n = 0; }
+    if (this != &o) { release(); p = o.p; n = o.n; s = o.s; in_arena = o.in_arena; o.p = nullptr; o.n = 0; }
     return *this;
   }
   void alloc(pcb_ctx *ctx, size_t count) {
     release();
     s = ctx->stream; n = count;
-    PCB_CUDA(cudaMallocAsync((void **)&p, (count ? count : 1) * sizeof(T), s));
+    const size_t bytes = (((count ? count : 1) * sizeof(T)) + 255) & ~(size_t)255;
+    if (ctx->arena_on) {
+      ctx->arena_need += bytes;
+      if (ctx->arena_off + bytes <= ctx->arena_cap) {
+        p = (T *)(ctx->arena + ctx->arena_off);
+        ctx->arena_off += bytes;
+        in_arena = true;
+        return;
+      }
+    }
+    in_arena = false;
+    PCB_CUDA(cudaMallocAsync((void **)&p, bytes, s));
   }
   void release() {
-    if (p) { cudaFreeAsync(p, s); p = nullptr; n = 0; }
+    if (p && !in_arena) cudaFreeAsync(p, s);
+    p = nullptr; n = 0; in_arena = false;
   }
   T *detach() { T *q = p; p = nullptr; n = 0; return q; }
   ~DevBuf() { release(); }
@@ -227,6 +247,9 @@ struct MergeOut {            // device pointers, caller-owned
   int32_t *row_call_n, *call_mut;
 };
 void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out);
+void merge_libraries_dev(pcb_ctx *ctx, int32_t n1, const int32_t *vbc1, const int32_t *geno1, const int32_t *size1, int32_t n2,
+                         const int32_t *vbc2, const int32_t *geno2, const int32_t *size2, int32_t n_ids, int32_t *size1_out,
+                         int32_t *target2, int32_t *klass2);
 void tag_rows_dev(pcb_ctx *ctx, int32_t n_rows, const int32_t *row_bc, const int32_t *row_up, const int32_t *row_size,
                   int32_t n_bc_ids, int32_t n_up_ids, double min_ratio, uint8_t *collision, uint8_t *up_collision, uint8_t *usable);
 

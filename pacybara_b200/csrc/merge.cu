@@ -66,6 +66,8 @@ __global__ void uf_union_kernel(const int32_t *__restrict__ pq, const int32_t *_
 // counters: [0] buckets of this shard, [1] components of this shard, [2] medium list, [3] large list, [4] visiting pairs
 // of this shard, [5] components the small kernel declined, [6] declined components too big for the medium kernel
 enum { CNT_BUCKETS = 0, CNT_COMPS, CNT_MEDIUM, CNT_LARGE, CNT_VISITS, CNT_DECLINED, CNT_LATE, CNT_N };
+// status: [0] error code, [1] detail, [2] links, [3] tests (generic kernels), [4 ..] 32 slots of (links, tests) from the small kernel
+constexpr int STATUS_N = 4 + 64;
 
 // key = (not mine, label): this shard's components first, buckets of a component together in ascending order
 __global__ void comp_keys_kernel(int32_t *parent, int32_t U, int bbits, int32_t shard_rank, int32_t shard_count,
@@ -228,32 +230,29 @@ constexpr int MED_READS = 128, MED_BUCKETS = 128, MED_CALLS = 256, MED_PAIRS = 2
 
 // Components of more than 32 reads: medium if a local copy fits the medium kernel's shared memory, else large.
 // force_large: every component goes on the large list (the PCB_REPLAY_THREAD / PCB_REPLAY_WARP shapes).
+// Also: comp_calls[comp] = genotype entries of the component's reads -- the length of its call region (an upper bound of
+// its rows' calls); a scan turns the counts into the regions' offsets, so no component has to take its region from a
+// shared cursor (2*10^6 same-address atomics at the 2*10^7-read size).
 __global__ void classify_kernel(MergeCtx c, int32_t force_large, int32_t *__restrict__ counters, int32_t *__restrict__ medium,
-                                int32_t *__restrict__ large) {
+                                int32_t *__restrict__ large, int64_t *__restrict__ comp_calls) {
   const int32_t comp = blockIdx.x * blockDim.x + threadIdx.x;
-  if (comp >= counters[CNT_COMPS]) return;
+  const int32_t n_comp = counters[CNT_COMPS];
+  if (comp > n_comp) return;
+  if (comp == n_comp) { comp_calls[comp] = 0; return; }
   const int32_t b_lo = c.comp_ptr[comp], b_hi = c.comp_ptr[comp + 1];
-  int32_t reads = 0;
-  if (!force_large) {
-    for (int32_t bi = b_lo; bi < b_hi && reads <= MED_READS; bi++) {
-      const int32_t b = c.comp_buckets[bi];
-      reads += c.bucket_ptr[b + 1] - c.bucket_ptr[b];
+  int64_t reads = 0, nnz = 0;
+  for (int32_t bi = b_lo; bi < b_hi; bi++) {
+    const int32_t b = c.comp_buckets[bi];
+    reads += c.bucket_ptr[b + 1] - c.bucket_ptr[b];
+    for (int32_t x = c.bucket_ptr[b]; x < c.bucket_ptr[b + 1]; x++) {
+      const int32_t r = c.bucket_reads[x];
+      nnz += c.geno_ptr[r + 1] - c.geno_ptr[r];
     }
-    if (reads <= SMALL_READS) return;
   }
-  bool fits = !force_large && reads <= MED_READS && b_hi - b_lo <= MED_BUCKETS &&
-              c.cpair_ptr[comp + 1] - c.cpair_ptr[comp] <= MED_PAIRS;
-  if (fits) {
-    int32_t nnz = 0;
-    for (int32_t bi = b_lo; bi < b_hi && nnz <= MED_CALLS; bi++) {
-      const int32_t b = c.comp_buckets[bi];
-      for (int32_t x = c.bucket_ptr[b]; x < c.bucket_ptr[b + 1]; x++) {
-        const int32_t r = c.bucket_reads[x];
-        nnz += c.geno_ptr[r + 1] - c.geno_ptr[r];
-      }
-    }
-    fits = nnz <= MED_CALLS;
-  }
+  comp_calls[comp] = nnz;
+  if (!force_large && reads <= SMALL_READS) return;
+  const bool fits = !force_large && reads <= MED_READS && b_hi - b_lo <= MED_BUCKETS &&
+                    c.cpair_ptr[comp + 1] - c.cpair_ptr[comp] <= MED_PAIRS && nnz <= MED_CALLS;
   if (fits) medium[atomicAdd(&counters[CNT_MEDIUM], 1)] = comp;
   else large[atomicAdd(&counters[CNT_LARGE], 1)] = comp;
 }
@@ -292,14 +291,20 @@ __global__ void __launch_bounds__(SMALL_BLOCK) component_kernel_small(MergeCtx c
                                                                       int32_t *__restrict__ declined, int32_t *__restrict__ late) {
   __shared__ SmallSmem sm_all[SMALL_BLOCK / 32];
   __shared__ int32_t jthr[33];
+  __shared__ int32_t tally[2];
   if (threadIdx.x < 33) jthr[threadIdx.x] = c.prm.jthr[threadIdx.x];
+  if (threadIdx.x < 2) tally[threadIdx.x] = 0;
   __syncthreads();
   const int32_t comp = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
-  if (comp >= n_comp) return;
   const int lane = threadIdx.x & 31;
-  const int rc = process_component_small(c, comp, lane, &sm_all[threadIdx.x >> 5], jthr, MED_CALLS, MED_PAIRS);
-  if (lane == 0 && rc == 1) declined[atomicAdd(&counters[CNT_DECLINED], 1)] = comp;
-  if (lane == 0 && rc == 2) late[atomicAdd(&counters[CNT_LATE], 1)] = comp;
+  if (comp < n_comp) {
+    const int rc = process_component_small(c, comp, lane, &sm_all[threadIdx.x >> 5], jthr, tally, MED_CALLS, MED_PAIRS);
+    if (lane == 0 && rc == 1) declined[atomicAdd(&counters[CNT_DECLINED], 1)] = comp;
+    if (lane == 0 && rc == 2) late[atomicAdd(&counters[CNT_LATE], 1)] = comp;
+  }
+  __syncthreads();
+  // links / tests: one atomic per block and counter, spread over 32 slots (status[4 + 2 * slot + which])
+  if (threadIdx.x < 2 && tally[threadIdx.x]) atomicAdd(&c.status[4 + 2 * (blockIdx.x & 31) + threadIdx.x], tally[threadIdx.x]);
 }
 
 // The generic warp replay (merge_warp.cuh) on a LOCAL copy of one component: reads, calls, buckets and visiting pairs
@@ -586,8 +591,8 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
     PCB_LAUNCH(ctx, bucket_of_read_kernel, grid_for(R, 256), 256, 0, in.bucket_ptr, in.bucket_reads, R, U, bor_own.p);
     bor = bor_own.p;
   }
-  DevBuf<int32_t> status(ctx, 4), medium(ctx, (size_t)U + 1), large(ctx, (size_t)U + 1), declined(ctx, (size_t)U + 1), late(ctx, (size_t)U + 1);
-  PCB_CUDA(cudaMemsetAsync(status.p, 0, 4 * sizeof(int32_t), ctx->stream));
+  DevBuf<int32_t> status(ctx, STATUS_N), medium(ctx, (size_t)U + 1), large(ctx, (size_t)U + 1), declined(ctx, (size_t)U + 1), late(ctx, (size_t)U + 1);
+  PCB_CUDA(cudaMemsetAsync(status.p, 0, STATUS_N * sizeof(int32_t), ctx->stream));
   MergeCtx c;
   memset(&c, 0, sizeof(c));
   c.R = R; c.U = U;
@@ -616,7 +621,12 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   c.prm.maxDiff = in.max_diff; c.prm.minQual = in.min_qual; c.prm.minMatches = in.min_matches; c.prm.minJaccard = in.min_jaccard;
   jaccard_thresholds(c.prm);
   const int32_t force_large = shape != PCB_REPLAY_AUTO ? 1 : 0;
-  PCB_LAUNCH(ctx, classify_kernel, grid_for((size_t)U, 128), 128, 0, c, force_large, counters.p, medium.p, large.p);
+  DevBuf<int64_t> comp_calls(ctx, (size_t)U + 2);
+  PCB_LAUNCH(ctx, classify_kernel, grid_for((size_t)U + 1, 128), 128, 0, c, force_large, counters.p, medium.p, large.p, comp_calls.p);
+  if (!in.shard_layout) {                                  // regions in component order
+    exclusive_scan_i64(ctx, comp_calls.p, comp_calls.p, (size_t)U + 1);        // (entries past the last component are never read)
+    c.call_off = comp_calls.p;
+  }
   // every output starts as "not produced": entries of reads other shards own, the row fields of non-representative reads
   PCB_LAUNCH(ctx, init_outputs_kernel, grid_for((size_t)(R > nnz ? R : nnz) + 1, 256), 256, 0, R, nnz, out);
   int32_t h_cnt[CNT_N];                                                 // the one round trip of the preprocessing
@@ -647,7 +657,7 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   run_large(ctx, c, large.p, n_large, R, shape);
   stage_end(ctx, PCB_STAT_T_REPLAY_NS);
 
-  int32_t h_status[4], h_late = 0;
+  int32_t h_status[STATUS_N], h_late = 0;
   PCB_CUDA(cudaMemcpyAsync(h_status, status.p, sizeof(h_status), cudaMemcpyDeviceToHost, ctx->stream));
   PCB_CUDA(cudaMemcpyAsync(&h_late, counters.p + CNT_LATE, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   PCB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -657,6 +667,7 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
     PCB_CUDA(cudaStreamSynchronize(ctx->stream));
   }
   stage_end(ctx, PCB_STAT_T_SCATTER_NS);
+  for (int slot = 0; slot < 32; slot++) { h_status[2] += h_status[4 + 2 * slot]; h_status[3] += h_status[5 + 2 * slot]; }
   ctx->stats[PCB_STAT_LINKS] = h_status[2];
   ctx->stats[PCB_STAT_TESTS] = h_status[3];
   if (h_status[0] == 3)

@@ -59,7 +59,10 @@ SIMT_FN uint32_t small_hash(int32_t mut) { return ((uint32_t)mut * 0x9E3779B1u) 
 // tier), 1 = not eligible (more than 32 live mutations, huge qualities), 2 = not eligible AND more than med_calls
 // genotype entries or med_pairs rows (too big for the medium kernel's local copy as well).
 // jthr: MergeParams::jthr somewhere a lane can index cheaply (shared memory on the device).
-SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, SmallSmem *sm, const int32_t *jthr, int32_t med_calls, int32_t med_pairs) {
+// tally: two counters (links, tests) the caller sums up (shared memory per block on the device: same-address global
+// atomics from every component would serialise in L2).
+SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, SmallSmem *sm, const int32_t *jthr, int32_t *tally,
+                                    int32_t med_calls, int32_t med_pairs) {
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t lt = (1u << lane) - 1u;
   // The component's buckets are comp_buckets[b_lo .. b_hi) (ascending bucket id), bucket b's reads are
@@ -84,7 +87,6 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
   if (n > SMALL_READS) return 3;
   const bool has = lane < n;
   const int32_t minQual = c.prm.minQual, minMatches = c.prm.minMatches;
-  const double minJaccard = c.prm.minJaccard;
   const int32_t bkt = simt::popc(starts & (2u * (1u << lane) - 1u)) - 1;              // my bucket: last start <= lane
   const int32_t bsrc = has ? bkt : 0;
   const int32_t k_in_b = lane - simt::shfl(FULL, mystart, bsrc), x0_of_b = simt::shfl(FULL, myx0, bsrc);
@@ -409,8 +411,8 @@ SIMT_FN int process_component_small(const MergeCtx &c, int32_t comp, int lane, S
     }
   }
   if (lane == 0) {
-    if (n_links) simt::atomic_add(&c.status[2], n_links);
-    if (n_tests) simt::atomic_add(&c.status[3], n_tests);
+    if (n_links) simt::atomic_add(&tally[0], n_links);
+    if (n_tests) simt::atomic_add(&tally[1], n_tests);
     if (up_err_head >= 0) { c.status[0] = 3; c.status[1] = up_err_head; }
   }
 #undef PCB_LINK

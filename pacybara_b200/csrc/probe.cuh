@@ -261,9 +261,12 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu) {
       }
     }
   }
-  if (n_walked) {
-    simt::atomic_add_u64(&a.counters[1], n_started); simt::atomic_add_u64(&a.counters[2], n_cells);
-    simt::atomic_add_u64(&a.counters[4], n_walked); simt::atomic_add_u64(&a.counters[5], n_sided);
+  // one set of atomics per warp (a warp's totals fit 32 bits: it is one of ~10^4 warps of a persistent grid)
+  const uint32_t w_started = (uint32_t)simt::reduce_add(FULL, (int32_t)n_started), w_cells = (uint32_t)simt::reduce_add(FULL, (int32_t)n_cells);
+  const uint32_t w_walked = (uint32_t)simt::reduce_add(FULL, (int32_t)n_walked), w_sided = (uint32_t)simt::reduce_add(FULL, (int32_t)n_sided);
+  if (lane == 0 && w_walked) {
+    simt::atomic_add_u64(&a.counters[1], w_started); simt::atomic_add_u64(&a.counters[2], w_cells);
+    simt::atomic_add_u64(&a.counters[4], w_walked); simt::atomic_add_u64(&a.counters[5], w_sided);
   }
 }
 

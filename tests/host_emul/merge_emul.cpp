@@ -130,7 +130,7 @@ extern "C" int emul_merge(int32_t R, int32_t U, const int32_t *bucket_ptr, const
     if (label[comp_buckets[comp_ptr[comp]]] % shard_count != shard_rank) continue;
     if (use_small) {
       int rc[32];
-      simt_emul::run_warp([&](int lane) { rc[lane] = process_component_small(c, comp, lane, &smem, c.prm.jthr, 1 << 30, 1 << 30); }, (unsigned)(use_small + comp));
+      simt_emul::run_warp([&](int lane) { rc[lane] = process_component_small(c, comp, lane, &smem, c.prm.jthr, &c.status[2], 1 << 30, 1 << 30); }, (unsigned)(use_small + comp));
       for (int l = 1; l < 32; l++) if (rc[l] != rc[0]) return -2;
       if (rc[0] == 0) { n_small++; continue; }
     }
