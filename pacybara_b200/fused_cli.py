@@ -55,8 +55,11 @@ def main(argv=None) -> int:
     try:
         ra, names = ingest.arrays_from_files(ctx, bc_file, geno_file, o["uptag"] or None, log=log)
         bad = [r for r in names["ids"] if "-" in r]
-        if bad:
+        if bad:                           # (the same files on every rank: every rank leaves here)
             log(f"ERROR: read id {bad[0]!r} contains '-'", file=sys.stderr)
+            ctx.close()
+            if world > 1:
+                dist.destroy_process_group()
             return 1
         params = dict(max_diff=o["max_diff"], min_qual=o["min_qual"], min_jaccard=o["min_jaccard"], min_matches=o["min_matches"])
         if world == 1:
@@ -70,11 +73,15 @@ def main(argv=None) -> int:
             log(f" - {out['n_buckets']} barcode groups, {out['n_edges']} barcode pairs, {len(table)} rows")
             hostdata.write_clusters_csv(o["out"], table)
             log("Done!")
-    finally:
+    except Exception:
         ctx.close()
-        if world > 1:
-            dist.barrier()
+        if world > 1:                     # no barrier on the way out of an error: the other ranks may not get there
             dist.destroy_process_group()
+        raise
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 

@@ -103,6 +103,23 @@ def upload_sharded(arrs: Dict, rank: int, world: int, dev) -> Dict:
     return out
 
 
+class ShardError(RuntimeError):
+    """A local stage failed on some rank; every rank raises this at the same point instead of hanging in the next collective."""
+
+
+def _all_ranks_ok(stage: str, local_error, dev) -> None:
+    """Collective: ranks agree on whether `stage` went through everywhere (an error raised on one rank only -- a missing
+    uptag in a component it owns, a full hit buffer, no memory -- would leave the others blocked in the next all-gather)."""
+    import torch
+    import torch.distributed as dist
+    flag = torch.tensor([0 if local_error is None else 1], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if int(flag.item()):
+        if local_error is not None:
+            raise local_error
+        raise ShardError(f"another rank failed in stage '{stage}'")
+
+
 def cluster_reads_sharded(ctx: Context, arrs: Dict, params: Dict, rank: int, world: int, on_device: bool = True,
                           full_table: bool = False, combine: bool = False) -> Dict:
     """`arrs`: dict of torch tensors (seq, qual, length, lexrank, geno_ptr, geno_mut, geno_q, mut_rank[, up_id]),
@@ -138,7 +155,12 @@ def cluster_reads_sharded(ctx: Context, arrs: Dict, params: Dict, rank: int, wor
     # 2. my slice of the target buckets (every pair has one query side and one target side)
     lo, hi = shard_range(U, rank, world)
     bseq, blen = b["bucket_seq"].contiguous(), b["bucket_len"].contiguous()
-    ei, ej, ed = ctx.edit_pairs(bseq, blen, (2 if full_table else 1) * max_diff, t_range=(lo, hi))
+    err = None
+    try:
+        ei, ej, ed = ctx.edit_pairs(bseq, blen, (2 if full_table else 1) * max_diff, t_range=(lo, hi))
+    except Exception as e:          # noqa: BLE001 - re-raised on every rank below
+        err = e
+    _all_ranks_ok("pair search", err, dev)
     lib_stages("index", "probe", "hits")
     local_stats = dict(pairs_scored=ctx.stat("pairs_scored"), cells=ctx.stat("cells"), probe_ns=ctx.stat("probe_ns"))
     # 3. exchange edges
@@ -154,11 +176,16 @@ def cluster_reads_sharded(ctx: Context, arrs: Dict, params: Dict, rank: int, wor
                         geno_mut=a["geno_mut"], geno_q=a["geno_q"], mut_rank=a["mut_rank"], max_diff=max_diff,
                         min_qual=int(params["min_qual"]), min_jaccard=float(params["min_jaccard"]),
                         min_matches=int(params["min_matches"]))
-    if full_table:
-        out = ctx.merge(prob, PairList(ei, ej, ed, ped), shard=(rank, world), pairs_sorted=True, shard_layout=combine)
-    else:
-        out = ctx.merge(prob, PairList(ei, ej, ed, ped), shard=(rank, world), bucket_seq=bseq, bucket_len=blen,
-                        on_demand_k=2 * max_diff, pairs_sorted=True, shard_layout=combine)
+    err = None
+    try:
+        if full_table:
+            out = ctx.merge(prob, PairList(ei, ej, ed, ped), shard=(rank, world), pairs_sorted=True, shard_layout=combine)
+        else:
+            out = ctx.merge(prob, PairList(ei, ej, ed, ped), shard=(rank, world), bucket_seq=bseq, bucket_len=blen,
+                            on_demand_k=2 * max_diff, pairs_sorted=True, shard_layout=combine)
+    except Exception as e:          # noqa: BLE001 - e.g. PCB_E_UPTAG, raised only where the component lives
+        err = e
+    _all_ranks_ok("merge", err, dev)
     lib_stages("prep", "replay", "scatter")
     local_stats.update(links=ctx.stat("links"), tests=ctx.stat("tests"), components=ctx.stat("components"))
     # 5. result
