@@ -283,29 +283,28 @@ __global__ void large_scratch_kernel(MergeCtx c, const int32_t *__restrict__ lis
 }
 
 // ------------------------------------------------------------------------------------------ replay kernels
+constexpr int SMALL_BLOCK = 128;
 // One warp per component of at most 32 reads, one lane per read (merge_small.cuh).  A component it is not eligible
 // for (more than 32 live mutations, huge qualities) goes on the declined list -- or, when a local copy would not fit
 // the medium kernel either, on the late list the host looks at after the step.
-// One-warp blocks, a fixed grid, every warp strides over the components: a warp's registers and shared memory are free
-// for the next component the moment it is done (four-warp blocks held 4 x 8 KB until their slowest warp finished:
-// ncu r02d, 18 of 28 possible warps resident), and components come in label order, i.e. in random order of size.
-__global__ void __launch_bounds__(32) component_kernel_small(MergeCtx c, int32_t n_comp, int32_t *__restrict__ counters,
-                                                             int32_t *__restrict__ declined, int32_t *__restrict__ late) {
-  __shared__ SmallSmem sm;
+__global__ void __launch_bounds__(SMALL_BLOCK) component_kernel_small(MergeCtx c, int32_t n_comp, int32_t *__restrict__ counters,
+                                                                      int32_t *__restrict__ declined, int32_t *__restrict__ late) {
+  __shared__ SmallSmem sm_all[SMALL_BLOCK / 32];
   __shared__ int32_t jthr[33];
   __shared__ int32_t tally[2];
-  const int lane = threadIdx.x;
-  jthr[lane] = c.prm.jthr[lane];
-  if (lane == 0) { jthr[32] = c.prm.jthr[32]; tally[0] = 0; tally[1] = 0; }
-  __syncwarp();
-  for (int32_t comp = (int32_t)blockIdx.x; comp < n_comp; comp += (int32_t)gridDim.x) {
-    const int rc = process_component_small(c, comp, lane, &sm, jthr, tally, MED_CALLS, MED_PAIRS);
+  if (threadIdx.x < 33) jthr[threadIdx.x] = c.prm.jthr[threadIdx.x];
+  if (threadIdx.x < 2) tally[threadIdx.x] = 0;
+  __syncthreads();
+  const int32_t comp = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (comp < n_comp) {
+    const int rc = process_component_small(c, comp, lane, &sm_all[threadIdx.x >> 5], jthr, tally, MED_CALLS, MED_PAIRS);
     if (lane == 0 && rc == 1) declined[atomicAdd(&counters[CNT_DECLINED], 1)] = comp;
     if (lane == 0 && rc == 2) late[atomicAdd(&counters[CNT_LATE], 1)] = comp;
-    __syncwarp();
   }
-  // links / tests: one atomic per warp and counter, spread over 32 slots (status[4 + 2 * slot + which])
-  if (lane < 2 && tally[lane]) atomicAdd(&c.status[4 + 2 * (blockIdx.x & 31) + lane], tally[lane]);
+  __syncthreads();
+  // links / tests: one atomic per block and counter, spread over 32 slots (status[4 + 2 * slot + which])
+  if (threadIdx.x < 2 && tally[threadIdx.x]) atomicAdd(&c.status[4 + 2 * (blockIdx.x & 31) + threadIdx.x], tally[threadIdx.x]);
 }
 
 // The generic warp replay (merge_warp.cuh) on a LOCAL copy of one component: reads, calls, buckets and visiting pairs
@@ -649,9 +648,8 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
     PCB_CUDA(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
   }
   if (shape == PCB_REPLAY_AUTO && n_comp > 0) {
-    const unsigned small_grid = (unsigned)ctx->sm_count * 28u;          // 28 one-warp blocks fit an SM (8 KB of shared memory each)
-    PCB_LAUNCH(ctx, component_kernel_small, (unsigned)n_comp < small_grid ? (unsigned)n_comp : small_grid, 32, 0, c, n_comp, counters.p,
-               declined.p, late.p);
+    PCB_LAUNCH(ctx, component_kernel_small, grid_for((size_t)n_comp * 32, SMALL_BLOCK), SMALL_BLOCK, 0, c, n_comp, counters.p, declined.p,
+               late.p);
     // whatever it declined (the count is only known on the device): a fixed grid walks the list
     PCB_LAUNCH(ctx, component_kernel_medium, medium_grid / 4u, 32, sizeof(MediumSmem), c, declined.p, counters.p + CNT_DECLINED);
   }
