@@ -224,6 +224,27 @@ def add_opaque():
         print("  ", row)
 
 
+DENSE_GEN = dict(n_clones=450, n_reads=3200, bc_len=13, pattern="SW", p_err=0.01, p_near=0.0, seed=61)
+
+
+def add_dense():
+    """Adds tests/golden/x_dense_sw.json.gz: the reference template's SWSW... barcode design at a density where the link
+    graph percolates (450 clones in 2^13 codes: nearly all reads hang together in ONE component)."""
+    lib = synth.make_library(name="x_dense_sw", **DENSE_GEN)
+    fastq, geno, uptag = lib_texts(lib)
+    case = run_case("x_dense_sw", fastq, geno, uptag, "canonical", _params({}), note=f"synth.make_library({DENSE_GEN})")
+    assert case["exit_code"] == 0, case["stderr_tail"]
+    with gzip.GzipFile(os.path.join(GOLDEN_DIR, "x_dense_sw.json.gz"), "wb", mtime=0) as fh:
+        fh.write(json.dumps(case, indent=0).encode())
+    ipath = os.path.join(GOLDEN_DIR, "INDEX.json")
+    with open(ipath) as fh:
+        index = [e for e in json.load(fh) if e["name"] != "x_dense_sw"]
+    index.append(dict(name="x_dense_sw", exit_code=case["exit_code"], n_rows=case["n_rows"], digest=case["digest"]))
+    with open(ipath, "w") as fh:
+        json.dump(index, fh, indent=1)
+    print(f"x_dense_sw exit={case['exit_code']} rows={case['n_rows']} ed_rows={len(case['ed_rows'])}")
+
+
 def add_textquirks():
     """Adds tests/golden/x_textquirks.json.gz (and its INDEX entry) without touching the other fixtures."""
     fastq, geno, uptag = textquirks_texts()
@@ -241,6 +262,10 @@ def add_textquirks():
 
 
 def main():
+    if "--add-dense" in sys.argv:
+        if not ref_runner.available():
+            sys.exit("reference scripts not found")
+        return add_dense()
     if "--add-opaque" in sys.argv:
         if not ref_runner.available():
             sys.exit("reference scripts not found")

@@ -170,10 +170,12 @@ def make_library(n_clones: int, n_reads: int, bc_len: int = 25, *, seed: int = 1
                  q_clone=(60, 93), q_private=(5, 30), p_private: float = 0.15,
                  p_private_hq: float = 0.01, p_dropout: float = 0.03,
                  base_q=(30, 93), skew: float = 0.0, id_style: str = "padded",
-                 name: str = "custom") -> Library:
+                 name: str = "custom", pattern: Optional[str] = None) -> Library:
     """Generate a library.
 
-    * barcodes are uniform over ACGT (``bc_len`` nt, or 2 x ``bc_len`` when ``combo``);
+    * barcodes are uniform over ACGT (``bc_len`` nt, or 2 x ``bc_len`` when ``combo``), or follow a degenerate
+      ``pattern`` repeated to the barcode length: S = C/G, W = A/T, N = any (the reference's template designs its
+      barcode as SWSW..., templates/pacybara_parameters.txt:13 -- a DENSE code space: 2^25 codes for 25 nt);
     * ``p_near`` of the clones get a barcode 1-2 substitutions away from another clone
       (half of them with the same genotype) -- this plants the buckets adjacent to two
       clusters that make the reference's row-order dependence observable (SURVEY KAT-3);
@@ -188,6 +190,12 @@ def make_library(n_clones: int, n_reads: int, bc_len: int = 25, *, seed: int = 1
     L = bc_len * (2 if combo else 1)
     lmax = min(64, L + 6)
     clone_bc = rng.integers(0, 4, size=(n_clones, L), dtype=np.int64).astype(np.uint8)
+    if pattern:
+        pat = (pattern * (L // len(pattern) + 1))[:L]
+        bit = rng.integers(0, 2, size=(n_clones, L)).astype(np.uint8)
+        lo = np.array([{"S": 1, "W": 0}.get(c, 255) for c in pat], dtype=np.uint8)      # codes: A0 C1 G2 T3 -> S = 1 + bit, W = 3 * bit
+        is_s, is_w = lo == 1, lo == 0
+        clone_bc = np.where(is_s[None, :], 1 + bit, np.where(is_w[None, :], 3 * bit, clone_bc)).astype(np.uint8)
 
     # clone genotypes (CSR over clones)
     n_mut = rng.integers(0, 4, size=n_clones)
@@ -303,6 +311,9 @@ CONFIGS = {
     "cfg4": dict(gen=dict(n_clones=1_000_000, n_reads=10_000_000, bc_len=25, p_err=0.001,
                           p_collide=0.05, q_clone=(20, 50), q_private=(3, 15)), max_diff=2, min_qual=27),
     "cfg5": dict(gen=dict(n_clones=2_000_000, n_reads=20_000_000, bc_len=25), max_diff=2, min_qual=32),
+    # not a BASELINE.json config: the reference template's SWSW... barcode design, where 10^6 clones sit in 2^25 codes and
+    # the link graph percolates into giant components (hard part 1)
+    "dense": dict(gen=dict(n_clones=1_000_000, n_reads=10_000_000, bc_len=25, pattern="SW"), max_diff=2, min_qual=32),
 }
 
 
