@@ -412,7 +412,7 @@ def main():
     per_query = (kk + 1) * (2 * kk + 1)
     algo_bytes = (U // world) * per_query * 20 + pairs * 24 + (E // world) * 12
     roof_probe = dict(bound="hbm", achieved=algo_bytes / probe_s / 1e9, peak=hbm_peak, unit="GB/s",
-                      frac=algo_bytes / probe_s / 1e9 / hbm_peak, traffic=None, kernel="probe_kernel<false, true>",
+                      frac=algo_bytes / probe_s / 1e9 / hbm_peak, traffic=None, kernel="probe_kernel_lanes (probe.cuh)",
                       note="integer-ALU bound kernel: the HBM fraction is small by construction, see roofline_alu")
     # the replay (merge.cu).  Algorithmic bytes per launch: per read 16 B of inputs (lexrank, barcode id,
     # bucket, genotype offset) + 12 B of per-read outputs; 8 B per genotype entry; 32 B per output row; 4 B per call.
