@@ -86,7 +86,9 @@ enum {
   PCB_STAT_ROWS = 16,          /* rows of the last pcb_cluster_reads with PCB_CLUSTER_COMPACT_ROWS */
   PCB_STAT_CALLS = 17,         /* consensus genotype entries of those rows */
   PCB_STAT_CANDIDATES = 18,    /* candidate pairs the seed index produced (before the composition / length filters) */
-  PCB_STAT_COUNT = 19
+  PCB_STAT_HUGE_COMPONENTS = 19, /* components replayed by the whole device (giant tier) in the last merge */
+  PCB_STAT_HUGE_ROUNDS = 20,   /* rounds of deterministic reservations their main loop took */
+  PCB_STAT_COUNT = 21
 };
 
 typedef struct pcb_ctx pcb_ctx;
@@ -100,12 +102,18 @@ int64_t pcb_stat(const pcb_ctx *ctx, int which);
 /*
  * Options of a context.  PCB_OPT_REPLAY_SHAPE: which launch shape replays the components in pcb_merge /
  * pcb_cluster_reads -- PCB_REPLAY_AUTO (default: one warp per component with one lane per read for components of
- * at most 32 reads, the generic warp kernel for the rest), PCB_REPLAY_THREAD (one thread per component) or
- * PCB_REPLAY_WARP (the generic warp kernel for everything).  All shapes give identical results; the knob exists
- * for measurements and for the parity tests, which run every shape.
+ * at most 32 reads, the generic warp kernel up to PCB_OPT_HUGE_READS reads, the whole device beyond),
+ * PCB_REPLAY_THREAD (one thread per component), PCB_REPLAY_WARP (the generic warp kernel for everything) or
+ * PCB_REPLAY_HUGE (every component through the giant tier: seed step per bucket, main loop in rounds of deterministic
+ * reservations, consensus per cluster).  All shapes give identical results; the knob exists for measurements and for
+ * the parity tests, which run every shape.
+ * Giant tier: PCB_OPT_HUGE_READS = reads above which a component is replayed by the whole device (default 256);
+ * PCB_OPT_HUGE_CAP = slots of a warp's scratch table, a power of two >= 16 (default 2048; units that need more wait
+ * for a few warps with scratch sized on demand); PCB_OPT_HUGE_WINDOW = rows per round (default 32768).
  */
-enum { PCB_OPT_REPLAY_SHAPE = 0, PCB_OPT_TRACE = 1 /* 1: host-side lap times of the stages on stderr (development aid) */ };
-enum { PCB_REPLAY_AUTO = 0, PCB_REPLAY_THREAD = 1, PCB_REPLAY_WARP = 2 };
+enum { PCB_OPT_REPLAY_SHAPE = 0, PCB_OPT_TRACE = 1 /* 1: host-side lap times of the stages on stderr (development aid) */,
+       PCB_OPT_HUGE_READS = 2, PCB_OPT_HUGE_CAP = 3, PCB_OPT_HUGE_WINDOW = 4 };
+enum { PCB_REPLAY_AUTO = 0, PCB_REPLAY_THREAD = 1, PCB_REPLAY_WARP = 2, PCB_REPLAY_HUGE = 3 };
 int pcb_set_option(pcb_ctx *ctx, int option, int64_t value);
 /* Block until everything queued on the context's stream has finished. */
 int pcb_sync(pcb_ctx *ctx);

@@ -18,11 +18,11 @@ MERGE_PAIRS_SORTED = 1
 MERGE_SHARD_LAYOUT = 2
 STAT = dict(pairs_scored=0, cells=1, edges=2, seed_len=3, kernel_launches=4, components=5, links=6, tests=7,
             buckets=8, probe_ns=9, t_bucket_ns=10, t_index_ns=11, t_hits_ns=12, t_prep_ns=13, t_replay_ns=14,
-            t_scatter_ns=15, rows=16, calls=17, candidates=18)
+            t_scatter_ns=15, rows=16, calls=17, candidates=18, huge_components=19, huge_rounds=20)
 
 # every symbol include/pacybara_b200.h declares
-REPLAY_SHAPES = dict(auto=0, small=0, thread=1, warp=2)
-OPT_REPLAY_SHAPE = 0
+REPLAY_SHAPES = dict(auto=0, small=0, thread=1, warp=2, huge=3)
+OPT_REPLAY_SHAPE, OPT_TRACE, OPT_HUGE_READS, OPT_HUGE_CAP, OPT_HUGE_WINDOW = range(5)
 
 SYMBOLS = ["pcb_abi_version", "pcb_last_error", "pcb_ctx_create", "pcb_ctx_destroy", "pcb_stat", "pcb_set_option", "pcb_sync",
            "pcb_stream", "pcb_bucket", "pcb_edit_pairs", "pcb_edit_pairs_fetch", "pcb_sort_edges", "pcb_merge", "pcb_cluster_reads", "pcb_compact_shard", "pcb_match_barcodes", "pcb_tag_rows", "pcb_merge_libraries",

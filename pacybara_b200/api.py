@@ -80,6 +80,22 @@ class Context:
         self._check(self.lib.pcb_set_option(self.h, _lib.OPT_REPLAY_SHAPE, _lib.REPLAY_SHAPES[shape]))
         if os.environ.get("PCB_TRACE"):
             self._check(self.lib.pcb_set_option(self.h, 1, 1))
+        # giant-tier knobs: environment > set_huge() > the library's defaults, applied per call like the shape
+        for env, opt, default in (("PCB_HUGE_READS", _lib.OPT_HUGE_READS, 256), ("PCB_HUGE_CAP", _lib.OPT_HUGE_CAP, 2048),
+                                  ("PCB_HUGE_WINDOW", _lib.OPT_HUGE_WINDOW, 32768)):
+            v = int(os.environ[env]) if os.environ.get(env) else getattr(self, "_huge", {}).get(opt, default)
+            if getattr(self, "_huge_set", {}).get(opt) != v:
+                self._check(self.lib.pcb_set_option(self.h, opt, v))
+                self._huge_set = dict(getattr(self, "_huge_set", {}))
+                self._huge_set[opt] = v
+
+    def set_huge(self, reads: Optional[int] = None, cap: Optional[int] = None, window: Optional[int] = None):
+        """Knobs of the giant tier (pcb_set_option): component size above which it is used, slots of a warp's scratch
+        table, rows per round.  Results do not depend on them."""
+        self._huge = dict(getattr(self, "_huge", {}))
+        for v, opt in ((reads, _lib.OPT_HUGE_READS), (cap, _lib.OPT_HUGE_CAP), (window, _lib.OPT_HUGE_WINDOW)):
+            if v is not None:
+                self._huge[opt] = int(v)
 
     def stream_handle(self) -> int:
         return int(self.lib.pcb_stream(self.h) or 0)

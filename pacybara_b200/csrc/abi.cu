@@ -242,11 +242,14 @@ int64_t pcb_stat(const pcb_ctx *ctx, int which) {
 
 int pcb_set_option(pcb_ctx *ctx, int option, int64_t value) {
   if (!ctx) return PCB_E_STATE;
-  if (option == PCB_OPT_REPLAY_SHAPE && value >= PCB_REPLAY_AUTO && value <= PCB_REPLAY_WARP) {
+  if (option == PCB_OPT_REPLAY_SHAPE && value >= PCB_REPLAY_AUTO && value <= PCB_REPLAY_HUGE) {
     ctx->replay_shape = (int)value;
     return PCB_OK;
   }
   if (option == PCB_OPT_TRACE) { ctx->trace = value != 0; return PCB_OK; }
+  if (option == PCB_OPT_HUGE_READS && value >= 0 && value <= INT32_MAX) { ctx->huge_reads = (int)value; return PCB_OK; }
+  if (option == PCB_OPT_HUGE_CAP && value >= 16 && value <= (1 << 20) && (value & (value - 1)) == 0) { ctx->huge_cap = (int)value; return PCB_OK; }
+  if (option == PCB_OPT_HUGE_WINDOW && value >= 1 && value <= (1 << 24)) { ctx->huge_window = (int)value; return PCB_OK; }
   ctx->err = "pcb_set_option: unknown option or value";
   return PCB_E_INPUT;
 }

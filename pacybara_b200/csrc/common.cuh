@@ -54,6 +54,10 @@ struct pcb_ctx {
   std::string err;
   int64_t stats[PCB_STAT_COUNT] = {0};
   int replay_shape = PCB_REPLAY_AUTO;      // pcb_set_option(PCB_OPT_REPLAY_SHAPE)
+  int huge_reads = 256;                    // PCB_OPT_HUGE_READS: components above it are replayed by the whole device (merge_huge.cuh)
+  int huge_cap = 2048;                     // PCB_OPT_HUGE_CAP: slots of one warp's scratch table in that tier
+  int huge_window = 32768;                 // PCB_OPT_HUGE_WINDOW: rows per round
+  int huge_warps_per_sm = 24;
   bool medium_attr_set = false;            // the medium replay kernel's shared-memory opt-in (merge.cu)
   int trace = 0;                           // pcb_set_option(PCB_OPT_TRACE): host-side lap times on stderr
   // Workspace arena: the temporaries of one call are carved out of one long-lived allocation with a bump pointer and

@@ -30,6 +30,7 @@
 #include "merge_core.h"
 #include "merge_small.cuh"
 #include "merge_warp.cuh"
+#include "merge_huge.cuh"
 
 namespace pcb {
 
@@ -65,7 +66,8 @@ __global__ void uf_union_kernel(const int32_t *__restrict__ pq, const int32_t *_
 
 // counters: [0] buckets of this shard, [1] components of this shard, [2] medium list, [3] large list, [4] visiting pairs
 // of this shard, [5] components the small kernel declined, [6] declined components too big for the medium kernel
-enum { CNT_BUCKETS = 0, CNT_COMPS, CNT_MEDIUM, CNT_LARGE, CNT_VISITS, CNT_DECLINED, CNT_LATE, CNT_N };
+// [7] giant components (merge_huge.cuh)
+enum { CNT_BUCKETS = 0, CNT_COMPS, CNT_MEDIUM, CNT_LARGE, CNT_VISITS, CNT_DECLINED, CNT_LATE, CNT_HUGE, CNT_N };
 // status: [0] error code, [1] detail, [2] links, [3] tests (generic kernels), [4 ..] 32 slots of (links, tests) from the small kernel
 constexpr int STATUS_N = 4 + 64;
 
@@ -168,24 +170,53 @@ __global__ void visit_count_kernel(const int32_t *__restrict__ pq, const int32_t
 }
 
 // Pairs sorted by (q, r): the rows a component's passes visit, in order, are the visiting pairs found by walking the
-// adjacency rows of its buckets in ascending bucket order -- once per pass.  One thread per component.
-__global__ void visit_walk_kernel(const int32_t *__restrict__ comp_ptr, const int32_t *__restrict__ comp_buckets, const int32_t *__restrict__ counters,
+// adjacency rows of its buckets in ascending bucket order -- once per pass.  One thread per BUCKET (in component order):
+// g[e][i] = rows at distance e + 1 in the adjacency row of the i-th bucket; after an exclusive scan of each g[e] over
+// the bucket list, the rows of bucket i in pass e of component c (buckets i0 .. i1) start at
+//   sum_e' G[e'][i0]  +  sum_{e' < e} (G[e'][i1] - G[e'][i0])  +  G[e][i] - G[e][i0]
+// (everything before the component, the earlier passes of the component, the earlier buckets of this pass) -- however
+// many buckets the component has: a giant component costs what its buckets cost.
+__global__ void visit_cnt_kernel(const int32_t *__restrict__ comp_buckets, const int32_t *__restrict__ comp_of_b,
+                                 const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ ped, int32_t U, int32_t max_diff,
+                                 uint32_t *__restrict__ g) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > U) return;
+  uint32_t n[3] = {0u, 0u, 0u};
+  if (i < U) {
+    const int32_t b = comp_buckets[i];
+    if (comp_of_b[b] >= 0)
+      for (int32_t e = row_ptr[b]; e < row_ptr[b + 1]; e++) {
+        const int32_t ed = ped[e];
+        if (ed == 1) n[0]++; else if (ed == 2) n[1]++; else if (ed == 3) n[2]++;
+      }
+  }
+  for (int32_t e = 0; e < max_diff; e++) g[(size_t)e * ((size_t)U + 1) + i] = n[e];
+}
+__global__ void visit_fill_kernel(const int32_t *__restrict__ comp_buckets, const int32_t *__restrict__ comp_of_b,
+                                  const int32_t *__restrict__ comp_ptr, const int32_t *__restrict__ counters,
                                   const int32_t *__restrict__ row_ptr, const int32_t *__restrict__ pr, const int32_t *__restrict__ ped,
-                                  int32_t max_diff, const uint32_t *__restrict__ off, int32_t *__restrict__ cpair_ptr,
+                                  int32_t U, int32_t max_diff, const uint32_t *__restrict__ g, int32_t *__restrict__ cpair_ptr,
                                   int32_t *__restrict__ cq, int32_t *__restrict__ cr, int32_t *__restrict__ ce) {
-  const int32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-  const int32_t n_comp = counters[CNT_COMPS];
-  if (c > n_comp) return;
-  cpair_ptr[c] = (int32_t)off[4 * (size_t)c];
-  if (c == n_comp || off[4 * (size_t)c] == off[4 * (size_t)c + 4]) return;
-  for (int32_t ed = 1; ed <= max_diff; ed++) {
-    uint32_t at = off[4 * (size_t)c + ed];
-    if (at == off[4 * (size_t)c + ed + 1]) continue;
-    for (int32_t bi = comp_ptr[c]; bi < comp_ptr[c + 1]; bi++) {
-      const int32_t a = comp_buckets[bi];
-      for (int32_t e = row_ptr[a]; e < row_ptr[a + 1]; e++)
-        if (ped[e] == ed) { cq[at] = a; cr[at] = pr[e]; ce[at] = ed; at++; }
-    }
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= U) return;
+  const int32_t b = comp_buckets[i], comp = comp_of_b[b];
+  if (comp < 0) return;
+  const int32_t i0 = comp_ptr[comp], i1 = comp_ptr[comp + 1];
+  const size_t ld = (size_t)U + 1;
+  uint32_t base = 0;
+  for (int32_t e = 0; e < max_diff; e++) base += g[e * ld + i0];
+  uint32_t at[3] = {0u, 0u, 0u}, acc = base;
+  for (int32_t e = 0; e < max_diff; e++) {
+    at[e] = acc + (g[e * ld + i] - g[e * ld + i0]);
+    acc += g[e * ld + i1] - g[e * ld + i0];
+  }
+  if (i == i0) cpair_ptr[comp] = (int32_t)base;
+  if (i == i1 - 1 && comp == counters[CNT_COMPS] - 1) cpair_ptr[comp + 1] = (int32_t)acc;      // end of this shard's last component
+  for (int32_t e = row_ptr[b]; e < row_ptr[b + 1]; e++) {
+    const int32_t ed = ped[e];
+    uint32_t k;
+    if (ed == 1) k = at[0]++; else if (ed == 2 && max_diff >= 2) k = at[1]++; else if (ed == 3 && max_diff >= 3) k = at[2]++; else continue;
+    cq[k] = b; cr[k] = pr[e]; ce[k] = ed;
   }
 }
 
@@ -228,51 +259,68 @@ __global__ void bucket_of_read_kernel(const int32_t *__restrict__ bucket_ptr, co
 // ------------------------------------------------------------------------------------------ tiers
 constexpr int MED_READS = 128, MED_BUCKETS = 128, MED_CALLS = 256, MED_PAIRS = 256;
 
-// Components of more than 32 reads: medium if a local copy fits the medium kernel's shared memory, else large.
-// force_large: every component goes on the large list (the PCB_REPLAY_THREAD / PCB_REPLAY_WARP shapes).
-// Also: comp_calls[comp] = genotype entries of the component's reads -- the length of its call region (an upper bound of
-// its rows' calls); a scan turns the counts into the regions' offsets, so no component has to take its region from a
-// shared cursor (2*10^6 same-address atomics at the 2*10^7-read size).
-__global__ void classify_kernel(MergeCtx c, int32_t force_large, int32_t *__restrict__ counters, int32_t *__restrict__ medium,
-                                int32_t *__restrict__ large, int64_t *__restrict__ comp_calls) {
-  const int32_t comp = blockIdx.x * blockDim.x + threadIdx.x;
-  const int32_t n_comp = counters[CNT_COMPS];
-  if (comp > n_comp) return;
-  if (comp == n_comp) { comp_calls[comp] = 0; return; }
-  const int32_t b_lo = c.comp_ptr[comp], b_hi = c.comp_ptr[comp + 1];
-  int64_t reads = 0, nnz = 0;
-  for (int32_t bi = b_lo; bi < b_hi; bi++) {
-    const int32_t b = c.comp_buckets[bi];
-    reads += c.bucket_ptr[b + 1] - c.bucket_ptr[b];
-    for (int32_t x = c.bucket_ptr[b]; x < c.bucket_ptr[b + 1]; x++) {
-      const int32_t r = c.bucket_reads[x];
-      nnz += c.geno_ptr[r + 1] - c.geno_ptr[r];
+// reads and genotype entries per component: one thread per bucket in component order, one atomic per run of equal
+// components inside a warp (the list is grouped by component; a giant component is 1/32 of its buckets in atomics)
+__global__ void comp_stats_kernel(const int32_t *__restrict__ comp_buckets, const int32_t *__restrict__ comp_of_b,
+                                  const int32_t *__restrict__ bucket_ptr, const int32_t *__restrict__ bucket_reads,
+                                  const int32_t *__restrict__ geno_ptr, int32_t U, int32_t *__restrict__ comp_reads,
+                                  int64_t *__restrict__ comp_calls) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int32_t comp = -1, reads = 0, nnz = 0;
+  if (i < U) {
+    const int32_t b = comp_buckets[i];
+    comp = comp_of_b[b];
+    if (comp >= 0) {
+      reads = bucket_ptr[b + 1] - bucket_ptr[b];
+      for (int32_t x = bucket_ptr[b]; x < bucket_ptr[b + 1]; x++) { const int32_t r = bucket_reads[x]; nnz += geno_ptr[r + 1] - geno_ptr[r]; }
     }
   }
-  comp_calls[comp] = nnz;
-  if (!force_large && reads <= SMALL_READS) return;
-  const bool fits = !force_large && reads <= MED_READS && b_hi - b_lo <= MED_BUCKETS &&
+  for (int o = 1; o < 32; o <<= 1) {                          // segmented sums towards the first lane of every run
+    const int32_t c2 = __shfl_down_sync(PCB_FULL, comp, o), r2 = __shfl_down_sync(PCB_FULL, reads, o), n2 = __shfl_down_sync(PCB_FULL, nnz, o);
+    if (lane + o < 32 && c2 == comp) { reads += r2; nnz += n2; }
+  }
+  const int32_t prev = __shfl_up_sync(PCB_FULL, comp, 1);
+  if (comp >= 0 && (lane == 0 || prev != comp)) {
+    atomicAdd(&comp_reads[comp], reads);
+    atomicAdd((unsigned long long *)&comp_calls[comp], (unsigned long long)nnz);
+  }
+}
+
+// Components of more than 32 reads: giant if above huge_reads (replayed by the whole device, merge_huge.cuh), else medium
+// if a local copy fits the medium kernel's shared memory, else large.  force: FORCE_LARGE puts every component on the
+// large list (the PCB_REPLAY_THREAD / PCB_REPLAY_WARP shapes), FORCE_HUGE on the giant list (PCB_REPLAY_HUGE).
+// comp_calls[comp] = genotype entries of the component's reads is also the length of its call region (an upper bound
+// of its rows' calls); a scan turns the counts into the regions' offsets.
+enum { FORCE_NONE = 0, FORCE_LARGE = 1, FORCE_HUGE = 2 };
+__global__ void classify_kernel(MergeCtx c, const int32_t *__restrict__ comp_reads, const int64_t *__restrict__ comp_calls, int32_t force,
+                                int32_t huge_reads, int32_t *__restrict__ counters, int32_t *__restrict__ medium,
+                                int32_t *__restrict__ large, int32_t *__restrict__ hcomp, int32_t *__restrict__ huge_of_comp) {
+  const int32_t comp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (comp >= counters[CNT_COMPS]) return;
+  const int32_t reads = comp_reads[comp];
+  const int64_t nnz = comp_calls[comp];
+  huge_of_comp[comp] = -1;
+  if (force == FORCE_NONE && reads <= SMALL_READS) return;
+  if (force == FORCE_HUGE || (force == FORCE_NONE && reads > huge_reads)) {
+    const int32_t h = atomicAdd(&counters[CNT_HUGE], 1);
+    hcomp[h] = comp; huge_of_comp[comp] = h;
+    return;
+  }
+  const bool fits = force == FORCE_NONE && reads <= MED_READS && c.comp_ptr[comp + 1] - c.comp_ptr[comp] <= MED_BUCKETS &&
                     c.cpair_ptr[comp + 1] - c.cpair_ptr[comp] <= MED_PAIRS && nnz <= MED_CALLS;
   if (fits) medium[atomicAdd(&counters[CNT_MEDIUM], 1)] = comp;
   else large[atomicAdd(&counters[CNT_LARGE], 1)] = comp;
 }
 
 // scratch of the large components (one thread each): table capacity, list length
-__global__ void large_scratch_kernel(MergeCtx c, const int32_t *__restrict__ list, int32_t n, int32_t *__restrict__ slot_cap,
+__global__ void large_scratch_kernel(const int32_t *__restrict__ comp_reads, const int64_t *__restrict__ comp_calls,
+                                     const int32_t *__restrict__ list, int32_t n, int32_t *__restrict__ slot_cap,
                                      int64_t *__restrict__ slot_sz, int64_t *__restrict__ list_sz) {
   const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
   if (i == n) { slot_sz[i] = 0; list_sz[i] = 0; return; }
-  const int32_t comp = list[i];
-  unsigned long long reads = 0, nnz = 0;
-  for (int32_t bi = c.comp_ptr[comp]; bi < c.comp_ptr[comp + 1]; bi++) {
-    const int32_t b = c.comp_buckets[bi];
-    reads += (unsigned long long)(c.bucket_ptr[b + 1] - c.bucket_ptr[b]);
-    for (int32_t x = c.bucket_ptr[b]; x < c.bucket_ptr[b + 1]; x++) {
-      const int32_t r = c.bucket_reads[x];
-      nnz += (unsigned long long)(c.geno_ptr[r + 1] - c.geno_ptr[r]);
-    }
-  }
+  const unsigned long long reads = (unsigned long long)comp_reads[list[i]], nnz = (unsigned long long)comp_calls[list[i]];
   unsigned long long need = 2ull * (reads > nnz ? reads : nnz);
   if (need < 2) need = 2;
   unsigned long long cap = 2;
@@ -456,6 +504,115 @@ __global__ void __launch_bounds__(THREAD_BLOCK) component_kernel_thread(MergeCtx
   if (PHASE == 3) component_consensus(c, st, s.list[i]);
 }
 
+// ------------------------------------------------------------------------------------------ giant components
+// Kernels around merge_huge.cuh.  Warps take units (buckets, window rows, cluster heads) from a list by ticket; each warp
+// owns one scratch of a pool (genotype table of `cap` slots + touched / run lists).
+constexpr int HUGE_BLOCK = 128;
+struct HugePool {
+  GenoSlot *slots;
+  int32_t *lists;
+  int32_t cap, n_warps;
+};
+__device__ __forceinline__ MergeState huge_state(const MergeCtx &c, const HugePool &pool, int32_t w) {
+  MergeState st;
+  st.r0 = 0;
+  st.rd_slot = c.rd_slot; st.rd_next = c.rd_next; st.sl_parent = c.sl_parent; st.sl_head = c.sl_head;
+  st.sl_tail = c.sl_tail; st.sl_size = c.sl_size; st.sl_key = c.sl_key;
+  st.slots = pool.slots + (size_t)w * (size_t)pool.cap;
+  st.slot_mask = pool.cap - 1;
+  st.lists = pool.lists + (size_t)w * (size_t)(8 + 2 * (size_t)pool.cap);
+  st.list_cap = pool.cap;
+  return st;
+}
+__device__ __forceinline__ int32_t huge_ticket(int32_t *counter, int lane) {
+  int32_t i = 0;
+  if (lane == 0) i = atomicAdd(counter, 1);
+  return __shfl_sync(PCB_FULL, i, 0);
+}
+
+__global__ void huge_rows_kernel(const int32_t *__restrict__ cpair_ptr, const int32_t *__restrict__ hcomp, int32_t n_huge, uint32_t *__restrict__ hrows) {
+  const int32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h <= n_huge) hrows[h] = h < n_huge ? (uint32_t)(cpair_ptr[hcomp[h] + 1] - cpair_ptr[hcomp[h]]) : 0u;
+}
+// the buckets the seed step has work for; the largest scratch one of them needs
+__global__ void huge_seedlist_kernel(MergeCtx c, HugeDev h, int32_t U, int32_t cap, const uint32_t *__restrict__ hrow_ptr, int32_t *__restrict__ seedl) {
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) h.k->total = (int32_t)hrow_ptr[h.n_huge];
+  if (i >= U) return;
+  const int32_t b = c.comp_buckets[i], comp = h.comp_of_b[b];
+  if (comp < 0 || h.huge_of_comp[comp] < 0) return;
+  const int32_t n = c.bucket_ptr[b + 1] - c.bucket_ptr[b];
+  if (n < 2) return;
+  seedl[atomicAdd(&h.k->n_seed, 1)] = b;
+  int32_t nnz = 0;
+  for (int32_t x = c.bucket_ptr[b]; x < c.bucket_ptr[b + 1]; x++) { const int32_t r = c.bucket_reads[x]; nnz += c.geno_ptr[r + 1] - c.geno_ptr[r]; }
+  const int32_t need = huge_need(nnz, n);
+  if (need > cap) atomicMax(&h.k->max_need, need);
+}
+// which: 0 = the seed list with ordinary scratch, 1 = the big list with big scratch
+__global__ void __launch_bounds__(HUGE_BLOCK) huge_seed_kernel(MergeCtx c, HugeDev h, HugePool pool, const int32_t *__restrict__ list, int which) {
+  const int32_t w = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  const MergeState st = huge_state(c, pool, w);
+  const int32_t n = which ? h.k->n_big : h.k->n_seed;
+  for (;;) {
+    const int32_t i = huge_ticket(&h.k->tk[which], lane);
+    if (i >= n) break;
+    huge_seed_item(c, st, h, pool.cap, which != 0, list[i], lane);
+  }
+}
+// one thread per read: which == 0 after the seed step (genotype entries per cell), which == 1 after the main loop
+// (rows of the lone reads, list of the cluster heads)
+__global__ void huge_reads_kernel(MergeCtx c, HugeDev h, int which) {
+  const int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= c.R) return;
+  const int32_t comp = h.comp_of_b[c.bucket_of_read[r]];
+  if (comp < 0) return;
+  const int32_t hi = h.huge_of_comp[comp];
+  if (hi < 0) return;
+  MergeState st;
+  st.r0 = 0; st.rd_slot = c.rd_slot; st.rd_next = c.rd_next; st.sl_parent = c.sl_parent; st.sl_head = c.sl_head;
+  st.sl_tail = c.sl_tail; st.sl_size = c.sl_size; st.sl_key = c.sl_key; st.slots = nullptr; st.slot_mask = 0; st.lists = nullptr; st.list_cap = 0;
+  if (which == 0) huge_count_read(c, st, r);
+  else huge_finish_read(c, st, h, hi, r);
+}
+__global__ void huge_advance_kernel(HugeDev h) { huge_advance(h); }
+__global__ void __launch_bounds__(HUGE_BLOCK) huge_reserve_kernel(MergeCtx c, HugeDev h) {
+  const int32_t idx = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  if (idx >= h.k->n_window) return;
+  HugePool none{nullptr, nullptr, 0, 0};
+  huge_reserve_item(c, huge_state(c, none, 0), h, idx, threadIdx.x & 31);
+}
+// which: 0 = the window with ordinary scratch, 1 = the winners those warps passed on, with big scratch
+__global__ void __launch_bounds__(HUGE_BLOCK) huge_exec_kernel(MergeCtx c, HugeDev h, HugePool pool, int which, int have_big) {
+  const int32_t w = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  const MergeState st = huge_state(c, pool, w);
+  const int32_t n = which ? h.k->n_heavy : h.k->n_window;
+  for (;;) {
+    const int32_t i = huge_ticket(which ? &h.k->ticket_heavy : &h.k->ticket, lane);
+    if (i >= n) break;
+    if (which) huge_heavy_item(c, st, h, pool.cap, i, lane);
+    else huge_row_item(c, st, h, pool.cap, have_big != 0, i, lane);
+  }
+}
+__global__ void __launch_bounds__(HUGE_BLOCK) huge_head_kernel(MergeCtx c, HugeDev h, HugePool pool, int which) {
+  const int32_t w = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  const MergeState st = huge_state(c, pool, w);
+  const int32_t n = which ? h.k->n_big : h.k->n_heads;
+  const int32_t *list = which ? h.big : h.heads;
+  for (;;) {
+    const int32_t i = huge_ticket(&h.k->tk[2 + which], lane);
+    if (i >= n) break;
+    huge_head_item(c, st, h, pool.cap, which != 0, list[i], lane);
+  }
+}
+__global__ void huge_tally_kernel(HugeDev h, int32_t *status) {
+  atomicAdd(&status[2], h.k->links);
+  atomicAdd(&status[3], h.k->tests);
+}
+
 __global__ void init_outputs_kernel(int32_t R, int64_t nnz, MergeOut out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < R) {
@@ -468,12 +625,31 @@ __global__ void init_outputs_kernel(int32_t R, int64_t nnz, MergeOut out) {
 // ------------------------------------------------------------------------------------------ host
 namespace {
 
+// cluster state in global memory (size R), shared by the large and the giant tier: allocated when first needed
+struct ClusterArrays {
+  DevBuf<int32_t> rd_slot, rd_next, sl_parent, sl_head, sl_tail, sl_size;
+  DevBuf<int64_t> sl_key;
+  bool ready = false;
+  void attach(pcb_ctx *ctx, MergeCtx &c, int32_t R) {
+    if (!ready) {
+      rd_slot.alloc(ctx, R); rd_next.alloc(ctx, R); sl_parent.alloc(ctx, R); sl_head.alloc(ctx, R); sl_tail.alloc(ctx, R); sl_size.alloc(ctx, R);
+      sl_key.alloc(ctx, R);
+      PCB_CUDA(cudaMemsetAsync(rd_slot.p, 0xFF, (size_t)R * sizeof(int32_t), ctx->stream));
+      PCB_CUDA(cudaMemsetAsync(rd_next.p, 0xFF, (size_t)R * sizeof(int32_t), ctx->stream));
+      ready = true;
+    }
+    c.rd_slot = rd_slot.p; c.rd_next = rd_next.p; c.sl_parent = sl_parent.p; c.sl_head = sl_head.p;
+    c.sl_tail = sl_tail.p; c.sl_size = sl_size.p; c.sl_key = sl_key.p;
+  }
+};
+
 // The generic replay on global state for a list of components (the large tier; every component under the forced shapes).
-void run_large(pcb_ctx *ctx, MergeCtx c, const int32_t *list, int32_t n, int32_t R, int shape) {
+void run_large(pcb_ctx *ctx, MergeCtx c, ClusterArrays &cl, const int32_t *comp_reads, const int64_t *comp_calls, const int32_t *list, int32_t n,
+               int32_t R, int shape) {
   if (n <= 0) return;
   DevBuf<int32_t> slot_cap(ctx, (size_t)n + 1);
   DevBuf<int64_t> slot_off(ctx, (size_t)n + 1), list_off(ctx, (size_t)n + 1);
-  PCB_LAUNCH(ctx, large_scratch_kernel, grid_for((size_t)n + 1, 128), 128, 0, c, list, n, slot_cap.p, slot_off.p, list_off.p);
+  PCB_LAUNCH(ctx, large_scratch_kernel, grid_for((size_t)n + 1, 128), 128, 0, comp_reads, comp_calls, list, n, slot_cap.p, slot_off.p, list_off.p);
   exclusive_scan_i64(ctx, slot_off.p, slot_off.p, (size_t)n + 1);
   exclusive_scan_i64(ctx, list_off.p, list_off.p, (size_t)n + 1);
   int64_t n_slots = 0, n_list = 0;
@@ -483,13 +659,8 @@ void run_large(pcb_ctx *ctx, MergeCtx c, const int32_t *list, int32_t n, int32_t
   DevBuf<GenoSlot> slots(ctx, (size_t)n_slots);
   DevBuf<int32_t> lists(ctx, (size_t)n_list + 1);
   PCB_CUDA(cudaMemsetAsync(slots.p, 0, (size_t)n_slots * sizeof(GenoSlot), ctx->stream));     // all-zero = empty
-  DevBuf<int32_t> rd_slot(ctx, R), rd_next(ctx, R), sl_parent(ctx, R), sl_head(ctx, R), sl_tail(ctx, R), sl_size(ctx, R);
-  DevBuf<int64_t> sl_key(ctx, R);
-  PCB_CUDA(cudaMemsetAsync(rd_slot.p, 0xFF, (size_t)R * sizeof(int32_t), ctx->stream));
-  PCB_CUDA(cudaMemsetAsync(rd_next.p, 0xFF, (size_t)R * sizeof(int32_t), ctx->stream));
+  cl.attach(ctx, c, R);
   c.slots = slots.p; c.lists = lists.p;
-  c.rd_slot = rd_slot.p; c.rd_next = rd_next.p; c.sl_parent = sl_parent.p; c.sl_head = sl_head.p;
-  c.sl_tail = sl_tail.p; c.sl_size = sl_size.p; c.sl_key = sl_key.p;
   LargeScratch s{list, slot_cap.p, slot_off.p, list_off.p};
   if (shape == PCB_REPLAY_THREAD) {
     const int per_warp = 4;               // best of a 1..32 sweep (divergent lanes serialise)
@@ -502,6 +673,105 @@ void run_large(pcb_ctx *ctx, MergeCtx c, const int32_t *list, int32_t n, int32_t
     PCB_LAUNCH(ctx, component_kernel_large, grid_for((size_t)n * 32, COMP_BLOCK), COMP_BLOCK, 0, c, s, n);
   }
   PCB_CUDA(cudaStreamSynchronize(ctx->stream));          // the scratch above is released when this returns
+}
+
+// a pool of warp scratches (zeroed tables)
+struct HugePoolBuf {
+  DevBuf<GenoSlot> slots;
+  DevBuf<int32_t> lists;
+  HugePool pool{nullptr, nullptr, 0, 0};
+  void make(pcb_ctx *ctx, int32_t cap, int32_t n_warps) {
+    slots.alloc(ctx, (size_t)cap * (size_t)n_warps);
+    lists.alloc(ctx, (size_t)(8 + 2 * (size_t)cap) * (size_t)n_warps);
+    PCB_CUDA(cudaMemsetAsync(slots.p, 0, (size_t)cap * (size_t)n_warps * sizeof(GenoSlot), ctx->stream));
+    pool = HugePool{slots.p, lists.p, cap, n_warps};
+  }
+  unsigned grid() const { return (unsigned)((pool.n_warps * 32 + HUGE_BLOCK - 1) / HUGE_BLOCK); }
+};
+int32_t pow2_at_least(int64_t v) { int64_t c = 16; while (c < v) c <<= 1; return (int32_t)(c > (1ll << 30) ? (1ll << 30) : c); }
+
+// The giant tier (merge_huge.cuh): seed step per bucket, main loop in rounds of deterministic reservations, consensus per
+// cluster -- all giant components of the call together.
+void run_huge(pcb_ctx *ctx, MergeCtx c, ClusterArrays &cl, const int32_t *comp_of_b, const int32_t *huge_of_comp, const int32_t *hcomp,
+              int32_t n_huge, int32_t R, int32_t U) {
+  if (n_huge <= 0) return;
+  HostTrace tr(ctx, "giant tier");
+  const int32_t cap = ctx->huge_cap, W = ctx->huge_window;
+  cl.attach(ctx, c, R);
+  DevBuf<uint32_t> hrow_ptr(ctx, (size_t)n_huge + 1);
+  DevBuf<int32_t> seedl(ctx, (size_t)U + 1), cell_nnz(ctx, R), win(ctx, W), carry0(ctx, W), carry1(ctx, W), heavy(ctx, W), heads(ctx, R), big(ctx, R);
+  DevBuf<unsigned long long> resv(ctx, R), cursor(ctx, n_huge);
+  DevBuf<HugeCounters> k(ctx, 1);
+  PCB_CUDA(cudaMemsetAsync(k.p, 0, sizeof(HugeCounters), ctx->stream));
+  PCB_CUDA(cudaMemsetAsync(resv.p, 0xFF, (size_t)R * sizeof(unsigned long long), ctx->stream));
+  PCB_CUDA(cudaMemsetAsync(cell_nnz.p, 0, (size_t)R * sizeof(int32_t), ctx->stream));
+  PCB_CUDA(cudaMemsetAsync(cursor.p, 0, (size_t)n_huge * sizeof(unsigned long long), ctx->stream));
+  c.cell_nnz = cell_nnz.p;
+  HugeDev h;
+  h.resv = resv.p; h.comp_of_b = comp_of_b; h.huge_of_comp = huge_of_comp; h.hcomp = hcomp; h.hrow_ptr = (const int32_t *)hrow_ptr.p;
+  h.cursor = cursor.p; h.n_huge = n_huge; h.W = W; h.win = win.p; h.carry[0] = carry0.p; h.carry[1] = carry1.p; h.heavy = heavy.p;
+  h.heads = heads.p; h.big = big.p; h.k = k.p;
+  PCB_LAUNCH(ctx, huge_rows_kernel, grid_for((size_t)n_huge + 1, 256), 256, 0, c.cpair_ptr, hcomp, n_huge, hrow_ptr.p);
+  exclusive_scan_u32(ctx, hrow_ptr.p, hrow_ptr.p, (size_t)n_huge + 1);
+  PCB_LAUNCH(ctx, huge_seedlist_kernel, grid_for(U, 256), 256, 0, c, h, U, cap, hrow_ptr.p, seedl.p);
+  HugeCounters hk;
+  auto read_counters = [&] {
+    PCB_CUDA(cudaMemcpyAsync(&hk, k.p, sizeof(hk), cudaMemcpyDeviceToHost, ctx->stream));
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  };
+  read_counters();
+  // scratch: one per resident warp; a few big ones sized for the largest unit that asked (re-made when one asks for more)
+  HugePoolBuf pool, bigpool;
+  pool.make(ctx, cap, ctx->sm_count * ctx->huge_warps_per_sm);
+  auto size_big = [&](int32_t need) {
+    const int32_t bcap = pow2_at_least(need);
+    int64_t nw = ((int64_t)1 << 24) / bcap;
+    bigpool.make(ctx, bcap, (int32_t)(nw < 1 ? 1 : nw > 64 ? 64 : nw));
+  };
+  if (hk.max_need > cap) size_big(hk.max_need);
+  tr.lap("lists");
+
+  // ---- seed step
+  PCB_LAUNCH(ctx, huge_seed_kernel, pool.grid(), HUGE_BLOCK, 0, c, h, pool.pool, seedl.p, 0);
+  if (bigpool.pool.cap) PCB_LAUNCH(ctx, huge_seed_kernel, bigpool.grid(), HUGE_BLOCK, 0, c, h, bigpool.pool, big.p, 1);
+  PCB_CUDA(cudaMemsetAsync(&k.p->n_big, 0, sizeof(int32_t), ctx->stream));
+  PCB_CUDA(cudaMemsetAsync(&k.p->max_need, 0, sizeof(int32_t), ctx->stream));
+  PCB_LAUNCH(ctx, huge_reads_kernel, grid_for(R, 256), 256, 0, c, h, 0);
+
+  // ---- main loop: rounds; the host looks at the counters once per batch
+  const int batch = 16;
+  int64_t rounds = 0;
+  if (hk.total > 0)
+    for (;;) {
+      for (int r = 0; r < batch; r++) {
+        PCB_LAUNCH(ctx, huge_advance_kernel, 1, 1, 0, h);
+        PCB_LAUNCH(ctx, huge_reserve_kernel, grid_for((size_t)W * 32, HUGE_BLOCK), HUGE_BLOCK, 0, c, h);
+        PCB_LAUNCH(ctx, huge_exec_kernel, pool.grid(), HUGE_BLOCK, 0, c, h, pool.pool, 0, bigpool.pool.cap ? 1 : 0);
+        if (bigpool.pool.cap) PCB_LAUNCH(ctx, huge_exec_kernel, bigpool.grid(), HUGE_BLOCK, 0, c, h, bigpool.pool, 1, 1);
+      }
+      read_counters();
+      rounds = hk.round;
+      if (hk.done) break;
+      if (hk.max_need > bigpool.pool.cap) size_big(hk.max_need);       // rows waiting for more scratch than any warp has
+      // (the earliest pending row wins every round, or waits at most one batch for the big scratch)
+      if (rounds > 2 * (int64_t)hk.total + 4 * batch) throw Error(PCB_E_STATE, "giant tier: the main loop makes no progress");
+    }
+  tr.lap("rounds");
+
+  // ---- consensus
+  PCB_CUDA(cudaMemsetAsync(&k.p->max_need, 0, sizeof(int32_t), ctx->stream));
+  PCB_LAUNCH(ctx, huge_reads_kernel, grid_for(R, 256), 256, 0, c, h, 1);
+  PCB_LAUNCH(ctx, huge_head_kernel, pool.grid(), HUGE_BLOCK, 0, c, h, pool.pool, 0);
+  read_counters();
+  if (hk.n_big > 0) {
+    if (hk.max_need > bigpool.pool.cap) size_big(hk.max_need);
+    PCB_LAUNCH(ctx, huge_head_kernel, bigpool.grid(), HUGE_BLOCK, 0, c, h, bigpool.pool, 1);
+  }
+  PCB_LAUNCH(ctx, huge_tally_kernel, 1, 1, 0, h, c.status);
+  PCB_CUDA(cudaStreamSynchronize(ctx->stream));          // the scratch above is released when this returns
+  ctx->stats[PCB_STAT_HUGE_ROUNDS] = rounds;
+  ctx->stats[PCB_STAT_HUGE_COMPONENTS] = n_huge;
+  tr.lap("consensus");
 }
 
 }  // namespace
@@ -563,24 +833,26 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
 
   // ---- visiting pairs per component
   DevBuf<int32_t> cpair_ptr(ctx, (size_t)U + 2), cq(ctx, (size_t)P), cr(ctx, (size_t)P), ce(ctx, (size_t)P);
-  {
+  PCB_CUDA(cudaMemsetAsync(cpair_ptr.p, 0, sizeof(int32_t), ctx->stream));            // (a shard that owns no component)
+  if (in.pairs_sorted || P == 0) {
+    const size_t ld = (size_t)U + 1;
+    DevBuf<uint32_t> g(ctx, ld * (size_t)(in.max_diff > 0 ? in.max_diff : 1));
+    PCB_LAUNCH(ctx, visit_cnt_kernel, grid_for(ld, 256), 256, 0, comp_buckets.p, comp_of_b.p, adj_ptr.p, in.pair_ed, U, in.max_diff, g.p);
+    for (int32_t e = 0; e < in.max_diff; e++) exclusive_scan_u32(ctx, g.p + e * ld, g.p + e * ld, ld);
+    PCB_LAUNCH(ctx, visit_fill_kernel, grid_for(U, 256), 256, 0, comp_buckets.p, comp_of_b.p, comp_ptr.p, counters.p, adj_ptr.p, in.pair_r,
+               in.pair_ed, U, in.max_diff, g.p, cpair_ptr.p, cq.p, cr.p, ce.p);
+  } else {
     DevBuf<uint32_t> cnt(ctx, 4 * ((size_t)U + 1) + 1);
     PCB_CUDA(cudaMemsetAsync(cnt.p, 0, (4 * ((size_t)U + 1) + 1) * sizeof(uint32_t), ctx->stream));
-    if (P > 0)
-      PCB_LAUNCH(ctx, visit_count_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_ed, P, in.max_diff, comp_of_b.p, cnt.p, counters.p);
+    PCB_LAUNCH(ctx, visit_count_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_ed, P, in.max_diff, comp_of_b.p, cnt.p, counters.p);
     exclusive_scan_u32(ctx, cnt.p, cnt.p, 4 * ((size_t)U + 1) + 1);
-    if (in.pairs_sorted || P == 0) {
-      PCB_LAUNCH(ctx, visit_walk_kernel, grid_for((size_t)U + 1, 128), 128, 0, comp_ptr.p, comp_buckets.p, counters.p, adj_ptr.p, in.pair_r,
-                 in.pair_ed, in.max_diff, cnt.p, cpair_ptr.p, cq.p, cr.p, ce.p);
-    } else {
-      DevBuf<uint64_t> k0(ctx, P), k1(ctx, P);
-      DevBuf<uint32_t> v0(ctx, P), v1(ctx, P);
-      PCB_LAUNCH(ctx, cpair_keys_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_ed, P, comp_of_b.p, U, in.max_diff, k0.p, v0.p);
-      int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, P, bbits + 3);
-      PCB_LAUNCH(ctx, cpair_gather_kernel, grid_for(P, 256), 256, 0, w ? v1.p : v0.p, counters.p, in.pair_q, in.pair_r, in.pair_ed, cq.p,
-                 cr.p, ce.p, P);
-      PCB_LAUNCH(ctx, cpair_ptr_kernel, grid_for((size_t)U + 1, 256), 256, 0, cnt.p, counters.p, cpair_ptr.p);
-    }
+    DevBuf<uint64_t> k0(ctx, P), k1(ctx, P);
+    DevBuf<uint32_t> v0(ctx, P), v1(ctx, P);
+    PCB_LAUNCH(ctx, cpair_keys_kernel, grid_for(P, 256), 256, 0, in.pair_q, in.pair_ed, P, comp_of_b.p, U, in.max_diff, k0.p, v0.p);
+    int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, P, bbits + 3);
+    PCB_LAUNCH(ctx, cpair_gather_kernel, grid_for(P, 256), 256, 0, w ? v1.p : v0.p, counters.p, in.pair_q, in.pair_r, in.pair_ed, cq.p,
+               cr.p, ce.p, P);
+    PCB_LAUNCH(ctx, cpair_ptr_kernel, grid_for((size_t)U + 1, 256), 256, 0, cnt.p, counters.p, cpair_ptr.p);
   }
 
   // ---- what the replay reads
@@ -592,6 +864,7 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
     bor = bor_own.p;
   }
   DevBuf<int32_t> status(ctx, STATUS_N), medium(ctx, (size_t)U + 1), large(ctx, (size_t)U + 1), declined(ctx, (size_t)U + 1), late(ctx, (size_t)U + 1);
+  DevBuf<int32_t> hcomp(ctx, (size_t)U + 1), huge_of_comp(ctx, (size_t)U + 1), comp_reads(ctx, (size_t)U + 1);
   PCB_CUDA(cudaMemsetAsync(status.p, 0, STATUS_N * sizeof(int32_t), ctx->stream));
   MergeCtx c;
   memset(&c, 0, sizeof(c));
@@ -620,19 +893,25 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   c.call_mut = out.call_mut; c.status = status.p;
   c.prm.maxDiff = in.max_diff; c.prm.minQual = in.min_qual; c.prm.minMatches = in.min_matches; c.prm.minJaccard = in.min_jaccard;
   jaccard_thresholds(c.prm);
-  const int32_t force_large = shape != PCB_REPLAY_AUTO ? 1 : 0;
-  DevBuf<int64_t> comp_calls(ctx, (size_t)U + 2);
-  PCB_LAUNCH(ctx, classify_kernel, grid_for((size_t)U + 1, 128), 128, 0, c, force_large, counters.p, medium.p, large.p, comp_calls.p);
+  const int32_t force = shape == PCB_REPLAY_AUTO ? FORCE_NONE : shape == PCB_REPLAY_HUGE ? FORCE_HUGE : FORCE_LARGE;
+  DevBuf<int64_t> comp_calls(ctx, (size_t)U + 2), comp_call_off;
+  PCB_CUDA(cudaMemsetAsync(comp_calls.p, 0, ((size_t)U + 2) * sizeof(int64_t), ctx->stream));
+  PCB_CUDA(cudaMemsetAsync(comp_reads.p, 0, ((size_t)U + 1) * sizeof(int32_t), ctx->stream));
+  PCB_LAUNCH(ctx, comp_stats_kernel, grid_for(U, 256), 256, 0, comp_buckets.p, comp_of_b.p, in.bucket_ptr, in.bucket_reads, in.geno_ptr, U,
+             comp_reads.p, comp_calls.p);
+  PCB_LAUNCH(ctx, classify_kernel, grid_for((size_t)U + 1, 128), 128, 0, c, comp_reads.p, comp_calls.p, force, ctx->huge_reads, counters.p,
+             medium.p, large.p, hcomp.p, huge_of_comp.p);
   if (!in.shard_layout) {                                  // regions in component order
-    exclusive_scan_i64(ctx, comp_calls.p, comp_calls.p, (size_t)U + 1);        // (entries past the last component are never read)
-    c.call_off = comp_calls.p;
+    comp_call_off.alloc(ctx, (size_t)U + 2);
+    exclusive_scan_i64(ctx, comp_calls.p, comp_call_off.p, (size_t)U + 1);     // (entries past the last component are never read)
+    c.call_off = comp_call_off.p;
   }
   // every output starts as "not produced": entries of reads other shards own, the row fields of non-representative reads
   PCB_LAUNCH(ctx, init_outputs_kernel, grid_for((size_t)(R > nnz ? R : nnz) + 1, 256), 256, 0, R, nnz, out);
   int32_t h_cnt[CNT_N];                                                 // the one round trip of the preprocessing
   PCB_CUDA(cudaMemcpyAsync(h_cnt, counters.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, ctx->stream));
   PCB_CUDA(cudaStreamSynchronize(ctx->stream));
-  const int32_t n_comp = h_cnt[CNT_COMPS], n_medium = h_cnt[CNT_MEDIUM], n_large = h_cnt[CNT_LARGE];
+  const int32_t n_comp = h_cnt[CNT_COMPS], n_medium = h_cnt[CNT_MEDIUM], n_large = h_cnt[CNT_LARGE], n_huge = h_cnt[CNT_HUGE];
   ctx->stats[PCB_STAT_COMPONENTS] = n_comp;
   stage_end(ctx, PCB_STAT_T_PREP_NS);
 
@@ -654,7 +933,9 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
     PCB_LAUNCH(ctx, component_kernel_medium, medium_grid / 4u, 32, sizeof(MediumSmem), c, declined.p, counters.p + CNT_DECLINED);
   }
   if (n_medium > 0) PCB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_copied, 0));
-  run_large(ctx, c, large.p, n_large, R, shape);
+  ClusterArrays cl;
+  run_large(ctx, c, cl, comp_reads.p, comp_calls.p, large.p, n_large, R, shape);
+  run_huge(ctx, c, cl, comp_of_b.p, huge_of_comp.p, hcomp.p, n_huge, R, U);
   stage_end(ctx, PCB_STAT_T_REPLAY_NS);
 
   int32_t h_status[STATUS_N], h_late = 0;
@@ -662,7 +943,7 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   PCB_CUDA(cudaMemcpyAsync(&h_late, counters.p + CNT_LATE, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
   PCB_CUDA(cudaStreamSynchronize(ctx->stream));
   if (h_late > 0) {                       // <= 32 reads, but too many calls or rows for either warp kernel's shared memory
-    run_large(ctx, c, late.p, h_late, R, PCB_REPLAY_WARP);
+    run_large(ctx, c, cl, comp_reads.p, comp_calls.p, late.p, h_late, R, PCB_REPLAY_WARP);
     PCB_CUDA(cudaMemcpyAsync(h_status, status.p, sizeof(h_status), cudaMemcpyDeviceToHost, ctx->stream));
     PCB_CUDA(cudaStreamSynchronize(ctx->stream));
   }

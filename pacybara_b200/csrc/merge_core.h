@@ -96,6 +96,7 @@ struct MergeCtx {
   int64_t *row_key, *row_call_off;
   int32_t *call_mut;                                 // [nnz]
   int32_t *status;                                   // [4]: error code, detail, #links, #tests
+  int32_t *cell_nnz;                                 // optional (merge_huge.cuh): genotype entries per cluster, kept at its root slot
   MergeParams prm;
 };
 

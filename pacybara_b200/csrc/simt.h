@@ -12,6 +12,7 @@
 
 #if defined(__CUDACC__)
 #define SIMT_FN __device__ __forceinline__
+#define SIMT_NOINLINE __device__ __noinline__
 
 namespace simt {
 SIMT_FN uint32_t ballot(uint32_t mask, bool p) { return __ballot_sync(mask, p); }
@@ -40,6 +41,8 @@ SIMT_FN T ld_stream(const T *p) {
   return out;
 }
 SIMT_FN unsigned long long atomic_add_u64(unsigned long long *p, unsigned long long v) { return atomicAdd(p, v); }
+SIMT_FN unsigned long long atomic_min_u64(unsigned long long *p, unsigned long long v) { return atomicMin(p, v); }
+SIMT_FN int32_t atomic_max(int32_t *p, int32_t v) { return atomicMax(p, v); }
 // sum over the four bytes of max(0, a_byte - b_byte)
 SIMT_FN uint32_t surplus4(uint32_t a, uint32_t b) { return __vsadu4(__vsubus4(a, b), 0u); }
 }  // namespace simt
@@ -47,6 +50,7 @@ SIMT_FN uint32_t surplus4(uint32_t a, uint32_t b) { return __vsadu4(__vsubus4(a,
 #else
 #include <math.h>
 #define SIMT_FN inline
+#define SIMT_NOINLINE inline
 
 namespace simt {
 // implemented by tests/host_emul/simt_emul.cpp; `lane` is implicit (the coroutine that is running)
@@ -69,6 +73,8 @@ inline float sqrt_f(float x) { return sqrtf(x); }
 template <typename T> inline T ld_stream(const T *p) { return *p; }
 inline uint32_t brev(uint32_t x) { uint32_t r = 0; for (int i = 0; i < 32; i++) r |= ((x >> i) & 1u) << (31 - i); return r; }
 inline unsigned long long atomic_add_u64(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+inline unsigned long long atomic_min_u64(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; if (v < o) *p = v; return o; }
+inline int32_t atomic_max(int32_t *p, int32_t v) { int32_t o = *p; if (v > o) *p = v; return o; }
 inline uint32_t surplus4(uint32_t a, uint32_t b) {
   uint32_t s = 0;
   for (int i = 0; i < 4; i++) { uint32_t x = (a >> (8 * i)) & 0xFFu, y = (b >> (8 * i)) & 0xFFu; if (x > y) s += x - y; }

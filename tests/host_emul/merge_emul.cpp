@@ -12,6 +12,7 @@
 
 #include "merge_core.h"
 #include "merge_small.cuh"
+#include "merge_huge.cuh"
 #include "simt_emul.h"
 
 using namespace pcb;
@@ -19,6 +20,100 @@ using namespace pcb;
 static int32_t uf_find(std::vector<int32_t> &p, int32_t x) {
   while (p[x] != x) { p[x] = p[p[x]]; x = p[x]; }
   return x;
+}
+
+// ---- the giant tier (merge_huge.cuh) with the host side of csrc/merge.cu (run_huge) restated: every "launch" runs its
+// units one after the other on an emulated warp, in shuffled order
+namespace {
+struct Scratch {
+  std::vector<GenoSlot> slots;
+  std::vector<int32_t> lists;
+  int32_t cap = 0;
+  void make(int32_t c) { cap = c; slots.assign((size_t)c, GenoSlot{0, 0, 0, 0, 0, 0}); lists.assign(8 + 2 * (size_t)c, 0); }
+  MergeState state(const MergeCtx &c) {
+    MergeState st;
+    st.r0 = 0; st.rd_slot = c.rd_slot; st.rd_next = c.rd_next; st.sl_parent = c.sl_parent; st.sl_head = c.sl_head;
+    st.sl_tail = c.sl_tail; st.sl_size = c.sl_size; st.sl_key = c.sl_key;
+    st.slots = slots.data(); st.slot_mask = cap - 1; st.lists = lists.data(); st.list_cap = cap;
+    return st;
+  }
+};
+int32_t pow2_at_least(int64_t v) { int64_t c = 16; while (c < v) c <<= 1; return (int32_t)c; }
+std::vector<int32_t> shuffled(int32_t n, uint32_t &rng) {
+  std::vector<int32_t> o(n);
+  std::iota(o.begin(), o.end(), 0);
+  for (int32_t i = n - 1; i > 0; i--) { rng = rng * 1664525u + 1013904223u; std::swap(o[i], o[(rng >> 8) % (uint32_t)(i + 1)]); }
+  return o;
+}
+}  // namespace
+
+static void emul_huge(MergeCtx &c, const std::vector<int32_t> &mine, int32_t n_comp, int32_t R, int32_t U, int32_t cap, int32_t W, unsigned seed) {
+  uint32_t rng = seed * 2654435761u + 99u;
+  const int32_t n_huge = (int32_t)mine.size();
+  if (n_huge == 0) return;
+  std::vector<int32_t> comp_of_b(U, -1), huge_of_comp(n_comp, -1), hcomp(mine), hrow_ptr(n_huge + 1, 0), cell_nnz(R, 0);
+  for (int32_t h = 0; h < n_huge; h++) {
+    const int32_t comp = mine[h];
+    huge_of_comp[comp] = h;
+    for (int32_t i = c.comp_ptr[comp]; i < c.comp_ptr[comp + 1]; i++) comp_of_b[c.comp_buckets[i]] = comp;
+    hrow_ptr[h + 1] = hrow_ptr[h] + (c.cpair_ptr[comp + 1] - c.cpair_ptr[comp]);
+  }
+  std::vector<unsigned long long> resv(R, ~0ull), cursor(n_huge, 0ull);
+  std::vector<int32_t> win(W), carry0(W), carry1(W), heavy(W), heads(R), big(std::max(R, U));
+  HugeCounters k;
+  memset(&k, 0, sizeof(k));
+  k.total = hrow_ptr[n_huge];
+  HugeDev h;
+  h.resv = resv.data(); h.comp_of_b = comp_of_b.data(); h.huge_of_comp = huge_of_comp.data(); h.hcomp = hcomp.data(); h.hrow_ptr = hrow_ptr.data();
+  h.cursor = cursor.data(); h.n_huge = n_huge; h.W = W; h.win = win.data(); h.carry[0] = carry0.data(); h.carry[1] = carry1.data();
+  h.heavy = heavy.data(); h.heads = heads.data(); h.big = big.data(); h.k = &k;
+  c.cell_nnz = cell_nnz.data();
+  Scratch ord, bigs;
+  ord.make(cap);
+  // seed step
+  std::vector<int32_t> seedl;
+  for (int32_t comp : mine)
+    for (int32_t i = c.comp_ptr[comp]; i < c.comp_ptr[comp + 1]; i++) {
+      const int32_t b = c.comp_buckets[i];
+      if (c.bucket_ptr[b + 1] - c.bucket_ptr[b] >= 2) seedl.push_back(b);
+    }
+  for (int32_t i : shuffled((int32_t)seedl.size(), rng))
+    simt_emul::run_warp([&](int lane) { huge_seed_item(c, ord.state(c), h, cap, false, seedl[i], lane); }, rng + (unsigned)i);
+  if (k.n_big) {
+    bigs.make(pow2_at_least(k.max_need));
+    for (int32_t i : shuffled(k.n_big, rng))
+      simt_emul::run_warp([&](int lane) { huge_seed_item(c, bigs.state(c), h, bigs.cap, true, big[i], lane); }, rng + (unsigned)i);
+  }
+  k.n_big = 0; k.max_need = 0;
+  for (int32_t r = 0; r < R; r++)
+    if (comp_of_b[c.bucket_of_read[r]] >= 0) huge_count_read(c, ord.state(c), r);
+  // main loop
+  for (int64_t round = 0; k.total > 0; round++) {
+    huge_advance(h);
+    if (k.done) break;
+    for (int32_t idx : shuffled(k.n_window, rng))
+      simt_emul::run_warp([&](int lane) { huge_reserve_item(c, ord.state(c), h, idx, lane); }, rng + (unsigned)idx);
+    for (int32_t idx : shuffled(k.n_window, rng))
+      simt_emul::run_warp([&](int lane) { huge_row_item(c, ord.state(c), h, cap, bigs.cap > 0, idx, lane); }, rng + (unsigned)idx);
+    for (int32_t idx : shuffled(k.n_heavy, rng))
+      simt_emul::run_warp([&](int lane) { huge_heavy_item(c, bigs.state(c), h, bigs.cap, idx, lane); }, rng + (unsigned)idx);
+    if (round % 3 == 2 && k.max_need > bigs.cap) bigs.make(pow2_at_least(k.max_need));
+  }
+  // consensus
+  k.max_need = 0;
+  for (int32_t r : shuffled(R, rng)) {
+    const int32_t comp = comp_of_b[c.bucket_of_read[r]];
+    if (comp >= 0) huge_finish_read(c, ord.state(c), h, huge_of_comp[comp], r);
+  }
+  for (int32_t i : shuffled(k.n_heads, rng))
+    simt_emul::run_warp([&](int lane) { huge_head_item(c, ord.state(c), h, cap, false, heads[i], lane); }, rng + (unsigned)i);
+  if (k.n_big) {
+    if (k.max_need > bigs.cap) bigs.make(pow2_at_least(k.max_need));
+    for (int32_t i : shuffled(k.n_big, rng))
+      simt_emul::run_warp([&](int lane) { huge_head_item(c, bigs.state(c), h, bigs.cap, true, big[i], lane); }, rng + (unsigned)i);
+  }
+  c.status[2] += k.links; c.status[3] += k.tests;
+  c.cell_nnz = nullptr;
 }
 
 extern "C" int emul_merge(int32_t R, int32_t U, const int32_t *bucket_ptr, const int32_t *bucket_reads,
@@ -30,7 +125,11 @@ extern "C" int emul_merge(int32_t R, int32_t U, const int32_t *bucket_ptr, const
                           int32_t *read_root, int32_t *read_pos, int32_t *row_size, int64_t *row_key,
                           int32_t *row_bc, int32_t *row_up, int64_t *row_call_off, int32_t *row_call_n,
                           int32_t *call_mut, int32_t *status,
-                          const uint64_t *planes, const int32_t *blen, int32_t compute_k, int32_t wide, int32_t use_small) {
+                          const uint64_t *planes, const int32_t *blen, int32_t compute_k, int32_t wide, int32_t use_small,
+                          int32_t mode, int32_t huge_cap, int32_t huge_window) {
+  // mode 2: every component through process_component_warp() on an emulated warp (merge_warp.cuh); mode 3: every component
+  // through the giant tier (merge_huge.cuh) -- units of a "launch" in shuffled order, scratch of huge_cap slots, windows of
+  // huge_window rows, the big scratch sized by the "host" between batches of 3 rounds, as csrc/merge.cu does.
   // use_small != 0: every component goes through process_component_small() on an emulated warp first (use_small =
   // lane-order seed), and through process_component() only if that declines.  status[1] returns how many it took.
   std::vector<int32_t> bucket_of_read(R);
@@ -124,10 +223,20 @@ extern "C" int emul_merge(int32_t R, int32_t U, const int32_t *bucket_ptr, const
   jaccard_thresholds(c.prm);
   int32_t n_small = 0;
   int64_t call_cursor = 0;
-  if (use_small) { c.call_off = nullptr; c.call_cursor = &call_cursor; }     // regions from the shared cursor, like csrc/merge.cu
+  if (use_small && mode != 3) { c.call_off = nullptr; c.call_cursor = &call_cursor; }     // regions from the shared cursor, like csrc/merge.cu
   static SmallSmem smem;
-  for (int32_t comp = 0; comp < n_comp; comp++) {
-    if (label[comp_buckets[comp_ptr[comp]]] % shard_count != shard_rank) continue;
+  std::vector<int32_t> mine;
+  for (int32_t comp = 0; comp < n_comp; comp++)
+    if (label[comp_buckets[comp_ptr[comp]]] % shard_count == shard_rank) mine.push_back(comp);
+  if (mode == 3) {
+    emul_huge(c, mine, n_comp, R, U, huge_cap, huge_window, (unsigned)use_small + 17u);
+    return n_comp;
+  }
+  for (int32_t comp : mine) {
+    if (mode == 2) {
+      simt_emul::run_warp([&](int lane) { process_component_warp(c, global_state(c, comp), comp, lane); }, (unsigned)(7 + comp));
+      continue;
+    }
     if (use_small) {
       int rc[32];
       simt_emul::run_warp([&](int lane) { rc[lane] = process_component_small(c, comp, lane, &smem, c.prm.jthr, &c.status[2], 1 << 30, 1 << 30); }, (unsigned)(use_small + comp));

@@ -363,7 +363,7 @@ def _rows_equal(a, b):
         assert np.array_equal(getattr(a, f), getattr(b, f)), f
 
 
-@pytest.mark.parametrize("shape", ["thread", "warp", "auto"])
+@pytest.mark.parametrize("shape", ["thread", "warp", "auto", "huge"])
 def test_many_small_random_libraries_both_replay_shapes(ctx, shape, monkeypatch):
     """120 tiny libraries with extreme settings (dense neighbours, collisions, short barcodes, d = 1..3,
     minMatches 1..3, minJaccard 0.1..0.9, low/high minQual, skewed clone sizes): the fused path must give the
@@ -371,6 +371,9 @@ def test_many_small_random_libraries_both_replay_shapes(ctx, shape, monkeypatch)
     from oracle import orc
     from pacybara_b200 import pipeline
     monkeypatch.setenv("PCB_REPLAY", shape)
+    if shape == "huge":                      # giant tier with scratch and windows so small that rows wait and are carried over
+        monkeypatch.setenv("PCB_HUGE_CAP", "32")
+        monkeypatch.setenv("PCB_HUGE_WINDOW", "5")
     rng = np.random.default_rng(2024)
     n_alignment = 0
     for case in range(120):
@@ -406,7 +409,7 @@ def test_big_buckets_with_collisions(ctx):
     of several hundred reads that do NOT collapse into one seed cluster (the quadratic case of the seed step).
     (Sized for the oracle: its literal restatement is quadratic in the product of two adjacent bucket sizes.)"""
     lib = synth.make_library(n_clones=24, n_reads=3000, p_err=0.004, p_near=0.2, p_collide=0.5, skew=0.5, seed=77)
-    for shape in ("thread", "warp", "auto"):
+    for shape in ("thread", "warp", "auto", "huge"):
         os.environ["PCB_REPLAY"] = shape
         try:
             _fused_vs_oracle(ctx, lib, max_diff=2)

@@ -41,7 +41,7 @@ def test_scaled_configs_against_the_complete_oracle(ctx, cfg, scale):
     ra, names = pipeline.arrays_from_library(lib, ctx)
     p = dict(max_diff=lib.params["max_diff"], min_qual=lib.params["min_qual"], min_jaccard=0.2, min_matches=1)
     want = canon.canon_table(util.oracle_table_for_library(lib, ra, names, **p))
-    for shape in ("thread", "warp", None):
+    for shape in ("thread", "warp", "huge", None):
         if shape:
             os.environ["PCB_REPLAY"] = shape
         try:
@@ -51,3 +51,20 @@ def test_scaled_configs_against_the_complete_oracle(ctx, cfg, scale):
                 assert got == want, (shape, full, canon.diff_tables(got, want))
         finally:
             os.environ.pop("PCB_REPLAY", None)
+
+
+def test_dense_barcode_space_giant_component(ctx):
+    """templates/pacybara_parameters.txt:13 -- a 25-nt SWSW... alphabet: at 10^6 reads most buckets hang together in one
+    component of the link graph.  It is replayed by the whole device (csrc/merge_huge.cuh: rounds of deterministic
+    reservations); the rows must be those of the oracle's sequential restatement, with the default knobs and with a
+    scratch / window small enough that rows wait for the big scratch and are carried from round to round."""
+    lib = synth.make_config("dense", seed=1, scale=0.1)
+    res = util.check_full_size_against_oracle_merge(ctx, lib)
+    assert ctx.stat("huge_components") >= 1 and ctx.stat("huge_rounds") >= 2
+    assert res["reads"] == lib.n_reads
+    os.environ.update(PCB_HUGE_CAP="128", PCB_HUGE_WINDOW="4096", PCB_HUGE_READS="64")
+    try:
+        util.check_full_size_against_oracle_merge(ctx, lib, n_spot=100)
+    finally:
+        for k in ("PCB_HUGE_CAP", "PCB_HUGE_WINDOW", "PCB_HUGE_READS"):
+            os.environ.pop(k, None)

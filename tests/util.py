@@ -85,7 +85,7 @@ def emul_lib():
         hdr = os.path.join(os.path.dirname(here), "..", "pacybara_b200", "csrc", "merge_core.h")
         csrc = os.path.dirname(hdr)
         deps = [src, hdr, os.path.join(here, "simt_emul.cpp"), os.path.join(here, "simt_emul.h")] + \
-               [os.path.join(csrc, f) for f in ("merge_small.cuh", "simt.h", "myers.cuh")]
+               [os.path.join(csrc, f) for f in ("merge_small.cuh", "merge_warp.cuh", "merge_huge.cuh", "simt.h", "myers.cuh")]
         if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
             cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
             subprocess.run([cxx, "-O1", "-std=c++17", "-shared", "-fPIC", "-x", "c++", "-I", csrc, "-I", here, "-o", so, src,
@@ -115,7 +115,9 @@ def emul_merge_small(p: hostdata.MergeProblem, pairs: hostdata.PairList, planes=
 
 
 def emul_merge(p: hostdata.MergeProblem, pairs: hostdata.PairList, shard=(0, 1), planes=None, blen=None,
-               compute_k=-1, use_small=0) -> Dict[str, np.ndarray]:
+               compute_k=-1, use_small=0, mode=0, huge_cap=64, huge_window=16) -> Dict[str, np.ndarray]:
+    """mode 0: process_component() per component (with use_small: the small-component warp kernel first); 2: the generic
+    warp replay (merge_warp.cuh) on an emulated warp; 3: the giant tier (merge_huge.cuh), use_small seeds the shuffles."""
     import ctypes as C
     R = p.n_reads
     nnz = int(p.geno_ptr[-1])
@@ -135,7 +137,7 @@ def emul_merge(p: hostdata.MergeProblem, pairs: hostdata.PairList, shard=(0, 1),
                               *[ptr(out[k]) for k, _ in hostdata.MERGE_OUTPUTS], ptr(out["call_mut"]), ptr(status),
                               ptr(planes), ptr(None if blen is None else np.ascontiguousarray(blen, dtype=np.int32)),
                               C.c_int32(compute_k), C.c_int32(0 if blen is None or int(np.max(blen)) <= 32 else 1),
-                              C.c_int32(use_small))
+                              C.c_int32(use_small), C.c_int32(mode), C.c_int32(huge_cap), C.c_int32(huge_window))
     if n < 0:
         raise RuntimeError(f"emul_merge: {n} (the small-component path needs component-order numbering / uniform lanes)")
     out = {k: v[:R] if k != "call_mut" else v[:nnz] for k, v in out.items()}
