@@ -80,6 +80,10 @@ class Context:
         self._check(self.lib.pcb_set_option(self.h, _lib.OPT_REPLAY_SHAPE, _lib.REPLAY_SHAPES[shape]))
         if os.environ.get("PCB_TRACE"):
             self._check(self.lib.pcb_set_option(self.h, 1, 1))
+        staged = 1 if os.environ.get("PCB_PROBE_STAGING") else 0
+        if getattr(self, "_staging_set", 0) != staged:
+            self._check(self.lib.pcb_set_option(self.h, _lib.OPT_PROBE_STAGING, staged))
+            self._staging_set = staged
         # giant-tier knobs: environment > set_huge() > the library's defaults, applied per call like the shape
         for env, opt, default in (("PCB_HUGE_READS", _lib.OPT_HUGE_READS, 256), ("PCB_HUGE_CAP", _lib.OPT_HUGE_CAP, 2048),
                                   ("PCB_HUGE_WINDOW", _lib.OPT_HUGE_WINDOW, 32768)):
@@ -177,6 +181,7 @@ class Context:
         if _is_dev(seq):
             _torch()
         mem = self._kind(seq, length)
+        self.set_replay_shape()
         U, stride = int(seq.shape[0]), int(seq.shape[1])
         lo, hi = (0, U) if q_range is None else q_range
         tlo, thi = (0, U) if t_range is None else t_range

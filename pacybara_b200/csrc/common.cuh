@@ -58,6 +58,7 @@ struct pcb_ctx {
   int huge_cap = 2048;                     // PCB_OPT_HUGE_CAP: slots of one warp's scratch table in that tier
   int huge_window = 32768;                 // PCB_OPT_HUGE_WINDOW: rows per round
   int huge_warps_per_sm = 24;
+  int probe_staging = 0;                   // PCB_OPT_PROBE_STAGING: long bins through shared memory by TMA bulk copies (probe.cuh)
   bool medium_attr_set = false;            // the medium replay kernel's shared-memory opt-in (merge.cu)
   int trace = 0;                           // pcb_set_option(PCB_OPT_TRACE): host-side lap times on stderr
   // Workspace arena: the temporaries of one call are carved out of one long-lived allocation with a bump pointer and

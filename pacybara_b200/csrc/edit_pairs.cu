@@ -200,7 +200,13 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(const ulonglong
 // that each carry their own pair through the recurrence, Ukkonen cut-off at checkpoints.
 __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel_lanes(ProbeArgs a) {
   __shared__ ProbeQueue queue[PROBE_WARPS];
-  probe_warp(a, threadIdx.x & 31, &queue[threadIdx.x >> 5]);
+  probe_warp<false>(a, threadIdx.x & 31, &queue[threadIdx.x >> 5], nullptr);
+}
+// the same with long bins staged through shared memory by TMA bulk copies (PCB_OPT_PROBE_STAGING; probe.cuh)
+__global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel_staged(ProbeArgs a) {
+  __shared__ ProbeQueue queue[PROBE_WARPS];
+  __shared__ ProbeStage stage[PROBE_WARPS];
+  probe_warp<true>(a, threadIdx.x & 31, &queue[threadIdx.x >> 5], &stage[threadIdx.x >> 5]);
 }
 
 __global__ void sketch_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int32_t U, uint32_t *__restrict__ sketch) {
@@ -358,7 +364,7 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
     const SeedGeom &g = idx[t].g;
     DevBuf<uint32_t> cursor(ctx, (size_t)g.nbins + 1);
     idx[t].bin_off.alloc(ctx, (size_t)g.nbins + 1);
-    if (lanes) idx[t].ent8.alloc(ctx, (size_t)T * g.npos); else idx[t].ent.alloc(ctx, (size_t)T * g.npos);
+    if (lanes) idx[t].ent8.alloc(ctx, (size_t)T * g.npos + 2); else idx[t].ent.alloc(ctx, (size_t)T * g.npos);
     PCB_CUDA(cudaMemsetAsync(idx[t].bin_off.p, 0, ((size_t)g.nbins + 1) * sizeof(uint32_t), ctx->stream));
     size_t n_slots = (size_t)T * g.npos;
     PCB_LAUNCH(ctx, seed_count_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, t_begin, T, g, idx[t].bin_off.p);
@@ -404,7 +410,8 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
         a.planes = (const Planes16 *)bc.planes.p; a.len = bc.len.p; a.sketch = sketch.p; a.q_begin = q_begin; a.q_end = q_end; a.g = g;
         a.bin_off = idx[t].bin_off.p; a.ent = idx[t].ent8.p; a.hit_key = hk0.p; a.hit_d = hv0.p; a.cap = cap; a.key_shift = key_shift;
         a.counters = counters.p; a.len_lo = idx[t].len_lo; a.len_hi = idx[t].len_hi;
-        PCB_LAUNCH(ctx, probe_kernel_lanes, n_cta, PROBE_WARPS * 32, 0, a);
+        if (ctx->probe_staging) PCB_LAUNCH(ctx, probe_kernel_staged, n_cta, PROBE_WARPS * 32, 0, a);
+        else PCB_LAUNCH(ctx, probe_kernel_lanes, n_cta, PROBE_WARPS * 32, 0, a);
       }
       else if (wide && self) launch(probe_kernel<true, true>, n_cta, idx[t]);
       else if (wide) launch(probe_kernel<true, false>, n_cta, idx[t]);

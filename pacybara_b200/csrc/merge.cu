@@ -339,9 +339,9 @@ __global__ void __launch_bounds__(SMALL_BLOCK) component_kernel_small(MergeCtx c
                                                                       int32_t *__restrict__ declined, int32_t *__restrict__ late) {
   __shared__ SmallSmem sm_all[SMALL_BLOCK / 32];
   __shared__ int32_t jthr[33];
-  __shared__ int32_t tally[2];
+  __shared__ int32_t tally[3];                       // links, tests, warps that are done
   if (threadIdx.x < 33) jthr[threadIdx.x] = c.prm.jthr[threadIdx.x];
-  if (threadIdx.x < 2) tally[threadIdx.x] = 0;
+  if (threadIdx.x < 3) tally[threadIdx.x] = 0;
   __syncthreads();
   const int32_t comp = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
@@ -350,9 +350,17 @@ __global__ void __launch_bounds__(SMALL_BLOCK) component_kernel_small(MergeCtx c
     if (lane == 0 && rc == 1) declined[atomicAdd(&counters[CNT_DECLINED], 1)] = comp;
     if (lane == 0 && rc == 2) late[atomicAdd(&counters[CNT_LATE], 1)] = comp;
   }
-  __syncthreads();
-  // links / tests: one atomic per block and counter, spread over 32 slots (status[4 + 2 * slot + which])
-  if (threadIdx.x < 2 && tally[threadIdx.x]) atomicAdd(&c.status[4 + 2 * (blockIdx.x & 31) + threadIdx.x], tally[threadIdx.x]);
+  // links / tests: one atomic per block and counter, spread over 32 slots (status[4 + 2 * slot + which]), added by
+  // whichever warp finishes last -- no barrier: a warp that is done leaves, its slot goes to the next block
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence_block();
+    if (atomicAdd(&tally[2], 1) == SMALL_BLOCK / 32 - 1) {
+      const int32_t links = atomicAdd(&tally[0], 0), tests = atomicAdd(&tally[1], 0);
+      if (links) atomicAdd(&c.status[4 + 2 * (blockIdx.x & 31)], links);
+      if (tests) atomicAdd(&c.status[5 + 2 * (blockIdx.x & 31)], tests);
+    }
+  }
 }
 
 // The generic warp replay (merge_warp.cuh) on a LOCAL copy of one component: reads, calls, buckets and visiting pairs

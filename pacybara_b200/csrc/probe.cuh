@@ -63,6 +63,17 @@ struct ProbeQueue {
   int32_t qi[PROBE_QUEUE], tj[PROBE_QUEUE];     // query, target (bit 31 of tj: run the recurrence over the reversed strings)
 };
 
+// Staging of long bins (the north star's "candidate barcodes staged through shared memory, TMA bulk copies where the
+// bucket is large"): when the warp walks bins together, their entries are fetched PROBE_STAGE entries at a time by
+// cp.async.bulk into one of two buffers (completion on an mbarrier), the next chunk in flight while the lanes filter
+// the current one.  A compile-time variant of probe_warp, measured against the direct streaming loads
+// (profiles/r02k_probe_staging.md).
+constexpr int PROBE_STAGE = 256;   // entries per chunk (2 KB)
+struct alignas(16) ProbeStage {
+  SeedEnt ent[2][PROBE_STAGE];
+  uint64_t bar[2];
+};
+
 PCB_HD uint32_t barcode_sketch(uint32_t L, uint32_t H, int32_t n) {
   return ((uint32_t)n << 24) | ((uint32_t)popc32(L & H) << 16) | ((uint32_t)popc32(~L & H) << 8) | (uint32_t)popc32(L & ~H);
 }
@@ -72,7 +83,8 @@ SIMT_FN uint32_t sketch_counts(uint32_t sk) {
   return (n - nc - ng - nt) | ((sk & 0xFFFFFFu) << 8);
 }
 
-SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu) {
+template <bool STAGED>
+SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu, ProbeStage *stg) {
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t lt = (1u << lane) - 1u;
   const SeedGeom g = a.g;
@@ -92,6 +104,30 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu) {
   int coop_p = -1;
   uint32_t c_at = 0, c_hi = 0, c_counts = 0, c_rev = 0;
   int32_t c_qi = 0, c_qm = 0;
+  // staged walk: the chunk generator (bins of the block's probes, in lane order) and the two buffers
+  uint32_t g_left = 0, g_at = 0, g_hi = 0, g_lo = 0;
+  int g_p = 0, cur = 0;
+  uint32_t s_base[2] = {0, 0}, s_n[2] = {0, 0}, s_lo[2] = {0, 0}, s_hi[2] = {0, 0}, s_phase = 0, s_off = 0;
+  int s_p[2] = {-1, -1};
+  if (STAGED) {
+    if (lane == 0) { simt::bar_init(&stg->bar[0], 1); simt::bar_init(&stg->bar[1], 1); }
+    simt::sync(FULL);
+  }
+  // next chunk of the bins into buffer b (uniform; lane 0 issues the copy); s_p[b] = -1 when the bins are used up
+  auto fill = [&](int b) {
+    if (g_at >= g_hi) {
+      if (g_left == 0u) { s_p[b] = -1; return; }
+      g_p = simt::ffs(g_left) - 1;
+      g_left &= g_left - 1u;
+      g_lo = simt::shfl(FULL, lo, g_p); g_hi = simt::shfl(FULL, hi, g_p);
+      g_at = g_lo & ~1u;                                   // 16-byte aligned source
+    }
+    uint32_t n = ((g_hi - g_at) + 1u) & ~1u;               // 16-byte multiple (the index is padded by one entry)
+    if (n > (uint32_t)PROBE_STAGE) n = PROBE_STAGE;
+    if (lane == 0) simt::bulk_load(stg->ent[b], &a.ent[g_at], n * (uint32_t)sizeof(SeedEnt), &stg->bar[b]);
+    s_base[b] = g_at; s_n[b] = n; s_lo[b] = g_lo; s_hi[b] = g_hi; s_p[b] = g_p;
+    g_at += n;
+  };
   // my pair
   bool active = false;
   uint32_t Pv = 0, Mv = 0, rl = 0, rh = 0, pL = 0, pH = 0;
@@ -127,6 +163,11 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu) {
         // short bins: every lane walks its own
         mode = simt::reduce_add(FULL, (int32_t)(hi - lo)) >= 32 * 12 ? 2 : 1;
         coop_p = -1; c_at = c_hi = 0;
+        if (STAGED && mode == 2) {
+          g_left = simt::ballot(FULL, lo < hi); g_at = g_hi = 0;
+          cur = 0; s_off = 0;
+          fill(0); fill(1);
+        }
         continue;
       }
       bool keep = false;
@@ -150,6 +191,38 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu) {
           }
         }
         kq = qi; krev = qrev;
+      } else if (STAGED) {
+        if (s_p[cur] < 0) { mode = 0; continue; }            // every bin of the block has been walked
+        if (coop_p != s_p[cur]) {                            // (the probe of this chunk: its query and filters)
+          coop_p = s_p[cur];
+          c_qi = simt::shfl(FULL, qi, coop_p); c_qm = simt::shfl(FULL, qm, coop_p);
+          c_counts = simt::shfl(FULL, qcounts, coop_p); c_rev = simt::shfl(FULL, qrev, coop_p);
+        }
+        if (s_off == 0) simt::bar_wait(&stg->bar[cur], (s_phase >> cur) & 1u);
+        const uint32_t e = s_base[cur] + s_off + (uint32_t)lane;
+        if (s_off + (uint32_t)lane < s_n[cur] && e >= s_lo[cur] && e < s_hi[cur]) {
+          const SeedEnt en = stg->ent[cur][s_off + (uint32_t)lane];
+          j = en.j;
+          n_walked++;
+          if (j != c_qi && is_query_side(c_qi, j)) {
+            n_sided++;
+            const uint32_t sk = en.sk;
+            const int32_t dl = c_qm - (int32_t)(sk >> 24);
+            if (dl <= k && -dl <= k) {
+              const uint32_t tc = sketch_counts(sk);
+              const uint32_t up = simt::surplus4(c_counts, tc), down = simt::surplus4(tc, c_counts);
+              keep = (int32_t)(up > down ? up : down) <= k;
+            }
+          }
+        }
+        kq = c_qi; krev = c_rev;
+        s_off += 32u;
+        if (s_off >= s_n[cur]) {                             // chunk used up: refill this buffer, go on with the other
+          simt::sync(FULL);
+          s_phase ^= 1u << cur;
+          fill(cur);
+          cur ^= 1; s_off = 0;
+        }
       } else {
         if (c_at >= c_hi) {                                  // next probe of the block that has entries
           const uint32_t left = simt::ballot(FULL, lo < hi);

@@ -45,6 +45,28 @@ SIMT_FN unsigned long long atomic_min_u64(unsigned long long *p, unsigned long l
 SIMT_FN int32_t atomic_max(int32_t *p, int32_t v) { return atomicMax(p, v); }
 // sum over the four bytes of max(0, a_byte - b_byte)
 SIMT_FN uint32_t surplus4(uint32_t a, uint32_t b) { return __vsadu4(__vsubus4(a, b), 0u); }
+// Bulk copy global -> shared through the TMA unit, completion counted in bytes on an mbarrier (one thread issues, any
+// thread waits).  dst / src / bytes must be multiples of 16.
+SIMT_FN uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+SIMT_FN void bar_init(uint64_t *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+SIMT_FN void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
+               "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+SIMT_FN void bar_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done)
+                 : "r"(smem_addr(bar)), "r"(parity)
+                 : "memory");
+}
 }  // namespace simt
 
 #else
@@ -80,5 +102,9 @@ inline uint32_t surplus4(uint32_t a, uint32_t b) {
   for (int i = 0; i < 4; i++) { uint32_t x = (a >> (8 * i)) & 0xFFu, y = (b >> (8 * i)) & 0xFFu; if (x > y) s += x - y; }
   return s;
 }
+// the emulated bulk copy completes at once
+inline void bar_init(uint64_t *bar, int) { *bar = 0; }
+inline void bulk_load(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
+inline void bar_wait(uint64_t *, uint32_t) {}
 }  // namespace simt
 #endif

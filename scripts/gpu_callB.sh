@@ -10,3 +10,5 @@ for c in cfg2 cfg4 cfg5; do
   python -c "
 import json;d=json.load(open('gpurun_out/r02j_bench_$c.json'));print(d['ms_per_step'],d['e2e']['ms_per_step'],d['stage_ms'],d['parity']['equal'],d['gpu_launches'])"
 done
+shard_profile 8:
+timeout 300 python tests/shard_profile.py 8 2>&1 | tail -2

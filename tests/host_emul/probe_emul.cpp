@@ -31,7 +31,7 @@ extern "C" int64_t emul_probe(const uint64_t *planes, const int32_t *len, int32_
       items.push_back({seed_bin(g, planes[2 * j], planes[2 * j + 1], p, p), j});
     }
   std::stable_sort(items.begin(), items.end(), [](auto &x, auto &y) { return x.first < y.first; });
-  std::vector<SeedEnt> ent(items.size() + 1);
+  std::vector<SeedEnt> ent(items.size() + 2);
   for (size_t i = 0; i < items.size(); i++) {
     const int32_t j = items[i].second;
     bin_off[items[i].first + 1]++;
@@ -50,8 +50,12 @@ extern "C" int64_t emul_probe(const uint64_t *planes, const int32_t *len, int32_
   a.bin_off = bin_off.data(); a.ent = ent.data(); a.hit_key = hk.data(); a.hit_d = hd.data(); a.cap = hit_cap;
   a.key_shift = 24; a.counters = counters; a.len_lo = 0; a.len_hi = 64;
   static ProbeQueue qu;
-  for (int32_t w = 0; w < n_warps; w++)                 // warps one after the other: they only share the block counter
-    simt_emul::run_warp([&](int lane) { probe_warp(a, lane, &qu); }, seed + (uint32_t)w);
+  static ProbeStage stg;
+  const bool staged = (seed & 0x80000000u) != 0;        // top bit of the seed: long bins through the staging buffers
+  for (int32_t w = 0; w < n_warps; w++) {               // warps one after the other: they only share the block counter
+    if (staged) simt_emul::run_warp([&](int lane) { probe_warp<true>(a, lane, &qu, &stg); }, seed + (uint32_t)w);
+    else simt_emul::run_warp([&](int lane) { probe_warp<false>(a, lane, &qu, nullptr); }, seed + (uint32_t)w);
+  }
   if (counters[0] > hit_cap) return -1;
   std::vector<std::pair<uint64_t, uint32_t>> hits(counters[0]);
   for (size_t i = 0; i < hits.size(); i++) hits[i] = {hk[i], hd[i]};

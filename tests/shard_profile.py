@@ -30,7 +30,7 @@ def main():
         U = b["n_buckets"]
         bseq, blen = b["bucket_seq"].contiguous(), b["bucket_len"].contiguous()
         lo, hi = multigpu.shard_range(U, 0, N)
-        (ei, ej, ed), t_pairs_shard = timed(lambda: ctx.edit_pairs(bseq, blen, 2, q_range=(lo, hi)))
+        (ei, ej, ed), t_pairs_shard = timed(lambda: ctx.edit_pairs(bseq, blen, 2, t_range=(lo, hi)))
         st_pairs = {k: round(ctx.stat(k) * 1e-6, 3) for k in ("t_index_ns", "probe_ns", "t_hits_ns")}
         (fi, fj, fd), t_pairs_all = timed(lambda: ctx.edit_pairs(bseq, blen, 2))
         fi, fj, fd = fi.clone(), fj.clone(), fd.clone()

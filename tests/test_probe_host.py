@@ -82,3 +82,18 @@ def test_the_filters_and_the_early_exit_do_work():
         assert np.array_equal(g, np.asarray(w))
     assert st["started"] < 0.7 * st["sided"]                     # composition + length filter
     assert st["cells"] < 0.7 * st["started"] * 25 * 25           # early exit
+
+
+@pytest.mark.parametrize("k,bc_len", [(2, 25), (4, 25), (3, 8), (4, 3), (6, 25)])
+def test_staged_walk_of_long_bins_finds_the_same_pairs(k, bc_len):
+    """probe_warp<STAGED>: bins walked through the two staging buffers (cp.async.bulk + mbarrier on the device, memcpy in the
+    emulator) -- short seeds make every bin long, so the chunking (odd bin starts, chunks of 256 entries, bins that end
+    inside a chunk, the refill order) is what is exercised."""
+    lib_ = synth.make_library(n_clones=150, n_reads=2500, bc_len=bc_len, p_err=0.04, p_near=0.4, seed=60 + k)
+    b = util.oracle_buckets(hostdata.FastqReads([], lib_.seq, lib_.qual, lib_.length))
+    got, st = probe(b["bucket_seq"], b["bucket_len"], k, seed=0x80000000 | (k + 1))
+    plain, st0 = probe(b["bucket_seq"], b["bucket_len"], k, seed=k + 1)
+    want = orc.edit_pairs(b["bucket_seq"], b["bucket_len"], k, method="brute")
+    for g, w in zip(got, want):
+        assert np.array_equal(g, np.asarray(w))
+    assert st["walked"] == st0["walked"] and st["sided"] == st0["sided"]      # the same entries pass by, staged or streamed
