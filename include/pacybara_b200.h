@@ -114,7 +114,9 @@ int64_t pcb_stat(const pcb_ctx *ctx, int which);
 enum { PCB_OPT_REPLAY_SHAPE = 0, PCB_OPT_TRACE = 1 /* 1: host-side lap times of the stages on stderr (development aid) */,
        PCB_OPT_HUGE_READS = 2, PCB_OPT_HUGE_CAP = 3, PCB_OPT_HUGE_WINDOW = 4,
        PCB_OPT_PROBE_STAGING = 5 /* 1: the pair search walks long bins through shared memory (cp.async.bulk + mbarrier)
-                                    instead of streaming loads; same results, kept for the measurement in profiles/ */ };
+                                    instead of streaming loads; same results, kept for the measurement in profiles/ */,
+       PCB_OPT_PROBE_CLASSES = 6 /* 1 (default): long bins of the seed index are grouped by target class so that a probe
+                                    skips most entries of pairs it does not own; 0: whole bins, parity rule */ };
 enum { PCB_REPLAY_AUTO = 0, PCB_REPLAY_THREAD = 1, PCB_REPLAY_WARP = 2, PCB_REPLAY_HUGE = 3 };
 int pcb_set_option(pcb_ctx *ctx, int option, int64_t value);
 /* Block until everything queued on the context's stream has finished. */

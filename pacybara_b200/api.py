@@ -84,6 +84,10 @@ class Context:
         if getattr(self, "_staging_set", 0) != staged:
             self._check(self.lib.pcb_set_option(self.h, _lib.OPT_PROBE_STAGING, staged))
             self._staging_set = staged
+        classes = 0 if os.environ.get("PCB_PROBE_CLASSES") == "0" else 1
+        if getattr(self, "_classes_set", 1) != classes:
+            self._check(self.lib.pcb_set_option(self.h, _lib.OPT_PROBE_CLASSES, classes))
+            self._classes_set = classes
         # giant-tier knobs: environment > set_huge() > the library's defaults, applied per call like the shape
         for env, opt, default in (("PCB_HUGE_READS", _lib.OPT_HUGE_READS, 256), ("PCB_HUGE_CAP", _lib.OPT_HUGE_CAP, 2048),
                                   ("PCB_HUGE_WINDOW", _lib.OPT_HUGE_WINDOW, 32768)):

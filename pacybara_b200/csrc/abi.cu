@@ -247,6 +247,7 @@ int pcb_set_option(pcb_ctx *ctx, int option, int64_t value) {
     return PCB_OK;
   }
   if (option == PCB_OPT_TRACE) { ctx->trace = value != 0; return PCB_OK; }
+  if (option == PCB_OPT_PROBE_CLASSES) { ctx->probe_classes = value != 0; return PCB_OK; }
   if (option == PCB_OPT_PROBE_STAGING) { ctx->probe_staging = value != 0; return PCB_OK; }
   if (option == PCB_OPT_HUGE_READS && value >= 0 && value <= INT32_MAX) { ctx->huge_reads = (int)value; return PCB_OK; }
   if (option == PCB_OPT_HUGE_CAP && value >= 16 && value <= (1 << 20) && (value & (value - 1)) == 0) { ctx->huge_cap = (int)value; return PCB_OK; }

@@ -18,18 +18,35 @@ namespace pcb {
 // flags[0] = first offending row + 1 (0xFFFFFFFF: none), flags[1] = min length, flags[2] = max length, flags[3] = opaque barcodes,
 // flags[4 + m] = barcodes of length m (m = 1..64): the pair search picks its seed lengths from that histogram
 constexpr int PACK_FLAGS = 4 + 66;
-__global__ void __launch_bounds__(128) pack_kernel(const uint8_t *__restrict__ seq, const int32_t *__restrict__ len,
-                                                   const int32_t *__restrict__ rows, int32_t n, int32_t stride,
-                                                   ulonglong2 *__restrict__ planes, int32_t *__restrict__ out_len, int32_t *flags,
-                                                   uint64_t *__restrict__ other) {
+constexpr int PACK_BLOCK = 128;
+// STAGED: the block's rows are one contiguous byte range (rows == nullptr); it is brought into shared memory with 16-byte
+// streaming loads and every thread then reads its own row from there -- a thread reading its 25-byte row straight from
+// global memory issues 25 one-byte loads at a 25-byte stride (450 GB/s in round 1, profiles/r01q_launches.md).
+template <bool STAGED>
+__global__ void __launch_bounds__(PACK_BLOCK) pack_kernel(const uint8_t *__restrict__ seq, const int32_t *__restrict__ len,
+                                                          const int32_t *__restrict__ rows, int32_t n, int32_t stride,
+                                                          ulonglong2 *__restrict__ planes, int32_t *__restrict__ out_len, int32_t *flags,
+                                                          uint64_t *__restrict__ other) {
+  extern __shared__ uint4 pack_sh[];
   __shared__ uint32_t sh_hist[66];
   if (threadIdx.x < 66) sh_hist[threadIdx.x] = 0;
+  const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint8_t *s = nullptr;
+  if (STAGED) {
+    const size_t row0 = (size_t)blockIdx.x * PACK_BLOCK;
+    const int32_t n_rows = n - (int32_t)row0 < PACK_BLOCK ? n - (int32_t)row0 : PACK_BLOCK;
+    const uint8_t *g = seq + row0 * (size_t)stride;
+    const uintptr_t a0 = (uintptr_t)g & ~(uintptr_t)15;            // (stays inside the allocation: those are 16-byte granular)
+    const int32_t head = (int32_t)((uintptr_t)g - a0);
+    const int32_t n_vec = (head + n_rows * stride + 15) >> 4;
+    for (int32_t v = threadIdx.x; v < n_vec; v += PACK_BLOCK) pack_sh[v] = __ldcs((const uint4 *)a0 + v);
+    s = (const uint8_t *)pack_sh + head + (size_t)threadIdx.x * stride;
+  }
   __syncthreads();
-  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
     int32_t row = rows ? rows[i] : i;
     int32_t m = len[row];
-    const uint8_t *s = seq + (size_t)row * stride;
+    if (!STAGED) s = seq + (size_t)row * stride;
     bool bad = m < 0 || m > stride;
     // The reference treats barcodes as opaque strings (src/pacybara_precluster.py:28-39).  One that does not fit the
     // 2-bit planes -- a character outside ACGT, more than 64 bases, or none -- is kept as such: its planes hold a
@@ -80,8 +97,13 @@ void pack_launch(pcb_ctx *ctx, const uint8_t *seq, const int32_t *len, const int
   PCB_CUDA(cudaMemsetAsync(flags.p, 0, PACK_FLAGS * sizeof(int32_t), ctx->stream));
   PCB_CUDA(cudaMemsetAsync(flags.p, 0xFF, sizeof(int32_t), ctx->stream));                 // flags[0] as unsigned: 0xFFFFFFFF = none
   PCB_CUDA(cudaMemsetAsync(flags.p + 1, 0x7F, sizeof(int32_t), ctx->stream));             // min length: a large value
-  if (n > 0) PCB_LAUNCH(ctx, pack_kernel, grid_for(n, 128), 128, 0, seq, len, rows, n, stride, out.planes.p, out.len.p, flags.p,
-                        allow_other ? out.other.p : nullptr);
+  const size_t stage_bytes = (size_t)PACK_BLOCK * (size_t)stride + 32;
+  if (n > 0 && rows == nullptr && stage_bytes <= 40 * 1024)
+    PCB_LAUNCH(ctx, pack_kernel<true>, grid_for(n, PACK_BLOCK), PACK_BLOCK, stage_bytes, seq, len, rows, n, stride, out.planes.p, out.len.p,
+               flags.p, allow_other ? out.other.p : nullptr);
+  else if (n > 0)
+    PCB_LAUNCH(ctx, pack_kernel<false>, grid_for(n, PACK_BLOCK), PACK_BLOCK, 0, seq, len, rows, n, stride, out.planes.p, out.len.p, flags.p,
+               allow_other ? out.other.p : nullptr);
 }
 void pack_finish(PackedBarcodes &out, const int32_t *h, bool allow_other) {
   if (h[0] != -1)

@@ -58,6 +58,7 @@ struct pcb_ctx {
   int huge_cap = 2048;                     // PCB_OPT_HUGE_CAP: slots of one warp's scratch table in that tier
   int huge_window = 32768;                 // PCB_OPT_HUGE_WINDOW: rows per round
   int huge_warps_per_sm = 24;
+  int probe_classes = 1;                   // PCB_OPT_PROBE_CLASSES: split long bins by target class (probe.cuh: owns_pair); 0 = parity rule only
   int probe_staging = 0;                   // PCB_OPT_PROBE_STAGING: long bins through shared memory by TMA bulk copies (probe.cuh)
   bool medium_attr_set = false;            // the medium replay kernel's shared-memory opt-in (merge.cu)
   int trace = 0;                           // pcb_set_option(PCB_OPT_TRACE): host-side lap times on stderr

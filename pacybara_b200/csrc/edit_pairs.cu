@@ -30,7 +30,7 @@ __global__ void seed_count_kernel(const ulonglong2 *__restrict__ planes, const i
   if (len[j] > 64) return;                       // an opaque barcode: not a target
   if (g.q > 0 && (p + g.q > len[j] || !((g.pos_mask >> p) & 1ull))) return;
   ulonglong2 pl = planes[j];
-  atomicAdd(&bin_cnt[seed_bin(g, pl.x, pl.y, p, p)], 1u);
+  atomicAdd(&bin_cnt[seed_slot(g, seed_bin(g, pl.x, pl.y, p, p), j)], 1u);
 }
 
 __global__ void seed_fill_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int32_t t_begin, int32_t U,
@@ -41,7 +41,7 @@ __global__ void seed_fill_kernel(const ulonglong2 *__restrict__ planes, const in
   if (len[j] > 64) return;
   if (g.q > 0 && (p + g.q > len[j] || !((g.pos_mask >> p) & 1ull))) return;
   ulonglong2 pl = planes[j];
-  uint32_t at = atomicAdd(&cursor[seed_bin(g, pl.x, pl.y, p, p)], 1u);
+  uint32_t at = atomicAdd(&cursor[seed_slot(g, seed_bin(g, pl.x, pl.y, p, p), j)], 1u);
   ent[at] = j;
 }
 
@@ -54,7 +54,7 @@ __global__ void seed_fill8_kernel(const ulonglong2 *__restrict__ planes, const i
   if (len[j] > 64) return;
   if (g.q > 0 && (p + g.q > len[j] || !((g.pos_mask >> p) & 1ull))) return;
   ulonglong2 pl = planes[j];
-  uint32_t at = atomicAdd(&cursor[seed_bin(g, pl.x, pl.y, p, p)], 1u);
+  uint32_t at = atomicAdd(&cursor[seed_slot(g, seed_bin(g, pl.x, pl.y, p, p), j)], 1u);
   SeedEnt e;
   e.j = j; e.sk = barcode_sketch((uint32_t)pl.x, (uint32_t)pl.y, len[j]);
   ent[at] = e;
@@ -329,6 +329,7 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
     g.npos = g.q == 0 ? 1 : bc.max_len - g.q + 1;
     g.nbins = g.q == 0 ? 1u : (uint32_t)g.npos << (2 * g.q);
     g.pos_mask = ~0ull;
+    g.cbits = 0;
     return g;
   };
   // the positions the probes of query lengths [lo, hi] can ask for: start of piece t (t * m / (k+1)) plus a shift in [-k, k]
@@ -361,15 +362,21 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
   ctx->stats[PCB_STAT_SEED_LEN] = idx[0].g.q;
   for (int t = 0; t < n_idx; t++) {
     idx[t].g.pos_mask = probe_positions(idx[t].g, idx[t].len_lo, idx[t].len_hi);
+    // long bins (about 8 entries or more, counted over ALL barcodes so that every shard of a multi-GPU search decides
+    // alike): 8 classes per bin, so that a probe skips most of what it does not own (probe.cuh: owns_pair)
+    if (lanes && idx[t].g.q > 0 && (uint64_t)U * (uint64_t)__builtin_popcountll(idx[t].g.pos_mask & (idx[t].g.npos >= 64 ? ~0ull : (1ull << idx[t].g.npos) - 1ull)) >= 8ull * idx[t].g.nbins &&
+        ((uint64_t)idx[t].g.nbins << 3) <= (1ull << 25))
+      idx[t].g.cbits = ctx->probe_classes ? 3 : 0;
     const SeedGeom &g = idx[t].g;
-    DevBuf<uint32_t> cursor(ctx, (size_t)g.nbins + 1);
-    idx[t].bin_off.alloc(ctx, (size_t)g.nbins + 1);
+    const size_t n_sub = (size_t)g.nbins << g.cbits;
+    DevBuf<uint32_t> cursor(ctx, n_sub + 1);
+    idx[t].bin_off.alloc(ctx, n_sub + 1);
     if (lanes) idx[t].ent8.alloc(ctx, (size_t)T * g.npos + 2); else idx[t].ent.alloc(ctx, (size_t)T * g.npos);
-    PCB_CUDA(cudaMemsetAsync(idx[t].bin_off.p, 0, ((size_t)g.nbins + 1) * sizeof(uint32_t), ctx->stream));
+    PCB_CUDA(cudaMemsetAsync(idx[t].bin_off.p, 0, (n_sub + 1) * sizeof(uint32_t), ctx->stream));
     size_t n_slots = (size_t)T * g.npos;
     PCB_LAUNCH(ctx, seed_count_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, t_begin, T, g, idx[t].bin_off.p);
-    exclusive_scan_u32(ctx, idx[t].bin_off.p, idx[t].bin_off.p, (size_t)g.nbins + 1);
-    PCB_CUDA(cudaMemcpyAsync(cursor.p, idx[t].bin_off.p, ((size_t)g.nbins + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+    exclusive_scan_u32(ctx, idx[t].bin_off.p, idx[t].bin_off.p, n_sub + 1);
+    PCB_CUDA(cudaMemcpyAsync(cursor.p, idx[t].bin_off.p, (n_sub + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
     if (lanes) PCB_LAUNCH(ctx, seed_fill8_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, t_begin, T, g, cursor.p, idx[t].ent8.p);
     else PCB_LAUNCH(ctx, seed_fill_kernel, grid_for(n_slots, 256), 256, 0, bc.planes.p, bc.len.p, t_begin, T, g, cursor.p, idx[t].ent.p);
   }

@@ -244,16 +244,22 @@ __global__ void cpair_ptr_kernel(const uint32_t *__restrict__ off, const int32_t
   if (c <= counters[CNT_COMPS]) cpair_ptr[c] = (int32_t)off[4 * (size_t)c];
 }
 
+// bucket of every read from the CSR: a warp takes 32 buckets, a lane writes the reads of its own bucket when they are
+// few, the warp together those of the bigger ones
 __global__ void bucket_of_read_kernel(const int32_t *__restrict__ bucket_ptr, const int32_t *__restrict__ bucket_reads, int32_t R, int32_t U,
                                       int32_t *__restrict__ bor) {
-  int32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-  if (x >= R) return;
-  int32_t lo = 0, hi = U;                       // last b with bucket_ptr[b] <= x
-  while (hi - lo > 1) {
-    int32_t mid = (lo + hi) >> 1;
-    if (bucket_ptr[mid] <= x) lo = mid; else hi = mid;
+  const int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int32_t lo = 0, n = 0;
+  if (b < U) { lo = bucket_ptr[b]; n = bucket_ptr[b + 1] - lo; }
+  if (n <= 16) for (int32_t x = 0; x < n; x++) bor[bucket_reads[lo + x]] = b;
+  uint32_t big = __ballot_sync(0xFFFFFFFFu, n > 16);
+  while (big) {
+    const int l = __ffs(big) - 1;
+    big &= big - 1u;
+    const int32_t blo = __shfl_sync(0xFFFFFFFFu, lo, l), bn = __shfl_sync(0xFFFFFFFFu, n, l), bb = __shfl_sync(0xFFFFFFFFu, b, l);
+    for (int32_t x = lane; x < bn; x += 32) bor[bucket_reads[blo + x]] = bb;
   }
-  bor[bucket_reads[x]] = lo;
 }
 
 // ------------------------------------------------------------------------------------------ tiers
@@ -868,7 +874,7 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   const int32_t *bor = in.bucket_of_read;
   if (!bor) {
     bor_own.alloc(ctx, R);
-    PCB_LAUNCH(ctx, bucket_of_read_kernel, grid_for(R, 256), 256, 0, in.bucket_ptr, in.bucket_reads, R, U, bor_own.p);
+    PCB_LAUNCH(ctx, bucket_of_read_kernel, grid_for(U, 256), 256, 0, in.bucket_ptr, in.bucket_reads, R, U, bor_own.p);
     bor = bor_own.p;
   }
   DevBuf<int32_t> status(ctx, STATUS_N), medium(ctx, (size_t)U + 1), large(ctx, (size_t)U + 1), declined(ctx, (size_t)U + 1), late(ctx, (size_t)U + 1);

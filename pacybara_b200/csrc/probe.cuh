@@ -31,7 +31,23 @@ struct SeedGeom {
   int32_t k;
   uint32_t nbins;
   uint64_t pos_mask; // positions a probe can ask for (piece start + shift of some query length): only those are indexed
+  int32_t cbits;     // every bin is split into 2^cbits sub-bins by the low bits of the target (its CLASS), see owns_pair()
 };
+
+// Which side of an unordered pair {i, j} probes for it.  cbits == 0: the parity rule of myers.cuh.  cbits > 0 (big
+// libraries, long bins): barcodes are ordered by (class, index), class = low bits of the index, and the smaller one is
+// the query side.  A bin's entries are grouped by class, so a query of class c starts its walk at sub-bin c: what it
+// skips are exactly pairs it does not own -- on average (C - 1) / 2C of every bin (44 % with 8 classes), where the
+// parity rule reads a whole bin to keep half of it.  Classes interleave, so any index range (a shard) holds all alike.
+PCB_HD bool owns_pair(const SeedGeom &g, int32_t i, int32_t j) {
+  if (g.cbits == 0) return j != i && is_query_side(i, j);
+  const int32_t mask = (1 << g.cbits) - 1;
+  return (j & mask) != (i & mask) ? (j & mask) > (i & mask) : j > i;
+}
+// sub-bin of target j in bin `bin`
+PCB_HD uint32_t seed_slot(const SeedGeom &g, uint32_t bin, int32_t j) {
+  return (bin << g.cbits) | ((uint32_t)j & ((1u << g.cbits) - 1u));
+}
 
 PCB_HD uint32_t seed_bin(const SeedGeom g, uint64_t L, uint64_t H, int src_pos, int bin_pos) {
   if (g.q == 0) return 0u;
@@ -153,7 +169,7 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu, ProbeStage
           if (p >= 0 && p < g.npos && qm >= a.len_lo && qm <= a.len_hi) {     // queries of other lengths use the other index
             const Planes16 pl = a.planes[qi];
             const uint32_t bin = seed_bin(g, pl.x, pl.y, st, p);
-            lo = a.bin_off[bin]; hi = a.bin_off[bin + 1];
+            lo = a.bin_off[seed_slot(g, bin, qi)]; hi = a.bin_off[(bin + 1u) << g.cbits];      // my class and the ones above
             qcounts = sketch_counts(a.sketch[qi]);
             // the seed matches exactly: the errors are before it or after it -- start the recurrence on the longer side
             qrev = (st < qm - (st + g.q)) ? 0x80000000u : 0u;
@@ -179,7 +195,7 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu, ProbeStage
           const SeedEnt en = a.ent[lo++];
           j = en.j;
           n_walked++;
-          if (j != qi && is_query_side(qi, j)) {
+          if (owns_pair(g, qi, j)) {
             n_sided++;
             const uint32_t sk = en.sk;
             const int32_t dl = qm - (int32_t)(sk >> 24);
@@ -204,7 +220,7 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu, ProbeStage
           const SeedEnt en = stg->ent[cur][s_off + (uint32_t)lane];
           j = en.j;
           n_walked++;
-          if (j != c_qi && is_query_side(c_qi, j)) {
+          if (owns_pair(g, c_qi, j)) {
             n_sided++;
             const uint32_t sk = en.sk;
             const int32_t dl = c_qm - (int32_t)(sk >> 24);
@@ -238,7 +254,7 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu, ProbeStage
           const SeedEnt en = simt::ld_stream(&a.ent[e]);
           j = en.j;
           n_walked++;
-          if (j != c_qi && is_query_side(c_qi, j)) {
+          if (owns_pair(g, c_qi, j)) {
             n_sided++;
             const uint32_t sk = en.sk;
             const int32_t dl = c_qm - (int32_t)(sk >> 24);

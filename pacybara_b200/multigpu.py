@@ -3,9 +3,10 @@
 What shards and what is exchanged:
   1. bucketing            replicated -- every rank buckets the whole read set (HBM-bound, a few ms;
                           it yields the identical bucket numbering everywhere without an exchange);
-  2. distance pairs       SHARDED by target bucket: rank r indexes its slice of [0, U) and scores the pairs
-                          whose target side lies in it (pcb_edit_pairs t_begin/t_end) -- the dominant kernel, and
-                          the index build divides with it;
+  2. distance pairs       SHARDED over a (query groups x target groups) grid of the ranks: a rank indexes the targets
+                          of its slice of [0, U) and scores the pairs whose query side lies in its query slice
+                          (pcb_edit_pairs q_begin/q_end, t_begin/t_end; pair_grid) -- the dominant kernel, and
+                          the index build divides with the target groups;
   3. edge exchange        the one real collective: all-gather of the per-rank edge lists (counts, then
                           the padded (i, j, d) payload) over NVLink, then pcb_sort_edges restores the
                           canonical row order;
@@ -30,6 +31,21 @@ from .hostdata import MERGE_OUTPUTS, MergeProblem, PairList
 
 def shard_range(n: int, rank: int, world: int):
     return (n * rank) // world, (n * (rank + 1)) // world
+
+
+def pair_grid(world: int):
+    """Ranks as a (query groups x target groups) grid for the pair search.  A rank indexes the targets of its target
+    group and probes with the queries of its query group, so the index build costs U / Gt and the per-probe work
+    (decode, query planes, bin bounds) U / Gq, while the bin entries walked are 1 / world either way.  Measured at
+    8 * 10^6 reads (profiles/r02j_shard_profile_n8.txt): index 1.4 ms and probe overhead 0.93 ms for all of U, so one
+    split of the queries pays from 4 ranks on: 1 x 2, 2 x 2, 2 x 4."""
+    gq = 2 if world >= 4 and world % 2 == 0 else 1
+    return gq, world // gq
+
+
+def pair_ranges(U: int, rank: int, world: int):
+    gq, gt = pair_grid(world)
+    return shard_range(U, rank % gq, gq), shard_range(U, rank // gq, gt)
 
 
 def gather_edges(ei, ej, ed, world: int):
@@ -152,12 +168,12 @@ def cluster_reads_sharded(ctx: Context, arrs: Dict, params: Dict, rank: int, wor
     b = ctx.bucket(a["seq"], None, a["length"], want_qsum=False)      # qualities are not needed for clustering
     lib_stages("bucket")
     U = b["n_buckets"]
-    # 2. my slice of the target buckets (every pair has one query side and one target side)
-    lo, hi = shard_range(U, rank, world)
+    # 2. my block of the (query, target) grid (every pair has one query side and one target side)
+    q_range, t_range = pair_ranges(U, rank, world)
     bseq, blen = b["bucket_seq"].contiguous(), b["bucket_len"].contiguous()
     err = None
     try:
-        ei, ej, ed = ctx.edit_pairs(bseq, blen, (2 if full_table else 1) * max_diff, t_range=(lo, hi))
+        ei, ej, ed = ctx.edit_pairs(bseq, blen, (2 if full_table else 1) * max_diff, q_range=q_range, t_range=t_range)
     except Exception as e:          # noqa: BLE001 - re-raised on every rank below
         err = e
     _all_ranks_ok("pair search", err, dev)
@@ -231,7 +247,10 @@ def cluster_reads_virtual(ctx: Context, arrs: Dict, params: Dict, world: int, fu
     b = ctx.bucket(arrs["seq"], None, arrs["length"], want_qsum=False)
     U = b["n_buckets"]
     bseq, blen = b["bucket_seq"].contiguous(), b["bucket_len"].contiguous()
-    parts = [ctx.edit_pairs(bseq, blen, (2 if full_table else 1) * max_diff, t_range=shard_range(U, r, world)) for r in range(world)]
+    parts = []
+    for r in range(world):
+        q_range, t_range = pair_ranges(U, r, world)
+        parts.append(ctx.edit_pairs(bseq, blen, (2 if full_table else 1) * max_diff, q_range=q_range, t_range=t_range))
     ei, ej, ed = (torch.cat([p[t] for p in parts]).contiguous() for t in range(3))        # the all-gather
     ctx.sort_edges(ei, ej, ed, U)
     ped = torch.where((ed >= 1) & (ed <= max_diff), ed, torch.zeros_like(ed))

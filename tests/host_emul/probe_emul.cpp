@@ -23,12 +23,14 @@ extern "C" int64_t emul_probe(const uint64_t *planes, const int32_t *len, int32_
   g.npos = g.q == 0 ? 1 : max_len - g.q + 1;
   g.nbins = g.q == 0 ? 1u : (uint32_t)g.npos << (2 * g.q);
   g.pos_mask = ~0ull;
-  std::vector<uint32_t> bin_off((size_t)g.nbins + 1, 0);
+  g.cbits = (seed & 0x40000000u) && g.q > 0 ? 3 : 0;   // bit 30 of the seed: bins split into 8 classes (owns_pair)
+  const size_t n_sub = (size_t)g.nbins << g.cbits;
+  std::vector<uint32_t> bin_off(n_sub + 1, 0);
   std::vector<std::pair<uint32_t, int32_t>> items;
   for (int32_t j = 0; j < U; j++)
     for (int32_t p = 0; p < g.npos; p++) {
       if (g.q > 0 && p + g.q > len[j]) continue;
-      items.push_back({seed_bin(g, planes[2 * j], planes[2 * j + 1], p, p), j});
+      items.push_back({seed_slot(g, seed_bin(g, planes[2 * j], planes[2 * j + 1], p, p), j), j});
     }
   std::stable_sort(items.begin(), items.end(), [](auto &x, auto &y) { return x.first < y.first; });
   std::vector<SeedEnt> ent(items.size() + 2);
@@ -37,7 +39,7 @@ extern "C" int64_t emul_probe(const uint64_t *planes, const int32_t *len, int32_
     bin_off[items[i].first + 1]++;
     ent[i].j = j; ent[i].sk = barcode_sketch((uint32_t)planes[2 * j], (uint32_t)planes[2 * j + 1], len[j]);
   }
-  for (uint32_t b = 0; b < g.nbins; b++) bin_off[b + 1] += bin_off[b];
+  for (size_t b = 0; b < n_sub; b++) bin_off[b + 1] += bin_off[b];
   unsigned long long hit_cap = 64ull * (unsigned long long)U * (unsigned long long)U + 4096;      // a pair can be found through every piece and shift
   if (hit_cap > (1ull << 24)) hit_cap = 1ull << 24;
   std::vector<uint64_t> hk(hit_cap);

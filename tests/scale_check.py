@@ -59,7 +59,7 @@ def main():
                rows=rows.n_rows, clusters=rows.n_clusters, pure_cluster_frac=float(pure[big].mean()) if big.any() else None,
                clusters_per_seen_clone=rows.n_clusters / n_clones_seen, max_cluster=int(sizes.max()),
                components=st["components"], links=st["links"], tests=st["tests"], pairs_scored=st["pairs_scored"],
-               seed_len=st["seed_len"], gen_s=round(t_gen, 1), wall_ms=round(t_run * 1e3, 1),
+               seed_len=st["seed_len"], huge_components=st["huge_components"], huge_rounds=st["huge_rounds"], gen_s=round(t_gen, 1), wall_ms=round(t_run * 1e3, 1),
                stage_ms={k[2:-3]: round(st[k] * 1e-6, 3) for k in st if k.startswith("t_")}, probe_ms=round(st["probe_ns"] * 1e-6, 3))
     if want_full:
         out2 = ctx.cluster_reads(*args, full_table=True, **p)

@@ -97,3 +97,21 @@ def test_staged_walk_of_long_bins_finds_the_same_pairs(k, bc_len):
     for g, w in zip(got, want):
         assert np.array_equal(g, np.asarray(w))
     assert st["walked"] == st0["walked"] and st["sided"] == st0["sided"]      # the same entries pass by, staged or streamed
+
+
+@pytest.mark.parametrize("k,bc_len,staged", [(2, 25, 0), (2, 25, 1), (4, 25, 0), (3, 8, 1), (6, 25, 0)])
+def test_bins_split_by_target_class_find_the_same_pairs(k, bc_len, staged):
+    """owns_pair with classes (big libraries): the query side of a pair is the smaller (class, index); a probe starts its walk
+    at its own class.  Same pairs, fewer entries walked; query shards stay disjoint and complete."""
+    lib_ = synth.make_library(n_clones=150, n_reads=2500, bc_len=bc_len, p_err=0.04, p_near=0.4, seed=80 + k)
+    b = util.oracle_buckets(hostdata.FastqReads([], lib_.seq, lib_.qual, lib_.length))
+    U = b["n_buckets"]
+    flag = 0x40000000 | (0x80000000 if staged else 0)
+    got, st = probe(b["bucket_seq"], b["bucket_len"], k, seed=flag | (k + 1))
+    plain, st0 = probe(b["bucket_seq"], b["bucket_len"], k, seed=k + 1)
+    want = orc.edit_pairs(b["bucket_seq"], b["bucket_len"], k, method="brute")
+    for g, w in zip(got, want):
+        assert np.array_equal(g, np.asarray(w))
+    assert st["walked"] < 0.75 * st0["walked"]
+    parts = [probe(b["bucket_seq"], b["bucket_len"], k, q_range=r, seed=flag | 9)[0] for r in ((0, U // 3), (U // 3, U))]
+    assert sum(len(p[0]) for p in parts) == len(want[0])
