@@ -329,7 +329,7 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
     g.npos = g.q == 0 ? 1 : bc.max_len - g.q + 1;
     g.nbins = g.q == 0 ? 1u : (uint32_t)g.npos << (2 * g.q);
     g.pos_mask = ~0ull;
-    g.cbits = 0;
+    g.cbits = 0; g.rbits = 0;
     return g;
   };
   // the positions the probes of query lengths [lo, hi] can ask for: start of piece t (t * m / (k+1)) plus a shift in [-k, k]
@@ -363,10 +363,13 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
   for (int t = 0; t < n_idx; t++) {
     idx[t].g.pos_mask = probe_positions(idx[t].g, idx[t].len_lo, idx[t].len_hi);
     // long bins (about 8 entries or more, counted over ALL barcodes so that every shard of a multi-GPU search decides
-    // alike): 8 classes per bin, so that a probe skips most of what it does not own (probe.cuh: owns_pair)
-    if (lanes && idx[t].g.q > 0 && (uint64_t)U * (uint64_t)__builtin_popcountll(idx[t].g.pos_mask & (idx[t].g.npos >= 64 ? ~0ull : (1ull << idx[t].g.npos) - 1ull)) >= 8ull * idx[t].g.nbins &&
-        ((uint64_t)idx[t].g.nbins << 3) <= (1ull << 25))
-      idx[t].g.cbits = ctx->probe_classes ? 3 : 0;
+    // alike): 8 classes per bin, so that a probe skips most of what it does not own (probe.cuh: owns_pair).  The first
+    // index decides the rule for the whole search -- every pair must have ONE owner whichever index its sides probe.
+    const bool long_bins = idx[t].g.q > 0 && ((uint64_t)idx[t].g.nbins << 3) <= (1ull << 25) &&
+        (uint64_t)U * (uint64_t)__builtin_popcountll(idx[t].g.pos_mask & (idx[t].g.npos >= 64 ? ~0ull : (1ull << idx[t].g.npos) - 1ull)) >= 8ull * idx[t].g.nbins;
+    if (t == 0) idx[0].g.rbits = (lanes && ctx->probe_classes && long_bins) ? 3 : 0;
+    idx[t].g.rbits = idx[0].g.rbits;
+    idx[t].g.cbits = long_bins ? idx[t].g.rbits : 0;
     const SeedGeom &g = idx[t].g;
     const size_t n_sub = (size_t)g.nbins << g.cbits;
     DevBuf<uint32_t> cursor(ctx, n_sub + 1);

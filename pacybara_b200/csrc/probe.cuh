@@ -32,6 +32,8 @@ struct SeedGeom {
   uint32_t nbins;
   uint64_t pos_mask; // positions a probe can ask for (piece start + shift of some query length): only those are indexed
   int32_t cbits;     // every bin is split into 2^cbits sub-bins by the low bits of the target (its CLASS), see owns_pair()
+  int32_t rbits;     // the ownership rule of the whole search (all its indexes): 0 = parity, else classes of rbits bits;
+                     // an index with sub-bins has cbits == rbits, one without walks whole bins under the same rule
 };
 
 // Which side of an unordered pair {i, j} probes for it.  cbits == 0: the parity rule of myers.cuh.  cbits > 0 (big
@@ -40,8 +42,8 @@ struct SeedGeom {
 // skips are exactly pairs it does not own -- on average (C - 1) / 2C of every bin (44 % with 8 classes), where the
 // parity rule reads a whole bin to keep half of it.  Classes interleave, so any index range (a shard) holds all alike.
 PCB_HD bool owns_pair(const SeedGeom &g, int32_t i, int32_t j) {
-  if (g.cbits == 0) return j != i && is_query_side(i, j);
-  const int32_t mask = (1 << g.cbits) - 1;
+  if (g.rbits == 0) return j != i && is_query_side(i, j);
+  const int32_t mask = (1 << g.rbits) - 1;
   return (j & mask) != (i & mask) ? (j & mask) > (i & mask) : j > i;
 }
 // sub-bin of target j in bin `bin`

@@ -23,7 +23,8 @@ extern "C" int64_t emul_probe(const uint64_t *planes, const int32_t *len, int32_
   g.npos = g.q == 0 ? 1 : max_len - g.q + 1;
   g.nbins = g.q == 0 ? 1u : (uint32_t)g.npos << (2 * g.q);
   g.pos_mask = ~0ull;
-  g.cbits = (seed & 0x40000000u) && g.q > 0 ? 3 : 0;   // bit 30 of the seed: bins split into 8 classes (owns_pair)
+  g.rbits = (seed & 0x40000000u) ? 3 : 0;              // bit 30 of the seed: the class rule, bins split into 8 classes (owns_pair)
+  g.cbits = g.q > 0 && !(seed & 0x20000000u) ? g.rbits : 0;      // (bit 29: whole bins under the class rule, as a second index has them)
   const size_t n_sub = (size_t)g.nbins << g.cbits;
   std::vector<uint32_t> bin_off(n_sub + 1, 0);
   std::vector<std::pair<uint32_t, int32_t>> items;

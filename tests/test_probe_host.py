@@ -115,3 +115,7 @@ def test_bins_split_by_target_class_find_the_same_pairs(k, bc_len, staged):
     assert st["walked"] < 0.75 * st0["walked"]
     parts = [probe(b["bucket_seq"], b["bucket_len"], k, q_range=r, seed=flag | 9)[0] for r in ((0, U // 3), (U // 3, U))]
     assert sum(len(p[0]) for p in parts) == len(want[0])
+    whole, st1 = probe(b["bucket_seq"], b["bucket_len"], k, seed=flag | 0x20000000 | 3)      # class rule over whole bins
+    for g, w in zip(whole, want):
+        assert np.array_equal(g, np.asarray(w))
+    assert st1["walked"] == st0["walked"]
