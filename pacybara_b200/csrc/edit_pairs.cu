@@ -28,9 +28,10 @@ __global__ void seed_count_kernel(const ulonglong2 *__restrict__ planes, const i
   if (i >= (size_t)U * g.npos) return;
   int32_t j = t_begin + (int32_t)(i / g.npos), p = (int32_t)(i % g.npos);
   if (len[j] > 64) return;                       // an opaque barcode: not a target
+  if (g.only_below && len[j] >= g.only_below) return;
   if (g.q > 0 && (p + g.q > len[j] || !((g.pos_mask >> p) & 1ull))) return;
   ulonglong2 pl = planes[j];
-  atomicAdd(&bin_cnt[seed_slot(g, seed_bin(g, pl.x, pl.y, p, p), j)], 1u);
+  atomicAdd(&bin_cnt[seed_slot(g, seed_bin(g, pl.x, pl.y, p, p), j, len[j])], 1u);
 }
 
 __global__ void seed_fill_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int32_t t_begin, int32_t U,
@@ -39,10 +40,11 @@ __global__ void seed_fill_kernel(const ulonglong2 *__restrict__ planes, const in
   if (i >= (size_t)U * g.npos) return;
   int32_t j = t_begin + (int32_t)(i / g.npos), p = (int32_t)(i % g.npos);
   if (len[j] > 64) return;
+  if (g.only_below && len[j] >= g.only_below) return;
   if (g.q > 0 && (p + g.q > len[j] || !((g.pos_mask >> p) & 1ull))) return;
   ulonglong2 pl = planes[j];
-  uint32_t at = atomicAdd(&cursor[seed_slot(g, seed_bin(g, pl.x, pl.y, p, p), j)], 1u);
-  ent[at] = j;
+  uint32_t at = atomicAdd(&cursor[seed_slot(g, seed_bin(g, pl.x, pl.y, p, p), j, len[j])], 1u);
+  ent[at] = len[j] < g.short_below ? (int32_t)((uint32_t)j | 0x80000000u) : j;      // sign bit: a short target (owned by the query)
 }
 
 // the same with (target, sketch) entries: the index of the lane-per-pair probe (probe.cuh)
@@ -52,9 +54,10 @@ __global__ void seed_fill8_kernel(const ulonglong2 *__restrict__ planes, const i
   if (i >= (size_t)U * g.npos) return;
   int32_t j = t_begin + (int32_t)(i / g.npos), p = (int32_t)(i % g.npos);
   if (len[j] > 64) return;
+  if (g.only_below && len[j] >= g.only_below) return;
   if (g.q > 0 && (p + g.q > len[j] || !((g.pos_mask >> p) & 1ull))) return;
   ulonglong2 pl = planes[j];
-  uint32_t at = atomicAdd(&cursor[seed_slot(g, seed_bin(g, pl.x, pl.y, p, p), j)], 1u);
+  uint32_t at = atomicAdd(&cursor[seed_slot(g, seed_bin(g, pl.x, pl.y, p, p), j, len[j])], 1u);
   SeedEnt e;
   e.j = j; e.sk = barcode_sketch((uint32_t)pl.x, (uint32_t)pl.y, len[j]);
   ent[at] = e;
@@ -170,7 +173,9 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel(const ulonglong
       int32_t j = 0;
       if (lo < hi) {
         j = ent[lo++];
-        keep = !SELF || (j != qi && is_query_side(qi, j));
+        const bool t_short = j < 0;                          // (only the self-join's main index marks short targets)
+        j &= 0x7FFFFFFF;
+        keep = !SELF || t_short || (j != qi && is_query_side(qi, j));
       }
       uint32_t mask = __ballot_sync(0xFFFFFFFFu, keep);
       if (keep) queue[warp][cnt + __popc(mask & lt_mask)] = make_int2(qi, j);
@@ -329,7 +334,7 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
     g.npos = g.q == 0 ? 1 : bc.max_len - g.q + 1;
     g.nbins = g.q == 0 ? 1u : (uint32_t)g.npos << (2 * g.q);
     g.pos_mask = ~0ull;
-    g.cbits = 0; g.rbits = 0;
+    g.cbits = 0; g.rbits = 0; g.short_below = 0; g.only_below = 0;
     return g;
   };
   // the positions the probes of query lengths [lo, hi] can ask for: start of piece t (t * m / (k+1)) plus a shift in [-k, k]
@@ -359,6 +364,10 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
   } else {
     idx[0].len_lo = 0;
   }
+  if (n_idx == 2 && self) {           // the self-join: short x long pairs belong to the long side, the second index holds the short barcodes only
+    idx[0].g.short_below = idx[0].len_lo;
+    idx[1].g.only_below = idx[0].len_lo;
+  }
   ctx->stats[PCB_STAT_SEED_LEN] = idx[0].g.q;
   for (int t = 0; t < n_idx; t++) {
     idx[t].g.pos_mask = probe_positions(idx[t].g, idx[t].len_lo, idx[t].len_hi);
@@ -369,7 +378,7 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
         (uint64_t)U * (uint64_t)__builtin_popcountll(idx[t].g.pos_mask & (idx[t].g.npos >= 64 ? ~0ull : (1ull << idx[t].g.npos) - 1ull)) >= 8ull * idx[t].g.nbins;
     if (t == 0) idx[0].g.rbits = (lanes && ctx->probe_classes && long_bins) ? 3 : 0;
     idx[t].g.rbits = idx[0].g.rbits;
-    idx[t].g.cbits = long_bins ? idx[t].g.rbits : 0;
+    idx[t].g.cbits = (long_bins && !idx[t].g.only_below) ? idx[t].g.rbits : 0;
     const SeedGeom &g = idx[t].g;
     const size_t n_sub = (size_t)g.nbins << g.cbits;
     DevBuf<uint32_t> cursor(ctx, n_sub + 1);

@@ -34,6 +34,12 @@ struct SeedGeom {
   int32_t cbits;     // every bin is split into 2^cbits sub-bins by the low bits of the target (its CLASS), see owns_pair()
   int32_t rbits;     // the ownership rule of the whole search (all its indexes): 0 = parity, else classes of rbits bits;
                      // an index with sub-bins has cbits == rbits, one without walks whole bins under the same rule
+  // Two indexes (edit_pairs.cu): barcodes shorter than q * (k + 1) cannot probe the main index (their pieces are shorter
+  // than its seeds).  A pair of a SHORT and a long barcode is therefore owned by the long one, which finds it through the
+  // main index like any other (the pigeonhole argument holds from either side); the second index only holds the short
+  // barcodes and only they probe it -- it costs what they cost, not a second pass over every target.
+  int32_t short_below;   // main index: a target shorter than this belongs to the (long) query whatever the rule says; 0: none
+  int32_t only_below;    // second index: only targets shorter than this are indexed; 0: all
 };
 
 // Which side of an unordered pair {i, j} probes for it.  cbits == 0: the parity rule of myers.cuh.  cbits > 0 (big
@@ -41,14 +47,20 @@ struct SeedGeom {
 // the query side.  A bin's entries are grouped by class, so a query of class c starts its walk at sub-bin c: what it
 // skips are exactly pairs it does not own -- on average (C - 1) / 2C of every bin (44 % with 8 classes), where the
 // parity rule reads a whole bin to keep half of it.  Classes interleave, so any index range (a shard) holds all alike.
-PCB_HD bool owns_pair(const SeedGeom &g, int32_t i, int32_t j) {
+PCB_HD bool owns_pair(const SeedGeom &g, int32_t i, int32_t j, int32_t target_len) {
+  if (target_len < g.short_below) return true;
   if (g.rbits == 0) return j != i && is_query_side(i, j);
   const int32_t mask = (1 << g.rbits) - 1;
   return (j & mask) != (i & mask) ? (j & mask) > (i & mask) : j > i;
 }
-// sub-bin of target j in bin `bin`
-PCB_HD uint32_t seed_slot(const SeedGeom &g, uint32_t bin, int32_t j) {
-  return (bin << g.cbits) | ((uint32_t)j & ((1u << g.cbits) - 1u));
+// sub-bin of target j (of length len_j) in bin `bin`; short targets sit in the last class, where every probe passes
+PCB_HD uint32_t seed_slot(const SeedGeom &g, uint32_t bin, int32_t j, int32_t len_j) {
+  const uint32_t mask = (1u << g.cbits) - 1u;
+  return (bin << g.cbits) | (len_j < g.short_below ? mask : ((uint32_t)j & mask));
+}
+// ... and where the walk of query i starts in it
+PCB_HD uint32_t seed_slot_of_query(const SeedGeom &g, uint32_t bin, int32_t i) {
+  return (bin << g.cbits) | ((uint32_t)i & ((1u << g.cbits) - 1u));
 }
 
 PCB_HD uint32_t seed_bin(const SeedGeom g, uint64_t L, uint64_t H, int src_pos, int bin_pos) {
@@ -171,7 +183,7 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu, ProbeStage
           if (p >= 0 && p < g.npos && qm >= a.len_lo && qm <= a.len_hi) {     // queries of other lengths use the other index
             const Planes16 pl = a.planes[qi];
             const uint32_t bin = seed_bin(g, pl.x, pl.y, st, p);
-            lo = a.bin_off[seed_slot(g, bin, qi)]; hi = a.bin_off[(bin + 1u) << g.cbits];      // my class and the ones above
+            lo = a.bin_off[seed_slot_of_query(g, bin, qi)]; hi = a.bin_off[(bin + 1u) << g.cbits];      // my class and the ones above
             qcounts = sketch_counts(a.sketch[qi]);
             // the seed matches exactly: the errors are before it or after it -- start the recurrence on the longer side
             qrev = (st < qm - (st + g.q)) ? 0x80000000u : 0u;
@@ -197,7 +209,7 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu, ProbeStage
           const SeedEnt en = a.ent[lo++];
           j = en.j;
           n_walked++;
-          if (owns_pair(g, qi, j)) {
+          if (owns_pair(g, qi, j, (int32_t)(en.sk >> 24))) {
             n_sided++;
             const uint32_t sk = en.sk;
             const int32_t dl = qm - (int32_t)(sk >> 24);
@@ -222,7 +234,7 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu, ProbeStage
           const SeedEnt en = stg->ent[cur][s_off + (uint32_t)lane];
           j = en.j;
           n_walked++;
-          if (owns_pair(g, c_qi, j)) {
+          if (owns_pair(g, c_qi, j, (int32_t)(en.sk >> 24))) {
             n_sided++;
             const uint32_t sk = en.sk;
             const int32_t dl = c_qm - (int32_t)(sk >> 24);
@@ -256,7 +268,7 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu, ProbeStage
           const SeedEnt en = simt::ld_stream(&a.ent[e]);
           j = en.j;
           n_walked++;
-          if (owns_pair(g, c_qi, j)) {
+          if (owns_pair(g, c_qi, j, (int32_t)(en.sk >> 24))) {
             n_sided++;
             const uint32_t sk = en.sk;
             const int32_t dl = c_qm - (int32_t)(sk >> 24);

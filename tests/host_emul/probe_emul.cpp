@@ -23,6 +23,7 @@ extern "C" int64_t emul_probe(const uint64_t *planes, const int32_t *len, int32_
   g.npos = g.q == 0 ? 1 : max_len - g.q + 1;
   g.nbins = g.q == 0 ? 1u : (uint32_t)g.npos << (2 * g.q);
   g.pos_mask = ~0ull;
+  g.short_below = 0; g.only_below = 0;
   g.rbits = (seed & 0x40000000u) ? 3 : 0;              // bit 30 of the seed: the class rule, bins split into 8 classes (owns_pair)
   g.cbits = g.q > 0 && !(seed & 0x20000000u) ? g.rbits : 0;      // (bit 29: whole bins under the class rule, as a second index has them)
   const size_t n_sub = (size_t)g.nbins << g.cbits;
@@ -31,7 +32,7 @@ extern "C" int64_t emul_probe(const uint64_t *planes, const int32_t *len, int32_
   for (int32_t j = 0; j < U; j++)
     for (int32_t p = 0; p < g.npos; p++) {
       if (g.q > 0 && p + g.q > len[j]) continue;
-      items.push_back({seed_slot(g, seed_bin(g, planes[2 * j], planes[2 * j + 1], p, p), j), j});
+      items.push_back({seed_slot(g, seed_bin(g, planes[2 * j], planes[2 * j + 1], p, p), j, len[j]), j});
     }
   std::stable_sort(items.begin(), items.end(), [](auto &x, auto &y) { return x.first < y.first; });
   std::vector<SeedEnt> ent(items.size() + 2);
