@@ -116,7 +116,10 @@ enum { PCB_OPT_REPLAY_SHAPE = 0, PCB_OPT_TRACE = 1 /* 1: host-side lap times of 
        PCB_OPT_PROBE_STAGING = 5 /* 1: the pair search walks long bins through shared memory (cp.async.bulk + mbarrier)
                                     instead of streaming loads; same results, kept for the measurement in profiles/ */,
        PCB_OPT_PROBE_CLASSES = 6 /* 1 (default): long bins of the seed index are grouped by target class so that a probe
-                                    skips most entries of pairs it does not own; 0: whole bins, parity rule */ };
+                                    skips most entries of pairs it does not own; 0: whole bins, parity rule */,
+       PCB_OPT_SEED_BINS_LOG2 = 7 /* the seed length of the pair search is capped so that its index has at most 2^value
+                                     bins (8..28, default 26): shorter seeds = a smaller table and longer bins */,
+       PCB_OPT_SMALL_WARPS = 8 /* warps per block of the small-component replay kernel: 1, 2 or 4 */ };
 enum { PCB_REPLAY_AUTO = 0, PCB_REPLAY_THREAD = 1, PCB_REPLAY_WARP = 2, PCB_REPLAY_HUGE = 3 };
 int pcb_set_option(pcb_ctx *ctx, int option, int64_t value);
 /* Block until everything queued on the context's stream has finished. */

@@ -88,6 +88,14 @@ class Context:
         if getattr(self, "_classes_set", 1) != classes:
             self._check(self.lib.pcb_set_option(self.h, _lib.OPT_PROBE_CLASSES, classes))
             self._classes_set = classes
+        sw = int(os.environ.get("PCB_SMALL_WARPS") or getattr(self, "_small_warps_default", 4))
+        if getattr(self, "_sw_set", 4) != sw:
+            self._check(self.lib.pcb_set_option(self.h, _lib.OPT_SMALL_WARPS, sw))
+            self._sw_set = sw
+        bins = int(os.environ.get("PCB_SEED_BINS_LOG2") or 26)
+        if getattr(self, "_bins_set", 26) != bins:
+            self._check(self.lib.pcb_set_option(self.h, _lib.OPT_SEED_BINS_LOG2, bins))
+            self._bins_set = bins
         # giant-tier knobs: environment > set_huge() > the library's defaults, applied per call like the shape
         for env, opt, default in (("PCB_HUGE_READS", _lib.OPT_HUGE_READS, 256), ("PCB_HUGE_CAP", _lib.OPT_HUGE_CAP, 2048),
                                   ("PCB_HUGE_WINDOW", _lib.OPT_HUGE_WINDOW, 32768)):

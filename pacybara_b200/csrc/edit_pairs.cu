@@ -330,7 +330,7 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
     SeedGeom g;
     g.k = k;
     g.q = q > 12 ? 12 : q;
-    while (g.q > 0 && ((uint64_t)(bc.max_len - g.q + 1) << (2 * g.q)) > (1ull << 26)) g.q--;
+    while (g.q > 0 && ((uint64_t)(bc.max_len - g.q + 1) << (2 * g.q)) > (1ull << ctx->seed_bins_log2)) g.q--;
     g.npos = g.q == 0 ? 1 : bc.max_len - g.q + 1;
     g.nbins = g.q == 0 ? 1u : (uint32_t)g.npos << (2 * g.q);
     g.pos_mask = ~0ull;

@@ -337,18 +337,21 @@ __global__ void large_scratch_kernel(const int32_t *__restrict__ comp_reads, con
 }
 
 // ------------------------------------------------------------------------------------------ replay kernels
-constexpr int SMALL_BLOCK = 128;
 // One warp per component of at most 32 reads, one lane per read (merge_small.cuh).  A component it is not eligible
 // for (more than 32 live mutations, huge qualities) goes on the declined list -- or, when a local copy would not fit
 // the medium kernel either, on the late list the host looks at after the step.
-__global__ void __launch_bounds__(SMALL_BLOCK) component_kernel_small(MergeCtx c, int32_t n_comp, int32_t *__restrict__ counters,
-                                                                      int32_t *__restrict__ declined, int32_t *__restrict__ late) {
-  __shared__ SmallSmem sm_all[SMALL_BLOCK / 32];
+// WARPS per block: an SM releases registers and shared memory per BLOCK, so a block whose other warps are done keeps their
+// share until its slowest component is through (25 % of the warp slots busy with 4 warps per block, profiles/r02q);
+// PCB_OPT_SMALL_WARPS picks the instantiation.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) component_kernel_small(MergeCtx c, int32_t n_comp, int32_t *__restrict__ counters,
+                                                                     int32_t *__restrict__ declined, int32_t *__restrict__ late) {
+  __shared__ SmallSmem sm_all[WARPS];
   __shared__ int32_t jthr[33];
   __shared__ int32_t tally[3];                       // links, tests, warps that are done
-  if (threadIdx.x < 33) jthr[threadIdx.x] = c.prm.jthr[threadIdx.x];
+  for (int i = threadIdx.x; i < 33; i += WARPS * 32) jthr[i] = c.prm.jthr[i];
   if (threadIdx.x < 3) tally[threadIdx.x] = 0;
-  __syncthreads();
+  if (WARPS > 1) __syncthreads(); else __syncwarp();
   const int32_t comp = (int32_t)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (comp < n_comp) {
@@ -357,11 +360,11 @@ __global__ void __launch_bounds__(SMALL_BLOCK) component_kernel_small(MergeCtx c
     if (lane == 0 && rc == 2) late[atomicAdd(&counters[CNT_LATE], 1)] = comp;
   }
   // links / tests: one atomic per block and counter, spread over 32 slots (status[4 + 2 * slot + which]), added by
-  // whichever warp finishes last -- no barrier: a warp that is done leaves, its slot goes to the next block
+  // whichever warp finishes last (no barrier at the end)
   __syncwarp();
   if (lane == 0) {
     __threadfence_block();
-    if (atomicAdd(&tally[2], 1) == SMALL_BLOCK / 32 - 1) {
+    if (atomicAdd(&tally[2], 1) == WARPS - 1) {
       const int32_t links = atomicAdd(&tally[0], 0), tests = atomicAdd(&tally[1], 0);
       if (links) atomicAdd(&c.status[4 + 2 * (blockIdx.x & 31)], links);
       if (tests) atomicAdd(&c.status[5 + 2 * (blockIdx.x & 31)], tests);
@@ -941,8 +944,12 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
     PCB_CUDA(cudaEventRecord(ctx->ev_copied, ctx->copy_stream));
   }
   if (shape == PCB_REPLAY_AUTO && n_comp > 0) {
-    PCB_LAUNCH(ctx, component_kernel_small, grid_for((size_t)n_comp * 32, SMALL_BLOCK), SMALL_BLOCK, 0, c, n_comp, counters.p, declined.p,
-               late.p);
+    if (ctx->small_warps == 1)
+      PCB_LAUNCH(ctx, component_kernel_small<1>, grid_for((size_t)n_comp * 32, 32), 32, 0, c, n_comp, counters.p, declined.p, late.p);
+    else if (ctx->small_warps == 2)
+      PCB_LAUNCH(ctx, component_kernel_small<2>, grid_for((size_t)n_comp * 32, 64), 64, 0, c, n_comp, counters.p, declined.p, late.p);
+    else
+      PCB_LAUNCH(ctx, component_kernel_small<4>, grid_for((size_t)n_comp * 32, 128), 128, 0, c, n_comp, counters.p, declined.p, late.p);
     // whatever it declined (the count is only known on the device): a fixed grid walks the list
     PCB_LAUNCH(ctx, component_kernel_medium, medium_grid / 4u, 32, sizeof(MediumSmem), c, declined.p, counters.p + CNT_DECLINED);
   }
