@@ -335,6 +335,14 @@ def main():
         t = torch.tensor([d2h_bytes, n_rows_local, stats["pairs_scored"], stats["cells"], launches], dtype=torch.int64, device=dev)
         dist.all_reduce(t)
         d2h_bytes, n_rows, pairs_all, cells_all, launches = (int(x) for x in t.tolist())
+        # how evenly the (query x target) blocks of the pair search and the component shards of the merge load the ranks
+        mine = torch.tensor([stats["pairs_scored"], n_rows_local, int(out["local_stats"].get("components", 0))], dtype=torch.int64, device=dev)
+        every = torch.empty(world * 3, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(every, mine)
+        every = every.view(world, 3).tolist()
+        shard_balance = dict(pairs_scored=[e[0] for e in every], rows=[e[1] for e in every], components=[e[2] for e in every],
+                             pair_grid="%d query x %d target groups" % multigpu.pair_grid(world),
+                             note="per rank; pairs: blocks of the pair grid, rows / components: shards by component label mod N")
         h2d_bytes += (world - 1) * pinned["mut_rank"].numel() * pinned["mut_rank"].element_size()
         # per stage: the slowest rank (what the step waits for), and which stage limits the step
         keys = sorted(stage_ms)
@@ -466,6 +474,8 @@ def main():
                 parity=parity)
     if stage_limit:
         line["stage_limit"] = stage_limit
+    if world > 1:
+        line["shard_balance"] = shard_balance
     if world == 1 and not args.no_files_e2e:
         try:
             line["files_e2e"] = files_e2e(args, ctx, lib, params)

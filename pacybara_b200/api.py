@@ -88,8 +88,8 @@ class Context:
         if getattr(self, "_classes_set", 1) != classes:
             self._check(self.lib.pcb_set_option(self.h, _lib.OPT_PROBE_CLASSES, classes))
             self._classes_set = classes
-        sw = int(os.environ.get("PCB_SMALL_WARPS") or getattr(self, "_small_warps_default", 4))
-        if getattr(self, "_sw_set", 4) != sw:
+        sw = int(os.environ.get("PCB_SMALL_WARPS") or getattr(self, "_small_warps_default", 1))
+        if getattr(self, "_sw_set", 1) != sw:
             self._check(self.lib.pcb_set_option(self.h, _lib.OPT_SMALL_WARPS, sw))
             self._sw_set = sw
         bins = int(os.environ.get("PCB_SEED_BINS_LOG2") or 26)
