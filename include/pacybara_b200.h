@@ -13,6 +13,7 @@
  *                        consensus genotype / barcode)
  *   pcb_cluster_reads <- the three of them back to back, nothing leaving the device
  *   pcb_compact_shard <- (multi-GPU) the part of a merge result one rank owns, compacted
+ *   pcb_concat_tokens <- src/pacybara_cluster.py:546-567 (writeOutput: the rows of clusters.csv.gz as text)
  * and, either side of the path:
  *   pcb_tag_rows       <- src/pacybara_translate.R:58-68, src/pacybara_softfilter.R:46-63      (f1)
  *   pcb_text_open, pcb_fastq_*, pcb_geno_*, pcb_uptag_*, pcb_rank_strings
@@ -265,6 +266,20 @@ int pcb_compact_shard(pcb_ctx *ctx, int mem_in, int mem_out, int32_t R, int64_t 
                       int32_t *n_own, int32_t *own_read, int32_t *own_root, int32_t *own_pos, int32_t *own_bucket,
                       int32_t *n_rows, int64_t *n_calls, int32_t *row_rep, int32_t *c_size, int64_t *c_key, int32_t *c_bc,
                       int32_t *c_up, int64_t *c_call_off, int32_t *c_call_n, int32_t *c_call_mut);
+
+/*
+ * a14 -- the writer (src/pacybara_cluster.py:546-567).  A row of clusters.csv.gz is made of slices of texts the caller
+ * already holds (read ids, mutation names, barcodes, uptags) and one-byte separators.
+ *   src [n_src]                    the bytes those slices come from (any concatenation of the caller's texts)
+ *   tok_off / tok_len [n_tok]      the slices ("tokens"): src[tok_off[t] .. tok_off[t] + tok_len[t])
+ *   item_tok / item_sep [n_items]  the output, item by item: token item_tok[k], followed by the byte item_sep[k] unless 0
+ *   out [out_cap], *out_len        the concatenation and its length.  PCB_E_CAPACITY (with *out_len = bytes needed) when
+ *                                  it does not fit; PCB_E_INPUT for a token outside src or an item naming no token.
+ * pacybara_b200/tablefmt.py lists the items of a cluster table (`vbc , ubc , id | id ... , size , mut ; mut ... \n`).
+ */
+int pcb_concat_tokens(pcb_ctx *ctx, int mem, const uint8_t *src, int64_t n_src, const int64_t *tok_off, const int32_t *tok_len,
+                      int64_t n_tok, const int32_t *item_tok, const uint8_t *item_sep, int64_t n_items, uint8_t *out, int64_t out_cap,
+                      int64_t *out_len);
 
 /*
  * f4 -- merging two cluster libraries by virtual barcode and genotype (src/pacybara_merge.R:48-101).

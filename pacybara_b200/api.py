@@ -278,6 +278,28 @@ class Context:
                                           self._in(row_size, np.int32, keep), int(n_bc_ids), int(n_up_ids), float(min_ratio), *ptrs))
         return {k: v[:n] for k, v in outs.items()}
 
+    # ------------------------------------------------------------------ a14
+    def concat_tokens(self, src: np.ndarray, tok_off: np.ndarray, tok_len: np.ndarray, item_tok: np.ndarray, item_sep: np.ndarray,
+                      size_hint: Optional[int] = None) -> bytes:
+        """Ragged concatenation on the device (pcb_concat_tokens): item k is src[tok_off[t] : tok_off[t] + tok_len[t]] for
+        t = item_tok[k], followed by the byte item_sep[k] unless that is 0.  Host arrays in, bytes out."""
+        keep: list = []
+        n_src, n_tok, n_items = int(src.shape[0]), int(tok_off.shape[0]), int(item_tok.shape[0])
+        cap = int(size_hint) if size_hint is not None else int(np.asarray(tok_len, dtype=np.int64)[np.asarray(item_tok, dtype=np.int64)].sum()
+                                                                 + np.count_nonzero(item_sep))
+        args = (self._in(src, np.uint8, keep), n_src, self._in(tok_off, np.int64, keep), self._in(tok_len, np.int32, keep), n_tok,
+                self._in(item_tok, np.int32, keep), self._in(item_sep, np.uint8, keep), n_items)
+        for _ in range(2):
+            out = np.empty(max(cap, 1), dtype=np.uint8)
+            n = C.c_int64(0)
+            rc = self.lib.pcb_concat_tokens(self.h, _lib.MEM_HOST, *args, out.ctypes.data_as(C.c_void_p), cap, C.byref(n))
+            if rc == _lib.PCB_E_CAPACITY and int(n.value) > cap:
+                cap = int(n.value)
+                continue
+            self._check(rc)
+            return out[:int(n.value)].tobytes()
+        self._check(rc)
+
     # ------------------------------------------------------------------ f4
     def merge_libraries(self, vbc1, geno1, size1, vbc2, geno2, size2, n_ids: int) -> Dict:
         """Rows of a second cluster library against a first one (pcb_merge_libraries): per row of the second library its

@@ -9,7 +9,7 @@ from typing import List
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "_pcb.so")
-SOURCES = ["prims.cu", "bucket.cu", "edit_pairs.cu", "merge.cu", "tagging.cu", "libmerge.cu", "ingest.cu", "abi.cu"]
+SOURCES = ["prims.cu", "bucket.cu", "edit_pairs.cu", "merge.cu", "tagging.cu", "libmerge.cu", "ingest.cu", "format.cu", "abi.cu"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-shared"]
 

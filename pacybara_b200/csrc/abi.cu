@@ -556,6 +556,25 @@ int pcb_merge_libraries(pcb_ctx *ctx, int mem, int32_t n1, const int32_t *vbc1, 
   });
 }
 
+// ---- a14: the writer's rows as a ragged concatenation (format.cu)
+int pcb_concat_tokens(pcb_ctx *ctx, int mem, const uint8_t *src, int64_t n_src, const int64_t *tok_off, const int32_t *tok_len, int64_t n_tok,
+                      const int32_t *item_tok, const uint8_t *item_sep, int64_t n_items, uint8_t *out, int64_t out_cap, int64_t *out_len) {
+  if (out_len) *out_len = 0;
+  return guarded(ctx, [&] {
+    if (n_src < 0 || n_tok < 0 || n_items < 0 || out_cap < 0 || !out_len) throw Error(PCB_E_INPUT, "bad shape");
+    if (n_items > 0 && (!tok_off || !tok_len || !item_tok || !item_sep)) throw Error(PCB_E_INPUT, "token and item arrays are required");
+    InArr<uint8_t> d_src(ctx, mem, src, n_src), d_sep(ctx, mem, item_sep, n_items);
+    InArr<int64_t> d_off(ctx, mem, tok_off, n_tok);
+    InArr<int32_t> d_len(ctx, mem, tok_len, n_tok), d_tok(ctx, mem, item_tok, n_items);
+    OutArr<uint8_t> o_out(ctx, mem, out, out_cap);
+    const int64_t total = concat_tokens_dev(ctx, d_src.p, n_src, d_off.p, d_len.p, n_tok, d_tok.p, d_sep.p, n_items, o_out.p, out_cap);
+    *out_len = total;
+    if (total > out_cap) throw Error(PCB_E_CAPACITY, "the output needs " + std::to_string(total) + " bytes");
+    o_out.commit(total);
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
 // ---- f2: tokenizers (ingest.cu)
 
 int pcb_text_open(pcb_ctx *ctx, int mem, const uint8_t *bytes, int64_t n_bytes, pcb_text **out, int64_t *n_lines, int64_t *n_exotic) {

@@ -255,6 +255,8 @@ struct MergeOut {            // device pointers, caller-owned
   int32_t *row_call_n, *call_mut;
 };
 void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out);
+int64_t concat_tokens_dev(pcb_ctx *ctx, const uint8_t *src, int64_t n_src, const int64_t *tok_off, const int32_t *tok_len, int64_t n_tok,
+                          const int32_t *item_tok, const uint8_t *item_sep, int64_t n_items, uint8_t *out, int64_t out_cap);
 void merge_libraries_dev(pcb_ctx *ctx, int32_t n1, const int32_t *vbc1, const int32_t *geno1, const int32_t *size1, int32_t n2,
                          const int32_t *vbc2, const int32_t *geno2, const int32_t *size2, int32_t n_ids, int32_t *size1_out,
                          int32_t *target2, int32_t *klass2);

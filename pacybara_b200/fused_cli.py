@@ -54,8 +54,9 @@ def main(argv=None) -> int:
     ctx = open_context_or_exit(local)
     try:
         ra, names = ingest.arrays_from_files(ctx, bc_file, geno_file, o["uptag"] or None, log=log)
-        bad = [r for r in names["ids"] if "-" in r]
-        if bad:                           # (the same files on every rank: every rank leaves here)
+        ids = names["ids"]
+        bad = [ids.any_contains(b"-")] if hasattr(ids, "any_contains") else [r for r in ids if "-" in r][:1]
+        if bad and bad[0] is not None:    # (the same files on every rank: every rank leaves here)
             log(f"ERROR: read id {bad[0]!r} contains '-'", file=sys.stderr)
             ctx.close()
             if world > 1:
@@ -69,9 +70,14 @@ def main(argv=None) -> int:
             log(f"Clustering {ra.n_reads} reads on {world} GPUs...")
             out = _cluster_sharded(ctx, ra, params, rank, world, full)
         if rank == 0:
-            table = pipeline.table_from_outputs(out, ra, names)
-            log(f" - {out['n_buckets']} barcode groups, {out['n_edges']} barcode pairs, {len(table)} rows")
-            hostdata.write_clusters_csv(o["out"], table)
+            text = pipeline.table_text_from_outputs(ctx, out, ra, names)      # formatted on the device when the slices are there
+            if text is not None:
+                log(f" - {out['n_buckets']} barcode groups, {out['n_edges']} barcode pairs, {text.count(b"\n") - 1} rows")
+                hostdata.write_clusters_text(o["out"], text)
+            else:
+                table = pipeline.table_from_outputs(out, ra, names)
+                log(f" - {out['n_buckets']} barcode groups, {out['n_edges']} barcode pairs, {len(table)} rows")
+                hostdata.write_clusters_csv(o["out"], table)
             log("Done!")
     except Exception:
         ctx.close()

@@ -458,11 +458,15 @@ def _rows_to_table_loop(rows, out, row_ptr, call_ptr, row_bc, row_up, member_ids
         out.append((vbc, ubc, "|".join(member_ids[lo:hi]), hi - lo, geno))
 
 
-def gzip_members(data: bytes, chunk: int = 8 << 20, level: int = 6) -> List[bytes]:
+def gzip_members(data: bytes, chunk: Optional[int] = None, level: int = 6) -> List[bytes]:
     """`data` as a sequence of gzip members compressed concurrently (zlib releases the GIL); their
-    concatenation is one valid gzip file (RFC 1952 2.2), which gzip.open, zcat and R's gzfile read as a whole."""
+    concatenation is one valid gzip file (RFC 1952 2.2), which gzip.open, zcat and R's gzfile read as a whole.
+    chunk: bytes per member; default: two members per host core, at least 1 MiB each."""
+    import os
     import zlib
     from concurrent.futures import ThreadPoolExecutor
+    if chunk is None:
+        chunk = max(1 << 20, -(-len(data) // (2 * (os.cpu_count() or 1))))
 
     def one(i):
         c = zlib.compressobj(level, zlib.DEFLATED, 31)
@@ -484,6 +488,13 @@ def write_clusters_csv(path: str, table: Sequence[Tuple[str, str, str, int, str]
         buf.write(f"{vbc},{ubc},{reads},{size},{geno}\n")
     with open(path, "wb") as fh:
         for member in gzip_members(buf.getvalue().encode("utf-8")):
+            fh.write(member)
+
+
+def write_clusters_text(path: str, text: bytes) -> None:
+    """The same file from the table's text (pacybara_b200/tablefmt.py)."""
+    with open(path, "wb") as fh:
+        for member in gzip_members(text):
             fh.write(member)
 
 
@@ -585,12 +596,19 @@ def rows_from_merge_outputs(out: Dict[str, np.ndarray]) -> ClusterRows:
     row_of_rep = np.full(R, -1, dtype=np.int64)
     row_of_rep[rep] = np.arange(n_rows)
     row_of_read = row_of_rep[out["read_root"]]
-    members = np.lexsort((out["read_pos"], row_of_read)).astype(np.int32)
     sizes = row_size[rep].astype(np.int64)
     row_ptr = np.zeros(n_rows + 1, dtype=np.int64)
     np.cumsum(sizes, out=row_ptr[1:])
-    if int(row_ptr[-1]) != R:
+    if int(row_ptr[-1]) != R or (R and int(row_of_read.min()) < 0):
         raise RuntimeError(f"merge outputs are inconsistent: rows hold {int(row_ptr[-1])} reads, expected {R}")
+    # a read's place in the table: start of its row + its position in the member list (no sort over the reads)
+    dest = row_ptr[row_of_read] + np.asarray(out["read_pos"]).astype(np.int64)
+    members = np.full(R, -1, dtype=np.int32)
+    if R and (int(dest.min()) < 0 or int(dest.max()) >= R):
+        raise RuntimeError("merge outputs are inconsistent: a read's position lies outside its row")
+    members[dest] = np.arange(R, dtype=np.int32)
+    if R and int(members.min()) < 0:
+        raise RuntimeError("merge outputs are inconsistent: two reads share a place in a row")
     ncall = out["row_call_n"][rep].astype(np.int64)
     call_ptr = np.zeros(n_rows + 1, dtype=np.int64)
     np.cumsum(ncall, out=call_ptr[1:])

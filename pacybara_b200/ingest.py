@@ -144,9 +144,10 @@ def arrays_from_bytes(ctx: Context, fastq: bytes, geno: bytes, uptag: Optional[b
                 raise KeyError(f"{j['missing']} bucketed read(s) have no genotype record")
             g = ge.geno_fetch()
             lap("geno_join")
-            mut_names = _slices(geno, g["mut_off"].cpu().numpy(), g["mut_len"].cpu().numpy())
+            mut_off, mut_len = g["mut_off"].cpu().numpy(), g["mut_len"].cpu().numpy()
+            mut_names = _slices(geno, mut_off, mut_len)
         lap("mut_names")
-        up_id, up_names = None, None
+        up_id, up_names, up_slices = None, None, None
         if uptag is not None:
             up = fq if uptag is fastq else Text(ctx, uptag)                # the same file: one copy, one index
             try:
@@ -158,12 +159,17 @@ def arrays_from_bytes(ctx: Context, fastq: bytes, geno: bytes, uptag: Optional[b
                 if uj["n_records"] > 0:                      # `if len(tags) > 0`, pacybara_cluster.py:376
                     u = up.uptag_fetch()
                     up_id = u["up_id"]
-                    up_names = _slices(uptag, u["tag_off"].cpu().numpy(), u["tag_len"].cpu().numpy())
+                    tag_off, tag_len = u["tag_off"].cpu().numpy(), u["tag_len"].cpu().numpy()
+                    up_names = _slices(uptag, tag_off, tag_len)
+                    up_slices = (uptag, tag_off, tag_len)
             finally:
                 if up is not fq:
                     up.close()
     lap("uptags")
-    ids = _slices(fastq, f["id_off"].cpu().numpy(), f["id_len"].cpu().numpy())
+    # the read ids stay slices of the FASTQ bytes: the writer formats the table from them on the device
+    # (pacybara_b200/tablefmt.py); the million Python strings are only made when somebody asks (LazyIds)
+    id_off, id_len = f["id_off"].cpu().numpy(), f["id_len"].cpu().numpy()
+    ids = LazyIds(fastq, id_off, id_len)
     lap("id_strings")
     mut_rank = torch.from_numpy(pipeline.mut_rank_of(mut_names)).to(dev)
     ra = pipeline.ReadArrays(seq=f["seq"], qual=f["qual"], length=f["length"], lexrank=lexrank, geno_ptr=g["geno_ptr"],
@@ -171,7 +177,51 @@ def arrays_from_bytes(ctx: Context, fastq: bytes, geno: bytes, uptag: Optional[b
     assert ra.n_reads == R
     _decoded.clear()
     lap("mut_rank")
-    return ra, dict(ids=ids, mut_names=mut_names, up_names=up_names)
+    slices = dict(ids=(fastq, id_off, id_len), muts=(geno, mut_off, mut_len), up=up_slices)
+    return ra, dict(ids=ids, mut_names=mut_names, up_names=up_names, slices=slices)
+
+
+class LazyIds:
+    """The read ids as a sequence of str that is only built (10^6 slices, 0.15 s) when it is indexed or iterated."""
+
+    def __init__(self, raw: bytes, off: np.ndarray, length: np.ndarray):
+        self.raw, self.off, self.length = raw, off, length
+        self._list: Optional[List[str]] = None
+
+    def _get(self) -> List[str]:
+        if self._list is None:
+            self._list = _slices(self.raw, self.off, self.length)
+            _decoded.clear()
+        return self._list
+
+    def __len__(self):
+        return int(self.off.shape[0])
+
+    def __getitem__(self, i):
+        return self._get()[i]
+
+    def __iter__(self):
+        return iter(self._get())
+
+    def __eq__(self, other):
+        return self._get() == (other._get() if isinstance(other, LazyIds) else other)
+
+    __hash__ = None
+
+    def any_contains(self, ch: bytes) -> Optional[str]:
+        """The first id that contains the byte `ch`, without building the strings (None: no id does)."""
+        buf = np.frombuffer(self.raw, dtype=np.uint8)
+        hits = np.flatnonzero(buf == ch[0])
+        if hits.size == 0 or len(self) == 0:
+            return None
+        order = np.argsort(self.off, kind="stable")
+        off, length = self.off[order].astype(np.int64), self.length[order].astype(np.int64)
+        k = np.searchsorted(off, hits, side="right") - 1
+        ok = (k >= 0) & (hits < off[np.maximum(k, 0)] + length[np.maximum(k, 0)])
+        if not ok.any():
+            return None
+        i = int(order[k[ok].min()])
+        return self.raw[int(self.off[i]): int(self.off[i]) + int(self.length[i])].decode("ascii")
 
 
 def arrays_from_files(ctx: Context, bc_file: str, geno_file: str, uptag_file: Optional[str] = None, log=None

@@ -99,7 +99,46 @@ def table_from_outputs(out: Dict, ra: ReadArrays, names: Dict, consensus=None):
             u = consensus([up_names[up_of[r]] for r in members])
         return b, u
 
-    return hostdata.rows_to_table(rows, names["ids"], bc_names, names["up_names"], names["mut_names"], on_alignment=on_alignment)
+    return hostdata.rows_to_table(rows, list(names["ids"]), bc_names, names["up_names"], names["mut_names"], on_alignment=on_alignment)
+
+
+def table_text_from_outputs(ctx: Context, out: Dict, ra: ReadArrays, names: Dict, consensus=None) -> Optional[bytes]:
+    """The text of clusters.csv (header + rows) with the rows formatted on the device (tablefmt / pcb_concat_tokens), or None
+    when that route is not available: no slice offsets (the line parsers loaded the files) -- table_from_outputs handles
+    that.  consensus: as for table_from_outputs (the few rows with a tied barcode vote are resolved on the host and their
+    strings handed to the formatter)."""
+    sl = names.get("slices")
+    if sl is None:
+        return None
+    from . import tablefmt
+    host = lambda a: a.cpu().numpy() if hasattr(a, "data_ptr") else np.asarray(a)
+    keys = ("read_root", "read_pos", "row_size", "row_key", "row_bc", "row_up", "row_call_off", "row_call_n", "call_mut")
+    rows = hostdata.rows_from_merge_outputs({k: host(out[k]) for k in keys})
+    as_slices = lambda t: tablefmt.Slices(np.frombuffer(t[0], dtype=np.uint8), np.asarray(t[1]), np.asarray(t[2]))
+    bor = host(out["bucket_of_read"])
+    bc = tablefmt.barcode_slices(host(ra.seq), host(ra.length), bor, int(out["n_buckets"]))
+    ids = as_slices(sl["ids"])
+    up = None
+    if sl.get("up") is not None:
+        up = as_slices(sl["up"])
+        if sl["up"][0] is sl["ids"][0]:                       # the uptag file is the barcode file: one copy of its bytes
+            up.text = ids.text
+    # rows whose barcode / uptag vote is tied among >= 3 reads: the reference aligns the members' strings (:484-511)
+    bc_text, up_text = {}, {}
+    need = np.flatnonzero((rows.row_bc == hostdata.NEEDS_ALIGNMENT) | (rows.row_up == hostdata.NEEDS_ALIGNMENT))
+    if need.size:
+        if consensus is None:
+            from .cluster import alignment_consensus as consensus
+        text_of = lambda s, i: s.text[int(s.off[i]): int(s.off[i]) + int(s.len[i])].tobytes().decode("ascii")
+        up_of = host(ra.up_id) if ra.up_id is not None else bor
+        up_src = up if up is not None else bc
+        for i in need.tolist():
+            members = rows.row_members[rows.row_ptr[i]: rows.row_ptr[i + 1]]
+            if rows.row_bc[i] == hostdata.NEEDS_ALIGNMENT:
+                bc_text[i] = consensus([text_of(bc, bor[r]) for r in members])
+            if rows.row_up[i] == hostdata.NEEDS_ALIGNMENT:
+                up_text[i] = consensus([text_of(up_src, up_of[r]) for r in members])
+    return tablefmt.table_bytes(ctx, rows, ids, bc, up, as_slices(sl["muts"]), bc_text, up_text)
 
 
 def arrays_from_text(fastq_stream, geno_stream, uptag_stream=None, ctx: Optional[Context] = None

@@ -103,9 +103,15 @@ def test_synthetic_files(ctx, tmp_path, cfg, scale, style):
         ref = pipeline.arrays_from_text(fq, ge, up, ctx)
     assert_same(host_view(ra, names), host_view(*ref))
     # and the clusters of the two loaders are the same table
-    a = pipeline.table_from_outputs(pipeline.cluster_reads(ctx, ra), ra, names)
+    out = pipeline.cluster_reads(ctx, ra)
+    a = pipeline.table_from_outputs(out, ra, names)
     b = pipeline.table_from_outputs(pipeline.cluster_reads(ctx, ref[0]), *ref)
     assert a == b and len(a) > 0
+    # the writer: rows formatted on the device from the slices of the input texts (pcb_concat_tokens) == the host loop's file
+    text = pipeline.table_text_from_outputs(ctx, out, ra, names)
+    want = "virtualBarcode,upBarcode,reads,size,geno\n" + "".join(f"{v},{u},{r},{s},{g}\n" for v, u, r, s, g in a)
+    assert text == want.encode("ascii")
+    assert pipeline.table_text_from_outputs(ctx, out, ref[0], ref[1]) is None          # line-parser route: no slices, host loop
 
 
 @pytest.mark.parametrize("what,fastq,geno", [
@@ -187,8 +193,10 @@ def test_quirky_files_against_the_reference_itself(ctx):
     assert names["ids"] == reads.ids and len(reads.ids) < case["fastq"].count("\n+")        # the '@' qualities dropped reads
     for full in (True, False):
         out = pipeline.cluster_reads(ctx, ra, full_table=full, **case["params"])
-        got = canon.canon_table(pipeline.table_from_outputs(out, ra, names))
-        assert got == util.golden_table(case)
+        table = pipeline.table_from_outputs(out, ra, names)
+        assert canon.canon_table(table) == util.golden_table(case)
+        text = pipeline.table_text_from_outputs(ctx, out, ra, names)                   # the device-formatted file, CRLF ids and all
+        assert text == ("virtualBarcode,upBarcode,reads,size,geno\n" + "".join(f"{v},{u},{r},{s},{g}\n" for v, u, r, s, g in table)).encode()
     # and the bucketing text the reference printed, from the tokenizer's matrices
     fq = ingest.fastq_from_bytes(ctx, case["fastq"].encode())
     res = ctx.bucket(fq.seq, fq.qual, fq.length)
