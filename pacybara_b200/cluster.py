@@ -150,24 +150,40 @@ def main(argv=None) -> int:
         print(USAGE)
         return 0
     from .api import open_context_or_exit
+    ctx = open_context_or_exit(0)
     log("Loading data...")
-    with hostdata.open_text(o["ed"]) as ed, hostdata.open_text(o["geno"]) as ge, hostdata.open_text(o["preclust"]) as pc:
-        up = hostdata.open_text(o["uptag"]) if o["uptag"] is not None else None
+    params = dict(max_diff=o["max_diff"], min_qual=o["min_qual"], min_jaccard=o["min_jaccard"], min_matches=o["min_matches"])
+    job, slices = None, None
+    try:
+        # genotypes and uptags through the device tokenizers (the line loaders cost a Python iteration per read)
+        from . import ingest
         try:
-            job = hostdata.load_cluster_job(ed, ge, pc, up, max_diff=o["max_diff"], min_qual=o["min_qual"],
-                                            min_jaccard=o["min_jaccard"], min_matches=o["min_matches"])
-        finally:
-            if up is not None:
-                up.close()
+            job, slices = ingest.cluster_job_from_files(ctx, o["ed"], o["geno"], o["preclust"], o["uptag"], **params)
+        except ingest.NeedsLineParser as e:
+            log(f" - tokenizer declined ({e}); using the line parser")
+    except BaseException:
+        ctx.close()
+        raise
+    if job is None:
+        with hostdata.open_text(o["ed"]) as ed, hostdata.open_text(o["geno"]) as ge, hostdata.open_text(o["preclust"]) as pc:
+            up = hostdata.open_text(o["uptag"]) if o["uptag"] is not None else None
+            try:
+                job = hostdata.load_cluster_job(ed, ge, pc, up, **params)
+            except BaseException:
+                ctx.close()
+                raise
+            finally:
+                if up is not None:
+                    up.close()
     bad = [r for r in job.ids if "-" in r]
     if bad:
         log(f"ERROR: read id {bad[0]!r} contains '-': the pair-id scheme of pacybara_cluster.py (:152-157,418) "
             "cannot represent it", file=sys.stderr)
+        ctx.close()
         return 1
     p = job.problem
     pairs = hostdata.dedupe_ed_rows(job.ed_q, job.ed_r, job.ed_d, p.n_buckets, p.max_diff)
     log(f"Clustering {p.n_reads} reads in {p.n_buckets} barcode groups, {len(pairs.q)} barcode pairs on the GPU...")
-    ctx = open_context_or_exit(0)
     out = ctx.merge(p, pairs)
     rows = hostdata.rows_from_merge_outputs(out)
     log(f" - {ctx.stat('components')} components, {ctx.stat('tests')} cluster tests, {ctx.stat('links')} links")
@@ -181,9 +197,25 @@ def main(argv=None) -> int:
             u = alignment_consensus([names[ids[r]] for r in members])
         return b, u
 
-    table = hostdata.rows_to_table(rows, job.ids, job.bc_names, job.up_names, job.mut_names, on_alignment=on_alignment)
     log(f"Writing output to file {o['out']}")
-    hostdata.write_clusters_csv(o["out"], table)
+    if slices is not None:
+        # the rows as a ragged concatenation of slices of the input texts, on the device (tablefmt / pcb_concat_tokens)
+        import numpy as np
+        from . import tablefmt
+        mk = lambda t: tablefmt.Slices(np.frombuffer(t[0], dtype=np.uint8), np.asarray(t[1]), np.asarray(t[2]))
+        bc_text, up_text = {}, {}
+        for i in np.flatnonzero((rows.row_bc == hostdata.NEEDS_ALIGNMENT) | (rows.row_up == hostdata.NEEDS_ALIGNMENT)).tolist():
+            b, u = on_alignment(i, rows.row_members[rows.row_ptr[i]: rows.row_ptr[i + 1]], int(rows.row_bc[i]), int(rows.row_up[i]))
+            if isinstance(b, str):
+                bc_text[i] = b
+            if isinstance(u, str):
+                up_text[i] = u
+        text = tablefmt.table_bytes(ctx, rows, mk(slices["ids"]), mk(slices["bc"]), mk(slices["up"]) if slices["up"] is not None else None,
+                                    mk(slices["muts"]), bc_text, up_text)
+        hostdata.write_clusters_text(o["out"], text)
+    else:
+        table = hostdata.rows_to_table(rows, job.ids, job.bc_names, job.up_names, job.mut_names, on_alignment=on_alignment)
+        hostdata.write_clusters_csv(o["out"], table)
     ctx.close()
     log("Done!")
     return 0

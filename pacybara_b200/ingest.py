@@ -181,6 +181,82 @@ def arrays_from_bytes(ctx: Context, fastq: bytes, geno: bytes, uptag: Optional[b
     return ra, dict(ids=ids, mut_names=mut_names, up_names=up_names, slices=slices)
 
 
+def cluster_job_from_files(ctx: Context, ed_file: str, geno_file: str, preclust_file: str, uptag_file: Optional[str],
+                           max_diff: int = 2, min_qual: int = 32, min_jaccard: float = 0.2, min_matches: int = 1):
+    """What hostdata.load_cluster_job builds for the pacybara_cluster.py drop-in, with the two big loaders -- genotypes and
+    uptags, one Python iteration per read in the line parsers (3.5 + 1.7 s at 10^6 reads) -- done by the device tokenizers:
+    the read ids of the bucket titles are laid out as a text of their own, which the joins take like the id slices of a
+    FASTQ.  Returns (ClusterJob, slices for tablefmt).  Raises NeedsLineParser when a tokenizer declines."""
+    with hostdata.open_text(preclust_file) as fh:
+        pc = hostdata.parse_preclust(fh)
+    if len(set(pc.ids)) != len(pc.ids):
+        raise hostdata.FormatError("a read id occurs in more than one bucket title")
+    title_index = {t: i for i, t in enumerate(pc.titles)}
+    with hostdata.open_text(ed_file) as fh:
+        ed_q, ed_r, ed_d = hostdata.parse_ed(fh, title_index)
+    id_len = np.fromiter((len(r) for r in pc.ids), dtype=np.int32, count=len(pc.ids))
+    id_off = np.zeros(len(pc.ids), dtype=np.int64)
+    if len(pc.ids) > 1:
+        np.cumsum(id_len[:-1].astype(np.int64) + 1, out=id_off[1:])
+    try:
+        ids_text = ("\n".join(pc.ids) + "\n").encode("ascii")
+    except UnicodeEncodeError:
+        raise NeedsLineParser("read ids outside plain ASCII") from None
+    raw = read_all([geno_file, uptag_file])
+    geno, uptag = raw[0], raw[1]
+
+    def decline(what: str, n):
+        raise NeedsLineParser(f"{what}: {n}")
+
+    up_id, up_names, up_slices = None, None, None
+    with Text(ctx, ids_text) as idt:
+        with Text(ctx, geno) as ge:
+            if ge.n_exotic:
+                decline("genoExtract has bytes outside plain ASCII text", ge.n_exotic)
+            j = ge.geno_join(idt, id_off, id_len)
+            if j["collisions"]:
+                decline("duplicate read ids (or a hash collision)", j["collisions"])
+            if j["malformed"]:
+                decline("genoExtract lines the tokenizer does not model", j["malformed"])
+            if j["repeated"]:
+                decline("reads naming a mutation twice", j["repeated"])
+            if j["missing"]:
+                raise KeyError(f"{j['missing']} bucketed read(s) have no genotype record")
+            g = ge.geno_fetch(device=False)
+            mut_off, mut_len = np.asarray(g["mut_off"]), np.asarray(g["mut_len"])
+            mut_names = _slices(geno, mut_off, mut_len)
+        if uptag is not None:
+            with Text(ctx, uptag) as up:
+                if up.n_exotic:
+                    decline("uptag FASTQ has bytes outside plain ASCII text", up.n_exotic)
+                uj = up.uptag_join(idt, id_off, id_len)
+                if uj["collisions"] or uj["too_long"]:
+                    decline("uptag records the tokenizer does not model", uj["collisions"] + uj["too_long"])
+                if uj["n_records"] > 0:                      # `if len(tags) > 0`, pacybara_cluster.py:376
+                    u = up.uptag_fetch(device=False)
+                    up_id = np.asarray(u["up_id"]).astype(np.int32)
+                    tag_off, tag_len = np.asarray(u["tag_off"]), np.asarray(u["tag_len"])
+                    up_names = _slices(uptag, tag_off, tag_len)
+                    up_slices = (uptag, tag_off, tag_len)
+    _decoded.clear()
+    n_per = np.diff(pc.bucket_ptr)
+    seq_id, bc_names = hostdata.intern_strings(pc.seqs)
+    bc_id = np.repeat(seq_id, n_per).astype(np.int32)
+    prob = hostdata.MergeProblem(n_reads=pc.n_reads, n_buckets=pc.n_buckets, bucket_ptr=pc.bucket_ptr, bucket_reads=pc.bucket_reads,
+                                 lexrank=hostdata.lexrank_of(pc.ids), bc_id=bc_id, up_id=up_id,
+                                 geno_ptr=np.asarray(g["geno_ptr"]).astype(np.int32), geno_mut=np.asarray(g["geno_mut"]).astype(np.int32),
+                                 geno_q=np.asarray(g["geno_q"]).astype(np.int32), mut_rank=pipeline.mut_rank_of(mut_names),
+                                 max_diff=max_diff, min_qual=min_qual, min_jaccard=min_jaccard, min_matches=min_matches)
+    job = hostdata.ClusterJob(prob, ed_q, ed_r, ed_d, pc.ids, bc_names, up_names, mut_names)
+    bc_len = np.fromiter((len(b) for b in bc_names), dtype=np.int32, count=len(bc_names))
+    bc_off = np.zeros(len(bc_names), dtype=np.int64)
+    if len(bc_names) > 1:
+        np.cumsum(bc_len[:-1], out=bc_off[1:])
+    slices = dict(ids=(ids_text, id_off, id_len), muts=(geno, mut_off, mut_len), up=up_slices,
+                  bc=("".join(bc_names).encode("ascii"), bc_off, bc_len))
+    return job, slices
+
+
 class LazyIds:
     """The read ids as a sequence of str that is only built (10^6 slices, 0.15 s) when it is indexed or iterated."""
 

@@ -14,7 +14,7 @@ FILL = -(1 << 31)
 
 CASES = [n for n in util.golden_names() if n not in ("kat10", "cfg1_full", "x_dense_sw")]
 FIELDS = ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut")
-SHAPES = [dict(mode=2), dict(mode=3, huge_cap=16, huge_window=4, use_small=1), dict(mode=3, huge_cap=1024, huge_window=64, use_small=2)]
+SHAPES = [dict(mode=2), dict(mode=3, huge_cap=16, huge_window=4, use_small=1), dict(mode=3, huge_cap=1024, huge_window=12, use_small=2)]
 
 
 @pytest.mark.parametrize("shape", SHAPES, ids=["warp", "huge-tight", "huge-roomy"])
@@ -42,7 +42,7 @@ def test_warp_and_giant_replay_match_the_reference(name, shape):
     (301, dict(n_clones=300, n_reads=2500, p_err=0.03, p_near=0.5, p_collide=0.2), 2),
     (302, dict(n_clones=200, n_reads=2000, p_err=0.04, p_near=0.6, p_private=0.5, p_private_hq=0.2, p_dropout=0.2), 2),
     (303, dict(n_clones=250, n_reads=2000, bc_len=10, p_err=0.03, p_near=0.5), 3),       # one giant component plus debris
-    (304, dict(n_clones=60, n_reads=1500, combo=True, p_err=0.01, p_near=0.4, skew=1.0), 3),
+    (304, dict(n_clones=40, n_reads=600, combo=True, p_err=0.01, p_near=0.4, skew=1.0), 3),
     (305, dict(n_clones=400, n_reads=2500, bc_len=9, p_err=0.02, p_near=0.3), 2),
 ])
 def test_giant_replay_vs_oracle_on_random_libraries(seed, kw, md):

@@ -84,12 +84,12 @@ def test_the_filters_and_the_early_exit_do_work():
     assert st["cells"] < 0.7 * st["started"] * 25 * 25           # early exit
 
 
-@pytest.mark.parametrize("k,bc_len", [(2, 25), (4, 25), (3, 8), (4, 3), (6, 25)])
+@pytest.mark.parametrize("k,bc_len", [(2, 25), (4, 25), (3, 8), (4, 3)])
 def test_staged_walk_of_long_bins_finds_the_same_pairs(k, bc_len):
     """probe_warp<STAGED>: bins walked through the two staging buffers (cp.async.bulk + mbarrier on the device, memcpy in the
     emulator) -- short seeds make every bin long, so the chunking (odd bin starts, chunks of 256 entries, bins that end
     inside a chunk, the refill order) is what is exercised."""
-    lib_ = synth.make_library(n_clones=150, n_reads=2500, bc_len=bc_len, p_err=0.04, p_near=0.4, seed=60 + k)
+    lib_ = synth.make_library(n_clones=100, n_reads=1200, bc_len=bc_len, p_err=0.04, p_near=0.4, seed=60 + k)
     b = util.oracle_buckets(hostdata.FastqReads([], lib_.seq, lib_.qual, lib_.length))
     got, st = probe(b["bucket_seq"], b["bucket_len"], k, seed=0x80000000 | (k + 1))
     plain, st0 = probe(b["bucket_seq"], b["bucket_len"], k, seed=k + 1)
@@ -99,11 +99,11 @@ def test_staged_walk_of_long_bins_finds_the_same_pairs(k, bc_len):
     assert st["walked"] == st0["walked"] and st["sided"] == st0["sided"]      # the same entries pass by, staged or streamed
 
 
-@pytest.mark.parametrize("k,bc_len,staged", [(2, 25, 0), (2, 25, 1), (4, 25, 0), (3, 8, 1), (6, 25, 0)])
+@pytest.mark.parametrize("k,bc_len,staged", [(2, 25, 0), (2, 25, 1), (4, 25, 0), (3, 8, 1)])
 def test_bins_split_by_target_class_find_the_same_pairs(k, bc_len, staged):
     """owns_pair with classes (big libraries): the query side of a pair is the smaller (class, index); a probe starts its walk
     at its own class.  Same pairs, fewer entries walked; query shards stay disjoint and complete."""
-    lib_ = synth.make_library(n_clones=150, n_reads=2500, bc_len=bc_len, p_err=0.04, p_near=0.4, seed=80 + k)
+    lib_ = synth.make_library(n_clones=100, n_reads=1200, bc_len=bc_len, p_err=0.04, p_near=0.4, seed=80 + k)
     b = util.oracle_buckets(hostdata.FastqReads([], lib_.seq, lib_.qual, lib_.length))
     U = b["n_buckets"]
     flag = 0x40000000 | (0x80000000 if staged else 0)
