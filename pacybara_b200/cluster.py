@@ -150,15 +150,22 @@ def main(argv=None) -> int:
         print(USAGE)
         return 0
     from .api import open_context_or_exit
-    ctx = open_context_or_exit(0)
     log("Loading data...")
     params = dict(max_diff=o["max_diff"], min_qual=o["min_qual"], min_jaccard=o["min_jaccard"], min_matches=o["min_matches"])
+    with hostdata.open_text(o["preclust"]) as fh:
+        pc = hostdata.parse_preclust(fh)
+    bad = [r for r in pc.ids if "-" in r]
+    if bad:                               # before any work (the reference dies at :418 once such a pair comes up)
+        log(f"ERROR: read id {bad[0]!r} contains '-': the pair-id scheme of pacybara_cluster.py (:152-157,418) "
+            "cannot represent it", file=sys.stderr)
+        return 1
+    ctx = open_context_or_exit(0)
     job, slices = None, None
     try:
         # genotypes and uptags through the device tokenizers (the line loaders cost a Python iteration per read)
         from . import ingest
         try:
-            job, slices = ingest.cluster_job_from_files(ctx, o["ed"], o["geno"], o["preclust"], o["uptag"], **params)
+            job, slices = ingest.cluster_job_from_files(ctx, o["ed"], o["geno"], o["preclust"], o["uptag"], pc=pc, **params)
         except ingest.NeedsLineParser as e:
             log(f" - tokenizer declined ({e}); using the line parser")
     except BaseException:
@@ -175,12 +182,6 @@ def main(argv=None) -> int:
             finally:
                 if up is not None:
                     up.close()
-    bad = [r for r in job.ids if "-" in r]
-    if bad:
-        log(f"ERROR: read id {bad[0]!r} contains '-': the pair-id scheme of pacybara_cluster.py (:152-157,418) "
-            "cannot represent it", file=sys.stderr)
-        ctx.close()
-        return 1
     p = job.problem
     pairs = hostdata.dedupe_ed_rows(job.ed_q, job.ed_r, job.ed_d, p.n_buckets, p.max_diff)
     log(f"Clustering {p.n_reads} reads in {p.n_buckets} barcode groups, {len(pairs.q)} barcode pairs on the GPU...")

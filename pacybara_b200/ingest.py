@@ -182,13 +182,14 @@ def arrays_from_bytes(ctx: Context, fastq: bytes, geno: bytes, uptag: Optional[b
 
 
 def cluster_job_from_files(ctx: Context, ed_file: str, geno_file: str, preclust_file: str, uptag_file: Optional[str],
-                           max_diff: int = 2, min_qual: int = 32, min_jaccard: float = 0.2, min_matches: int = 1):
+                           max_diff: int = 2, min_qual: int = 32, min_jaccard: float = 0.2, min_matches: int = 1, pc=None):
     """What hostdata.load_cluster_job builds for the pacybara_cluster.py drop-in, with the two big loaders -- genotypes and
     uptags, one Python iteration per read in the line parsers (3.5 + 1.7 s at 10^6 reads) -- done by the device tokenizers:
     the read ids of the bucket titles are laid out as a text of their own, which the joins take like the id slices of a
     FASTQ.  Returns (ClusterJob, slices for tablefmt).  Raises NeedsLineParser when a tokenizer declines."""
-    with hostdata.open_text(preclust_file) as fh:
-        pc = hostdata.parse_preclust(fh)
+    if pc is None:
+        with hostdata.open_text(preclust_file) as fh:
+            pc = hostdata.parse_preclust(fh)
     if len(set(pc.ids)) != len(pc.ids):
         raise hostdata.FormatError("a read id occurs in more than one bucket title")
     title_index = {t: i for i, t in enumerate(pc.titles)}
