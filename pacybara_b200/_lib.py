@@ -22,7 +22,7 @@ STAT = dict(pairs_scored=0, cells=1, edges=2, seed_len=3, kernel_launches=4, com
 
 # every symbol include/pacybara_b200.h declares
 REPLAY_SHAPES = dict(auto=0, small=0, thread=1, warp=2, huge=3)
-OPT_REPLAY_SHAPE, OPT_TRACE, OPT_HUGE_READS, OPT_HUGE_CAP, OPT_HUGE_WINDOW, OPT_PROBE_STAGING, OPT_PROBE_CLASSES, OPT_SEED_BINS_LOG2, OPT_SMALL_WARPS = range(9)
+OPT_REPLAY_SHAPE, OPT_TRACE, OPT_HUGE_READS, OPT_HUGE_CAP, OPT_HUGE_WINDOW, OPT_PROBE_STAGING, OPT_PROBE_CLASSES, OPT_SEED_BINS_LOG2, OPT_SMALL_WARPS, OPT_HUGE_BUCKETS = range(10)
 
 SYMBOLS = ["pcb_abi_version", "pcb_last_error", "pcb_ctx_create", "pcb_ctx_destroy", "pcb_stat", "pcb_set_option", "pcb_sync",
            "pcb_stream", "pcb_bucket", "pcb_edit_pairs", "pcb_edit_pairs_fetch", "pcb_sort_edges", "pcb_merge", "pcb_cluster_reads", "pcb_compact_shard", "pcb_match_barcodes", "pcb_tag_rows", "pcb_merge_libraries", "pcb_concat_tokens",

@@ -300,7 +300,7 @@ __global__ void comp_stats_kernel(const int32_t *__restrict__ comp_buckets, cons
 // of its rows' calls); a scan turns the counts into the regions' offsets.
 enum { FORCE_NONE = 0, FORCE_LARGE = 1, FORCE_HUGE = 2 };
 __global__ void classify_kernel(MergeCtx c, const int32_t *__restrict__ comp_reads, const int64_t *__restrict__ comp_calls, int32_t force,
-                                int32_t huge_reads, int32_t *__restrict__ counters, int32_t *__restrict__ medium,
+                                int32_t huge_reads, int32_t huge_buckets, int32_t *__restrict__ counters, int32_t *__restrict__ medium,
                                 int32_t *__restrict__ large, int32_t *__restrict__ hcomp, int32_t *__restrict__ huge_of_comp) {
   const int32_t comp = blockIdx.x * blockDim.x + threadIdx.x;
   if (comp >= counters[CNT_COMPS]) return;
@@ -308,7 +308,10 @@ __global__ void classify_kernel(MergeCtx c, const int32_t *__restrict__ comp_rea
   const int64_t nnz = comp_calls[comp];
   huge_of_comp[comp] = -1;
   if (force == FORCE_NONE && reads <= SMALL_READS) return;
-  if (force == FORCE_HUGE || (force == FORCE_NONE && reads > huge_reads)) {
+  // giant: many reads, or many BUCKETS (a chain of small buckets is what the rounds parallelise; a few big buckets -- collisions
+  // -- is what one warp with shared-memory state does well)
+  const int32_t n_b = c.comp_ptr[comp + 1] - c.comp_ptr[comp];
+  if (force == FORCE_HUGE || (force == FORCE_NONE && (reads > huge_reads || (huge_buckets > 0 && n_b > huge_buckets && reads > MED_READS)))) {
     const int32_t h = atomicAdd(&counters[CNT_HUGE], 1);
     hcomp[h] = comp; huge_of_comp[comp] = h;
     return;
@@ -916,7 +919,7 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   PCB_CUDA(cudaMemsetAsync(comp_reads.p, 0, ((size_t)U + 1) * sizeof(int32_t), ctx->stream));
   PCB_LAUNCH(ctx, comp_stats_kernel, grid_for(U, 256), 256, 0, comp_buckets.p, comp_of_b.p, in.bucket_ptr, in.bucket_reads, in.geno_ptr, U,
              comp_reads.p, comp_calls.p);
-  PCB_LAUNCH(ctx, classify_kernel, grid_for((size_t)U + 1, 128), 128, 0, c, comp_reads.p, comp_calls.p, force, ctx->huge_reads, counters.p,
+  PCB_LAUNCH(ctx, classify_kernel, grid_for((size_t)U + 1, 128), 128, 0, c, comp_reads.p, comp_calls.p, force, ctx->huge_reads, ctx->huge_buckets, counters.p,
              medium.p, large.p, hcomp.p, huge_of_comp.p);
   if (!in.shard_layout) {                                  // regions in component order
     comp_call_off.alloc(ctx, (size_t)U + 2);

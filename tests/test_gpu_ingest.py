@@ -273,3 +273,22 @@ def test_random_odd_texts_match_the_line_parser(ctx):
             assert dev[k] == ref[k], (k, fastq, geno)
         taken += 1
     assert taken > 100, (taken, declined, failed_alike)
+
+
+def test_concat_tokens_against_the_host_restatement(ctx):
+    """pcb_concat_tokens (csrc/format.cu): random slices, separators, empty tokens, the capacity retry."""
+    from pacybara_b200 import tablefmt
+    rng = np.random.default_rng(11)
+    src = rng.integers(32, 127, size=5000, dtype=np.uint8)
+    n_tok = 700
+    tok_off = rng.integers(0, 4900, size=n_tok).astype(np.int64)
+    tok_len = np.minimum(rng.integers(0, 40, size=n_tok), 5000 - tok_off).astype(np.int32)
+    item_tok = rng.integers(0, n_tok, size=20000).astype(np.int32)
+    item_sep = rng.choice(np.array([0, 44, 124, 10], dtype=np.uint8), size=20000)
+    want = tablefmt.concat_host(src, tok_off, tok_len, item_tok, item_sep)
+    assert ctx.concat_tokens(src, tok_off, tok_len, item_tok, item_sep) == want
+    assert ctx.concat_tokens(src, tok_off, tok_len, item_tok, item_sep, size_hint=10) == want      # too small a buffer: one retry
+    assert ctx.concat_tokens(src, tok_off, tok_len, item_tok[:0], item_sep[:0]) == b""
+    from pacybara_b200 import _lib
+    with pytest.raises(_lib.PcbError):
+        ctx.concat_tokens(src, tok_off + 6000, tok_len, item_tok, item_sep)                        # a token outside the source
