@@ -122,7 +122,7 @@ enum { PCB_OPT_REPLAY_SHAPE = 0, PCB_OPT_TRACE = 1 /* 1: host-side lap times of 
                                      bins (8..28, default 26): shorter seeds = a smaller table and longer bins */,
        PCB_OPT_SMALL_WARPS = 8 /* warps per block of the small-component replay kernel: 1, 2 or 4 */,
        PCB_OPT_HUGE_BUCKETS = 9 /* a component of more than 128 reads also goes to the giant tier when it has more than this
-                                   many buckets; 0 = only the read count decides */ };
+                                   many buckets (default 16); 0 = only the read count decides */ };
 enum { PCB_REPLAY_AUTO = 0, PCB_REPLAY_THREAD = 1, PCB_REPLAY_WARP = 2, PCB_REPLAY_HUGE = 3 };
 int pcb_set_option(pcb_ctx *ctx, int option, int64_t value);
 /* Block until everything queued on the context's stream has finished. */

@@ -92,8 +92,8 @@ class Context:
         if getattr(self, "_sw_set", 1) != sw:
             self._check(self.lib.pcb_set_option(self.h, _lib.OPT_SMALL_WARPS, sw))
             self._sw_set = sw
-        hb = int(os.environ.get("PCB_HUGE_BUCKETS") or getattr(self, "_huge_buckets_default", 0))
-        if getattr(self, "_hb_set", 0) != hb:
+        hb = int(os.environ.get("PCB_HUGE_BUCKETS") or getattr(self, "_huge_buckets_default", 16))
+        if getattr(self, "_hb_set", 16) != hb:
             self._check(self.lib.pcb_set_option(self.h, _lib.OPT_HUGE_BUCKETS, hb))
             self._hb_set = hb
         bins = int(os.environ.get("PCB_SEED_BINS_LOG2") or 26)

@@ -55,7 +55,7 @@ struct pcb_ctx {
   int64_t stats[PCB_STAT_COUNT] = {0};
   int replay_shape = PCB_REPLAY_AUTO;      // pcb_set_option(PCB_OPT_REPLAY_SHAPE)
   int huge_reads = 256;                    // PCB_OPT_HUGE_READS: components above it are replayed by the whole device (merge_huge.cuh)
-  int huge_buckets = 0;                    // PCB_OPT_HUGE_BUCKETS: ... or with more than this many buckets (and more than 128 reads); 0 = off
+  int huge_buckets = 16;                   // PCB_OPT_HUGE_BUCKETS: ... or with more than this many buckets (and more than 128 reads); 0 = off
   int huge_cap = 2048;                     // PCB_OPT_HUGE_CAP: slots of one warp's scratch table in that tier
   int huge_window = 32768;                 // PCB_OPT_HUGE_WINDOW: rows per round
   int huge_warps_per_sm = 24;

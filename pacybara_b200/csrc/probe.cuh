@@ -43,15 +43,17 @@ struct SeedGeom {
 };
 
 // Which side of an unordered pair {i, j} probes for it.  cbits == 0: the parity rule of myers.cuh.  cbits > 0 (big
-// libraries, long bins): barcodes are ordered by (class, index), class = low bits of the index, and the smaller one is
-// the query side.  A bin's entries are grouped by class, so a query of class c starts its walk at sub-bin c: what it
+// libraries, long bins): class = low bits of the index; between classes the smaller class is the query side, inside a
+// class the parity rule on the remaining bits decides.  A bin's entries are grouped by class, so a query of class c starts its walk at sub-bin c: what it
 // skips are exactly pairs it does not own -- on average (C - 1) / 2C of every bin (44 % with 8 classes), where the
 // parity rule reads a whole bin to keep half of it.  Classes interleave, so any index range (a shard) holds all alike.
 PCB_HD bool owns_pair(const SeedGeom &g, int32_t i, int32_t j, int32_t target_len) {
   if (target_len < g.short_below) return true;
   if (g.rbits == 0) return j != i && is_query_side(i, j);
   const int32_t mask = (1 << g.rbits) - 1;
-  return (j & mask) != (i & mask) ? (j & mask) > (i & mask) : j > i;
+  // (inside a class the parity rule on the remaining bits: "the smaller index" would hand the first of two query shards
+  // every same-class pair that straddles them -- 55 : 45 at 4 GPUs, profiles/r02w_bench_n4.json)
+  return (j & mask) != (i & mask) ? (j & mask) > (i & mask) : (j != i && is_query_side(i >> g.rbits, j >> g.rbits));
 }
 // sub-bin of target j (of length len_j) in bin `bin`; short targets sit in the last class, where every probe passes
 PCB_HD uint32_t seed_slot(const SeedGeom &g, uint32_t bin, int32_t j, int32_t len_j) {
