@@ -69,3 +69,18 @@ def test_rows_to_table_matches_a_plain_loop():
         assert ubc == ("None" if rows.row_up[i] < 0 else up[rows.row_up[i]])
         assert reads == "|".join(ids[r] for r in mem) and size == len(mem)
         assert geno == (";".join(mn[m] for m in calls) if len(calls) else "=")
+
+
+def test_lazy_ids_find_a_byte_without_building_the_strings():
+    """ingest.LazyIds.any_contains: the '-' check of the one-call program on the raw FASTQ bytes (quality strings are full of
+    '-', only the id slices count)."""
+    import numpy as np
+    from pacybara_b200 import ingest
+    raw = b"@r1 x\nACGT\n+\n--I-\n@q-2 y\nAC\n+\n-I\n@r3\nA\n+\n-\n"
+    off = np.array([1, 19, 34], dtype=np.int64)
+    length = np.array([2, 3, 2], dtype=np.int32)
+    ids = ingest.LazyIds(raw, off, length)
+    assert list(ids) == ["r1", "q-2", "r3"] and len(ids) == 3 and ids == ["r1", "q-2", "r3"]
+    assert ids.any_contains(b"-") == "q-2"
+    assert ingest.LazyIds(raw, off[[0, 2]], length[[0, 2]]).any_contains(b"-") is None
+    assert ingest.LazyIds(b"", off[:0], length[:0]).any_contains(b"-") is None
