@@ -214,6 +214,13 @@ __global__ void __launch_bounds__(PROBE_WARPS * 32) probe_kernel_staged(ProbeArg
   probe_warp<true>(a, threadIdx.x & 31, &queue[threadIdx.x >> 5], &stage[threadIdx.x >> 5]);
 }
 
+// the queries shorter than `below` in [q_begin, q_end), in any order (they probe the second index)
+__global__ void short_queries_kernel(const int32_t *__restrict__ len, int32_t q_begin, int32_t q_end, int32_t below, int32_t *__restrict__ list,
+                                     int32_t *__restrict__ n) {
+  const int32_t i = q_begin + (int32_t)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (i < q_end && len[i] < below) list[atomicAdd(n, 1)] = i;
+}
+
 __global__ void sketch_kernel(const ulonglong2 *__restrict__ planes, const int32_t *__restrict__ len, int32_t U, uint32_t *__restrict__ sketch) {
   int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < U) sketch[i] = barcode_sketch((uint32_t)planes[i].x, (uint32_t)planes[i].y, len[i]);
@@ -411,6 +418,16 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
     PCB_LAUNCH(ctx, kernel, n_cta, PROBE_WARPS * 32, 0, qs.planes.p, qs.len.p, (const uint64_t *)(self ? nullptr : qs.other.p), bc.planes.p, bc.len.p, q_begin, q_end, ix.g,
                ix.bin_off.p, ix.ent.p, hk0.p, hv0.p, cap, key_shift, counters.p, ix.len_lo, ix.len_hi);
   };
+  // the short barcodes as a list: the second index is probed by them alone (a probe loop over every barcode to find the few
+  // that qualify cost 70 us of the 270 us probe stage at 10^6 reads)
+  DevBuf<int32_t> short_list, short_n;
+  if (lanes && n_idx == 2 && idx[1].g.only_below) {
+    short_list.alloc(ctx, (size_t)(q_end - q_begin));
+    short_n.alloc(ctx, 1);
+    PCB_CUDA(cudaMemsetAsync(short_n.p, 0, sizeof(int32_t), ctx->stream));
+    PCB_LAUNCH(ctx, short_queries_kernel, grid_for((size_t)(q_end - q_begin), 256), 256, 0, bc.len.p, q_begin, q_end, idx[1].g.only_below,
+               short_list.p, short_n.p);
+  }
   for (int attempt = 0;; attempt++) {
     hk0.alloc(ctx, cap); hv0.alloc(ctx, cap);
     PCB_CUDA(cudaMemsetAsync(counters.p, 0, 6 * sizeof(unsigned long long), ctx->stream));
@@ -429,6 +446,11 @@ static void pair_search(pcb_ctx *ctx, const PackedBarcodes &bc, const PackedBarc
         a.planes = (const Planes16 *)bc.planes.p; a.len = bc.len.p; a.sketch = sketch.p; a.q_begin = q_begin; a.q_end = q_end; a.g = g;
         a.bin_off = idx[t].bin_off.p; a.ent = idx[t].ent8.p; a.hit_key = hk0.p; a.hit_d = hv0.p; a.cap = cap; a.key_shift = key_shift;
         a.counters = counters.p; a.len_lo = idx[t].len_lo; a.len_hi = idx[t].len_hi;
+        a.qlist = nullptr; a.qlist_n = nullptr;
+        if (idx[t].g.only_below && short_list.p) {            // only the short barcodes probe this index
+          a.qlist = short_list.p; a.qlist_n = short_n.p;
+          if (n_cta > (unsigned)ctx->sm_count) n_cta = (unsigned)ctx->sm_count;
+        }
         if (ctx->probe_staging) PCB_LAUNCH(ctx, probe_kernel_staged, n_cta, PROBE_WARPS * 32, 0, a);
         else PCB_LAUNCH(ctx, probe_kernel_lanes, n_cta, PROBE_WARPS * 32, 0, a);
       }

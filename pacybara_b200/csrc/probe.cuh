@@ -87,6 +87,8 @@ struct ProbeArgs {
   unsigned long long *counters;    // [0] hits, [1] pairs that entered the recurrence, [2] cells computed, [3] next block of probes,
                                    // [4] bin entries walked, [5] entries that passed the query-side rule (the filters' input)
   int32_t len_lo, len_hi;          // query lengths this index serves
+  const int32_t *qlist;            // optional: the queries of this launch as a list (the few short barcodes that probe the second
+  const int32_t *qlist_n;          //   index), its length on the device; nullptr: the range [q_begin, q_end)
 };
 
 constexpr int PROBE_QUEUE = 96;    // survivors waiting for a lane (at most 63 + 32)
@@ -123,7 +125,7 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu, ProbeStage
   const int k = g.k;
   const int n_shift = g.q == 0 ? 1 : 2 * k + 1;
   const int per_query = g.q == 0 ? 1 : (k + 1) * n_shift;
-  const unsigned long long n_probe = (unsigned long long)(a.q_end - a.q_begin) * per_query;
+  const unsigned long long n_probe = (unsigned long long)(a.qlist ? *a.qlist_n : a.q_end - a.q_begin) * per_query;
   const unsigned long long n_blocks = (n_probe + 31) / 32;
   uint32_t n_started = 0, n_cells = 0, n_walked = 0, n_sided = 0;      // per lane; widened when the warp is done
   int cnt = 0;                       // queued survivors (uniform)
@@ -176,7 +178,7 @@ SIMT_FN void probe_warp(const ProbeArgs &a, int lane, ProbeQueue *qu, ProbeStage
         const unsigned long long pid = blk * 32 + (unsigned)lane;
         lo = hi = 0; qi = -1;
         if (pid < n_probe) {
-          qi = a.q_begin + (int32_t)(pid / per_query);
+          qi = a.qlist ? a.qlist[pid / per_query] : a.q_begin + (int32_t)(pid / per_query);
           const int32_t rem = (int32_t)(pid % per_query);
           const int32_t t = rem / n_shift, s = rem % n_shift - (g.q == 0 ? 0 : k);
           qm = a.len[qi];

@@ -1,0 +1,10 @@
+# short-query list for the second index: parity + timing
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_match.py -m gpu -x -q > gpurun_out/r02x_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/r02x_pytest.log
+timeout 900 python -m pytest tests/test_gpu_scale.py -m gpu -x -q -k "cfg5 or scaled" > gpurun_out/r02x_pytest2.log 2>&1; echo "pytest scale rc=$?"; tail -3 gpurun_out/r02x_pytest2.log
+for c in cfg1 cfg2 cfg4 cfg5; do
+  PCB_BENCH_CONFIG=$c timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-files-e2e > gpurun_out/r02x_bench_$c.json 2> gpurun_out/r02x_$c.err; echo "$c rc=$?"
+  python -c "
+import json;d=json.load(open('gpurun_out/r02x_bench_$c.json'));print(round(d['ms_per_step'],3),round(d['e2e']['ms_per_step'],3),{k: round(v,3) for k,v in d['stage_ms'].items()},d['parity']['equal'],d['gpu_launches'])"
+done
+timeout 300 python tests/shard_profile.py 8 2>&1 | tail -1

@@ -52,7 +52,7 @@ extern "C" int64_t emul_probe(const uint64_t *planes, const int32_t *len, int32_
   ProbeArgs a;
   a.planes = (const Planes16 *)planes; a.len = len; a.sketch = sketch.data(); a.q_begin = q_begin; a.q_end = q_end; a.g = g;
   a.bin_off = bin_off.data(); a.ent = ent.data(); a.hit_key = hk.data(); a.hit_d = hd.data(); a.cap = hit_cap;
-  a.key_shift = 24; a.counters = counters; a.len_lo = 0; a.len_hi = 64;
+  a.key_shift = 24; a.counters = counters; a.len_lo = 0; a.len_hi = 64; a.qlist = nullptr; a.qlist_n = nullptr;
   static ProbeQueue qu;
   static ProbeStage stg;
   const bool staged = (seed & 0x80000000u) != 0;        // top bit of the seed: long bins through the staging buffers
