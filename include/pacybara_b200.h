@@ -270,6 +270,31 @@ int pcb_compact_shard(pcb_ctx *ctx, int mem_in, int mem_out, int32_t R, int64_t 
                       int32_t *c_up, int64_t *c_call_off, int32_t *c_call_n, int32_t *c_call_mut);
 
 /*
+ * (e) One rank's share of a multi-GPU step as two calls around the one collective (pacybara_b200/multigpu.py): every rank
+ * buckets the whole read set, searches ITS block of the (query groups x target groups) pair grid, all ranks all-gather
+ * their edge lists (NCCL, by the caller), and every rank merges the components it owns.  Device arrays only.
+ *   pcb_shard_pairs   buckets seq/len [R] (bucket_of_read [R] out, *n_buckets), then the pairs within k whose query side
+ *                     lies in slice q_group of n_q_groups of [0, U) and whose target side in slice t_group of n_t_groups;
+ *                     *n_edges pairs are left for pcb_edit_pairs_fetch.  The bucket arrays and the packed barcodes stay
+ *                     in the context for pcb_shard_merge.
+ *   pcb_shard_merge   gathered [world][3][m] int32: what the all-gather of the ranks' (ei, ej, ed) rows, padded to m
+ *                     columns, left; counts [world] (HOST array) = valid columns per rank.  Sorts the edges by (i, j) and
+ *                     runs pcb_merge's work for shard shard_rank of shard_count on the buckets of pcb_shard_pairs
+ *                     (on_demand != 0: transitive-rule distances beyond max_diff are scored from the retained barcodes,
+ *                     i.e. the search ran at k = max_diff; 0: the search ran at k = 2 * max_diff).  Outputs as pcb_merge.
+ */
+int pcb_shard_pairs(pcb_ctx *ctx, int mem, const uint8_t *seq, const int32_t *len, int32_t R, int32_t stride, int32_t k,
+                    int32_t q_group, int32_t n_q_groups, int32_t t_group, int32_t n_t_groups, int32_t *bucket_of_read,
+                    int32_t *n_buckets, int64_t *n_edges);
+int pcb_shard_merge(pcb_ctx *ctx, int mem, const int32_t *gathered, int32_t world, int64_t m, const int64_t *counts,
+                    const int32_t *bucket_of_read, const int32_t *lexrank, const int32_t *up_id, const int32_t *geno_ptr,
+                    const int32_t *geno_mut, const int32_t *geno_q, int64_t nnz, const int32_t *mut_rank, int32_t n_mut,
+                    int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches, int32_t on_demand,
+                    int32_t shard_rank, int32_t shard_count, int32_t flags, int64_t *n_edges, int32_t *read_root, int32_t *read_pos,
+                    int32_t *row_size, int64_t *row_key, int32_t *row_bc, int32_t *row_up, int64_t *row_call_off,
+                    int32_t *row_call_n, int32_t *call_mut);
+
+/*
  * a14 -- the writer (src/pacybara_cluster.py:546-567).  A row of clusters.csv.gz is made of slices of texts the caller
  * already holds (read ids, mutation names, barcodes, uptags) and one-byte separators.
  *   src [n_src]                    the bytes those slices come from (any concatenation of the caller's texts)

@@ -25,7 +25,7 @@ REPLAY_SHAPES = dict(auto=0, small=0, thread=1, warp=2, huge=3)
 OPT_REPLAY_SHAPE, OPT_TRACE, OPT_HUGE_READS, OPT_HUGE_CAP, OPT_HUGE_WINDOW, OPT_PROBE_STAGING, OPT_PROBE_CLASSES, OPT_SEED_BINS_LOG2, OPT_SMALL_WARPS, OPT_HUGE_BUCKETS = range(10)
 
 SYMBOLS = ["pcb_abi_version", "pcb_last_error", "pcb_ctx_create", "pcb_ctx_destroy", "pcb_stat", "pcb_set_option", "pcb_sync",
-           "pcb_stream", "pcb_bucket", "pcb_edit_pairs", "pcb_edit_pairs_fetch", "pcb_sort_edges", "pcb_merge", "pcb_cluster_reads", "pcb_compact_shard", "pcb_match_barcodes", "pcb_tag_rows", "pcb_merge_libraries", "pcb_concat_tokens",
+           "pcb_stream", "pcb_bucket", "pcb_edit_pairs", "pcb_edit_pairs_fetch", "pcb_sort_edges", "pcb_merge", "pcb_cluster_reads", "pcb_compact_shard", "pcb_match_barcodes", "pcb_tag_rows", "pcb_merge_libraries", "pcb_concat_tokens", "pcb_shard_pairs", "pcb_shard_merge",
            "pcb_text_open", "pcb_text_close", "pcb_fastq_records", "pcb_fastq_fetch", "pcb_rank_strings", "pcb_geno_join",
            "pcb_geno_fetch", "pcb_uptag_join", "pcb_uptag_fetch"]
 
@@ -73,6 +73,9 @@ def load():
         lib.pcb_match_barcodes.argtypes = [vp, C.c_int, vp, vp, i32, i32, vp, vp, i32, i32, i32, vp, vp, vp, C.POINTER(i64)]
         lib.pcb_tag_rows.argtypes = [vp, C.c_int, i32, vp, vp, vp, i32, i32, dbl, vp, vp, vp]
         lib.pcb_merge_libraries.argtypes = [vp, C.c_int, i32, vp, vp, vp, i32, vp, vp, vp, i32, vp, vp, vp]
+        lib.pcb_shard_pairs.argtypes = [vp, C.c_int, vp, vp, i32, i32, i32, i32, i32, i32, i32, vp, C.POINTER(i32), C.POINTER(i64)]
+        lib.pcb_shard_merge.argtypes = [vp, C.c_int, vp, i32, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, dbl, i32, i32, i32, i32,
+                                        i32, C.POINTER(i64)] + [vp] * 9
         lib.pcb_concat_tokens.argtypes = [vp, C.c_int, vp, i64, vp, vp, i64, vp, vp, i64, vp, i64, C.POINTER(i64)]
         p32, p64 = C.POINTER(i32), C.POINTER(i64)
         lib.pcb_text_open.argtypes = [vp, C.c_int, vp, i64, C.POINTER(vp), p64, p64]

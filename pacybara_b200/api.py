@@ -282,6 +282,54 @@ class Context:
                                           self._in(row_size, np.int32, keep), int(n_bc_ids), int(n_up_ids), float(min_ratio), *ptrs))
         return {k: v[:n] for k, v in outs.items()}
 
+    # ------------------------------------------------------------------ (e) one rank's share of a multi-GPU step
+    def shard_pairs(self, seq, length, k: int, q_group: int, n_q_groups: int, t_group: int, n_t_groups: int):
+        """Bucketing of the whole read set + this rank's block of the pair grid (pcb_shard_pairs), device tensors only.
+        Returns (bucket_of_read, n_buckets, n_edges); the edges wait for shard_edges_into, the buckets for shard_merge."""
+        torch = _torch()
+        mem = self._kind(seq, length)
+        self.set_replay_shape()
+        R, stride = int(seq.shape[0]), int(seq.shape[1])
+        keep: list = []
+        bor, p_bor = self._out(mem, (max(R, 1),), np.int32)
+        nb, ne = C.c_int32(0), C.c_int64(0)
+        self._check(self.lib.pcb_shard_pairs(self.h, mem, self._in(seq, np.uint8, keep), self._in(length, np.int32, keep), R, stride, int(k),
+                                             int(q_group), int(n_q_groups), int(t_group), int(n_t_groups), p_bor, C.byref(nb), C.byref(ne)))
+        return bor[:R], int(nb.value), int(ne.value)
+
+    def shard_edges_into(self, rows):
+        """This rank's edges into the three rows of a [3, m] int32 device tensor (pcb_edit_pairs_fetch), m >= n_edges."""
+        m = int(rows.shape[1])
+        ptr = lambda r: C.c_void_p(rows[r].data_ptr())
+        self._check(self.lib.pcb_edit_pairs_fetch(self.h, _lib.MEM_DEVICE, ptr(0), ptr(1), ptr(2), m))
+
+    def shard_merge(self, gathered, counts, bucket_of_read, lexrank, up_id, geno_ptr, geno_mut, geno_q, mut_rank, max_diff: int,
+                    min_qual: int, min_jaccard: float, min_matches: int, on_demand: bool, shard, shard_layout: bool = False):
+        """The gathered edge lists ([world, 3, m] int32 device tensor, counts per rank) -> this shard's rows (pcb_shard_merge).
+        Returns (outputs as merge(), total number of edges)."""
+        torch = _torch()
+        mem = self._kind(gathered, bucket_of_read, lexrank, up_id, geno_ptr, geno_mut, geno_q, mut_rank)
+        world, m = int(gathered.shape[0]), int(gathered.shape[2])
+        R, nnz = int(bucket_of_read.shape[0]), int(geno_mut.shape[0])
+        keep: list = []
+        cnt = np.ascontiguousarray(counts, dtype=np.int64)
+        outs, ptrs = {}, []
+        for name, dt in MERGE_OUTPUTS:
+            outs[name], ptr = self._out(mem, (max(R, 1),), dt)
+            ptrs.append(ptr)
+        outs["call_mut"], p_call = self._out(mem, (max(nnz, 1),), np.int32)
+        ne = C.c_int64(0)
+        self._check(self.lib.pcb_shard_merge(self.h, mem, C.c_void_p(gathered.data_ptr()), world, m, cnt.ctypes.data_as(C.c_void_p),
+                                             self._in(bucket_of_read, np.int32, keep), self._in(lexrank, np.int32, keep),
+                                             self._in(up_id, np.int32, keep), self._in(geno_ptr, np.int32, keep),
+                                             self._in(geno_mut, np.int32, keep), self._in(geno_q, np.int32, keep), nnz,
+                                             self._in(mut_rank, np.int32, keep), int(mut_rank.shape[0]), int(max_diff), int(min_qual),
+                                             float(min_jaccard), int(min_matches), 1 if on_demand else 0, int(shard[0]), int(shard[1]),
+                                             _lib.MERGE_SHARD_LAYOUT if shard_layout else 0, C.byref(ne), *ptrs, p_call))
+        out = {k: v[:R] for k, v in outs.items() if k != "call_mut"}
+        out["call_mut"] = outs["call_mut"][:nnz]
+        return out, int(ne.value)
+
     # ------------------------------------------------------------------ a14
     def concat_tokens(self, src: np.ndarray, tok_off: np.ndarray, tok_len: np.ndarray, item_tok: np.ndarray, item_sep: np.ndarray,
                       size_hint: Optional[int] = None) -> bytes:

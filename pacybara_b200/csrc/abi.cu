@@ -217,6 +217,14 @@ int pcb_ctx_create(int device, pcb_ctx **out) {
   }
 }
 
+// (e) what pcb_shard_pairs leaves for pcb_shard_merge: the bucket arrays and the packed barcodes of the whole read set
+struct pcb_shard_state {
+  pcb::DevBuf<int32_t> bptr, breads;
+  pcb::PackedBarcodes uniq;
+  int32_t R = 0, U = 0;
+  bool valid = false;
+};
+
 void pcb_ctx_destroy(pcb_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
@@ -230,6 +238,7 @@ void pcb_ctx_destroy(pcb_ctx *ctx) {
   if (ctx->ev_alloc) cudaEventDestroy(ctx->ev_alloc);
   if (ctx->ev_copied) cudaEventDestroy(ctx->ev_copied);
   if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+  if (ctx->shard) { delete ctx->shard; ctx->shard = nullptr; }
   if (ctx->arena) cudaFree(ctx->arena);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -370,6 +379,111 @@ int pcb_merge(pcb_ctx *ctx, int mem, int32_t R, int32_t U, const int32_t *bucket
     stage_collect(ctx);
     o_root.commit(R); o_pos.commit(R); o_size.commit(R); o_bc.commit(R); o_up.commit(R); o_calln.commit(R);
     o_call.commit(nnz); o_key.commit(R); o_calloff.commit(R);
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+// ---- (e) the sharded step as two calls around the one collective (pacybara_b200/multigpu.py)
+
+namespace {
+// the ranks' edge lists as the all-gather left them -- [world][3][m] int32, counts[r] valid columns -- as sort keys
+__global__ void gathered_keys_kernel(const int32_t *__restrict__ buf, int32_t world, int64_t m, const int64_t *__restrict__ start,
+                                     int64_t n, int shift, uint64_t *__restrict__ key, uint32_t *__restrict__ val) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int32_t r = 0;
+  while (r + 1 < world && start[r + 1] <= i) r++;
+  const int64_t c = i - start[r];
+  const int32_t *b = buf + (size_t)r * 3 * (size_t)m;
+  key[i] = ((uint64_t)(uint32_t)b[c] << shift) | (uint32_t)b[(size_t)m + c];
+  val[i] = (uint32_t)b[2 * (size_t)m + c];
+}
+}  // namespace
+
+int pcb_shard_pairs(pcb_ctx *ctx, int mem, const uint8_t *seq, const int32_t *len, int32_t R, int32_t stride, int32_t k,
+                    int32_t q_group, int32_t n_q_groups, int32_t t_group, int32_t n_t_groups, int32_t *bucket_of_read,
+                    int32_t *n_buckets, int64_t *n_edges) {
+  return guarded(ctx, [&] {
+    if (mem != PCB_MEM_DEVICE) throw Error(PCB_E_INPUT, "pcb_shard_pairs works on device arrays");
+    if (R < 0 || stride < 1 || !bucket_of_read) throw Error(PCB_E_INPUT, "bad shape");
+    if (n_q_groups < 1 || n_t_groups < 1 || q_group < 0 || q_group >= n_q_groups || t_group < 0 || t_group >= n_t_groups)
+      throw Error(PCB_E_INPUT, "bad pair grid");
+    if (!ctx->shard) ctx->shard = new pcb_shard_state();
+    pcb_shard_state &st = *ctx->shard;
+    st.valid = false;
+    st.bptr.alloc(ctx, (size_t)R + 1); st.breads.alloc(ctx, R > 0 ? R : 1);
+    st.uniq = PackedBarcodes();
+    st.R = R;
+    stage_begin(ctx);
+    BucketOut bo{bucket_of_read, st.bptr.p, st.breads.p, nullptr};
+    int32_t U = 0;
+    if (R > 0) {
+      BucketPending pending;
+      bucket_launch(ctx, seq, len, R, stride, bo, &st.uniq, pending);
+      stage_end(ctx, PCB_STAT_T_BUCKET_NS);
+      PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+      U = bucket_finish(ctx, bo, &st.uniq, pending);
+    } else {
+      st.uniq.n = 0; st.uniq.planes.alloc(ctx, 0); st.uniq.len.alloc(ctx, 0);
+      stage_end(ctx, PCB_STAT_T_BUCKET_NS);
+    }
+    st.U = U;
+    if (n_buckets) *n_buckets = U;
+    const int32_t q_lo = (int32_t)(((int64_t)U * q_group) / n_q_groups), q_hi = (int32_t)(((int64_t)U * (q_group + 1)) / n_q_groups);
+    const int32_t t_lo = (int32_t)(((int64_t)U * t_group) / n_t_groups), t_hi = (int32_t)(((int64_t)U * (t_group + 1)) / n_t_groups);
+    edit_pairs_dev(ctx, st.uniq, k, q_lo, q_hi, t_lo, t_hi);
+    stage_collect(ctx);
+    if (n_edges) *n_edges = ctx->edges.n;
+    st.valid = true;
+    PCB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }, false);       // the bucket arrays and the planes outlive the call: no workspace arena
+}
+
+int pcb_shard_merge(pcb_ctx *ctx, int mem, const int32_t *gathered, int32_t world, int64_t m, const int64_t *counts,
+                    const int32_t *bucket_of_read, const int32_t *lexrank, const int32_t *up_id, const int32_t *geno_ptr,
+                    const int32_t *geno_mut, const int32_t *geno_q, int64_t nnz, const int32_t *mut_rank, int32_t n_mut,
+                    int32_t max_diff, int32_t min_qual, double min_jaccard, int32_t min_matches, int32_t on_demand,
+                    int32_t shard_rank, int32_t shard_count, int32_t flags, int64_t *n_edges, int32_t *read_root, int32_t *read_pos,
+                    int32_t *row_size, int64_t *row_key, int32_t *row_bc, int32_t *row_up, int64_t *row_call_off,
+                    int32_t *row_call_n, int32_t *call_mut) {
+  return guarded(ctx, [&] {
+    if (mem != PCB_MEM_DEVICE) throw Error(PCB_E_INPUT, "pcb_shard_merge works on device arrays");
+    if (!ctx->shard || !ctx->shard->valid) throw Error(PCB_E_STATE, "pcb_shard_merge before pcb_shard_pairs");
+    pcb_shard_state &st = *ctx->shard;
+    if (world < 1 || m < 0 || nnz < 0 || !counts) throw Error(PCB_E_INPUT, "bad shape");
+    const int32_t R = st.R, U = st.U;
+    // ---- the gathered edges in canonical order (i, j)
+    stage_begin(ctx, PCB_STAT_T_PREP_NS, PCB_STAT_T_SCATTER_NS);
+    std::vector<int64_t> start((size_t)world + 1, 0);
+    for (int32_t r = 0; r < world; r++) {
+      if (counts[r] < 0 || counts[r] > m) throw Error(PCB_E_INPUT, "bad edge count");
+      start[r + 1] = start[r] + counts[r];
+    }
+    const int64_t E = start[world];
+    if (n_edges) *n_edges = E;
+    DevBuf<int32_t> ei(ctx, (size_t)E), ej(ctx, (size_t)E), ed(ctx, (size_t)E), ped(ctx, (size_t)E);
+    if (E > 0) {
+      DevBuf<int64_t> d_start(ctx, (size_t)world + 1);
+      PCB_CUDA(cudaMemcpyAsync(d_start.p, start.data(), ((size_t)world + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+      const int shift = bits_for((uint64_t)(U > 1 ? U - 1 : 1));
+      DevBuf<uint64_t> k0(ctx, E), k1(ctx, E);
+      DevBuf<uint32_t> v0(ctx, E), v1(ctx, E);
+      PCB_LAUNCH(ctx, gathered_keys_kernel, grid_for(E, 256), 256, 0, gathered, world, m, d_start.p, E, shift, k0.p, v0.p);
+      const int w = radix_sort_pairs(ctx, k0.p, v0.p, k1.p, v1.p, E, 2 * shift);
+      PCB_LAUNCH(ctx, edge_unpack_kernel, grid_for(E, 256), 256, 0, w ? k1.p : k0.p, w ? v1.p : v0.p, E, shift, ei.p, ej.p, ed.p);
+      PCB_LAUNCH(ctx, pairs_from_edges_kernel, grid_for(E, 256), 256, 0, ed.p, E, max_diff, ped.p);
+      PCB_CUDA(cudaStreamSynchronize(ctx->stream));          // (start[] is host memory of this frame)
+    }
+    MergeIn in{R, U, n_mut, st.bptr.p, st.breads.p, lexrank, bucket_of_read, up_id, geno_ptr, geno_mut, geno_q, mut_rank,
+               E, ei.p, ej.p, ed.p, ped.p, max_diff, min_qual, min_matches, min_jaccard, shard_rank, shard_count};
+    if (on_demand) { in.planes = st.uniq.planes.p; in.blen = st.uniq.len.p; in.compute_k = 2 * max_diff; in.wide = st.uniq.max_len > 32; }
+    in.nnz = nnz;
+    in.pairs_sorted = true;
+    in.shard_layout = (flags & PCB_MERGE_SHARD_LAYOUT) != 0;
+    in.bucket_of_read = bucket_of_read;
+    MergeOut out{read_root, read_pos, row_size, row_key, row_bc, row_up, row_call_off, row_call_n, call_mut};
+    merge_dev(ctx, in, out);
+    stage_collect(ctx);
     PCB_CUDA(cudaStreamSynchronize(ctx->stream));
   });
 }

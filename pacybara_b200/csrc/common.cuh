@@ -36,6 +36,7 @@ struct pcb_edges {
 };
 
 struct pcb_text;     // a text file on the device (ingest.cu)
+struct pcb_shard_state;     // what pcb_shard_pairs leaves for pcb_shard_merge (abi.cu)
 
 // packed length of a barcode that does not fit the 2-bit planes (non-ACGT character, more than 64 bases, empty): it is
 // bucketed by the exact bytes (planes = 128-bit hash) and takes no part in the pair search
@@ -73,6 +74,7 @@ struct pcb_ctx {
   size_t arena_cap = 0, arena_off = 0, arena_need = 0;
   bool arena_on = false;
   pcb_edges edges;
+  pcb_shard_state *shard = nullptr;
 };
 
 namespace pcb {

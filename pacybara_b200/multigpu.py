@@ -164,52 +164,54 @@ def cluster_reads_sharded(ctx: Context, arrs: Dict, params: Dict, rank: int, wor
     a = arrs if on_device else torch_stage("upload_allgather", lambda: upload_sharded(arrs, rank, world, dev))
     max_diff = int(params["max_diff"])
     R = int(a["length"].shape[0])
-    # 1. buckets (replicated)
-    b = ctx.bucket(a["seq"], None, a["length"], want_qsum=False)      # qualities are not needed for clustering
-    lib_stages("bucket")
-    U = b["n_buckets"]
-    # 2. my block of the (query, target) grid (every pair has one query side and one target side)
-    q_range, t_range = pair_ranges(U, rank, world)
-    bseq, blen = b["bucket_seq"].contiguous(), b["bucket_len"].contiguous()
-    err = None
+    # 1 + 2. buckets (replicated) and my block of the (query, target) grid of the pair search -- one library call; the
+    # bucket arrays and the packed barcodes stay in the context for the merge
+    gq, gt = pair_grid(world)
+    err, bor, U, n_mine = None, None, 0, 0
     try:
-        ei, ej, ed = ctx.edit_pairs(bseq, blen, (2 if full_table else 1) * max_diff, q_range=q_range, t_range=t_range)
+        bor, U, n_mine = ctx.shard_pairs(a["seq"], a["length"], (2 if full_table else 1) * max_diff, rank % gq, gq, rank // gq, gt)
     except Exception as e:          # noqa: BLE001 - re-raised on every rank below
         err = e
-    _all_ranks_ok("pair search", err, dev)
-    lib_stages("index", "probe", "hits")
+    lib_stages("bucket", "index", "probe", "hits")
     local_stats = dict(pairs_scored=ctx.stat("pairs_scored"), cells=ctx.stat("cells"), probe_ns=ctx.stat("probe_ns"))
-    # 3. exchange edges
-    ei, ej, ed = torch_stage("edge_allgather", lambda: gather_edges(ei, ej, ed, world))
 
-    def order_edges():
-        ctx.sort_edges(ei, ej, ed, U)
-        return torch.where((ed >= 1) & (ed <= max_diff), ed, torch.zeros_like(ed))
-    ped = torch_stage("edge_sort", order_edges)
-    # 4. my components
-    prob = MergeProblem(n_reads=R, n_buckets=U, bucket_ptr=b["bucket_ptr"].contiguous(), bucket_reads=b["bucket_reads"].contiguous(),
-                        lexrank=a["lexrank"], bc_id=b["bucket_of_read"].contiguous(), up_id=a.get("up_id"), geno_ptr=a["geno_ptr"],
-                        geno_mut=a["geno_mut"], geno_q=a["geno_q"], mut_rank=a["mut_rank"], max_diff=max_diff,
-                        min_qual=int(params["min_qual"]), min_jaccard=float(params["min_jaccard"]),
-                        min_matches=int(params["min_matches"]))
+    # 3. exchange edges: the counts (a negative count says "my search failed": every rank then raises at the same point
+    # instead of hanging in the next collective), then the padded (i, j, d) rows
+    def exchange():
+        n = torch.tensor([n_mine if err is None else -1], dtype=torch.int64, device=dev)
+        counts = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, n)
+        counts_h = counts.tolist()
+        if min(counts_h) < 0:
+            if err is not None:
+                raise err
+            raise ShardError("another rank failed in stage 'pair search'")
+        m = max(1, max(counts_h))
+        mine = torch.empty(3, m, dtype=torch.int32, device=dev)
+        if n_mine:
+            ctx.shard_edges_into(mine)          # (every library call returns with its stream drained)
+        allbuf = torch.empty(world, 3, m, dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(allbuf.view(world * 3, m), mine)
+        return allbuf, counts_h
+    allbuf, counts_h = torch_stage("edge_allgather", exchange)
+    # 4. my components (the edge sort is part of the library call and of its `prep` time)
     err = None
     try:
-        if full_table:
-            out = ctx.merge(prob, PairList(ei, ej, ed, ped), shard=(rank, world), pairs_sorted=True, shard_layout=combine)
-        else:
-            out = ctx.merge(prob, PairList(ei, ej, ed, ped), shard=(rank, world), bucket_seq=bseq, bucket_len=blen,
-                            on_demand_k=2 * max_diff, pairs_sorted=True, shard_layout=combine)
+        out, n_all = ctx.shard_merge(allbuf, counts_h, bor, a["lexrank"], a.get("up_id"), a["geno_ptr"], a["geno_mut"], a["geno_q"],
+                                     a["mut_rank"], max_diff, int(params["min_qual"]), float(params["min_jaccard"]),
+                                     int(params["min_matches"]), on_demand=not full_table, shard=(rank, world), shard_layout=combine)
     except Exception as e:          # noqa: BLE001 - e.g. PCB_E_UPTAG, raised only where the component lives
         err = e
     _all_ranks_ok("merge", err, dev)
     lib_stages("prep", "replay", "scatter")
     local_stats.update(links=ctx.stat("links"), tests=ctx.stat("tests"), components=ctx.stat("components"))
+    b = dict(bucket_of_read=bor, n_buckets=U)
     # 5. result
     if combine:
         for name in list(out.keys()):
             dist.all_reduce(out[name], op=dist.ReduceOp.MAX)
         torch.cuda.current_stream(ctx.device).synchronize()
-    extra = dict(bucket_of_read=b["bucket_of_read"], n_buckets=U, n_edges=int(ei.numel()), local_stats=local_stats, stage_ms=stage_ms)
+    extra = dict(bucket_of_read=b["bucket_of_read"], n_buckets=U, n_edges=n_all, local_stats=local_stats, stage_ms=stage_ms)
     if not on_device and not combine:
         # bucket ids travel for my reads only (row_bc names buckets; the barcode of a bucket is that of any of its reads)
         shard = ctx.compact_shard(dict(out, bucket_of_read=b["bucket_of_read"]), to_host=True)
