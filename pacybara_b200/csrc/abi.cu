@@ -411,8 +411,14 @@ int pcb_shard_pairs(pcb_ctx *ctx, int mem, const uint8_t *seq, const int32_t *le
     if (!ctx->shard) ctx->shard = new pcb_shard_state();
     pcb_shard_state &st = *ctx->shard;
     st.valid = false;
-    st.bptr.alloc(ctx, (size_t)R + 1); st.breads.alloc(ctx, R > 0 ? R : 1);
-    st.uniq = PackedBarcodes();
+    // what outlives the call comes from the pool, not from the workspace arena, and is kept from step to step
+    ctx->arena_on = false;
+    if (st.bptr.n < (size_t)R + 1) st.bptr.alloc(ctx, (size_t)R + 1);
+    if (st.breads.n < (size_t)(R > 0 ? R : 1)) st.breads.alloc(ctx, R > 0 ? R : 1);
+    if (st.uniq.planes.n < (size_t)R) st.uniq.planes.alloc(ctx, (size_t)R);
+    if (st.uniq.len.n < (size_t)R) st.uniq.len.alloc(ctx, (size_t)R);
+    ctx->arena_on = true;
+    st.uniq.n = 0; st.uniq.has_hist = false; st.uniq.n_opaque = 0; st.uniq.min_len = st.uniq.max_len = 0;
     st.R = R;
     stage_begin(ctx);
     BucketOut bo{bucket_of_read, st.bptr.p, st.breads.p, nullptr};
@@ -424,7 +430,7 @@ int pcb_shard_pairs(pcb_ctx *ctx, int mem, const uint8_t *seq, const int32_t *le
       PCB_CUDA(cudaStreamSynchronize(ctx->stream));
       U = bucket_finish(ctx, bo, &st.uniq, pending);
     } else {
-      st.uniq.n = 0; st.uniq.planes.alloc(ctx, 0); st.uniq.len.alloc(ctx, 0);
+      st.uniq.n = 0;
       stage_end(ctx, PCB_STAT_T_BUCKET_NS);
     }
     st.U = U;
@@ -436,7 +442,7 @@ int pcb_shard_pairs(pcb_ctx *ctx, int mem, const uint8_t *seq, const int32_t *le
     if (n_edges) *n_edges = ctx->edges.n;
     st.valid = true;
     PCB_CUDA(cudaStreamSynchronize(ctx->stream));
-  }, false);       // the bucket arrays and the planes outlive the call: no workspace arena
+  });
 }
 
 int pcb_shard_merge(pcb_ctx *ctx, int mem, const int32_t *gathered, int32_t world, int64_t m, const int64_t *counts,

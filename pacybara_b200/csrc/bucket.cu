@@ -298,7 +298,10 @@ void bucket_launch(pcb_ctx *ctx, const uint8_t *seq, const int32_t *len, int32_t
   PCB_LAUNCH(ctx, bucket_flag_first_kernel, grid_for(cap, 256), 256, 0, slot.p, cap, rank.p);
   exclusive_scan_u32(ctx, rank.p, rank.p, (size_t)R + 1);               // rank[R] = U
   tr.lap("insert..scan");
-  if (unique_out) { unique_out->planes.alloc(ctx, (size_t)R); unique_out->len.alloc(ctx, (size_t)R); }
+  if (unique_out) {                          // (a caller that keeps them across calls brings buffers that are large enough)
+    if (unique_out->planes.n < (size_t)R) unique_out->planes.alloc(ctx, (size_t)R);
+    if (unique_out->len.n < (size_t)R) unique_out->len.alloc(ctx, (size_t)R);
+  }
   tr.lap("unique allocs");
   PCB_LAUNCH(ctx, bucket_number_kernel, grid_for(cap, 256), 256, 0, slot.p, cap, rank.p, st.pk.planes.p, st.pk.len.p, bucket_cnt.p,
              unique_out ? unique_out->planes.p : nullptr, unique_out ? unique_out->len.p : nullptr);
