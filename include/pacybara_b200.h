@@ -12,6 +12,7 @@
  *   pcb_merge         <- src/pacybara_cluster.py:385-477,515-537  (seed + main clustering,
  *                        consensus genotype / barcode)
  *   pcb_cluster_reads <- the three of them back to back, nothing leaving the device
+ *   pcb_shard_pairs, pcb_shard_merge <- (multi-GPU) one rank's share of a step: the two calls around the edge all-gather
  *   pcb_compact_shard <- (multi-GPU) the part of a merge result one rank owns, compacted
  *   pcb_concat_tokens <- src/pacybara_cluster.py:546-567 (writeOutput: the rows of clusters.csv.gz as text)
  * and, either side of the path:
