@@ -19,7 +19,8 @@
 //                 replay on a LOCAL copy of the component in shared memory (reads, calls, state, scratch), the
 //                 handful of such components of a library would otherwise be the tail of the step; it runs on a
 //                 second stream beside the small kernel, and takes whatever that kernel declines afterwards.
-//                 Bigger: the generic replay on global state (scratch sized per component).
+//                 Bigger: the generic replay on global state (scratch sized per component).  Beyond huge_reads reads (or
+//                 huge_buckets buckets): the giant tier, merge_huge.cuh -- the whole device inside one component.
 //   call regions  a component's rows put their calls into a region as long as its reads' call lists, taken from a
 //                 shared cursor as components come by: the layout of call_mut is not reproducible from run to
 //                 run, the rows (row_call_off / row_call_n / the calls themselves) are.
@@ -804,6 +805,7 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   if (in.min_matches < 1) throw Error(PCB_E_INPUT, "minMatches must be at least 1");
   if (in.min_qual < 1) throw Error(PCB_E_INPUT, "minQual must be a positive integer");
   if (in.shard_count < 1 || in.shard_rank < 0 || in.shard_rank >= in.shard_count) throw Error(PCB_E_INPUT, "bad shard");
+  ctx->stats[PCB_STAT_HUGE_COMPONENTS] = ctx->stats[PCB_STAT_HUGE_ROUNDS] = 0;
   if (R == 0 || U == 0) return;
   const int64_t nnz = in.nnz >= 0 ? in.nnz : (int64_t)read_scalar(ctx, in.geno_ptr + R);
   const int bbits = bits_for((uint64_t)(U > 1 ? U - 1 : 1));
