@@ -92,6 +92,8 @@ class Context:
         if getattr(self, "_sw_set", 1) != sw:
             self._check(self.lib.pcb_set_option(self.h, _lib.OPT_SMALL_WARPS, sw))
             self._sw_set = sw
+        if os.environ.get("PCB_SMALL_PAD"):
+            self._check(self.lib.pcb_set_option(self.h, 100, int(os.environ["PCB_SMALL_PAD"])))
         hb = int(os.environ.get("PCB_HUGE_BUCKETS") or getattr(self, "_huge_buckets_default", 16))
         if getattr(self, "_hb_set", 16) != hb:
             self._check(self.lib.pcb_set_option(self.h, _lib.OPT_HUGE_BUCKETS, hb))

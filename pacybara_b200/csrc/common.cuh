@@ -60,6 +60,7 @@ struct pcb_ctx {
   int huge_cap = 2048;                     // PCB_OPT_HUGE_CAP: slots of one warp's scratch table in that tier
   int huge_window = 32768;                 // PCB_OPT_HUGE_WINDOW: rows per round
   int huge_warps_per_sm = 24;
+  int small_pad = 0;                       // (measurement aid) extra dynamic shared memory per block of the small kernel: lowers its occupancy
   int small_warps = 1;                     // PCB_OPT_SMALL_WARPS: warps per block of the small-component replay kernel (1, 2 or 4)
   int seed_bins_log2 = 26;                 // PCB_OPT_SEED_BINS_LOG2: the seed length is capped so that the index has at most 2^this bins
   int probe_classes = 1;                   // PCB_OPT_PROBE_CLASSES: split long bins by target class (probe.cuh: owns_pair); 0 = parity rule only

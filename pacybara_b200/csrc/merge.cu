@@ -950,7 +950,7 @@ void merge_dev(pcb_ctx *ctx, const MergeIn &in, const MergeOut &out) {
   }
   if (shape == PCB_REPLAY_AUTO && n_comp > 0) {
     if (ctx->small_warps == 1)
-      PCB_LAUNCH(ctx, component_kernel_small<1>, grid_for((size_t)n_comp * 32, 32), 32, 0, c, n_comp, counters.p, declined.p, late.p);
+      PCB_LAUNCH(ctx, component_kernel_small<1>, grid_for((size_t)n_comp * 32, 32), 32, (size_t)ctx->small_pad, c, n_comp, counters.p, declined.p, late.p);
     else if (ctx->small_warps == 2)
       PCB_LAUNCH(ctx, component_kernel_small<2>, grid_for((size_t)n_comp * 32, 64), 64, 0, c, n_comp, counters.p, declined.p, late.p);
     else
