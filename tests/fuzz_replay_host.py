@@ -76,6 +76,22 @@ def one(seed: int) -> str:
     for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
         if not np.array_equal(getattr(got, f), getattr(want, f)):
             return f"small-component kernel: {f} differs ({kw}, {params})"
+    # the generic warp replay (csrc/merge_warp.cuh) and the giant tier (csrc/merge_huge.cuh: rounds of deterministic
+    # reservations) on emulated warps, with scratch tables and windows drawn small enough that rows are carried from round
+    # to round and units wait for the big scratch -- the caller's row order (shuffled or not) is what they must replay
+    for label, kw_emul in (("warp replay", dict(mode=2)),
+                           ("giant tier", dict(mode=3, huge_cap=int(rng.choice([16, 32, 64, 1024])), huge_window=int(rng.choice([1, 3, 8, 40])),
+                                               use_small=seed))):
+        alt = util.emul_merge(prob, pairs, **kw_emul)
+        STATS[label] = STATS.get(label, 0) + 1
+        if int(alt["status"][0]) == 3:
+            return f"{label} reports a missing uptag, the oracle does not"
+        got = hostdata.rows_from_merge_outputs(alt)
+        for f in ("row_ptr", "row_members", "row_bc", "row_up", "call_ptr", "call_mut"):
+            if not np.array_equal(getattr(got, f), getattr(want, f)):
+                return f"{label}: {f} differs ({kw}, {params}, {kw_emul})"
+        if int(alt["status"][2]) != int(out["status"][2]):
+            return f"{label}: {int(alt['status'][2])} links, the thread replay made {int(out['status'][2])}"
     # on-demand distances: only the pairs a pass can visit are listed, the transitive rule scores the rest on the spot,
     # and two shards put together are the whole (canonical row order only: that is what the fused call produces)
     keep = ed <= params["max_diff"]
@@ -116,7 +132,8 @@ def main():
         seed += 1
         n += 1
     print(f"{n} libraries, {len(bad)} discrepancies, seeds {seed - n}..{seed - 1}; "
-          f"{STATS['small']} of {STATS['components']} components went through the small-component warp kernel")
+          f"{STATS['small']} of {STATS['components']} components went through the small-component warp kernel; "
+          f"{STATS.get('warp replay', 0)} libraries through the generic warp replay, {STATS.get('giant tier', 0)} through the giant tier")
     return 1 if bad else 0
 
 
