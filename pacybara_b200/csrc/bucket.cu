@@ -56,12 +56,22 @@ __global__ void __launch_bounds__(PACK_BLOCK) pack_kernel(const uint8_t *__restr
     if (other != nullptr && (m < 1 || m > 64)) bad = true;
     uint64_t L = 0, H = 0, X = 0;
     if (!bad && !opaque) {
-      for (int32_t t = 0; t < m; t++) {
-        uint32_t c = base_code(s[t]);
-        if (c > 3u) { if (other == nullptr) { opaque = true; break; } X |= 1ull << t; c = 0u; }
-        L |= (uint64_t)(c & 1u) << t;
-        H |= (uint64_t)((c >> 1) & 1u) << t;
+      // base -> (L, H) bit without a compare chain: A 0x41, C 0x43, G 0x47, T 0x54 have H = bit 2 and L = bit 1 ^ bit 2;
+      // the character is a base iff it is the one its own code names.  32-bit halves: a 64-bit shift is several instructions.
+      uint32_t l0 = 0, h0 = 0, x0 = 0, l1 = 0, h1 = 0, x1 = 0;
+      const int32_t m0 = m < 32 ? m : 32;
+      for (int32_t t = 0; t < m0; t++) {
+        const uint32_t ch = s[t], hb = (ch >> 2) & 1u, lb = ((ch >> 1) ^ (ch >> 2)) & 1u;
+        const uint32_t ok = ((0x54474341u >> (8u * (lb | (hb << 1)))) & 0xFFu) == ch ? 1u : 0u;
+        l0 |= (lb & ok) << t; h0 |= (hb & ok) << t; x0 |= (ok ^ 1u) << t;
       }
+      for (int32_t t = 32; t < m; t++) {
+        const uint32_t ch = s[t], hb = (ch >> 2) & 1u, lb = ((ch >> 1) ^ (ch >> 2)) & 1u;
+        const uint32_t ok = ((0x54474341u >> (8u * (lb | (hb << 1)))) & 0xFFu) == ch ? 1u : 0u;
+        l1 |= (lb & ok) << (t - 32); h1 |= (hb & ok) << (t - 32); x1 |= (ok ^ 1u) << (t - 32);
+      }
+      L = ((uint64_t)l1 << 32) | l0; H = ((uint64_t)h1 << 32) | h0; X = ((uint64_t)x1 << 32) | x0;
+      if (X != 0 && other == nullptr) { opaque = true; L = H = X = 0; }       // a character that is no base: an opaque barcode
     }
     if (opaque) {
       uint64_t h1 = 0x9E3779B97F4A7C15ull ^ (uint64_t)m, h2 = 0xC2B2AE3D27D4EB4Full + (uint64_t)m;
