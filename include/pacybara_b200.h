@@ -110,7 +110,7 @@ int64_t pcb_stat(const pcb_ctx *ctx, int which);
  * reservations, consensus per cluster).  All shapes give identical results; the knob exists for measurements and for
  * the parity tests, which run every shape.
  * Giant tier: PCB_OPT_HUGE_READS = reads above which a component is replayed by the whole device (default 256);
- * PCB_OPT_HUGE_CAP = slots of a warp's scratch table, a power of two >= 16 (default 2048; units that need more wait
+ * PCB_OPT_HUGE_CAP = slots of a warp's scratch table, a power of two >= 16 (default 1024; units that need more wait
  * for a few warps with scratch sized on demand); PCB_OPT_HUGE_WINDOW = rows per round (default 32768).
  */
 enum { PCB_OPT_REPLAY_SHAPE = 0, PCB_OPT_TRACE = 1 /* 1: host-side lap times of the stages on stderr (development aid) */,

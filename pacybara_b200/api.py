@@ -92,6 +92,8 @@ class Context:
         if getattr(self, "_sw_set", 1) != sw:
             self._check(self.lib.pcb_set_option(self.h, _lib.OPT_SMALL_WARPS, sw))
             self._sw_set = sw
+        if os.environ.get("PCB_HUGE_WARPS"):
+            self._check(self.lib.pcb_set_option(self.h, 101, int(os.environ["PCB_HUGE_WARPS"])))
         if os.environ.get("PCB_SMALL_PAD"):
             self._check(self.lib.pcb_set_option(self.h, 100, int(os.environ["PCB_SMALL_PAD"])))
         hb = int(os.environ.get("PCB_HUGE_BUCKETS") or getattr(self, "_huge_buckets_default", 16))
@@ -103,7 +105,7 @@ class Context:
             self._check(self.lib.pcb_set_option(self.h, _lib.OPT_SEED_BINS_LOG2, bins))
             self._bins_set = bins
         # giant-tier knobs: environment > set_huge() > the library's defaults, applied per call like the shape
-        for env, opt, default in (("PCB_HUGE_READS", _lib.OPT_HUGE_READS, 256), ("PCB_HUGE_CAP", _lib.OPT_HUGE_CAP, 2048),
+        for env, opt, default in (("PCB_HUGE_READS", _lib.OPT_HUGE_READS, 256), ("PCB_HUGE_CAP", _lib.OPT_HUGE_CAP, 1024),
                                   ("PCB_HUGE_WINDOW", _lib.OPT_HUGE_WINDOW, 32768)):
             v = int(os.environ[env]) if os.environ.get(env) else getattr(self, "_huge", {}).get(opt, default)
             if getattr(self, "_huge_set", {}).get(opt) != v:

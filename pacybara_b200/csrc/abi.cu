@@ -257,6 +257,7 @@ int pcb_set_option(pcb_ctx *ctx, int option, int64_t value) {
   }
   if (option == PCB_OPT_TRACE) { ctx->trace = value != 0; return PCB_OK; }
   if (option == 100 && value >= 0 && value <= 32768) { ctx->small_pad = (int)value; return PCB_OK; }      // measurement aid, not in the header
+  if (option == 101 && value >= 1 && value <= 64) { ctx->huge_warps_per_sm = (int)value; return PCB_OK; }  // measurement aid: resident warps of the giant tier
   if (option == PCB_OPT_HUGE_BUCKETS && value >= 0 && value <= INT32_MAX) { ctx->huge_buckets = (int)value; return PCB_OK; }
   if (option == PCB_OPT_SMALL_WARPS && (value == 1 || value == 2 || value == 4)) { ctx->small_warps = (int)value; return PCB_OK; }
   if (option == PCB_OPT_SEED_BINS_LOG2 && value >= 8 && value <= 28) { ctx->seed_bins_log2 = (int)value; return PCB_OK; }

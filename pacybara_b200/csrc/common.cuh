@@ -57,9 +57,9 @@ struct pcb_ctx {
   int replay_shape = PCB_REPLAY_AUTO;      // pcb_set_option(PCB_OPT_REPLAY_SHAPE)
   int huge_reads = 256;                    // PCB_OPT_HUGE_READS: components above it are replayed by the whole device (merge_huge.cuh)
   int huge_buckets = 16;                   // PCB_OPT_HUGE_BUCKETS: ... or with more than this many buckets (and more than 128 reads); 0 = off
-  int huge_cap = 2048;                     // PCB_OPT_HUGE_CAP: slots of one warp's scratch table in that tier
+  int huge_cap = 1024;                     // PCB_OPT_HUGE_CAP: slots of one warp's scratch table in that tier
   int huge_window = 32768;                 // PCB_OPT_HUGE_WINDOW: rows per round
-  int huge_warps_per_sm = 24;
+  int huge_warps_per_sm = 40;
   int small_pad = 0;                       // (measurement aid) extra dynamic shared memory per block of the small kernel: lowers its occupancy
   int small_warps = 1;                     // PCB_OPT_SMALL_WARPS: warps per block of the small-component replay kernel (1, 2 or 4)
   int seed_bins_log2 = 26;                 // PCB_OPT_SEED_BINS_LOG2: the seed length is capped so that the index has at most 2^this bins
